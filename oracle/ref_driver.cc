@@ -1,0 +1,135 @@
+/* TEST INFRASTRUCTURE ONLY — driver around the UNMODIFIED reference libscuff (compiled from
+ * /root/reference into oracle/_ref/libscuff_ref.so by oracle/Makefile).  It only calls the
+ * reference's public/internal API (libscuff.h:363-365, libscuffInternals.h:67-392) and dumps
+ * results as raw little-endian doubles so tests / bench.py can compare the CUDA path with the
+ * reference's own CPU output.  Never linked into, imported by or timed as the product.
+ *
+ *   ref_driver geom   <geo> <out.txt>
+ *   ref_driver matrix <geo> <wRe> <wIm> <out.bin> [--kbloch kx ky] [--imag] [--repeat n]
+ *                     [--cache-in f] [--cache-out f] [--block nsa nsb]
+ *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
+ *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <omp.h>
+#include <libhrutil.h>
+#include "libscuff.h"
+#include "libscuffInternals.h"
+using namespace scuff;
+
+static double Now()
+{ struct timespec ts; clock_gettime(CLOCK_MONOTONIC,&ts); return ts.tv_sec+1e-9*ts.tv_nsec; }
+
+static int DumpGeom(RWGGeometry *G, const char *Out)
+{ FILE *f=fopen(Out,"w"); if(!f) return 1;
+  fprintf(f,"NumSurfaces %i\nNumRegions %i\nTotalBFs %i\nLDim %i\n",G->NumSurfaces,G->NumRegions,G->TotalBFs,G->LDim);
+  for(int nd=0; nd<G->LDim; nd++)
+   fprintf(f,"LBV %.17g %.17g %.17g\n",G->LBasis->GetEntryD(0,nd),G->LBasis->GetEntryD(1,nd),G->LBasis->GetEntryD(2,nd));
+  for(int nr=0; nr<G->NumRegions; nr++)
+   { fprintf(f,"Region %i %s %s",nr,G->RegionLabels[nr],G->RegionMPs[nr]->Name);
+     for(int nd=0; nd<G->LDim; nd++) fprintf(f," %i",(int)G->RegionIsExtended[nd][nr]);
+     fprintf(f,"\n");
+   }
+  for(int ns=0; ns<G->NumSurfaces; ns++)
+   { RWGSurface *S=G->Surfaces[ns];
+     fprintf(f,"Surface %i %s IsPEC %i Regions %i %i BFOffset %i Mate %i NV %i NP %i NE %i NBF %i\n",ns,S->Label,
+             (int)S->IsPEC,S->RegionIndices[0],S->RegionIndices[1],G->BFIndexOffset[ns],G->Mate[ns],
+             S->NumVertices,S->NumPanels,S->NumEdges,S->NumBFs);
+     for(int nv=0; nv<S->NumVertices; nv++)
+      fprintf(f,"V %.17g %.17g %.17g\n",S->Vertices[3*nv],S->Vertices[3*nv+1],S->Vertices[3*nv+2]);
+     for(int np=0; np<S->NumPanels; np++)
+      { RWGPanel *P=S->Panels[np];
+        fprintf(f,"P %i %i %i %.17g %.17g %.17g %.17g %.17g\n",P->VI[0],P->VI[1],P->VI[2],
+                P->Centroid[0],P->Centroid[1],P->Centroid[2],P->Radius,P->Area);
+      }
+     for(int ne=0; ne<S->NumEdges; ne++)
+      { RWGEdge *E=S->Edges[ne];
+        fprintf(f,"E %i %i %i %i %i %i %i %i %.17g\n",E->iV1,E->iV2,E->iQP,E->iQM,E->iPPanel,E->iMPanel,
+                E->PIndex,E->MIndex,E->Length);
+      }
+   }
+  fclose(f); return 0;
+}
+
+int main(int argc, char **argv)
+{ if(argc<3) { fprintf(stderr,"usage: see header\n"); return 2; }
+  const char *Cmd=argv[1];
+  SetLogFileName("/dev/null");
+  RWGGeometry *G=new RWGGeometry(argv[2]);
+
+  if(!strcmp(Cmd,"geom")) return DumpGeom(G,argv[3]);
+
+  if(!strcmp(Cmd,"matrix"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); const char *Out=argv[5];
+     double kBloch[2]; bool HavekBloch=false, Imag=false; int Repeat=1;
+     const char *CacheIn=0,*CacheOut=0; int nsa=-1,nsb=-1;
+     for(int n=6;n<argc;n++)
+      { if(!strcmp(argv[n],"--kbloch")) { kBloch[0]=atof(argv[n+1]); kBloch[1]=atof(argv[n+2]); HavekBloch=true; n+=2; }
+        else if(!strcmp(argv[n],"--imag")) Imag=true;
+        else if(!strcmp(argv[n],"--repeat")) Repeat=atoi(argv[++n]);
+        else if(!strcmp(argv[n],"--cache-in")) CacheIn=argv[++n];
+        else if(!strcmp(argv[n],"--cache-out")) CacheOut=argv[++n];
+        else if(!strcmp(argv[n],"--block")) { nsa=atoi(argv[n+1]); nsb=atoi(argv[n+2]); n+=2; }
+      }
+     if(CacheIn) PreloadCache(CacheIn);
+     HMatrix *M;
+     if(nsa>=0) M=new HMatrix(G->Surfaces[nsa]->NumBFs,G->Surfaces[nsb]->NumBFs,Imag?LHM_REAL:LHM_COMPLEX);
+     else M=G->AllocateBEMMatrix(Imag);
+     printf("{\"NR\": %i, \"NC\": %i, \"real\": %i, \"threads\": %i, \"times\": [",M->NR,M->NC,(int)Imag,omp_get_max_threads());
+     for(int r=0;r<Repeat;r++)
+      { double t0=Now();
+        if(nsa>=0) G->AssembleBEMMatrixBlock(nsa,nsb,Omega,HavekBloch?kBloch:0,M);
+        else G->AssembleBEMMatrix(Omega,HavekBloch?kBloch:0,M);
+        printf("%s%.6f",r?", ":"",Now()-t0);
+      }
+     printf("], \"eps\": [");
+     for(int nr=0;nr<G->NumRegions;nr++)
+      printf("%s[%.17g, %.17g]",nr?", ":"",real(G->EpsTF[nr]),imag(G->EpsTF[nr]));
+     printf("], \"mu\": [");
+     for(int nr=0;nr<G->NumRegions;nr++)
+      printf("%s[%.17g, %.17g]",nr?", ":"",real(G->MuTF[nr]),imag(G->MuTF[nr]));
+     printf("]}\n");
+     if(CacheOut) StoreCache(CacheOut);
+     FILE *f=fopen(Out,"wb"); if(!f) return 1;
+     size_t N=(size_t)M->NR*M->NC;
+     if(Imag) fwrite(M->DM,sizeof(double),N,f); else fwrite(M->ZM,sizeof(cdouble),N,f);
+     fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"ppis"))
+   { cdouble k(atof(argv[3]),atof(argv[4]));
+     FILE *fi=fopen(argv[5],"r"), *fo=fopen(argv[6],"wb"); if(!fi||!fo) return 1;
+     int nsa,npa,iQa,nsb,npb,iQb; int N=0;
+     while(fscanf(fi,"%i %i %i %i %i %i",&nsa,&npa,&iQa,&nsb,&npb,&iQb)==6)
+      { GetPPIArgStruct Args; InitGetPPIArgs(&Args);
+        Args.Sa=G->Surfaces[nsa]; Args.Sb=G->Surfaces[nsb];
+        Args.npa=npa; Args.npb=npb; Args.iQa=iQa; Args.iQb=iQb; Args.k=k;
+        GetPanelPanelInteractions(&Args);
+        double Rec[5]={real(Args.H[0]),imag(Args.H[0]),real(Args.H[1]),imag(Args.H[1]),(double)Args.WhichAlgorithm};
+        fwrite(Rec,sizeof(double),5,fo); N++;
+      }
+     fclose(fi); fclose(fo); printf("{\"n\": %i}\n",N); return 0;
+   }
+
+  if(!strcmp(Cmd,"fippi"))
+   { FILE *fi=fopen(argv[3],"r"), *fo=fopen(argv[4],"wb"); if(!fi||!fo) return 1;
+     int nsa,npa,nsb,npb; int N=0;
+     while(fscanf(fi,"%i %i %i %i",&nsa,&npa,&nsb,&npb)==4)
+      { double *Va[3],*Vb[3],*OVa[3],*OVb[3]; double rRel;
+        int ncv=AssessPanelPair(G->Surfaces[nsa],npa,G->Surfaces[nsb],npb,&rRel,Va,Vb);
+        int Flipped=CanonicallyOrderVertices(Va,Vb,ncv,OVa,OVb);
+        QIFIPPIData QIFD; memset(&QIFD,0,sizeof(QIFD));
+        ComputeQIFIPPIData(OVa,OVb,ncv,&QIFD);
+        double Hdr[3]={(double)ncv,rRel,(double)Flipped};
+        fwrite(Hdr,sizeof(double),3,fo);
+        for(int i=0;i<3;i++) fwrite(OVa[i],sizeof(double),3,fo);
+        for(int i=0;i<3;i++) fwrite(OVb[i],sizeof(double),3,fo);
+        fwrite(&QIFD,sizeof(double),36,fo); N++;
+      }
+     fclose(fi); fclose(fo); printf("{\"n\": %i}\n",N); return 0;
+   }
+
+  fprintf(stderr,"unknown command %s\n",Cmd); return 2;
+}
