@@ -1,0 +1,127 @@
+/* libscuff_cuda — C ABI of the B200 (sm_100a) implementation of SCUFF-EM's dense BEM
+ * system-matrix assembly.
+ *
+ * This is the drop-in boundary: plain pointers and sizes only.  Each entry point names the
+ * reference interface (HomerReid/scuff-em, paths relative to the reference root) it replaces
+ * or feeds.  The host-side C++ mirror of the reference API (include/libscuff_b200.h:
+ * RWGGeometry::AssembleBEMMatrix / AssembleBEMMatrixBlock, HMatrix) marshals to these calls;
+ * INTEGRATION.md shows the shim a maintainer would add to the reference's libscuff.
+ *
+ * All functions return 0 on success and a non-zero status on failure;
+ * scuffcuda_last_error() returns the message (the C++ shim turns it into ErrExit(), the
+ * reference's error convention, libs/libhrutil/libhrutil.h:136).
+ * There is NO CPU fallback: without a CUDA device scuffcuda_create() fails.
+ */
+#ifndef LIBSCUFF_CUDA_H
+#define LIBSCUFF_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct scuffcuda_context scuffcuda_context;
+
+/* ---- context ------------------------------------------------------------------------ */
+/* One context per device (one host process/thread per GPU for sweep sharding,
+ * SURVEY §8e).  Owns the device copy of the geometry, the FIPPI table
+ * (GlobalFIPPICache, libs/libscuff/FIPPICache.cc:405) and device matrices.            */
+int  scuffcuda_create(int device, scuffcuda_context **ctx);
+void scuffcuda_destroy(scuffcuda_context *ctx);
+const char *scuffcuda_last_error(scuffcuda_context *ctx);   /* ctx may be NULL        */
+int  scuffcuda_device_count(void);
+
+/* ---- geometry ----------------------------------------------------------------------- */
+/* Flattened RWGSurface (libs/libscuff/libscuff.h:174-328): what the hot path reads from
+ * Sa->Vertices, Sa->Panels[np]->{VI,Centroid,Radius}, Sa->Edges[ne]->{iPPanel,iMPanel,
+ * PIndex,MIndex,Length}.  Must be re-sent after RWGSurface::Transform/UnTransform
+ * (RWGSurface.cc:588-668) because vertices, centroids move.
+ *   vertices      [3*num_vertices]  xyz
+ *   panel_vi      [3*num_panels]    vertex indices
+ *   panel_centroid[3*num_panels], panel_radius[num_panels]  (as InitRWGPanel computed them)
+ *   edge_topo     [8*num_edges]     iV1,iV2,iQP,iQM,iPPanel,iMPanel,PIndex,MIndex
+ *                                   (iMPanel==-1: half-RWG edge, only the P panel)
+ *   edge_length   [num_edges]                                                          */
+int scuffcuda_set_num_surfaces(scuffcuda_context *ctx, int num_surfaces);
+int scuffcuda_set_surface(scuffcuda_context *ctx, int ns,
+                          int num_vertices, const double *vertices,
+                          int num_panels, const int *panel_vi,
+                          const double *panel_centroid, const double *panel_radius,
+                          int num_edges, const int *edge_topo, const double *edge_length,
+                          int is_pec);
+
+/* ---- device matrices (the HMatrix the path fills; libs/libhmat/libhmat.h:165-383) ---- */
+/* Column-major, ZM[nr + nc*NR] complex128 or DM[...] float64 (LHM_REAL), kept resident
+ * in HBM so that the LU consumer runs on the device.                                   */
+int scuffcuda_matrix_create(scuffcuda_context *ctx, int num_rows, int num_cols, int is_real, int *handle);
+int scuffcuda_matrix_destroy(scuffcuda_context *ctx, int handle);
+int scuffcuda_matrix_zero(scuffcuda_context *ctx, int handle);
+/* HMatrix::InsertBlock(M, RowOffset, ColOffset, NR, NC, BRowOffset, BColOffset)
+ * within one matrix — the Mate[] diagonal-block reuse of AssembleBEMMatrix.cc:731-737  */
+int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int handle, int dst_row, int dst_col,
+                                int num_rows, int num_cols, int src_row, int src_col);
+/* upper -> lower triangle copy of the square sub-block at (offset,offset) of size n
+ * (AssembleBEMMatrix.cc:753-758, SurfaceSurfaceInteractions.cc:573-583)                */
+int scuffcuda_matrix_symmetrize(scuffcuda_context *ctx, int handle, int offset, int n);
+/* host <-> device; host buffer is column-major with leading dimension ld (elements)    */
+int scuffcuda_matrix_download(scuffcuda_context *ctx, int handle, void *host, long ld);
+int scuffcuda_matrix_upload(scuffcuda_context *ctx, int handle, const void *host, long ld);
+/* raw device pointer (for zero-copy consumers such as torch / cuSOLVER callers)        */
+int scuffcuda_matrix_device_ptr(scuffcuda_context *ctx, int handle, void **dptr);
+/* downstream consumer: HMatrix::LUFactorize / LUSolve (libs/libhmat/LBWrappers.cc:150-230)
+ * via cuSOLVER getrf/getrs on the resident matrix; rhs is host memory [n*nrhs].        */
+int scuffcuda_lu_factor(scuffcuda_context *ctx, int handle);
+int scuffcuda_lu_solve(scuffcuda_context *ctx, int handle, void *rhs_host, int nrhs);
+
+/* ---- assembly ----------------------------------------------------------------------- */
+/* Mirror of GetSSIArgStruct (libs/libscuff/libscuffInternals.h:217-264) as filled by
+ * AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:371-387) and GetSurfaceSurfaceInteractions
+ * (SurfaceSurfaceInteractions.cc:462-492): material values are evaluated on the host by
+ * MatProp::GetEpsMu and passed by value.                                               */
+typedef struct scuffcuda_ssi_args {
+  double omega[2];          /* Omega (re, im)                                           */
+  double eps_a[2], mu_a[2]; /* first common region; eps_a==0 => skipped                 */
+  double sign_a;
+  double eps_b[2], mu_b[2]; /* second common region; eps_b==0 => absent                 */
+  double sign_b;
+  int    symmetric;         /* Args->Symmetric: compute nea<=neb, then mirror           */
+  int    accumulate;        /* Args->Accumulate: do not zero the block first            */
+  int    row_offset, col_offset;
+  int    use_displacement;  /* Args->Displacement != 0                                  */
+  double displacement[3];
+  int    force_taylor_duffy;/* RWGGeometry::DisableCache (PanelPanelInteractions.cc:589)*/
+  int    far_only;          /* debug/bench: evaluate only rRel>4 pairs                  */
+  int    reserved[7];
+} scuffcuda_ssi_args;
+
+/* GetSurfaceSurfaceInteractions(Args) on the device: adds the (nsa,nsb) block into the
+ * device matrix `handle` at (row_offset,col_offset).                                   */
+int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb,
+                             const scuffcuda_ssi_args *args, int handle);
+
+/* PPI algorithm counters of the last assemble_block call, same order as the reference's
+ * log line (SurfaceSurfaceInteractions.cc:550-558; libscuffInternals.h PPIALG_*):
+ * [0] low-order cubature, [1] high-order cubature, [2] Taylor-Duffy, [3] high-k TD,
+ * [4] desingularised; counted per (panel pair, Q pair) PPI the reference would evaluate */
+int scuffcuda_get_ppi_counts(scuffcuda_context *ctx, unsigned long long counts[5]);
+
+/* device time (ms, CUDA events on the context's stream) of the kernels of the last
+ * assemble_block call: [0] total, [1] far-field kernel, [2] near/singular kernels,
+ * [3] FIPPI table build, [4] classification/plan                                       */
+int scuffcuda_get_last_timing(scuffcuda_context *ctx, double ms[5]);
+int scuffcuda_synchronize(scuffcuda_context *ctx);
+
+/* ---- FIPPI table (PreloadCache / StoreCache, libs/libscuff/libscuff.h:662-663;
+ *      file format FIPPICache.cc:209-400: "FIPPICACHE\0" + 352-byte records)  --------- */
+int scuffcuda_fippi_preload(scuffcuda_context *ctx, const char *filename);
+int scuffcuda_fippi_store(scuffcuda_context *ctx, const char *filename);
+int scuffcuda_fippi_num_records(scuffcuda_context *ctx, long *n);
+
+/* ---- measurement helpers ------------------------------------------------------------ */
+/* dependent-chain-free DFMA microkernel: returns achieved FP64 TFLOP/s (2 flop per FMA);
+ * used as the in-run FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry) */
+int scuffcuda_measure_fp64_peak(scuffcuda_context *ctx, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,322 @@
+// libscuff_cuda: the C ABI (include/libscuff_cuda.h).  Host-side marshalling only; all
+// integrals run in the CUDA kernels of this directory.  No CPU fallback exists: every entry
+// point that computes needs a live CUDA context.
+#include <complex>
+#include <cstdio>
+#include <cstdarg>
+#include <cstring>
+#include <algorithm>
+#include "kernels.h"
+
+using namespace scuffcuda;
+typedef std::complex<double> cdouble;
+
+static std::string g_lastError;
+
+static int fail(scuffcuda_context *ctx, const char *fmt, ...)
+{ char buf[1024]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_lastError = buf; if (ctx) ctx->err = buf;
+  return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CKS(call) do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(ctx, "%s:%d: %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
+
+extern "C" {
+
+int scuffcuda_device_count(void)
+{ int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+const char *scuffcuda_last_error(scuffcuda_context *ctx)
+{ return ctx ? ctx->err.c_str() : g_lastError.c_str(); }
+
+int scuffcuda_create(int device, scuffcuda_context **out)
+{ scuffcuda_context *ctx = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+   return fail(nullptr, "libscuff_cuda: no CUDA device available (%s); this library has no CPU fallback",
+               e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= n) return fail(nullptr, "libscuff_cuda: invalid device %d (have %d)", device, n);
+  ctx = new scuffcuda_context; ctx->device = device;
+  CK(cudaSetDevice(device));
+  CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
+  ctx->smCount = prop.multiProcessorCount;
+  CKS(cusolverDnCreate(&ctx->solver));
+  CKS(cusolverDnSetStream(ctx->solver, ctx->stream));
+  CK(cudaMalloc(&ctx->dcounters, 16 * sizeof(unsigned long long)));
+  CK(cudaMemset(ctx->dcounters, 0, 16 * sizeof(unsigned long long)));
+  *out = ctx;
+  return 0;
+}
+
+void scuffcuda_destroy(scuffcuda_context *ctx)
+{ if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (auto &s : ctx->surfaces) if (s.dpanels) cudaFree(s.dpanels);
+  for (auto &m : ctx->matrices) { if (m.second.d) cudaFree(m.second.d); if (m.second.ipiv) cudaFree(m.second.ipiv); }
+  for (auto &p : ctx->plans) if (p.dnear) cudaFree(p.dnear);
+  if (ctx->fippi.drec) cudaFree(ctx->fippi.drec);
+  if (ctx->dcounters) cudaFree(ctx->dcounters);
+  if (ctx->dscratch) cudaFree(ctx->dscratch);
+  if (ctx->solver) cusolverDnDestroy(ctx->solver);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int scuffcuda_synchronize(scuffcuda_context *ctx)
+{ CK(cudaSetDevice(ctx->device)); CK(cudaStreamSynchronize(ctx->stream)); return 0; }
+
+// ------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------
+int scuffcuda_set_num_surfaces(scuffcuda_context *ctx, int n)
+{ if (n < 0) return fail(ctx, "invalid number of surfaces %d", n);
+  CK(cudaSetDevice(ctx->device));
+  for (size_t i = n; i < ctx->surfaces.size(); i++) if (ctx->surfaces[i].dpanels) cudaFree(ctx->surfaces[i].dpanels);
+  ctx->surfaces.resize(n);
+  return 0;
+}
+
+int scuffcuda_set_surface(scuffcuda_context *ctx, int ns, int NV, const double *V, int NP, const int *PVI,
+                          const double *PC, const double *PR, int NE, const int *ET, const double *EL, int isPEC)
+{ if (ns < 0 || ns >= (int)ctx->surfaces.size()) return fail(ctx, "set_surface: invalid surface index %d", ns);
+  if (NV <= 0 || NP <= 0 || NE < 0 || !V || !PVI || !PC || !PR || (NE > 0 && (!ET || !EL)))
+   return fail(ctx, "set_surface: invalid arguments");
+  CK(cudaSetDevice(ctx->device));
+  Surface &S = ctx->surfaces[ns];
+  static const double TU[6] = SCUFF_TCR4_U, TV[6] = SCUFF_TCR4_V;
+  S.NV = NV; S.NP = NP; S.NE = NE; S.isPEC = (isPEC != 0);
+  S.V.assign(V, V + 3 * (size_t)NV);
+  S.hpanels.assign(NP, PanelRec());
+  for (int np = 0; np < NP; np++)
+   { PanelRec &P = S.hpanels[np];
+     for (int i = 0; i < 3; i++)
+      { int vi = PVI[3 * np + i];
+        if (vi < 0 || vi >= NV) return fail(ctx, "set_surface: panel %d has invalid vertex index %d", np, vi);
+        for (int m = 0; m < 3; m++) P.V[3 * i + m] = V[3 * vi + m];
+      }
+     for (int m = 0; m < 3; m++) P.C[m] = PC[3 * np + m];
+     P.R = PR[np];
+     // cubature points exactly as GetPPIs_Cubature forms them (PanelPanelInteractions.cc:232-236,292-296)
+     const double *V0 = P.V; double A[3], B[3];
+     for (int m = 0; m < 3; m++) { A[m] = P.V[3 + m] - V0[m]; B[m] = P.V[6 + m] - V0[m]; }
+     for (int p = 0; p < 6; p++)
+      for (int m = 0; m < 3; m++)
+       { volatile double X = V0[m] + TU[p] * A[m]; X = X + TV[p] * B[m];
+         P.x[3 * p + m] = X - P.C[m];
+       }
+     for (int i = 0; i < 3; i++) { P.sl[i] = 0.0; P.ei[i] = -1; }
+     P.pad = 0;
+   }
+  for (int ne = 0; ne < NE; ne++)
+   { const int *e = ET + 8 * ne;
+     int iP = e[4], iM = e[5], PI = e[6], MI = e[7];
+     if (iP < 0 || iP >= NP || PI < 0 || PI > 2) return fail(ctx, "set_surface: edge %d has invalid P panel", ne);
+     S.hpanels[iP].ei[PI] = ne; S.hpanels[iP].sl[PI] = EL[ne];
+     if (iM >= 0)
+      { if (iM >= NP || MI < 0 || MI > 2) return fail(ctx, "set_surface: edge %d has invalid M panel", ne);
+        S.hpanels[iM].ei[MI] = ne; S.hpanels[iM].sl[MI] = -EL[ne];
+      }
+   }
+  if (S.dpanels) { cudaFree(S.dpanels); S.dpanels = nullptr; }
+  CK(cudaMalloc(&S.dpanels, (size_t)NP * sizeof(PanelRec)));
+  CK(cudaMemcpyAsync(S.dpanels, S.hpanels.data(), (size_t)NP * sizeof(PanelRec), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  static uint64_t gen = 0; S.generation = ++gen;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// matrices
+// ------------------------------------------------------------------------------------------
+static Matrix *get_matrix(scuffcuda_context *ctx, int h)
+{ auto it = ctx->matrices.find(h); return it == ctx->matrices.end() ? nullptr : &it->second; }
+
+int scuffcuda_matrix_create(scuffcuda_context *ctx, int NR, int NC, int isReal, int *handle)
+{ if (NR <= 0 || NC <= 0) return fail(ctx, "matrix_create: invalid size %dx%d", NR, NC);
+  CK(cudaSetDevice(ctx->device));
+  Matrix M; M.NR = NR; M.NC = NC; M.isReal = (isReal != 0);
+  size_t bytes = (size_t)NR * NC * (M.isReal ? 1 : 2) * sizeof(double);
+  CK(cudaMalloc(&M.d, bytes));
+  CK(cudaMemsetAsync(M.d, 0, bytes, ctx->stream));
+  int h = ctx->nextHandle++;
+  ctx->matrices[h] = M; *handle = h;
+  return 0;
+}
+int scuffcuda_matrix_destroy(scuffcuda_context *ctx, int h)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  if (M->d) cudaFree(M->d); if (M->ipiv) cudaFree(M->ipiv);
+  ctx->matrices.erase(h); return 0;
+}
+int scuffcuda_matrix_zero(scuffcuda_context *ctx, int h)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  CK(cudaSetDevice(ctx->device));
+  launch_zero_block(ctx, *M, 0, M->NR, 0, M->NC); M->factored = false; CK(cudaGetLastError()); return 0;
+}
+int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int h, int dr, int dc, int nr, int nc, int sr, int sc)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  if (dr < 0 || dc < 0 || sr < 0 || sc < 0 || dr + nr > M->NR || sr + nr > M->NR || dc + nc > M->NC || sc + nc > M->NC)
+   return fail(ctx, "matrix_copy_block: block out of range");
+  CK(cudaSetDevice(ctx->device));
+  launch_copy_block(ctx, *M, dr, dc, nr, nc, sr, sc); CK(cudaGetLastError()); return 0;
+}
+int scuffcuda_matrix_symmetrize(scuffcuda_context *ctx, int h, int off, int n)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  if (off < 0 || off + n > M->NR || off + n > M->NC) return fail(ctx, "matrix_symmetrize: block out of range");
+  CK(cudaSetDevice(ctx->device));
+  launch_symmetrize(ctx, *M, off, n); CK(cudaGetLastError()); return 0;
+}
+int scuffcuda_matrix_download(scuffcuda_context *ctx, int h, void *host, long ld)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  if (ld < M->NR) return fail(ctx, "matrix_download: ld < NR");
+  CK(cudaSetDevice(ctx->device));
+  size_t es = (M->isReal ? 1 : 2) * sizeof(double);
+  CK(cudaMemcpy2DAsync(host, ld * es, M->d, M->NR * es, M->NR * es, M->NC, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int scuffcuda_matrix_upload(scuffcuda_context *ctx, int h, const void *host, long ld)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  if (ld < M->NR) return fail(ctx, "matrix_upload: ld < NR");
+  CK(cudaSetDevice(ctx->device));
+  size_t es = (M->isReal ? 1 : 2) * sizeof(double);
+  CK(cudaMemcpy2DAsync(M->d, M->NR * es, host, ld * es, M->NR * es, M->NC, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream)); M->factored = false;
+  return 0;
+}
+int scuffcuda_matrix_device_ptr(scuffcuda_context *ctx, int h, void **dptr)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  *dptr = M->d; return 0;
+}
+
+int scuffcuda_lu_factor(scuffcuda_context *ctx, int h)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  if (M->NR != M->NC) return fail(ctx, "lu_factor: matrix is not square");
+  CK(cudaSetDevice(ctx->device));
+  int n = M->NR, lwork = 0;
+  if (!M->ipiv) CK(cudaMalloc(&M->ipiv, (size_t)n * sizeof(int)));
+  if (M->isReal) CKS(cusolverDnDgetrf_bufferSize(ctx->solver, n, n, M->d, n, &lwork));
+  else CKS(cusolverDnZgetrf_bufferSize(ctx->solver, n, n, (cuDoubleComplex *)M->d, n, &lwork));
+  size_t need = (size_t)lwork * (M->isReal ? 1 : 2) * sizeof(double) + 256;
+  if (need > ctx->scratchBytes)
+   { if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
+     CK(cudaMalloc(&ctx->dscratch, need)); ctx->scratchBytes = need; }
+  int *dinfo = (int *)ctx->dscratch; void *work = (char *)ctx->dscratch + 256;
+  if (M->isReal) CKS(cusolverDnDgetrf(ctx->solver, n, n, M->d, n, (double *)work, M->ipiv, dinfo));
+  else CKS(cusolverDnZgetrf(ctx->solver, n, n, (cuDoubleComplex *)M->d, n, (cuDoubleComplex *)work, M->ipiv, dinfo));
+  int info = 0;
+  CK(cudaMemcpyAsync(&info, dinfo, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (info != 0) return fail(ctx, "lu_factor: getrf info=%d", info);
+  M->factored = true;
+  return 0;
+}
+
+int scuffcuda_lu_solve(scuffcuda_context *ctx, int h, void *rhs, int nrhs)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  if (!M->factored) return fail(ctx, "lu_solve: matrix has not been factored");
+  CK(cudaSetDevice(ctx->device));
+  int n = M->NR; size_t es = (M->isReal ? 1 : 2) * sizeof(double);
+  size_t need = (size_t)n * nrhs * es + 256;
+  if (need > ctx->scratchBytes)
+   { if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
+     CK(cudaMalloc(&ctx->dscratch, need)); ctx->scratchBytes = need; }
+  int *dinfo = (int *)ctx->dscratch; void *dB = (char *)ctx->dscratch + 256;
+  CK(cudaMemcpyAsync(dB, rhs, (size_t)n * nrhs * es, cudaMemcpyHostToDevice, ctx->stream));
+  if (M->isReal) CKS(cusolverDnDgetrs(ctx->solver, CUBLAS_OP_N, n, nrhs, M->d, n, M->ipiv, (double *)dB, n, dinfo));
+  else CKS(cusolverDnZgetrs(ctx->solver, CUBLAS_OP_N, n, nrhs, (cuDoubleComplex *)M->d, n, M->ipiv, (cuDoubleComplex *)dB, n, dinfo));
+  CK(cudaMemcpyAsync(rhs, dB, (size_t)n * nrhs * es, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// assembly
+// ------------------------------------------------------------------------------------------
+static cdouble csqrt2(cdouble z)   // libs/libhrutil/libhrutil.cc:692-699
+{ cdouble r = std::sqrt(z); return (imag(r) < 0.0) ? -r : r; }
+
+int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args *a, int h)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  int NS = (int)ctx->surfaces.size();
+  if (nsa < 0 || nsa >= NS || nsb < 0 || nsb >= NS) return fail(ctx, "assemble_block: invalid surface index");
+  Surface &Sa = ctx->surfaces[nsa], &Sb = ctx->surfaces[nsb];
+  if (!Sa.dpanels || !Sb.dpanels) return fail(ctx, "assemble_block: surface not set");
+  int NBFA = Sa.isPEC ? Sa.NE : 2 * Sa.NE, NBFB = Sb.isPEC ? Sb.NE : 2 * Sb.NE;
+  if (a->row_offset < 0 || a->col_offset < 0 || a->row_offset + NBFA > M->NR || a->col_offset + NBFB > M->NC)
+   return fail(ctx, "assemble_block: block (%d+%d, %d+%d) exceeds matrix %dx%d", a->row_offset, NBFA, a->col_offset, NBFB, M->NR, M->NC);
+  if (a->symmetric && nsa != nsb) return fail(ctx, "assemble_block: symmetric requires nsa==nsb");
+  CK(cudaSetDevice(ctx->device));
+
+  cudaEvent_t ev[4]; for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ev[i]));
+  CK(cudaEventRecord(ev[0], ctx->stream));
+  CK(cudaMemsetAsync(ctx->dcounters, 0, 16 * sizeof(unsigned long long), ctx->stream));
+  M->factored = false;
+
+  if (!a->accumulate) launch_zero_block(ctx, *M, a->row_offset, NBFA, a->col_offset, NBFB);
+
+  cdouble Omega(a->omega[0], a->omega[1]);
+  const cdouble II(0.0, 1.0);
+  double farMs = 0, nearMs = 0;
+  for (int region = 0; region < 2; region++)
+   { cdouble Eps = region == 0 ? cdouble(a->eps_a[0], a->eps_a[1]) : cdouble(a->eps_b[0], a->eps_b[1]);
+     cdouble Mu = region == 0 ? cdouble(a->mu_a[0], a->mu_a[1]) : cdouble(a->mu_b[0], a->mu_b[1]);
+     double Sign = region == 0 ? a->sign_a : a->sign_b;
+     if (Eps == 0.0) continue;                      // SurfaceSurfaceInteractions.cc:177,294
+     if (region == 1 && (Sa.isPEC || Sb.isPEC)) continue;
+     cdouble k = csqrt2(Eps * Mu) * Omega;
+     if (real(k) == 0.0 && imag(k) == 0.0) continue; // EdgeEdgeInteractions.cc:74-79: GC=0
+     cdouble PreFac1 = Sign * II * Mu * Omega;
+     cdouble PreFac2 = -Sign * II * k;
+     cdouble PreFac3 = -Sign * II * Eps * Omega;
+     KParams K = make_kparams(real(k), imag(k));
+     StampParams SP;
+     SP.M = M->d; SP.ld = M->NR; SP.isReal = M->isReal ? 1 : 0;
+     SP.rowOff = a->row_offset; SP.colOff = a->col_offset;
+     SP.aPEC = Sa.isPEC; SP.bPEC = Sb.isPEC; SP.symmetric = a->symmetric ? 1 : 0;
+     SP.c1 = mk(real(PreFac1), imag(PreFac1));
+     SP.c2 = mk(real(PreFac2), imag(PreFac2));
+     SP.c3 = mk(real(PreFac3), imag(PreFac3));
+     int kmode = (imag(k) == 0.0) ? KMODE_REAL : ((real(k) == 0.0) ? KMODE_IMAG : KMODE_CPLX);
+
+     FarArgs F;
+     F.pa = Sa.dpanels; F.NPa = Sa.NP; F.pb = Sb.dpanels; F.NPb = Sb.NP; F.TA = 32;
+     F.symmetric = SP.symmetric; F.useDisp = a->use_displacement ? 1 : 0;
+     for (int i = 0; i < 3; i++) F.L[i] = a->use_displacement ? a->displacement[i] : 0.0;
+     F.K = K; F.S = SP; F.counters = ctx->dcounters;
+     CK(cudaEventRecord(ev[1], ctx->stream));
+     launch_far(ctx, F, kmode);
+     CK(cudaGetLastError());
+     CK(cudaEventRecord(ev[2], ctx->stream));
+     if (!a->far_only)
+      { if (run_near(ctx, nsa, nsb, a, K, SP, kmode, std::abs(k))) return 1; }
+     CK(cudaEventRecord(ev[3], ctx->stream));
+     CK(cudaEventSynchronize(ev[3]));
+     float t; cudaEventElapsedTime(&t, ev[1], ev[2]); farMs += t;
+     cudaEventElapsedTime(&t, ev[2], ev[3]); nearMs += t;
+   }
+  if (a->symmetric)
+   launch_symmetrize(ctx, *M, a->row_offset, NBFA);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ev[3], ctx->stream));
+  CK(cudaEventSynchronize(ev[3]));
+  float tot; cudaEventElapsedTime(&tot, ev[0], ev[3]);
+  ctx->timing[0] = tot; ctx->timing[1] = farMs; ctx->timing[2] = nearMs;
+  unsigned long long hc[16];
+  CK(cudaMemcpy(hc, ctx->dcounters, sizeof hc, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < 5; i++) ctx->counts[i] = hc[i];
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+  return 0;
+}
+
+int scuffcuda_get_ppi_counts(scuffcuda_context *ctx, unsigned long long c[5])
+{ for (int i = 0; i < 5; i++) c[i] = ctx->counts[i]; return 0; }
+int scuffcuda_get_last_timing(scuffcuda_context *ctx, double ms[5])
+{ for (int i = 0; i < 5; i++) ms[i] = ctx->timing[i]; return 0; }
+
+int scuffcuda_measure_fp64_peak(scuffcuda_context *ctx, double *tflops)
+{ CK(cudaSetDevice(ctx->device)); *tflops = run_fp64_peak(ctx); CK(cudaGetLastError()); return 0; }
+
+}  // extern "C"

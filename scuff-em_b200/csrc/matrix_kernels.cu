@@ -1,0 +1,98 @@
+// HMatrix-side device utilities: ZeroBlock, InsertBlock (Mate reuse), upper->lower symmetric fill
+// (libs/libhmat/HMatrix.cc:381-447; AssembleBEMMatrix.cc:731-737,753-758), and the DFMA
+// microbenchmark used as the FP64 roofline denominator.
+#include "kernels.h"
+
+namespace scuffcuda {
+
+__global__ void zero_block_kernel(double *M, long ld, int w, int rowOff, int nRows, int colOff, int nCols)
+{ long n = (long)nRows * nCols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+   { int r = (int)(i % nRows), c = (int)(i / nRows);
+     size_t idx = ((size_t)(rowOff + r) + (size_t)(colOff + c) * ld) * w;
+     M[idx] = 0.0; if (w == 2) M[idx + 1] = 0.0;
+   }
+}
+
+__global__ void copy_block_kernel(double *M, long ld, int w, int dstRow, int dstCol, int nRows, int nCols, int srcRow, int srcCol)
+{ long n = (long)nRows * nCols;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+   { int r = (int)(i % nRows), c = (int)(i / nRows);
+     size_t s = ((size_t)(srcRow + r) + (size_t)(srcCol + c) * ld) * w;
+     size_t d = ((size_t)(dstRow + r) + (size_t)(dstCol + c) * ld) * w;
+     M[d] = M[s]; if (w == 2) M[d + 1] = M[s + 1];
+   }
+}
+
+// lower(r,c) = upper(c,r) for r>c, 32x32 tiles through shared memory so both the read and the
+// write are coalesced (column-major: consecutive rows are contiguous)
+template <int W>
+__global__ void symmetrize_kernel(double *M, long ld, int off, int n)
+{ __shared__ double tile[32][33 * W];
+  int bx = blockIdx.x, by = blockIdx.y;      // tile (row block by, col block bx) of the UPPER part: by <= bx
+  if (by > bx) return;
+  int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
+  for (int j = ty; j < 32; j += 8)
+   { int r = by * 32 + tx, c = bx * 32 + j;
+     if (r < n && c < n)
+      { size_t idx = ((size_t)(off + r) + (size_t)(off + c) * ld) * W;
+        for (int q = 0; q < W; q++) tile[j][tx * W + q] = M[idx + q];
+      }
+   }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8)
+   { int r = bx * 32 + tx, c = by * 32 + j;   // transposed position
+     if (r < n && c < n && r > c)
+      { size_t idx = ((size_t)(off + r) + (size_t)(off + c) * ld) * W;
+        for (int q = 0; q < W; q++) M[idx + q] = tile[tx][j * W + q];
+      }
+   }
+}
+
+void launch_zero_block(scuffcuda_context *ctx, const Matrix &M, int rowOff, int nRows, int colOff, int nCols)
+{ if (nRows <= 0 || nCols <= 0) return;
+  int w = M.isReal ? 1 : 2;
+  if (rowOff == 0 && colOff == 0 && nRows == M.NR && nCols == M.NC)
+   { cudaMemsetAsync(M.d, 0, (size_t)M.NR * M.NC * w * sizeof(double), ctx->stream); return; }
+  zero_block_kernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(M.d, M.NR, w, rowOff, nRows, colOff, nCols);
+}
+void launch_copy_block(scuffcuda_context *ctx, const Matrix &M, int dstRow, int dstCol, int nRows, int nCols, int srcRow, int srcCol)
+{ if (nRows <= 0 || nCols <= 0) return;
+  copy_block_kernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(M.d, M.NR, M.isReal ? 1 : 2, dstRow, dstCol, nRows, nCols, srcRow, srcCol);
+}
+void launch_symmetrize(scuffcuda_context *ctx, const Matrix &M, int off, int n)
+{ if (n <= 1) return;
+  int t = (n + 31) / 32; dim3 grid(t, t), block(32, 8);
+  if (M.isReal) symmetrize_kernel<1><<<grid, block, 0, ctx->stream>>>(M.d, M.NR, off, n);
+  else symmetrize_kernel<2><<<grid, block, 0, ctx->stream>>>(M.d, M.NR, off, n);
+}
+
+// ---- FP64 peak: 8 independent DFMA chains per thread ----
+__global__ void dfma_peak_kernel(double *out, int iters)
+{ double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-7;
+  for (int i = 0; i < iters; i++)
+   { a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c); }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+double run_fp64_peak(scuffcuda_context *ctx)
+{ int blocks = ctx->smCount * 8, threads = 256, iters = 20000;
+  double *d; cudaMalloc(&d, (size_t)blocks * threads * sizeof(double));
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, 1000);
+  double best = 0;
+  for (int rep = 0; rep < 3; rep++)
+   { cudaEventRecord(e0, ctx->stream);
+     dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+     cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
+     float ms; cudaEventElapsedTime(&ms, e0, e1);
+     double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+     if (tf > best) best = tf;
+   }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  return best;
+}
+
+}  // namespace scuffcuda

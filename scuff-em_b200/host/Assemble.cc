@@ -1,0 +1,146 @@
+// RWGGeometry::AssembleBEMMatrix / AssembleBEMMatrixBlock with the reference's signatures
+// (libs/libscuff/libscuff.h:363-365,500-508) marshalled to the device through the C ABI.
+// Control flow restated from AssembleBEMMatrix.cc:349-391 (compact block), :684-765 (full matrix,
+// Mate reuse, symmetric fill) and GetSurfaceSurfaceInteractions SurfaceSurfaceInteractions.cc:
+// 426-492 (common regions, Eps/Mu/Sign selection, OmitRegion, early returns).
+#include <cstdlib>
+#include "host_internal.h"
+
+namespace scuff {
+
+// CountCommonRegions, SurfaceSurfaceInteractions.cc:62-90
+static int CountCommonRegions(RWGSurface *Sa, RWGSurface *Sb, int CommonRegionIndices[2], double Signs[2])
+{ int n = 0;
+  if (Sa->RegionIndices[0] == Sb->RegionIndices[0]) { CommonRegionIndices[n] = Sa->RegionIndices[0]; Signs[n] = +1.0; n++; }
+  else if (Sa->RegionIndices[0] == Sb->RegionIndices[1]) { CommonRegionIndices[n] = Sa->RegionIndices[0]; Signs[n] = -1.0; n++; }
+  if (Sa->RegionIndices[1] == Sb->RegionIndices[0]) { CommonRegionIndices[n] = Sa->RegionIndices[1]; Signs[n] = -1.0; n++; }
+  else if (!Sa->IsPEC && !Sb->IsPEC && Sa->RegionIndices[1] == Sb->RegionIndices[1]) { CommonRegionIndices[n] = Sa->RegionIndices[1]; Signs[n] = +1.0; n++; }
+  return n;
+}
+
+HMatrix *RWGGeometry::AllocateBEMMatrix(bool PureImagFreq, bool Packed)
+{ int Storage = Packed ? LHM_SYMMETRIC : LHM_NORMAL;
+  int DataType = (!LBasis && PureImagFreq) ? LHM_REAL : LHM_COMPLEX;
+  return new HMatrix(TotalBFs, TotalBFs, DataType, Storage);
+}
+
+void *RWGGeometry::CreateABMBAccelerator(int, int, bool, bool) { return 0; }   // PBC block cache: not yet on the device path
+void RWGGeometry::DestroyABMBAccelerator(void *) {}
+
+// device-side GetSurfaceSurfaceInteractions for one block of M (device twin), no host copy-back
+static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omega, HMatrix *M,
+                                  int RowOffset, int ColOffset, bool Symmetric, bool Accumulate,
+                                  const double *Displacement, bool OmitRegion1, bool OmitRegion2)
+{ scuffcuda_context *ctx = GetCudaContext();
+  RWGSurface *Sa = G->Surfaces[nsa], *Sb = G->Surfaces[nsb];
+  G->UpdateCachedEpsMuValues(Omega);
+  G->SyncDeviceGeometry();
+  M->EnsureDevice();
+
+  scuffcuda_ssi_args A; memset(&A, 0, sizeof A);
+  A.omega[0] = real(Omega); A.omega[1] = imag(Omega);
+  A.symmetric = Symmetric; A.accumulate = Accumulate;
+  A.row_offset = RowOffset; A.col_offset = ColOffset;
+  if (Displacement) { A.use_displacement = 1; for (int i = 0; i < 3; i++) A.displacement[i] = Displacement[i]; }
+  A.force_taylor_duffy = RWGGeometry::DisableCache ? 1 : 0;
+  const char *fo = getenv("SCUFF_CUDA_FAR_ONLY"); A.far_only = (fo && fo[0] == '1');
+
+  double Signs[2]; int CR[2];
+  int NumCommonRegions = CountCommonRegions(Sa, Sb, CR, Signs);
+  cdouble EpsA = 0.0, MuA = 0.0, EpsB = 0.0, MuB = 0.0; double SignA = 0.0, SignB = 0.0;
+  if (NumCommonRegions >= 1) { EpsA = G->EpsTF[CR[0]]; MuA = G->MuTF[CR[0]]; SignA = Signs[0]; }
+  if (NumCommonRegions == 2) { EpsB = G->EpsTF[CR[1]]; MuB = G->MuTF[CR[1]]; SignB = Signs[1]; }
+  if (OmitRegion1) { EpsA = MuA = 0.0; SignA = 0.0; }
+  if (OmitRegion2) { EpsB = MuB = 0.0; SignB = 0.0; }
+  // note: with zero common regions (or both omitted) the reference still zeroes the block
+  // unless Accumulate is set; assemble_block does the same with eps_a = eps_b = 0
+  A.eps_a[0] = real(EpsA); A.eps_a[1] = imag(EpsA); A.mu_a[0] = real(MuA); A.mu_a[1] = imag(MuA); A.sign_a = SignA;
+  A.eps_b[0] = real(EpsB); A.eps_b[1] = imag(EpsB); A.mu_b[0] = real(MuB); A.mu_b[1] = imag(MuB); A.sign_b = SignB;
+
+  if (scuffcuda_assemble_block(ctx, nsa, nsb, &A, M->DeviceHandle)) ErrExit("%s", scuffcuda_last_error(ctx));
+  unsigned long long c[5]; scuffcuda_get_ppi_counts(ctx, c);
+  for (int i = 0; i < 5; i++) G->LastPPICounts[i] += c[i];
+  M->HostStale = true;
+}
+
+void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double *kBloch,
+                                         HMatrix *M, HMatrix **GradM, int RowOffset, int ColOffset,
+                                         void *Accelerator, bool TransposeAccelerator,
+                                         int NumTorqueAxes, HMatrix **dMdT, double *GammaMatrix)
+{ (void)Accelerator; (void)GammaMatrix; (void)kBloch;
+  if (TransposeAccelerator) ErrExit("%s:%i: TransposeAccelerator not implemented", __FILE__, __LINE__);
+  if (nsa < 0 || nsa >= NumSurfaces || nsb < 0 || nsb >= NumSurfaces) ErrExit("AssembleBEMMatrixBlock: invalid surface indices (%i,%i)", nsa, nsb);
+  if (GradM || (NumTorqueAxes > 0 && dMdT))
+   ErrExit("AssembleBEMMatrixBlock: GradM / dMdT derivative blocks are not yet available on the device path");
+  if (getenv("SCUFF_TBLOCK_PATH")) Warn("SCUFF_TBLOCK_PATH is ignored by the device assembly path");
+  // the caller may have written into M on the host (e.g. other blocks): keep both sides coherent
+  bool fresh = (M->DeviceHandle == 0);
+  M->EnsureDevice();
+  if (fresh) M->SyncToDevice();
+  for (int i = 0; i < 5; i++) LastPPICounts[i] = 0;
+  if (LBasis == 0)
+   { AssembleBlockOnDevice(this, nsa, nsb, Omega, M, RowOffset, ColOffset, nsa == nsb, false, 0, false, false);
+     M->SyncToHost();
+     return; }
+  AssembleBEMMatrixBlockPBC(nsa, nsb, Omega, kBloch, M, RowOffset, ColOffset);
+  M->SyncToHost();
+}
+
+HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *M)
+{ if (LBasis == 0 && kBloch != 0 && (kBloch[0] != 0.0 || kBloch[1] != 0.0))
+   ErrExit("%s:%i: Bloch wavevector is undefined for compact geometries", __FILE__, __LINE__);
+  if (LBasis != 0 && kBloch == 0)
+   ErrExit("%s:%i: Bloch wavevector must be specified for PBC geometries", __FILE__, __LINE__);
+  if (M == NULL) M = AllocateBEMMatrix();
+  else if (M->NR != TotalBFs || M->NC != TotalBFs)
+   { Warn("wrong-size matrix passed to AssembleBEMMatrix; reallocating...");
+     M = AllocateBEMMatrix(); }
+  AssembleBEMMatrixDevice(Omega, kBloch, M);
+  M->SyncToHost();
+  return M;
+}
+
+// same as AssembleBEMMatrix but leaves the result in HBM only (M->HostStale == true): the form
+// the on-device LU consumer and the sweep drivers use
+void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M)
+{ scuffcuda_context *ctx = GetCudaContext();
+  M->EnsureDevice();
+  for (int i = 0; i < 5; i++) LastPPICounts[i] = 0;
+  bool MatrixIsSymmetric = (!kBloch || (kBloch[0] == 0.0 && kBloch[1] == 0.0));
+  int nspStart = MatrixIsSymmetric ? 1 : 0;
+  for (int ns = 0; ns < NumSurfaces; ns++)
+   for (int nsp = nspStart * ns; nsp < NumSurfaces; nsp++)
+    { int nsm;
+      if (ns == nsp && (nsm = Mate[ns]) != -1)
+       { int ThisOffset = BFIndexOffset[ns], MateOffset = BFIndexOffset[nsm], Dim = Surfaces[ns]->NumBFs;
+         SyncDeviceGeometry();
+         if (scuffcuda_matrix_copy_block(ctx, M->DeviceHandle, ThisOffset, ThisOffset, Dim, Dim, MateOffset, MateOffset))
+          ErrExit("%s", scuffcuda_last_error(ctx));
+         M->HostStale = true; }
+      else if (LBasis == 0)
+       AssembleBlockOnDevice(this, ns, nsp, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false);
+      else
+       AssembleBEMMatrixBlockPBC(ns, nsp, Omega, kBloch, M, BFIndexOffset[ns], BFIndexOffset[nsp]);
+    }
+  if (MatrixIsSymmetric)
+   { if (scuffcuda_matrix_symmetrize(ctx, M->DeviceHandle, 0, TotalBFs)) ErrExit("%s", scuffcuda_last_error(ctx));
+     M->HostStale = true; }
+}
+
+HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, HMatrix *M) { return AssembleBEMMatrix(Omega, 0, M); }
+
+void RWGGeometry::InitPBCData()
+{ for (int nd = 0; nd < LDim; nd++) RegionIsExtended[nd] = (bool *)calloc(NumRegions, sizeof(bool)); }
+
+void RWGGeometry::AssembleBEMMatrixBlockPBC(int, int, cdouble, double *, HMatrix *, int, int)
+{ ErrExit("periodic (LATTICE) geometries are not yet supported by the device assembly path"); }
+
+// PreloadCache / StoreCache (libscuff.h:662-663 -> GlobalFIPPICache.PreLoad/Store)
+void PreloadCache(const char *FileName)
+{ scuffcuda_context *ctx = GetCudaContext();
+  if (scuffcuda_fippi_preload(ctx, FileName)) Warn("%s", scuffcuda_last_error(ctx)); }
+void StoreCache(const char *FileName)
+{ scuffcuda_context *ctx = GetCudaContext();
+  if (scuffcuda_fippi_store(ctx, FileName)) Warn("%s", scuffcuda_last_error(ctx)); }
+
+}  // namespace scuff

@@ -1,0 +1,88 @@
+// extern "C" facade over the C++ mirror (RWGGeometry / HMatrix) for ctypes callers (tests, bench.py).
+// ErrExit() is converted into an error return + message instead of exit().
+#include <stdexcept>
+#include "host_internal.h"
+using namespace scuff;
+
+static std::string g_err;
+static void Thrower(const char *msg) { throw std::runtime_error(msg); }
+#define GUARD(body, failret) try { SetErrExitHandler(Thrower); body } catch (std::exception &e) { g_err = e.what(); return failret; }
+
+extern "C" {
+
+const char *scuffb200_last_error() { return g_err.c_str(); }
+int scuffb200_set_device(int dev) { GUARD(SetCudaDevice(dev); return 0;, 1) }
+void *scuffb200_context() { GUARD(return (void *)GetCudaContext();, 0) }
+
+void *scuffb200_geometry_open(const char *geofile) { GUARD(return (void *)new RWGGeometry(geofile);, 0) }
+void scuffb200_geometry_close(void *G) { delete (RWGGeometry *)G; }
+
+// out[0..7] = NumSurfaces, TotalBFs, NumRegions, LDim, TotalPanels, TotalEdges, AllSurfacesClosed, 0
+int scuffb200_geometry_info(void *g, int *out)
+{ RWGGeometry *G = (RWGGeometry *)g;
+  out[0] = G->NumSurfaces; out[1] = G->TotalBFs; out[2] = G->NumRegions; out[3] = G->LDim;
+  out[4] = G->TotalPanels; out[5] = G->TotalEdges; out[6] = G->AllSurfacesClosed; out[7] = 0; return 0; }
+// out[0..9] = NV, NP, NE, NBF, IsPEC, Region0, Region1, BFIndexOffset, Mate, NumHalfRWGEdges
+int scuffb200_surface_info(void *g, int ns, int *out)
+{ RWGGeometry *G = (RWGGeometry *)g; if (ns < 0 || ns >= G->NumSurfaces) return 1;
+  RWGSurface *S = G->Surfaces[ns];
+  out[0] = S->NumVertices; out[1] = S->NumPanels; out[2] = S->NumEdges; out[3] = S->NumBFs; out[4] = S->IsPEC;
+  out[5] = S->RegionIndices[0]; out[6] = S->RegionIndices[1]; out[7] = G->BFIndexOffset[ns]; out[8] = G->Mate[ns]; out[9] = S->NumHalfRWGEdges; return 0; }
+const char *scuffb200_surface_label(void *g, int ns) { return ((RWGGeometry *)g)->Surfaces[ns]->Label; }
+const char *scuffb200_region_label(void *g, int nr) { return ((RWGGeometry *)g)->RegionLabels[nr]; }
+const char *scuffb200_region_material(void *g, int nr) { return ((RWGGeometry *)g)->RegionMPs[nr]->Name; }
+// V[3NV], PVI[3NP], PC[3NP], PR[NP], PA[NP], ET[8NE], EL[NE]
+int scuffb200_surface_arrays(void *g, int ns, double *V, int *PVI, double *PC, double *PR, double *PA, int *ET, double *EL)
+{ RWGGeometry *G = (RWGGeometry *)g; if (ns < 0 || ns >= G->NumSurfaces) return 1;
+  RWGSurface *S = G->Surfaces[ns];
+  memcpy(V, S->Vertices, 3 * S->NumVertices * sizeof(double));
+  for (int np = 0; np < S->NumPanels; np++)
+   { RWGPanel *P = S->Panels[np];
+     for (int i = 0; i < 3; i++) { PVI[3 * np + i] = P->VI[i]; PC[3 * np + i] = P->Centroid[i]; }
+     PR[np] = P->Radius; PA[np] = P->Area; }
+  for (int ne = 0; ne < S->NumEdges; ne++)
+   { RWGEdge *E = S->Edges[ne]; int *e = ET + 8 * ne;
+     e[0] = E->iV1; e[1] = E->iV2; e[2] = E->iQP; e[3] = E->iQM; e[4] = E->iPPanel; e[5] = E->iMPanel; e[6] = E->PIndex; e[7] = E->MIndex;
+     EL[ne] = E->Length; }
+  return 0; }
+// eps/mu per region at Omega: out[4*nr + {0,1,2,3}] = Re eps, Im eps, Re mu, Im mu
+int scuffb200_eps_mu(void *g, double wr, double wi, double *out)
+{ RWGGeometry *G = (RWGGeometry *)g;
+  GUARD(G->UpdateCachedEpsMuValues(cdouble(wr, wi));
+        for (int nr = 0; nr < G->NumRegions; nr++)
+         { out[4 * nr] = real(G->EpsTF[nr]); out[4 * nr + 1] = imag(G->EpsTF[nr]); out[4 * nr + 2] = real(G->MuTF[nr]); out[4 * nr + 3] = imag(G->MuTF[nr]); }
+        return 0;, 1) }
+int scuffb200_transform(void *g, const char *line) { GUARD(((RWGGeometry *)g)->Transform(line); return 0;, 1) }
+int scuffb200_untransform(void *g) { GUARD(((RWGGeometry *)g)->UnTransform(); return 0;, 1) }
+int scuffb200_zero_region(void *g, int nr, int zero)
+{ RWGGeometry *G = (RWGGeometry *)g; if (nr < 0 || nr >= G->NumRegions) return 1;
+  if (zero) G->RegionMPs[nr]->Zero(); else G->RegionMPs[nr]->UnZero(); return 0; }
+
+void *scuffb200_matrix_alloc(void *g, int pure_imag) { GUARD(return (void *)((RWGGeometry *)g)->AllocateBEMMatrix(pure_imag != 0);, 0) }
+void *scuffb200_matrix_new(int nr, int nc, int is_real) { GUARD(return (void *)new HMatrix(nr, nc, is_real ? LHM_REAL : LHM_COMPLEX);, 0) }
+void scuffb200_matrix_free(void *m) { delete (HMatrix *)m; }
+void *scuffb200_matrix_data(void *m) { HMatrix *M = (HMatrix *)m; return M->RealComplex == LHM_REAL ? (void *)M->DM : (void *)M->ZM; }
+int scuffb200_matrix_shape(void *m, int *out) { HMatrix *M = (HMatrix *)m; out[0] = M->NR; out[1] = M->NC; out[2] = (M->RealComplex == LHM_REAL); return 0; }
+int scuffb200_matrix_sync_host(void *m) { GUARD(((HMatrix *)m)->SyncToHost(); return 0;, 1) }
+int scuffb200_matrix_device_handle(void *m) { return ((HMatrix *)m)->DeviceHandle; }
+
+// RWGGeometry::AssembleBEMMatrix(Omega, kBloch, M); to_host=0 leaves the result in HBM only
+int scuffb200_assemble(void *g, void *m, double wr, double wi, const double *kBloch, int to_host)
+{ RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
+  GUARD(if (to_host) { HMatrix *R = G->AssembleBEMMatrix(cdouble(wr, wi), (double *)kBloch, M); if (R != M) { delete R; throw std::runtime_error("wrong-size matrix"); } }
+        else
+         { if (G->LBasis == 0 && kBloch != 0 && (kBloch[0] != 0.0 || kBloch[1] != 0.0)) ErrExit("Bloch wavevector is undefined for compact geometries");
+           if (G->LBasis != 0 && kBloch == 0) ErrExit("Bloch wavevector must be specified for PBC geometries");
+           G->AssembleBEMMatrixDevice(cdouble(wr, wi), (double *)kBloch, M); }
+        return 0;, 1) }
+int scuffb200_assemble_block(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off)
+{ RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
+  GUARD(G->AssembleBEMMatrixBlock(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, 0, row_off, col_off); return 0;, 1) }
+int scuffb200_ppi_counts(void *g, unsigned long long *out) { for (int i = 0; i < 5; i++) out[i] = ((RWGGeometry *)g)->LastPPICounts[i]; return 0; }
+int scuffb200_lu_factorize(void *m) { GUARD(return ((HMatrix *)m)->LUFactorize();, 1) }
+int scuffb200_lu_solve(void *m, void *x) { GUARD(return ((HMatrix *)m)->LUSolve((HMatrix *)x);, 1) }
+int scuffb200_preload_cache(const char *f) { GUARD(PreloadCache(f); return 0;, 1) }
+int scuffb200_store_cache(const char *f) { GUARD(StoreCache(f); return 0;, 1) }
+int scuffb200_set_disable_cache(int v) { RWGGeometry::DisableCache = (v != 0); return 0; }
+
+}  // extern "C"

@@ -1,0 +1,71 @@
+// Error/log conventions and small helpers of the host-side mirror.
+// Reference: libs/libhrutil/libhrutil.h:100-151 (ErrExit/Warn/Log), libhrutil.cc:228-235 (Tokenize).
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <mutex>
+#include "host_internal.h"
+
+namespace scuff {
+
+static ErrExitHandler g_handler = 0;
+static std::string g_logFile;
+static scuffcuda_context *g_ctx = 0;
+static int g_device = -1;
+
+void SetErrExitHandler(ErrExitHandler h) { g_handler = h; }
+void SetLogFileName(const char *name) { g_logFile = name ? name : ""; }
+
+void ErrExit(const char *fmt, ...)
+{ char buf[2048]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  Log("error: %s (aborting)", buf);
+  if (g_handler) { g_handler(buf); }
+  fprintf(stderr, "error: %s (aborting)\n", buf);
+  exit(1);
+}
+void Warn(const char *fmt, ...)
+{ char buf[2048]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  fprintf(stderr, "**warning: %s \n", buf);
+  Log("warning: %s", buf);
+}
+void Log(const char *fmt, ...)
+{ if (g_logFile.empty()) return;
+  FILE *f = fopen(g_logFile.c_str(), "a"); if (!f) return;
+  char buf[2048]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  time_t t = time(0); struct tm tmv; localtime_r(&t, &tmv); char ts[64];
+  strftime(ts, sizeof ts, "%D::%T", &tmv);
+  fprintf(f, "%s: %s\n", ts, buf); fclose(f);
+}
+
+void SetCudaDevice(int device)
+{ if (g_ctx && device != g_device) { scuffcuda_destroy(g_ctx); g_ctx = 0; }
+  g_device = device;
+}
+
+scuffcuda_context *GetCudaContext()
+{ if (g_ctx) return g_ctx;
+  int dev = g_device;
+  if (dev < 0)
+   { const char *s = getenv("SCUFF_CUDA_DEVICE"); if (!s) s = getenv("LOCAL_RANK");
+     dev = s ? atoi(s) : 0; }
+  if (scuffcuda_create(dev, &g_ctx))
+   ErrExit("libscuff_cuda: %s", scuffcuda_last_error(0));
+  g_device = dev;
+  return g_ctx;
+}
+
+// whitespace tokenizer (in place)
+int Tokenize(char *s, char **Tokens, int MaxTokens, const char *Separators)
+{ int n = 0; char *save = 0;
+  for (char *t = strtok_r(s, Separators, &save); t; t = strtok_r(0, Separators, &save))
+   { if (n < MaxTokens) Tokens[n] = t; n++; }
+  return n;
+}
+
+char *vstrdup(const char *fmt, ...)
+{ char buf[2048]; va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  return strdup(buf);
+}
+
+}  // namespace scuff

@@ -1,0 +1,284 @@
+"""ctypes binding of the two in-tree shared libraries (tests / bench.py use this; it is plumbing).
+
+  libscuff_cuda.so  — the C ABI (include/libscuff_cuda.h): CUDA kernels for sm_100a
+  libscuff_b200.so  — the host-side C++ mirror of the reference API (include/libscuff_b200.h:
+                      RWGGeometry::AssembleBEMMatrix[Block], HMatrix) through its extern "C" facade
+
+There is no Python or CPU implementation of the path behind these classes: if the libraries are
+missing, or no CUDA device is present, the calls raise.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB = os.path.join(_HERE, "libscuff_cuda.so")
+HOST_LIB = os.path.join(_HERE, "libscuff_b200.so")
+
+
+class ScuffError(RuntimeError):
+    pass
+
+
+class SSIArgs(C.Structure):
+    """scuffcuda_ssi_args (include/libscuff_cuda.h)"""
+    _fields_ = [("omega", C.c_double * 2),
+                ("eps_a", C.c_double * 2), ("mu_a", C.c_double * 2), ("sign_a", C.c_double),
+                ("eps_b", C.c_double * 2), ("mu_b", C.c_double * 2), ("sign_b", C.c_double),
+                ("symmetric", C.c_int), ("accumulate", C.c_int),
+                ("row_offset", C.c_int), ("col_offset", C.c_int),
+                ("use_displacement", C.c_int), ("displacement", C.c_double * 3),
+                ("force_taylor_duffy", C.c_int), ("far_only", C.c_int),
+                ("reserved", C.c_int * 7)]
+
+
+_cuda = None
+_host = None
+
+
+def cuda_lib():
+    global _cuda
+    if _cuda is None:
+        if not os.path.exists(CUDA_LIB):
+            raise ScuffError(f"{CUDA_LIB} not built: run python -c 'import __graft_entry__ as g; g.build()'")
+        L = C.CDLL(CUDA_LIB, mode=C.RTLD_GLOBAL)
+        L.scuffcuda_last_error.restype = C.c_char_p
+        L.scuffcuda_last_error.argtypes = [C.c_void_p]
+        L.scuffcuda_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.scuffcuda_destroy.argtypes = [C.c_void_p]
+        L.scuffcuda_set_num_surfaces.argtypes = [C.c_void_p, C.c_int]
+        L.scuffcuda_set_surface.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.scuffcuda_matrix_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.scuffcuda_matrix_destroy.argtypes = [C.c_void_p, C.c_int]
+        L.scuffcuda_matrix_zero.argtypes = [C.c_void_p, C.c_int]
+        L.scuffcuda_matrix_copy_block.argtypes = [C.c_void_p] + [C.c_int] * 7
+        L.scuffcuda_matrix_symmetrize.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.scuffcuda_matrix_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long]
+        L.scuffcuda_matrix_upload.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_long]
+        L.scuffcuda_matrix_device_ptr.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        L.scuffcuda_lu_factor.argtypes = [C.c_void_p, C.c_int]
+        L.scuffcuda_lu_solve.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.scuffcuda_assemble_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SSIArgs), C.c_int]
+        L.scuffcuda_get_ppi_counts.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        L.scuffcuda_get_last_timing.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.scuffcuda_synchronize.argtypes = [C.c_void_p]
+        L.scuffcuda_fippi_preload.argtypes = [C.c_void_p, C.c_char_p]
+        L.scuffcuda_fippi_store.argtypes = [C.c_void_p, C.c_char_p]
+        L.scuffcuda_fippi_num_records.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+        L.scuffcuda_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        _cuda = L
+    return _cuda
+
+
+def host_lib():
+    global _host
+    if _host is None:
+        cuda_lib()
+        if not os.path.exists(HOST_LIB):
+            raise ScuffError(f"{HOST_LIB} not built: run python -c 'import __graft_entry__ as g; g.build()'")
+        L = C.CDLL(HOST_LIB)
+        L.scuffb200_last_error.restype = C.c_char_p
+        L.scuffb200_context.restype = C.c_void_p
+        L.scuffb200_geometry_open.restype = C.c_void_p
+        L.scuffb200_geometry_open.argtypes = [C.c_char_p]
+        L.scuffb200_geometry_close.argtypes = [C.c_void_p]
+        L.scuffb200_geometry_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_surface_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        for f in ("scuffb200_surface_label", "scuffb200_region_label", "scuffb200_region_material"):
+            getattr(L, f).restype = C.c_char_p
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+        L.scuffb200_surface_arrays.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7
+        L.scuffb200_eps_mu.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p]
+        L.scuffb200_transform.argtypes = [C.c_void_p, C.c_char_p]
+        L.scuffb200_untransform.argtypes = [C.c_void_p]
+        L.scuffb200_zero_region.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.scuffb200_matrix_alloc.restype = C.c_void_p
+        L.scuffb200_matrix_alloc.argtypes = [C.c_void_p, C.c_int]
+        L.scuffb200_matrix_new.restype = C.c_void_p
+        L.scuffb200_matrix_new.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.scuffb200_matrix_free.argtypes = [C.c_void_p]
+        L.scuffb200_matrix_data.restype = C.c_void_p
+        L.scuffb200_matrix_data.argtypes = [C.c_void_p]
+        L.scuffb200_matrix_shape.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_matrix_sync_host.argtypes = [C.c_void_p]
+        L.scuffb200_matrix_device_handle.argtypes = [C.c_void_p]
+        L.scuffb200_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]
+        L.scuffb200_assemble_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                               C.c_void_p, C.c_int, C.c_int]
+        L.scuffb200_ppi_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_lu_factorize.argtypes = [C.c_void_p]
+        L.scuffb200_lu_solve.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_preload_cache.argtypes = [C.c_char_p]
+        L.scuffb200_store_cache.argtypes = [C.c_char_p]
+        L.scuffb200_set_device.argtypes = [C.c_int]
+        _host = L
+    return _host
+
+
+def _check(rc):
+    if rc:
+        raise ScuffError(host_lib().scuffb200_last_error().decode())
+
+
+def set_device(dev):
+    _check(host_lib().scuffb200_set_device(int(dev)))
+
+
+def context():
+    """the process-wide scuffcuda_context* (as int) the C++ mirror uses"""
+    p = host_lib().scuffb200_context()
+    if not p:
+        raise ScuffError(host_lib().scuffb200_last_error().decode())
+    return p
+
+
+class HMatrix:
+    """scuff::HMatrix (column-major); .array is a numpy view of the HOST copy, shape (NR, NC)"""
+
+    def __init__(self, ptr, owner=True):
+        self.ptr = ptr
+        self.owner = owner
+        sh = (C.c_int * 3)()
+        host_lib().scuffb200_matrix_shape(ptr, sh)
+        self.NR, self.NC, self.is_real = sh[0], sh[1], bool(sh[2])
+
+    @classmethod
+    def new(cls, nr, nc, is_real=False):
+        p = host_lib().scuffb200_matrix_new(nr, nc, int(is_real))
+        if not p:
+            raise ScuffError(host_lib().scuffb200_last_error().decode())
+        return cls(p)
+
+    @property
+    def array(self):
+        _check(host_lib().scuffb200_matrix_sync_host(self.ptr))
+        data = host_lib().scuffb200_matrix_data(self.ptr)
+        n = self.NR * self.NC
+        if self.is_real:
+            buf = (C.c_double * n).from_address(data)
+            a = np.frombuffer(buf, dtype=np.float64)
+        else:
+            buf = (C.c_double * (2 * n)).from_address(data)
+            a = np.frombuffer(buf, dtype=np.complex128)
+        return a.reshape(self.NC, self.NR).T   # column-major storage
+
+    @property
+    def device_handle(self):
+        return host_lib().scuffb200_matrix_device_handle(self.ptr)
+
+    def lu_factorize(self):
+        _check(host_lib().scuffb200_lu_factorize(self.ptr))
+
+    def lu_solve(self, X):
+        _check(host_lib().scuffb200_lu_solve(self.ptr, X.ptr))
+
+    def __del__(self):
+        if getattr(self, "owner", False) and self.ptr and _host is not None:
+            _host.scuffb200_matrix_free(self.ptr)
+            self.ptr = None
+
+
+class RWGGeometry:
+    """scuff::RWGGeometry from a .scuffgeo file"""
+
+    def __init__(self, geofile):
+        L = host_lib()
+        self.ptr = L.scuffb200_geometry_open(os.fsencode(geofile))
+        if not self.ptr:
+            raise ScuffError(L.scuffb200_last_error().decode())
+        info = (C.c_int * 8)()
+        L.scuffb200_geometry_info(self.ptr, info)
+        (self.NumSurfaces, self.TotalBFs, self.NumRegions, self.LDim,
+         self.TotalPanels, self.TotalEdges, self.AllSurfacesClosed, _) = list(info)
+
+    def surface(self, ns):
+        L = host_lib()
+        si = (C.c_int * 10)()
+        if L.scuffb200_surface_info(self.ptr, ns, si):
+            raise ScuffError("invalid surface index")
+        NV, NP, NE = si[0], si[1], si[2]
+        V = np.zeros((NV, 3)); PVI = np.zeros((NP, 3), dtype=np.int32); PC = np.zeros((NP, 3))
+        PR = np.zeros(NP); PA = np.zeros(NP); ET = np.zeros((max(NE, 1), 8), dtype=np.int32); EL = np.zeros(max(NE, 1))
+        L.scuffb200_surface_arrays(self.ptr, ns, V.ctypes.data, PVI.ctypes.data, PC.ctypes.data, PR.ctypes.data,
+                                   PA.ctypes.data, ET.ctypes.data, EL.ctypes.data)
+        return dict(Label=L.scuffb200_surface_label(self.ptr, ns).decode(), NV=NV, NP=NP, NE=NE, NBF=si[3],
+                    IsPEC=bool(si[4]), Regions=(si[5], si[6]), BFOffset=si[7], Mate=si[8], NumHalfRWGEdges=si[9],
+                    V=V, PVI=PVI, PC=PC, PR=PR, PA=PA, ET=ET[:NE], EL=EL[:NE])
+
+    def regions(self):
+        L = host_lib()
+        return [(L.scuffb200_region_label(self.ptr, nr).decode(), L.scuffb200_region_material(self.ptr, nr).decode())
+                for nr in range(self.NumRegions)]
+
+    def eps_mu(self, omega):
+        out = np.zeros((self.NumRegions, 4))
+        _check(host_lib().scuffb200_eps_mu(self.ptr, float(np.real(omega)), float(np.imag(omega)), out.ctypes.data))
+        return out[:, 0] + 1j * out[:, 1], out[:, 2] + 1j * out[:, 3]
+
+    def transform(self, line):
+        _check(host_lib().scuffb200_transform(self.ptr, line.encode()))
+
+    def untransform(self):
+        _check(host_lib().scuffb200_untransform(self.ptr))
+
+    def zero_region(self, nr, zero=True):
+        _check(host_lib().scuffb200_zero_region(self.ptr, nr, int(zero)))
+
+    def AllocateBEMMatrix(self, PureImagFreq=False):
+        p = host_lib().scuffb200_matrix_alloc(self.ptr, int(PureImagFreq))
+        if not p:
+            raise ScuffError(host_lib().scuffb200_last_error().decode())
+        return HMatrix(p)
+
+    def AssembleBEMMatrix(self, Omega, kBloch=None, M=None, to_host=True):
+        if M is None:
+            M = self.AllocateBEMMatrix()
+        kb = None
+        if kBloch is not None:
+            kb = (C.c_double * 2)(float(kBloch[0]), float(kBloch[1]))
+        _check(host_lib().scuffb200_assemble(self.ptr, M.ptr, float(np.real(Omega)), float(np.imag(Omega)),
+                                              kb, int(to_host)))
+        return M
+
+    def AssembleBEMMatrixBlock(self, nsa, nsb, Omega, M, kBloch=None, RowOffset=0, ColOffset=0):
+        kb = None
+        if kBloch is not None:
+            kb = (C.c_double * 2)(float(kBloch[0]), float(kBloch[1]))
+        _check(host_lib().scuffb200_assemble_block(self.ptr, M.ptr, nsa, nsb, float(np.real(Omega)),
+                                                    float(np.imag(Omega)), kb, RowOffset, ColOffset))
+        return M
+
+    def ppi_counts(self):
+        out = (C.c_ulonglong * 5)()
+        host_lib().scuffb200_ppi_counts(self.ptr, out)
+        return list(out)
+
+    def close(self):
+        if self.ptr and _host is not None:
+            _host.scuffb200_geometry_close(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        self.close()
+
+
+def PreloadCache(fn):
+    _check(host_lib().scuffb200_preload_cache(os.fsencode(fn)))
+
+
+def StoreCache(fn):
+    _check(host_lib().scuffb200_store_cache(os.fsencode(fn)))
+
+
+def last_timing():
+    t = (C.c_double * 5)()
+    cuda_lib().scuffcuda_get_last_timing(context(), t)
+    return list(t)
+
+
+def measure_fp64_peak():
+    v = C.c_double()
+    if cuda_lib().scuffcuda_measure_fp64_peak(context(), C.byref(v)):
+        raise ScuffError(cuda_lib().scuffcuda_last_error(context()).decode())
+    return v.value

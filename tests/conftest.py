@@ -1,0 +1,81 @@
+"""Shared test plumbing.  `-m gpu` tests need a B200; everything else runs on CPU.
+
+The oracle (oracle/: numpy restatement + oracle/_ref, the UNMODIFIED reference compiled from
+/root/reference by oracle/Makefile) is test infrastructure: only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline/reference arm may use it.
+"""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+import hashlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GEODIR = os.path.join(ROOT, "tests", "golden", "geometries")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200)")
+
+
+def load_pyscuff():
+    spec = importlib.util.spec_from_file_location("pyscuff", os.path.join(ROOT, "scuff-em_b200", "pyscuff.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="session")
+def ps():
+    return load_pyscuff()
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    spec = importlib.util.spec_from_file_location("scuff_oracle", os.path.join(ROOT, "oracle", "scuff_oracle.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def have_ref():
+    return os.path.exists(REF_DRIVER)
+
+
+def ref_matrix(geo, omega, kbloch=None, imag=False, block=None, cache_in=None, cache_out=None, tmpdir="/tmp/scuff_ref_cache"):
+    """Run the UNMODIFIED reference (oracle/_ref/ref_driver) and return (M, info).  Results are cached on disk."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
+    os.makedirs(tmpdir, exist_ok=True)
+    key = hashlib.md5(repr((geo, complex(omega), kbloch, imag, block, cache_in)).encode()).hexdigest()[:16]
+    out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
+    meta = out + ".json"
+    if not (os.path.exists(out) and os.path.exists(meta)) or cache_out:
+        cmd = [REF_DRIVER, "matrix", os.path.basename(geo), repr(float(np.real(omega))), repr(float(np.imag(omega))), out]
+        if kbloch is not None:
+            cmd += ["--kbloch", repr(float(kbloch[0])), repr(float(kbloch[1]))]
+        if imag:
+            cmd += ["--imag"]
+        if block is not None:
+            cmd += ["--block", str(block[0]), str(block[1])]
+        if cache_in:
+            cmd += ["--cache-in", cache_in]
+        if cache_out:
+            cmd += ["--cache-out", cache_out]
+        r = subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True)
+        open(meta, "w").write(r.stdout.strip().splitlines()[-1])
+    info = json.load(open(meta))
+    dt = np.float64 if info["real"] else np.complex128
+    M = np.fromfile(out, dtype=dt).reshape(info["NC"], info["NR"]).T
+    return M, info
+
+
+def rel_fro(A, B):
+    return np.linalg.norm(A - B) / np.linalg.norm(B)
