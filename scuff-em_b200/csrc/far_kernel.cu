@@ -82,8 +82,7 @@ far_kernel(const FarArgs A)
       }
    }
   // algorithm counter (reference log line SurfaceSurfaceInteractions.cc:550-558)
-  for (int o = 16; o > 0; o >>= 1) nPPI += __shfl_down_sync(0xffffffffu, nPPI, o);
-  if ((threadIdx.x & 31) == 0 && nPPI) atomicAdd(A.counters, nPPI);
+  if (nPPI) atomicAdd(A.counters, nPPI);
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)

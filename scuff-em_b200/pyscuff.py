@@ -134,7 +134,7 @@ def context():
 
 
 class HMatrix:
-    """scuff::HMatrix (column-major); .array is a numpy view of the HOST copy, shape (NR, NC)"""
+    """scuff::HMatrix (column-major); .array is a numpy COPY of the host data, shape (NR, NC)"""
 
     def __init__(self, ptr, owner=True):
         self.ptr = ptr
@@ -161,7 +161,7 @@ class HMatrix:
         else:
             buf = (C.c_double * (2 * n)).from_address(data)
             a = np.frombuffer(buf, dtype=np.complex128)
-        return a.reshape(self.NC, self.NR).T   # column-major storage
+        return np.array(a.reshape(self.NC, self.NR).T)   # column-major storage; copy (the HMatrix may be freed)
 
     @property
     def device_handle(self):
