@@ -121,4 +121,17 @@ SCUFF_HD int canonical_order(const double *const Va[3], const double *const Vb[3
    }
 }
 
+// FIPPI cache key (FIPPICache.cc:120-156): 15 floats, vertex differences taken in FLOAT arithmetic
+// relative to OVa[0] — translation invariant to float precision.
+SCUFF_HD void fippi_key(const double *const OVa[3], const double *const OVb[3], float k[15])
+{ for (int m = 0; m < 3; m++)
+   { float v0 = (float)OVa[0][m];
+     k[0 + m] = ((float)OVa[1][m]) - v0;
+     k[3 + m] = ((float)OVa[2][m]) - v0;
+     k[6 + m] = ((float)OVb[0][m]) - v0;
+     k[9 + m] = ((float)OVb[1][m]) - v0;
+     k[12 + m] = ((float)OVb[2][m]) - v0;
+   }
+}
+
 }  // namespace scuffcuda

@@ -54,8 +54,16 @@ struct NearPair
   unsigned char ia[3], ib[3];      // AssessPanelPair vertex order (common vertices first)
   unsigned char oa[3], ob[3];      // canonical order; if flipped, oa indexes panel b's vertices
   int flipped;
-  int rec;                         // FIPPI record index (-1: none needed yet)
+  int rec;                         // FIPPI record index (-1: none needed)
+  // Symmetric blocks visit an unordered pair once, but the reference evaluates PPI(pb,pa) (not
+  // PPI(pa,pb)) for the edge pairs whose lower-numbered edge lies on pb.  For ncv==0 the
+  // "canonical" ordering is not symmetric under swapping the panels (AssessPanelPair.cc:413-451), so
+  // the swapped order has its own canonical vertices, key and FIPPI record:
+  unsigned char oa2[3], ob2[3];
+  unsigned char flipped2, hasSwap;
+  int rec2;
 };
+static_assert(sizeof(NearPair) == 44, "NearPair layout");
 
 struct Plan
 { uint64_t genA = 0, genB = 0;
