@@ -233,6 +233,7 @@ class RWGGeometry
    void InitPBCData();
    void AssembleBEMMatrixBlockPBC(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset, int ColOffset);
    std::vector<char> DeviceDirty;
+   unsigned long long DeviceId;
    void AddRegion(const char *RegionLabel, const char *MaterialName, int LineNum);
    bool PointInRegion(int nr, const double X[3]);
    unsigned long long LastPPICounts[5];

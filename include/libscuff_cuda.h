@@ -115,6 +115,8 @@ int scuffcuda_synchronize(scuffcuda_context *ctx);
 int scuffcuda_fippi_preload(scuffcuda_context *ctx, const char *filename);
 int scuffcuda_fippi_store(scuffcuda_context *ctx, const char *filename);
 int scuffcuda_fippi_num_records(scuffcuda_context *ctx, long *n);
+/* drop every record (and the pair plans that index them); next assembly rebuilds the table on the device */
+int scuffcuda_fippi_clear(scuffcuda_context *ctx);
 
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* dependent-chain-free DFMA microkernel: returns achieved FP64 TFLOP/s (2 flop per FMA);

@@ -254,6 +254,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   CK(cudaEventRecord(ev[0], ctx->stream));
   CK(cudaMemsetAsync(ctx->dcounters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   M->factored = false;
+  ctx->timing[3] = 0.0;
 
   if (!a->accumulate) launch_zero_block(ctx, *M, a->row_offset, NBFA, a->col_offset, NBFB);
 

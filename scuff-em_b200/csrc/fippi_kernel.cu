@@ -1,8 +1,113 @@
-// Device builder of FIPPI records (stub; filled in below)
+// Device builder of the FIPPI table (QIFIPPIData records, libscuffInternals.h:282-293): one thread per
+// record runs the reference's adaptive cubature decision-for-decision (hcubature.cuh) on the integrands of
+// fippi_integrands.cuh.  Compiled with -fmad=false so that error estimates and threshold comparisons
+// are rounded like the reference's SSE2 arithmetic.  The table is built once per geometry and stays
+// resident in HBM across the frequency sweep (ComputeQIFIPPIData QIFIPPICubature.cc:465-487).
+#include <vector>
+#include <algorithm>
 #include "kernels.h"
+#include "fippi_integrands.cuh"
+#include "generated_tables.h"
+
 namespace scuffcuda {
+
+static_assert(sizeof(SCPXEntry) == sizeof(PXEntry) && sizeof(SCPCEntry) == sizeof(PCEntry), "generated table layout");
+
+struct FIPPIDeviceTables { PXEntry *cePX = nullptr, *cvPX = nullptr; PCEntry *cePC = nullptr, *cvPC = nullptr; };
+static FIPPIDeviceTables g_ft[64];
+
+static int fippi_tables(scuffcuda_context *ctx, FIPPITables &T)
+{ FIPPIDeviceTables &G = g_ft[ctx->device & 63];
+  if (!G.cePX)
+   { if (cudaMalloc(&G.cePX, sizeof SC_CE_PX_H) != cudaSuccess || cudaMalloc(&G.cePC, sizeof SC_CE_PC_H) != cudaSuccess
+         || cudaMalloc(&G.cvPX, sizeof SC_CV_PX_H) != cudaSuccess || cudaMalloc(&G.cvPC, sizeof SC_CV_PC_H) != cudaSuccess)
+      { ctx->err = "FIPPI table allocation failed"; return 1; }
+     cudaMemcpy(G.cePX, SC_CE_PX_H, sizeof SC_CE_PX_H, cudaMemcpyHostToDevice);
+     cudaMemcpy(G.cePC, SC_CE_PC_H, sizeof SC_CE_PC_H, cudaMemcpyHostToDevice);
+     cudaMemcpy(G.cvPX, SC_CV_PX_H, sizeof SC_CV_PX_H, cudaMemcpyHostToDevice);
+     cudaMemcpy(G.cvPC, SC_CV_PC_H, sizeof SC_CV_PC_H, cudaMemcpyHostToDevice);
+   }
+  T.cePX = G.cePX; T.cePXn = SC_CE_PX_N; T.cePC = G.cePC; T.cePCn = SC_CE_PC_N;
+  T.cvPX = G.cvPX; T.cvPXn = SC_CV_PX_N; T.cvPC = G.cvPC; T.cvPCn = SC_CV_PC_N;
+  return 0;
+}
+
+#define FIPPI_REGION_BYTES 608   /* >= sizeof(HCRegion<3>) */
+static_assert(sizeof(HCRegion<3>) <= FIPPI_REGION_BYTES, "region size");
+
+// verts: 18 doubles per item (OVa[0..2], OVb[0..2]); out: 36 doubles per item; status: per item
+__global__ void __launch_bounds__(64)
+fippi_build_kernel(const FIPPITables T, const double *verts, const int *ncvs, const int *items, int nItems,
+                   char *pool, int capacity, double *out, int *status)
+{ const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nItems) return;
+  const int it = items[t];
+  const double *V = verts + 18 * (size_t)it;
+  const double *OVa[3] = { V, V + 3, V + 6 }, *OVb[3] = { V + 9, V + 12, V + 15 };
+  char *mypool = pool + (size_t)t * ((size_t)capacity * (FIPPI_REGION_BYTES + sizeof(int)));
+  int *heap = (int *)(mypool + (size_t)capacity * FIPPI_REGION_BYTES);
+  double val[HC_FDIM], err[HC_FDIM];
+  int st;
+  if (ncvs[it] == 0)
+   { CFD3D f; f.setup(OVa, OVb);
+     st = hcubature_run<3>(f, 1000000, 1.0e-10, 1.0e-6, (HCRegion<3> *)mypool, heap, capacity, val, err);
+   }
+  else
+   { TDFIPPI f; f.setup(&T, OVa[0], OVa[1], OVa[2], OVb[1], OVb[2]);
+     if (f.commonEdge) st = hcubature_run<1>(f, 10000, 0.0, 1.0e-5, (HCRegion<1> *)mypool, heap, capacity, val, err);
+     else              st = hcubature_run<2>(f, 10000, 0.0, 1.0e-5, (HCRegion<2> *)mypool, heap, capacity, val, err);
+   }
+  status[t] = st;
+  if (st) return;
+  double *o = out + FIPPI_REC_DOUBLES * (size_t)it;
+  for (int j = 0; j < HC_FDIM; j++) o[j] = val[j];
+  for (int m = 0; m < 3; m++) o[33 + m] = (OVa[0][m] + OVa[1][m] + OVa[2][m]) / 3.0;
+}
+
 int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds, const std::vector<double> &verts,
                           const std::vector<int> &ncvs)
-{ ctx->err = "FIPPI records missing from the preloaded cache and the device FIPPI builder is not available yet";
-  return 1; }
+{ const int n = (int)recIds.size();
+  if (n == 0) return 0;
+  FIPPITables T; if (fippi_tables(ctx, T)) return 1;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, ctx->stream);
+  double *dverts = nullptr, *dout = nullptr; int *dncv = nullptr, *ditems = nullptr, *dstatus = nullptr; char *dpool = nullptr;
+  auto cleanup = [&]() { cudaFree(dverts); cudaFree(dout); cudaFree(dncv); cudaFree(ditems); cudaFree(dstatus); cudaFree(dpool); cudaEventDestroy(e0); cudaEventDestroy(e1); };
+  if (cudaMalloc(&dverts, (size_t)n * 18 * sizeof(double)) != cudaSuccess || cudaMalloc(&dout, (size_t)n * FIPPI_REC_DOUBLES * sizeof(double)) != cudaSuccess
+      || cudaMalloc(&dncv, n * sizeof(int)) != cudaSuccess || cudaMalloc(&ditems, n * sizeof(int)) != cudaSuccess || cudaMalloc(&dstatus, n * sizeof(int)) != cudaSuccess)
+   { ctx->err = "FIPPI builder allocation failed"; cleanup(); return 1; }
+  cudaMemcpy(dverts, verts.data(), (size_t)n * 18 * sizeof(double), cudaMemcpyHostToDevice);
+  cudaMemcpy(dncv, ncvs.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+
+  std::vector<int> todo(n); for (int i = 0; i < n; i++) todo[i] = i;
+  // pass 1: small region pools, many records in flight; pass 2: the few records that need more regions
+  const int caps[3] = { 384, 4096, 15200 }; const int batches[3] = { 24576, 2048, 512 };
+  for (int pass = 0; pass < 3 && !todo.empty(); pass++)
+   { const int cap = caps[pass], batch = std::min(batches[pass], (int)todo.size());
+     size_t perThread = (size_t)cap * (FIPPI_REGION_BYTES + sizeof(int));
+     if (dpool) { cudaFree(dpool); dpool = nullptr; }
+     if (cudaMalloc(&dpool, perThread * batch) != cudaSuccess) { ctx->err = "FIPPI builder pool allocation failed"; cleanup(); return 1; }
+     std::vector<int> next, st(batch);
+     for (size_t first = 0; first < todo.size(); first += batch)
+      { int m = (int)std::min((size_t)batch, todo.size() - first);
+        cudaMemcpyAsync(ditems, todo.data() + first, m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        fippi_build_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>(T, dverts, dncv, ditems, m, dpool, cap, dout, dstatus);
+        cudaMemcpyAsync(st.data(), dstatus, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("fippi_build_kernel: ") + cudaGetErrorString(e); cleanup(); return 1; }
+        for (int i = 0; i < m; i++) if (st[i]) next.push_back(todo[first + i]);
+      }
+     todo.swap(next);
+   }
+  if (!todo.empty()) { ctx->err = "FIPPI builder: region pool exhausted"; cleanup(); return 1; }
+  std::vector<double> hout((size_t)n * FIPPI_REC_DOUBLES);
+  cudaMemcpy(hout.data(), dout, hout.size() * sizeof(double), cudaMemcpyDeviceToHost);
+  for (int i = 0; i < n; i++)
+   std::copy(hout.begin() + (size_t)i * FIPPI_REC_DOUBLES, hout.begin() + (size_t)(i + 1) * FIPPI_REC_DOUBLES,
+             ctx->fippi.hrec.begin() + (size_t)recIds[i] * FIPPI_REC_DOUBLES);
+  cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); ctx->timing[3] += ms;
+  cleanup();
+  return 0;
 }
+
+}  // namespace scuffcuda

@@ -363,4 +363,13 @@ int scuffcuda_fippi_store(scuffcuda_context *ctx, const char *filename)
 
 int scuffcuda_fippi_num_records(scuffcuda_context *ctx, long *n) { *n = (long)ctx->fippi.keys.size(); return 0; }
 
+int scuffcuda_fippi_clear(scuffcuda_context *ctx)
+{ cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  for (auto &p : ctx->plans) if (p.dnear) cudaFree(p.dnear);
+  ctx->plans.clear();
+  FIPPITable &T = ctx->fippi;
+  T.index.clear(); T.keys.clear(); T.hrec.clear(); T.dcount = 0;
+  return 0;
+}
+
 }  // extern "C"

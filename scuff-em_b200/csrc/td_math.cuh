@@ -1,0 +1,212 @@
+// Taylor-Duffy evaluation of singular panel-pair integrals (frequency dependent) and the p-adaptive
+// Clenshaw-Curtis cubature that integrates the reduced integrand.
+//
+// Reference semantics: TaylorDuffy() libs/libscuff/TaylorDuffy.cc:277-368 (driver), TaylorDuffySum
+// :152-258 (integrand: sum over sub-regions d and powers n of P_dn(y) K_n(X_d(y))), GetX :491-547,
+// GetScriptP :552-622, GetScriptK :896-935, ExpRelV3P0 :829-891, ComputeGeometricParameters :1265-1526,
+// and pcubature libs/libSGJC/pcubature.c:300-400 (nested Clenshaw-Curtis levels, error = difference
+// to the previous level, per-component convergence test converged.h, stop when numEval > MaxEval).
+// The polynomial coefficient maps (CMVStoUpsilon) come from generated_tables.h as data.
+//
+// Implemented here: the common-triangle case (ncv == 3, 1-D integral), which the reference uses at
+// every frequency; the common-edge / common-vertex cases are only reached in the short-wavelength
+// regime (|k| R > pi) and are reported as unsupported by the dispatcher.
+#pragma once
+#include "ppi_math.cuh"
+#include "fippi_math.cuh"
+
+namespace scuffcuda {
+
+struct UpsEntry { unsigned char cas, d, n, mono, input; double coef; };
+
+struct TDTables
+{ const double *ccx, *ccw;          // Clenshaw-Curtis nodes / weights (clencurt.h layout)
+  const UpsEntry *ups; int upsStart[5];
+};
+
+#define TD_NUMWPOWERS 5
+#define TD_Y1TERM 1
+
+// complex helpers with std::complex-like semantics
+SCUFF_HD cd cexp_(cd z) { double e = exp(z.x), s, c; sincos(z.y, &s, &c); return mk(e * c, e * s); }
+SCUFF_HD double cabs_(cd z) { return hypot(z.x, z.y); }
+
+// ExpRel(n,Z) = (e^Z - first n Taylor terms) / (Z^n/n!)   (TaylorDuffy.cc:829-891)
+SCUFF_HD cd exprel_v3p0(int n, cd Z)
+{ if (Z.y == 0.0)
+   { double X = Z.x;
+     if (fabs(X) < 0.1)
+      { double Sum = 1.0, Term = 1.0;
+        for (int m = 1; m < 100; m++)
+         { Term *= X / ((double)(m + n)); Sum += Term;
+           if (fabs(Term) < 1.0e-8 * fabs(Sum)) break; }
+        return mk(Sum, 0.0);
+      }
+     double Sum = exp(X), Term = 1.0;
+     for (int m = 0; m < n; m++) { Sum -= Term; Term *= X / ((double)(m + 1)); }
+     return mk(Sum / Term, 0.0);
+   }
+  if (cabs_(Z) < 0.1)
+   { cd Sum = mk(1.0, 0.0), Term = mk(1.0, 0.0);
+     for (int m = 1; m < 100; m++)
+      { double dv = (double)(m + n);
+        Term = Term * mk(Z.x / dv, Z.y / dv); Sum += Term;
+        if (norm2(Term) < 1.0e-16 * norm2(Sum)) break; }
+     return Sum;
+   }
+  cd Sum = cexp_(Z), Term = mk(1.0, 0.0);
+  for (int m = 0; m < n; m++)
+   { Sum -= Term; double dv = (double)(m + 1); Term = Term * mk(Z.x / dv, Z.y / dv); }
+  return cdiv(Sum, Term);
+}
+
+// per-call workspace for the common-triangle case with the two P polynomials the assembly needs:
+// P0 = 1 (TD_UNITY), P1 = (x-Q).(x'-Q') (TD_PMCHWG1); kernel e^{ikr}/(4 pi r) (TD_HELMHOLTZ)
+struct TDCommonTriangle
+{ double A2, AdB, B2;
+  double U[2][3][TD_NUMWPOWERS][2];   // [P][region][n][ {1, y} ]
+  int nMin[2], nMax[2];
+  cd k;
+};
+
+SCUFF_HD void td_ct_setup(const TDTables &T, const double *V1, const double *V2, const double *V3,
+                          const double *Q, const double *QP, cd k, TDCommonTriangle &W)
+{ double A[3], B[3], D[3], DP[3];
+  sub3(V2, V1, A); sub3(V3, V2, B); sub3(V1, Q, D); sub3(V1, QP, DP);
+  W.A2 = dot3(A, A); W.AdB = dot3(A, B); W.B2 = dot3(B, B); W.k = k;
+  for (int np = 0; np < 2; np++)
+   { double in[19];
+     for (int i = 0; i < 19; i++) in[i] = 0.0;
+     if (np == 0) in[18] = 1.0;                                   // S = 1
+     else
+      { // common triangle: A' = A, B' = B  (inputs: 4 C, then M11 M12 M13 M14 M22 M23 M24 M33 M34 M44, V1..V4, S)
+        in[4 + 2] = dot3(A, A); in[4 + 3] = dot3(A, B); in[4 + 5] = dot3(B, A); in[4 + 6] = dot3(B, B);
+        in[14] = dot3(A, DP); in[15] = dot3(B, DP); in[16] = dot3(D, A); in[17] = dot3(D, B);
+        in[18] = dot3(D, DP);
+      }
+     for (int d = 0; d < 3; d++) for (int n = 0; n < TD_NUMWPOWERS; n++) { W.U[np][d][n][0] = 0.0; W.U[np][d][n][1] = 0.0; }
+     int nMin = TD_NUMWPOWERS - 1, nMax = -1;
+     double U2[3][TD_NUMWPOWERS];   // y^2 monomial: contributes to the nMin/nMax scan only
+     for (int d = 0; d < 3; d++) for (int n = 0; n < TD_NUMWPOWERS; n++) U2[d][n] = 0.0;
+     for (int e = T.upsStart[3]; e < T.upsStart[4]; e++)
+      { const UpsEntry &E = T.ups[e];
+        double v = E.coef * in[E.input];
+        if (E.mono == 0) W.U[np][E.d][E.n][0] += v;
+        else if (E.mono == TD_Y1TERM) W.U[np][E.d][E.n][1] += v;
+        else U2[E.d][E.n] += v;
+      }
+     for (int n = 0; n < TD_NUMWPOWERS; n++) for (int d = 0; d < 3; d++)
+      if (fabs(W.U[np][d][n][0]) > 1.0e-8 || fabs(W.U[np][d][n][1]) > 1.0e-8 || fabs(U2[d][n]) > 1.0e-8)
+       { if (n < nMin) nMin = n; if (n > nMax) nMax = n; }
+     W.nMin[np] = nMin; W.nMax[np] = nMax;
+   }
+}
+
+// integrand at y in [0,1]: f[0..3] = Re/Im of the two P x Helmholtz integrals (TaylorDuffySum)
+SCUFF_HD void td_ct_integrand(const TDCommonTriangle &W, double y, double f[4])
+{ double X[3], u1, u2;
+  u1 = 1.0; u2 = y;       X[0] = sqrt(W.A2 * u1 * u1 + 2.0 * W.AdB * u1 * u2 + W.B2 * u2 * u2);
+  u1 = y;   u2 = (y - 1); X[1] = sqrt(W.A2 * u1 * u1 + 2.0 * W.AdB * u1 * u2 + W.B2 * u2 * u2);
+  u1 = y;   u2 = 1.0;     X[2] = sqrt(W.A2 * u1 * u1 + 2.0 * W.AdB * u1 * u2 + W.B2 * u2 * u2);
+  const cd IK = mk(-W.k.y, W.k.x);
+  for (int np = 0; np < 2; np++)
+   { const int nMin = W.nMin[np], nMax = W.nMax[np];
+     cd K[3][7];
+     for (int d = 0; d < 3; d++)
+      { cd IKX = mk(IK.x * X[d], IK.y * X[d]), eIKX = cexp_(IKX), mIKX = mk(-IKX.x, -IKX.y);
+        for (int n = nMin + 1; n <= nMax + 1; n++)
+         { cd t = eIKX * exprel_v3p0(n, mIKX); double dn = n * X[d]; K[d][n] = mk(t.x / dn, t.y / dn); }
+      }
+     cd Sum = mk(0.0, 0.0);
+     for (int n = nMin; n <= nMax; n++)
+      for (int d = 0; d < 3; d++)
+       { double p = W.U[np][d][n][0] + y * W.U[np][d][n][1];
+         Sum += p * K[d][n + 1]; }
+     const double s = 1.0 / (4.0 * M_PI);     // Jacobian = 1
+     f[2 * np] = Sum.x * s; f[2 * np + 1] = Sum.y * s;
+   }
+}
+
+// 1-D p-adaptive Clenshaw-Curtis over [0,1] for an FDIM-component integrand (pcubature.c semantics).
+// cache: caller-provided scratch of at least FDIM*(2^(maxM+1)+1) doubles, element e at cache[e*stride]
+// (stride = number of threads sharing the scratch block on the device, so accesses coalesce).
+template <int FDIM, typename F>
+SCUFF_HD int pcubature_1d(const TDTables &T, F &func, double relTol, double absTol, int maxEval,
+                          double *cache, size_t stride, double val[FDIM], double err[FDIM], int maxM)
+{ const double c = 0.5, r = 0.5, V = 0.5;
+  int m = 0, numEval = 0;
+  { double fv[FDIM];
+    func(c, fv);                  for (int j = 0; j < FDIM; j++) cache[(size_t)(j) * stride] = fv[j];
+    func(c + r * T.ccx[0], fv);   for (int j = 0; j < FDIM; j++) cache[(size_t)(FDIM + j) * stride] = fv[j];
+    func(c - r * T.ccx[0], fv);   for (int j = 0; j < FDIM; j++) cache[(size_t)(2 * FDIM + j) * stride] = fv[j];
+  }
+  for (;;)
+   { for (int pass = 0; pass < 2; pass++)
+      { // pass 0: rule of order m; pass 1: order m-1 (error estimate)
+        double acc[FDIM];
+        for (int j = 0; j < FDIM; j++) acc[j] = 0.0;
+        if (pass == 1 && m == 0)
+         { double w = V * 2; for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(j) * stride] * w; }
+        else
+         { const int mid = m - pass;
+           const double *wb = T.ccw + mid + (1 << mid) - 1;
+           double w = V * wb[0];
+           for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(j) * stride] * w;
+           w = V * wb[1];
+           for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(FDIM + j) * stride] * w;
+           for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(2 * FDIM + j) * stride] * w;
+           for (int kk = 1; kk <= mid; kk++)
+            { const double *wk = wb + 1 + (1 << (kk - 1));
+              const int nx = 1 << (kk - 1);
+              const double *cv = cache + (size_t)FDIM * ((1 << kk) + 1) * stride;   // level kk starts after 2^kk+1 points
+              for (int i = 0; i < nx; i++)
+               { double ww = V * wk[i];
+                 for (int j = 0; j < FDIM; j++) acc[j] += cv[(size_t)((2 * i) * FDIM + j) * stride] * ww;
+                 for (int j = 0; j < FDIM; j++) acc[j] += cv[(size_t)((2 * i + 1) * FDIM + j) * stride] * ww;
+               }
+            }
+         }
+        if (pass == 0) { for (int j = 0; j < FDIM; j++) val[j] = acc[j]; }
+        else { for (int j = 0; j < FDIM; j++) err[j] = fabs(val[j] - acc[j]); }
+      }
+     bool conv = true;
+     for (int j = 0; j < FDIM; j++) if (err[j] > absTol && err[j] > fabs(val[j]) * relTol) { conv = false; break; }
+     if (conv || (numEval > maxEval && maxEval)) return 0;
+     m += 1;
+     if (m > maxM) return 1;
+     const int nx = 1 << (m - 1);
+     const double *x = T.ccx + nx;
+     double *cv = cache + (size_t)FDIM * ((1 << m) + 1) * stride;
+     for (int i = 0; i < nx; i++)
+      { double fv[FDIM];
+        func(c + r * x[i], fv); for (int j = 0; j < FDIM; j++) cv[(size_t)((2 * i) * FDIM + j) * stride] = fv[j];
+        func(c - r * x[i], fv); for (int j = 0; j < FDIM; j++) cv[(size_t)((2 * i + 1) * FDIM + j) * stride] = fv[j];
+      }
+     numEval += 2 * nx;
+   }
+}
+
+struct TDCTFunctor
+{ const TDCommonTriangle *W;
+  SCUFF_HD void operator()(double y, double f[4]) const { td_ct_integrand(*W, y, f); }
+};
+
+// H[0], H[1] of a common-triangle panel pair (PanelPanelInteractions.cc:449-491 with ncv == 3):
+// H0 = R1 - 4 R0 / k^2, H1 = 0.  Vertices in AssessPanelPair order (V1,V2,V3).  Returns pcubature status.
+SCUFF_HD int td_common_triangle(const TDTables &T, const double *V1, const double *V2, const double *V3,
+                                const double *Q, const double *QP, cd k, double *cache, size_t stride, cd &H0, cd &H1)
+{ TDCommonTriangle W;
+  td_ct_setup(T, V1, V2, V3, Q, QP, k, W);
+  TDCTFunctor F; F.W = &W;
+  double val[4], err[4];
+  int st = pcubature_1d<4>(T, F, 1.0e-10, 0.0, 1000, cache, stride, val, err, 9);
+  cd R0 = mk(val[0], val[1]), R1 = mk(val[2], val[3]);
+  cd k2 = k * k;
+  cd t = cdiv(mk(4.0 * R0.x, 4.0 * R0.y), k2);
+  H0 = R1 - t; H1 = mk(0.0, 0.0);
+  return st;
+}
+
+#define TD_CACHE_DOUBLES (4 * ((1 << 10) + 1))   /* MaxEval = 1000 stops at level 9: 1025 points */
+
+}  // namespace scuffcuda

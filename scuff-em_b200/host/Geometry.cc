@@ -637,6 +637,7 @@ RWGGeometry::RWGGeometry(const char *pGeoFileName, int pLogLevel)
          Mate[ns] = nsp; } }
   SurfaceMoved = (int *)calloc(NumSurfaces, sizeof(int));
   DeviceDirty.assign(NumSurfaces, 1);
+  DeviceId = 0;
 }
 
 RWGGeometry::~RWGGeometry()
@@ -682,10 +683,13 @@ void RWGGeometry::UnTransform()
 
 void RWGGeometry::SyncDeviceGeometry()
 { scuffcuda_context *ctx = GetCudaContext();
-  static RWGGeometry *lastOwner = 0;
-  if (lastOwner != this)
-   { if (scuffcuda_set_num_surfaces(ctx, NumSurfaces)) ErrExit("%s", scuffcuda_last_error(ctx));
-     DeviceDirty.assign(NumSurfaces, 1); lastOwner = this; }
+  // the device context holds ONE geometry at a time; a process-unique id (not the object address,
+  // which the allocator may recycle) tells whether it is ours
+  static unsigned long long deviceOwner = 0, nextId = 0;
+  if (DeviceId == 0) DeviceId = ++nextId;
+  if (deviceOwner != DeviceId)
+   { if (scuffcuda_set_num_surfaces(ctx, 0) || scuffcuda_set_num_surfaces(ctx, NumSurfaces)) ErrExit("%s", scuffcuda_last_error(ctx));
+     DeviceDirty.assign(NumSurfaces, 1); deviceOwner = DeviceId; }
   for (int ns = 0; ns < NumSurfaces; ns++)
    { if (!DeviceDirty[ns]) continue;
      RWGSurface *S = Surfaces[ns];

@@ -83,6 +83,8 @@ int scuffb200_lu_factorize(void *m) { GUARD(return ((HMatrix *)m)->LUFactorize()
 int scuffb200_lu_solve(void *m, void *x) { GUARD(return ((HMatrix *)m)->LUSolve((HMatrix *)x);, 1) }
 int scuffb200_preload_cache(const char *f) { GUARD(PreloadCache(f); return 0;, 1) }
 int scuffb200_store_cache(const char *f) { GUARD(StoreCache(f); return 0;, 1) }
+int scuffb200_clear_cache() { GUARD(if (scuffcuda_fippi_clear(GetCudaContext())) ErrExit("%s", scuffcuda_last_error(GetCudaContext())); return 0;, 1) }
+long scuffb200_cache_records() { long n = 0; GUARD(scuffcuda_fippi_num_records(GetCudaContext(), &n); return n;, -1) }
 int scuffb200_set_disable_cache(int v) { RWGGeometry::DisableCache = (v != 0); return 0; }
 
 }  // extern "C"

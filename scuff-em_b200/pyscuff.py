@@ -66,6 +66,7 @@ def cuda_lib():
         L.scuffcuda_fippi_preload.argtypes = [C.c_void_p, C.c_char_p]
         L.scuffcuda_fippi_store.argtypes = [C.c_void_p, C.c_char_p]
         L.scuffcuda_fippi_num_records.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
+        L.scuffcuda_fippi_clear.argtypes = [C.c_void_p]
         L.scuffcuda_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _cuda = L
     return _cuda
@@ -112,6 +113,7 @@ def host_lib():
         L.scuffb200_preload_cache.argtypes = [C.c_char_p]
         L.scuffb200_store_cache.argtypes = [C.c_char_p]
         L.scuffb200_set_device.argtypes = [C.c_int]
+        L.scuffb200_cache_records.restype = C.c_long
         _host = L
     return _host
 
@@ -269,6 +271,14 @@ def PreloadCache(fn):
 
 def StoreCache(fn):
     _check(host_lib().scuffb200_store_cache(os.fsencode(fn)))
+
+
+def ClearCache():
+    _check(host_lib().scuffb200_clear_cache())
+
+
+def cache_records():
+    return host_lib().scuffb200_cache_records()
 
 
 def last_timing():

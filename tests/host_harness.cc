@@ -67,3 +67,40 @@ int hh_ppi(const double *Va, const double *Vb, int iQa, int iQb, double kr, doub
 }
 
 }
+
+// ---- Taylor-Duffy common-triangle check ----
+#include "../scuff-em_b200/csrc/td_math.cuh"
+#include "../scuff-em_b200/csrc/generated_tables.h"
+extern "C" int hh_td_ct(const double *V, int iQa, int iQb, double kr, double ki, double *out4)
+{ static_assert(sizeof(SCUpsEntry) == sizeof(UpsEntry), "layout");
+  TDTables T; T.ccx = SC_CC_X_H; T.ccw = SC_CC_W_H; T.ups = (const UpsEntry *)SC_UPS_H;
+  for (int i = 0; i < 5; i++) T.upsStart[i] = SC_UPS_START_H[i];
+  static double cache[TD_CACHE_DOUBLES];
+  cd H0, H1;
+  int st = td_common_triangle(T, V, V + 3, V + 6, V + 3 * iQa, V + 3 * iQb, mk(kr, ki), cache, 1, H0, H1);
+  out4[0] = H0.x; out4[1] = H0.y; out4[2] = H1.x; out4[3] = H1.y;
+  return st;
+}
+
+// ---- FIPPI builder check (adaptive cubature replica) ----
+#include "../scuff-em_b200/csrc/fippi_integrands.cuh"
+#include <vector>
+extern "C" int hh_fippi(const double *V, int ncv, double *out36, int *nregions)
+{ static_assert(sizeof(SCPXEntry) == sizeof(PXEntry) && sizeof(SCPCEntry) == sizeof(PCEntry), "layout");
+  FIPPITables T;
+  T.cePX = (const PXEntry *)SC_CE_PX_H; T.cePXn = SC_CE_PX_N; T.cePC = (const PCEntry *)SC_CE_PC_H; T.cePCn = SC_CE_PC_N;
+  T.cvPX = (const PXEntry *)SC_CV_PX_H; T.cvPXn = SC_CV_PX_N; T.cvPC = (const PCEntry *)SC_CV_PC_H; T.cvPCn = SC_CV_PC_N;
+  const int cap = 16000;
+  std::vector<char> pool((size_t)cap * 608); std::vector<int> heap(cap);
+  const double *OVa[3] = { V, V + 3, V + 6 }, *OVb[3] = { V + 9, V + 12, V + 15 };
+  double val[HC_FDIM], err[HC_FDIM]; int st;
+  if (ncv == 0) { CFD3D f; f.setup(OVa, OVb); st = hcubature_run<3>(f, 1000000, 1.0e-10, 1.0e-6, (HCRegion<3> *)pool.data(), heap.data(), cap, val, err); }
+  else
+   { TDFIPPI f; f.setup(&T, OVa[0], OVa[1], OVa[2], OVb[1], OVb[2]);
+     if (f.commonEdge) st = hcubature_run<1>(f, 10000, 0.0, 1.0e-5, (HCRegion<1> *)pool.data(), heap.data(), cap, val, err);
+     else st = hcubature_run<2>(f, 10000, 0.0, 1.0e-5, (HCRegion<2> *)pool.data(), heap.data(), cap, val, err); }
+  for (int j = 0; j < 33; j++) out36[j] = val[j];
+  for (int m = 0; m < 3; m++) out36[33 + m] = (OVa[0][m] + OVa[1][m] + OVa[2][m]) / 3.0;
+  (void)nregions;
+  return st;
+}

@@ -1,0 +1,67 @@
+"""Full BEM matrix parity against the UNMODIFIED reference (oracle/_ref) — relative Frobenius error per
+block <= 1e-10 (BASELINE.json north_star).  Here the FIPPI table is preloaded from the reference's own
+cache file (StoreCache -> PreloadCache round trip through the reference's binary format), so these
+tests pin everything that depends on frequency; tests/test_fippi_gpu.py pins the device FIPPI builder."""
+import os
+import numpy as np
+import pytest
+from conftest import GEODIR, ref_matrix
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+CASES = [("PECSphere_501", 1.0, False), ("PECSphere_501", 0.01, False), ("PECSphere_255", 0.1j, False),
+         ("PECSphere_255", 0.1j, True), ("SiO2Sphere_501", 1.0, False), ("SiSphere_255", 0.01, False),
+         ("PECSpheres_255", 0.1, False), ("SiSpheres_255", 0.1, False), ("LossySphere_327", 1.0, False),
+         ("PECSpheres_327", 1.0j, True), ("E10Spheres_327", 0.5j, False), ("GoldSphere_501", 0.3, False)]
+
+
+def block_errors(G, M, Mref):
+    errs = {}
+    offs = [G.surface(ns)["BFOffset"] for ns in range(G.NumSurfaces)] + [G.TotalBFs]
+    for a in range(G.NumSurfaces):
+        for b in range(G.NumSurfaces):
+            A = M[offs[a]:offs[a + 1], offs[b]:offs[b + 1]]
+            B = Mref[offs[a]:offs[a + 1], offs[b]:offs[b + 1]]
+            nb = np.linalg.norm(B)
+            errs[(a, b)] = np.linalg.norm(A - B) / nb if nb > 0 else np.linalg.norm(A)
+    return errs
+
+
+@pytest.mark.parametrize("name,omega,imag", CASES)
+def test_full_matrix(ps, name, omega, imag, tmp_path):
+    geo = os.path.join(GEODIR, name + ".scuffgeo")
+    cache = str(tmp_path / "ref.cache")
+    Mref, info = ref_matrix(geo, omega, imag=imag, cache_out=cache)
+    ps.PreloadCache(cache)
+    G = ps.RWGGeometry(geo)
+    Mh = G.AllocateBEMMatrix(imag)
+    assert Mh.is_real == bool(info["real"])
+    M = G.AssembleBEMMatrix(omega, M=Mh).array
+    errs = block_errors(G, M, Mref)
+    print(name, omega, "real" if imag else "complex", "block errs", {k: float("%.2e" % v) for k, v in errs.items()},
+          "counts", G.ppi_counts())
+    assert max(errs.values()) <= TOL
+    assert np.linalg.norm(M - Mref) / np.linalg.norm(Mref) <= TOL
+
+
+def test_lu_solve_downstream(ps, tmp_path):
+    """downstream consumer: on-device LU (cuSOLVER) of the assembled matrix vs numpy solve of the reference matrix"""
+    geo = os.path.join(GEODIR, "PECSphere_501.scuffgeo")
+    cache = str(tmp_path / "ref.cache")
+    Mref, _ = ref_matrix(geo, 1.0, cache_out=cache)
+    ps.PreloadCache(cache)
+    G = ps.RWGGeometry(geo)
+    Mh = G.AssembleBEMMatrix(1.0, to_host=False)
+    rng = np.random.default_rng(1)
+    rhs = rng.standard_normal(G.TotalBFs) + 1j * rng.standard_normal(G.TotalBFs)
+    X = ps.HMatrix.new(G.TotalBFs, 1, False)
+    import ctypes as C
+    host = ps.host_lib()
+    buf = (C.c_double * (2 * G.TotalBFs)).from_address(host.scuffb200_matrix_data(X.ptr))
+    np.frombuffer(buf, dtype=np.complex128)[:] = rhs
+    Mh.lu_factorize()
+    Mh.lu_solve(X)
+    x = X.array[:, 0]
+    xref = np.linalg.solve(Mref, rhs)
+    assert np.linalg.norm(x - xref) / np.linalg.norm(xref) <= 1e-8
