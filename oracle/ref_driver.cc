@@ -9,6 +9,10 @@
  *                     [--cache-in f] [--cache-out f] [--block nsa nsb]
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
+ *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n]
+ *        GetEdgeEdgeInteractions (EdgeEdgeInteractions.cc:50-217) on a seeded random sample of edge pairs
+ *        of surface 0 in the exterior medium (k=Omega): the per-element work of AssembleBEMMatrix on a
+ *        bounded sample of a large mesh.  out.bin: records {nea, neb, Re GC0, Im GC0, Re GC1, Im GC1}.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -129,6 +133,35 @@ int main(int argc, char **argv)
         fwrite(&QIFD,sizeof(double),36,fo); N++;
       }
      fclose(fi); fclose(fo); printf("{\"n\": %i}\n",N); return 0;
+   }
+
+  if(!strcmp(Cmd,"eeisample"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); long NPairs=atol(argv[5]); unsigned long long Seed=strtoull(argv[6],0,10);
+     const char *Out=argv[7]; int Repeat=1;
+     for(int n=8;n<argc;n++) if(!strcmp(argv[n],"--repeat")) Repeat=atoi(argv[++n]);
+     RWGSurface *S=G->Surfaces[0]; int NE=S->NumEdges;
+     int *ea=(int *)malloc(NPairs*sizeof(int)), *eb=(int *)malloc(NPairs*sizeof(int));
+     double *Rec=(double *)malloc(NPairs*6*sizeof(double));
+     unsigned long long x=Seed*2862933555777941757ULL+3037000493ULL;   // 64-bit LCG (Knuth MMIX constants below)
+     for(long n=0;n<NPairs;n++)
+      { x=x*6364136223846793005ULL+1442695040888963407ULL; ea[n]=(int)((x>>33)%(unsigned long long)NE);
+        x=x*6364136223846793005ULL+1442695040888963407ULL; eb[n]=(int)((x>>33)%(unsigned long long)NE); }
+     printf("{\"n\": %li, \"NE\": %i, \"threads\": %i, \"times\": [",NPairs,NE,omp_get_max_threads());
+     for(int r=0;r<Repeat;r++)
+      { double t0=Now();
+#pragma omp parallel for schedule(dynamic,256)
+        for(long n=0;n<NPairs;n++)
+         { GetEEIArgStruct Args; InitGetEEIArgs(&Args);
+           Args.Sa=S; Args.Sb=S; Args.nea=ea[n]; Args.neb=eb[n]; Args.k=Omega;
+           GetEdgeEdgeInteractions(&Args);
+           double *R=Rec+6*n; R[0]=ea[n]; R[1]=eb[n];
+           R[2]=real(Args.GC[0]); R[3]=imag(Args.GC[0]); R[4]=real(Args.GC[1]); R[5]=imag(Args.GC[1]);
+         }
+        printf("%s%.6f",r?", ":"",Now()-t0);
+      }
+     printf("]}\n");
+     FILE *f=fopen(Out,"wb"); if(!f) return 1;
+     fwrite(Rec,sizeof(double),6*NPairs,f); fclose(f); return 0;
    }
 
   fprintf(stderr,"unknown command %s\n",Cmd); return 2;

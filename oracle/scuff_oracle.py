@@ -1,0 +1,232 @@
+"""TEST INFRASTRUCTURE ONLY — CPU (numpy) restatement of the reference's far-field assembly path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` leg may import
+this module; the product (scuff-em_b200/) never does and fails loudly without its CUDA library.
+
+What is restated here (HomerReid/scuff-em, paths relative to the reference root), in the REFERENCE's
+own formulation (one PPI per (panel pair, Q, Q') — NOT the Q-independent moment formulation the CUDA
+kernels use, so that the two are independent derivations of the same numbers):
+
+  * AssessPanelPair's rRel / far test                libs/libscuff/AssessPanelPair.cc:147-172
+  * GetTCR(4) 6-point rule                           libs/libTriInt/TCR.cc:83-91
+  * GetPPIs_Cubature + AssembleInnerPPIIntegrand     libs/libscuff/PanelPanelInteractions.cc:108-201,211-350
+  * ExpRel                                           libs/libscuff/PanelPanelInteractions.cc:84-103
+  * GetEdgeEdgeInteractions                          libs/libscuff/EdgeEdgeInteractions.cc:154-188
+  * GSSIThread prefactors and stamping               libs/libscuff/SurfaceSurfaceInteractions.cc:165-176,203-327
+  * symmetric fill                                   libs/libscuff/AssembleBEMMatrix.cc:753-758
+
+Near / singular panel pairs (rRel <= 4: desingularisation + FIPPI, Taylor-Duffy) are NOT restated:
+for those the checker is the UNMODIFIED reference itself, compiled by oracle/Makefile into
+oracle/_ref (tests/conftest.py: ref_matrix).
+
+Pinning: tests/test_oracle.py checks this restatement against (a) the reference's own known-answer
+values for far panel pairs, unitTests/unit-test-PPIs.cc:70-79 (float precision, as the reference's
+EqualFloat does), and (b) golden PPI / matrix-entry vectors produced by oracle/_ref and committed
+under tests/golden/ by tests/golden/make_golden.py (<= 1e-13).
+"""
+import numpy as np
+
+# GetTCR(4): libs/libTriInt/TCR.cc:83-91 (13-digit literals; the numbers are the contract)
+TCR4 = np.array([[0.0915762135098, 0.0915762135098, 0.0549758718276],
+                 [0.8168475729805, 0.0915762135098, 0.0549758718276],
+                 [0.0915762135098, 0.8168475729805, 0.0549758718276],
+                 [0.1081030181681, 0.4459484909160, 0.1116907948390],
+                 [0.4459484909160, 0.1081030181681, 0.1116907948390],
+                 [0.4459484909160, 0.4459484909160, 0.1116907948390]])
+DESING_RADIUS = 4.0   # PanelPanelInteractions.cc:57
+
+
+def parse_geom_dump(fn):
+    """tests/golden/geom/*.geom.txt: the reference's own RWGGeometry dumped by oracle/_ref/ref_driver geom"""
+    S, hdr, regions = [], {}, []
+    for l in open(fn):
+        t = l.split()
+        if t[0] in ("NumSurfaces", "NumRegions", "TotalBFs", "LDim"):
+            hdr[t[0]] = int(t[1])
+        elif t[0] == "Region":
+            regions.append((t[2], t[3]))
+        elif t[0] == "Surface":
+            S.append(dict(Label=t[2], IsPEC=bool(int(t[4])), Regions=(int(t[6]), int(t[7])), BFOffset=int(t[9]),
+                          Mate=int(t[11]), NV=int(t[13]), NP=int(t[15]), NE=int(t[17]), NBF=int(t[19]), V=[], P=[], E=[]))
+        elif t[0] in "VPE":
+            S[-1][t[0]].append([float(x) for x in t[1:]])
+    for s in S:
+        V, P, E = np.array(s["V"]), np.array(s["P"]), np.array(s["E"])
+        s.update(V=V, PVI=P[:, :3].astype(int), PC=P[:, 3:6], PR=P[:, 6], PA=P[:, 7],
+                 ET=E[:, :8].astype(int), EL=E[:, 8])
+    return hdr, regions, S
+
+
+def exprel(x, n=4):
+    """ExpRel(x,n) with the reference's truncation (PanelPanelInteractions.cc:84-103); scalar complex x"""
+    term = 1.0 + 0j
+    m = 1
+    while m < n:
+        term *= x / m
+        m += 1
+    s = 0j
+    while m < 100:
+        term *= x / m
+        s += term
+        if abs(term) ** 2 < 1.0e-16 * abs(s) ** 2:   # reference compares norms squared (abs(Term) < 1e-8 abs(Sum))
+            break
+        m += 1
+    return s
+
+
+def ppi_cubature(Va, Qa, Vb, Qb, k, desingularize=False):
+    """GetPPIs_Cubature(order 4): H[0], H[1] of one (panel, Q ; panel', Q') pair.  Va, Vb: (3,3) vertices."""
+    ik = 1j * k
+    A, B = Va[1] - Va[0], Va[2] - Va[0]
+    AP, BP = Vb[1] - Vb[0], Vb[2] - Vb[0]
+    H = np.zeros(2, dtype=complex)
+    for (u, v, w) in TCR4:
+        X = Va[0] + u * A + v * B
+        F = X - Qa
+        HI = np.zeros(2, dtype=complex)
+        for (up, vp, wp) in TCR4:
+            XP = Vb[0] + up * AP + vp * BP
+            FP = XP - Qb
+            R = X - XP
+            hPlus = np.dot(F, FP) + 4.0 / (ik * ik)
+            FxFP = np.cross(F, FP)
+            r = np.sqrt(np.dot(R, R))
+            Phi = (exprel(ik * r, 4) if desingularize else np.exp(ik * r)) / (4.0 * np.pi * r)
+            if not np.isfinite(Phi.real):
+                Phi = 0.0
+            Phi *= wp
+            Psi = Phi * (ik - 1.0 / r) / r
+            HI[0] += hPlus * Phi
+            HI[1] += np.dot(FxFP, R) * Psi
+        H += w * HI
+    return H
+
+
+def rrel_matrix(Sa, Sb, displacement=None):
+    """rRel = |Ca - Cb (- L)| / max(Ra, Rb) for all panel pairs (AssessPanelPair.cc:161-166)"""
+    D = Sa["PC"][:, None, :] - Sb["PC"][None, :, :]
+    if displacement is not None:
+        D = D - np.asarray(displacement)[None, None, :]
+    r2 = (D[..., 0] * D[..., 0] + D[..., 1] * D[..., 1]) + D[..., 2] * D[..., 2]
+    return np.sqrt(r2) / np.maximum(Sa["PR"][:, None], Sb["PR"][None, :])
+
+
+def _panel_points(S):
+    """cubature points X[p, n, :] and weights of every panel, formed as GetPPIs_Cubature does"""
+    V0 = S["V"][S["PVI"][:, 0]]
+    A = S["V"][S["PVI"][:, 1]] - V0
+    B = S["V"][S["PVI"][:, 2]] - V0
+    X = V0[:, None, :] + TCR4[None, :, 0, None] * A[:, None, :] + TCR4[None, :, 1, None] * B[:, None, :]
+    return X, TCR4[:, 2]
+
+
+def far_ppis(Sa, Sb, k, displacement=None):
+    """H0[pa,pb,iQa,iQb], H1[...] for ALL panel pairs by 6x6 cubature (vectorised GetPPIs_Cubature),
+    plus the far mask rRel > 4.  Memory O(NPa*NPb*36): meant for meshes of a few hundred panels."""
+    ik = 1j * k
+    Xa, w = _panel_points(Sa)
+    Xb, _ = _panel_points(Sb)
+    if displacement is not None:
+        Xb = Xb + np.asarray(displacement)[None, None, :]
+    R = Xa[:, None, :, None, :] - Xb[None, :, None, :, :]            # (Pa,Pb,6,6,3)
+    r = np.sqrt(np.einsum("abpqm,abpqm->abpq", R, R))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Phi = np.exp(ik * r) / (4.0 * np.pi * r)
+        Phi = np.where(np.isfinite(Phi.real), Phi, 0.0)
+        ww = w[:, None] * w[None, :]
+        Phi = Phi * ww[None, None]
+        Psi = np.where(r > 0, Phi * (ik - 1.0 / r) / r, 0.0)
+    NPa, NPb = Xa.shape[0], Xb.shape[0]
+    H0 = np.zeros((NPa, NPb, 3, 3), dtype=complex)
+    H1 = np.zeros((NPa, NPb, 3, 3), dtype=complex)
+    Qa = Sa["V"][Sa["PVI"]]                                          # (Pa,3,3)
+    Qb = Sb["V"][Sb["PVI"]]
+    if displacement is not None:
+        Qb = Qb + np.asarray(displacement)[None, None, :]
+    for i in range(3):
+        F = Xa - Qa[:, i, None, :]                                   # (Pa,6,3)
+        for j in range(3):
+            FP = Xb - Qb[:, j, None, :]                              # (Pb,6,3)
+            hPlus = np.einsum("apm,bqm->abpq", F, FP) + 4.0 / (ik * ik)
+            FxFP = np.cross(F[:, None, :, None, :], FP[None, :, None, :, :])
+            hTimes = np.einsum("abpqm,abpqm->abpq", FxFP, R)
+            H0[:, :, i, j] = np.einsum("abpq,abpq->ab", hPlus, Phi)
+            H1[:, :, i, j] = np.einsum("abpq,abpq->ab", hTimes, Psi)
+    return H0, H1, rrel_matrix(Sa, Sb, displacement) > DESING_RADIUS
+
+
+def edge_edge_far(Sa, Sb, k, displacement=None):
+    """GC0[nea,neb], GC1[nea,neb] (EdgeEdgeInteractions.cc:154-188) using ONLY far panel pairs
+    (non-far PPIs contribute 0), and allfar[nea,neb] = all (up to 4) panel pairs of the edge pair are far."""
+    H0, H1, far = far_ppis(Sa, Sb, k, displacement)
+    H0 = np.where(far[:, :, None, None], H0, 0.0)
+    H1 = np.where(far[:, :, None, None], H1, 0.0)
+    Ea, Eb = Sa["ET"], Sb["ET"]
+    GC0 = np.zeros((len(Ea), len(Eb)), dtype=complex)
+    GC1 = np.zeros_like(GC0)
+    allfar = np.ones(GC0.shape, dtype=bool)
+    for (ca, ia, sa) in ((4, 6, +1.0), (5, 7, -1.0)):       # P panel (+), M panel (-)
+        pa, qa = Ea[:, ca], Ea[:, ia]
+        va = pa >= 0
+        for (cb, ib, sb) in ((4, 6, +1.0), (5, 7, -1.0)):
+            pb, qb = Eb[:, cb], Eb[:, ib]
+            vb = pb >= 0
+            m = va[:, None] & vb[None, :]
+            h0 = H0[np.where(va, pa, 0)[:, None], np.where(vb, pb, 0)[None, :], np.where(va, qa, 0)[:, None], np.where(vb, qb, 0)[None, :]]
+            h1 = H1[np.where(va, pa, 0)[:, None], np.where(vb, pb, 0)[None, :], np.where(va, qa, 0)[:, None], np.where(vb, qb, 0)[None, :]]
+            GC0 += np.where(m, sa * sb * h0, 0.0)
+            GC1 += np.where(m, sa * sb * h1, 0.0)
+            allfar &= np.where(m, far[np.where(va, pa, 0)[:, None], np.where(vb, pb, 0)[None, :]], True)
+    ll = Sa["EL"][:, None] * Sb["EL"][None, :]
+    return ll * GC0, ll * GC1 / (1j * k), allfar
+
+
+def csqrt2(z):
+    """libs/libhrutil/libhrutil.cc:692-699: square root with non-negative imaginary part"""
+    r = np.sqrt(complex(z))
+    return -r if r.imag < 0 else r
+
+
+def stamp_block(Sa, Sb, omega, eps, mu, sign, symmetric, displacement=None):
+    """One region's contribution to the (Sa,Sb) block using far panel pairs only (GSSIThread
+    SurfaceSurfaceInteractions.cc:165-176,203-266).  Returns (block, allfar_mask_on_BF_level)."""
+    k = csqrt2(eps * mu) * omega
+    GC0, GC1, allfar = edge_edge_far(Sa, Sb, k, displacement)
+    PreFac1 = sign * 1j * mu * omega
+    PreFac2 = -sign * 1j * k
+    PreFac3 = -sign * 1j * eps * omega
+    aP, bP = Sa["IsPEC"], Sb["IsPEC"]
+    NA, NB = len(Sa["ET"]), len(Sb["ET"])
+    if aP and bP:
+        B = PreFac1 * GC0
+        mask = allfar
+    elif aP and not bP:
+        B = np.zeros((NA, 2 * NB), dtype=complex)
+        B[:, 0::2] = PreFac1 * GC0
+        B[:, 1::2] = PreFac2 * GC1
+        mask = np.repeat(allfar, 2, axis=1)
+    elif not aP and bP:
+        B = np.zeros((2 * NA, NB), dtype=complex)
+        B[0::2, :] = PreFac1 * GC0
+        B[1::2, :] = PreFac2 * GC1
+        mask = np.repeat(allfar, 2, axis=0)
+    else:
+        B = np.zeros((2 * NA, 2 * NB), dtype=complex)
+        B[0::2, 0::2] = PreFac1 * GC0
+        B[0::2, 1::2] = PreFac2 * GC1
+        B[1::2, 0::2] = PreFac2 * GC1
+        B[1::2, 1::2] = PreFac3 * GC0
+        mask = np.kron(allfar, np.ones((2, 2), dtype=bool))
+    return B, mask
+
+
+def far_matrix_single_surface(S, omega, eps_out=1.0, mu_out=1.0, eps_in=None, mu_in=1.0):
+    """Far-pair-only BEM matrix of ONE closed surface: PEC (eps_in None) or PMCHWT dielectric
+    (exterior region + interior region, both sign +1 on the diagonal block,
+    CountCommonRegions SurfaceSurfaceInteractions.cc:62-90).  Equivalent to the CUDA path run with
+    scuffcuda_ssi_args.far_only = 1.  Returns (M, mask of entries whose panel pairs are ALL far)."""
+    M, mask = stamp_block(S, S, omega, eps_out, mu_out, +1.0, True)
+    if eps_in is not None and not S["IsPEC"]:
+        M2, _ = stamp_block(S, S, omega, eps_in, mu_in, +1.0, True)
+        M = M + M2
+    return M, mask

@@ -1,0 +1,79 @@
+"""Pins the CPU oracle (oracle/scuff_oracle.py, numpy restatement of the far-field path) against
+ (a) the reference's OWN known answers, unitTests/unit-test-PPIs.cc:70-79 (cases NCLW/NCMW/NCSW: panel pair (0,223)
+     of PECSphere_R0P75_414 — the no-common-vertex cases the 6x6 cubature serves), compared as the reference's
+     test compares them (EqualFloat: equal after rounding to float; we allow 2 float ulps), and
+ (b) golden vectors written by the UNMODIFIED reference (oracle/_ref) through tests/golden/make_golden.py."""
+import json
+import os
+import numpy as np
+import pytest
+from conftest import GOLDEN
+
+# unitTests/unit-test-PPIs.cc:70-79
+REF_KNOWN = {0.1: (-5.380869460e+00 - 7.929329541e-01j, -1.203784538e-04 - 1.244908468e-07j),
+             5.0: (-1.097563488e-03 - 1.833260738e-03j, -8.115226086e-04 + 3.380858352e-04j),
+             5.0 + 20.0j: (+4.102927698e-18 + 3.052119470e-17j, -5.053807314e-16 - 5.115425623e-16j)}
+
+
+def surf(oracle, name):
+    return oracle.parse_geom_dump(os.path.join(GOLDEN, "geom", name + ".geom.txt"))[2]
+
+
+def panel(S, np_):
+    return S["V"][S["PVI"][np_]]
+
+
+def test_reference_known_answers(oracle):
+    S = surf(oracle, "PECSphere_R0P75_414")[0]
+    assert oracle.rrel_matrix(S, S)[0, 223] > 4.0          # a far pair: PPIALG_LOCUBATURE
+    Va, Vb = panel(S, 0), panel(S, 223)
+    for k, exact in REF_KNOWN.items():
+        H = oracle.ppi_cubature(Va, Va[0], Vb, Vb[0], k)
+        for n in range(2):
+            for got, want in ((H[n].real, exact[n].real), (H[n].imag, exact[n].imag)):
+                assert abs(got - want) <= 3e-7 * abs(want) + 1e-30, (k, n, got, want)
+
+
+def test_ppis_vs_reference_golden(oracle):
+    g = json.load(open(os.path.join(GOLDEN, "ppi_golden.json")))
+    S = surf(oracle, g["geometry"])[0]
+    nfar = 0
+    for kk, rows in zip(g["k"], g["H"]):
+        k = complex(kk[0], kk[1])
+        for (nsa, npa, iQa, nsb, npb, iQb), r in zip(g["pairs"], rows):
+            if int(r[4]) != 0:      # only PPIALG_LOCUBATURE is restated in numpy; the rest is checked with oracle/_ref
+                continue
+            Va, Vb = panel(S, npa), panel(S, npb)
+            H = oracle.ppi_cubature(Va, Va[iQa], Vb, Vb[iQb], k)
+            ref = np.array([complex(r[0], r[1]), complex(r[2], r[3])])
+            assert np.all(np.abs(H - ref) <= 1e-13 * np.abs(ref) + 1e-300), (k, npa, npb, H, ref)
+            nfar += 1
+    assert nfar > 50
+
+
+def test_desingularised_integrand_is_consistent(oracle):
+    """ExpRel(x,4) = exp(x) - 1 - x - x^2/2 - x^3/6 to the reference's 1e-8 truncation"""
+    for x in (0.3j, 0.05 + 0.2j, -1.5, 2.0j):
+        want = np.exp(x) - 1 - x - x * x / 2 - x ** 3 / 6
+        assert abs(oracle.exprel(x, 4) - want) <= 1e-7 * abs(want)
+
+
+@pytest.mark.parametrize("name,omega,eps_in", [("PECSphere_255", 1.0, None), ("PECSphere_255", 0.1j, None),
+                                               ("PECSphere_501", 0.7 + 0.3j, None), ("SiSphere_255", 0.01, "golden")])
+def test_far_matrix_entries_vs_reference(oracle, name, omega, eps_in):
+    """all-far entries of the restated matrix == the reference's AssembleBEMMatrix entries (<= 1e-12)"""
+    Z = np.load(os.path.join(GOLDEN, "matrix_samples.npz"))
+    key = "%s@%r@0" % (name, complex(omega))
+    idx, val = Z[key + "/idx"], Z[key + "/val"]
+    S = surf(oracle, name)[0]
+    if eps_in == "golden":
+        eps_in = complex(*json.load(open(os.path.join(GOLDEN, "eps_golden.json")))["SiSphere_255@0.01"])
+    M, mask = oracle.far_matrix_single_surface(S, omega, eps_in=eps_in)
+    # reference fills nea<=neb and mirrors: compare on the upper triangle position of each sample
+    r, c = np.minimum(idx[:, 0], idx[:, 1]), np.maximum(idx[:, 0], idx[:, 1])
+    if not S["IsPEC"]:
+        r, c = idx[:, 0], idx[:, 1]
+    sel = mask[r, c]
+    assert sel.sum() > 1000
+    got, want = M[r, c][sel], val[sel]
+    assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
