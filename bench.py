@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: dense BEM system-matrix assembly (RWGGeometry::AssembleBEMMatrix) of a synthetic
+refined PEC sphere with N ~ 20k RWG edges at real frequency (BASELINE.json metric / configs[4]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--nu 26] [--omega 1.0]
+
+A "step" = one AssembleBEMMatrix(omega_j) of the whole N x N complex matrix at one frequency point of a sweep
+(omega_j = omega * (1 + 0.01 j)); with --gpus N the points of the sweep go round-robin over the ranks with no
+data-path collective (weak scaling: K points per rank).  Geometry and the frequency-independent FIPPI table are
+resident in HBM when the timed region starts (`value`); `e2e` is the same metric through the reference-facing
+call with HOST buffers: panels re-sent host->device and the assembled matrix copied back into the caller's
+HMatrix::ZM inside the timed region.
+
+--impl reference times the reference's own CPU implementation (oracle/_ref, the unmodified reference compiled by
+oracle/Makefile) with all host threads on a bounded, seeded random sample of the SAME workload's edge pairs
+(GetEdgeEdgeInteractions per matrix entry, ref_driver eeisample).
+"""
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "scuff-em_b200")
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+FLOP_PER_POINT_PAIR = 97          # one kernel evaluation at one cubature point pair
+POINT_PAIRS = 36                  # 6x6 rule
+METRIC = "bem_assembly_gelements_per_s"
+UNIT = "G-elements/s"
+
+
+def _load(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_mesh(nu, rank):
+    meshgen = _load("meshgen", os.path.join(PKG, "meshgen.py"))
+    d = os.path.join(tempfile.gettempdir(), "scuff_b200_bench_rank%d" % rank)
+    return meshgen.write_sphere_geo(d, nu)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([t.strip() for t in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def run_reference_sample(geo, omega, npairs, seed, repeat, out, sweep=False):
+    r = subprocess.run([REF_DRIVER, "eeisample", os.path.basename(geo), repr(omega.real), repr(omega.imag), str(npairs), str(seed), out,
+                        "--repeat", str(repeat)] + (["--sweep"] if sweep else []), cwd=os.path.dirname(geo), capture_output=True, text=True, check=True)
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def reference_arm(a, rank, world):
+    if rank != 0:
+        return 0
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+    if not os.path.exists(REF_DRIVER):
+        line["unavailable"] = "oracle/_ref/ref_driver not built (make -C oracle needs /root/reference)"
+        print(json.dumps(line))
+        return 0
+    geo = make_mesh(a.nu, 0)
+    omega = complex(a.omega)
+    npairs = a.ref_pairs
+    out = os.path.join(tempfile.gettempdir(), "scuff_ref_sample.bin")
+    # ONE process, W+K passes over the same seeded sample at the sweep's frequency points omega_j: pass 0 is cold
+    # (builds the reference's FIPPI cache), later passes are the warm steady state of a frequency sweep
+    info = run_reference_sample(geo, omega, npairs, 7, a.warmup + a.steps, out, sweep=True)
+    colds, times = info["times"][:1], info["times"][a.warmup:]
+    t = sum(times) / len(times)
+    # reference fills nea<=neb and mirrors (AssembleBEMMatrix.cc:753-758): one GetEdgeEdgeInteractions = 2 full-matrix entries
+    value = 2.0 * npairs / t / 1e9
+    N = 30 * a.nu * a.nu
+    line.update({"value": value, "ms_per_step": 1e3 * t,
+                 "config": {"workload": "icosphere PEC N=%d edges (nu=%d), omega=%g: AssembleBEMMatrix, complex128 %dx%d" % (N, a.nu, a.omega, N, N)},
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["threads"], "kind": "reference",
+                                  "sample": "%d seeded random edge pairs of the same mesh per step through the reference's GetEdgeEdgeInteractions "
+                                            "(OpenMP, warm FIPPI cache; cold first pass %.2f s vs warm %.2f s); full-matrix elements = 2 x unique "
+                                            "edge pairs (reference mirrors the upper triangle)" % (npairs, sum(colds) / len(colds), t),
+                                  "cold_value": 2.0 * npairs / (sum(colds) / len(colds)) / 1e9},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "extrapolated_full_matrix_s": N * (N + 1) / 2 / (npairs / t)})
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nu", type=int, default=26, help="icosphere frequency: 30 nu^2 RWG edges (26 -> 20280)")
+    ap.add_argument("--omega", type=float, default=1.0)
+    ap.add_argument("--ref-pairs", type=int, default=2000000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-lu", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.impl == "reference":
+        return reference_arm(a, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU reference)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ps = _load("pyscuff", os.path.join(PKG, "pyscuff.py"))
+    ps.set_device(local)
+    geo = make_mesh(a.nu, rank)
+    G = ps.RWGGeometry(geo)
+    N, P = G.TotalBFs, G.TotalPanels
+    M = G.AllocateBEMMatrix()
+    peak = ps.measure_fp64_peak()                      # in-run DFMA peak (MEASURED_PEAKS.json has no FP64 entry)
+
+    def omega_of(j):                                   # sweep point j -> rank j % world
+        return a.omega * (1.0 + 0.01 * j)
+
+    # cold pass: builds the frequency-independent FIPPI table on the device (kept resident for the sweep)
+    t0 = time.perf_counter()
+    G.AssembleBEMMatrix(omega_of(rank), M=M, to_host=False)
+    cold_s = time.perf_counter() - t0
+    cold_t = ps.last_timing()
+    for w in range(a.warmup):
+        G.AssembleBEMMatrix(omega_of(rank), M=M, to_host=False)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = ps.launch_count()
+    far_ms, near_ms, tot_ms = [], [], []
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        G.AssembleBEMMatrix(omega_of(rank + world * s), M=M, to_host=False)   # returns after the stream has drained
+        t = ps.last_timing()
+        tot_ms.append(t[0]); far_ms.append(t[1]); near_ms.append(t[2])
+    barrier()
+    elapsed = time.perf_counter() - t0
+    launches = ps.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        tt = torch.tensor([elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed = float(tt.item())
+    far_pairs, near_pairs = ps.pair_counts()
+    ppi_counts = G.ppi_counts()
+    value = world * a.steps * float(N) * N / elapsed / 1e9
+
+    # ---- end to end through the reference-facing call with host buffers ----
+    tb0 = ps.transfer_bytes()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(a.e2e_steps):
+        G.mark_geometry_dirty()                        # panels travel host->device again, as after a Transform()
+        G.AssembleBEMMatrix(omega_of(rank + world * s), M=M, to_host=True)    # fills the caller's HMatrix::ZM
+    barrier()
+    e2e_elapsed = time.perf_counter() - t0
+    tb1 = ps.transfer_bytes()
+    if world > 1:
+        tt = torch.tensor([e2e_elapsed], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_elapsed = float(tt.item())
+    e2e_value = world * a.e2e_steps * float(N) * N / e2e_elapsed / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    t_far = sum(far_ms) / len(far_ms) * 1e-3
+    flops = FLOP_PER_POINT_PAIR * POINT_PAIRS * float(far_pairs)
+    achieved = flops / t_far / 1e12
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "icosphere PEC N=%d edges (nu=%d, %d panels), omega=%g..: AssembleBEMMatrix, complex128 %dx%d (%.2f GB) resident in HBM"
+                                   % (N, a.nu, P, a.omega, N, N, 16.0 * N * N / 1e9),
+                       "sharding": "frequency points round-robin over ranks, no data-path collective" if world > 1 else "single GPU",
+                       "l2": "each step writes the %.1f GB matrix (>> 126 MB L2), no flush needed" % (16.0 * N * N / 1e9)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (tb1[0] - tb0[0]) // a.e2e_steps,
+                    "d2h_bytes_per_step": (tb1[1] - tb0[1]) // a.e2e_steps, "steps": a.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / a.e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "kernel": "far_kernel<KMODE_REAL>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak, "traffic": None,
+                         "algorithmic": "%d flop/point pair x %d point pairs x %d far panel pairs per launch" % (FLOP_PER_POINT_PAIR, POINT_PAIRS, far_pairs),
+                         "kernel_ms": 1e3 * t_far,
+                         "peak_source": "in-run DFMA microkernel (scuffcuda_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry"},
+            "breakdown_ms": {"total_device": sum(tot_ms) / len(tot_ms), "far_kernel": 1e3 * t_far, "near_singular": sum(near_ms) / len(near_ms),
+                             "cold_first_assembly_s": cold_s, "cold_fippi_build_ms": cold_t[3]},
+            "pairs": {"far": int(far_pairs), "near": int(near_pairs), "reference_ppi_counts": [int(c) for c in ppi_counts]},
+            "clocks": clocks}
+    hbm = None
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    line["store_phase"] = {"bytes": 16.0 * N * N, "min_ms_at_measured_hbm": (16.0 * N * N / (hbm * 1e9) * 1e3) if hbm else None,
+                           "hbm_gbs": hbm, "source": "measured" if hbm else "absent"}
+
+    # ---- downstream consumer (timed separately, not the optimisation target): on-device LU + solve ----
+    if not a.no_lu and world == 1:
+        try:
+            X = ps.HMatrix.new(N, 1, False)
+            t0 = time.perf_counter(); M.lu_factorize(); t_lu = time.perf_counter() - t0
+            t0 = time.perf_counter(); M.lu_solve(X); t_sv = time.perf_counter() - t0
+            line["lu"] = {"factor_s": t_lu, "solve_s": t_sv, "omega_points_per_s": 1.0 / (elapsed / a.steps + t_lu + t_sv)}
+        except Exception as e:  # noqa
+            line["lu"] = {"error": str(e)[:200]}
+
+    # ---- CPU baseline beside it + full-size parity on the sampled entries ----
+    if world == 1 and not a.no_cpu_baseline and os.path.exists(REF_DRIVER):
+        out = os.path.join(tempfile.gettempdir(), "scuff_ref_sample_rank0.bin")
+        info = run_reference_sample(geo, complex(a.omega), a.ref_pairs, 7, 2, out)
+        rec = np.fromfile(out).reshape(-1, 6)
+        warm = info["times"][1]
+        line["cpu_baseline"] = {"value": 2.0 * a.ref_pairs / warm / 1e9, "unit": UNIT, "cores": info["threads"], "kind": "reference",
+                                "sample": "%d seeded random edge pairs of the same mesh through the reference's GetEdgeEdgeInteractions (OpenMP, "
+                                          "warm FIPPI cache %.2f s; cold pass %.2f s); full-matrix elements = 2 x unique edge pairs"
+                                          % (a.ref_pairs, warm, info["times"][0])}
+        # parity at full size: M[nea,neb] = i*omega*GC0 (PEC in vacuum, SurfaceSurfaceInteractions.cc:165-176,205-217)
+        G.AssembleBEMMatrix(a.omega, M=M, to_host=False)
+        import ctypes as C
+        dptr = C.c_void_p()
+        ps.cuda_lib().scuffcuda_matrix_device_ptr(ps.context(), M.device_handle, C.byref(dptr))
+
+        class _Arr:  # zero-copy view of the resident matrix for indexing the sampled entries
+            __cuda_array_interface__ = {"shape": (N * N * 2,), "typestr": "<f8", "data": (dptr.value, False), "version": 2}
+        flat = torch.as_tensor(_Arr(), device="cuda")
+        ea = torch.as_tensor(rec[:, 0].astype(np.int64), device="cuda"); eb = torch.as_tensor(rec[:, 1].astype(np.int64), device="cuda")
+        idx = 2 * (ea + eb * N)
+        got = (flat[idx] + 1j * flat[idx + 1]).cpu().numpy()
+        want = 1j * a.omega * (rec[:, 2] + 1j * rec[:, 3])
+        line["parity_full_size"] = {"entries": int(len(want)), "rel_err": float(np.linalg.norm(got - want) / np.linalg.norm(want)),
+                                    "max_abs_err": float(np.abs(got - want).max()), "max_abs": float(np.abs(want).max())}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -86,6 +86,7 @@ class HMatrix
    cdouble *ZM;
    bool ownsM;
    char *ErrMsg;
+   bool Pinned;               /* DM/ZM is page-locked memory from scuffcuda_host_alloc        */
  };
 
 /*--------------------------------------------------------------------------------------*/

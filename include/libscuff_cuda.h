@@ -15,6 +15,7 @@
 #ifndef LIBSCUFF_CUDA_H
 #define LIBSCUFF_CUDA_H
 
+#include <stddef.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -103,6 +104,18 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb,
  * [0] low-order cubature, [1] high-order cubature, [2] Taylor-Duffy, [3] high-k TD,
  * [4] desingularised; counted per (panel pair, Q pair) PPI the reference would evaluate */
 int scuffcuda_get_ppi_counts(scuffcuda_context *ctx, unsigned long long counts[5]);
+
+/* panel pairs of the last assemble_block call: [0] far pairs integrated by the far-field kernel (each ONCE, for
+ * all its (Q,Q') combinations), [1] near/singular pairs (rRel <= 4)                                        */
+int scuffcuda_get_pair_counts(scuffcuda_context *ctx, unsigned long long counts[2]);
+/* bookkeeping for measurement: CUDA kernels launched by this context since creation, and bytes this
+ * context copied host->device [0] / device->host [1] since creation                                       */
+int scuffcuda_get_launch_count(scuffcuda_context *ctx, unsigned long long *n);
+int scuffcuda_get_transfer_bytes(scuffcuda_context *ctx, unsigned long long bytes[2]);
+/* pinned (page-locked, zero-filled) host memory for HMatrix::ZM/DM (libs/libhmat/HMatrix.cc:325-360 allocates
+ * with mallocEC) so that the copy-back of an assembled matrix runs at full PCIe rate                       */
+int scuffcuda_host_alloc(scuffcuda_context *ctx, size_t bytes, void **ptr);
+int scuffcuda_host_free(scuffcuda_context *ctx, void *ptr);
 
 /* device time (ms, CUDA events on the context's stream) of the kernels of the last
  * assemble_block call: [0] total, [1] far-field kernel, [2] near/singular kernels,

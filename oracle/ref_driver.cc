@@ -9,7 +9,7 @@
  *                     [--cache-in f] [--cache-out f] [--block nsa nsb]
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
- *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n]
+ *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
  *        GetEdgeEdgeInteractions (EdgeEdgeInteractions.cc:50-217) on a seeded random sample of edge pairs
  *        of surface 0 in the exterior medium (k=Omega): the per-element work of AssembleBEMMatrix on a
  *        bounded sample of a large mesh.  out.bin: records {nea, neb, Re GC0, Im GC0, Re GC1, Im GC1}.
@@ -138,7 +138,10 @@ int main(int argc, char **argv)
   if(!strcmp(Cmd,"eeisample"))
    { cdouble Omega(atof(argv[3]),atof(argv[4])); long NPairs=atol(argv[5]); unsigned long long Seed=strtoull(argv[6],0,10);
      const char *Out=argv[7]; int Repeat=1;
-     for(int n=8;n<argc;n++) if(!strcmp(argv[n],"--repeat")) Repeat=atoi(argv[++n]);
+     bool Sweep=false;   // --sweep: pass r runs at Omega*(1+0.01 r), the frequency points of a sweep (FIPPI cache stays warm)
+     for(int n=8;n<argc;n++)
+      { if(!strcmp(argv[n],"--repeat")) Repeat=atoi(argv[++n]);
+        else if(!strcmp(argv[n],"--sweep")) Sweep=true; }
      RWGSurface *S=G->Surfaces[0]; int NE=S->NumEdges;
      int *ea=(int *)malloc(NPairs*sizeof(int)), *eb=(int *)malloc(NPairs*sizeof(int));
      double *Rec=(double *)malloc(NPairs*6*sizeof(double));
@@ -148,11 +151,12 @@ int main(int argc, char **argv)
         x=x*6364136223846793005ULL+1442695040888963407ULL; eb[n]=(int)((x>>33)%(unsigned long long)NE); }
      printf("{\"n\": %li, \"NE\": %i, \"threads\": %i, \"times\": [",NPairs,NE,omp_get_max_threads());
      for(int r=0;r<Repeat;r++)
-      { double t0=Now();
+      { cdouble OmegaR = Sweep ? Omega*(1.0+0.01*r) : Omega;
+        double t0=Now();
 #pragma omp parallel for schedule(dynamic,256)
         for(long n=0;n<NPairs;n++)
          { GetEEIArgStruct Args; InitGetEEIArgs(&Args);
-           Args.Sa=S; Args.Sb=S; Args.nea=ea[n]; Args.neb=eb[n]; Args.k=Omega;
+           Args.Sa=S; Args.Sb=S; Args.nea=ea[n]; Args.neb=eb[n]; Args.k=OmegaR;
            GetEdgeEdgeInteractions(&Args);
            double *R=Rec+6*n; R[0]=ea[n]; R[1]=eb[n];
            R[2]=real(Args.GC[0]); R[3]=imag(Args.GC[0]); R[4]=real(Args.GC[1]); R[5]=imag(Args.GC[1]);

@@ -103,6 +103,9 @@ struct scuffcuda_context
   std::vector<scuffcuda::Plan> plans;
   scuffcuda::FIPPITable fippi;
   unsigned long long counts[5] = {0, 0, 0, 0, 0};
+  unsigned long long pairCounts[2] = {0, 0};  // far / near panel pairs of the last assemble_block call
+  unsigned long long launches = 0;            // kernels launched by this context since creation
+  unsigned long long h2dBytes = 0, d2hBytes = 0;
   double timing[5] = {0, 0, 0, 0, 0};
   unsigned long long *dcounters = nullptr;   // device counters (near-list length, algorithm counts)
   void *dscratch = nullptr; size_t scratchBytes = 0;

@@ -51,7 +51,7 @@ far_kernel(const FarArgs A)
   for (int i = 0; i < 3; i++) { slb[i] = Pb->sl[i]; eib[i] = Pb->ei[i]; }
 
   typedef typename KScalar<KMODE>::type S;
-  unsigned long long nPPI = 0;
+  unsigned long long nPPI = 0; unsigned int nPairs = 0;
 
   for (int ia = 0; ia < nA; ia++)
    { const int pa = a0 + ia;
@@ -61,6 +61,7 @@ far_kernel(const FarArgs A)
      const double rRel = pair_rrel(Pa, Pa[3], Cb, Rb, A.useDisp != 0, A.L, D);
      if (!(rRel > SCUFF_DESING_RADIUS)) continue;
 
+     nPairs++;
      Moments<S> M;
      panel_pair_moments<KMODE, false>(Pa + 13, xb, D, A.K, M);
 
@@ -83,6 +84,7 @@ far_kernel(const FarArgs A)
    }
   // algorithm counter (reference log line SurfaceSurfaceInteractions.cc:550-558)
   if (nPPI) atomicAdd(A.counters, nPPI);
+  if (nPairs) atomicAdd(A.counters + 5, (unsigned long long)nPairs);
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
@@ -94,6 +96,7 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   A.TA = TA;
   dim3 grid(bTiles, (A.NPa + TA - 1) / TA);
   size_t smem = (size_t)TA * sizeof(PanelRec);
+  ctx->launches++;
   if (kmode == KMODE_REAL) far_kernel<KMODE_REAL><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
   else if (kmode == KMODE_IMAG) far_kernel<KMODE_IMAG><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
   else far_kernel<KMODE_CPLX><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);

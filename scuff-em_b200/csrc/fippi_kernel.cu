@@ -90,6 +90,7 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
      for (size_t first = 0; first < todo.size(); first += batch)
       { int m = (int)std::min((size_t)batch, todo.size() - first);
         cudaMemcpyAsync(ditems, todo.data() + first, m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        ctx->launches++;
         fippi_build_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>(T, dverts, dncv, ditems, m, dpool, cap, dout, dstatus);
         cudaMemcpyAsync(st.data(), dstatus, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);

@@ -54,15 +54,18 @@ void launch_zero_block(scuffcuda_context *ctx, const Matrix &M, int rowOff, int 
   int w = M.isReal ? 1 : 2;
   if (rowOff == 0 && colOff == 0 && nRows == M.NR && nCols == M.NC)
    { cudaMemsetAsync(M.d, 0, (size_t)M.NR * M.NC * w * sizeof(double), ctx->stream); return; }
+  ctx->launches++;
   zero_block_kernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(M.d, M.NR, w, rowOff, nRows, colOff, nCols);
 }
 void launch_copy_block(scuffcuda_context *ctx, const Matrix &M, int dstRow, int dstCol, int nRows, int nCols, int srcRow, int srcCol)
 { if (nRows <= 0 || nCols <= 0) return;
+  ctx->launches++;
   copy_block_kernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(M.d, M.NR, M.isReal ? 1 : 2, dstRow, dstCol, nRows, nCols, srcRow, srcCol);
 }
 void launch_symmetrize(scuffcuda_context *ctx, const Matrix &M, int off, int n)
 { if (n <= 1) return;
   int t = (n + 31) / 32; dim3 grid(t, t), block(32, 8);
+  ctx->launches++;
   if (M.isReal) symmetrize_kernel<1><<<grid, block, 0, ctx->stream>>>(M.d, M.NR, off, n);
   else symmetrize_kernel<2><<<grid, block, 0, ctx->stream>>>(M.d, M.NR, off, n);
 }

@@ -210,6 +210,7 @@ static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, 
   for (int attempt = 0; attempt < 2; attempt++)
    { if (cudaMalloc(&dlist, cap * sizeof(int2)) != cudaSuccess) { status = failc(ctx, "near list alloc", cudaGetLastError()); return nullptr; }
      cudaMemsetAsync(dcount, 0, sizeof(unsigned long long), ctx->stream);
+     ctx->launches++;
      near_list_kernel<<<grid, NEAR_THREADS, TA * 4 * sizeof(double), ctx->stream>>>(Sa.dpanels, Sa.NP, Sb.dpanels, Sb.NP, TA, symmetric ? 1 : 0,
                                                                                     useDisp ? 1 : 0, P.L[0], P.L[1], P.L[2], dlist, dcount, cap);
      cudaMemcpyAsync(&count, dcount, sizeof count, cudaMemcpyDeviceToHost, ctx->stream);
@@ -228,6 +229,7 @@ static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, 
      float *dkeys = nullptr;
      if (cudaMalloc(&P.dnear, count * sizeof(NearPair)) != cudaSuccess || cudaMalloc(&dkeys, 2 * count * 15 * sizeof(float)) != cudaSuccess)
       { status = failc(ctx, "near plan alloc", cudaGetLastError()); cudaFree(dlist); return nullptr; }
+     ctx->launches++;
      near_assess_kernel<<<(unsigned)((count + 127) / 128), 128, 0, ctx->stream>>>(Sa.dpanels, Sb.dpanels, dlist, (int)count, useDisp ? 1 : 0,
                                                                                   P.L[0], P.L[1], P.L[2], symmetric ? 1 : 0, P.dnear, dkeys, dkeys + count * 15);
      P.hnear.resize(count);
@@ -300,11 +302,14 @@ int run_near(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args 
   Plan *P = get_plan(ctx, nsa, nsb, a->symmetric != 0, a->use_displacement != 0, L, status);
   if (!P) return status ? status : 1;
   if (P->nNear == 0) return 0;
+  { unsigned long long nn = (unsigned long long)P->nNear;
+    cudaMemcpyAsync(ctx->dcounters + 6, &nn, sizeof nn, cudaMemcpyHostToDevice, ctx->stream); cudaStreamSynchronize(ctx->stream); }
   NearArgs A;
   A.pa = ctx->surfaces[nsa].dpanels; A.pb = ctx->surfaces[nsb].dpanels; A.near = P->dnear; A.nNear = P->nNear;
   A.useDisp = a->use_displacement ? 1 : 0; for (int i = 0; i < 3; i++) A.L[i] = A.useDisp ? L[i] : 0.0;
   A.forceTD = a->force_taylor_duffy ? 1 : 0; A.kabs = kabs; A.fippi = ctx->fippi.drec;
   A.K = K; A.S = SP; A.counters = ctx->dcounters;
+  ctx->launches++;
   near_desing_kernel<<<(P->nNear + NEAR_THREADS - 1) / NEAR_THREADS, NEAR_THREADS, 0, ctx->stream>>>(A);
   CKN(cudaGetLastError());
   return run_td(ctx, *P, A, kmode);

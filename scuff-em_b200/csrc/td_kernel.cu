@@ -83,6 +83,7 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
   for (int first = 0; first < total; first += batch)
    { int n = std::min(batch, total - first);
      // grid covers exactly `batch` threads so that the scratch stride is fixed
+     ctx->launches++;
      td_ct_kernel<<<batch / 64, 64, 0, ctx->stream>>>(A, T, dIdx, first, n, scr, dStatus);
    }
   int st = 0;

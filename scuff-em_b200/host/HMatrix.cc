@@ -8,14 +8,19 @@ namespace scuff {
 
 HMatrix::HMatrix(int NRows, int NCols, int pRealComplex, int pStorageType, void *data)
 { NR = NRows; NC = NCols; RealComplex = pRealComplex; StorageType = pStorageType;
-  ipiv = 0; DM = 0; ZM = 0; ErrMsg = 0; DeviceHandle = 0; HostStale = false;
+  ipiv = 0; DM = 0; ZM = 0; ErrMsg = 0; DeviceHandle = 0; HostStale = false; Pinned = false;
   if (StorageType != LHM_NORMAL)
    ErrExit("HMatrix: packed storage is not supported by the device assembly path");
   size_t n = (size_t)NR * NC;
   if (data) { ownsM = false; if (RealComplex == LHM_REAL) DM = (double *)data; else ZM = (cdouble *)data; }
   else
    { ownsM = true;
-     if (RealComplex == LHM_REAL) DM = (double *)calloc(n, sizeof(double));
+     // large matrices come back from HBM over PCIe: page-locked host memory when a device is present
+     size_t bytes = n * (RealComplex == LHM_REAL ? sizeof(double) : sizeof(cdouble));
+     void *p = 0;
+     if (bytes >= ((size_t)32 << 20) && scuffcuda_device_count() > 0 && scuffcuda_host_alloc(GetCudaContext(), bytes, &p) == 0 && p)
+      { Pinned = true; if (RealComplex == LHM_REAL) DM = (double *)p; else ZM = (cdouble *)p; }
+     else if (RealComplex == LHM_REAL) DM = (double *)calloc(n, sizeof(double));
      else ZM = (cdouble *)calloc(n, sizeof(cdouble));
      if (!DM && !ZM) ErrMsg = strdup("out of memory");
    }
@@ -23,7 +28,8 @@ HMatrix::HMatrix(int NRows, int NCols, int pRealComplex, int pStorageType, void 
 
 HMatrix::~HMatrix()
 { if (DeviceHandle) scuffcuda_matrix_destroy(GetCudaContext(), DeviceHandle);
-  if (ownsM) { if (DM) free(DM); if (ZM) free(ZM); }
+  if (ownsM && Pinned) scuffcuda_host_free(GetCudaContext(), DM ? (void *)DM : (void *)ZM);
+  else if (ownsM) { if (DM) free(DM); if (ZM) free(ZM); }
   if (ipiv) free(ipiv);
 }
 

@@ -54,6 +54,8 @@ int scuffb200_eps_mu(void *g, double wr, double wi, double *out)
         return 0;, 1) }
 int scuffb200_transform(void *g, const char *line) { GUARD(((RWGGeometry *)g)->Transform(line); return 0;, 1) }
 int scuffb200_untransform(void *g) { GUARD(((RWGGeometry *)g)->UnTransform(); return 0;, 1) }
+// marks every surface as moved (what Transform()/UnTransform() do): the next assembly re-sends the panels to the device
+int scuffb200_mark_geometry_dirty(void *g) { RWGGeometry *G = (RWGGeometry *)g; G->DeviceDirty.assign(G->NumSurfaces, 1); return 0; }
 int scuffb200_zero_region(void *g, int nr, int zero)
 { RWGGeometry *G = (RWGGeometry *)g; if (nr < 0 || nr >= G->NumRegions) return 1;
   if (zero) G->RegionMPs[nr]->Zero(); else G->RegionMPs[nr]->UnZero(); return 0; }

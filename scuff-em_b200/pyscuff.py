@@ -67,6 +67,11 @@ def cuda_lib():
         L.scuffcuda_fippi_store.argtypes = [C.c_void_p, C.c_char_p]
         L.scuffcuda_fippi_num_records.argtypes = [C.c_void_p, C.POINTER(C.c_long)]
         L.scuffcuda_fippi_clear.argtypes = [C.c_void_p]
+        L.scuffcuda_get_pair_counts.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        L.scuffcuda_get_launch_count.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        L.scuffcuda_get_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        L.scuffcuda_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
+        L.scuffcuda_host_free.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffcuda_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _cuda = L
     return _cuda
@@ -224,6 +229,9 @@ class RWGGeometry:
     def untransform(self):
         _check(host_lib().scuffb200_untransform(self.ptr))
 
+    def mark_geometry_dirty(self):
+        host_lib().scuffb200_mark_geometry_dirty(C.c_void_p(self.ptr))
+
     def zero_region(self, nr, zero=True):
         _check(host_lib().scuffb200_zero_region(self.ptr, nr, int(zero)))
 
@@ -285,6 +293,24 @@ def last_timing():
     t = (C.c_double * 5)()
     cuda_lib().scuffcuda_get_last_timing(context(), t)
     return list(t)
+
+
+def pair_counts():
+    c = (C.c_ulonglong * 2)()
+    cuda_lib().scuffcuda_get_pair_counts(context(), c)
+    return list(c)
+
+
+def launch_count():
+    n = C.c_ulonglong()
+    cuda_lib().scuffcuda_get_launch_count(context(), C.byref(n))
+    return n.value
+
+
+def transfer_bytes():
+    b = (C.c_ulonglong * 2)()
+    cuda_lib().scuffcuda_get_transfer_bytes(context(), b)
+    return list(b)
 
 
 def measure_fp64_peak():
