@@ -131,6 +131,10 @@ int scuffcuda_fippi_num_records(scuffcuda_context *ctx, long *n);
 /* drop every record (and the pair plans that index them); next assembly rebuilds the table on the device */
 int scuffcuda_fippi_clear(scuffcuda_context *ctx);
 
+/* ---- self-test of the kernels' FP64 elementary functions (csrc/fastmath.cuh): for each x[i] writes
+ *      out[6i..] = { rsqrt(|x|), rsqrt one-step variant, sin x, cos x, exp(-|x|), 0 }; host buffers          */
+int scuffcuda_selftest_math(scuffcuda_context *ctx, int n, const double *x, double *out);
+
 /* ---- measurement helpers ------------------------------------------------------------ */
 /* dependent-chain-free DFMA microkernel: returns achieved FP64 TFLOP/s (2 flop per FMA);
  * used as the in-run FP64 roofline denominator (MEASURED_PEAKS.json has no FP64 entry) */

@@ -291,6 +291,16 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      SP.c2 = mk(real(PreFac2), imag(PreFac2));
      SP.c3 = mk(real(PreFac3), imag(PreFac3));
      int kmode = (imag(k) == 0.0) ? KMODE_REAL : ((real(k) == 0.0) ? KMODE_IMAG : KMODE_CPLX);
+     { // the FP64 sincos range reduction of the far kernel is exact for |Re k| * distance < 1e5
+       double ext = 0.0;
+       for (const Surface *S : { &Sa, &Sb })
+        for (const PanelRec &P : S->hpanels)
+         ext = std::max(ext, std::sqrt(P.C[0] * P.C[0] + P.C[1] * P.C[1] + P.C[2] * P.C[2]) + P.R);
+       ext = 2.0 * ext + (a->use_displacement ? std::sqrt(a->displacement[0] * a->displacement[0] + a->displacement[1] * a->displacement[1]
+                                                          + a->displacement[2] * a->displacement[2]) : 0.0);
+       if (std::fabs(real(k)) * ext >= SCUFF_MAX_KR)
+        return fail(ctx, "assemble_block: |Re k| * geometry extent = %g exceeds the supported range %g", std::fabs(real(k)) * ext, SCUFF_MAX_KR);
+     }
 
      FarArgs F;
      F.pa = Sa.dpanels; F.NPa = Sa.NP; F.pb = Sb.dpanels; F.NPb = Sb.NP; F.TA = 32;
@@ -338,6 +348,9 @@ int scuffcuda_host_alloc(scuffcuda_context *ctx, size_t bytes, void **p)
 { CK(cudaSetDevice(ctx->device)); CK(cudaHostAlloc(p, bytes, cudaHostAllocDefault)); memset(*p, 0, bytes); return 0; }
 int scuffcuda_host_free(scuffcuda_context *ctx, void *p)
 { CK(cudaSetDevice(ctx->device)); CK(cudaFreeHost(p)); return 0; }
+
+int scuffcuda_selftest_math(scuffcuda_context *ctx, int n, const double *x, double *out)
+{ CK(cudaSetDevice(ctx->device)); return run_fastmath_selftest(ctx, n, x, out); }
 
 int scuffcuda_measure_fp64_peak(scuffcuda_context *ctx, double *tflops)
 { CK(cudaSetDevice(ctx->device)); *tflops = run_fp64_peak(ctx); CK(cudaGetLastError()); return 0; }

@@ -1,24 +1,127 @@
-// Far-field panel-pair kernel: every panel pair with rRel > 4 (the reference's
-// PPIALG_LOCUBATURE branch, PanelPanelInteractions.cc:420-424) is integrated ONCE with the 6x6
-// order-4 rule into Q-independent moments (ppi_math.cuh) and scattered, with RWG signs and edge
-// lengths, into the up-to-nine edge-pair entries it feeds (stamp.cuh).
+// Far-field panel-pair kernel: every panel pair with rRel > 4 (the reference's PPIALG_LOCUBATURE branch,
+// PanelPanelInteractions.cc:420-424) is integrated ONCE with the 6x6 order-4 rule and scattered, with RWG signs and
+// edge lengths, into the up-to-nine edge-pair entries it feeds (the reference re-evaluates the same panel pair for
+// every (Q,Q') combination and every edge pair: 4.5-9x redundant).
 //
-// Mapping: one thread per panel pair.  A CTA owns a tile of TA a-panels (staged in shared memory,
-// broadcast reads) x 128 b-panels (one per lane, kept in registers for the whole tile).
-// FP64 DFMA-bound; panel data is 288 B per panel and is read once per tile.
+// Formulation.  With X = V0 + u A + v B (A = V1-V0, B = V2-V0) the RWG factor of vertex i is
+//     X - V_i = (u - [i==1]) A + (v - [i==2]) B ,
+// so all nine (Q_a,Q_b) combinations of a panel pair follow from the 3x3 barycentric moments
+//     MPhi[m][n] = sum_{p,p'} w_p w_p' {1,u,v}_m {1,u',v'}_n Phi(r_pp') ,   MPsi likewise with Psi:
+//     H0_ij = sum_{X in {A,B}, Y in {A',B'}} (X.Y) <(x-d_i)(y-d_j) Phi> + 4/(ik)^2 <Phi>
+//     H1_ij = sum_{X,Y} ((X x Y).E_ij) <(x-d_i)(y-d_j) Psi> ,   E_ij = V_i - V'_j (- L)
+// (identical, term by term, to GetPPIs_Cubature's  (F.F' + 4/(ik)^2) Phi  and  ((F x F').R) Psi  because
+// (F x F').R = (F x F').(R - F + F') and R - F + F' = V_i - V'_j.)  The inner loop per point pair is: R, r^2,
+// 1/r (MUFU seed + FP64 Newton), sincos / exp with FP64 range reduction (fastmath.cuh), Phi (and Psi), and three
+// complex accumulations whose multipliers u', v' are immediates.  PEC/PEC blocks need only H0 (the stamp uses GC[0]
+// only, SurfaceSurfaceInteractions.cc:205-217), so the Psi half is compiled out (template PSI=false).
+//
+// Mapping: one thread per panel pair.  A CTA owns a tile of TA a-panels — brought into shared memory with ONE 1-D TMA
+// bulk copy (cp.async.bulk + mbarrier; a tile of PanelRec is contiguous) and read by broadcast — x 128 b-panels, one
+// per lane, whose cubature points stay in registers for the whole tile.  FP64-pipe bound.
+#include <stdint.h>
 #include "context.h"
 #include "classify.cuh"
 #include "stamp.cuh"
 #include "kernels.h"
+#include "fastmath.cuh"
 
 namespace scuffcuda {
 
 #define FAR_THREADS 128
 
-template <int KMODE>
-__global__ void __launch_bounds__(FAR_THREADS)
+// w_p * {1, u_p, v_p} of the 6-point rule (TCR.cc:83-91 literals)
+__constant__ double c_far_wm[6][3] = {
+  { 0.0549758718276, 0.0549758718276 * 0.0915762135098, 0.0549758718276 * 0.0915762135098 },
+  { 0.0549758718276, 0.0549758718276 * 0.8168475729805, 0.0549758718276 * 0.0915762135098 },
+  { 0.0549758718276, 0.0549758718276 * 0.0915762135098, 0.0549758718276 * 0.8168475729805 },
+  { 0.1116907948390, 0.1116907948390 * 0.1081030181681, 0.1116907948390 * 0.4459484909160 },
+  { 0.1116907948390, 0.1116907948390 * 0.4459484909160, 0.1116907948390 * 0.1081030181681 },
+  { 0.1116907948390, 0.1116907948390 * 0.4459484909160, 0.1116907948390 * 0.4459484909160 } };
+
+__device__ __forceinline__ constexpr double tcr_u(int p)
+{ return p == 1 ? 0.8168475729805 : (p == 0 || p == 2) ? 0.0915762135098 : (p == 3) ? 0.1081030181681 : 0.4459484909160; }
+__device__ __forceinline__ constexpr double tcr_v(int p)
+{ return p == 2 ? 0.8168475729805 : (p == 0 || p == 1) ? 0.0915762135098 : (p == 4) ? 0.1081030181681 : 0.4459484909160; }
+__device__ __forceinline__ constexpr double tcr_w(int p) { return p < 3 ? 0.0549758718276 : 0.1116907948390; }
+
+// Phi * w' (and Psi * w') at one point pair; cw = w'/(4 pi)
+template <int KMODE, bool PSI, typename S>
+__device__ __forceinline__ void helm_fast(double r2, double cw, const KParams &K, S &Phi, S &Psi);
+
+template <>
+__device__ __forceinline__ void helm_fast<KMODE_REAL, false, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
+{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+  double s, c; sincos_fast(K.kr * r, s, c);
+  const double f = cw * rinv;
+  Phi = mk(f * c, f * s);
+}
+template <>
+__device__ __forceinline__ void helm_fast<KMODE_REAL, true, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
+{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+  double s, c; sincos_fast(K.kr * r, s, c);
+  const double f = cw * rinv;
+  Phi = mk(f * c, f * s);
+  const double a = -rinv * rinv, b = K.kr * rinv;          // Psi = Phi (ik - 1/r)/r
+  Psi = mk(fma(Phi.x, a, -Phi.y * b), fma(Phi.x, b, Phi.y * a));
+}
+template <>
+__device__ __forceinline__ void helm_fast<KMODE_IMAG, false, double>(double r2, double cw, const KParams &K, double &Phi, double &Psi)
+{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+  Phi = cw * rinv * exp_neg_fast(-K.ki * r);
+}
+template <>
+__device__ __forceinline__ void helm_fast<KMODE_IMAG, true, double>(double r2, double cw, const KParams &K, double &Phi, double &Psi)
+{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+  Phi = cw * rinv * exp_neg_fast(-K.ki * r);
+  Psi = Phi * (-K.ki - rinv) * rinv;
+}
+template <>
+__device__ __forceinline__ void helm_fast<KMODE_CPLX, false, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
+{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+  double s, c; sincos_fast(K.kr * r, s, c);
+  const double y = -K.ki * r;
+  const double f = cw * rinv * (y <= 0.0 ? exp_neg_fast(y) : exp(y));
+  Phi = mk(f * c, f * s);
+}
+template <>
+__device__ __forceinline__ void helm_fast<KMODE_CPLX, true, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
+{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+  double s, c; sincos_fast(K.kr * r, s, c);
+  const double y = -K.ki * r;
+  const double f = cw * rinv * (y <= 0.0 ? exp_neg_fast(y) : exp(y));
+  Phi = mk(f * c, f * s);
+  const double a = -K.ki * rinv - rinv * rinv, b = K.kr * rinv;
+  Psi = mk(fma(Phi.x, a, -Phi.y * b), fma(Phi.x, b, Phi.y * a));
+}
+
+__device__ __forceinline__ void sadd(double &a, double b) { a += b; }
+__device__ __forceinline__ void sadd(cd &a, cd b) { a.x += b.x; a.y += b.y; }
+__device__ __forceinline__ double ssub(double a, double b) { return a - b; }
+__device__ __forceinline__ cd ssub(cd a, cd b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double dot3(const double *a, const double *b) { return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0])); }
+__device__ __forceinline__ void cross3(const double *a, const double *b, double *c)
+{ c[0] = fma(a[1], b[2], -a[2] * b[1]); c[1] = fma(a[2], b[0], -a[0] * b[2]); c[2] = fma(a[0], b[1], -a[1] * b[0]); }
+
+// ---- 1-D TMA bulk copy global -> shared, completion on an mbarrier ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_1d(void *dstSmem, const void *srcGlobal, uint32_t bytes, uint64_t *bar)
+{ const uint32_t b = smem_u32(bar), d = smem_u32(dstSmem);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(d), "l"(srcGlobal), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{ const uint32_t b = smem_u32(bar); uint32_t ok;
+  do { asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                    : "=r"(ok) : "r"(b), "r"(phase) : "memory"); } while (!ok);
+}
+
+template <int KMODE, bool PSI>
+__global__ void __launch_bounds__(FAR_THREADS, PSI ? 2 : 3)
 far_kernel(const FarArgs A)
-{ extern __shared__ double sm[];
+{ extern __shared__ __align__(128) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  typedef typename KScalar<KMODE>::type S;
   const int TA = A.TA;
   const int a0 = blockIdx.y * TA;
   const int bBase = blockIdx.x * FAR_THREADS;
@@ -26,31 +129,27 @@ far_kernel(const FarArgs A)
   if (A.symmetric && bBase + FAR_THREADS - 1 < a0) return;
   const int nA = min(TA, A.NPa - a0);
 
-  // stage the a-tile (nA * 36 doubles) in shared memory
-  { const double *src = (const double *)(A.pa + a0);
-    const int n = nA * 36;
-    for (int i = threadIdx.x; i < n; i += FAR_THREADS) sm[i] = src[i];
-  }
+  // stage the a-tile (nA contiguous PanelRec) with one TMA bulk copy
+  if (threadIdx.x == 0)
+   { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
+  if (threadIdx.x == 0) tma_load_1d(sm, A.pa + a0, (uint32_t)(nA * sizeof(PanelRec)), &bar);
 
   const int pb = bBase + threadIdx.x;
-  if (pb >= A.NPb) return;
-  if (A.symmetric && pb < a0) return;
-
-  // this lane's b-panel
-  const PanelRec *Pb = A.pb + pb;
-  double Cb[3], Rb, xb[18], qb[9], slb[3]; int eib[3];
+  const bool live = pb < A.NPb && !(A.symmetric && pb < a0);
+  // this lane's b-panel: cubature points (local coordinates) in registers
+  const PanelRec *Pb = A.pb + (live ? pb : 0);
+  double Cb[3], xb[18];
 #pragma unroll
   for (int i = 0; i < 3; i++) Cb[i] = Pb->C[i];
-  Rb = Pb->R;
+  const double Rb = Pb->R;
 #pragma unroll
   for (int i = 0; i < 18; i++) xb[i] = Pb->x[i];
-#pragma unroll
-  for (int i = 0; i < 9; i++) qb[i] = Pb->V[i] - Cb[i % 3];
-#pragma unroll
-  for (int i = 0; i < 3; i++) { slb[i] = Pb->sl[i]; eib[i] = Pb->ei[i]; }
 
-  typedef typename KScalar<KMODE>::type S;
+  mbar_wait(&bar, 0);
+  if (!live) return;
+
   unsigned long long nPPI = 0; unsigned int nPairs = 0;
 
   for (int ia = 0; ia < nA; ia++)
@@ -60,31 +159,133 @@ far_kernel(const FarArgs A)
      double D[3];
      const double rRel = pair_rrel(Pa, Pa[3], Cb, Rb, A.useDisp != 0, A.L, D);
      if (!(rRel > SCUFF_DESING_RADIUS)) continue;
-
      nPairs++;
-     Moments<S> M;
-     panel_pair_moments<KMODE, false>(Pa + 13, xb, D, A.K, M);
 
+     // ---- 3x3 barycentric moments of Phi (and Psi) ----
+     S mPhi[3][3], mPsi[3][3];
+#pragma unroll
+     for (int m = 0; m < 3; m++)
+#pragma unroll
+      for (int n = 0; n < 3; n++) { szero(mPhi[m][n]); if (PSI) szero(mPsi[m][n]); }
+
+#pragma unroll 1
+     for (int p = 0; p < 6; p++)
+      { const double y0 = Pa[13 + 3 * p] + D[0], y1 = Pa[14 + 3 * p] + D[1], y2 = Pa[15 + 3 * p] + D[2];
+        S a0_, au, av, b0_, bu, bv;
+        szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
+#pragma unroll
+        for (int pp = 0; pp < 6; pp++)
+         { const double R0 = y0 - xb[3 * pp], R1 = y1 - xb[3 * pp + 1], R2 = y2 - xb[3 * pp + 2];
+           const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
+           S Phi, Psi;
+           helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
+           sadd(a0_, Phi); fma_acc(au, tcr_u(pp), Phi); fma_acc(av, tcr_v(pp), Phi);
+           if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi); }
+         }
+        const double w0 = c_far_wm[p][0], w1 = c_far_wm[p][1], w2 = c_far_wm[p][2];
+        fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
+        fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
+        fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
+        if (PSI)
+         { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
+           fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
+           fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); }
+      }
+
+     // ---- contraction to the nine (Q_a,Q_b) combinations and scatter ----
      const int *eia = (const int *)(Pa + 34);
+     int eib[3]; double slb[3];
+#pragma unroll
+     for (int j = 0; j < 3; j++) { eib[j] = Pb->ei[j]; slb[j] = Pb->sl[j]; }
+     double Aa[3], Ba[3], Ab[3], Bb[3], E00[3];
+#pragma unroll
+     for (int m = 0; m < 3; m++)
+      { const double va0 = Pa[4 + m], vb0 = Pb->V[m];
+        Aa[m] = Pa[7 + m] - va0; Ba[m] = Pa[10 + m] - va0;
+        Ab[m] = Pb->V[3 + m] - vb0; Bb[m] = Pb->V[6 + m] - vb0;
+        E00[m] = (va0 - vb0) - (A.useDisp ? A.L[m] : 0.0); }
+     const double dAA = dot3(Aa, Ab), dAB = dot3(Aa, Bb), dBA = dot3(Ba, Ab), dBB = dot3(Ba, Bb);
+     // rows of the a-side shifted moments: row 1 ~ (u - [i==1]), row 2 ~ (v - [i==2])
+     S r1s[3], r2s[3], q1s[3], q2s[3];
+#pragma unroll
+     for (int n = 0; n < 3; n++)
+      { r1s[n] = ssub(mPhi[1][n], mPhi[0][n]); r2s[n] = ssub(mPhi[2][n], mPhi[0][n]);
+        if (PSI) { q1s[n] = ssub(mPsi[1][n], mPsi[0][n]); q2s[n] = ssub(mPsi[2][n], mPsi[0][n]); } }
+     const cd c4m = A.K.c4 * tocd(mPhi[0][0]);
+     // triple products for H1
+     double tAA = 0, tAB = 0, tBA = 0, tBB = 0, AbN = 0, BbN = 0, AaNp = 0, BaNp = 0;
+     if (PSI)
+      { double Na[3], Nb[3], eA[3], eB[3];
+        cross3(Aa, Ba, Na); cross3(Ab, Bb, Nb);
+        cross3(E00, Aa, eA); cross3(E00, Ba, eB);         // (X x Y).E = Y.(E x X)
+        tAA = dot3(Ab, eA); tAB = dot3(Bb, eA); tBA = dot3(Ab, eB); tBB = dot3(Bb, eB);
+        AbN = dot3(Ab, Na); BbN = dot3(Bb, Na); AaNp = dot3(Aa, Nb); BaNp = dot3(Ba, Nb); }
+
 #pragma unroll
      for (int i = 0; i < 3; i++)
       { const int ea = eia[i];
         if (ea < 0) continue;
-        double qa[3] = { Pa[4 + 3 * i] - Pa[0], Pa[5 + 3 * i] - Pa[1], Pa[6 + 3 * i] - Pa[2] };
         const double sla = Pa[31 + i];
+        const S *U = (i == 1) ? r1s : mPhi[1], *V = (i == 2) ? r2s : mPhi[2];
+        const S *UQ = (i == 1) ? q1s : mPsi[1], *VQ = (i == 2) ? q2s : mPsi[2];
 #pragma unroll
         for (int j = 0; j < 3; j++)
          { if (eib[j] < 0) continue;
-           cd H0, H1;
-           contract_moments(M, qa, qb + 3 * j, D, A.K, H0, H1);
+           // b-side shift: column 1 ~ (u' - [j==1]), column 2 ~ (v' - [j==2])
+           const S Uu = (j == 1) ? ssub(U[1], U[0]) : U[1], Uv = (j == 2) ? ssub(U[2], U[0]) : U[2];
+           const S Vu = (j == 1) ? ssub(V[1], V[0]) : V[1], Vv = (j == 2) ? ssub(V[2], V[0]) : V[2];
+           S h0; szero(h0);
+           fma_acc(h0, dAA, Uu); fma_acc(h0, dAB, Uv); fma_acc(h0, dBA, Vu); fma_acc(h0, dBB, Vv);
+           cd H0 = tocd(h0) + c4m, H1 = mk(0.0, 0.0);
+           if (PSI)
+            { const S Pu = (j == 1) ? ssub(UQ[1], UQ[0]) : UQ[1], Pv = (j == 2) ? ssub(UQ[2], UQ[0]) : UQ[2];
+              const S Qu = (j == 1) ? ssub(VQ[1], VQ[0]) : VQ[1], Qv = (j == 2) ? ssub(VQ[2], VQ[0]) : VQ[2];
+              // (X x Y).E_ij with E_ij = E00 + {0,A,B}_i - {0,A',B'}_j
+              const double cAA = tAA - (i == 2 ? AbN : 0.0) - (j == 2 ? AaNp : 0.0);
+              const double cAB = tAB - (i == 2 ? BbN : 0.0) + (j == 1 ? AaNp : 0.0);
+              const double cBA = tBA + (i == 1 ? AbN : 0.0) - (j == 2 ? BaNp : 0.0);
+              const double cBB = tBB + (i == 1 ? BbN : 0.0) + (j == 1 ? BaNp : 0.0);
+              S h1; szero(h1);
+              fma_acc(h1, cAA, Pu); fma_acc(h1, cAB, Pv); fma_acc(h1, cBA, Qu); fma_acc(h1, cBB, Qv);
+              H1 = tocd(h1); }
            scatter_ppi(A.S, A.K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
            nPPI += (A.symmetric && pa != pb && ea == eib[j]) ? 2 : 1;
          }
       }
    }
-  // algorithm counter (reference log line SurfaceSurfaceInteractions.cc:550-558)
+  // algorithm counters (reference log line SurfaceSurfaceInteractions.cc:550-558)
   if (nPPI) atomicAdd(A.counters, nPPI);
   if (nPairs) atomicAdd(A.counters + 5, (unsigned long long)nPairs);
+}
+
+// ---- self-test of fastmath.cuh (tests/test_fastmath_gpu.py) ----
+__global__ void fastmath_selftest_kernel(int n, const double *x, double *out)
+{ int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = fabs(x[i]) + 1e-300;
+  double s, c; sincos_fast(x[i], s, c);
+  out[6 * i + 0] = rsqrt_fast<true>(a); out[6 * i + 1] = rsqrt_fast<false>(a);
+  out[6 * i + 2] = s; out[6 * i + 3] = c;
+  out[6 * i + 4] = exp_neg_fast(-fabs(x[i])); out[6 * i + 5] = 0.0;
+}
+int run_fastmath_selftest(scuffcuda_context *ctx, int n, const double *xh, double *outh)
+{ double *dx = nullptr, *dout = nullptr;
+  if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&dout, 6 * (size_t)n * sizeof(double)) != cudaSuccess)
+   { cudaFree(dx); ctx->err = "selftest allocation failed"; return 1; }
+  cudaMemcpyAsync(dx, xh, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  ctx->launches++;
+  fastmath_selftest_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dx, dout);
+  cudaMemcpyAsync(outh, dout, 6 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dx); cudaFree(dout);
+  if (e != cudaSuccess) { ctx->err = std::string("fastmath selftest: ") + cudaGetErrorString(e); return 1; }
+  return 0;
+}
+
+template <int KMODE>
+static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi)
+{ if (psi) far_kernel<KMODE, true><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
+  else far_kernel<KMODE, false><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
@@ -96,10 +297,11 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   A.TA = TA;
   dim3 grid(bTiles, (A.NPa + TA - 1) / TA);
   size_t smem = (size_t)TA * sizeof(PanelRec);
+  const bool psi = !(A.S.aPEC && A.S.bPEC);     // PEC/PEC blocks stamp GC[0] only
   ctx->launches++;
-  if (kmode == KMODE_REAL) far_kernel<KMODE_REAL><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
-  else if (kmode == KMODE_IMAG) far_kernel<KMODE_IMAG><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
-  else far_kernel<KMODE_CPLX><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
+  if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi);
+  else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi);
+  else launch_far_mode<KMODE_CPLX>(ctx, A, grid, smem, psi);
 }
 
 }  // namespace scuffcuda

@@ -16,6 +16,8 @@ struct FarArgs
 };
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &A, int kmode);
+int run_fastmath_selftest(scuffcuda_context *ctx, int n, const double *x, double *out);
+#define SCUFF_MAX_KR 1.0e5   /* fast-path range of the FP64 sincos reduction (fastmath.cuh) */
 
 #define SW_THRESHOLD (1.0 * M_PI)      // PanelPanelInteractions.cc:58
 #define VERYSW_THRESHOLD 20.0          // PanelPanelInteractions.cc:59

@@ -72,6 +72,7 @@ def cuda_lib():
         L.scuffcuda_get_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
         L.scuffcuda_host_alloc.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]
         L.scuffcuda_host_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffcuda_selftest_math.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.scuffcuda_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _cuda = L
     return _cuda
