@@ -50,14 +50,14 @@ __device__ __forceinline__ void helm_fast(double r2, double cw, const KParams &K
 
 template <>
 __device__ __forceinline__ void helm_fast<KMODE_REAL, false, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
-{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
   double s, c; sincos_fast(K.kr * r, s, c);
   const double f = cw * rinv;
   Phi = mk(f * c, f * s);
 }
 template <>
 __device__ __forceinline__ void helm_fast<KMODE_REAL, true, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
-{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
   double s, c; sincos_fast(K.kr * r, s, c);
   const double f = cw * rinv;
   Phi = mk(f * c, f * s);
@@ -66,18 +66,18 @@ __device__ __forceinline__ void helm_fast<KMODE_REAL, true, cd>(double r2, doubl
 }
 template <>
 __device__ __forceinline__ void helm_fast<KMODE_IMAG, false, double>(double r2, double cw, const KParams &K, double &Phi, double &Psi)
-{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
   Phi = cw * rinv * exp_neg_fast(-K.ki * r);
 }
 template <>
 __device__ __forceinline__ void helm_fast<KMODE_IMAG, true, double>(double r2, double cw, const KParams &K, double &Phi, double &Psi)
-{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
   Phi = cw * rinv * exp_neg_fast(-K.ki * r);
   Psi = Phi * (-K.ki - rinv) * rinv;
 }
 template <>
 __device__ __forceinline__ void helm_fast<KMODE_CPLX, false, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
-{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
   double s, c; sincos_fast(K.kr * r, s, c);
   const double y = -K.ki * r;
   const double f = cw * rinv * (y <= 0.0 ? exp_neg_fast(y) : exp(y));
@@ -85,7 +85,7 @@ __device__ __forceinline__ void helm_fast<KMODE_CPLX, false, cd>(double r2, doub
 }
 template <>
 __device__ __forceinline__ void helm_fast<KMODE_CPLX, true, cd>(double r2, double cw, const KParams &K, cd &Phi, cd &Psi)
-{ const double rinv = rsqrt_fast(r2), r = r2 * rinv;
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
   double s, c; sincos_fast(K.kr * r, s, c);
   const double y = -K.ki * r;
   const double f = cw * rinv * (y <= 0.0 ? exp_neg_fast(y) : exp(y));
@@ -116,8 +116,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
                     : "=r"(ok) : "r"(b), "r"(phase) : "memory"); } while (!ok);
 }
 
+// exact-decision far test without sqrt/divide on the common path: rRel > 4  <=>  sqrt(r2)/Rmax > 4.  Away from the
+// threshold by more than 1e-9 relative the comparison of squares decides; inside that band the reference's own
+// expression (classify.cuh pair_rrel) is evaluated.
+__device__ __forceinline__ bool pair_is_far(const double *Ca, double Ra, const double *Cb, double Rb, bool useDisp, const double *L, double D[3])
+{ if (useDisp)
+   { D[0] = SC_SUB(SC_SUB(Ca[0], Cb[0]), L[0]); D[1] = SC_SUB(SC_SUB(Ca[1], Cb[1]), L[1]); D[2] = SC_SUB(SC_SUB(Ca[2], Cb[2]), L[2]); }
+  else
+   { D[0] = SC_SUB(Ca[0], Cb[0]); D[1] = SC_SUB(Ca[1], Cb[1]); D[2] = SC_SUB(Ca[2], Cb[2]); }
+  double r2 = SC_MUL(D[0], D[0]);
+  r2 = SC_ADD(r2, SC_MUL(D[1], D[1]));
+  r2 = SC_ADD(r2, SC_MUL(D[2], D[2]));
+  const double Rm = fmax(Ra, Rb), t = 16.0 * Rm * Rm;
+  if (r2 > t * (1.0 + 1.0e-9)) return true;
+  if (r2 < t * (1.0 - 1.0e-9)) return false;
+  return sqrt(r2) / Rm > SCUFF_DESING_RADIUS;
+}
+
+// shared-memory layout (doubles): a-tile [TA][36] | b cubature points [18][128] | b stash [12][128] | b edge ids (int)[3][128]
+#define FAR_SMEM_BYTES(TA) ((size_t)((TA) * 36 + 30 * FAR_THREADS) * sizeof(double) + 3 * FAR_THREADS * sizeof(int))
+
 template <int KMODE, bool PSI>
-__global__ void __launch_bounds__(FAR_THREADS, PSI ? 2 : 3)
+__global__ void __launch_bounds__(FAR_THREADS, PSI ? 3 : 4)
 far_kernel(const FarArgs A)
 { extern __shared__ __align__(128) double sm[];
   __shared__ __align__(8) uint64_t bar;
@@ -128,24 +148,36 @@ far_kernel(const FarArgs A)
   // symmetric: skip tiles entirely below the diagonal
   if (A.symmetric && bBase + FAR_THREADS - 1 < a0) return;
   const int nA = min(TA, A.NPa - a0);
+  const int tid = threadIdx.x;
+  double *sXb = sm + TA * 36 + tid;                    // element k at sXb[k * FAR_THREADS]
+  double *sSt = sm + TA * 36 + 18 * FAR_THREADS + tid;
+  int *sEi = (int *)(sm + TA * 36 + 30 * FAR_THREADS) + tid;
 
   // stage the a-tile (nA contiguous PanelRec) with one TMA bulk copy
-  if (threadIdx.x == 0)
+  if (tid == 0)
    { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  if (threadIdx.x == 0) tma_load_1d(sm, A.pa + a0, (uint32_t)(nA * sizeof(PanelRec)), &bar);
+  if (tid == 0) tma_load_1d(sm, A.pa + a0, (uint32_t)(nA * sizeof(PanelRec)), &bar);
 
-  const int pb = bBase + threadIdx.x;
+  const int pb = bBase + tid;
   const bool live = pb < A.NPb && !(A.symmetric && pb < a0);
-  // this lane's b-panel: cubature points (local coordinates) in registers
+  // this lane's b-panel: centroid/radius in registers, cubature points and the epilogue data in shared memory
   const PanelRec *Pb = A.pb + (live ? pb : 0);
-  double Cb[3], xb[18];
+  double Cb[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) Cb[i] = Pb->C[i];
   const double Rb = Pb->R;
 #pragma unroll
-  for (int i = 0; i < 18; i++) xb[i] = Pb->x[i];
+  for (int i = 0; i < 18; i++) sXb[i * FAR_THREADS] = Pb->x[i];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+   { const double v0 = Pb->V[m];
+     sSt[m * FAR_THREADS] = v0 + (A.useDisp ? A.L[m] : 0.0);        // V'_0 (+ L)
+     sSt[(3 + m) * FAR_THREADS] = Pb->V[3 + m] - v0;                 // A'
+     sSt[(6 + m) * FAR_THREADS] = Pb->V[6 + m] - v0;                 // B'
+     sSt[(9 + m) * FAR_THREADS] = Pb->sl[m];
+     sEi[m * FAR_THREADS] = Pb->ei[m]; }
 
   mbar_wait(&bar, 0);
   if (!live) return;
@@ -157,8 +189,7 @@ far_kernel(const FarArgs A)
      if (A.symmetric && pb < pa) continue;
      const double *Pa = sm + ia * 36;
      double D[3];
-     const double rRel = pair_rrel(Pa, Pa[3], Cb, Rb, A.useDisp != 0, A.L, D);
-     if (!(rRel > SCUFF_DESING_RADIUS)) continue;
+     if (!pair_is_far(Pa, Pa[3], Cb, Rb, A.useDisp != 0, A.L, D)) continue;
      nPairs++;
 
      // ---- 3x3 barycentric moments of Phi (and Psi) ----
@@ -175,7 +206,7 @@ far_kernel(const FarArgs A)
         szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
 #pragma unroll
         for (int pp = 0; pp < 6; pp++)
-         { const double R0 = y0 - xb[3 * pp], R1 = y1 - xb[3 * pp + 1], R2 = y2 - xb[3 * pp + 2];
+         { const double R0 = y0 - sXb[(3 * pp) * FAR_THREADS], R1 = y1 - sXb[(3 * pp + 1) * FAR_THREADS], R2 = y2 - sXb[(3 * pp + 2) * FAR_THREADS];
            const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
            S Phi, Psi;
            helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
@@ -196,14 +227,14 @@ far_kernel(const FarArgs A)
      const int *eia = (const int *)(Pa + 34);
      int eib[3]; double slb[3];
 #pragma unroll
-     for (int j = 0; j < 3; j++) { eib[j] = Pb->ei[j]; slb[j] = Pb->sl[j]; }
+     for (int j = 0; j < 3; j++) { eib[j] = sEi[j * FAR_THREADS]; slb[j] = sSt[(9 + j) * FAR_THREADS]; }
      double Aa[3], Ba[3], Ab[3], Bb[3], E00[3];
 #pragma unroll
      for (int m = 0; m < 3; m++)
-      { const double va0 = Pa[4 + m], vb0 = Pb->V[m];
+      { const double va0 = Pa[4 + m];
         Aa[m] = Pa[7 + m] - va0; Ba[m] = Pa[10 + m] - va0;
-        Ab[m] = Pb->V[3 + m] - vb0; Bb[m] = Pb->V[6 + m] - vb0;
-        E00[m] = (va0 - vb0) - (A.useDisp ? A.L[m] : 0.0); }
+        Ab[m] = sSt[(3 + m) * FAR_THREADS]; Bb[m] = sSt[(6 + m) * FAR_THREADS];
+        E00[m] = va0 - sSt[m * FAR_THREADS]; }
      const double dAA = dot3(Aa, Ab), dAB = dot3(Aa, Bb), dBA = dot3(Ba, Ab), dBB = dot3(Ba, Bb);
      // rows of the a-side shifted moments: row 1 ~ (u - [i==1]), row 2 ~ (v - [i==2])
      S r1s[3], r2s[3], q1s[3], q2s[3];
@@ -248,7 +279,7 @@ far_kernel(const FarArgs A)
               S h1; szero(h1);
               fma_acc(h1, cAA, Pu); fma_acc(h1, cAB, Pv); fma_acc(h1, cBA, Qu); fma_acc(h1, cBB, Qv);
               H1 = tocd(h1); }
-           scatter_ppi(A.S, A.K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
+           scatter_ppi<PSI>(A.S, A.K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
            nPPI += (A.symmetric && pa != pb && ea == eib[j]) ? 2 : 1;
          }
       }
@@ -284,8 +315,13 @@ int run_fastmath_selftest(scuffcuda_context *ctx, int n, const double *xh, doubl
 
 template <int KMODE>
 static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi)
-{ if (psi) far_kernel<KMODE, true><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
-  else far_kernel<KMODE, false><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
+{ // ask for the shared-memory carve-out that lets 3-4 CTAs (41.5 KB each) share an SM
+  if (psi)
+   { cudaFuncSetAttribute(far_kernel<KMODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+     far_kernel<KMODE, true><<<grid, FAR_THREADS, smem, ctx->stream>>>(A); }
+  else
+   { cudaFuncSetAttribute(far_kernel<KMODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+     far_kernel<KMODE, false><<<grid, FAR_THREADS, smem, ctx->stream>>>(A); }
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
@@ -296,7 +332,7 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   while (TA > 2 && (long)bTiles * ((A.NPa + TA - 1) / TA) < 4L * ctx->smCount) TA >>= 1;
   A.TA = TA;
   dim3 grid(bTiles, (A.NPa + TA - 1) / TA);
-  size_t smem = (size_t)TA * sizeof(PanelRec);
+  size_t smem = FAR_SMEM_BYTES(TA);
   const bool psi = !(A.S.aPEC && A.S.bPEC);     // PEC/PEC blocks stamp GC[0] only
   ctx->launches++;
   if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi);

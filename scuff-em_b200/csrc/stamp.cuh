@@ -36,6 +36,7 @@ __device__ __forceinline__ void stamp_edge_pair(const StampParams &P, int ea, in
 // Scatter the contribution of the PPI (pa,iQa ; pb,iQb) = (H0,H1) to its edge pair, handling
 // the upper-triangle convention of Symmetric blocks (only nea<=neb is stored; an unordered
 // panel pair p!=q visited once feeds (e,f) or (f,e), twice the value when e==f).
+template <bool NEED_G1 = true>
 __device__ __forceinline__ void scatter_ppi(const StampParams &P, const KParams &K,
                                             int pa, int pb, int ea, int eb, double sla, double slb,
                                             cd H0, cd H1)
@@ -49,7 +50,7 @@ __device__ __forceinline__ void scatter_ppi(const StampParams &P, const KParams 
      diag = (ea == eb);
    }
   cd g0 = s * H0;
-  cd g1 = s * (K.ooik * H1);
+  cd g1 = NEED_G1 ? s * (K.ooik * H1) : mk(0.0, 0.0);   // PEC/PEC blocks stamp GC[0] only
   stamp_edge_pair(P, ea, eb, g0, g1, diag);
 }
 

@@ -30,67 +30,87 @@ static int td_tables(scuffcuda_context *ctx, TDTables &T)
   return 0;
 }
 
-__global__ void __launch_bounds__(64)
-td_ct_kernel(const NearArgs A, const TDTables T, const int *tdIdx, int first, int nItems, double *scratch, int *status)
+// items[t] = 9*nearIndex + 3*i + j : one (pair, Q_a, Q_b) combination that feeds a matrix entry
+__global__ void __launch_bounds__(128)
+td_ct_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, double *scratch, int maxM, int *itemStatus)
 { const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nItems) return;
-  const int item = first + t;
-  const NearPair N = A.near[tdIdx[item / 9]];
+  const int item = items[t];
+  const NearPair N = A.near[item / 9];
   const int i = (item % 9) / 3, j = item % 3;
   const PanelRec &Pa = A.pa[N.pa], &Pb = A.pb[N.pb];
   const int ea = Pa.ei[i], eb = Pb.ei[j];
-  if (ea < 0 || eb < 0) return;
-  if (A.S.symmetric && N.pa == N.pb && ea > eb) return;
   double Va[9], Vb[9];
   for (int q = 0; q < 9; q++) { Va[q] = Pa.V[q]; Vb[q] = A.useDisp ? (Pb.V[q] + 1.0 * A.L[q % 3]) : Pb.V[q]; }
   cd H0, H1;
   int st = td_common_triangle(T, Va + 3 * N.ia[0], Va + 3 * N.ia[1], Va + 3 * N.ia[2], Va + 3 * i, Vb + 3 * j,
-                              mk(A.K.kr, A.K.ki), scratch + t, (size_t)gridDim.x * blockDim.x, H0, H1);
-  if (st) atomicExch(status, 1);
+                              mk(A.K.kr, A.K.ki), scratch + t, (size_t)gridDim.x * blockDim.x, H0, H1, maxM);
+  itemStatus[t] = st;
+  if (st) return;     // needs more Clenshaw-Curtis levels than this pass holds: redone by the next pass
   scatter_ppi(A.S, A.K, N.pa, N.pb, ea, eb, Pa.sl[i], Pb.sl[j], H0, H1);
   atomicAdd(A.counters + 2, (A.S.symmetric && N.pa != N.pb && ea == eb) ? 2ull : 1ull);
+}
+
+static int td_grow_scratch(scuffcuda_context *ctx, size_t need)
+{ if (need <= ctx->scratchBytes) return 0;
+  if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
+  if (cudaMalloc(&ctx->dscratch, need) != cudaSuccess) { cudaGetLastError(); ctx->err = "Taylor-Duffy scratch allocation failed"; return 1; }
+  ctx->scratchBytes = need; return 0;
 }
 
 int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
 { (void)kmode;
   // classify on the host (cheap: O(#near pairs)): which pairs need Taylor-Duffy / high-order cubature
   const Surface &Sa = ctx->surfaces[P.nsa], &Sb = ctx->surfaces[P.nsb];
-  std::vector<int> td;
+  std::vector<int> items;
   for (int n = 0; n < P.nNear; n++)
    { const NearPair &N = P.hnear[n]; bool verySW;
      int alg = near_algorithm(N.ncv, A.kabs, Sa.hpanels[N.pa].R, Sb.hpanels[N.pb].R, A.forceTD, verySW);
      if (alg == 4) continue;
-     if (alg == 2 && N.ncv == 3 && !verySW) { td.push_back(n); continue; }
+     if (alg == 2 && N.ncv == 3 && !verySW)
+      { // the (Q_a,Q_b) combinations that feed a matrix entry
+        const PanelRec &Pa = Sa.hpanels[N.pa], &Pb = Sb.hpanels[N.pb];
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+         { const int ea = Pa.ei[i], eb = Pb.ei[j];
+           if (ea < 0 || eb < 0) continue;
+           if (A.S.symmetric && N.pa == N.pb && ea > eb) continue;
+           items.push_back(9 * n + 3 * i + j); }
+        continue; }
      ctx->err = "short-wavelength regime (|k|*panel radius > pi) or SCUFF_DISABLE_CACHE: high-order cubature / "
                 "common-edge and common-vertex Taylor-Duffy are not yet available on the device path";
      return 1;
    }
-  if (td.empty()) return 0;
+  if (items.empty()) return 0;
   TDTables T; if (td_tables(ctx, T)) return 1;
-  int *dIdx = nullptr, *dStatus = nullptr;
-  const int batch = 32768;
-  size_t need = td.size() * sizeof(int) + 256 + (size_t)batch * TD_CACHE_DOUBLES * sizeof(double);
-  if (need > ctx->scratchBytes)
-   { if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
-     if (cudaMalloc(&ctx->dscratch, need) != cudaSuccess) { ctx->err = "Taylor-Duffy scratch allocation failed"; return 1; }
-     ctx->scratchBytes = need; }
-  dStatus = (int *)ctx->dscratch; dIdx = (int *)((char *)ctx->dscratch + 256);
-  double *scr = (double *)((char *)ctx->dscratch + 256 + ((td.size() * sizeof(int) + 255) / 256) * 256);
-  cudaMemsetAsync(dStatus, 0, sizeof(int), ctx->stream);
-  cudaMemcpyAsync(dIdx, td.data(), td.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-  cudaStreamSynchronize(ctx->stream);   // td (host vector) must outlive the copy
-  const int total = (int)td.size() * 9;
-  for (int first = 0; first < total; first += batch)
-   { int n = std::min(batch, total - first);
-     // grid covers exactly `batch` threads so that the scratch stride is fixed
-     ctx->launches++;
-     td_ct_kernel<<<batch / 64, 64, 0, ctx->stream>>>(A, T, dIdx, first, n, scr, dStatus);
+  // pass 0: every item at once with room for Clenshaw-Curtis levels <= 6 (65 points; the common case),
+  // pass 1: the items that asked for more, with the full MaxEval=1000 budget (level 9, 1025 points), in batches
+  const int passM[2] = { 6, 9 }, passBatch[2] = { 1 << 30, 32768 };
+  std::vector<int> status;
+  for (int pass = 0; pass < 2 && !items.empty(); pass++)
+   { const int maxM = passM[pass];
+     const size_t perItem = (size_t)4 * ((1u << maxM) + 1) * sizeof(double);
+     const int batch = (int)std::min<size_t>(items.size(), (size_t)passBatch[pass]);
+     const int threads = ((batch + 127) / 128) * 128;
+     const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
+     if (td_grow_scratch(ctx, hdr + (size_t)threads * perItem)) return 1;
+     int *dItems = (int *)ctx->dscratch, *dStatus = dItems + batch;
+     double *scr = (double *)((char *)ctx->dscratch + hdr);
+     std::vector<int> next;
+     for (size_t first = 0; first < items.size(); first += batch)
+      { const int n = (int)std::min<size_t>(batch, items.size() - first);
+        cudaMemcpyAsync(dItems, items.data() + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        ctx->launches++;
+        // the grid always spans `threads` threads so that the scratch stride is fixed
+        td_ct_kernel<<<threads / 128, 128, 0, ctx->stream>>>(A, T, dItems, n, scr, maxM, dStatus);
+        status.resize(n);
+        cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("td_ct_kernel: ") + cudaGetErrorString(e); return 1; }
+        for (int q = 0; q < n; q++) if (status[q]) next.push_back(items[first + q]);
+      }
+     items.swap(next);
    }
-  int st = 0;
-  cudaMemcpyAsync(&st, dStatus, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) { ctx->err = std::string("td_ct_kernel: ") + cudaGetErrorString(e); return 1; }
-  if (st) { ctx->err = "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"; return 1; }
+  if (!items.empty()) { ctx->err = "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"; return 1; }
   return 0;
 }
 

@@ -102,23 +102,43 @@ SCUFF_HD void td_ct_setup(const TDTables &T, const double *V1, const double *V2,
    }
 }
 
-// integrand at y in [0,1]: f[0..3] = Re/Im of the two P x Helmholtz integrals (TaylorDuffySum)
+// ExpRel(n,Z) with exp(Z) supplied by the caller (same value cexp_(Z) would return: hoisted out of the loop over n)
+SCUFF_HD cd exprel_v3p0_pre(int n, cd Z, cd expZ, bool small)
+{ if (small) return exprel_v3p0(n, Z);
+  if (Z.y == 0.0)
+   { double X = Z.x, Sum = expZ.x, Term = 1.0;
+     for (int m = 0; m < n; m++) { Sum -= Term; Term *= X / ((double)(m + 1)); }
+     return mk(Sum / Term, 0.0);
+   }
+  cd Sum = expZ, Term = mk(1.0, 0.0);
+  for (int m = 0; m < n; m++)
+   { Sum -= Term; double dv = (double)(m + 1); Term = Term * mk(Z.x / dv, Z.y / dv); }
+  return cdiv(Sum, Term);
+}
+
+// integrand at y in [0,1]: f[0..3] = Re/Im of the two P x Helmholtz integrals (TaylorDuffySum).
+// K_n(X_d) depends on neither P polynomial, so it is evaluated once for the union of their n ranges, and the two
+// complex exponentials per sub-region are evaluated once (the reference recomputes them for every n and P; same values).
 SCUFF_HD void td_ct_integrand(const TDCommonTriangle &W, double y, double f[4])
 { double X[3], u1, u2;
   u1 = 1.0; u2 = y;       X[0] = sqrt(W.A2 * u1 * u1 + 2.0 * W.AdB * u1 * u2 + W.B2 * u2 * u2);
   u1 = y;   u2 = (y - 1); X[1] = sqrt(W.A2 * u1 * u1 + 2.0 * W.AdB * u1 * u2 + W.B2 * u2 * u2);
   u1 = y;   u2 = 1.0;     X[2] = sqrt(W.A2 * u1 * u1 + 2.0 * W.AdB * u1 * u2 + W.B2 * u2 * u2);
   const cd IK = mk(-W.k.y, W.k.x);
+  const int nLo = (W.nMin[0] < W.nMin[1] ? W.nMin[0] : W.nMin[1]), nHi = (W.nMax[0] > W.nMax[1] ? W.nMax[0] : W.nMax[1]);
+  cd K[3][7];
+  for (int d = 0; d < 3; d++)
+   { cd IKX = mk(IK.x * X[d], IK.y * X[d]), eIKX = cexp_(IKX), mIKX = mk(-IKX.x, -IKX.y);
+     // exprel_v3p0's own branch conditions (TaylorDuffy.cc:829-891)
+     const bool small = (mIKX.y == 0.0) ? (fabs(mIKX.x) < 0.1) : (cabs_(mIKX) < 0.1);
+     cd emIKX = mk(0.0, 0.0);
+     if (!small) emIKX = (mIKX.y == 0.0) ? mk(exp(mIKX.x), 0.0) : cexp_(mIKX);
+     for (int n = nLo + 1; n <= nHi + 1; n++)
+      { cd t = eIKX * exprel_v3p0_pre(n, mIKX, emIKX, small); double dn = n * X[d]; K[d][n] = mk(t.x / dn, t.y / dn); }
+   }
   for (int np = 0; np < 2; np++)
-   { const int nMin = W.nMin[np], nMax = W.nMax[np];
-     cd K[3][7];
-     for (int d = 0; d < 3; d++)
-      { cd IKX = mk(IK.x * X[d], IK.y * X[d]), eIKX = cexp_(IKX), mIKX = mk(-IKX.x, -IKX.y);
-        for (int n = nMin + 1; n <= nMax + 1; n++)
-         { cd t = eIKX * exprel_v3p0(n, mIKX); double dn = n * X[d]; K[d][n] = mk(t.x / dn, t.y / dn); }
-      }
-     cd Sum = mk(0.0, 0.0);
-     for (int n = nMin; n <= nMax; n++)
+   { cd Sum = mk(0.0, 0.0);
+     for (int n = W.nMin[np]; n <= W.nMax[np]; n++)
       for (int d = 0; d < 3; d++)
        { double p = W.U[np][d][n][0] + y * W.U[np][d][n][1];
          Sum += p * K[d][n + 1]; }
@@ -194,12 +214,12 @@ struct TDCTFunctor
 // H[0], H[1] of a common-triangle panel pair (PanelPanelInteractions.cc:449-491 with ncv == 3):
 // H0 = R1 - 4 R0 / k^2, H1 = 0.  Vertices in AssessPanelPair order (V1,V2,V3).  Returns pcubature status.
 SCUFF_HD int td_common_triangle(const TDTables &T, const double *V1, const double *V2, const double *V3,
-                                const double *Q, const double *QP, cd k, double *cache, size_t stride, cd &H0, cd &H1)
+                                const double *Q, const double *QP, cd k, double *cache, size_t stride, cd &H0, cd &H1, int maxM = 9)
 { TDCommonTriangle W;
   td_ct_setup(T, V1, V2, V3, Q, QP, k, W);
   TDCTFunctor F; F.W = &W;
   double val[4], err[4];
-  int st = pcubature_1d<4>(T, F, 1.0e-10, 0.0, 1000, cache, stride, val, err, 9);
+  int st = pcubature_1d<4>(T, F, 1.0e-10, 0.0, 1000, cache, stride, val, err, maxM);
   cd R0 = mk(val[0], val[1]), R1 = mk(val[2], val[3]);
   cd k2 = k * k;
   cd t = cdiv(mk(4.0 * R0.x, 4.0 * R0.y), k2);
