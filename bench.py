@@ -162,8 +162,10 @@ def main():
     M = G.AllocateBEMMatrix()
     peak = ps.measure_fp64_peak()                      # in-run DFMA peak (MEASURED_PEAKS.json has no FP64 entry)
 
-    def omega_of(j):                                   # sweep point j -> rank j % world
+    def omega_of(j):                                   # sweep point j
         return a.omega * (1.0 + 0.01 * j)
+    sweep = _load("sweep", os.path.join(PKG, "sweep.py"))
+    mine = [w for _, w in sweep.points_for_rank([omega_of(j) for j in range(world * a.steps)], rank, world)]   # point j -> rank j % world
 
     # cold pass: builds the frequency-independent FIPPI table on the device (kept resident for the sweep)
     t0 = time.perf_counter()
@@ -182,7 +184,7 @@ def main():
     barrier()
     t0 = time.perf_counter()
     for s in range(a.steps):
-        G.AssembleBEMMatrix(omega_of(rank + world * s), M=M, to_host=False)   # returns after the stream has drained
+        G.AssembleBEMMatrix(mine[s], M=M, to_host=False)   # returns after the stream has drained
         t = ps.last_timing()
         tot_ms.append(t[0]); far_ms.append(t[1]); near_ms.append(t[2])
     barrier()

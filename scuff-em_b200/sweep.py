@@ -1,0 +1,41 @@
+"""Sweep sharding: the frequency / imaginary-frequency / Bloch-vector points of a sweep are independent
+units — every point needs only the immutable geometry and the frequency-independent FIPPI table, both replicated on
+every GPU — so point j goes to rank j mod world with NO data-path collective; only the per-point scalar results are
+gathered on rank 0 (host objects through torch.distributed, backend nccl on GPU boxes, gloo in the CPU tests).
+This mirrors how the reference's applications loop over frequencies (scuff-scatter.cc:373-472,
+scuff-cas3D/CasimirIntegrand.cc:296-312); one process per GPU replaces the reference's single process."""
+import torch.distributed as dist
+
+
+def points_for_rank(points, rank, world):
+    """round-robin: the (global index, point) pairs rank `rank` evaluates"""
+    return [(j, p) for j, p in enumerate(points) if j % world == rank]
+
+
+def gather_results(local, npoints, rank, world):
+    """local: list of (global index, result) from this rank -> on rank 0 the list of results in point order
+    (None on other ranks)."""
+    if world == 1:
+        parts = [local]
+    else:
+        parts = [None] * world if rank == 0 else None
+        dist.gather_object(local, parts, dst=0)
+        if rank != 0:
+            return None
+    out = [None] * npoints
+    for part in parts:
+        for j, r in part:
+            if out[j] is not None:
+                raise RuntimeError("sweep point %d evaluated twice" % j)
+            out[j] = r
+    missing = [j for j, r in enumerate(out) if r is None]
+    if missing:
+        raise RuntimeError("sweep points not evaluated: %s" % missing[:8])
+    return out
+
+
+def run_sweep(points, evaluate, rank=0, world=1):
+    """evaluate(point) -> picklable result (e.g. a few floats: power, log-det, trace).  Returns the ordered results on
+    rank 0.  `evaluate` is where RWGGeometry.AssembleBEMMatrix(+LU) runs on this rank's GPU."""
+    local = [(j, evaluate(p)) for j, p in points_for_rank(points, rank, world)]
+    return gather_results(local, len(points), rank, world)
