@@ -82,13 +82,13 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
    }
   if (items.empty()) return 0;
   TDTables T; if (td_tables(ctx, T)) return 1;
-  // pass 0: every item at once with room for Clenshaw-Curtis levels <= 6 (65 points; the common case),
+  // pass 0: every item at once with room for Clenshaw-Curtis levels <= 6 (129 points; the common case),
   // pass 1: the items that asked for more, with the full MaxEval=1000 budget (level 9, 1025 points), in batches
   const int passM[2] = { 6, 9 }, passBatch[2] = { 1 << 30, 32768 };
   std::vector<int> status;
   for (int pass = 0; pass < 2 && !items.empty(); pass++)
    { const int maxM = passM[pass];
-     const size_t perItem = (size_t)4 * ((1u << maxM) + 1) * sizeof(double);
+     const size_t perItem = (size_t)4 * ((1u << (maxM + 1)) + 1) * sizeof(double);   // level m holds 2^(m+1)+1 points
      const int batch = (int)std::min<size_t>(items.size(), (size_t)passBatch[pass]);
      const int threads = ((batch + 127) / 128) * 128;
      const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
