@@ -19,11 +19,14 @@
 // bulk copy (cp.async.bulk + mbarrier; a tile of PanelRec is contiguous) and read by broadcast — x 128 b-panels, one
 // per lane, whose cubature points stay in registers for the whole tile.  FP64-pipe bound.
 #include <stdint.h>
+#include <cstdlib>
 #include "context.h"
 #include "classify.cuh"
 #include "stamp.cuh"
 #include "kernels.h"
 #include "fastmath.cuh"
+#include "sw_kernels.h"
+#include "generated_tcr20.h"
 
 namespace scuffcuda {
 
@@ -116,6 +119,68 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
                     : "=r"(ok) : "r"(b), "r"(phase) : "memory"); } while (!ok);
 }
 
+// Contraction of the 3x3 moments to the nine (Q_a,Q_b) combinations and scatter into the matrix.
+// Va0/Aa/Ba: vertex 0 and edge vectors of panel a; Vb0 (already displaced by L), Ab, Bb of panel b.
+template <typename S, bool PSI>
+__device__ __forceinline__ void contract_scatter(const S (&mPhi)[3][3], const S (&mPsi)[3][3],
+                                                 const double *Va0, const double *Aa, const double *Ba,
+                                                 const double *Vb0, const double *Ab, const double *Bb,
+                                                 const int *eia, const double *sla3, const int *eib, const double *slb,
+                                                 int pa, int pb, const StampParams &SP, const KParams &K, int symmetric,
+                                                 unsigned long long &nPPI)
+{ double E00[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++) E00[m] = Va0[m] - Vb0[m];
+  const double dAA = dot3(Aa, Ab), dAB = dot3(Aa, Bb), dBA = dot3(Ba, Ab), dBB = dot3(Ba, Bb);
+  // rows of the a-side shifted moments: row 1 ~ (u - [i==1]), row 2 ~ (v - [i==2])
+  S r1s[3], r2s[3], q1s[3], q2s[3];
+#pragma unroll
+  for (int n = 0; n < 3; n++)
+   { r1s[n] = ssub(mPhi[1][n], mPhi[0][n]); r2s[n] = ssub(mPhi[2][n], mPhi[0][n]);
+     if (PSI) { q1s[n] = ssub(mPsi[1][n], mPsi[0][n]); q2s[n] = ssub(mPsi[2][n], mPsi[0][n]); } }
+  const cd c4m = K.c4 * tocd(mPhi[0][0]);
+  // triple products for H1
+  double tAA = 0, tAB = 0, tBA = 0, tBB = 0, AbN = 0, BbN = 0, AaNp = 0, BaNp = 0;
+  if (PSI)
+   { double Na[3], Nb[3], eA[3], eB[3];
+     cross3(Aa, Ba, Na); cross3(Ab, Bb, Nb);
+     cross3(E00, Aa, eA); cross3(E00, Ba, eB);         // (X x Y).E = Y.(E x X)
+     tAA = dot3(Ab, eA); tAB = dot3(Bb, eA); tBA = dot3(Ab, eB); tBB = dot3(Bb, eB);
+     AbN = dot3(Ab, Na); BbN = dot3(Bb, Na); AaNp = dot3(Aa, Nb); BaNp = dot3(Ba, Nb); }
+
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+   { const int ea = eia[i];
+     if (ea < 0) continue;
+     const double sla = sla3[i];
+     const S *U = (i == 1) ? r1s : mPhi[1], *V = (i == 2) ? r2s : mPhi[2];
+     const S *UQ = (i == 1) ? q1s : mPsi[1], *VQ = (i == 2) ? q2s : mPsi[2];
+#pragma unroll
+     for (int j = 0; j < 3; j++)
+      { if (eib[j] < 0) continue;
+        // b-side shift: column 1 ~ (u' - [j==1]), column 2 ~ (v' - [j==2])
+        const S Uu = (j == 1) ? ssub(U[1], U[0]) : U[1], Uv = (j == 2) ? ssub(U[2], U[0]) : U[2];
+        const S Vu = (j == 1) ? ssub(V[1], V[0]) : V[1], Vv = (j == 2) ? ssub(V[2], V[0]) : V[2];
+        S h0; szero(h0);
+        fma_acc(h0, dAA, Uu); fma_acc(h0, dAB, Uv); fma_acc(h0, dBA, Vu); fma_acc(h0, dBB, Vv);
+        cd H0 = tocd(h0) + c4m, H1 = mk(0.0, 0.0);
+        if (PSI)
+         { const S Pu = (j == 1) ? ssub(UQ[1], UQ[0]) : UQ[1], Pv = (j == 2) ? ssub(UQ[2], UQ[0]) : UQ[2];
+           const S Qu = (j == 1) ? ssub(VQ[1], VQ[0]) : VQ[1], Qv = (j == 2) ? ssub(VQ[2], VQ[0]) : VQ[2];
+           // (X x Y).E_ij with E_ij = E00 + {0,A,B}_i - {0,A',B'}_j
+           const double cAA = tAA - (i == 2 ? AbN : 0.0) - (j == 2 ? AaNp : 0.0);
+           const double cAB = tAB - (i == 2 ? BbN : 0.0) + (j == 1 ? AaNp : 0.0);
+           const double cBA = tBA + (i == 1 ? AbN : 0.0) - (j == 2 ? BaNp : 0.0);
+           const double cBB = tBB + (i == 1 ? BbN : 0.0) + (j == 1 ? BaNp : 0.0);
+           S h1; szero(h1);
+           fma_acc(h1, cAA, Pu); fma_acc(h1, cAB, Pv); fma_acc(h1, cBA, Qu); fma_acc(h1, cBB, Qv);
+           H1 = tocd(h1); }
+        scatter_ppi<PSI>(SP, K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
+        nPPI += (symmetric && pa != pb && ea == eib[j]) ? 2 : 1;
+      }
+   }
+}
+
 // exact-decision far test without sqrt/divide on the common path: rRel > 4  <=>  sqrt(r2)/Rmax > 4.  Away from the
 // threshold by more than 1e-9 relative the comparison of squares decides; inside that band the reference's own
 // expression (classify.cuh pair_rrel) is evaluated.
@@ -133,80 +198,83 @@ __device__ __forceinline__ bool pair_is_far(const double *Ca, double Ra, const d
   return sqrt(r2) / Rm > SCUFF_DESING_RADIUS;
 }
 
-// shared-memory layout (doubles): a-tile [TA][36] | b cubature points [18][128] | b stash [12][128] | b edge ids (int)[3][128]
-#define FAR_SMEM_BYTES(TA) ((size_t)((TA) * 36 + 30 * FAR_THREADS) * sizeof(double) + 3 * FAR_THREADS * sizeof(int))
+// shared-memory layout (doubles): b-tile [TB][36] | lane (a) cubature points [18][128] | lane stash [16][128] | lane edge ids (int)[3][128]
+#define FAR_SMEM_BYTES(TA) ((size_t)((TA) * 36 + 34 * FAR_THREADS) * sizeof(double) + 3 * FAR_THREADS * sizeof(int))
 
-template <int KMODE, bool PSI>
-__global__ void __launch_bounds__(FAR_THREADS, PSI ? 3 : 4)
+// Thread mapping: lane <-> a-panel (matrix ROW side), tile <-> b-panels (column side).  The matrix is column-major, so
+// the RED.ADD.F64 of one warp for entry (e_a(lane), e_b) go to neighbouring rows of ONE column (edges of consecutive
+// panels are nearly consecutive) instead of 32 different columns: ~4-8x fewer L2 atomic sectors per warp instruction.
+template <int KMODE, bool PSI, int MINB>
+__global__ void __launch_bounds__(FAR_THREADS, MINB)
 far_kernel(const FarArgs A)
 { extern __shared__ __align__(128) double sm[];
   __shared__ __align__(8) uint64_t bar;
   typedef typename KScalar<KMODE>::type S;
-  const int TA = A.TA;
-  const int a0 = blockIdx.y * TA;
-  const int bBase = blockIdx.x * FAR_THREADS;
-  // symmetric: skip tiles entirely below the diagonal
-  if (A.symmetric && bBase + FAR_THREADS - 1 < a0) return;
-  const int nA = min(TA, A.NPa - a0);
+  const int TB = A.TA;
+  const int b0 = blockIdx.y * TB;
+  const int aBase = blockIdx.x * FAR_THREADS;
+  const int nB = min(TB, A.NPb - b0);
+  // symmetric: only pa <= pb is visited; skip CTAs whose b-tile lies entirely below their a-lanes
+  if (A.symmetric && b0 + nB - 1 < aBase) return;
   const int tid = threadIdx.x;
-  double *sXb = sm + TA * 36 + tid;                    // element k at sXb[k * FAR_THREADS]
-  double *sSt = sm + TA * 36 + 18 * FAR_THREADS + tid;
-  int *sEi = (int *)(sm + TA * 36 + 30 * FAR_THREADS) + tid;
+  double *sXa = sm + TB * 36 + tid;                    // element k at sXa[k * FAR_THREADS]
+  double *sSt = sm + TB * 36 + 18 * FAR_THREADS + tid;
+  int *sEi = (int *)(sm + TB * 36 + 34 * FAR_THREADS) + tid;
 
-  // stage the a-tile (nA contiguous PanelRec) with one TMA bulk copy
+  // stage the b-tile (nB contiguous PanelRec) with one TMA bulk copy
   if (tid == 0)
    { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
   __syncthreads();
-  if (tid == 0) tma_load_1d(sm, A.pa + a0, (uint32_t)(nA * sizeof(PanelRec)), &bar);
+  if (tid == 0) tma_load_1d(sm, A.pb + b0, (uint32_t)(nB * sizeof(PanelRec)), &bar);
 
-  const int pb = bBase + tid;
-  const bool live = pb < A.NPb && !(A.symmetric && pb < a0);
-  // this lane's b-panel: centroid/radius in registers, cubature points and the epilogue data in shared memory
-  const PanelRec *Pb = A.pb + (live ? pb : 0);
-  double Cb[3];
+  const int pa = aBase + tid;
+  const bool live = pa < A.NPa && !(A.symmetric && pa > b0 + nB - 1);
+  // this lane's a-panel: cubature points, centroid/radius and the epilogue data in shared memory (thread-private columns)
+  const PanelRec *Pa = A.pa + (live ? pa : 0);
 #pragma unroll
-  for (int i = 0; i < 3; i++) Cb[i] = Pb->C[i];
-  const double Rb = Pb->R;
-#pragma unroll
-  for (int i = 0; i < 18; i++) sXb[i * FAR_THREADS] = Pb->x[i];
+  for (int i = 0; i < 18; i++) sXa[i * FAR_THREADS] = Pa->x[i];
 #pragma unroll
   for (int m = 0; m < 3; m++)
-   { const double v0 = Pb->V[m];
-     sSt[m * FAR_THREADS] = v0 + (A.useDisp ? A.L[m] : 0.0);        // V'_0 (+ L)
-     sSt[(3 + m) * FAR_THREADS] = Pb->V[3 + m] - v0;                 // A'
-     sSt[(6 + m) * FAR_THREADS] = Pb->V[6 + m] - v0;                 // B'
-     sSt[(9 + m) * FAR_THREADS] = Pb->sl[m];
-     sEi[m * FAR_THREADS] = Pb->ei[m]; }
+   { const double v0 = Pa->V[m];
+     sSt[m * FAR_THREADS] = v0;                                      // V_0
+     sSt[(3 + m) * FAR_THREADS] = Pa->V[3 + m] - v0;                 // A
+     sSt[(6 + m) * FAR_THREADS] = Pa->V[6 + m] - v0;                 // B
+     sSt[(9 + m) * FAR_THREADS] = Pa->sl[m];
+     sSt[(12 + m) * FAR_THREADS] = Pa->C[m];
+     sEi[m * FAR_THREADS] = Pa->ei[m]; }
+  sSt[15 * FAR_THREADS] = Pa->R;
 
   mbar_wait(&bar, 0);
   if (!live) return;
 
   unsigned long long nPPI = 0; unsigned int nPairs = 0;
 
-  for (int ia = 0; ia < nA; ia++)
-   { const int pa = a0 + ia;
+  for (int ib = 0; ib < nB; ib++)
+   { const int pb = b0 + ib;
      if (A.symmetric && pb < pa) continue;
-     const double *Pa = sm + ia * 36;
+     const double *Pb = sm + ib * 36;
      double D[3];
-     if (!pair_is_far(Pa, Pa[3], Cb, Rb, A.useDisp != 0, A.L, D)) continue;
+     { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
+       if (!pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D)) continue; }
      nPairs++;
 
-     // ---- 3x3 barycentric moments of Phi (and Psi) ----
-     S mPhi[3][3], mPsi[3][3];
+     // ---- 3x3 barycentric moments: mX[n over b (outer, tile)][m over a (inner, lane)] ----
+     S xPhi[3][3], xPsi[3][3];
 #pragma unroll
      for (int m = 0; m < 3; m++)
 #pragma unroll
-      for (int n = 0; n < 3; n++) { szero(mPhi[m][n]); if (PSI) szero(mPsi[m][n]); }
+      for (int n = 0; n < 3; n++) { szero(xPhi[m][n]); if (PSI) szero(xPsi[m][n]); }
 
 #pragma unroll 1
      for (int p = 0; p < 6; p++)
-      { const double y0 = Pa[13 + 3 * p] + D[0], y1 = Pa[14 + 3 * p] + D[1], y2 = Pa[15 + 3 * p] + D[2];
+      { // R = X_a - X_b = x_a(lane) - (x_b(tile) - D)
+        const double y0 = Pb[13 + 3 * p] - D[0], y1 = Pb[14 + 3 * p] - D[1], y2 = Pb[15 + 3 * p] - D[2];
         S a0_, au, av, b0_, bu, bv;
         szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
 #pragma unroll
         for (int pp = 0; pp < 6; pp++)
-         { const double R0 = y0 - sXb[(3 * pp) * FAR_THREADS], R1 = y1 - sXb[(3 * pp + 1) * FAR_THREADS], R2 = y2 - sXb[(3 * pp + 2) * FAR_THREADS];
+         { const double R0 = sXa[(3 * pp) * FAR_THREADS] - y0, R1 = sXa[(3 * pp + 1) * FAR_THREADS] - y1, R2 = sXa[(3 * pp + 2) * FAR_THREADS] - y2;
            const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
            S Phi, Psi;
            helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
@@ -214,79 +282,149 @@ far_kernel(const FarArgs A)
            if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi); }
          }
         const double w0 = c_far_wm[p][0], w1 = c_far_wm[p][1], w2 = c_far_wm[p][2];
-        fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
-        fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
-        fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
+        fma_acc(xPhi[0][0], w0, a0_); fma_acc(xPhi[0][1], w0, au); fma_acc(xPhi[0][2], w0, av);
+        fma_acc(xPhi[1][0], w1, a0_); fma_acc(xPhi[1][1], w1, au); fma_acc(xPhi[1][2], w1, av);
+        fma_acc(xPhi[2][0], w2, a0_); fma_acc(xPhi[2][1], w2, au); fma_acc(xPhi[2][2], w2, av);
         if (PSI)
-         { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
-           fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
-           fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); }
+         { fma_acc(xPsi[0][0], w0, b0_); fma_acc(xPsi[0][1], w0, bu); fma_acc(xPsi[0][2], w0, bv);
+           fma_acc(xPsi[1][0], w1, b0_); fma_acc(xPsi[1][1], w1, bu); fma_acc(xPsi[1][2], w1, bv);
+           fma_acc(xPsi[2][0], w2, b0_); fma_acc(xPsi[2][1], w2, bu); fma_acc(xPsi[2][2], w2, bv); }
       }
 
      // ---- contraction to the nine (Q_a,Q_b) combinations and scatter ----
-     const int *eia = (const int *)(Pa + 34);
-     int eib[3]; double slb[3];
+     { S mPhi[3][3], mPsi[3][3];
 #pragma unroll
-     for (int j = 0; j < 3; j++) { eib[j] = sEi[j * FAR_THREADS]; slb[j] = sSt[(9 + j) * FAR_THREADS]; }
-     double Aa[3], Ba[3], Ab[3], Bb[3], E00[3];
+       for (int m = 0; m < 3; m++)
 #pragma unroll
-     for (int m = 0; m < 3; m++)
-      { const double va0 = Pa[4 + m];
-        Aa[m] = Pa[7 + m] - va0; Ba[m] = Pa[10 + m] - va0;
-        Ab[m] = sSt[(3 + m) * FAR_THREADS]; Bb[m] = sSt[(6 + m) * FAR_THREADS];
-        E00[m] = va0 - sSt[m * FAR_THREADS]; }
-     const double dAA = dot3(Aa, Ab), dAB = dot3(Aa, Bb), dBA = dot3(Ba, Ab), dBB = dot3(Ba, Bb);
-     // rows of the a-side shifted moments: row 1 ~ (u - [i==1]), row 2 ~ (v - [i==2])
-     S r1s[3], r2s[3], q1s[3], q2s[3];
+        for (int n = 0; n < 3; n++) { mPhi[m][n] = xPhi[n][m]; mPsi[m][n] = xPsi[n][m]; }
+       int eia[3]; double sla[3], Aa[3], Ba[3], Ab[3], Bb[3], Va0[3], Vb0[3];
 #pragma unroll
-     for (int n = 0; n < 3; n++)
-      { r1s[n] = ssub(mPhi[1][n], mPhi[0][n]); r2s[n] = ssub(mPhi[2][n], mPhi[0][n]);
-        if (PSI) { q1s[n] = ssub(mPsi[1][n], mPsi[0][n]); q2s[n] = ssub(mPsi[2][n], mPsi[0][n]); } }
-     const cd c4m = A.K.c4 * tocd(mPhi[0][0]);
-     // triple products for H1
-     double tAA = 0, tAB = 0, tBA = 0, tBB = 0, AbN = 0, BbN = 0, AaNp = 0, BaNp = 0;
-     if (PSI)
-      { double Na[3], Nb[3], eA[3], eB[3];
-        cross3(Aa, Ba, Na); cross3(Ab, Bb, Nb);
-        cross3(E00, Aa, eA); cross3(E00, Ba, eB);         // (X x Y).E = Y.(E x X)
-        tAA = dot3(Ab, eA); tAB = dot3(Bb, eA); tBA = dot3(Ab, eB); tBB = dot3(Bb, eB);
-        AbN = dot3(Ab, Na); BbN = dot3(Bb, Na); AaNp = dot3(Aa, Nb); BaNp = dot3(Ba, Nb); }
-
-#pragma unroll
-     for (int i = 0; i < 3; i++)
-      { const int ea = eia[i];
-        if (ea < 0) continue;
-        const double sla = Pa[31 + i];
-        const S *U = (i == 1) ? r1s : mPhi[1], *V = (i == 2) ? r2s : mPhi[2];
-        const S *UQ = (i == 1) ? q1s : mPsi[1], *VQ = (i == 2) ? q2s : mPsi[2];
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-         { if (eib[j] < 0) continue;
-           // b-side shift: column 1 ~ (u' - [j==1]), column 2 ~ (v' - [j==2])
-           const S Uu = (j == 1) ? ssub(U[1], U[0]) : U[1], Uv = (j == 2) ? ssub(U[2], U[0]) : U[2];
-           const S Vu = (j == 1) ? ssub(V[1], V[0]) : V[1], Vv = (j == 2) ? ssub(V[2], V[0]) : V[2];
-           S h0; szero(h0);
-           fma_acc(h0, dAA, Uu); fma_acc(h0, dAB, Uv); fma_acc(h0, dBA, Vu); fma_acc(h0, dBB, Vv);
-           cd H0 = tocd(h0) + c4m, H1 = mk(0.0, 0.0);
-           if (PSI)
-            { const S Pu = (j == 1) ? ssub(UQ[1], UQ[0]) : UQ[1], Pv = (j == 2) ? ssub(UQ[2], UQ[0]) : UQ[2];
-              const S Qu = (j == 1) ? ssub(VQ[1], VQ[0]) : VQ[1], Qv = (j == 2) ? ssub(VQ[2], VQ[0]) : VQ[2];
-              // (X x Y).E_ij with E_ij = E00 + {0,A,B}_i - {0,A',B'}_j
-              const double cAA = tAA - (i == 2 ? AbN : 0.0) - (j == 2 ? AaNp : 0.0);
-              const double cAB = tAB - (i == 2 ? BbN : 0.0) + (j == 1 ? AaNp : 0.0);
-              const double cBA = tBA + (i == 1 ? AbN : 0.0) - (j == 2 ? BaNp : 0.0);
-              const double cBB = tBB + (i == 1 ? BbN : 0.0) + (j == 1 ? BaNp : 0.0);
-              S h1; szero(h1);
-              fma_acc(h1, cAA, Pu); fma_acc(h1, cAB, Pv); fma_acc(h1, cBA, Qu); fma_acc(h1, cBB, Qv);
-              H1 = tocd(h1); }
-           scatter_ppi<PSI>(A.S, A.K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
-           nPPI += (A.symmetric && pa != pb && ea == eib[j]) ? 2 : 1;
-         }
-      }
+       for (int m = 0; m < 3; m++)
+        { eia[m] = sEi[m * FAR_THREADS]; sla[m] = sSt[(9 + m) * FAR_THREADS];
+          Va0[m] = sSt[m * FAR_THREADS]; Aa[m] = sSt[(3 + m) * FAR_THREADS]; Ba[m] = sSt[(6 + m) * FAR_THREADS];
+          Vb0[m] = Pb[4 + m] + (A.useDisp ? A.L[m] : 0.0);
+          Ab[m] = Pb[7 + m] - Pb[4 + m]; Bb[m] = Pb[10 + m] - Pb[4 + m]; }
+       contract_scatter<S, PSI>(mPhi, mPsi, Va0, Aa, Ba, Vb0, Ab, Bb, eia, sla, (const int *)(Pb + 34), Pb + 31,
+                                pa, pb, A.S, A.K, A.symmetric, nPPI);
+     }
    }
   // algorithm counters (reference log line SurfaceSurfaceInteractions.cc:550-558)
   if (nPPI) atomicAdd(A.counters, nPPI);
   if (nPairs) atomicAdd(A.counters + 5, (unsigned long long)nPairs);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// High-order cubature (78 x 78 points, GetTCR(20)) for near pairs without common vertices in the short-wavelength
+// regime (PPIALG_HOCUBATURE, PanelPanelInteractions.cc:437-441).  One WARP per panel pair: lanes split the 78 outer
+// points, every lane sweeps the 78 inner points (broadcast shared-memory reads), the 3x3 complex moments are reduced with
+// warp shuffles and lane 0 contracts and scatters.
+// ------------------------------------------------------------------------------------------------------------------
+#define HO_NPTS SC_TCR20_NPTS
+#define HO_WARPS 4
+
+__device__ __forceinline__ double wsum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v; }
+__device__ __forceinline__ cd wsum(cd v) { return mk(wsum(v.x), wsum(v.y)); }
+
+template <int KMODE, bool PSI>
+__global__ void __launch_bounds__(32 * HO_WARPS)
+ho_kernel(const NearArgs A, const int *idx, int n, const double *tcr)
+{ extern __shared__ __align__(16) double sm[];
+  typedef typename KScalar<KMODE>::type S;
+  double *sT = sm;
+  for (int i = threadIdx.x; i < 3 * HO_NPTS; i += blockDim.x) sT[i] = tcr[i];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int w = blockIdx.x * HO_WARPS + warp;
+  double *sX = sm + 3 * HO_NPTS * (1 + warp);
+  const bool live = w < n;
+  const NearPair N = A.near[idx[live ? w : 0]];
+  const PanelRec &Pa = A.pa[N.pa], &Pb = A.pb[N.pb];
+  // everything relative to panel a's centroid
+  double Va0[3], Aa[3], Ba[3], Vb0[3], Ab[3], Bb[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+   { Va0[m] = Pa.V[m]; Aa[m] = Pa.V[3 + m] - Pa.V[m]; Ba[m] = Pa.V[6 + m] - Pa.V[m];
+     Vb0[m] = Pb.V[m] + (A.useDisp ? A.L[m] : 0.0); Ab[m] = Pb.V[3 + m] - Pb.V[m]; Bb[m] = Pb.V[6 + m] - Pb.V[m]; }
+  __syncthreads();
+  for (int q = lane; q < HO_NPTS; q += 32)
+#pragma unroll
+   for (int m = 0; m < 3; m++) sX[3 * q + m] = (Vb0[m] - Pa.C[m]) + sT[3 * q] * Ab[m] + sT[3 * q + 1] * Bb[m];
+  __syncwarp();
+
+  S mPhi[3][3], mPsi[3][3];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+   for (int k = 0; k < 3; k++) { szero(mPhi[m][k]); szero(mPsi[m][k]); }
+  if (live)
+   for (int p = lane; p < HO_NPTS; p += 32)
+    { const double u = sT[3 * p], v = sT[3 * p + 1], wp = sT[3 * p + 2];
+      const double y0 = (Va0[0] - Pa.C[0]) + u * Aa[0] + v * Ba[0], y1 = (Va0[1] - Pa.C[1]) + u * Aa[1] + v * Ba[1],
+                   y2 = (Va0[2] - Pa.C[2]) + u * Aa[2] + v * Ba[2];
+      S a0_, au, av, b0_, bu, bv;
+      szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
+#pragma unroll 2
+      for (int pp = 0; pp < HO_NPTS; pp++)
+       { const double R0 = y0 - sX[3 * pp], R1 = y1 - sX[3 * pp + 1], R2 = y2 - sX[3 * pp + 2];
+         const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
+         S Phi, Psi; szero(Psi);
+         helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * sT[3 * pp + 2], A.K, Phi, Psi);
+         const double up = sT[3 * pp], vp = sT[3 * pp + 1];
+         sadd(a0_, Phi); fma_acc(au, up, Phi); fma_acc(av, vp, Phi);
+         if (PSI) { sadd(b0_, Psi); fma_acc(bu, up, Psi); fma_acc(bv, vp, Psi); }
+       }
+      const double w0 = wp, w1 = wp * u, w2 = wp * v;
+      fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
+      fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
+      fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
+      if (PSI)
+       { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
+         fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
+         fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); }
+    }
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+#pragma unroll
+   for (int k = 0; k < 3; k++) { mPhi[m][k] = wsum(mPhi[m][k]); if (PSI) mPsi[m][k] = wsum(mPsi[m][k]); }
+  if (!live || lane != 0) return;
+  int eia[3], eib[3]; double sla[3], slb[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++) { eia[m] = Pa.ei[m]; eib[m] = Pb.ei[m]; sla[m] = Pa.sl[m]; slb[m] = Pb.sl[m]; }
+  unsigned long long nPPI = 0;
+  contract_scatter<S, PSI>(mPhi, mPsi, Va0, Aa, Ba, Vb0, Ab, Bb, eia, sla, eib, slb, N.pa, N.pb, A.S, A.K, A.S.symmetric, nPPI);
+  if (nPPI) atomicAdd(A.counters + 1, nPPI);
+}
+
+template <int KMODE>
+static void launch_ho_mode(scuffcuda_context *ctx, const NearArgs &A, const int *didx, int n, const double *dtcr, bool psi)
+{ const size_t smem = (size_t)3 * HO_NPTS * (1 + HO_WARPS) * sizeof(double);
+  const int blocks = (n + HO_WARPS - 1) / HO_WARPS;
+  if (psi) ho_kernel<KMODE, true><<<blocks, 32 * HO_WARPS, smem, ctx->stream>>>(A, didx, n, dtcr);
+  else ho_kernel<KMODE, false><<<blocks, 32 * HO_WARPS, smem, ctx->stream>>>(A, didx, n, dtcr);
+}
+
+int run_ho(scuffcuda_context *ctx, const NearArgs &A, const int *hoIdx, int n, int kmode)
+{ if (n <= 0) return 0;
+  static double *dtcr[64] = { nullptr };
+  double *&T = dtcr[ctx->device & 63];
+  if (!T)
+   { if (cudaMalloc(&T, sizeof SC_TCR20_H) != cudaSuccess) { ctx->err = "high-order cubature table allocation failed"; return 1; }
+     cudaMemcpy(T, SC_TCR20_H, sizeof SC_TCR20_H, cudaMemcpyHostToDevice); }
+  int *didx = nullptr;
+  if (cudaMalloc(&didx, (size_t)n * sizeof(int)) != cudaSuccess) { ctx->err = "high-order cubature index allocation failed"; return 1; }
+  cudaMemcpyAsync(didx, hoIdx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+  const bool psi = !(A.S.aPEC && A.S.bPEC);
+  ctx->launches++;
+  if (kmode == KMODE_REAL) launch_ho_mode<KMODE_REAL>(ctx, A, didx, n, T, psi);
+  else if (kmode == KMODE_IMAG) launch_ho_mode<KMODE_IMAG>(ctx, A, didx, n, T, psi);
+  else launch_ho_mode<KMODE_CPLX>(ctx, A, didx, n, T, psi);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(didx);
+  if (e != cudaSuccess) { ctx->err = std::string("ho_kernel: ") + cudaGetErrorString(e); return 1; }
+  return 0;
 }
 
 // ---- self-test of fastmath.cuh (tests/test_fastmath_gpu.py) ----
@@ -313,31 +451,37 @@ int run_fastmath_selftest(scuffcuda_context *ctx, int n, const double *xh, doubl
   return 0;
 }
 
+template <int KMODE, bool PSI, int MINB>
+static void launch_far_inst(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem)
+{ // ask for the shared-memory carve-out that lets MINB CTAs (~46 KB each) share an SM
+  cudaFuncSetAttribute(far_kernel<KMODE, PSI, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  far_kernel<KMODE, PSI, MINB><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
+}
 template <int KMODE>
-static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi)
-{ // ask for the shared-memory carve-out that lets 3-4 CTAs (41.5 KB each) share an SM
-  if (psi)
-   { cudaFuncSetAttribute(far_kernel<KMODE, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-     far_kernel<KMODE, true><<<grid, FAR_THREADS, smem, ctx->stream>>>(A); }
-  else
-   { cudaFuncSetAttribute(far_kernel<KMODE, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-     far_kernel<KMODE, false><<<grid, FAR_THREADS, smem, ctx->stream>>>(A); }
+static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi, int minb)
+{ if (psi) { if (minb >= 3) launch_far_inst<KMODE, true, 3>(ctx, A, grid, smem); else launch_far_inst<KMODE, true, 2>(ctx, A, grid, smem); }
+  else { if (minb >= 4) launch_far_inst<KMODE, false, 4>(ctx, A, grid, smem); else launch_far_inst<KMODE, false, 3>(ctx, A, grid, smem); }
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
 { FarArgs A = Ain;
-  // tile height: enough CTAs to fill the machine on small meshes, 32 on large ones
-  int bTiles = (A.NPb + FAR_THREADS - 1) / FAR_THREADS;
-  int TA = 32;
-  while (TA > 2 && (long)bTiles * ((A.NPa + TA - 1) / TA) < 4L * ctx->smCount) TA >>= 1;
-  A.TA = TA;
-  dim3 grid(bTiles, (A.NPa + TA - 1) / TA);
-  size_t smem = FAR_SMEM_BYTES(TA);
+  // lanes: 128 a-panels (rows); tile: TB b-panels (columns) in shared memory.  Tile height: enough CTAs to fill the
+  // machine on small meshes, 32 on large ones
+  int aTiles = (A.NPa + FAR_THREADS - 1) / FAR_THREADS;
+  int TB = 32;
+  while (TB > 2 && (long)aTiles * ((A.NPb + TB - 1) / TB) < 4L * ctx->smCount) TB >>= 1;
+  A.TA = TB;
+  dim3 grid(aTiles, (A.NPb + TB - 1) / TB);
+  size_t smem = FAR_SMEM_BYTES(TB);
   const bool psi = !(A.S.aPEC && A.S.bPEC);     // PEC/PEC blocks stamp GC[0] only
+  // resident CTAs per SM (register budget 168 vs 128 per thread): tuning knob, default from measurements
+  static int minbEnv = -1;
+  if (minbEnv < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB"); minbEnv = e ? atoi(e) : 0; }
+  const int minb = minbEnv > 0 ? minbEnv : (psi ? 3 : 4);
   ctx->launches++;
-  if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi);
-  else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi);
-  else launch_far_mode<KMODE_CPLX>(ctx, A, grid, smem, psi);
+  if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi, minb);
+  else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi, minb);
+  else launch_far_mode<KMODE_CPLX>(ctx, A, grid, smem, psi, minb);
 }
 
 }  // namespace scuffcuda

@@ -1,0 +1,351 @@
+// Taylor-Duffy for panel pairs with ONE or TWO common vertices (TD_COMMONVERTEX / TD_COMMONEDGE), used by the reference
+// in the short-wavelength regime |k| R > pi and whenever the FIPPI cache is disabled
+// (PanelPanelInteractions.cc:449-491).  Reference semantics restated here:
+//   TaylorDuffy()               libs/libscuff/TaylorDuffy.cc:277-368   (driver, once-integrable Helmholtz kernels)
+//   TaylorDuffySum()            :152-258   integrand  sum_d sum_n P_dn(y) K_n(X_d(y)) * Jacobian/(4 pi)
+//   GetX / GetScriptP / GetScriptK  :491-547, :552-622, :896-935
+//   ComputeGeometricParameters  :1265-1526 (C, M, V, S inputs of the three P polynomials TD_UNITY, TD_PMCHWG1, TD_PMCHWC)
+//   pcubature                   libs/libSGJC/pcubature.c:300-400: p-adaptive tensor Clenshaw-Curtis, refine the dimension
+//                               with the largest error estimate, stop when converged (RelTol 1e-10, per component) or
+//                               numEval > MaxEval = 1000 (the 3-D common-vertex case normally stops on the budget, so the
+//                               level sequence is part of the contract).
+// The Upsilon coefficient maps come from generated_tables.h as data.  One thread per (panel pair, Q_a, Q_b) item; the
+// function-value cache of the cubature lives in a strided HBM scratch block.
+#include <vector>
+#include <algorithm>
+#include "kernels.h"
+#include "sw_kernels.h"
+#include "classify.cuh"
+#include "stamp.cuh"
+#include "td_math.cuh"
+
+namespace scuffcuda {
+
+#define TDG_NUMMONO 22
+#define TDG_MAXPTS 2304            /* >= 27 + 1000 + last increment (see run_td_general) */
+#define TDG_FDIM 6
+#define TDG_MAXENT 48
+#define SC_TD_MAXLEVEL 10          /* device Clenshaw-Curtis tables hold levels <= 10 (generated_tables.h SC_CC_MAXM) */
+
+// monomial ordering of TaylorDuffy.cc:53-79
+enum { M_1 = 0, M_Y1 = 1, M_Y12 = 2, M_Y2 = 3, M_Y1Y2 = 4, M_Y22 = 5, M_Y12Y2 = 7, M_Y1Y22 = 8, M_Y12Y22 = 10,
+       M_Y2Y3 = 15, M_Y1Y2Y3 = 17, M_Y22Y3 = 18, M_Y12Y2Y3 = 19, M_Y1Y22Y32 = 20, M_Y22Y32 = 21 };
+
+struct TDGen
+{ int cas, numRegions, nOffset;
+  double A2, B2, AP2, BP2, L2, AdB, AdAP, AdBP, AdL, BdAP, BdBP, APdBP, BPdL;
+  double U[3][6][TD_NUMWPOWERS][TDG_NUMMONO];     // [P slot][region][n][monomial]
+  int nMin[3], nMax[3];
+  cd k;
+};
+
+__device__ void tdg_setup(const TDTables &T, int cas, const double *V1, const double *V2, const double *V3,
+                          const double *V2Pin, const double *V3P, const double *Q, const double *QP, cd k, TDGen &W)
+{ const double *V2P = (cas == 2) ? V2 : V2Pin;              // TaylorDuffy.cc:1286-1289
+  double A[3], B[3], AP[3], BP[3], L[3], D[3], DP[3], DeltaD[3];
+  sub3(V2, V1, A); sub3(V3, V2, B); sub3(V2P, V1, AP); sub3(V3P, V2P, BP);
+  W.cas = cas; W.k = k;
+  W.A2 = dot3(A, A); W.AdB = dot3(A, B); W.B2 = dot3(B, B);
+  W.AP2 = W.BP2 = W.L2 = W.AdAP = W.AdBP = W.AdL = W.BdAP = W.BdBP = W.APdBP = W.BPdL = 0.0;
+  if (cas == 2)
+   { sub3(BP, B, L);
+     W.BP2 = dot3(BP, BP); W.AdBP = dot3(A, BP); W.L2 = dot3(L, L); W.AdL = dot3(A, L); W.BPdL = dot3(BP, L);
+     W.numRegions = 6; W.nOffset = 2; }
+  else
+   { W.AP2 = dot3(AP, AP); W.BP2 = dot3(BP, BP); W.AdAP = dot3(A, AP); W.AdBP = dot3(A, BP);
+     W.BdAP = dot3(B, AP); W.BdBP = dot3(B, BP); W.APdBP = dot3(AP, BP);
+     W.numRegions = 2; W.nOffset = 3; }
+  sub3(V1, Q, D); sub3(V1, QP, DP); sub3(QP, Q, DeltaD);
+  double DPxD[3]; cross3(DP, D, DPxD);
+  for (int np = 0; np < 3; np++)
+   { // inputs: C[4], M11 M12 M13 M14 M22 M23 M24 M33 M34 M44, V[4], S
+     double in[19];
+     for (int i = 0; i < 19; i++) in[i] = 0.0;
+     if (np == 0) in[18] = 1.0;                                          // TD_UNITY
+     else if (np == 1)                                                   // TD_PMCHWG1
+      { in[4 + 2] = dot3(A, AP); in[4 + 3] = dot3(A, BP); in[4 + 5] = dot3(B, AP); in[4 + 6] = dot3(B, BP);
+        in[14] = dot3(A, DP); in[15] = dot3(B, DP); in[16] = dot3(D, AP); in[17] = dot3(D, BP);
+        in[18] = dot3(D, DP); }
+     else                                                                // TD_PMCHWC
+      { double S[3];
+        cross3(A, AP, S); in[4 + 2] = -dot3(S, DeltaD);
+        cross3(A, BP, S); in[4 + 3] = -dot3(S, DeltaD);
+        cross3(B, AP, S); in[4 + 5] = -dot3(S, DeltaD);
+        cross3(B, BP, S); in[4 + 6] = -dot3(S, DeltaD);
+        in[14] = -dot3(A, DPxD); in[15] = -dot3(B, DPxD); in[16] = dot3(AP, DPxD); in[17] = dot3(BP, DPxD); }
+     for (int d = 0; d < 6; d++) for (int n = 0; n < TD_NUMWPOWERS; n++) for (int m = 0; m < TDG_NUMMONO; m++) W.U[np][d][n][m] = 0.0;
+     for (int e = T.upsStart[cas]; e < T.upsStart[cas + 1]; e++)
+      { const UpsEntry &E = T.ups[e];
+        W.U[np][E.d][E.n][E.mono] += E.coef * in[E.input]; }
+     int nMin = TD_NUMWPOWERS - 1, nMax = -1;
+     for (int n = 0; n < TD_NUMWPOWERS; n++) for (int d = 0; d < W.numRegions; d++) for (int m = 0; m < TDG_NUMMONO; m++)
+      if (fabs(W.U[np][d][n][m]) > 1.0e-8) { if (n < nMin) nMin = n; if (n > nMax) nMax = n; }
+     W.nMin[np] = nMin; W.nMax[np] = nMax;
+   }
+}
+
+// integrand (TaylorDuffySum, once-integrable branch): f[0..5] = Re/Im of the three P x K integrals
+__device__ void tdg_integrand(const TDGen &W, const double *y, double f[TDG_FDIM])
+{ const int NR = W.numRegions, nOff = W.nOffset;
+  double yInner, Jac;
+  if (W.cas == 2) { yInner = y[1]; Jac = y[0]; } else { yInner = y[2]; Jac = y[1]; }
+  if (Jac == 0.0) { for (int i = 0; i < TDG_FDIM; i++) f[i] = 0.0; return; }
+  double X[6];
+  if (W.cas == 2)
+   { const double y1 = y[0], y2 = y[1]; double u1, u2, xi2;
+#define TDG_XE(d) X[d] = sqrt(u1 * u1 * W.A2 + u2 * u2 * W.BP2 + xi2 * xi2 * W.L2 + 2.0 * (u1 * (u2 * W.AdBP + xi2 * W.AdL) + u2 * xi2 * W.BPdL))
+     u1 = -y1;      u2 = -y1 * y2;         xi2 = (1.0 - y1 + y1 * y2); TDG_XE(0);
+     u1 = y1;       u2 = y1 * y2;          xi2 = (1.0 - y1);           TDG_XE(1);
+     u1 = -y1 * y2; u2 = y1 * (1.0 - y2);  xi2 = (1.0 - y1);           TDG_XE(2);
+     u1 = y1 * y2;  u2 = -y1 * (1.0 - y2); xi2 = (1.0 - y1 * y2);      TDG_XE(3);
+     u1 = -y1 * y2; u2 = -y1;              xi2 = 1.0;                  TDG_XE(4);
+     u1 = y1 * y2;  u2 = y1;               xi2 = (1.0 - y1);           TDG_XE(5);
+#undef TDG_XE
+   }
+  else
+   { const double y1 = y[0], y2 = y[1], y3 = y[2]; double xi1, xi2, eta1, eta2;
+#define TDG_XV(d) X[d] = sqrt(xi1 * xi1 * W.A2 + xi2 * xi2 * W.B2 + eta1 * eta1 * W.AP2 + eta2 * eta2 * W.BP2 \
+                              + 2.0 * xi1 * (xi2 * W.AdB - eta1 * W.AdAP - eta2 * W.AdBP) - 2.0 * xi2 * (eta1 * W.BdAP + eta2 * W.BdBP) \
+                              + 2.0 * eta1 * eta2 * W.APdBP)
+     xi1 = 1.0; xi2 = y1;      eta1 = y2;  eta2 = y2 * y3; TDG_XV(0);
+     xi1 = y2;  xi2 = y2 * y3; eta1 = 1.0; eta2 = y1;      TDG_XV(1);
+#undef TDG_XV
+   }
+  // ExpRel table per region for the union of the n ranges: HELMHOLTZ needs n in [nMin+nOff, nMax+nOff] of P slots 0,1;
+  // GRADHELMHOLTZ needs n-2 .. n-1 of slot 2
+  int lo = 99, hi = -1;
+  for (int np = 0; np < 2; np++) if (W.nMax[np] >= W.nMin[np]) { lo = min(lo, W.nMin[np] + nOff); hi = max(hi, W.nMax[np] + nOff); }
+  if (W.nMax[2] >= W.nMin[2]) { lo = min(lo, W.nMin[2] + nOff - 2); hi = max(hi, W.nMax[2] + nOff - 1); }
+  if (lo < 0) lo = 0;
+  const cd IK = mk(-W.k.y, W.k.x);
+  cd E[6][9], eIKXv[6];
+  for (int d = 0; d < NR; d++)
+   { cd IKX = mk(IK.x * X[d], IK.y * X[d]), mIKX = mk(-IKX.x, -IKX.y);
+     eIKXv[d] = cexp_(IKX);
+     const bool small = (mIKX.y == 0.0) ? (fabs(mIKX.x) < 0.1) : (cabs_(mIKX) < 0.1);
+     cd emIKX = mk(0.0, 0.0);
+     if (!small) emIKX = (mIKX.y == 0.0) ? mk(exp(mIKX.x), 0.0) : cexp_(mIKX);
+     for (int n = lo; n <= hi && n < 9; n++) E[d][n] = exprel_v3p0_pre(n, mIKX, emIKX, small);
+   }
+  for (int npk = 0; npk < 3; npk++)
+   { const int nMin = W.nMin[npk], nMax = W.nMax[npk];
+     cd Sum = mk(0.0, 0.0);
+     for (int n = nMin; n <= nMax; n++)
+      for (int d = 0; d < NR; d++)
+       { const double *Up = W.U[npk][d][n];
+         double P0, P1;
+         if (W.cas == 2)
+          { const double y1 = y[0], y12 = y1 * y1;
+            P0 = Up[M_1] + Up[M_Y1] * y1 + Up[M_Y12] * y12;
+            P1 = Up[M_Y2] + Up[M_Y1Y2] * y1 + Up[M_Y12Y2] * y12; }
+         else
+          { const double y1 = y[0], y12 = y1 * y1, y2 = y[1], y22 = y2 * y2;
+            P0 = Up[M_1] + Up[M_Y1] * y1 + Up[M_Y2] * y2 + Up[M_Y12] * y12 + Up[M_Y1Y2] * y1 * y2 + Up[M_Y22] * y22
+                 + Up[M_Y12Y2] * y12 * y2 + Up[M_Y1Y22] * y1 * y22;
+            P1 = Up[M_Y2Y3] * y2 + Up[M_Y1Y2Y3] * y1 * y2 + Up[M_Y22Y3] * y22 + Up[M_Y12Y2Y3] * y12 * y2; }
+         const int nn = n + nOff;
+         cd Kv;
+         if (npk < 2)      // TD_HELMHOLTZ: e^{ikX} ExpRel(n,-ikX) / (n X)
+          { cd t = eIKXv[d] * E[d][nn]; const double dn = nn * X[d]; Kv = mk(t.x / dn, t.y / dn); }
+         else              // TD_GRADHELMHOLTZ
+          { cd t1 = IK * E[d][nn - 1]; const double d1 = (double)nn - 1.0; t1 = mk(t1.x / d1, t1.y / d1);
+            const double d2 = ((double)nn - 2.0) * X[d]; cd t2 = mk(E[d][nn - 2].x / d2, E[d][nn - 2].y / d2);
+            cd t = eIKXv[d] * (t1 - t2); const double xx = X[d] * X[d]; Kv = mk(t.x / xx, t.y / xx); }
+         Sum += (P0 + yInner * P1) * Kv;
+       }
+     const double s = Jac / (4.0 * M_PI);
+     f[2 * npk] = Sum.x * s; f[2 * npk + 1] = Sum.y * s;
+   }
+}
+
+// ---- p-adaptive tensor Clenshaw-Curtis cubature over [0,1]^DIM (pcubature.c) ----
+struct PCEnt { unsigned char m[3]; signed char mi; int off; int cnt[3]; };
+
+template <int DIM>
+__device__ __forceinline__ double pc_weight(const TDTables &T, const PCEnt &e, int d, int li, int Md)
+{ // weight of local point li of entry e along dimension d for a rule of level Md (Md < 0: trivial midpoint rule)
+  int pairIdx;
+  if (d != e.mi)
+   { if (li == 0) return (Md < 0) ? 2.0 : T.ccw[Md + (1 << Md) - 1];
+     pairIdx = (li - 1) >> 1; }
+  else
+   { const int lo = e.m[d] ? (1 << (e.m[d] - 1)) : 0;
+     pairIdx = lo + (li >> 1); }
+  if (Md < 0 || pairIdx >= (1 << Md)) return 0.0;
+  return T.ccw[Md + (1 << Md) - 1 + 1 + pairIdx];
+}
+
+template <int DIM>
+__device__ __forceinline__ double pc_coord(const TDTables &T, const PCEnt &e, int d, int li)
+{ if (d != e.mi)
+   { if (li == 0) return 0.5;
+     const int i = (li - 1) >> 1; return ((li - 1) & 1) ? 0.5 - 0.5 * T.ccx[i] : 0.5 + 0.5 * T.ccx[i]; }
+  const int lo = e.m[d] ? (1 << (e.m[d] - 1)) : 0; const int i = lo + (li >> 1);
+  return (li & 1) ? 0.5 - 0.5 * T.ccx[i] : 0.5 + 0.5 * T.ccx[i];
+}
+
+// integral of the rule with levels M[] (M[md] decremented when md < DIM) from the cached values
+template <int DIM>
+__device__ void pc_evals(const TDTables &T, const PCEnt *ent, int nEnt, const int *m, int md, const double *cache, size_t stride, double *val)
+{ for (int j = 0; j < TDG_FDIM; j++) val[j] = 0.0;
+  int M[3];
+  for (int d = 0; d < DIM; d++) M[d] = m[d] - (d == md ? 1 : 0);
+  double V = 1.0; for (int d = 0; d < DIM; d++) V *= 0.5;
+  for (int ie = 0; ie < nEnt; ie++)
+   { const PCEnt &e = ent[ie];
+     if (!(e.mi >= DIM || (int)e.m[e.mi] + (e.mi == md ? 1 : 0) <= m[e.mi])) continue;
+     const int n0 = e.cnt[0], n1 = DIM > 1 ? e.cnt[1] : 1, n2 = DIM > 2 ? e.cnt[2] : 1;
+     int q = 0;
+     for (int i0 = 0; i0 < n0; i0++)
+      { const double w0 = V * pc_weight<DIM>(T, e, 0, i0, M[0]);
+        if (w0 == 0.0) { q += n1 * n2; continue; }
+        for (int i1 = 0; i1 < n1; i1++)
+         { const double w1 = DIM > 1 ? w0 * pc_weight<DIM>(T, e, 1, i1, M[1]) : w0;
+           if (w1 == 0.0) { q += n2; continue; }
+           for (int i2 = 0; i2 < n2; i2++, q++)
+            { const double w = DIM > 2 ? w1 * pc_weight<DIM>(T, e, 2, i2, M[2]) : w1;
+              if (w == 0.0) continue;
+              const double *cv = cache + (size_t)(e.off + q) * TDG_FDIM * stride;
+              for (int j = 0; j < TDG_FDIM; j++) val[j] += cv[(size_t)j * stride] * w;
+            }
+         }
+      }
+   }
+}
+
+template <int DIM>
+__device__ int pc_add_entry(const TDTables &T, const TDGen &W, PCEnt *ent, int &nEnt, int &nPts, const int *m, int mi,
+                            double *cache, size_t stride)
+{ if (nEnt >= TDG_MAXENT) return 2;
+  PCEnt &e = ent[nEnt];
+  for (int d = 0; d < 3; d++) { e.m[d] = d < DIM ? (unsigned char)m[d] : 0; e.cnt[d] = 1; }
+  e.mi = (signed char)mi; e.off = nPts;
+  int total = 1;
+  for (int d = 0; d < DIM; d++)
+   { e.cnt[d] = (d == mi) ? (m[d] == 0 ? 2 : (1 << m[d])) : ((1 << (m[d] + 1)) + 1);
+     total *= e.cnt[d]; }
+  if (nPts + total > TDG_MAXPTS) return 2;
+  const int n0 = e.cnt[0], n1 = DIM > 1 ? e.cnt[1] : 1, n2 = DIM > 2 ? e.cnt[2] : 1;
+  int q = 0; double y[3] = { 0.0, 0.0, 0.0 }, f[TDG_FDIM];
+  for (int i0 = 0; i0 < n0; i0++)
+   { y[0] = pc_coord<DIM>(T, e, 0, i0);
+     for (int i1 = 0; i1 < n1; i1++)
+      { if (DIM > 1) y[1] = pc_coord<DIM>(T, e, 1, i1);
+        for (int i2 = 0; i2 < n2; i2++, q++)
+         { if (DIM > 2) y[2] = pc_coord<DIM>(T, e, 2, i2);
+           tdg_integrand(W, y, f);
+           double *cv = cache + (size_t)(nPts + q) * TDG_FDIM * stride;
+           for (int j = 0; j < TDG_FDIM; j++) cv[(size_t)j * stride] = f[j];
+         }
+      }
+   }
+  nPts += total; nEnt++;
+  return 0;
+}
+
+template <int DIM>
+__device__ int pcubature_nd(const TDTables &T, const TDGen &W, double relTol, double absTol, int maxEval,
+                            double *cache, size_t stride, double val[TDG_FDIM], double err[TDG_FDIM])
+{ PCEnt ent[TDG_MAXENT]; int nEnt = 0, nPts = 0, numEval = 0;
+  int m[3] = { 0, 0, 0 };
+  int st = pc_add_entry<DIM>(T, W, ent, nEnt, nPts, m, DIM, cache, stride);
+  if (st) return st;
+  for (;;)
+   { pc_evals<DIM>(T, ent, nEnt, m, DIM, cache, stride, val);
+     for (int j = 0; j < TDG_FDIM; j++) err[j] = 0.0;
+     int mi = 0; double maxerr = 0.0;
+     for (int i = 0; i < DIM; i++)
+      { double val1[TDG_FDIM], emax = 0.0;
+        pc_evals<DIM>(T, ent, nEnt, m, i, cache, stride, val1);
+        for (int j = 0; j < TDG_FDIM; j++)
+         { const double e = fabs(val[j] - val1[j]);
+           if (e > emax) emax = e;
+           if (e > err[j]) err[j] = e; }
+        if (emax > maxerr) { maxerr = emax; mi = i; }
+      }
+     bool conv = true;
+     for (int j = 0; j < TDG_FDIM; j++) if (err[j] > absTol && err[j] > fabs(val[j]) * relTol) { conv = false; break; }
+     if (conv || (numEval > maxEval && maxEval)) return 0;
+     m[mi] += 1;
+     if (m[mi] > SC_TD_MAXLEVEL) return 1;
+     int newPts = 1;
+     for (int d = 0; d < DIM; d++) newPts *= (d == mi) ? (1 << m[d]) : ((1 << (m[d] + 1)) + 1);
+     st = pc_add_entry<DIM>(T, W, ent, nEnt, nPts, m, mi, cache, stride);
+     if (st) return st;
+     numEval += newPts;
+   }
+}
+
+// items[t] = 18*nearIndex + 9*swapped + 3*i + j
+__global__ void __launch_bounds__(64)
+td_general_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, double *scratch, int *itemStatus)
+{ const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nItems) return;
+  const int item = items[t];
+  const NearPair N = A.near[item / 18];
+  const int swapped = (item % 18) / 9, i = (item % 9) / 3, j = item % 3;
+  const PanelRec &Pa = A.pa[N.pa], &Pb = A.pb[N.pb];
+  const int ea = Pa.ei[i], eb = Pb.ei[j];
+  double Va[9], Vb[9];
+  for (int q = 0; q < 9; q++) { Va[q] = Pa.V[q]; Vb[q] = A.useDisp ? (Pb.V[q] + 1.0 * A.L[q % 3]) : Pb.V[q]; }
+  const double *V1, *V2, *V3, *V2P, *V3P, *Q, *QP; int ncv = N.ncv;
+  if (!swapped)
+   { V1 = Va + 3 * N.ia[0]; V2 = Va + 3 * N.ia[1]; V3 = Va + 3 * N.ia[2]; V2P = Vb + 3 * N.ib[1]; V3P = Vb + 3 * N.ib[2];
+     Q = Va + 3 * i; QP = Vb + 3 * j; }
+  else
+   { // the reference evaluates PPI(pb,pa) for this entry: AssessPanelPair with the panels exchanged
+     unsigned char ja[3], jb[3];
+     ncv = assess_vertices(Vb, Va, fmax(Pa.R, Pb.R), ja, jb);
+     V1 = Vb + 3 * ja[0]; V2 = Vb + 3 * ja[1]; V3 = Vb + 3 * ja[2]; V2P = Va + 3 * jb[1]; V3P = Va + 3 * jb[2];
+     Q = Vb + 3 * j; QP = Va + 3 * i; }
+  TDGen W;
+  const cd k = mk(A.K.kr, A.K.ki);
+  tdg_setup(T, ncv, V1, V2, V3, V2P, V3P, Q, QP, k, W);
+  double val[TDG_FDIM], err[TDG_FDIM];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  int st = (ncv == 2) ? pcubature_nd<2>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err)
+                      : pcubature_nd<3>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
+  itemStatus[t] = st;
+  if (st) return;
+  const cd R0 = mk(val[0], val[1]), R1 = mk(val[2], val[3]), R2 = mk(val[4], val[5]);
+  const cd k2 = k * k;
+  cd H0 = R1 - cdiv(mk(4.0 * R0.x, 4.0 * R0.y), k2), H1 = R2;
+  // a diagonal edge pair (ea == eb, pa != pb) of a symmetric block receives PPI(pa,pb) + PPI(pb,pa): both orders are
+  // separate items, scatter_ppi would double each
+  if (A.S.symmetric && N.pa != N.pb && ea == eb) { H0 = 0.5 * H0; H1 = 0.5 * H1; }
+  scatter_ppi(A.S, A.K, N.pa, N.pb, ea, eb, Pa.sl[i], Pb.sl[j], H0, H1);
+  atomicAdd(A.counters + 2, 1ull);
+}
+
+int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T, const int *items, int nItems)
+{ if (nItems <= 0) return 0;
+  // capacity: 27 initial points + at most MaxEval (1000) before the last refinement + the last increment (< what is
+  // already there) -> TDG_MAXPTS points x 6 doubles per item; items are processed in batches
+  const size_t perItem = (size_t)TDG_MAXPTS * TDG_FDIM * sizeof(double);
+  const int batch = std::min(nItems, 8192);
+  const int threads = ((batch + 63) / 64) * 64;
+  const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
+  const size_t need = hdr + (size_t)threads * perItem;
+  if (need > ctx->scratchBytes)
+   { if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
+     if (cudaMalloc(&ctx->dscratch, need) != cudaSuccess) { cudaGetLastError(); ctx->err = "Taylor-Duffy scratch allocation failed"; return 1; }
+     ctx->scratchBytes = need; }
+  int *dItems = (int *)ctx->dscratch, *dStatus = dItems + batch;
+  double *scr = (double *)((char *)ctx->dscratch + hdr);
+  std::vector<int> status(batch);
+  for (int first = 0; first < nItems; first += batch)
+   { const int n = std::min(batch, nItems - first);
+     cudaMemcpyAsync(dItems, items + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+     ctx->launches++;
+     td_general_kernel<<<threads / 64, 64, 0, ctx->stream>>>(A, T, dItems, n, scr, dStatus);
+     cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+     cudaError_t e = cudaStreamSynchronize(ctx->stream);
+     if (e != cudaSuccess) { ctx->err = std::string("td_general_kernel: ") + cudaGetErrorString(e); return 1; }
+     for (int q = 0; q < n; q++)
+      if (status[q]) { ctx->err = status[q] == 1 ? "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"
+                                                 : "Taylor-Duffy cubature exceeded its function-value cache"; return 1; }
+   }
+  return 0;
+}
+
+}  // namespace scuffcuda

@@ -7,6 +7,7 @@
 #include "kernels.h"
 #include "stamp.cuh"
 #include "td_math.cuh"
+#include "sw_kernels.h"
 #include "generated_tables.h"
 
 namespace scuffcuda {
@@ -62,24 +63,35 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
 { (void)kmode;
   // classify on the host (cheap: O(#near pairs)): which pairs need Taylor-Duffy / high-order cubature
   const Surface &Sa = ctx->surfaces[P.nsa], &Sb = ctx->surfaces[P.nsb];
-  std::vector<int> items;
+  std::vector<int> items, hoIdx, genItems;
   for (int n = 0; n < P.nNear; n++)
    { const NearPair &N = P.hnear[n]; bool verySW;
      int alg = near_algorithm(N.ncv, A.kabs, Sa.hpanels[N.pa].R, Sb.hpanels[N.pb].R, A.forceTD, verySW);
      if (alg == 4) continue;
-     if (alg == 2 && N.ncv == 3 && !verySW)
-      { // the (Q_a,Q_b) combinations that feed a matrix entry
-        const PanelRec &Pa = Sa.hpanels[N.pa], &Pb = Sb.hpanels[N.pb];
-        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
-         { const int ea = Pa.ei[i], eb = Pb.ei[j];
-           if (ea < 0 || eb < 0) continue;
-           if (A.S.symmetric && N.pa == N.pb && ea > eb) continue;
+     if (alg == 1) { hoIdx.push_back(n); continue; }                  // high-order cubature
+     if (alg == 2 && verySW)
+      { ctx->err = "very-short-wavelength regime (|k|*panel radius > 20): high-k Taylor-Duffy is not yet available on the device path";
+        return 1; }
+     // the (Q_a,Q_b) combinations that feed a matrix entry
+     const PanelRec &Pa = Sa.hpanels[N.pa], &Pb = Sb.hpanels[N.pb];
+     for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+      { const int ea = Pa.ei[i], eb = Pb.ei[j];
+        if (ea < 0 || eb < 0) continue;
+        if (N.ncv == 3)
+         { if (A.S.symmetric && N.pa == N.pb && ea > eb) continue;
            items.push_back(9 * n + 3 * i + j); }
-        continue; }
-     ctx->err = "short-wavelength regime (|k|*panel radius > pi) or SCUFF_DISABLE_CACHE: high-order cubature / "
-                "common-edge and common-vertex Taylor-Duffy are not yet available on the device path";
-     return 1;
+        else if (!A.S.symmetric) genItems.push_back(18 * n + 3 * i + j);
+        else
+         { // symmetric block, pa < pb visited once: entry (min,max)(ea,eb) is EEI(nea<=neb), whose panel order decides
+           // which of PPI(pa,pb) / PPI(pb,pa) the reference evaluates; a diagonal edge pair gets both
+           if (ea <= eb) genItems.push_back(18 * n + 3 * i + j);
+           if (ea >= eb) genItems.push_back(18 * n + 9 + 3 * i + j); }
+      }
    }
+  if (run_ho(ctx, A, hoIdx.data(), (int)hoIdx.size(), kmode)) return 1;
+  if (!genItems.empty())
+   { TDTables TG; if (td_tables(ctx, TG)) return 1;
+     if (run_td_general(ctx, A, TG, genItems.data(), (int)genItems.size())) return 1; }
   if (items.empty()) return 0;
   TDTables T; if (td_tables(ctx, T)) return 1;
   // pass 0: every item at once with room for Clenshaw-Curtis levels <= 6 (129 points; the common case),
