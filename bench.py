@@ -29,7 +29,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.join(ROOT, "scuff-em_b200")
 REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-FLOP_PER_POINT_PAIR = 97          # one kernel evaluation at one cubature point pair
+# one kernel evaluation at one cubature point pair = 97 flop for the full (Phi and Psi) evaluation the
+# PMCHWT blocks need; PEC/PEC blocks stamp GC[0] only, their kernel variant drops Psi (9) and the Psi-moment half (34)
+FLOP_PER_POINT_PAIR = {"pec": 54, "dielectric": 97}
 POINT_PAIRS = 36                  # 6x6 rule
 METRIC = "bem_assembly_gelements_per_s"
 UNIT = "G-elements/s"
@@ -42,10 +44,10 @@ def _load(name, path):
     return mod
 
 
-def make_mesh(nu, rank):
+def make_mesh(nu, rank, material=None):
     meshgen = _load("meshgen", os.path.join(PKG, "meshgen.py"))
     d = os.path.join(tempfile.gettempdir(), "scuff_b200_bench_rank%d" % rank)
-    return meshgen.write_sphere_geo(d, nu)
+    return meshgen.write_sphere_geo(d, nu, material)
 
 
 class ClockSampler(threading.Thread):
@@ -127,6 +129,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nu", type=int, default=26, help="icosphere frequency: 30 nu^2 RWG edges (26 -> 20280)")
     ap.add_argument("--omega", type=float, default=1.0)
+    ap.add_argument("--material", default=None, help="e.g. CONST_EPS_10: PMCHWT dielectric sphere (2N x 2N matrix) instead of PEC")
     ap.add_argument("--ref-pairs", type=int, default=2000000)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-lu", action="store_true")
@@ -156,7 +159,7 @@ def main():
 
     ps = _load("pyscuff", os.path.join(PKG, "pyscuff.py"))
     ps.set_device(local)
-    geo = make_mesh(a.nu, rank)
+    geo = make_mesh(a.nu, rank, a.material)
     G = ps.RWGGeometry(geo)
     N, P = G.TotalBFs, G.TotalPanels
     M = G.AllocateBEMMatrix()
@@ -221,21 +224,25 @@ def main():
         return 0
 
     t_far = sum(far_ms) / len(far_ms) * 1e-3
-    flops = FLOP_PER_POINT_PAIR * POINT_PAIRS * float(far_pairs)
+    kind = "dielectric" if a.material else "pec"
+    fpp = FLOP_PER_POINT_PAIR[kind]
+    flops = fpp * POINT_PAIRS * float(far_pairs)
     achieved = flops / t_far / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": 1e3 * elapsed / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "icosphere PEC N=%d edges (nu=%d, %d panels), omega=%g..: AssembleBEMMatrix, complex128 %dx%d (%.2f GB) resident in HBM"
-                                   % (N, a.nu, P, a.omega, N, N, 16.0 * N * N / 1e9),
+            "config": {"workload": "icosphere %s %d edges (nu=%d, %d panels), omega=%g..: AssembleBEMMatrix, complex128 %dx%d (%.2f GB) resident in HBM"
+                                   % (a.material or "PEC", G.TotalEdges, a.nu, P, a.omega, N, N, 16.0 * N * N / 1e9),
                        "sharding": "frequency points round-robin over ranks, no data-path collective" if world > 1 else "single GPU",
                        "l2": "each step writes the %.1f GB matrix (>> 126 MB L2), no flush needed" % (16.0 * N * N / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (tb1[0] - tb0[0]) // a.e2e_steps,
                     "d2h_bytes_per_step": (tb1[1] - tb0[1]) // a.e2e_steps, "steps": a.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / a.e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "far_kernel<KMODE_REAL>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "far_kernel<KMODE_REAL,%s>" % ("PSI" if a.material else "PEC"), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": None,
-                         "algorithmic": "%d flop/point pair x %d point pairs x %d far panel pairs per launch" % (FLOP_PER_POINT_PAIR, POINT_PAIRS, far_pairs),
+                         "algorithmic": "%d flop/point pair (SURVEY 8d: 97 full, 54 for the PEC variant without the Psi half) x %d point pairs x %d far panel "
+                                        "pairs per step (%d launch(es))" % (fpp, POINT_PAIRS, far_pairs, 2 if a.material else 1),
+                         "achieved_at_97": 97.0 * POINT_PAIRS * float(far_pairs) / t_far / 1e12,
                          "kernel_ms": 1e3 * t_far,
                          "peak_source": "in-run DFMA microkernel (scuffcuda_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry"},
             "breakdown_ms": {"total_device": sum(tot_ms) / len(tot_ms), "far_kernel": 1e3 * t_far, "near_singular": sum(near_ms) / len(near_ms),
@@ -261,7 +268,7 @@ def main():
             line["lu"] = {"error": str(e)[:200]}
 
     # ---- CPU baseline beside it + full-size parity on the sampled entries ----
-    if world == 1 and not a.no_cpu_baseline and os.path.exists(REF_DRIVER):
+    if world == 1 and not a.no_cpu_baseline and not a.material and os.path.exists(REF_DRIVER):
         out = os.path.join(tempfile.gettempdir(), "scuff_ref_sample_rank0.bin")
         info = run_reference_sample(geo, complex(a.omega), a.ref_pairs, 7, 2, out)
         rec = np.fromfile(out).reshape(-1, 6)

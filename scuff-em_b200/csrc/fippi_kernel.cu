@@ -6,7 +6,7 @@
 #include <vector>
 #include <algorithm>
 #include "kernels.h"
-#include "fippi_integrands.cuh"
+#include "fippi_build.cuh"
 #include "generated_tables.h"
 
 namespace scuffcuda {
@@ -32,38 +32,6 @@ static int fippi_tables(scuffcuda_context *ctx, FIPPITables &T)
   return 0;
 }
 
-#define FIPPI_REGION_BYTES 608   /* >= sizeof(HCRegion<3>) */
-static_assert(sizeof(HCRegion<3>) <= FIPPI_REGION_BYTES, "region size");
-
-// verts: 18 doubles per item (OVa[0..2], OVb[0..2]); out: 36 doubles per item; status: per item
-__global__ void __launch_bounds__(64)
-fippi_build_kernel(const FIPPITables T, const double *verts, const int *ncvs, const int *items, int nItems,
-                   char *pool, int capacity, double *out, int *status)
-{ const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nItems) return;
-  const int it = items[t];
-  const double *V = verts + 18 * (size_t)it;
-  const double *OVa[3] = { V, V + 3, V + 6 }, *OVb[3] = { V + 9, V + 12, V + 15 };
-  char *mypool = pool + (size_t)t * ((size_t)capacity * (FIPPI_REGION_BYTES + sizeof(int)));
-  int *heap = (int *)(mypool + (size_t)capacity * FIPPI_REGION_BYTES);
-  double val[HC_FDIM], err[HC_FDIM];
-  int st;
-  if (ncvs[it] == 0)
-   { CFD3D f; f.setup(OVa, OVb);
-     st = hcubature_run<3>(f, 1000000, 1.0e-10, 1.0e-6, (HCRegion<3> *)mypool, heap, capacity, val, err);
-   }
-  else
-   { TDFIPPI f; f.setup(&T, OVa[0], OVa[1], OVa[2], OVb[1], OVb[2]);
-     if (f.commonEdge) st = hcubature_run<1>(f, 10000, 0.0, 1.0e-5, (HCRegion<1> *)mypool, heap, capacity, val, err);
-     else              st = hcubature_run<2>(f, 10000, 0.0, 1.0e-5, (HCRegion<2> *)mypool, heap, capacity, val, err);
-   }
-  status[t] = st;
-  if (st) return;
-  double *o = out + FIPPI_REC_DOUBLES * (size_t)it;
-  for (int j = 0; j < HC_FDIM; j++) o[j] = val[j];
-  for (int m = 0; m < 3; m++) o[33 + m] = (OVa[0][m] + OVa[1][m] + OVa[2][m]) / 3.0;
-}
-
 int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds, const std::vector<double> &verts,
                           const std::vector<int> &ncvs)
 { const int n = (int)recIds.size();
@@ -78,7 +46,19 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
   cudaMemcpy(dverts, verts.data(), (size_t)n * 18 * sizeof(double), cudaMemcpyHostToDevice);
   cudaMemcpy(dncv, ncvs.data(), n * sizeof(int), cudaMemcpyHostToDevice);
 
-  std::vector<int> todo(n); for (int i = 0; i < n; i++) todo[i] = i;
+  // integration case of every record: 0 no common vertex (3-D), 1 common edge (1-D), 2 common vertex (2-D); the
+  // common-edge test is the float comparison of V2 and V2' that the integrand setup makes (fippi_integrands.cuh)
+  std::vector<int> byCase[3];
+  for (int i = 0; i < n; i++)
+   { const double *V = &verts[18 * (size_t)i];
+     int c = 0;
+     if (ncvs[i] != 0)
+      c = (((float)V[3] == (float)V[12]) && ((float)V[4] == (float)V[13]) && ((float)V[5] == (float)V[14])) ? 1 : 2;
+     byCase[c].push_back(i); }
+  const fippi_launch_fn launchers[3] = { fippi_launch_case0, fippi_launch_case1, fippi_launch_case2 };
+  std::vector<int> todo;
+  for (int c = 0; c < 3; c++)
+   { todo = byCase[c];
   // pass 1: small region pools, many records in flight; pass 2: the few records that need more regions
   const int caps[3] = { 384, 4096, 15200 }; const int batches[3] = { 24576, 2048, 512 };
   for (int pass = 0; pass < 3 && !todo.empty(); pass++)
@@ -91,13 +71,17 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
       { int m = (int)std::min((size_t)batch, todo.size() - first);
         cudaMemcpyAsync(ditems, todo.data() + first, m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
         ctx->launches++;
-        fippi_build_kernel<<<(m + 63) / 64, 64, 0, ctx->stream>>>(T, dverts, dncv, ditems, m, dpool, cap, dout, dstatus);
+        launchers[c](ctx->stream, T, dverts, ditems, m, dpool, cap, dout, dstatus);
         cudaMemcpyAsync(st.data(), dstatus, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->err = std::string("fippi_build_kernel: ") + cudaGetErrorString(e); cleanup(); return 1; }
-        for (int i = 0; i < m; i++) if (st[i]) next.push_back(todo[first + i]);
+        for (int i = 0; i < m; i++)
+         { if (st[i] == 3) { ctx->err = "FIPPI builder: integration case mismatch"; cleanup(); return 1; }
+           if (st[i]) next.push_back(todo[first + i]); }
       }
      todo.swap(next);
+   }
+     if (!todo.empty()) break;
    }
   if (!todo.empty()) { ctx->err = "FIPPI builder: region pool exhausted"; cleanup(); return 1; }
   std::vector<double> hout((size_t)n * FIPPI_REC_DOUBLES);

@@ -63,7 +63,23 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
 { (void)kmode;
   // classify on the host (cheap: O(#near pairs)): which pairs need Taylor-Duffy / high-order cubature
   const Surface &Sa = ctx->surfaces[P.nsa], &Sb = ctx->surfaces[P.nsb];
-  std::vector<int> items, hoIdx, genItems;
+  // The algorithm of a near pair depends on the frequency only through the short-wavelength tests |k| R > pi, 20
+  // (near_algorithm).  While |k| * (largest panel radius) <= pi no pair can switch, so the item lists of the previous
+  // frequency point of the sweep are reused (they are O(#near pairs) host work otherwise).
+  struct ListCache { bool valid = false; uint64_t genA = 0, genB = 0; int nsa = -1, nsb = -1, forceTD = 0, nNear = 0; bool symmetric = false, useDisp = false;
+                     double L[3] = { 0, 0, 0 }; std::vector<int> items, hoIdx, genItems; };
+  static ListCache g_cache[64];
+  ListCache &C = g_cache[ctx->device & 63];
+  double Rmax = 0.0;
+  for (const PanelRec &Q : Sa.hpanels) Rmax = std::max(Rmax, Q.R);
+  for (const PanelRec &Q : Sb.hpanels) Rmax = std::max(Rmax, Q.R);
+  const bool noSW = !(A.kabs * Rmax > SW_THRESHOLD);
+  const bool reuse = C.valid && noSW && C.genA == P.genA && C.genB == P.genB && C.nsa == P.nsa && C.nsb == P.nsb && C.forceTD == A.forceTD
+                     && C.nNear == P.nNear && C.symmetric == P.symmetric && C.useDisp == P.useDisp
+                     && C.L[0] == P.L[0] && C.L[1] == P.L[1] && C.L[2] == P.L[2];
+  std::vector<int> &items = C.items, &hoIdx = C.hoIdx, &genItems = C.genItems;
+  if (!reuse)
+   { C.valid = false; items.clear(); hoIdx.clear(); genItems.clear();
   for (int n = 0; n < P.nNear; n++)
    { const NearPair &N = P.hnear[n]; bool verySW;
      int alg = near_algorithm(N.ncv, A.kabs, Sa.hpanels[N.pa].R, Sb.hpanels[N.pb].R, A.forceTD, verySW);
@@ -88,29 +104,33 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
            if (ea >= eb) genItems.push_back(18 * n + 9 + 3 * i + j); }
       }
    }
+     C.valid = noSW; C.genA = P.genA; C.genB = P.genB; C.nsa = P.nsa; C.nsb = P.nsb; C.forceTD = A.forceTD; C.nNear = P.nNear;
+     C.symmetric = P.symmetric; C.useDisp = P.useDisp; for (int q = 0; q < 3; q++) C.L[q] = P.L[q];
+   }
   if (run_ho(ctx, A, hoIdx.data(), (int)hoIdx.size(), kmode)) return 1;
   if (!genItems.empty())
    { TDTables TG; if (td_tables(ctx, TG)) return 1;
      if (run_td_general(ctx, A, TG, genItems.data(), (int)genItems.size())) return 1; }
   if (items.empty()) return 0;
   TDTables T; if (td_tables(ctx, T)) return 1;
+  std::vector<int> work(items);
   // pass 0: every item at once with room for Clenshaw-Curtis levels <= 6 (129 points; the common case),
   // pass 1: the items that asked for more, with the full MaxEval=1000 budget (level 9, 1025 points), in batches
   const int passM[2] = { 6, 9 }, passBatch[2] = { 1 << 30, 32768 };
   std::vector<int> status;
-  for (int pass = 0; pass < 2 && !items.empty(); pass++)
+  for (int pass = 0; pass < 2 && !work.empty(); pass++)
    { const int maxM = passM[pass];
      const size_t perItem = (size_t)4 * ((1u << (maxM + 1)) + 1) * sizeof(double);   // level m holds 2^(m+1)+1 points
-     const int batch = (int)std::min<size_t>(items.size(), (size_t)passBatch[pass]);
+     const int batch = (int)std::min<size_t>(work.size(), (size_t)passBatch[pass]);
      const int threads = ((batch + 127) / 128) * 128;
      const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
      if (td_grow_scratch(ctx, hdr + (size_t)threads * perItem)) return 1;
      int *dItems = (int *)ctx->dscratch, *dStatus = dItems + batch;
      double *scr = (double *)((char *)ctx->dscratch + hdr);
      std::vector<int> next;
-     for (size_t first = 0; first < items.size(); first += batch)
-      { const int n = (int)std::min<size_t>(batch, items.size() - first);
-        cudaMemcpyAsync(dItems, items.data() + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+     for (size_t first = 0; first < work.size(); first += batch)
+      { const int n = (int)std::min<size_t>(batch, work.size() - first);
+        cudaMemcpyAsync(dItems, work.data() + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
         ctx->launches++;
         // the grid always spans `threads` threads so that the scratch stride is fixed
         td_ct_kernel<<<threads / 128, 128, 0, ctx->stream>>>(A, T, dItems, n, scr, maxM, dStatus);
@@ -118,11 +138,11 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
         cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         if (e != cudaSuccess) { ctx->err = std::string("td_ct_kernel: ") + cudaGetErrorString(e); return 1; }
-        for (int q = 0; q < n; q++) if (status[q]) next.push_back(items[first + q]);
+        for (int q = 0; q < n; q++) if (status[q]) next.push_back(work[first + q]);
       }
-     items.swap(next);
+     work.swap(next);
    }
-  if (!items.empty()) { ctx->err = "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"; return 1; }
+  if (!work.empty()) { ctx->err = "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"; return 1; }
   return 0;
 }
 

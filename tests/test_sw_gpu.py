@@ -31,12 +31,12 @@ def test_short_wavelength_matrix(ps, name, omega, imag, tmp_path):
     assert max(errs.values()) <= TOL
 
 
-def test_disable_cache_forces_taylor_duffy(ps):
+def test_disable_cache_forces_taylor_duffy(ps, monkeypatch):
     """RWGGeometry::DisableCache (env SCUFF_DISABLE_CACHE in the reference, RWGGeometry.cc:402)"""
     geo = os.path.join(GEODIR, "PECSphere_255.scuffgeo")
     omega = 1.0
     Mref, _ = ref_matrix(geo, omega, env={"SCUFF_DISABLE_CACHE": "1"})
-    ps.host_lib().scuffb200_set_disable_cache(1)
+    monkeypatch.setenv("SCUFF_DISABLE_CACHE", "1")       # read by the RWGGeometry constructor, as in the reference
     try:
         G = ps.RWGGeometry(geo)
         M = G.AssembleBEMMatrix(omega).array
