@@ -245,6 +245,19 @@ int scuffcuda_lu_solve(scuffcuda_context *ctx, int h, void *rhs, int nrhs)
 // ------------------------------------------------------------------------------------------
 // assembly
 // ------------------------------------------------------------------------------------------
+// second, high-priority stream per context for the near/singular kernels: they are latency-bound (one thread per
+// adaptive cubature) and overlap with the FP64-bound far kernel; both scatter with atomics into the same matrix
+static cudaStream_t near_stream(scuffcuda_context *ctx)
+{ static std::map<scuffcuda_context *, cudaStream_t> streams;
+  auto it = streams.find(ctx);
+  if (it != streams.end()) return it->second;
+  int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); s = ctx->stream; }
+  streams[ctx] = s;
+  return s;
+}
+
 static cdouble csqrt2(cdouble z)   // libs/libhrutil/libhrutil.cc:692-699
 { cdouble r = std::sqrt(z); return (imag(r) < 0.0) ? -r : r; }
 
@@ -260,7 +273,8 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   if (a->symmetric && nsa != nsb) return fail(ctx, "assemble_block: symmetric requires nsa==nsb");
   CK(cudaSetDevice(ctx->device));
 
-  cudaEvent_t ev[4]; for (int i = 0; i < 4; i++) CK(cudaEventCreate(&ev[i]));
+  cudaEvent_t ev[7]; for (int i = 0; i < 7; i++) CK(cudaEventCreate(&ev[i]));
+  cudaStream_t sMain = ctx->stream, sNear = near_stream(ctx);
   CK(cudaEventRecord(ev[0], ctx->stream));
   CK(cudaMemsetAsync(ctx->dcounters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   M->factored = false;
@@ -307,16 +321,24 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      F.symmetric = SP.symmetric; F.useDisp = a->use_displacement ? 1 : 0;
      for (int i = 0; i < 3; i++) F.L[i] = a->use_displacement ? a->displacement[i] : 0.0;
      F.K = K; F.S = SP; F.counters = ctx->dcounters;
-     CK(cudaEventRecord(ev[1], ctx->stream));
+     CK(cudaEventRecord(ev[1], sMain));           // also: the block is zeroed, the counters reset
      launch_far(ctx, F, kmode);
      CK(cudaGetLastError());
-     CK(cudaEventRecord(ev[2], ctx->stream));
+     CK(cudaEventRecord(ev[2], sMain));
      if (!a->far_only)
-      { if (run_near(ctx, nsa, nsb, a, K, SP, kmode, std::abs(k))) return 1; }
-     CK(cudaEventRecord(ev[3], ctx->stream));
+      { // near/singular work on the second stream, concurrently with the far kernel
+        CK(cudaStreamWaitEvent(sNear, ev[1], 0));
+        CK(cudaEventRecord(ev[4], sNear));
+        ctx->stream = sNear;
+        int rc = run_near(ctx, nsa, nsb, a, K, SP, kmode, std::abs(k));
+        ctx->stream = sMain;
+        if (rc) return 1;
+        CK(cudaEventRecord(ev[5], sNear));
+        CK(cudaStreamWaitEvent(sMain, ev[5], 0)); }
+     CK(cudaEventRecord(ev[3], sMain));
      CK(cudaEventSynchronize(ev[3]));
      float t; cudaEventElapsedTime(&t, ev[1], ev[2]); farMs += t;
-     cudaEventElapsedTime(&t, ev[2], ev[3]); nearMs += t;
+     if (!a->far_only) { cudaEventElapsedTime(&t, ev[4], ev[5]); nearMs += t; }
    }
   if (a->symmetric)
    launch_symmetrize(ctx, *M, a->row_offset, NBFA);
@@ -329,7 +351,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   CK(cudaMemcpy(hc, ctx->dcounters, sizeof hc, cudaMemcpyDeviceToHost));
   for (int i = 0; i < 5; i++) ctx->counts[i] = hc[i];
   ctx->pairCounts[0] = hc[5]; ctx->pairCounts[1] = hc[6];
-  for (int i = 0; i < 4; i++) cudaEventDestroy(ev[i]);
+  for (int i = 0; i < 7; i++) cudaEventDestroy(ev[i]);
   return 0;
 }
 

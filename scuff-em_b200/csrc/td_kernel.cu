@@ -32,7 +32,7 @@ static int td_tables(scuffcuda_context *ctx, TDTables &T)
 }
 
 // items[t] = 9*nearIndex + 3*i + j : one (pair, Q_a, Q_b) combination that feeds a matrix entry
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 td_ct_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, double *scratch, int maxM, int *itemStatus)
 { const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nItems) return;
@@ -116,7 +116,9 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
   std::vector<int> work(items);
   // pass 0: every item at once with room for Clenshaw-Curtis levels <= 6 (129 points; the common case),
   // pass 1: the items that asked for more, with the full MaxEval=1000 budget (level 9, 1025 points), in batches
-  const int passM[2] = { 6, 9 }, passBatch[2] = { 1 << 30, 32768 };
+  // with HBM to spare every item gets room for the full budget at once (level 9: 64 KB per item) and nobody restarts
+  const bool roomy = (size_t)items.size() * 4 * 1025 * sizeof(double) <= ((size_t)8 << 30);
+  const int passM[2] = { roomy ? 9 : 6, 9 }, passBatch[2] = { 1 << 30, 32768 };
   std::vector<int> status;
   for (int pass = 0; pass < 2 && !work.empty(); pass++)
    { const int maxM = passM[pass];

@@ -160,35 +160,34 @@ SCUFF_HD int pcubature_1d(const TDTables &T, F &func, double relTol, double absT
     func(c + r * T.ccx[0], fv);   for (int j = 0; j < FDIM; j++) cache[(size_t)(FDIM + j) * stride] = fv[j];
     func(c - r * T.ccx[0], fv);   for (int j = 0; j < FDIM; j++) cache[(size_t)(2 * FDIM + j) * stride] = fv[j];
   }
+  double prev[FDIM];
+  for (int j = 0; j < FDIM; j++) prev[j] = 0.0;
   for (;;)
-   { for (int pass = 0; pass < 2; pass++)
-      { // pass 0: rule of order m; pass 1: order m-1 (error estimate)
-        double acc[FDIM];
-        for (int j = 0; j < FDIM; j++) acc[j] = 0.0;
-        if (pass == 1 && m == 0)
-         { double w = V * 2; for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(j) * stride] * w; }
-        else
-         { const int mid = m - pass;
-           const double *wb = T.ccw + mid + (1 << mid) - 1;
-           double w = V * wb[0];
-           for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(j) * stride] * w;
-           w = V * wb[1];
-           for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(FDIM + j) * stride] * w;
-           for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(2 * FDIM + j) * stride] * w;
-           for (int kk = 1; kk <= mid; kk++)
-            { const double *wk = wb + 1 + (1 << (kk - 1));
-              const int nx = 1 << (kk - 1);
-              const double *cv = cache + (size_t)FDIM * ((1 << kk) + 1) * stride;   // level kk starts after 2^kk+1 points
-              for (int i = 0; i < nx; i++)
-               { double ww = V * wk[i];
-                 for (int j = 0; j < FDIM; j++) acc[j] += cv[(size_t)((2 * i) * FDIM + j) * stride] * ww;
-                 for (int j = 0; j < FDIM; j++) acc[j] += cv[(size_t)((2 * i + 1) * FDIM + j) * stride] * ww;
-               }
-            }
-         }
-        if (pass == 0) { for (int j = 0; j < FDIM; j++) val[j] = acc[j]; }
-        else { for (int j = 0; j < FDIM; j++) err[j] = fabs(val[j] - acc[j]); }
-      }
+   { // rule of order m from the cached values; the error estimate is the difference to the rule of order m-1, which
+     // is exactly the previous iteration's value (same points, weights and summation order), or the midpoint rule at m = 0
+     { double acc[FDIM];
+       for (int j = 0; j < FDIM; j++) acc[j] = 0.0;
+       const int mid = m;
+       const double *wb = T.ccw + mid + (1 << mid) - 1;
+       double w = V * wb[0];
+       for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(j) * stride] * w;
+       w = V * wb[1];
+       for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(FDIM + j) * stride] * w;
+       for (int j = 0; j < FDIM; j++) acc[j] += cache[(size_t)(2 * FDIM + j) * stride] * w;
+       for (int kk = 1; kk <= mid; kk++)
+        { const double *wk = wb + 1 + (1 << (kk - 1));
+          const int nx = 1 << (kk - 1);
+          const double *cv = cache + (size_t)FDIM * ((1 << kk) + 1) * stride;   // level kk starts after 2^kk+1 points
+#pragma unroll 2
+          for (int i = 0; i < nx; i++)
+           { double ww = V * wk[i];
+             for (int j = 0; j < FDIM; j++) acc[j] += cv[(size_t)((2 * i) * FDIM + j) * stride] * ww;
+             for (int j = 0; j < FDIM; j++) acc[j] += cv[(size_t)((2 * i + 1) * FDIM + j) * stride] * ww;
+           }
+        }
+       if (m == 0) { const double w0 = V * 2; for (int j = 0; j < FDIM; j++) prev[j] = 0.0 + cache[(size_t)(j) * stride] * w0; }
+       for (int j = 0; j < FDIM; j++) { val[j] = acc[j]; err[j] = fabs(val[j] - prev[j]); prev[j] = acc[j]; }
+     }
      bool conv = true;
      for (int j = 0; j < FDIM; j++) if (err[j] > absTol && err[j] > fabs(val[j]) * relTol) { conv = false; break; }
      if (conv || (numEval > maxEval && maxEval)) return 0;
