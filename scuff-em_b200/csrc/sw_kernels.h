@@ -12,7 +12,7 @@ struct TDTables;
 int run_ho(scuffcuda_context *ctx, const NearArgs &A, const int *hoIdx, int n, int kmode);
 
 // Taylor-Duffy for common-vertex / common-edge pairs (PPIALG_TD), 3-D / 2-D p-adaptive Clenshaw-Curtis cubature;
-// items[t] = 18*nearIndex + 9*swapped + 3*i + j  (host memory)
+// items[t] = 36*nearIndex + 18*highk + 9*swapped + 3*i + j  (host memory)
 int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T, const int *items, int nItems);
 
 }  // namespace scuffcuda

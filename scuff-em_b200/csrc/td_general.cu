@@ -32,7 +32,7 @@ enum { M_1 = 0, M_Y1 = 1, M_Y12 = 2, M_Y2 = 3, M_Y1Y2 = 4, M_Y22 = 5, M_Y12Y2 = 
        M_Y2Y3 = 15, M_Y1Y2Y3 = 17, M_Y22Y3 = 18, M_Y12Y2Y3 = 19, M_Y1Y22Y32 = 20, M_Y22Y32 = 21 };
 
 struct TDGen
-{ int cas, numRegions, nOffset;
+{ int cas, numRegions, nOffset, hk;   // hk: high-k kernels (twice-integrable path, TaylorDuffy.cc:336-342)
   double A2, B2, AP2, BP2, L2, AdB, AdAP, AdBP, AdL, BdAP, BdBP, APdBP, BPdL;
   double U[3][6][TD_NUMWPOWERS][TDG_NUMMONO];     // [P slot][region][n][monomial]
   int nMin[3], nMax[3];
@@ -40,17 +40,19 @@ struct TDGen
 };
 
 __device__ void tdg_setup(const TDTables &T, int cas, const double *V1, const double *V2, const double *V3,
-                          const double *V2Pin, const double *V3P, const double *Q, const double *QP, cd k, TDGen &W)
-{ const double *V2P = (cas == 2) ? V2 : V2Pin;              // TaylorDuffy.cc:1286-1289
+                          const double *V2Pin, const double *V3P, const double *Q, const double *QP, cd k, TDGen &W, int hk = 0)
+{ const double *V2P = (cas >= 2) ? V2 : V2Pin;              // TaylorDuffy.cc:1286-1289
+  if (cas == 3) V3P = V3;
   double A[3], B[3], AP[3], BP[3], L[3], D[3], DP[3], DeltaD[3];
   sub3(V2, V1, A); sub3(V3, V2, B); sub3(V2P, V1, AP); sub3(V3P, V2P, BP);
-  W.cas = cas; W.k = k;
+  W.cas = cas; W.k = k; W.hk = hk;
   W.A2 = dot3(A, A); W.AdB = dot3(A, B); W.B2 = dot3(B, B);
   W.AP2 = W.BP2 = W.L2 = W.AdAP = W.AdBP = W.AdL = W.BdAP = W.BdBP = W.APdBP = W.BPdL = 0.0;
   if (cas == 2)
    { sub3(BP, B, L);
      W.BP2 = dot3(BP, BP); W.AdBP = dot3(A, BP); W.L2 = dot3(L, L); W.AdL = dot3(A, L); W.BPdL = dot3(BP, L);
      W.numRegions = 6; W.nOffset = 2; }
+  else if (cas == 3) { W.numRegions = 3; W.nOffset = 1; }
   else
    { W.AP2 = dot3(AP, AP); W.BP2 = dot3(BP, BP); W.AdAP = dot3(A, AP); W.AdBP = dot3(A, BP);
      W.BdAP = dot3(B, AP); W.BdBP = dot3(B, BP); W.APdBP = dot3(AP, BP);
@@ -84,9 +86,134 @@ __device__ void tdg_setup(const TDTables &T, int cas, const double *V1, const do
    }
 }
 
+// ---- high-k ("very short wavelength", |k| R > 20) kernels: twice-integrable Taylor-Duffy path ----------------------
+// GetQFPIntegral (TaylorDuffy.cc:627-770), negative powers only:  Int = int_0^1 [(y+P)^2 + Q2]^{p/2} dy,
+// Inty = int_0^1 y [(y+P)^2 + Q2]^{p/2} dy, with the reference's small-Q2 switches (they change the numbers)
+__device__ void qfp_integral(double P, double Q2, int p, double &I, double &Iy)
+{ const double P2 = P * P, PP1 = P + 1.0, PP12 = PP1 * PP1, Q4 = Q2 * Q2;
+  const double S2 = P * P + Q2, S = sqrt(S2), T2 = PP1 * PP1 + Q2, T = sqrt(T2);
+  const double SignP = (P > 0.0) ? 1.0 : -1.0;
+  switch (p)
+   { case -1:
+       I = (Q2 < 1.0e-8) ? SignP * log(1.0 + 1.0 / P) : log((PP1 + T) / (P + S));
+       Iy = -P * I + (T - S); return;
+     case -2:
+       if (Q2 < 1.0e-8) I = 1.0 / (P * PP1);
+       else { const double Q = sqrt(Q2); I = (atan(PP1 / Q) - atan(P / Q)) / Q; }
+       Iy = -P * I + log(T / S); return;
+     case -3:
+       I = (Q2 < 1.0e-8) ? SignP * (1.0 / (2.0 * S2) - 1.0 / (2.0 * T2)) : (PP1 / T - P / S) / Q2;
+       Iy = -P * I + 1.0 / S - 1.0 / T; return;
+     case -4:
+       if (Q2 < 1.0e-6) { const double S3 = S * S2, T3 = T * T2; I = SignP * (1.0 / (3.0 * S3) - 1.0 / (3.0 * T3)); }
+       else { const double Q = sqrt(Q2), at = (atan(PP1 / Q) - atan(P / Q)) / Q; I = ((Q2 - P * PP1) / (S2 * T2) + at) / (2.0 * Q2); }
+       Iy = -P * I + 1.0 / (2.0 * S2) - 1.0 / (2.0 * T2); return;
+     case -5:
+      { const double S3 = S2 * S, T3 = T2 * T;
+        if (Q2 < 1.0e-4) { const double S4 = S3 * S, T4 = T3 * T; I = SignP * (1.0 / (4.0 * S4) - 1.0 / (4.0 * T4)); }
+        else I = (PP1 * (2.0 * PP12 + 3.0 * Q2) * S3 - P * (2.0 * P2 + 3.0 * Q2) * T3) / (3.0 * Q4 * S3 * T3);
+        Iy = -P * I + 1.0 / (3.0 * S3) - 1.0 / (3.0 * T3); return; }
+     case -6:
+      { const double S4 = S2 * S2, T4 = T2 * T2;
+        if (Q2 < 1.0e-4) { const double S5 = S4 * S, T5 = T4 * T; I = SignP * (1.0 / (5.0 * S5) - 1.0 / (5.0 * T5)); }
+        else
+         { const double Q = sqrt(Q2), at = (atan(PP1 / Q) - atan(P / Q)) / Q;
+           I = (3.0 * PP1 / T2 + 2.0 * Q2 * PP1 / T4 - 3.0 * P / S2 - 2.0 * Q2 * P / S4 + 3 * at) / (8.0 * Q4); }
+        Iy = -P * I + 1.0 / (4.0 * S4) - 1.0 / (4.0 * T4); return; }
+     default: I = Iy = nan(""); return;       // the reference ErrExit()s for other powers
+   }
+}
+
+// Px^2 + 2Qx + R -> A^2 [(x+B)^2 + G2]  (PQRtoABG2, TaylorDuffy.cc:375-389, including the B = 0 snap)
+__device__ __forceinline__ void pqr_to_abg2(double P, double Q, double R, double &A, double &B, double &G2)
+{ A = sqrt(P); B = Q / P;
+  const double ROverP = R / P;
+  G2 = ROverP - B * B;
+  if (fabs(G2) < 1.0e-6 * ROverP) { B = 0.0; G2 = ROverP; }
+}
+
+// z^p for complex z, real p, as std::pow(complex, double): exp(p log z)
+__device__ __forceinline__ cd cpow_(cd z, double p)
+{ if (z.y == 0.0 && z.x > 0.0) return mk(pow(z.x, p), 0.0);
+  const double lr = log(cabs_(z)), th = atan2(z.y, z.x);
+  const double e = exp(p * lr); double s, c; sincos(p * th, &s, &c);
+  return mk(e * c, e * s);
+}
+
+__device__ void tdg_integrand_hk(const TDGen &W, const double *y, double f[TDG_FDIM])
+{ const int NR = W.numRegions, nOff = W.nOffset;
+  double Jac = 1.0;
+  if (W.cas == 2) Jac = y[0]; else if (W.cas == 1) Jac = y[1];
+  for (int i = 0; i < TDG_FDIM; i++) f[i] = 0.0;
+  if (Jac == 0.0) return;
+  double Av[6], Bv[6], G2v[6];
+  if (W.cas == 3)        // GetAlphaBetaGamma2, TaylorDuffy.cc:398-418
+   { const double A2 = W.A2, AdB = W.AdB, B2 = W.B2, C2 = A2 + B2 + 2.0 * AdB, CdB = AdB + B2;
+     Av[0] = sqrt(B2); Av[1] = sqrt(C2); Av[2] = sqrt(A2);
+     Bv[0] = AdB / B2; Bv[1] = -CdB / C2; Bv[2] = AdB / A2;
+     G2v[0] = A2 / B2 - (AdB * AdB) / (B2 * B2); G2v[1] = B2 / C2 - (CdB * CdB) / (C2 * C2); G2v[2] = B2 / A2 - (AdB * AdB) / (A2 * A2); }
+  else if (W.cas == 2)   // :419-457
+   { const double y1 = y[0], y12 = y1 * y1, A2 = W.A2, BP2 = W.BP2, L2 = W.L2, AdBP = W.AdBP, AdL = W.AdL, BPdL = W.BPdL;
+     pqr_to_abg2((BP2 - 2.0 * BPdL + L2) * y12, y1 * (L2 + BPdL * (y1 - 1.0) - (AdL + L2 - AdBP) * y1),
+                 L2 - 2 * AdL * y1 - 2 * L2 * y1 + A2 * y12 + 2 * AdL * y12 + L2 * y12, Av[0], Bv[0], G2v[0]);
+     pqr_to_abg2(BP2 * y12, (BPdL + AdBP * y1 - BPdL * y1) * y1, L2 + 2 * AdL * y1 - 2 * L2 * y1 + (A2 - 2 * AdL + L2) * y12, Av[1], Bv[1], G2v[1]);
+     pqr_to_abg2((A2 + 2 * AdBP + BP2) * y12, y1 * (AdL * (-1 + y1) + BPdL * (-1 + y1) - (AdBP + BP2) * y1),
+                 L2 + 2 * BPdL * y1 - 2 * L2 * y1 + BP2 * y12 - 2 * BPdL * y12 + L2 * y12, Av[2], Bv[2], G2v[2]);
+     pqr_to_abg2((A2 + 2 * AdBP - 2 * AdL + BP2 - 2 * BPdL + L2) * y12, y1 * (AdL - L2 - (AdBP + BP2) * y1 + BPdL * (1 + y1)),
+                 L2 - 2 * BPdL * y1 + BP2 * y12, Av[3], Bv[3], G2v[3]);
+     pqr_to_abg2(A2 * y12, (AdBP * y1 - AdL) * y1, L2 - 2 * BPdL * y1 + BP2 * y12, Av[4], Bv[4], G2v[4]);
+     pqr_to_abg2(A2 * y12, y1 * (AdL + AdBP * y1 - AdL * y1), L2 + 2 * BPdL * y1 - 2 * L2 * y1 + BP2 * y12 - 2 * BPdL * y12 + L2 * y12,
+                 Av[5], Bv[5], G2v[5]); }
+  else                   // :458-484
+   { const double y1 = y[0], y2 = y[1], y22 = y2 * y2;
+     pqr_to_abg2(W.BP2 * y22, -W.AdBP * y2 - W.BdBP * y1 * y2 + W.APdBP * y22,
+                 W.A2 + W.B2 * y1 * y1 + W.AP2 * y2 * y2 + 2.0 * W.AdB * y1 - 2.0 * W.AdAP * y2 - 2.0 * W.BdAP * y1 * y2, Av[0], Bv[0], G2v[0]);
+     pqr_to_abg2(W.B2 * y22, W.AdB * y22 - W.BdAP * y2 - W.BdBP * y1 * y2,
+                 W.A2 * y2 * y2 + W.AP2 + W.BP2 * y1 * y1 - 2 * W.AdAP * y2 - 2 * W.AdBP * y2 * y1 + 2 * W.APdBP * y1, Av[1], Bv[1], G2v[1]); }
+  const double Fact[7] = { 1.0, 1.0, 2.0, 6.0, 24.0, 120.0, 620.0 };     // TaylorDuffy.cc:777 (620, as written)
+  const cd mIK = mk(W.k.y, -W.k.x);                                       // -i k
+  const int numPK = (W.cas == 3) ? 2 : 3;
+  for (int npk = 0; npk < numPK; npk++)
+   { const int nMin = W.nMin[npk], nMax = W.nMax[npk];
+     cd Sum = mk(0.0, 0.0);
+     for (int n = nMin; n <= nMax; n++)
+      for (int d = 0; d < NR; d++)
+       { const double *Up = W.U[npk][d][n];
+         double P0, P1;
+         if (W.cas == 3) { P0 = Up[M_1]; P1 = Up[M_Y1]; }
+         else if (W.cas == 2)
+          { const double y1 = y[0], y12 = y1 * y1;
+            P0 = Up[M_1] + Up[M_Y1] * y1 + Up[M_Y12] * y12;
+            P1 = Up[M_Y2] + Up[M_Y1Y2] * y1 + Up[M_Y12Y2] * y12; }
+         else
+          { const double y1 = y[0], y12 = y1 * y1, y2 = y[1], y22 = y2 * y2;
+            P0 = Up[M_1] + Up[M_Y1] * y1 + Up[M_Y2] * y2 + Up[M_Y12] * y12 + Up[M_Y1Y2] * y1 * y2 + Up[M_Y22] * y22
+                 + Up[M_Y12Y2] * y12 * y2 + Up[M_Y1Y22] * y1 * y22;
+            P1 = Up[M_Y2Y3] * y2 + Up[M_Y1Y2Y3] * y1 * y2 + Up[M_Y22Y3] * y22 + Up[M_Y12Y2Y3] * y12 * y2; }
+         const int nn = n + nOff;
+         double I, Iy; qfp_integral(Bv[d], G2v[d], -(nn + 1), I, Iy);
+         const cd z = mk(mIK.x * Av[d], mIK.y * Av[d]);
+         cd J, L;
+         if (npk < 2)      // TD_HIGHK_HELMHOLTZ
+          { const cd pw = cpow_(z, -(double)nn); const double c = Fact[nn - 1];
+            const cd t = mk(c * pw.x, c * pw.y);
+            J = mk(t.x * I / Av[d], t.y * I / Av[d]); L = mk(t.x * Iy / Av[d], t.y * Iy / Av[d]); }
+         else              // TD_HIGHK_GRADHELMHOLTZ
+          { const double A3 = Av[d] * Av[d] * Av[d];
+            const cd pw = cpow_(z, -(double)(nn - 2)); const double c = -(nn - 1) * Fact[nn - 3];
+            const cd t = mk(c * pw.x, c * pw.y);
+            J = mk(t.x * I / A3, t.y * I / A3); L = mk(t.x * Iy / A3, t.y * Iy / A3); }
+         Sum += P0 * J + P1 * L;
+       }
+     const double s = Jac / (4.0 * M_PI);
+     f[2 * npk] = Sum.x * s; f[2 * npk + 1] = Sum.y * s;
+   }
+}
+
 // integrand (TaylorDuffySum, once-integrable branch): f[0..5] = Re/Im of the three P x K integrals
 __device__ void tdg_integrand(const TDGen &W, const double *y, double f[TDG_FDIM])
-{ const int NR = W.numRegions, nOff = W.nOffset;
+{ if (W.hk) { tdg_integrand_hk(W, y, f); return; }
+  const int NR = W.numRegions, nOff = W.nOffset;
   double yInner, Jac;
   if (W.cas == 2) { yInner = y[1]; Jac = y[0]; } else { yInner = y[2]; Jac = y[1]; }
   if (Jac == 0.0) { for (int i = 0; i < TDG_FDIM; i++) f[i] = 0.0; return; }
@@ -276,14 +403,14 @@ __device__ int pcubature_nd(const TDTables &T, const TDGen &W, double relTol, do
    }
 }
 
-// items[t] = 18*nearIndex + 9*swapped + 3*i + j
+// items[t] = 36*nearIndex + 18*highk + 9*swapped + 3*i + j
 __global__ void __launch_bounds__(64)
 td_general_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, double *scratch, int *itemStatus)
 { const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= nItems) return;
   const int item = items[t];
-  const NearPair N = A.near[item / 18];
-  const int swapped = (item % 18) / 9, i = (item % 9) / 3, j = item % 3;
+  const NearPair N = A.near[item / 36];
+  const int hk = (item % 36) / 18, swapped = (item % 18) / 9, i = (item % 9) / 3, j = item % 3;
   const PanelRec &Pa = A.pa[N.pa], &Pb = A.pb[N.pb];
   const int ea = Pa.ei[i], eb = Pb.ei[j];
   double Va[9], Vb[9];
@@ -300,21 +427,27 @@ td_general_kernel(const NearArgs A, const TDTables T, const int *items, int nIte
      Q = Vb + 3 * j; QP = Va + 3 * i; }
   TDGen W;
   const cd k = mk(A.K.kr, A.K.ki);
-  tdg_setup(T, ncv, V1, V2, V3, V2P, V3P, Q, QP, k, W);
+  tdg_setup(T, ncv, V1, V2, V3, V2P, V3P, Q, QP, k, W, hk);
   double val[TDG_FDIM], err[TDG_FDIM];
+  for (int q = 0; q < TDG_FDIM; q++) val[q] = 0.0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  int st = (ncv == 2) ? pcubature_nd<2>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err)
-                      : pcubature_nd<3>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
+  // integral dimension = 4 - WhichCase - TwiceIntegrable (TaylorDuffy.cc:355)
+  const int dim = 4 - ncv - hk;
+  int st = 0;
+  if (dim == 0) tdg_integrand_hk(W, nullptr, val);
+  else if (dim == 1) st = pcubature_nd<1>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
+  else if (dim == 2) st = pcubature_nd<2>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
+  else st = pcubature_nd<3>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
   itemStatus[t] = st;
   if (st) return;
   const cd R0 = mk(val[0], val[1]), R1 = mk(val[2], val[3]), R2 = mk(val[4], val[5]);
   const cd k2 = k * k;
-  cd H0 = R1 - cdiv(mk(4.0 * R0.x, 4.0 * R0.y), k2), H1 = R2;
+  cd H0 = R1 - cdiv(mk(4.0 * R0.x, 4.0 * R0.y), k2), H1 = (ncv == 3) ? mk(0.0, 0.0) : R2;
   // a diagonal edge pair (ea == eb, pa != pb) of a symmetric block receives PPI(pa,pb) + PPI(pb,pa): both orders are
   // separate items, scatter_ppi would double each
   if (A.S.symmetric && N.pa != N.pb && ea == eb) { H0 = 0.5 * H0; H1 = 0.5 * H1; }
   scatter_ppi(A.S, A.K, N.pa, N.pb, ea, eb, Pa.sl[i], Pb.sl[j], H0, H1);
-  atomicAdd(A.counters + 2, 1ull);
+  atomicAdd(A.counters + (hk ? 3 : 2), 1ull);
 }
 
 int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T, const int *items, int nItems)

@@ -85,9 +85,7 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
      int alg = near_algorithm(N.ncv, A.kabs, Sa.hpanels[N.pa].R, Sb.hpanels[N.pb].R, A.forceTD, verySW);
      if (alg == 4) continue;
      if (alg == 1) { hoIdx.push_back(n); continue; }                  // high-order cubature
-     if (alg == 2 && verySW)
-      { ctx->err = "very-short-wavelength regime (|k|*panel radius > 20): high-k Taylor-Duffy is not yet available on the device path";
-        return 1; }
+     const int hk = (alg == 2 && verySW) ? 18 : 0;                    // high-k Taylor-Duffy kernels (PPIALG_HKTD)
      // the (Q_a,Q_b) combinations that feed a matrix entry
      const PanelRec &Pa = Sa.hpanels[N.pa], &Pb = Sb.hpanels[N.pb];
      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
@@ -95,13 +93,13 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
         if (ea < 0 || eb < 0) continue;
         if (N.ncv == 3)
          { if (A.S.symmetric && N.pa == N.pb && ea > eb) continue;
-           items.push_back(9 * n + 3 * i + j); }
-        else if (!A.S.symmetric) genItems.push_back(18 * n + 3 * i + j);
+           if (hk) genItems.push_back(36 * n + hk + 3 * i + j); else items.push_back(9 * n + 3 * i + j); }
+        else if (!A.S.symmetric) genItems.push_back(36 * n + hk + 3 * i + j);
         else
          { // symmetric block, pa < pb visited once: entry (min,max)(ea,eb) is EEI(nea<=neb), whose panel order decides
            // which of PPI(pa,pb) / PPI(pb,pa) the reference evaluates; a diagonal edge pair gets both
-           if (ea <= eb) genItems.push_back(18 * n + 3 * i + j);
-           if (ea >= eb) genItems.push_back(18 * n + 9 + 3 * i + j); }
+           if (ea <= eb) genItems.push_back(36 * n + hk + 3 * i + j);
+           if (ea >= eb) genItems.push_back(36 * n + hk + 9 + 3 * i + j); }
       }
    }
      C.valid = noSW; C.genA = P.genA; C.genB = P.genB; C.nsa = P.nsa; C.nsb = P.nsb; C.forceTD = A.forceTD; C.nNear = P.nNear;

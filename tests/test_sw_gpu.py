@@ -31,6 +31,25 @@ def test_short_wavelength_matrix(ps, name, omega, imag, tmp_path):
     assert max(errs.values()) <= TOL
 
 
+# |k| R > 20 for (some) panels: high-k Taylor-Duffy kernels (PPIALG_HKTD), twice-integrable reduction
+HK_CASES = [("PECSphere_255", 90.0, False), ("PECSpheres_327", 100.0j, True), ("SiSphere_255", 30.0, False)]
+
+
+@pytest.mark.parametrize("name,omega,imag", HK_CASES)
+def test_very_short_wavelength_matrix(ps, name, omega, imag, tmp_path):
+    geo = os.path.join(GEODIR, name + ".scuffgeo")
+    cache = str(tmp_path / "ref.cache")
+    Mref, info = ref_matrix(geo, omega, imag=imag, cache_out=cache)
+    ps.PreloadCache(cache)
+    G = ps.RWGGeometry(geo)
+    M = G.AssembleBEMMatrix(omega, M=G.AllocateBEMMatrix(imag)).array
+    counts = G.ppi_counts()
+    errs = block_errors(G, M, Mref)
+    print(name, omega, "block errs", {k: float("%.2e" % v) for k, v in errs.items()}, "counts", counts, "timing", ps.last_timing())
+    assert counts[3] > 0                             # high-k Taylor-Duffy was exercised
+    assert max(errs.values()) <= TOL
+
+
 def test_disable_cache_forces_taylor_duffy(ps, monkeypatch):
     """RWGGeometry::DisableCache (env SCUFF_DISABLE_CACHE in the reference, RWGGeometry.cc:402)"""
     geo = os.path.join(GEODIR, "PECSphere_255.scuffgeo")
