@@ -228,7 +228,9 @@ class RWGGeometry
 
    /* AssembleBEMMatrix without the final device->host copy: the matrix stays in HBM
     * (M->HostStale) for the on-device LU consumer and the sweep drivers                   */
-   void AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M);
+   /* ColBegin/ColEnd (ColEnd > 0): column-block assembly across GPUs — fill only the global columns [ColBegin, ColEnd)
+    * of the UPPER triangle (symmetric case) and do not mirror; the caller gathers the column blocks and mirrors once   */
+   void AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M, int ColBegin = 0, int ColEnd = 0);
 
    /* internal */
    void InitPBCData();

@@ -91,7 +91,12 @@ typedef struct scuffcuda_ssi_args {
   double displacement[3];
   int    force_taylor_duffy;/* RWGGeometry::DisableCache (PanelPanelInteractions.cc:589)*/
   int    far_only;          /* debug/bench: evaluate only rRel>4 pairs                  */
-  int    reserved[7];
+  int    col_begin, col_end;/* column-block assembly across GPUs: write only the GLOBAL matrix columns
+                             * [col_begin, col_end) (and skip the panel pairs that cannot reach them);
+                             * col_end == 0: all columns.  Symmetric blocks still fill the upper triangle
+                             * only and are NOT mirrored when a range is given (the caller mirrors the
+                             * gathered matrix with scuffcuda_matrix_symmetrize)               */
+  int    reserved[5];
 } scuffcuda_ssi_args;
 
 /* GetSurfaceSurfaceInteractions(Args) on the device: adds the (nsa,nsb) block into the

@@ -304,6 +304,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      SP.c1 = mk(real(PreFac1), imag(PreFac1));
      SP.c2 = mk(real(PreFac2), imag(PreFac2));
      SP.c3 = mk(real(PreFac3), imag(PreFac3));
+     SP.colLo = a->col_end > 0 ? a->col_begin : 0; SP.colHi = a->col_end > 0 ? a->col_end : 0x7fffffff;
      int kmode = (imag(k) == 0.0) ? KMODE_REAL : ((real(k) == 0.0) ? KMODE_IMAG : KMODE_CPLX);
      { // the FP64 sincos range reduction of the far kernel is exact for |Re k| * distance < 1e5
        double ext = 0.0;
@@ -340,7 +341,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      float t; cudaEventElapsedTime(&t, ev[1], ev[2]); farMs += t;
      if (!a->far_only) { cudaEventElapsedTime(&t, ev[4], ev[5]); nearMs += t; }
    }
-  if (a->symmetric)
+  if (a->symmetric && a->col_end <= 0)
    launch_symmetrize(ctx, *M, a->row_offset, NBFA);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev[3], ctx->stream));

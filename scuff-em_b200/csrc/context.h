@@ -44,6 +44,7 @@ struct StampParams
 { double *M; long ld; int isReal;
   int rowOff, colOff; int aPEC, bPEC; int symmetric;
   cd c1, c2, c3;   // PreFac1, PreFac2/(ik), PreFac3
+  int colLo, colHi; // only matrix columns in [colLo, colHi) are written (column-block assembly across GPUs); 0,INT_MAX = all
 };
 
 // near-pair plan for one (nsa, nsb, displacement): list of panel pairs with rRel<=4 and

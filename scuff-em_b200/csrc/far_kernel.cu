@@ -257,24 +257,39 @@ far_kernel(const FarArgs A)
      double D[3];
      { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
        if (!pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D)) continue; }
+     if (A.S.colHi != 0x7fffffff)
+      { // column-block assembly: skip pairs none of whose entries can fall into the owned column range
+        const int *eb3 = (const int *)(Pb + 34);
+        int loA = 0x7fffffff, hiA = -1, loB = 0x7fffffff, hiB = -1;
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+         { const int e = sEi[m * FAR_THREADS], f = eb3[m];
+           if (e >= 0) { loA = min(loA, e); hiA = max(hiA, e); }
+           if (f >= 0) { loB = min(loB, f); hiB = max(hiB, f); } }
+        if (hiA < 0 || hiB < 0) continue;
+        // symmetric blocks store entry (min(e,f), max(e,f)): its column is max(e,f); otherwise the column is f
+        const int w = A.S.bPEC ? 1 : 2;
+        const int lo = A.S.colOff + w * (A.symmetric ? max(loA, loB) : loB), hi = A.S.colOff + w * (A.symmetric ? max(hiA, hiB) : hiB) + w - 1;
+        if (hi < A.S.colLo || lo >= A.S.colHi) continue; }
      nPairs++;
 
-     // ---- 3x3 barycentric moments: mX[n over b (outer, tile)][m over a (inner, lane)] ----
-     S xPhi[3][3], xPsi[3][3];
+     // ---- 3x3 barycentric moments m[m over a (outer loop: this lane's points)][n over b (inner loop: tile panel's points,
+     //      broadcast shared-memory reads)] ----
+     S mPhi[3][3], mPsi[3][3];
 #pragma unroll
      for (int m = 0; m < 3; m++)
 #pragma unroll
-      for (int n = 0; n < 3; n++) { szero(xPhi[m][n]); if (PSI) szero(xPsi[m][n]); }
+      for (int n = 0; n < 3; n++) { szero(mPhi[m][n]); szero(mPsi[m][n]); }
 
 #pragma unroll 1
      for (int p = 0; p < 6; p++)
-      { // R = X_a - X_b = x_a(lane) - (x_b(tile) - D)
-        const double y0 = Pb[13 + 3 * p] - D[0], y1 = Pb[14 + 3 * p] - D[1], y2 = Pb[15 + 3 * p] - D[2];
+      { // R = X_a - X_b = (x_a(lane) + D) - x_b(tile)
+        const double y0 = sXa[(3 * p) * FAR_THREADS] + D[0], y1 = sXa[(3 * p + 1) * FAR_THREADS] + D[1], y2 = sXa[(3 * p + 2) * FAR_THREADS] + D[2];
         S a0_, au, av, b0_, bu, bv;
         szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
 #pragma unroll
         for (int pp = 0; pp < 6; pp++)
-         { const double R0 = sXa[(3 * pp) * FAR_THREADS] - y0, R1 = sXa[(3 * pp + 1) * FAR_THREADS] - y1, R2 = sXa[(3 * pp + 2) * FAR_THREADS] - y2;
+         { const double R0 = y0 - Pb[13 + 3 * pp], R1 = y1 - Pb[14 + 3 * pp], R2 = y2 - Pb[15 + 3 * pp];
            const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
            S Phi, Psi;
            helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
@@ -282,21 +297,17 @@ far_kernel(const FarArgs A)
            if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi); }
          }
         const double w0 = c_far_wm[p][0], w1 = c_far_wm[p][1], w2 = c_far_wm[p][2];
-        fma_acc(xPhi[0][0], w0, a0_); fma_acc(xPhi[0][1], w0, au); fma_acc(xPhi[0][2], w0, av);
-        fma_acc(xPhi[1][0], w1, a0_); fma_acc(xPhi[1][1], w1, au); fma_acc(xPhi[1][2], w1, av);
-        fma_acc(xPhi[2][0], w2, a0_); fma_acc(xPhi[2][1], w2, au); fma_acc(xPhi[2][2], w2, av);
+        fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
+        fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
+        fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
         if (PSI)
-         { fma_acc(xPsi[0][0], w0, b0_); fma_acc(xPsi[0][1], w0, bu); fma_acc(xPsi[0][2], w0, bv);
-           fma_acc(xPsi[1][0], w1, b0_); fma_acc(xPsi[1][1], w1, bu); fma_acc(xPsi[1][2], w1, bv);
-           fma_acc(xPsi[2][0], w2, b0_); fma_acc(xPsi[2][1], w2, bu); fma_acc(xPsi[2][2], w2, bv); }
+         { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
+           fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
+           fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); }
       }
 
      // ---- contraction to the nine (Q_a,Q_b) combinations and scatter ----
-     { S mPhi[3][3], mPsi[3][3];
-#pragma unroll
-       for (int m = 0; m < 3; m++)
-#pragma unroll
-        for (int n = 0; n < 3; n++) { mPhi[m][n] = xPhi[n][m]; mPsi[m][n] = xPsi[n][m]; }
+     {
        int eia[3]; double sla[3], Aa[3], Ba[3], Ab[3], Bb[3], Va0[3], Vb0[3];
 #pragma unroll
        for (int m = 0; m < 3; m++)
@@ -460,7 +471,8 @@ static void launch_far_inst(scuffcuda_context *ctx, const FarArgs &A, dim3 grid,
 template <int KMODE>
 static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi, int minb)
 { if (psi) { if (minb >= 3) launch_far_inst<KMODE, true, 3>(ctx, A, grid, smem); else launch_far_inst<KMODE, true, 2>(ctx, A, grid, smem); }
-  else { if (minb >= 4) launch_far_inst<KMODE, false, 4>(ctx, A, grid, smem); else launch_far_inst<KMODE, false, 3>(ctx, A, grid, smem); }
+  else { if (minb >= 5) launch_far_inst<KMODE, false, 5>(ctx, A, grid, smem); else if (minb == 4) launch_far_inst<KMODE, false, 4>(ctx, A, grid, smem);
+         else launch_far_inst<KMODE, false, 3>(ctx, A, grid, smem); }
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
@@ -468,16 +480,16 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   // lanes: 128 a-panels (rows); tile: TB b-panels (columns) in shared memory.  Tile height: enough CTAs to fill the
   // machine on small meshes, 32 on large ones
   int aTiles = (A.NPa + FAR_THREADS - 1) / FAR_THREADS;
-  int TB = 32;
+  const bool psi = !(A.S.aPEC && A.S.bPEC);     // PEC/PEC blocks stamp GC[0] only
+  // resident CTAs per SM (register budget 168 / 128 / 96 per thread): tuning knob, default from measurements
+  static int minbEnv = -1;
+  if (minbEnv < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB"); minbEnv = e ? atoi(e) : 0; }
+  const int minb = minbEnv > 0 ? minbEnv : (psi ? 3 : 4);
+  int TB = (minb >= 5) ? 16 : 32;              // 5 CTAs/SM need the smaller tile to fit shared memory
   while (TB > 2 && (long)aTiles * ((A.NPb + TB - 1) / TB) < 4L * ctx->smCount) TB >>= 1;
   A.TA = TB;
   dim3 grid(aTiles, (A.NPb + TB - 1) / TB);
   size_t smem = FAR_SMEM_BYTES(TB);
-  const bool psi = !(A.S.aPEC && A.S.bPEC);     // PEC/PEC blocks stamp GC[0] only
-  // resident CTAs per SM (register budget 168 vs 128 per thread): tuning knob, default from measurements
-  static int minbEnv = -1;
-  if (minbEnv < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB"); minbEnv = e ? atoi(e) : 0; }
-  const int minb = minbEnv > 0 ? minbEnv : (psi ? 3 : 4);
   ctx->launches++;
   if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi, minb);
   else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi, minb);

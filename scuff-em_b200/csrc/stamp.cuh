@@ -8,7 +8,8 @@
 namespace scuffcuda {
 
 __device__ __forceinline__ void add_entry(const StampParams &P, int row, int col, cd v)
-{ size_t idx = (size_t)row + (size_t)col * (size_t)P.ld;
+{ if (col < P.colLo || col >= P.colHi) return;
+  size_t idx = (size_t)row + (size_t)col * (size_t)P.ld;
   if (P.isReal) atomicAdd(P.M + idx, v.x);
   else { atomicAdd(P.M + 2 * idx, v.x); atomicAdd(P.M + 2 * idx + 1, v.y); }
 }

@@ -67,14 +67,14 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
   // (near_algorithm).  While |k| * (largest panel radius) <= pi no pair can switch, so the item lists of the previous
   // frequency point of the sweep are reused (they are O(#near pairs) host work otherwise).
   struct ListCache { bool valid = false; uint64_t genA = 0, genB = 0; int nsa = -1, nsb = -1, forceTD = 0, nNear = 0; bool symmetric = false, useDisp = false;
-                     double L[3] = { 0, 0, 0 }; std::vector<int> items, hoIdx, genItems; };
+                     double L[3] = { 0, 0, 0 }; std::vector<int> items, hoIdx, genItems; int colLo = 0, colHi = 0; };
   static ListCache g_cache[64];
   ListCache &C = g_cache[ctx->device & 63];
   double Rmax = 0.0;
   for (const PanelRec &Q : Sa.hpanels) Rmax = std::max(Rmax, Q.R);
   for (const PanelRec &Q : Sb.hpanels) Rmax = std::max(Rmax, Q.R);
   const bool noSW = !(A.kabs * Rmax > SW_THRESHOLD);
-  const bool reuse = C.valid && noSW && C.genA == P.genA && C.genB == P.genB && C.nsa == P.nsa && C.nsb == P.nsb && C.forceTD == A.forceTD
+  const bool reuse = C.valid && noSW && C.colLo == A.S.colLo && C.colHi == A.S.colHi && C.genA == P.genA && C.genB == P.genB && C.nsa == P.nsa && C.nsb == P.nsb && C.forceTD == A.forceTD
                      && C.nNear == P.nNear && C.symmetric == P.symmetric && C.useDisp == P.useDisp
                      && C.L[0] == P.L[0] && C.L[1] == P.L[1] && C.L[2] == P.L[2];
   std::vector<int> &items = C.items, &hoIdx = C.hoIdx, &genItems = C.genItems;
@@ -91,6 +91,9 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
      for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
       { const int ea = Pa.ei[i], eb = Pb.ei[j];
         if (ea < 0 || eb < 0) continue;
+        { // column-block assembly: only items whose matrix column is owned
+          const int w = A.S.bPEC ? 1 : 2, ec = A.S.symmetric ? std::max(ea, eb) : eb;
+          if (A.S.colOff + w * ec + w - 1 < A.S.colLo || A.S.colOff + w * ec >= A.S.colHi) continue; }
         if (N.ncv == 3)
          { if (A.S.symmetric && N.pa == N.pb && ea > eb) continue;
            if (hk) genItems.push_back(36 * n + hk + 3 * i + j); else items.push_back(9 * n + 3 * i + j); }
@@ -102,6 +105,7 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
            if (ea >= eb) genItems.push_back(36 * n + hk + 9 + 3 * i + j); }
       }
    }
+     C.colLo = A.S.colLo; C.colHi = A.S.colHi;
      C.valid = noSW; C.genA = P.genA; C.genB = P.genB; C.nsa = P.nsa; C.nsb = P.nsb; C.forceTD = A.forceTD; C.nNear = P.nNear;
      C.symmetric = P.symmetric; C.useDisp = P.useDisp; for (int q = 0; q < 3; q++) C.L[q] = P.L[q];
    }

@@ -30,7 +30,8 @@ void RWGGeometry::DestroyABMBAccelerator(void *) {}
 // device-side GetSurfaceSurfaceInteractions for one block of M (device twin), no host copy-back
 static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omega, HMatrix *M,
                                   int RowOffset, int ColOffset, bool Symmetric, bool Accumulate,
-                                  const double *Displacement, bool OmitRegion1, bool OmitRegion2)
+                                  const double *Displacement, bool OmitRegion1, bool OmitRegion2,
+                                  int ColBegin = 0, int ColEnd = 0)
 { scuffcuda_context *ctx = GetCudaContext();
   RWGSurface *Sa = G->Surfaces[nsa], *Sb = G->Surfaces[nsb];
   G->UpdateCachedEpsMuValues(Omega);
@@ -43,6 +44,7 @@ static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omeg
   A.row_offset = RowOffset; A.col_offset = ColOffset;
   if (Displacement) { A.use_displacement = 1; for (int i = 0; i < 3; i++) A.displacement[i] = Displacement[i]; }
   A.force_taylor_duffy = RWGGeometry::DisableCache ? 1 : 0;
+  A.col_begin = ColBegin; A.col_end = ColEnd;
   const char *fo = getenv("SCUFF_CUDA_FAR_ONLY"); A.far_only = (fo && fo[0] == '1');
 
   double Signs[2]; int CR[2];
@@ -102,8 +104,9 @@ HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *
 
 // same as AssembleBEMMatrix but leaves the result in HBM only (M->HostStale == true): the form
 // the on-device LU consumer and the sweep drivers use
-void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M)
+void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M, int ColBegin, int ColEnd)
 { scuffcuda_context *ctx = GetCudaContext();
+  const bool Partial = ColEnd > 0;
   M->EnsureDevice();
   for (int i = 0; i < 5; i++) LastPPICounts[i] = 0;
   bool MatrixIsSymmetric = (!kBloch || (kBloch[0] == 0.0 && kBloch[1] == 0.0));
@@ -111,6 +114,7 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
   for (int ns = 0; ns < NumSurfaces; ns++)
    for (int nsp = nspStart * ns; nsp < NumSurfaces; nsp++)
     { int nsm;
+      if (Partial && (BFIndexOffset[nsp] >= ColEnd || BFIndexOffset[nsp] + Surfaces[nsp]->NumBFs <= ColBegin)) continue;
       if (ns == nsp && (nsm = Mate[ns]) != -1)
        { int ThisOffset = BFIndexOffset[ns], MateOffset = BFIndexOffset[nsm], Dim = Surfaces[ns]->NumBFs;
          SyncDeviceGeometry();
@@ -118,11 +122,11 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
           ErrExit("%s", scuffcuda_last_error(ctx));
          M->HostStale = true; }
       else if (LBasis == 0)
-       AssembleBlockOnDevice(this, ns, nsp, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false);
+       AssembleBlockOnDevice(this, ns, nsp, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false, ColBegin, ColEnd);
       else
        AssembleBEMMatrixBlockPBC(ns, nsp, Omega, kBloch, M, BFIndexOffset[ns], BFIndexOffset[nsp]);
     }
-  if (MatrixIsSymmetric)
+  if (MatrixIsSymmetric && !Partial)
    { if (scuffcuda_matrix_symmetrize(ctx, M->DeviceHandle, 0, TotalBFs)) ErrExit("%s", scuffcuda_last_error(ctx));
      M->HostStale = true; }
 }

@@ -77,6 +77,17 @@ int scuffb200_assemble(void *g, void *m, double wr, double wi, const double *kBl
            if (G->LBasis != 0 && kBloch == 0) ErrExit("Bloch wavevector must be specified for PBC geometries");
            G->AssembleBEMMatrixDevice(cdouble(wr, wi), (double *)kBloch, M); }
         return 0;, 1) }
+// column-block assembly (multi-GPU): upper-triangle entries of the global columns [c0,c1) only, left in HBM, not mirrored
+int scuffb200_assemble_columns(void *g, void *m, double wr, double wi, int c0, int c1)
+{ RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
+  GUARD(if (G->LBasis != 0) ErrExit("column-block assembly is not available for periodic geometries");
+        G->AssembleBEMMatrixDevice(cdouble(wr, wi), 0, M, c0, c1); return 0;, 1) }
+// mirror the upper triangle of the (gathered) device matrix into the lower one
+int scuffb200_matrix_symmetrize(void *m)
+{ HMatrix *M = (HMatrix *)m;
+  GUARD(M->EnsureDevice();
+        if (scuffcuda_matrix_symmetrize(GetCudaContext(), M->DeviceHandle, 0, M->NR)) ErrExit("%s", scuffcuda_last_error(GetCudaContext()));
+        M->HostStale = true; return 0;, 1) }
 int scuffb200_assemble_block(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off)
 { RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
   GUARD(G->AssembleBEMMatrixBlock(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, 0, row_off, col_off); return 0;, 1) }

@@ -29,7 +29,7 @@ class SSIArgs(C.Structure):
                 ("row_offset", C.c_int), ("col_offset", C.c_int),
                 ("use_displacement", C.c_int), ("displacement", C.c_double * 3),
                 ("force_taylor_duffy", C.c_int), ("far_only", C.c_int),
-                ("reserved", C.c_int * 7)]
+                ("col_begin", C.c_int), ("col_end", C.c_int), ("reserved", C.c_int * 5)]
 
 
 _cuda = None
@@ -111,6 +111,8 @@ def host_lib():
         L.scuffb200_matrix_sync_host.argtypes = [C.c_void_p]
         L.scuffb200_matrix_device_handle.argtypes = [C.c_void_p]
         L.scuffb200_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]
+        L.scuffb200_assemble_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
+        L.scuffb200_matrix_symmetrize.argtypes = [C.c_void_p]
         L.scuffb200_assemble_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                                C.c_void_p, C.c_int, C.c_int]
         L.scuffb200_ppi_counts.argtypes = [C.c_void_p, C.c_void_p]
@@ -174,6 +176,20 @@ class HMatrix:
     @property
     def device_handle(self):
         return host_lib().scuffb200_matrix_device_handle(self.ptr)
+
+    def symmetrize(self):
+        _check(host_lib().scuffb200_matrix_symmetrize(self.ptr))
+
+    def device_tensor(self):
+        """zero-copy torch view (float64, length NR*NC*(1|2), column-major) of the HBM-resident matrix"""
+        import torch
+        dptr = C.c_void_p()
+        cuda_lib().scuffcuda_matrix_device_ptr(context(), self.device_handle, C.byref(dptr))
+        n = self.NR * self.NC * (1 if self.is_real else 2)
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (dptr.value, False), "version": 2}
+        return torch.as_tensor(_Arr(), device="cuda")
 
     def lu_factorize(self):
         _check(host_lib().scuffb200_lu_factorize(self.ptr))
@@ -250,6 +266,11 @@ class RWGGeometry:
             kb = (C.c_double * 2)(float(kBloch[0]), float(kBloch[1]))
         _check(host_lib().scuffb200_assemble(self.ptr, M.ptr, float(np.real(Omega)), float(np.imag(Omega)),
                                               kb, int(to_host)))
+        return M
+
+    def AssembleBEMMatrixColumns(self, Omega, M, c0, c1):
+        """column-block assembly for multi-GPU: upper-triangle entries of global columns [c0,c1), resident in HBM, not mirrored"""
+        _check(host_lib().scuffb200_assemble_columns(self.ptr, M.ptr, float(np.real(Omega)), float(np.imag(Omega)), int(c0), int(c1)))
         return M
 
     def AssembleBEMMatrixBlock(self, nsa, nsb, Omega, M, kBloch=None, RowOffset=0, ColOffset=0):

@@ -39,3 +39,31 @@ def run_sweep(points, evaluate, rank=0, world=1):
     rank 0.  `evaluate` is where RWGGeometry.AssembleBEMMatrix(+LU) runs on this rank's GPU."""
     local = [(j, evaluate(p)) for j, p in points_for_rank(points, rank, world)]
     return gather_results(local, len(points), rank, world)
+
+
+# ---- one very large matrix across GPUs (SURVEY.md §8e, second row) ----------------------------------------------
+def column_ranges(n, world):
+    """Column blocks [c_r, c_{r+1}) of an n x n SYMMETRIC matrix with equal upper-triangle area (work ~ c_{r+1}^2 - c_r^2):
+    c_r = round(n sqrt(r / world))."""
+    cuts = [int(round(n * (r / world) ** 0.5)) for r in range(world + 1)]
+    cuts[0], cuts[-1] = 0, n
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def gather_columns(flat, n, elem_doubles, ranges, rank, world, dst=0):
+    """flat: this rank's zero-copy float64 view of its n x n column-major device matrix.  Column block r (contiguous in
+    column-major storage) travels from rank r straight into rank dst's matrix at the same offset (NCCL send/recv over
+    NVLink); nothing is staged."""
+    if world == 1:
+        return
+    reqs = []
+    if rank == dst:
+        for r, (c0, c1) in enumerate(ranges):
+            if r != dst and c1 > c0:
+                reqs.append(dist.irecv(flat[c0 * n * elem_doubles:c1 * n * elem_doubles], src=r))
+    else:
+        c0, c1 = ranges[rank]
+        if c1 > c0:
+            reqs.append(dist.isend(flat[c0 * n * elem_doubles:c1 * n * elem_doubles], dst=dst))
+    for q in reqs:
+        q.wait()

@@ -61,3 +61,54 @@ def test_single_rank_and_errors():
         sweep.gather_results([(0, 1.0)], 2, 0, 1)
     with pytest.raises(RuntimeError):
         sweep.gather_results([(0, 1.0), (0, 2.0)], 1, 0, 1)
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sweep = _load()
+    n = 37
+    ranges = sweep.column_ranges(n, world)
+    # column-major n x n complex matrix as 2*n*n doubles; rank r fills its own columns with (r+1)*1000 + flat index
+    flat = torch.zeros(2 * n * n, dtype=torch.float64)
+    c0, c1 = ranges[rank]
+    flat[2 * n * c0:2 * n * c1] = (rank + 1) * 1000.0 + torch.arange(2 * n * c0, 2 * n * c1, dtype=torch.float64)
+    sweep.gather_columns(flat, n, 2, ranges, rank, world, dst=0)
+    q.put((rank, ranges, flat.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_column_block_gather_world2():
+    import torch
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {}
+    for _ in range(2):
+        rank, ranges, flat = q.get(timeout=120)
+        got[rank] = (ranges, flat)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ranges, flat = got[0]
+    n = 37
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and ranges[0][1] == ranges[1][0]
+    for r, (c0, c1) in enumerate(ranges):
+        want = (r + 1) * 1000.0 + torch.arange(2 * n * c0, 2 * n * c1, dtype=torch.float64)
+        assert torch.equal(flat[2 * n * c0:2 * n * c1], want)
+
+
+def test_column_ranges_balance_upper_triangle():
+    sweep = _load()
+    for n, w in ((20280, 8), (501, 4), (10, 3), (5, 8)):
+        rs = sweep.column_ranges(n, w)
+        assert rs[0][0] == 0 and rs[-1][1] == n and all(a[1] == b[0] for a, b in zip(rs, rs[1:])) and all(c1 >= c0 for c0, c1 in rs)
+    rs = sweep.column_ranges(20280, 8)
+    areas = [c1 * c1 - c0 * c0 for c0, c1 in rs]
+    assert max(areas) / min(areas) < 1.01
