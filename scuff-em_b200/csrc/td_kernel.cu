@@ -4,6 +4,7 @@
 // reference's tolerances (RelTol 1e-10, MaxEval 1000), its function-value cache living in a strided
 // HBM scratch block.
 #include <vector>
+#include <cstdlib>
 #include "kernels.h"
 #include "stamp.cuh"
 #include "td_math.cuh"
@@ -50,6 +51,141 @@ td_ct_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, d
   if (st) return;     // needs more Clenshaw-Curtis levels than this pass holds: redone by the next pass
   scatter_ppi(A.S, A.K, N.pa, N.pb, ea, eb, Pa.sl[i], Pb.sl[j], H0, H1);
   atomicAdd(A.counters + 2, (A.S.symmetric && N.pa != N.pb && ea == eb) ? 2ull : 1ull);
+}
+
+// Cooperative pair-level kernel.  All (Q_a,Q_b) combinations of a common-triangle panel pair share the expensive part of
+// the reduced integrand — K_n(X_d(y)) depends only on the triangle and k — so TD_GROUP lanes take one PAIR: the 2^m new
+// points of Clenshaw-Curtis level m are evaluated in parallel by the lanes (K once per point, then the <= 9 polynomial
+// contractions), the quadrature sums are reduced with warp shuffles, and every item keeps its own convergence state, so
+// each one stops exactly where the reference's independent pcubature call stops (pcubature.c: RelTol 1e-10 per
+// component, numEval > MaxEval = 1000); only the floating-point summation order of the quadrature sum differs.
+#define TD_GROUP 8
+#define TD_COOP_MAXM 9
+#define TD_COOP_NPTS ((1 << (TD_COOP_MAXM + 1)) + 1)
+#define TD_COOP_UDBL 64                                          /* doubles of coefficients per item (60 used) */
+#define TD_COOP_PAIR_DBL (9 * TD_COOP_UDBL + 9 * 4 * TD_COOP_NPTS)  /* scratch doubles per pair */
+
+// f[it][0..3] for all items of the pair at one point y
+__device__ void td_ct_pair_eval(double A2, double AdB, double B2, cd k, int nLo, int nHi, int nIt, const double *Uc, const int *nmm,
+                                double y, double *fout /* [nIt][4] at stride 4 */)
+{ double X[3], u1, u2;
+  u1 = 1.0; u2 = y;       X[0] = sqrt(A2 * u1 * u1 + 2.0 * AdB * u1 * u2 + B2 * u2 * u2);
+  u1 = y;   u2 = (y - 1); X[1] = sqrt(A2 * u1 * u1 + 2.0 * AdB * u1 * u2 + B2 * u2 * u2);
+  u1 = y;   u2 = 1.0;     X[2] = sqrt(A2 * u1 * u1 + 2.0 * AdB * u1 * u2 + B2 * u2 * u2);
+  const cd IK = mk(-k.y, k.x);
+  cd K[3][7];
+  for (int d = 0; d < 3; d++)
+   { cd IKX = mk(IK.x * X[d], IK.y * X[d]), eIKX = cexp_(IKX), mIKX = mk(-IKX.x, -IKX.y);
+     const bool small = (mIKX.y == 0.0) ? (fabs(mIKX.x) < 0.1) : (cabs_(mIKX) < 0.1);
+     cd emIKX = mk(0.0, 0.0);
+     if (!small) emIKX = (mIKX.y == 0.0) ? mk(exp(mIKX.x), 0.0) : cexp_(mIKX);
+     for (int n = nLo + 1; n <= nHi + 1; n++)
+      { cd t = eIKX * exprel_v3p0_pre(n, mIKX, emIKX, small); double dn = n * X[d]; K[d][n] = mk(t.x / dn, t.y / dn); }
+   }
+  const double s = 1.0 / (4.0 * M_PI);
+  for (int it = 0; it < nIt; it++)
+   { const double *U = Uc + it * TD_COOP_UDBL;        // [np][d][n][2]
+     for (int np = 0; np < 2; np++)
+      { cd Sum = mk(0.0, 0.0);
+        for (int n = nmm[4 * it + 2 * np]; n <= nmm[4 * it + 2 * np + 1]; n++)
+         for (int d = 0; d < 3; d++)
+          { const double *u = U + ((np * 3 + d) * TD_NUMWPOWERS + n) * 2;
+            Sum += (u[0] + y * u[1]) * K[d][n + 1]; }
+        fout[4 * it + 2 * np] = Sum.x * s; fout[4 * it + 2 * np + 1] = Sum.y * s;
+      }
+   }
+}
+
+// pairs[g] = 512*nearIndex + 9-bit mask of the (i,j) combinations (bit 3i+j) that feed a matrix entry
+__global__ void __launch_bounds__(128)
+td_ct_pair_kernel(const NearArgs A, const TDTables T, const int *pairs, int nPairs, double *scratch, int *pairStatus)
+{ const int g = (blockIdx.x * blockDim.x + threadIdx.x) / TD_GROUP;
+  const int gl = threadIdx.x & (TD_GROUP - 1);
+  if (g >= nPairs) return;                                                  // whole groups leave together
+  const unsigned gmask = ((1u << TD_GROUP) - 1u) << ((threadIdx.x & 31) & ~(TD_GROUP - 1));
+  const int code = pairs[g];
+  const NearPair N = A.near[code >> 9];
+  const PanelRec &Pa = A.pa[N.pa], &Pb = A.pb[N.pb];
+  int itIJ[9], nIt = 0;
+  for (int b = 0; b < 9; b++) if (code & (1 << b)) itIJ[nIt++] = b;
+  double Va[9], Vb[9];
+  for (int q = 0; q < 9; q++) { Va[q] = Pa.V[q]; Vb[q] = A.useDisp ? (Pb.V[q] + 1.0 * A.L[q % 3]) : Pb.V[q]; }
+  const cd k = mk(A.K.kr, A.K.ki);
+  double *Uc = scratch + (size_t)g * TD_COOP_PAIR_DBL;                      // [it][64]
+  double *cache = Uc + 9 * TD_COOP_UDBL;                                    // [point][nIt][4]
+  __shared__ int s_nmm[128 / TD_GROUP][36];                                 // nMin/nMax per item and polynomial
+  int *nmm = s_nmm[threadIdx.x / TD_GROUP];
+  double A2 = 0, AdB = 0, B2 = 0;
+  { // per-item polynomial coefficients (lanes split the items); the geometric parameters are item independent
+    TDCommonTriangle W;
+    for (int it = gl; it < nIt + TD_GROUP; it += TD_GROUP)
+     { const int itc = it < nIt ? it : 0;
+       td_ct_setup(T, Va + 3 * N.ia[0], Va + 3 * N.ia[1], Va + 3 * N.ia[2], Va + 3 * (itIJ[itc] / 3), Vb + 3 * (itIJ[itc] % 3), k, W);
+       A2 = W.A2; AdB = W.AdB; B2 = W.B2;
+       if (it < nIt)
+        { double *U = Uc + it * TD_COOP_UDBL;
+          for (int np = 0; np < 2; np++) for (int d = 0; d < 3; d++) for (int n = 0; n < TD_NUMWPOWERS; n++)
+           { U[((np * 3 + d) * TD_NUMWPOWERS + n) * 2] = W.U[np][d][n][0]; U[((np * 3 + d) * TD_NUMWPOWERS + n) * 2 + 1] = W.U[np][d][n][1]; }
+          nmm[4 * it] = W.nMin[0]; nmm[4 * it + 1] = W.nMax[0]; nmm[4 * it + 2] = W.nMin[1]; nmm[4 * it + 3] = W.nMax[1]; }
+       if (it >= nIt) break;
+     }
+  }
+  __syncwarp(gmask);
+  int nLo = TD_NUMWPOWERS, nHi = -1;
+  for (int q = 0; q < 2 * nIt; q++) { nLo = min(nLo, nmm[2 * q]); nHi = max(nHi, nmm[2 * q + 1]); }
+  const double c = 0.5, r = 0.5, V = 0.5;
+  const int pstride = 4 * nIt;
+  if (gl < 3)
+   { const double y = (gl == 0) ? c : (gl == 1 ? c + r * T.ccx[0] : c - r * T.ccx[0]);
+     td_ct_pair_eval(A2, AdB, B2, k, nLo, nHi, nIt, Uc, nmm, y, cache + (size_t)gl * pstride); }
+  __syncwarp(gmask);
+  int m = 0, numEval = 0, st = 0;
+  unsigned active = (1u << nIt) - 1u;
+  double prev[9][4], fin[9][4];
+  for (;;)
+   { const double *wb = T.ccw + m + (1 << m) - 1;
+     const int npts = (1 << (m + 1)) + 1;
+     const bool budget = numEval > 1000;
+     for (int it = 0; it < nIt; it++)
+      { if (!(active & (1u << it))) continue;
+        double acc[4] = { 0, 0, 0, 0 };
+        for (int e = gl; e < npts; e += TD_GROUP)
+         { const double w = V * (e == 0 ? wb[0] : wb[1 + ((e - 1) >> 1)]);
+           const double *cv = cache + (size_t)e * pstride + 4 * it;
+           for (int q = 0; q < 4; q++) acc[q] += cv[q] * w; }
+#pragma unroll
+        for (int o = TD_GROUP / 2; o > 0; o >>= 1)
+         for (int q = 0; q < 4; q++) acc[q] += __shfl_xor_sync(gmask, acc[q], o);
+        if (m == 0) for (int q = 0; q < 4; q++) prev[it][q] = cache[4 * it + q] * (V * 2);   // trivial (midpoint) rule
+        bool conv = true;
+        for (int q = 0; q < 4; q++)
+         { const double err = fabs(acc[q] - prev[it][q]); prev[it][q] = acc[q];
+           if (err > 0.0 && err > fabs(acc[q]) * 1.0e-10) conv = false; }
+        if (conv || budget) { for (int q = 0; q < 4; q++) fin[it][q] = acc[q]; active &= ~(1u << it); }
+      }
+     if (!active) break;
+     m += 1;
+     if (m > TD_COOP_MAXM) { st = 1; break; }
+     const int nx = 1 << (m - 1);
+     const double *x = T.ccx + nx;
+     double *cvl = cache + (size_t)((1 << m) + 1) * pstride;
+     for (int q2 = gl; q2 < 2 * nx; q2 += TD_GROUP)
+      { const double y = (q2 & 1) ? c - r * x[q2 >> 1] : c + r * x[q2 >> 1];
+        td_ct_pair_eval(A2, AdB, B2, k, nLo, nHi, nIt, Uc, nmm, y, cvl + (size_t)q2 * pstride); }
+     __syncwarp(gmask);
+     numEval += 2 * nx;
+   }
+  if (gl == 0) pairStatus[g] = st;
+  if (st) return;
+  const cd k2 = k * k;
+  for (int it = gl; it < nIt; it += TD_GROUP)
+   { const int i = itIJ[it] / 3, j = itIJ[it] % 3;
+     const int ea = Pa.ei[i], eb = Pb.ei[j];
+     const cd R0 = mk(fin[it][0], fin[it][1]), R1 = mk(fin[it][2], fin[it][3]);
+     const cd H0 = R1 - cdiv(mk(4.0 * R0.x, 4.0 * R0.y), k2), H1 = mk(0.0, 0.0);
+     scatter_ppi(A.S, A.K, N.pa, N.pb, ea, eb, Pa.sl[i], Pb.sl[j], H0, H1);
+     atomicAdd(A.counters + 2, (A.S.symmetric && N.pa != N.pb && ea == eb) ? 2ull : 1ull);
+   }
 }
 
 static int td_grow_scratch(scuffcuda_context *ctx, size_t need)
@@ -116,6 +252,36 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
   if (items.empty()) return 0;
   TDTables T; if (td_tables(ctx, T)) return 1;
   std::vector<int> work(items);
+  static int coopEnv = -1;
+  if (coopEnv < 0) { const char *e = getenv("SCUFF_CUDA_TD_COOP"); coopEnv = e ? atoi(e) : 1; }
+  if (coopEnv)
+   { // cooperative pair-level kernel: group the items by panel pair (items of a pair are contiguous in `work`)
+     std::vector<int> pairs;
+     for (size_t q = 0; q < work.size(); q++)
+      { const int n = work[q] / 9, b = work[q] % 9;
+        if (!pairs.empty() && (pairs.back() >> 9) == n) pairs.back() |= (1 << b); else pairs.push_back(512 * n + (1 << b)); }
+     const size_t perPair = (size_t)TD_COOP_PAIR_DBL * sizeof(double);
+     const int batch = (int)std::min<size_t>(pairs.size(), ((size_t)12 << 30) / perPair);
+     const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
+     if (td_grow_scratch(ctx, hdr + (size_t)batch * perPair)) return 1;
+     int *dPairs = (int *)ctx->dscratch, *dStatus = dPairs + batch;
+     double *scr = (double *)((char *)ctx->dscratch + hdr);
+     std::vector<int> status;
+     for (size_t first = 0; first < pairs.size(); first += batch)
+      { const int n = (int)std::min<size_t>(batch, pairs.size() - first);
+        cudaMemcpyAsync(dPairs, pairs.data() + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+        ctx->launches++;
+        const long threads = (long)n * TD_GROUP;
+        td_ct_pair_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(A, T, dPairs, n, scr, dStatus);
+        status.resize(n);
+        cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->err = std::string("td_ct_pair_kernel: ") + cudaGetErrorString(e); return 1; }
+        for (int q = 0; q < n; q++)
+         if (status[q]) { ctx->err = "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"; return 1; }
+      }
+     return 0;
+   }
   // pass 0: every item at once with room for Clenshaw-Curtis levels <= 6 (129 points; the common case),
   // pass 1: the items that asked for more, with the full MaxEval=1000 budget (level 9, 1025 points), in batches
   // with HBM to spare every item gets room for the full budget at once (level 9: 64 KB per item) and nobody restarts

@@ -115,7 +115,8 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
    for (int nsp = nspStart * ns; nsp < NumSurfaces; nsp++)
     { int nsm;
       if (Partial && (BFIndexOffset[nsp] >= ColEnd || BFIndexOffset[nsp] + Surfaces[nsp]->NumBFs <= ColBegin)) continue;
-      if (ns == nsp && (nsm = Mate[ns]) != -1)
+      // (column-block mode assembles mates directly: the mate's diagonal block may belong to another rank)
+      if (!Partial && ns == nsp && (nsm = Mate[ns]) != -1)
        { int ThisOffset = BFIndexOffset[ns], MateOffset = BFIndexOffset[nsm], Dim = Surfaces[ns]->NumBFs;
          SyncDeviceGeometry();
          if (scuffcuda_matrix_copy_block(ctx, M->DeviceHandle, ThisOffset, ThisOffset, Dim, Dim, MateOffset, MateOffset))
