@@ -19,6 +19,7 @@
 // bulk copy (cp.async.bulk + mbarrier; a tile of PanelRec is contiguous) and read by broadcast — x 128 b-panels, one
 // per lane, whose cubature points stay in registers for the whole tile.  FP64-pipe bound.
 #include <stdint.h>
+#include <algorithm>
 #include <cstdlib>
 #include "context.h"
 #include "classify.cuh"
@@ -96,6 +97,67 @@ __device__ __forceinline__ void helm_fast<KMODE_CPLX, true, cd>(double r2, doubl
   const double a = -K.ki * rinv - rinv * rinv, b = K.kr * rinv;
   Psi = mk(fma(Phi.x, a, -Phi.y * b), fma(Phi.x, b, Phi.y * a));
 }
+
+// "Small-phase" variant for fine meshes: every point pair of a far panel pair has r = r0 + delta with r0 = |C_a - C_b| and
+// |delta| <= R_a + R_b.  When |k| (R_a + R_b) <= 1/8 for all panels (the launcher checks), exp(ik r) = exp(ik r0) exp(ik delta):
+// the pair factor is applied ONCE to the accumulated moments (they are linear in Phi and Psi), and exp(ik delta) needs no
+// range reduction, no quadrant logic and only degree-9/10 Taylor polynomials (truncation < 3e-18 at |t| <= 1/8).
+template <int KMODE, bool PSI, typename S>
+__device__ __forceinline__ void helm_small(double r2, double cw, const KParams &K, double r0, S &Phi, S &Psi);
+
+__device__ __forceinline__ void sincos_small(double t, double &s, double &c)
+{ const double z = t * t;
+  double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);       // 1/9!, -1/7!
+  ps = fma(z, ps, 8.3333333333333332e-03); ps = fma(z, ps, -1.6666666666666666e-01);
+  s = fma(t * z, ps, t);
+  double pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);        // -1/10!, 1/8!
+  pc = fma(z, pc, -1.3888888888888889e-03); pc = fma(z, pc, 4.1666666666666664e-02); pc = fma(z, pc, -0.5);
+  c = fma(z, pc, 1.0);
+}
+__device__ __forceinline__ double exp_small(double s)                          // |s| <= 1/8, Taylor to s^10
+{ double p = 2.7557319223985888e-07;
+  p = fma(p, s, 2.7557319223985893e-06); p = fma(p, s, 2.4801587301587302e-05); p = fma(p, s, 1.9841269841269841e-04);
+  p = fma(p, s, 1.3888888888888889e-03); p = fma(p, s, 8.3333333333333332e-03); p = fma(p, s, 4.1666666666666664e-02);
+  p = fma(p, s, 1.6666666666666666e-01); p = fma(p, s, 0.5); p = fma(p, s, 1.0);
+  return fma(p, s, 1.0);
+}
+template <>
+__device__ __forceinline__ void helm_small<KMODE_REAL, false, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  double s, c; sincos_small(K.kr * (r - r0), s, c);
+  const double f = cw * rinv;
+  Phi = mk(f * c, f * s);
+}
+template <>
+__device__ __forceinline__ void helm_small<KMODE_REAL, true, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  double s, c; sincos_small(K.kr * (r - r0), s, c);
+  const double f = cw * rinv;
+  Phi = mk(f * c, f * s);
+  const double a = -rinv * rinv, b = K.kr * rinv;
+  Psi = mk(fma(Phi.x, a, -Phi.y * b), fma(Phi.x, b, Phi.y * a));
+}
+template <>
+__device__ __forceinline__ void helm_small<KMODE_IMAG, false, double>(double r2, double cw, const KParams &K, double r0, double &Phi, double &Psi)
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  Phi = cw * rinv * exp_small(-K.ki * (r - r0));
+}
+template <>
+__device__ __forceinline__ void helm_small<KMODE_IMAG, true, double>(double r2, double cw, const KParams &K, double r0, double &Phi, double &Psi)
+{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  Phi = cw * rinv * exp_small(-K.ki * (r - r0));
+  Psi = Phi * (-K.ki - rinv) * rinv;
+}
+// general complex k never takes the small-phase path (the launcher does not select it)
+template <>
+__device__ __forceinline__ void helm_small<KMODE_CPLX, false, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+{ helm_fast<KMODE_CPLX, false, cd>(r2, cw, K, Phi, Psi); }
+template <>
+__device__ __forceinline__ void helm_small<KMODE_CPLX, true, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+{ helm_fast<KMODE_CPLX, true, cd>(r2, cw, K, Phi, Psi); }
+
+__device__ __forceinline__ void smul(double &a, double f) { a *= f; }
+__device__ __forceinline__ void smul(cd &a, cd f) { a = mk(fma(a.x, f.x, -a.y * f.y), fma(a.x, f.y, a.y * f.x)); }
 
 __device__ __forceinline__ void sadd(double &a, double b) { a += b; }
 __device__ __forceinline__ void sadd(cd &a, cd b) { a.x += b.x; a.y += b.y; }
@@ -204,7 +266,7 @@ __device__ __forceinline__ bool pair_is_far(const double *Ca, double Ra, const d
 // Thread mapping: lane <-> a-panel (matrix ROW side), tile <-> b-panels (column side).  The matrix is column-major, so
 // the RED.ADD.F64 of one warp for entry (e_a(lane), e_b) go to neighbouring rows of ONE column (edges of consecutive
 // panels are nearly consecutive) instead of 32 different columns: ~4-8x fewer L2 atomic sectors per warp instruction.
-template <int KMODE, bool PSI, int MINB>
+template <int KMODE, bool PSI, int MINB, bool SMALL>
 __global__ void __launch_bounds__(FAR_THREADS, MINB)
 far_kernel(const FarArgs A)
 { extern __shared__ __align__(128) double sm[];
@@ -273,6 +335,8 @@ far_kernel(const FarArgs A)
         if (hi < A.S.colLo || lo >= A.S.colHi) continue; }
      nPairs++;
 
+     double r0 = 0.0;
+     if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
      // ---- 3x3 barycentric moments m[m over a (outer loop: this lane's points)][n over b (inner loop: tile panel's points,
      //      broadcast shared-memory reads)] ----
      S mPhi[3][3], mPsi[3][3];
@@ -292,7 +356,8 @@ far_kernel(const FarArgs A)
          { const double R0 = y0 - Pb[13 + 3 * pp], R1 = y1 - Pb[14 + 3 * pp], R2 = y2 - Pb[15 + 3 * pp];
            const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
            S Phi, Psi;
-           helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
+           if (SMALL) helm_small<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, r0, Phi, Psi);
+           else helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
            sadd(a0_, Phi); fma_acc(au, tcr_u(pp), Phi); fma_acc(av, tcr_v(pp), Phi);
            if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi); }
          }
@@ -306,6 +371,16 @@ far_kernel(const FarArgs A)
            fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); }
       }
 
+     if (SMALL)
+      { // the pair factor exp(ik r0), once for all moments
+        S E0;
+        if (KMODE == KMODE_IMAG) { const double e = exp_neg_fast(-A.K.ki * r0); E0 = *reinterpret_cast<const S *>(&e); }
+        else { double s0, c0; sincos_fast(A.K.kr * r0, s0, c0); const cd e = mk(c0, s0); E0 = *reinterpret_cast<const S *>(&e); }
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+         for (int n = 0; n < 3; n++) { smul(mPhi[m][n], E0); if (PSI) smul(mPsi[m][n], E0); }
+      }
      // ---- contraction to the nine (Q_a,Q_b) combinations and scatter ----
      {
        int eia[3]; double sla[3], Aa[3], Ba[3], Ab[3], Bb[3], Va0[3], Vb0[3];
@@ -462,17 +537,24 @@ int run_fastmath_selftest(scuffcuda_context *ctx, int n, const double *xh, doubl
   return 0;
 }
 
-template <int KMODE, bool PSI, int MINB>
+template <int KMODE, bool PSI, int MINB, bool SMALL>
 static void launch_far_inst(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem)
 { // ask for the shared-memory carve-out that lets MINB CTAs (~46 KB each) share an SM
-  cudaFuncSetAttribute(far_kernel<KMODE, PSI, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  far_kernel<KMODE, PSI, MINB><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
+  cudaFuncSetAttribute(far_kernel<KMODE, PSI, MINB, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  far_kernel<KMODE, PSI, MINB, SMALL><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
 }
+// resident CTAs per SM: 4 (128 registers) for the PEC variant, 3 (168) with the Psi half — measured best (3 / 4 / 5 tried)
 template <int KMODE>
-static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi, int minb)
-{ if (psi) { if (minb >= 3) launch_far_inst<KMODE, true, 3>(ctx, A, grid, smem); else launch_far_inst<KMODE, true, 2>(ctx, A, grid, smem); }
-  else { if (minb >= 5) launch_far_inst<KMODE, false, 5>(ctx, A, grid, smem); else if (minb == 4) launch_far_inst<KMODE, false, 4>(ctx, A, grid, smem);
-         else launch_far_inst<KMODE, false, 3>(ctx, A, grid, smem); }
+static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi, bool small)
+{ if (psi) { if (small) launch_far_inst<KMODE, true, 3, true>(ctx, A, grid, smem); else launch_far_inst<KMODE, true, 3, false>(ctx, A, grid, smem); }
+  else { if (small) launch_far_inst<KMODE, false, 4, true>(ctx, A, grid, smem); else launch_far_inst<KMODE, false, 4, false>(ctx, A, grid, smem); }
+}
+
+// largest panel radius of the surface whose device panels are `d`
+static double surface_rmax(scuffcuda_context *ctx, const PanelRec *d)
+{ for (const Surface &S : ctx->surfaces)
+   if (S.dpanels == d) { double r = 0.0; for (const PanelRec &P : S.hpanels) r = std::max(r, P.R); return r; }
+  return 1.0e300;
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
@@ -481,19 +563,20 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   // machine on small meshes, 32 on large ones
   int aTiles = (A.NPa + FAR_THREADS - 1) / FAR_THREADS;
   const bool psi = !(A.S.aPEC && A.S.bPEC);     // PEC/PEC blocks stamp GC[0] only
-  // resident CTAs per SM (register budget 168 / 128 / 96 per thread): tuning knob, default from measurements
-  static int minbEnv = -1;
-  if (minbEnv < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB"); minbEnv = e ? atoi(e) : 0; }
-  const int minb = minbEnv > 0 ? minbEnv : (psi ? 3 : 4);
-  int TB = (minb >= 5) ? 16 : 32;              // 5 CTAs/SM need the smaller tile to fit shared memory
+  int TB = 32;
   while (TB > 2 && (long)aTiles * ((A.NPb + TB - 1) / TB) < 4L * ctx->smCount) TB >>= 1;
   A.TA = TB;
   dim3 grid(aTiles, (A.NPb + TB - 1) / TB);
   size_t smem = FAR_SMEM_BYTES(TB);
+  // small-phase variant when |k| (R_a + R_b) <= 1/8 for every panel pair (fine meshes); SCUFF_CUDA_FAR_SMALL=0 disables
+  static int smallEnv = -1;
+  if (smallEnv < 0) { const char *e = getenv("SCUFF_CUDA_FAR_SMALL"); smallEnv = e ? atoi(e) : 1; }
+  const double kk = (kmode == KMODE_REAL) ? fabs(A.K.kr) : fabs(A.K.ki);
+  const bool small = smallEnv && kmode != KMODE_CPLX && kk * (surface_rmax(ctx, A.pa) + surface_rmax(ctx, A.pb)) <= 0.125;
   ctx->launches++;
-  if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi, minb);
-  else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi, minb);
-  else launch_far_mode<KMODE_CPLX>(ctx, A, grid, smem, psi, minb);
+  if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi, small);
+  else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi, small);
+  else launch_far_mode<KMODE_CPLX>(ctx, A, grid, smem, psi, small);
 }
 
 }  // namespace scuffcuda

@@ -123,7 +123,11 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
           ErrExit("%s", scuffcuda_last_error(ctx));
          M->HostStale = true; }
       else if (LBasis == 0)
-       AssembleBlockOnDevice(this, ns, nsp, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false, ColBegin, ColEnd);
+       { // column-block mode: a mated diagonal block takes its mate's values (as the Mate copy does; the two differ at the
+         // 1e-9 level through the float-precision FIPPI keys), computed here from the mate's panels into this block
+         int nsA = ns, nsB = nsp;
+         if (Partial && ns == nsp && Mate[ns] != -1) nsA = nsB = Mate[ns];
+         AssembleBlockOnDevice(this, nsA, nsB, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false, ColBegin, ColEnd); }
       else
        AssembleBEMMatrixBlockPBC(ns, nsp, Omega, kBloch, M, BFIndexOffset[ns], BFIndexOffset[nsp]);
     }
