@@ -16,7 +16,7 @@ GEODIR = os.path.join(HERE, "geometries")
 DRV = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
 NAMES = ["PECSphere_501", "PECSphere_255", "PECSphere_R0P75_414", "PECSpheres_255", "PECSpheres_327", "SiO2Sphere_501",
          "GoldSphere_501", "SiSphere_255", "SiSpheres_255", "LossySphere_327", "E10Spheres_327", "PECPlate_40", "SiSlab_40",
-         "SphereSlabArray"]
+         "SphereSlabArray", "OpenPlate_40"]
 CASES = [("PECSphere_501", 1.0, False), ("PECSphere_501", 0.01, False), ("PECSphere_255", 0.1j, False),
          ("PECSphere_255", 0.1j, True), ("PECSphere_255", 1.0, False), ("SiO2Sphere_501", 1.0, False),
          ("SiSphere_255", 0.01, False), ("PECSpheres_255", 0.1, False), ("SiSpheres_255", 0.1, False),

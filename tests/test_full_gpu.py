@@ -13,7 +13,8 @@ TOL = 1e-10
 CASES = [("PECSphere_501", 1.0, False), ("PECSphere_501", 0.01, False), ("PECSphere_255", 0.1j, False),
          ("PECSphere_255", 0.1j, True), ("SiO2Sphere_501", 1.0, False), ("SiSphere_255", 0.01, False),
          ("PECSpheres_255", 0.1, False), ("SiSpheres_255", 0.1, False), ("LossySphere_327", 1.0, False),
-         ("PECSpheres_327", 1.0j, True), ("E10Spheres_327", 0.5j, False), ("GoldSphere_501", 0.3, False)]
+         ("PECSpheres_327", 1.0j, True), ("E10Spheres_327", 0.5j, False), ("GoldSphere_501", 0.3, False),
+         ("OpenPlate_40", 1.0, False), ("OpenPlate_40", 2.0j, True)]   # open PEC surface: exterior edges carry no basis function
 
 
 def block_errors(G, M, Mref):

@@ -7,7 +7,7 @@ import pytest
 from conftest import GEODIR, GOLDEN
 
 COMPACT = ["PECSphere_501", "PECSphere_255", "PECSphere_R0P75_414", "PECSpheres_255", "PECSpheres_327",
-           "SiO2Sphere_501", "GoldSphere_501", "SiSphere_255", "SiSpheres_255", "LossySphere_327", "E10Spheres_327"]
+           "SiO2Sphere_501", "GoldSphere_501", "SiSphere_255", "SiSpheres_255", "LossySphere_327", "E10Spheres_327", "OpenPlate_40"]
 
 
 def parse_dump(fn):
