@@ -33,7 +33,12 @@ def block_errors(G, M, Mref):
 def test_full_matrix(ps, name, omega, imag, tmp_path):
     geo = os.path.join(GEODIR, name + ".scuffgeo")
     cache = str(tmp_path / "ref.cache")
-    Mref, info = ref_matrix(geo, omega, imag=imag, cache_out=cache)
+    # On structured meshes (all panels congruent) the multi-threaded reference is not reproducible against ITSELF to 1e-10:
+    # threads that miss the translation-invariant FIPPI cache simultaneously each use their own record and only one is
+    # stored (measured run-to-run 1.6e-10 .. 4.9e-10 on OpenPlate_40, 1.5e-8 vs its own single-threaded run).  The
+    # single-threaded reference is deterministic and is what the stored cache describes.
+    env = {"OMP_NUM_THREADS": "1"} if name.startswith("OpenPlate") else None
+    Mref, info = ref_matrix(geo, omega, imag=imag, cache_out=cache, env=env)
     ps.PreloadCache(cache)
     G = ps.RWGGeometry(geo)
     Mh = G.AllocateBEMMatrix(imag)
