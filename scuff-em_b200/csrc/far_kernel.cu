@@ -548,7 +548,12 @@ static void launch_far_inst(scuffcuda_context *ctx, const FarArgs &A, dim3 grid,
 // resident CTAs per SM: 4 (128 registers) for the PEC variant, 3 (168) with the Psi half — measured best (3 / 4 / 5 tried)
 template <int KMODE>
 static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi, bool small)
-{ if (psi) { if (small) launch_far_inst<KMODE, true, 3, true>(ctx, A, grid, smem); else launch_far_inst<KMODE, true, 3, false>(ctx, A, grid, smem); }
+{ static int psiMinb = -1;
+  if (psiMinb < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB_PSI"); psiMinb = e ? atoi(e) : 3; }
+  if (psi)
+   { if (small) launch_far_inst<KMODE, true, 3, true>(ctx, A, grid, smem);
+     else if (psiMinb == 2) launch_far_inst<KMODE, true, 2, false>(ctx, A, grid, smem);
+     else launch_far_inst<KMODE, true, 3, false>(ctx, A, grid, smem); }
   else { if (small) launch_far_inst<KMODE, false, 4, true>(ctx, A, grid, smem); else launch_far_inst<KMODE, false, 4, false>(ctx, A, grid, smem); }
 }
 

@@ -127,7 +127,9 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
          // 1e-9 level through the float-precision FIPPI keys), computed here from the mate's panels into this block
          int nsA = ns, nsB = nsp;
          if (Partial && ns == nsp && Mate[ns] != -1) nsA = nsB = Mate[ns];
-         AssembleBlockOnDevice(this, nsA, nsB, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false, ColBegin, ColEnd); }
+         // the whole matrix is mirrored once at the end: tell the block not to mirror itself (all columns, no mirror)
+         const int ce = (!Partial && MatrixIsSymmetric) ? 0x7fffffff : ColEnd;
+         AssembleBlockOnDevice(this, nsA, nsB, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false, ColBegin, ce); }
       else
        AssembleBEMMatrixBlockPBC(ns, nsp, Omega, kBloch, M, BFIndexOffset[ns], BFIndexOffset[nsp]);
     }
