@@ -6,7 +6,8 @@
  *
  *   ref_driver geom   <geo> <out.txt>
  *   ref_driver matrix <geo> <wRe> <wIm> <out.bin> [--kbloch kx ky] [--imag] [--repeat n]
- *                     [--cache-in f] [--cache-out f] [--block nsa nsb]
+ *                     [--cache-in f] [--cache-out f] [--block nsa nsb] [--transfile f --trans n]
+ *                     (--trans: apply the n-th transformation of a .trans file first, as scuff-cas3D does)
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
  *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
@@ -68,7 +69,7 @@ int main(int argc, char **argv)
   if(!strcmp(Cmd,"matrix"))
    { cdouble Omega(atof(argv[3]),atof(argv[4])); const char *Out=argv[5];
      double kBloch[2]; bool HavekBloch=false, Imag=false; int Repeat=1;
-     const char *CacheIn=0,*CacheOut=0; int nsa=-1,nsb=-1;
+     const char *CacheIn=0,*CacheOut=0,*TransFile=0; int nsa=-1,nsb=-1,nTrans=-1;
      for(int n=6;n<argc;n++)
       { if(!strcmp(argv[n],"--kbloch")) { kBloch[0]=atof(argv[n+1]); kBloch[1]=atof(argv[n+2]); HavekBloch=true; n+=2; }
         else if(!strcmp(argv[n],"--imag")) Imag=true;
@@ -76,6 +77,13 @@ int main(int argc, char **argv)
         else if(!strcmp(argv[n],"--cache-in")) CacheIn=argv[++n];
         else if(!strcmp(argv[n],"--cache-out")) CacheOut=argv[++n];
         else if(!strcmp(argv[n],"--block")) { nsa=atoi(argv[n+1]); nsb=atoi(argv[n+2]); n+=2; }
+        else if(!strcmp(argv[n],"--transfile")) TransFile=argv[++n];
+        else if(!strcmp(argv[n],"--trans")) nTrans=atoi(argv[++n]);
+      }
+     if(TransFile && nTrans>=0)
+      { GTCList GTCs=ReadTransFile(TransFile);
+        if(nTrans>=(int)GTCs.size()) { fprintf(stderr,"no transformation %i in %s\n",nTrans,TransFile); return 2; }
+        G->Transform(GTCs[nTrans]);
       }
      if(CacheIn) PreloadCache(CacheIn);
      HMatrix *M;

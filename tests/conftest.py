@@ -49,12 +49,12 @@ def have_ref():
     return os.path.exists(REF_DRIVER)
 
 
-def ref_matrix(geo, omega, kbloch=None, imag=False, block=None, cache_in=None, cache_out=None, tmpdir="/tmp/scuff_ref_cache", env=None):
+def ref_matrix(geo, omega, kbloch=None, imag=False, block=None, cache_in=None, cache_out=None, tmpdir="/tmp/scuff_ref_cache", env=None, trans=None):
     """Run the UNMODIFIED reference (oracle/_ref/ref_driver) and return (M, info).  Results are cached on disk."""
     if not have_ref():
         pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
     os.makedirs(tmpdir, exist_ok=True)
-    key = hashlib.md5(repr((geo, complex(omega), kbloch, imag, block, cache_in, sorted((env or {}).items()))).encode()).hexdigest()[:16]
+    key = hashlib.md5(repr((geo, complex(omega), kbloch, imag, block, cache_in, sorted((env or {}).items()), trans)).encode()).hexdigest()[:16]
     out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
     meta = out + ".json"
     if not (os.path.exists(out) and os.path.exists(meta)) or cache_out:
@@ -69,6 +69,8 @@ def ref_matrix(geo, omega, kbloch=None, imag=False, block=None, cache_in=None, c
             cmd += ["--cache-in", cache_in]
         if cache_out:
             cmd += ["--cache-out", cache_out]
+        if trans is not None:
+            cmd += ["--transfile", trans[0], "--trans", str(trans[1])]
         r = subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True,
                            env=dict(os.environ, **(env or {})))
         open(meta, "w").write(r.stdout.strip().splitlines()[-1])
