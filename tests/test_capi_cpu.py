@@ -51,3 +51,14 @@ def test_ssi_args_layout(ps):
         subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
         n = int(subprocess.run([exe], capture_output=True, text=True, check=True).stdout)
     assert n == C.sizeof(ps.SSIArgs)
+
+
+def test_argument_checks_before_any_device_work(ps):
+    """errors the reference raises from AssembleBEMMatrix itself (AssembleBEMMatrix.cc:692-695) need no device"""
+    G = ps.RWGGeometry(os.path.join(ROOT, "tests", "golden", "geometries", "PECSphere_255.scuffgeo"))
+    with pytest.raises(ps.ScuffError, match="Bloch wavevector is undefined for compact"):
+        G.AssembleBEMMatrix(1.0, kBloch=(0.1, 0.2))
+    P = ps.RWGGeometry(os.path.join(ROOT, "tests", "golden", "geometries", "SiSlab_40.scuffgeo"))
+    assert P.LDim == 2
+    with pytest.raises(ps.ScuffError, match="Bloch wavevector must be specified"):
+        P.AssembleBEMMatrix(1.0)
