@@ -56,14 +56,16 @@ def gather_columns(flat, n, elem_doubles, ranges, rank, world, dst=0):
     NVLink); nothing is staged."""
     if world == 1:
         return
-    reqs = []
+    ops = []
     if rank == dst:
         for r, (c0, c1) in enumerate(ranges):
             if r != dst and c1 > c0:
-                reqs.append(dist.irecv(flat[c0 * n * elem_doubles:c1 * n * elem_doubles], src=r))
+                ops.append(dist.P2POp(dist.irecv, flat[c0 * n * elem_doubles:c1 * n * elem_doubles], r))
     else:
         c0, c1 = ranges[rank]
         if c1 > c0:
-            reqs.append(dist.isend(flat[c0 * n * elem_doubles:c1 * n * elem_doubles], dst=dst))
-    for q in reqs:
-        q.wait()
+            ops.append(dist.P2POp(dist.isend, flat[c0 * n * elem_doubles:c1 * n * elem_doubles], dst))
+    if ops:
+        # one batch: the receives from all peers progress concurrently (unbatched NCCL P2P ops are serialised)
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
