@@ -181,13 +181,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
                     : "=r"(ok) : "r"(b), "r"(phase) : "memory"); } while (!ok);
 }
 
-// out-of-line scatter for the dielectric (PSI) variant: nine inlined copies of the 2x2 stamp (8 atomics + 64-bit address
-// arithmetic each) made the kernel 74 KB of SASS and cost ~17 % of the cycles in instruction-fetch stalls
-template <bool PSI>
-__device__ __noinline__ void scatter_ppi_ool(const StampParams &SP, const KParams &K, int pa, int pb, int ea, int eb,
-                                             double sla, double slb, cd H0, cd H1)
-{ scatter_ppi<PSI>(SP, K, pa, pb, ea, eb, sla, slb, H0, H1); }
-
+// (an out-of-line scatter to shrink the 74 KB dielectric kernel was tried: the calls at 240 live registers made it 2x slower)
 // Contraction of the 3x3 moments to the nine (Q_a,Q_b) combinations and scatter into the matrix.
 // Va0/Aa/Ba: vertex 0 and edge vectors of panel a; Vb0 (already displaced by L), Ab, Bb of panel b.
 template <typename S, bool PSI>
@@ -244,8 +238,7 @@ __device__ __forceinline__ void contract_scatter(const S (&mPhi)[3][3], const S 
            S h1; szero(h1);
            fma_acc(h1, cAA, Pu); fma_acc(h1, cAB, Pv); fma_acc(h1, cBA, Qu); fma_acc(h1, cBB, Qv);
            H1 = tocd(h1); }
-        if (PSI) scatter_ppi_ool<PSI>(SP, K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
-        else scatter_ppi<PSI>(SP, K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
+        scatter_ppi<PSI>(SP, K, pa, pb, ea, eib[j], sla, slb[j], H0, H1);
         nPPI += (symmetric && pa != pb && ea == eib[j]) ? 2 : 1;
       }
    }

@@ -5,6 +5,8 @@
 // resident in HBM across the frequency sweep (ComputeQIFIPPIData QIFIPPICubature.cc:465-487).
 #include <vector>
 #include <algorithm>
+#include <thread>
+#include <string>
 #include "kernels.h"
 #include "fippi_build.cuh"
 #include "generated_tables.h"
@@ -56,34 +58,52 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
       c = (((float)V[3] == (float)V[12]) && ((float)V[4] == (float)V[13]) && ((float)V[5] == (float)V[14])) ? 1 : 2;
      byCase[c].push_back(i); }
   const fippi_launch_fn launchers[3] = { fippi_launch_case0, fippi_launch_case1, fippi_launch_case2 };
-  std::vector<int> todo;
-  for (int c = 0; c < 3; c++)
-   { todo = byCase[c];
-  // pass 1: small region pools, many records in flight; pass 2: the few records that need more regions
-  const int caps[3] = { 384, 4096, 15200 }; const int batches[3] = { 24576, 2048, 512 };
-  for (int pass = 0; pass < 3 && !todo.empty(); pass++)
-   { const int cap = caps[pass], batch = std::min(batches[pass], (int)todo.size());
-     size_t perThread = (size_t)cap * (FIPPI_REGION_BYTES + sizeof(int));
-     if (dpool) { cudaFree(dpool); dpool = nullptr; }
-     if (cudaMalloc(&dpool, perThread * batch) != cudaSuccess) { ctx->err = "FIPPI builder pool allocation failed"; cleanup(); return 1; }
-     std::vector<int> next, st(batch);
-     for (size_t first = 0; first < todo.size(); first += batch)
-      { int m = (int)std::min((size_t)batch, todo.size() - first);
-        cudaMemcpyAsync(ditems, todo.data() + first, m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
-        ctx->launches++;
-        launchers[c](ctx->stream, T, dverts, ditems, m, dpool, cap, dout, dstatus);
-        cudaMemcpyAsync(st.data(), dstatus, m * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) { ctx->err = std::string("fippi_build_kernel: ") + cudaGetErrorString(e); cleanup(); return 1; }
-        for (int i = 0; i < m; i++)
-         { if (st[i] == 3) { ctx->err = "FIPPI builder: integration case mismatch"; cleanup(); return 1; }
-           if (st[i]) next.push_back(todo[first + i]); }
-      }
-     todo.swap(next);
-   }
-     if (!todo.empty()) break;
-   }
-  if (!todo.empty()) { ctx->err = "FIPPI builder: region pool exhausted"; cleanup(); return 1; }
+  // The three integration cases run concurrently (one host thread + stream each): the 1-D / 2-D cases are short grids of
+  // long-running threads that would otherwise leave the GPU idle.  Within a case: pass 0 gives every record a small region
+  // pool, the records that need more are redone with larger pools; the batch of each pass is sized from the free HBM
+  // (a quarter each), so that even the rare 15 200-region records run thousands at a time.
+  size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+  const size_t budget = std::max<size_t>((size_t)1 << 30, freeB / 4);
+  std::string errs[3]; int rcs[3] = { 0, 0, 0 };
+  auto run_case = [&](int c)
+  { cudaSetDevice(ctx->device);
+    std::vector<int> todo = byCase[c];
+    if (todo.empty()) return;
+    cudaStream_t st_ = nullptr; cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking);
+    int *ditems_c = nullptr, *dstatus_c = nullptr; char *dpool_c = nullptr;
+    auto fail = [&](const std::string &m) { errs[c] = m; rcs[c] = 1; };
+    if (cudaMalloc(&ditems_c, todo.size() * sizeof(int)) != cudaSuccess || cudaMalloc(&dstatus_c, todo.size() * sizeof(int)) != cudaSuccess)
+     fail("FIPPI builder allocation failed");
+    const int caps[3] = { 384, 4096, 15200 };
+    for (int pass = 0; pass < 3 && !todo.empty() && !rcs[c]; pass++)
+     { const int cap = caps[pass];
+       const size_t perThread = (size_t)cap * (FIPPI_REGION_BYTES + sizeof(int));
+       const int batch = (int)std::min<size_t>(todo.size(), std::max<size_t>(64, budget / perThread));
+       if (dpool_c) { cudaFree(dpool_c); dpool_c = nullptr; }
+       if (cudaMalloc(&dpool_c, perThread * batch) != cudaSuccess) { cudaGetLastError(); fail("FIPPI builder pool allocation failed"); break; }
+       std::vector<int> next, st(batch);
+       for (size_t first = 0; first < todo.size() && !rcs[c]; first += batch)
+        { int m = (int)std::min((size_t)batch, todo.size() - first);
+          cudaMemcpyAsync(ditems_c, todo.data() + first, m * sizeof(int), cudaMemcpyHostToDevice, st_);
+          __atomic_fetch_add(&ctx->launches, 1ull, __ATOMIC_RELAXED);
+          launchers[c](st_, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c);
+          cudaMemcpyAsync(st.data(), dstatus_c, m * sizeof(int), cudaMemcpyDeviceToHost, st_);
+          cudaError_t e = cudaStreamSynchronize(st_);
+          if (e != cudaSuccess) { fail(std::string("fippi_build_kernel: ") + cudaGetErrorString(e)); break; }
+          for (int i = 0; i < m; i++)
+           { if (st[i] == 3) { fail("FIPPI builder: integration case mismatch"); break; }
+             if (st[i]) next.push_back(todo[first + i]); }
+        }
+       todo.swap(next);
+     }
+    if (!rcs[c] && !todo.empty()) fail("FIPPI builder: region pool exhausted");
+    cudaFree(ditems_c); cudaFree(dstatus_c); cudaFree(dpool_c); cudaStreamDestroy(st_);
+  };
+  cudaStreamSynchronize(ctx->stream);
+  { std::thread t1(run_case, 1), t2(run_case, 2);
+    run_case(0);
+    t1.join(); t2.join(); }
+  for (int c = 0; c < 3; c++) if (rcs[c]) { ctx->err = errs[c]; cleanup(); return 1; }
   std::vector<double> hout((size_t)n * FIPPI_REC_DOUBLES);
   cudaMemcpy(hout.data(), dout, hout.size() * sizeof(double), cudaMemcpyDeviceToHost);
   for (int i = 0; i < n; i++)
