@@ -347,29 +347,47 @@ far_kernel(const __grid_constant__ FarArgs A)
       for (int n = 0; n < 3; n++) { szero(mPhi[m][n]); szero(mPsi[m][n]); }
 
 #pragma unroll 1
-     for (int p = 0; p < 6; p++)
-      { // R = X_a - X_b = (x_a(lane) + D) - x_b(tile)
+     for (int p = 0; p < 6; p += 2)
+      { // two outer points per iteration share the broadcast loads of the tile panel's points and give the scheduler two
+        // independent dependency chains per inner point.  R = X_a - X_b = (x_a(lane) + D) - x_b(tile)
         const double y0 = sXa[(3 * p) * FAR_THREADS] + D[0], y1 = sXa[(3 * p + 1) * FAR_THREADS] + D[1], y2 = sXa[(3 * p + 2) * FAR_THREADS] + D[2];
-        S a0_, au, av, b0_, bu, bv;
+        const double z0 = sXa[(3 * p + 3) * FAR_THREADS] + D[0], z1 = sXa[(3 * p + 4) * FAR_THREADS] + D[1], z2 = sXa[(3 * p + 5) * FAR_THREADS] + D[2];
+        S a0_, au, av, b0_, bu, bv, c0_, cu, cv, d0_, du, dv;
         szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
+        szero(c0_); szero(cu); szero(cv); szero(d0_); szero(du); szero(dv);
 #pragma unroll
         for (int pp = 0; pp < 6; pp++)
-         { const double R0 = y0 - Pb[13 + 3 * pp], R1 = y1 - Pb[14 + 3 * pp], R2 = y2 - Pb[15 + 3 * pp];
+         { const double xb0 = Pb[13 + 3 * pp], xb1 = Pb[14 + 3 * pp], xb2 = Pb[15 + 3 * pp];
+           const double R0 = y0 - xb0, R1 = y1 - xb1, R2 = y2 - xb2;
+           const double Q0 = z0 - xb0, Q1 = z1 - xb1, Q2 = z2 - xb2;
            const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
-           S Phi, Psi;
-           if (SMALL) helm_small<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, r0, Phi, Psi);
-           else helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
+           const double q2 = fma(Q2, Q2, fma(Q1, Q1, Q0 * Q0));
+           S Phi, Psi, Phj, Psj;
+           if (SMALL) { helm_small<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, r0, Phi, Psi);
+                        helm_small<KMODE, PSI, S>(q2, SCUFF_OO4PI * tcr_w(pp), A.K, r0, Phj, Psj); }
+           else { helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
+                  helm_fast<KMODE, PSI, S>(q2, SCUFF_OO4PI * tcr_w(pp), A.K, Phj, Psj); }
            sadd(a0_, Phi); fma_acc(au, tcr_u(pp), Phi); fma_acc(av, tcr_v(pp), Phi);
-           if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi); }
+           sadd(c0_, Phj); fma_acc(cu, tcr_u(pp), Phj); fma_acc(cv, tcr_v(pp), Phj);
+           if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi);
+                      sadd(d0_, Psj); fma_acc(du, tcr_u(pp), Psj); fma_acc(dv, tcr_v(pp), Psj); }
          }
-        const double w0 = c_far_wm[p][0], w1 = c_far_wm[p][1], w2 = c_far_wm[p][2];
-        fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
-        fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
-        fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
-        if (PSI)
-         { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
-           fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
-           fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); }
+        { const double w0 = c_far_wm[p][0], w1 = c_far_wm[p][1], w2 = c_far_wm[p][2];
+          fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
+          fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
+          fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
+          if (PSI)
+           { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
+             fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
+             fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); } }
+        { const double w0 = c_far_wm[p + 1][0], w1 = c_far_wm[p + 1][1], w2 = c_far_wm[p + 1][2];
+          fma_acc(mPhi[0][0], w0, c0_); fma_acc(mPhi[0][1], w0, cu); fma_acc(mPhi[0][2], w0, cv);
+          fma_acc(mPhi[1][0], w1, c0_); fma_acc(mPhi[1][1], w1, cu); fma_acc(mPhi[1][2], w1, cv);
+          fma_acc(mPhi[2][0], w2, c0_); fma_acc(mPhi[2][1], w2, cu); fma_acc(mPhi[2][2], w2, cv);
+          if (PSI)
+           { fma_acc(mPsi[0][0], w0, d0_); fma_acc(mPsi[0][1], w0, du); fma_acc(mPsi[0][2], w0, dv);
+             fma_acc(mPsi[1][0], w1, d0_); fma_acc(mPsi[1][1], w1, du); fma_acc(mPsi[1][2], w1, dv);
+             fma_acc(mPsi[2][0], w2, d0_); fma_acc(mPsi[2][1], w2, du); fma_acc(mPsi[2][2], w2, dv); } }
       }
 
      if (SMALL)
@@ -555,7 +573,12 @@ static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid,
    { if (small) launch_far_inst<KMODE, true, 3, true>(ctx, A, grid, smem);
      else if (psiMinb == 2) launch_far_inst<KMODE, true, 2, false>(ctx, A, grid, smem);
      else launch_far_inst<KMODE, true, 3, false>(ctx, A, grid, smem); }
-  else { if (small) launch_far_inst<KMODE, false, 4, true>(ctx, A, grid, smem); else launch_far_inst<KMODE, false, 4, false>(ctx, A, grid, smem); }
+  else
+   { static int pecMinb = -1;
+     if (pecMinb < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB"); pecMinb = e ? atoi(e) : 3; }   // 3 CTAs/SM (165 registers, no spills) measured 2-4 % faster than 4 with the two-point loop
+     if (small) launch_far_inst<KMODE, false, 4, true>(ctx, A, grid, smem);
+     else if (pecMinb == 3) launch_far_inst<KMODE, false, 3, false>(ctx, A, grid, smem);
+     else launch_far_inst<KMODE, false, 4, false>(ctx, A, grid, smem); }
 }
 
 // largest panel radius of the surface whose device panels are `d`
