@@ -12,10 +12,10 @@
 
 namespace scuffcuda {
 
-#define FC_CAP 384                       /* regions per record in this pass (heap in shared memory) */
-#define FC_WARPS 4
 #define FC_F_DBL (33 * HC_FDIM)          /* function values of one region */
-#define FC_WARP_DBL (FC_F_DBL + 3 * HC_FDIM + FC_CAP + 4)   /* + |t| table + heap errmax + diff[3] */
+#define FC_FIXED_DBL (FC_F_DBL + 3 * HC_FDIM + 4)   /* + |t| table + diff[3] */
+// shared memory per warp for a region pool of `cap` regions: fixed part + heap errmax (double) + heap region index (short)
+__host__ __device__ inline size_t fc_warp_bytes(int cap) { return (((size_t)(FC_FIXED_DBL + cap) * 8 + (size_t)cap * 2) + 15) / 16 * 16; }
 
 struct FCRegion { double val[HC_FDIM], err[HC_FDIM], c[3], hw[3], vol; int splitDim, pad; };
 static_assert(sizeof(FCRegion) <= FIPPI_REGION_BYTES, "region size");
@@ -77,15 +77,15 @@ __device__ __forceinline__ void fc_component(const double *F, double *T, int j, 
   val = result; err = fabs(hsub(res5th, result));
 }
 
+template <int FC_WARPS>
 __global__ void __launch_bounds__(32 * FC_WARPS)
-fippi_coop_kernel(const double *verts, const int *items, int nItems, char *pool, double *out, int *status)
-{ extern __shared__ double fsm[];
+fippi_coop_kernel(const double *verts, const int *items, int nItems, char *pool, int FC_CAP, double *out, int *status)
+{ extern __shared__ __align__(16) unsigned char fsmRaw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.x * FC_WARPS + warp;
   if (t >= nItems) return;                              // whole warps leave together
-  double *F = fsm + (size_t)warp * FC_WARP_DBL, *T = F + FC_F_DBL, *hErr = T + 3 * HC_FDIM, *diffS = hErr + FC_CAP;
-  __shared__ short hIdxAll[FC_WARPS][FC_CAP];
-  short *hIdx = hIdxAll[warp];
+  double *F = (double *)(fsmRaw + (size_t)warp * fc_warp_bytes(FC_CAP)), *T = F + FC_F_DBL, *diffS = T + 3 * HC_FDIM, *hErr = diffS + 4;
+  short *hIdx = (short *)(hErr + FC_CAP);
   const int it = items[t];
   const double *V = verts + 18 * (size_t)it;
   const double *OVa[3] = { V, V + 3, V + 6 }, *OVb[3] = { V + 9, V + 12, V + 15 };
@@ -189,13 +189,21 @@ fippi_coop_kernel(const double *verts, const int *items, int nItems, char *pool,
   if (lane < 3) o[33 + lane] = (OVa[0][lane] + OVa[1][lane] + OVa[2][lane]) / 3.0;
 }
 
-// launcher used by fippi_kernel.cu; pool must hold n * FC_CAP * FIPPI_REGION_BYTES bytes
-int fippi_coop_capacity() { return FC_CAP; }
-void fippi_launch_coop(cudaStream_t s, const double *verts, const int *items, int n, char *pool, double *out, int *status)
-{ const size_t smem = (size_t)FC_WARPS * FC_WARP_DBL * sizeof(double);
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(fippi_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
-  fippi_coop_kernel<<<(n + FC_WARPS - 1) / FC_WARPS, 32 * FC_WARPS, smem, s>>>(verts, items, n, pool, out, status);
+// launcher used by fippi_kernel.cu; pool must hold n * cap * FIPPI_REGION_BYTES bytes.  Small pools: 4 records per CTA;
+// large pools (heap of up to 15 200 entries = 150 KB of shared memory): one record per CTA.  Returns false if the heap
+// does not fit into shared memory (the caller then uses the one-thread-per-record kernel).
+bool fippi_launch_coop(cudaStream_t s, const double *verts, const int *items, int n, char *pool, int cap, double *out, int *status)
+{ if (cap > 32000) return false;
+  if (fc_warp_bytes(cap) * 4 <= 100 * 1024)
+   { const size_t smem = fc_warp_bytes(cap) * 4;
+     cudaFuncSetAttribute(fippi_coop_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+     fippi_coop_kernel<4><<<(n + 3) / 4, 128, smem, s>>>(verts, items, n, pool, cap, out, status); }
+  else
+   { const size_t smem = fc_warp_bytes(cap);
+     if (smem > 220 * 1024) return false;
+     cudaFuncSetAttribute(fippi_coop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+     fippi_coop_kernel<1><<<n, 32, smem, s>>>(verts, items, n, pool, cap, out, status); }
+  return true;
 }
 
 }  // namespace scuffcuda

@@ -6,6 +6,8 @@
 #include <vector>
 #include <algorithm>
 #include <thread>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 #include "kernels.h"
@@ -15,8 +17,7 @@
 namespace scuffcuda {
 
 // warp-cooperative builder for the no-common-vertex case (fippi_coop.cu)
-int fippi_coop_capacity();
-void fippi_launch_coop(cudaStream_t s, const double *verts, const int *items, int n, char *pool, double *out, int *status);
+bool fippi_launch_coop(cudaStream_t s, const double *verts, const int *items, int n, char *pool, int cap, double *out, int *status);
 
 static_assert(sizeof(SCPXEntry) == sizeof(PXEntry) && sizeof(SCPCEntry) == sizeof(PCEntry), "generated table layout");
 
@@ -82,9 +83,10 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
     const int caps[3] = { 384, 4096, 15200 };
     static int coopEnv = -1;
     if (coopEnv < 0) { const char *e = getenv("SCUFF_CUDA_FIPPI_COOP"); coopEnv = e ? atoi(e) : 1; }
-    const bool coop = (c == 0) && coopEnv && fippi_coop_capacity() == caps[0];
+    const bool coop = (c == 0) && coopEnv;
     for (int pass = 0; pass < 3 && !todo.empty() && !rcs[c]; pass++)
      { const int cap = caps[pass];
+       const auto tPass = std::chrono::steady_clock::now();
        const size_t perThread = (size_t)cap * (FIPPI_REGION_BYTES + sizeof(int));
        const int batch = (int)std::min<size_t>(todo.size(), std::max<size_t>(64, budget / perThread));
        if (dpool_c) { cudaFree(dpool_c); dpool_c = nullptr; }
@@ -94,9 +96,9 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
         { int m = (int)std::min((size_t)batch, todo.size() - first);
           cudaMemcpyAsync(ditems_c, todo.data() + first, m * sizeof(int), cudaMemcpyHostToDevice, st_);
           __atomic_fetch_add(&ctx->launches, 1ull, __ATOMIC_RELAXED);
-          // pass 0 of the 3-D case: one warp per record (same bits, ~20x shorter latency); later passes: one thread per record
-          if (coop && pass == 0) fippi_launch_coop(st_, dverts, ditems_c, m, dpool_c, dout, dstatus_c);
-          else launchers[c](st_, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c);
+          // the 3-D case: one warp per record (same bits as one thread per record, far shorter latency per record)
+          if (!(coop && fippi_launch_coop(st_, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c)))
+           launchers[c](st_, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c);
           cudaMemcpyAsync(st.data(), dstatus_c, m * sizeof(int), cudaMemcpyDeviceToHost, st_);
           cudaError_t e = cudaStreamSynchronize(st_);
           if (e != cudaSuccess) { fail(std::string("fippi_build_kernel: ") + cudaGetErrorString(e)); break; }
@@ -104,6 +106,10 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
            { if (st[i] == 3) { fail("FIPPI builder: integration case mismatch"); break; }
              if (st[i]) next.push_back(todo[first + i]); }
         }
+       if (getenv("SCUFF_CUDA_FIPPI_DEBUG"))
+        fprintf(stderr, "[fippi] case %d pass %d (cap %d, batch %d%s): %zu records, %zu need a larger pool, %.1f ms\n", c, pass, cap, batch,
+                coop ? ", warp-cooperative" : "", todo.size(), next.size(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tPass).count());
        todo.swap(next);
      }
     if (!rcs[c] && !todo.empty()) fail("FIPPI builder: region pool exhausted");
