@@ -17,7 +17,7 @@
 namespace scuffcuda {
 
 // warp-cooperative builder for the no-common-vertex case (fippi_coop.cu)
-bool fippi_launch_coop(cudaStream_t s, const double *verts, const int *items, int n, char *pool, int cap, double *out, int *status);
+bool fippi_launch_coop(cudaStream_t s, int c, const FIPPITables &T, const double *verts, const int *items, int n, char *pool, int cap, double *out, int *status);
 
 static_assert(sizeof(SCPXEntry) == sizeof(PXEntry) && sizeof(SCPCEntry) == sizeof(PCEntry), "generated table layout");
 
@@ -83,7 +83,7 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
     const int caps[3] = { 384, 4096, 15200 };
     static int coopEnv = -1;
     if (coopEnv < 0) { const char *e = getenv("SCUFF_CUDA_FIPPI_COOP"); coopEnv = e ? atoi(e) : 1; }
-    const bool coop = (c == 0) && coopEnv;
+    const bool coop = coopEnv == 1 || (coopEnv == 3 && c == 0);   // 1: all cases warp-cooperative, 3: only the 3-D case, 0: none
     for (int pass = 0; pass < 3 && !todo.empty() && !rcs[c]; pass++)
      { const int cap = caps[pass];
        const auto tPass = std::chrono::steady_clock::now();
@@ -97,7 +97,7 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
           cudaMemcpyAsync(ditems_c, todo.data() + first, m * sizeof(int), cudaMemcpyHostToDevice, st_);
           __atomic_fetch_add(&ctx->launches, 1ull, __ATOMIC_RELAXED);
           // the 3-D case: one warp per record (same bits as one thread per record, far shorter latency per record)
-          if (!(coop && fippi_launch_coop(st_, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c)))
+          if (!(coop && fippi_launch_coop(st_, c, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c)))
            launchers[c](st_, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c);
           cudaMemcpyAsync(st.data(), dstatus_c, m * sizeof(int), cudaMemcpyDeviceToHost, st_);
           cudaError_t e = cudaStreamSynchronize(st_);
