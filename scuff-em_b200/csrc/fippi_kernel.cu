@@ -63,7 +63,11 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
      if (ncvs[i] != 0)
       c = (((float)V[3] == (float)V[12]) && ((float)V[4] == (float)V[13]) && ((float)V[5] == (float)V[14])) ? 1 : 2;
      byCase[c].push_back(i); }
+#ifdef SCUFF_SERIAL_FIPPI
   const fippi_launch_fn launchers[3] = { fippi_launch_case0, fippi_launch_case1, fippi_launch_case2 };
+#else
+  const fippi_launch_fn launchers[3] = { nullptr, nullptr, nullptr };   // built without the one-thread-per-record kernels
+#endif
   // The three integration cases run concurrently (one host thread + stream each): the 1-D / 2-D cases are short grids of
   // long-running threads that would otherwise leave the GPU idle.  Within a case: pass 0 gives every record a small region
   // pool, the records that need more are redone with larger pools; the batch of each pass is sized from the free HBM
@@ -83,7 +87,7 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
     const int caps[3] = { 384, 4096, 15200 };
     static int coopEnv = -1;
     if (coopEnv < 0) { const char *e = getenv("SCUFF_CUDA_FIPPI_COOP"); coopEnv = e ? atoi(e) : 1; }
-    const bool coop = coopEnv == 1 || (coopEnv == 3 && c == 0);   // 1: all cases warp-cooperative, 3: only the 3-D case, 0: none
+    const bool coop = coopEnv == 1 || (coopEnv == 3 && c == 0) || !launchers[c];   // 1: all cases warp-cooperative, 3: only the 3-D case, 0: none
     for (int pass = 0; pass < 3 && !todo.empty() && !rcs[c]; pass++)
      { const int cap = caps[pass];
        const auto tPass = std::chrono::steady_clock::now();
@@ -98,7 +102,8 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
           __atomic_fetch_add(&ctx->launches, 1ull, __ATOMIC_RELAXED);
           // the 3-D case: one warp per record (same bits as one thread per record, far shorter latency per record)
           if (!(coop && fippi_launch_coop(st_, c, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c)))
-           launchers[c](st_, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c);
+           { if (!launchers[c]) { fail("FIPPI builder: the one-thread-per-record kernels were not built (make SERIAL_FIPPI=1)"); break; }
+             launchers[c](st_, T, dverts, ditems_c, m, dpool_c, cap, dout, dstatus_c); }
           cudaMemcpyAsync(st.data(), dstatus_c, m * sizeof(int), cudaMemcpyDeviceToHost, st_);
           cudaError_t e = cudaStreamSynchronize(st_);
           if (e != cudaSuccess) { fail(std::string("fippi_build_kernel: ") + cudaGetErrorString(e)); break; }
