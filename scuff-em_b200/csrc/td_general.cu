@@ -311,9 +311,22 @@ __device__ __forceinline__ double pc_coord(const TDTables &T, const PCEnt &e, in
   return (li & 1) ? 0.5 - 0.5 * T.ccx[i] : 0.5 + 0.5 * T.ccx[i];
 }
 
-// integral of the rule with levels M[] (M[md] decremented when md < DIM) from the cached values
+// ---- group-cooperative evaluation: TDG_GROUP lanes share one item.  The points of every cache entry are enumerated
+// linearly (q = (i0*n1 + i1)*n2 + i2, the storage order); lanes stride q, both when evaluating the integrand at new points
+// and when forming the quadrature sums, which are then reduced with warp shuffles (identical totals on all lanes, so every
+// decision is group-uniform).  Decisions are those of pcubature.c; only the summation order of the quadrature sums differs.
+#define TDG_GROUP 8
+
+__device__ __forceinline__ double grp_sum(double v, unsigned gmask)
+{
+#pragma unroll
+  for (int o = TDG_GROUP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v; }
+
+// integral of the rule with levels M[] (M[md] decremented when md < DIM) from the cached values; cache[(pt*FDIM + j)]
 template <int DIM>
-__device__ void pc_evals(const TDTables &T, const PCEnt *ent, int nEnt, const int *m, int md, const double *cache, size_t stride, double *val)
+__device__ void pc_evals(const TDTables &T, const PCEnt *ent, int nEnt, const int *m, int md, const double *cache,
+                         int gl, unsigned gmask, double *val)
 { for (int j = 0; j < TDG_FDIM; j++) val[j] = 0.0;
   int M[3];
   for (int d = 0; d < DIM; d++) M[d] = m[d] - (d == md ? 1 : 0);
@@ -321,28 +334,24 @@ __device__ void pc_evals(const TDTables &T, const PCEnt *ent, int nEnt, const in
   for (int ie = 0; ie < nEnt; ie++)
    { const PCEnt &e = ent[ie];
      if (!(e.mi >= DIM || (int)e.m[e.mi] + (e.mi == md ? 1 : 0) <= m[e.mi])) continue;
-     const int n0 = e.cnt[0], n1 = DIM > 1 ? e.cnt[1] : 1, n2 = DIM > 2 ? e.cnt[2] : 1;
-     int q = 0;
-     for (int i0 = 0; i0 < n0; i0++)
-      { const double w0 = V * pc_weight<DIM>(T, e, 0, i0, M[0]);
-        if (w0 == 0.0) { q += n1 * n2; continue; }
-        for (int i1 = 0; i1 < n1; i1++)
-         { const double w1 = DIM > 1 ? w0 * pc_weight<DIM>(T, e, 1, i1, M[1]) : w0;
-           if (w1 == 0.0) { q += n2; continue; }
-           for (int i2 = 0; i2 < n2; i2++, q++)
-            { const double w = DIM > 2 ? w1 * pc_weight<DIM>(T, e, 2, i2, M[2]) : w1;
-              if (w == 0.0) continue;
-              const double *cv = cache + (size_t)(e.off + q) * TDG_FDIM * stride;
-              for (int j = 0; j < TDG_FDIM; j++) val[j] += cv[(size_t)j * stride] * w;
-            }
-         }
+     const int n1 = DIM > 1 ? e.cnt[1] : 1, n2 = DIM > 2 ? e.cnt[2] : 1;
+     const int total = e.cnt[0] * n1 * n2;
+     for (int q = gl; q < total; q += TDG_GROUP)
+      { const int i2 = q % n2, i1 = (q / n2) % n1, i0 = q / (n1 * n2);
+        double w = V * pc_weight<DIM>(T, e, 0, i0, M[0]);
+        if (DIM > 1 && w != 0.0) w *= pc_weight<DIM>(T, e, 1, i1, M[1]);
+        if (DIM > 2 && w != 0.0) w *= pc_weight<DIM>(T, e, 2, i2, M[2]);
+        if (w == 0.0) continue;
+        const double *cv = cache + (size_t)(e.off + q) * TDG_FDIM;
+        for (int j = 0; j < TDG_FDIM; j++) val[j] += cv[j] * w;
       }
    }
+  for (int j = 0; j < TDG_FDIM; j++) val[j] = grp_sum(val[j], gmask);
 }
 
 template <int DIM>
 __device__ int pc_add_entry(const TDTables &T, const TDGen &W, PCEnt *ent, int &nEnt, int &nPts, const int *m, int mi,
-                            double *cache, size_t stride)
+                            double *cache, int gl, unsigned gmask)
 { if (nEnt >= TDG_MAXENT) return 2;
   PCEnt &e = ent[nEnt];
   for (int d = 0; d < 3; d++) { e.m[d] = d < DIM ? (unsigned char)m[d] : 0; e.cnt[d] = 1; }
@@ -352,38 +361,36 @@ __device__ int pc_add_entry(const TDTables &T, const TDGen &W, PCEnt *ent, int &
    { e.cnt[d] = (d == mi) ? (m[d] == 0 ? 2 : (1 << m[d])) : ((1 << (m[d] + 1)) + 1);
      total *= e.cnt[d]; }
   if (nPts + total > TDG_MAXPTS) return 2;
-  const int n0 = e.cnt[0], n1 = DIM > 1 ? e.cnt[1] : 1, n2 = DIM > 2 ? e.cnt[2] : 1;
-  int q = 0; double y[3] = { 0.0, 0.0, 0.0 }, f[TDG_FDIM];
-  for (int i0 = 0; i0 < n0; i0++)
-   { y[0] = pc_coord<DIM>(T, e, 0, i0);
-     for (int i1 = 0; i1 < n1; i1++)
-      { if (DIM > 1) y[1] = pc_coord<DIM>(T, e, 1, i1);
-        for (int i2 = 0; i2 < n2; i2++, q++)
-         { if (DIM > 2) y[2] = pc_coord<DIM>(T, e, 2, i2);
-           tdg_integrand(W, y, f);
-           double *cv = cache + (size_t)(nPts + q) * TDG_FDIM * stride;
-           for (int j = 0; j < TDG_FDIM; j++) cv[(size_t)j * stride] = f[j];
-         }
-      }
+  const int n1 = DIM > 1 ? e.cnt[1] : 1, n2 = DIM > 2 ? e.cnt[2] : 1;
+  for (int q = gl; q < total; q += TDG_GROUP)
+   { const int i2 = q % n2, i1 = (q / n2) % n1, i0 = q / (n1 * n2);
+     double y[3] = { 0.0, 0.0, 0.0 }, f[TDG_FDIM];
+     y[0] = pc_coord<DIM>(T, e, 0, i0);
+     if (DIM > 1) y[1] = pc_coord<DIM>(T, e, 1, i1);
+     if (DIM > 2) y[2] = pc_coord<DIM>(T, e, 2, i2);
+     tdg_integrand(W, y, f);
+     double *cv = cache + (size_t)(nPts + q) * TDG_FDIM;
+     for (int j = 0; j < TDG_FDIM; j++) cv[j] = f[j];
    }
+  __syncwarp(gmask);
   nPts += total; nEnt++;
   return 0;
 }
 
 template <int DIM>
 __device__ int pcubature_nd(const TDTables &T, const TDGen &W, double relTol, double absTol, int maxEval,
-                            double *cache, size_t stride, double val[TDG_FDIM], double err[TDG_FDIM])
+                            double *cache, int gl, unsigned gmask, double val[TDG_FDIM], double err[TDG_FDIM])
 { PCEnt ent[TDG_MAXENT]; int nEnt = 0, nPts = 0, numEval = 0;
   int m[3] = { 0, 0, 0 };
-  int st = pc_add_entry<DIM>(T, W, ent, nEnt, nPts, m, DIM, cache, stride);
+  int st = pc_add_entry<DIM>(T, W, ent, nEnt, nPts, m, DIM, cache, gl, gmask);
   if (st) return st;
   for (;;)
-   { pc_evals<DIM>(T, ent, nEnt, m, DIM, cache, stride, val);
+   { pc_evals<DIM>(T, ent, nEnt, m, DIM, cache, gl, gmask, val);
      for (int j = 0; j < TDG_FDIM; j++) err[j] = 0.0;
      int mi = 0; double maxerr = 0.0;
      for (int i = 0; i < DIM; i++)
       { double val1[TDG_FDIM], emax = 0.0;
-        pc_evals<DIM>(T, ent, nEnt, m, i, cache, stride, val1);
+        pc_evals<DIM>(T, ent, nEnt, m, i, cache, gl, gmask, val1);
         for (int j = 0; j < TDG_FDIM; j++)
          { const double e = fabs(val[j] - val1[j]);
            if (e > emax) emax = e;
@@ -397,7 +404,7 @@ __device__ int pcubature_nd(const TDTables &T, const TDGen &W, double relTol, do
      if (m[mi] > SC_TD_MAXLEVEL) return 1;
      int newPts = 1;
      for (int d = 0; d < DIM; d++) newPts *= (d == mi) ? (1 << m[d]) : ((1 << (m[d] + 1)) + 1);
-     st = pc_add_entry<DIM>(T, W, ent, nEnt, nPts, m, mi, cache, stride);
+     st = pc_add_entry<DIM>(T, W, ent, nEnt, nPts, m, mi, cache, gl, gmask);
      if (st) return st;
      numEval += newPts;
    }
@@ -406,8 +413,11 @@ __device__ int pcubature_nd(const TDTables &T, const TDGen &W, double relTol, do
 // items[t] = 36*nearIndex + 18*highk + 9*swapped + 3*i + j
 __global__ void __launch_bounds__(64)
 td_general_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, double *scratch, int *itemStatus)
-{ const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nItems) return;
+{ const int t = (blockIdx.x * blockDim.x + threadIdx.x) / TDG_GROUP;          // item handled by this group of lanes
+  const int gl = threadIdx.x & (TDG_GROUP - 1);
+  if (t >= nItems) return;                                                  // whole groups leave together
+  const unsigned gmask = ((1u << TDG_GROUP) - 1u) << ((threadIdx.x & 31) & ~(TDG_GROUP - 1));
+  double *cache = scratch + (size_t)t * TDG_MAXPTS * TDG_FDIM;
   const int item = items[t];
   const NearPair N = A.near[item / 36];
   const int hk = (item % 36) / 18, swapped = (item % 18) / 9, i = (item % 9) / 3, j = item % 3;
@@ -430,14 +440,14 @@ td_general_kernel(const NearArgs A, const TDTables T, const int *items, int nIte
   tdg_setup(T, ncv, V1, V2, V3, V2P, V3P, Q, QP, k, W, hk);
   double val[TDG_FDIM], err[TDG_FDIM];
   for (int q = 0; q < TDG_FDIM; q++) val[q] = 0.0;
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
   // integral dimension = 4 - WhichCase - TwiceIntegrable (TaylorDuffy.cc:355)
   const int dim = 4 - ncv - hk;
   int st = 0;
   if (dim == 0) tdg_integrand_hk(W, nullptr, val);
-  else if (dim == 1) st = pcubature_nd<1>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
-  else if (dim == 2) st = pcubature_nd<2>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
-  else st = pcubature_nd<3>(T, W, 1.0e-10, 0.0, 1000, scratch + t, stride, val, err);
+  else if (dim == 1) st = pcubature_nd<1>(T, W, 1.0e-10, 0.0, 1000, cache, gl, gmask, val, err);
+  else if (dim == 2) st = pcubature_nd<2>(T, W, 1.0e-10, 0.0, 1000, cache, gl, gmask, val, err);
+  else st = pcubature_nd<3>(T, W, 1.0e-10, 0.0, 1000, cache, gl, gmask, val, err);
+  if (gl != 0) return;
   itemStatus[t] = st;
   if (st) return;
   const cd R0 = mk(val[0], val[1]), R1 = mk(val[2], val[3]), R2 = mk(val[4], val[5]);
@@ -456,9 +466,9 @@ int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T,
   // already there) -> TDG_MAXPTS points x 6 doubles per item; items are processed in batches
   const size_t perItem = (size_t)TDG_MAXPTS * TDG_FDIM * sizeof(double);
   const int batch = std::min(nItems, 8192);
-  const int threads = ((batch + 63) / 64) * 64;
+  const long threads = (((long)batch * TDG_GROUP + 63) / 64) * 64;
   const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
-  const size_t need = hdr + (size_t)threads * perItem;
+  const size_t need = hdr + (size_t)batch * perItem;
   if (need > ctx->scratchBytes)
    { if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
      if (cudaMalloc(&ctx->dscratch, need) != cudaSuccess) { cudaGetLastError(); ctx->err = "Taylor-Duffy scratch allocation failed"; return 1; }
@@ -470,7 +480,7 @@ int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T,
    { const int n = std::min(batch, nItems - first);
      cudaMemcpyAsync(dItems, items + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
      ctx->launches++;
-     td_general_kernel<<<threads / 64, 64, 0, ctx->stream>>>(A, T, dItems, n, scr, dStatus);
+     td_general_kernel<<<(unsigned)(threads / 64), 64, 0, ctx->stream>>>(A, T, dItems, n, scr, dStatus);
      cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
      cudaError_t e = cudaStreamSynchronize(ctx->stream);
      if (e != cudaSuccess) { ctx->err = std::string("td_general_kernel: ") + cudaGetErrorString(e); return 1; }
