@@ -51,7 +51,8 @@ def make_mesh(nu, rank, material=None):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons every 200 ms while the timed region runs (B200_PROFILING.md)"""
+    """nvidia-smi clocks + throttle reasons every 50 ms while the timed region runs (B200_PROFILING.md; the timed region of
+    the default run is only ~0.25 s long)"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -62,7 +63,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([t.strip() for t in line.split(",")])
         except Exception:
