@@ -25,12 +25,15 @@ __device__ __forceinline__ void stamp_edge_pair(const StampParams &P, int ea, in
    { int X = P.rowOff + 2 * ea, Y = P.colOff + eb;
      add_entry(P, X, Y, P.c1 * g0); add_entry(P, X + 1, Y, P.c2 * g1); }
   else
-   { int X = P.rowOff + 2 * ea, Y = P.colOff + 2 * eb;
-     cd v12 = P.c2 * g1;
-     add_entry(P, X, Y, P.c1 * g0);
-     add_entry(P, X, Y + 1, v12);
-     if (!diag) add_entry(P, X + 1, Y, v12);
-     add_entry(P, X + 1, Y + 1, P.c3 * g0);
+   { const int X = P.rowOff + 2 * ea, Y = P.colOff + 2 * eb;
+     const cd v11 = P.c1 * g0, v12 = P.c2 * g1, v22 = P.c3 * g0;
+     // the 2x2 PMCHWT stamp as a rolled loop (keeps the nine inlined copies of this function small: the dielectric far
+     // kernel was instruction-fetch bound): e = 0..3 -> (X,Y), (X,Y+1), (X+1,Y), (X+1,Y+1)
+#pragma unroll 1
+     for (int e = 0; e < 4; e++)
+      { if (e == 2 && diag) continue;
+        const cd v = (e == 0) ? v11 : ((e == 3) ? v22 : v12);
+        add_entry(P, X + (e >> 1), Y + (e & 1), v); }
    }
 }
 

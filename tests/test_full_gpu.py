@@ -73,3 +73,28 @@ def test_lu_solve_downstream(ps, tmp_path):
     x = X.array[:, 0]
     xref = np.linalg.solve(Mref, rhs)
     assert np.linalg.norm(x - xref) / np.linalg.norm(xref) <= 1e-8
+
+
+def test_casimir_energy_integrand_downstream(ps, tmp_path):
+    """downstream quantity of the imaginary-frequency path (scuff-cas3D, CasimirIntegrand.cc:296-312,428-451): the energy
+    integrand log det(M) - log det(M_infinity) with M_infinity = the diagonal blocks; <= 1e-8 relative (north_star)"""
+    geo = os.path.join(GEODIR, "PECSpheres_327.scuffgeo")
+    vals = []
+    for xi in (0.3, 1.0):
+        cache = str(tmp_path / ("ref%g.cache" % xi))
+        Mref, info = ref_matrix(geo, 1j * xi, imag=True, cache_out=cache)
+        ps.ClearCache()
+        ps.PreloadCache(cache)
+        G = ps.RWGGeometry(geo)
+        M = G.AssembleBEMMatrix(1j * xi, M=G.AllocateBEMMatrix(True)).array
+        n = G.surface(1)["BFOffset"]
+
+        def integrand(A):
+            s, ld = np.linalg.slogdet(A)
+            s1, l1 = np.linalg.slogdet(A[:n, :n])
+            s2, l2 = np.linalg.slogdet(A[n:, n:])
+            return ld - l1 - l2
+        mine, ref = integrand(M), integrand(Mref)
+        vals.append((xi, mine, ref))
+        assert abs(mine - ref) <= 1e-8 * abs(ref), (xi, mine, ref)
+    print("Casimir energy integrand (xi, mine, reference):", vals)
