@@ -54,3 +54,28 @@ def test_reference_api_errors(ps):
     # omega = 0: k = 0 -> GC = 0 (EdgeEdgeInteractions.cc:74-79): the matrix is exactly zero
     Z = G.AssembleBEMMatrix(0.0).array
     assert np.all(Z == 0)
+
+
+def test_region_linearity_and_accumulate(ps):
+    """Linearity the domain offers: the PMCHWT matrix is the sum of its exterior-region and interior-region parts
+    (MatProp::Zero() on one region at a time, as scuff-neq / scuff-cas3D use it; SurfaceSurfaceInteractions.cc:177,294), and
+    Args->Accumulate adds a block on top of what the matrix holds."""
+    G = ps.RWGGeometry(os.path.join(GEODIR, "SiSphere_255.scuffgeo"))
+    omega = 0.6
+    full = G.AssembleBEMMatrix(omega).array
+    G.zero_region(1, True)
+    ext = G.AssembleBEMMatrix(omega).array
+    G.zero_region(1, False); G.zero_region(0, True)
+    inn = G.AssembleBEMMatrix(omega).array
+    G.zero_region(0, False)
+    assert np.linalg.norm(ext) > 0 and np.linalg.norm(inn) > 0
+    assert np.linalg.norm(ext + inn - full) <= 1e-13 * np.linalg.norm(full)
+    # accumulate through the C ABI: the same block added twice
+    L, ctx = ps.cuda_lib(), ps.context()
+    M = G.AssembleBEMMatrix(omega, to_host=False)
+    a = _args(ps, symmetric=1, accumulate=1)
+    a.omega[0] = omega
+    assert L.scuffcuda_assemble_block(ctx, 0, 0, C.byref(a), M.device_handle) == 0, L.scuffcuda_last_error(ctx)
+    host = np.zeros((G.TotalBFs, G.TotalBFs), dtype=np.complex128, order="F")
+    assert L.scuffcuda_matrix_download(ctx, M.device_handle, host.ctypes.data, G.TotalBFs) == 0
+    assert np.linalg.norm(host - (full + ext)) <= 1e-13 * np.linalg.norm(full)
