@@ -168,6 +168,8 @@ class RWGSurface
    double RMax[3], RMin[3];
    double tolVecClose;
    int TotalStraddlers;
+   /* PBCSetup.cc:142-302: promote exterior edges that have a lattice-translated partner to full RWG edges */
+   void AddStraddlers(HMatrix *LBasis, int NumStraddlers[MAXLDIM]);
 
    /* internal */
    void *OTGT, *GT;             /* one-time and current rigid transformations */
@@ -220,6 +222,7 @@ class RWGGeometry
    int LDim;
    HMatrix *LBasis;
    bool *RegionIsExtended[MAXLDIM];
+   int *NumStraddlers[MAXLDIM];   /* NumStraddlers[nd][ns] (PBCSetup.cc:318-333) */
    char *GeoFileName;
    int LogLevel;
    double tolVecClose;

@@ -140,9 +140,6 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
 
 HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, HMatrix *M) { return AssembleBEMMatrix(Omega, 0, M); }
 
-void RWGGeometry::InitPBCData()
-{ for (int nd = 0; nd < LDim; nd++) RegionIsExtended[nd] = (bool *)calloc(NumRegions, sizeof(bool)); }
-
 void RWGGeometry::AssembleBEMMatrixBlockPBC(int, int, cdouble, double *, HMatrix *, int, int)
 { ErrExit("periodic (LATTICE) geometries are not yet supported by the device assembly path"); }
 

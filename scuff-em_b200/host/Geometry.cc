@@ -480,7 +480,7 @@ RWGGeometry::RWGGeometry(const char *pGeoFileName, int pLogLevel)
   GeoFileName = strdup(pGeoFileName);
   Surfaces = 0; AllSurfacesClosed = 1;
   LDim = 0; LBasis = 0;
-  for (int nd = 0; nd < MAXLDIM; nd++) RegionIsExtended[nd] = 0;
+  for (int nd = 0; nd < MAXLDIM; nd++) { RegionIsExtended[nd] = 0; NumStraddlers[nd] = 0; }
   tolVecClose = 0.0;
   NumRegions = 1;
   RegionLabels = (char **)malloc(sizeof(char *)); RegionLabels[0] = strdup("EXTERIOR");
@@ -646,7 +646,7 @@ RWGGeometry::~RWGGeometry()
   for (int nr = 0; nr < NumRegions; nr++) { free(RegionLabels[nr]); delete RegionMPs[nr]; }
   free(RegionLabels); free(RegionMPs);
   free(BFIndexOffset); free(EdgeIndexOffset); free(PanelIndexOffset); free(EpsTF); free(MuTF); free(Mate); free(SurfaceMoved);
-  for (int nd = 0; nd < MAXLDIM; nd++) free(RegionIsExtended[nd]);
+  for (int nd = 0; nd < MAXLDIM; nd++) { free(RegionIsExtended[nd]); free(NumStraddlers[nd]); }
   delete LBasis; free(GeoFileName);
 }
 
@@ -679,6 +679,107 @@ void RWGGeometry::Transform(const char *TransLine)
 void RWGGeometry::UnTransform()
 { for (int ns = 0; ns < NumSurfaces; ns++)
    if (Surfaces[ns]->GT) { Surfaces[ns]->UnTransform(); DeviceDirty[ns] = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Periodic geometries: straddlers (reference semantics: PBCSetup.cc:64-118 FindPartnerEdge, :142-302 AddStraddlers,
+// :307-372 InitPBCData).  An exterior edge on the unit-cell boundary whose translate by a lattice vector is another
+// exterior edge becomes a full RWG edge: one vertex (the partner's Q vertex shifted back by the lattice vector) and one
+// panel {iV1, iV2, new vertex} are appended, and the edge is appended to Edges[] AFTER the interior edges — which fixes
+// the matrix row/column order of periodic geometries.
+// ---------------------------------------------------------------------------------------------------------------
+static bool VecCloseL1(const double *a, const double *b, double abstol)      // libhrutil/Vector.cc:294-297
+{ return fabs(a[0] - b[0]) + fabs(a[1] - b[1]) + fabs(a[2] - b[2]) <= 3 * abstol; }
+
+void RWGSurface::AddStraddlers(HMatrix *LBasis, int NumStraddlersOut[MAXLDIM])
+{ const int LDim = LBasis->NC;
+  for (int nd = 0; nd < MAXLDIM; nd++) NumStraddlersOut[nd] = 0;
+  std::vector<double> NewV; std::vector<RWGPanel *> NewP; std::vector<RWGEdge *> NewE;
+  for (int nei = 0; nei < NumExteriorEdges; nei++)
+   { RWGEdge *E = HalfRWGEdges[nei];
+     if (!E) continue;
+     const double *V1 = Vertices + 3 * E->iV1, *V2 = Vertices + 3 * E->iV2;
+     int partner = -1, whichBV = 0; double V[3];
+     for (int nd = 0; nd < LDim && partner < 0; nd++)
+      { double V1T[3], V2T[3];
+        for (int nc = 0; nc < 3; nc++) { V1T[nc] = V1[nc] + LBasis->GetEntryD(nc, nd); V2T[nc] = V2[nc] + LBasis->GetEntryD(nc, nd); }
+        for (int neip = 0; neip < NumExteriorEdges; neip++)
+         { RWGEdge *EP = HalfRWGEdges[neip];
+           if (!EP) continue;
+           const double *V1P = Vertices + 3 * EP->iV1, *V2P = Vertices + 3 * EP->iV2;
+           if ((VecCloseL1(V1T, V1P, tolVecClose) && VecCloseL1(V2T, V2P, tolVecClose))
+               || (VecCloseL1(V1T, V2P, tolVecClose) && VecCloseL1(V2T, V1P, tolVecClose)))
+            { for (int nc = 0; nc < 3; nc++) V[nc] = Vertices[3 * EP->iQP + nc];
+              for (int nc = 0; nc < 3; nc++) V[nc] -= LBasis->GetEntryD(nc, nd);
+              NumStraddlersOut[nd]++; whichBV = nd; partner = neip; break; }
+         }
+      }
+     (void)whichBV;
+     if (partner < 0) continue;
+     const int NumNew = (int)NewE.size();
+     NewV.insert(NewV.end(), V, V + 3);
+     for (int nc = 0; nc < 3; nc++) { RMax[nc] = fmax(RMax[nc], V[nc]); RMin[nc] = fmin(RMin[nc], V[nc]); }
+     E->iQM = NumVertices + NumNew;
+     E->iMPanel = NumPanels + NumNew;
+     E->Index = NumEdges + NumNew;
+     E->MIndex = 2;
+     E->Radius = VecDistance(E->Centroid, Vertices + 3 * E->iQP);
+     E->Radius = fmax(E->Radius, VecDistance(E->Centroid, V));
+     E->Radius = fmax(E->Radius, VecDistance(E->Centroid, Vertices + 3 * E->iV1));
+     E->Radius = fmax(E->Radius, VecDistance(E->Centroid, Vertices + 3 * E->iV2));
+     NewE.push_back(E);
+     HalfRWGEdges[nei] = 0;
+     RWGPanel *P = (RWGPanel *)calloc(1, sizeof(RWGPanel));
+     P->VI[0] = E->iV1; P->VI[1] = E->iV2; P->VI[2] = E->iQM;
+     P->EI[0] = P->EI[1] = P->EI[2] = -1;
+     P->Index = NumPanels + NumNew; P->ZHatFlipped = false;
+     NewP.push_back(P);
+   }
+  const int NumNew = (int)NewE.size();
+  TotalStraddlers = NumNew;
+  if (NumNew == 0) return;
+  Vertices = (double *)realloc(Vertices, 3 * (size_t)(NumVertices + NumNew) * sizeof(double));
+  memcpy(Vertices + 3 * NumVertices, NewV.data(), 3 * (size_t)NumNew * sizeof(double));
+  NumVertices += NumNew;
+  Edges = (RWGEdge **)realloc(Edges, (size_t)(NumEdges + NumNew) * sizeof(RWGEdge *));
+  memcpy(Edges + NumEdges, NewE.data(), NumNew * sizeof(RWGEdge *));
+  NumEdges += NumNew;
+  Panels = (RWGPanel **)realloc(Panels, (size_t)(NumPanels + NumNew) * sizeof(RWGPanel *));
+  memcpy(Panels + NumPanels, NewP.data(), NumNew * sizeof(RWGPanel *));
+  NumPanels += NumNew;
+  for (int np = NumPanels - NumNew; np < NumPanels; np++) InitRWGPanel(Panels[np], Vertices);
+  // defragment the list of exterior edges
+  int keep = 0;
+  for (int nei = 0; nei < NumExteriorEdges; nei++)
+   if (HalfRWGEdges[nei]) { HalfRWGEdges[keep] = HalfRWGEdges[nei]; HalfRWGEdges[keep]->Index = keep; keep++; }
+  NumExteriorEdges = NumHalfRWGEdges = keep;
+  NumBFs = IsPEC ? NumEdges : 2 * NumEdges;
+  for (int ne = 0; ne < NumEdges; ne++)
+   { RWGEdge *E = Edges[ne];
+     Panels[E->iPPanel]->EI[E->PIndex] = ne;
+     if (E->iMPanel >= 0) Panels[E->iMPanel]->EI[E->MIndex] = ne; }
+  for (int ne = 0; ne < NumHalfRWGEdges; ne++)
+   { RWGEdge *E = HalfRWGEdges[ne]; Panels[E->iPPanel]->EI[E->PIndex] = -(ne + 1); }
+}
+
+void RWGGeometry::InitPBCData()
+{ TotalBFs = TotalPanels = 0;
+  for (int nd = 0; nd < LDim; nd++)
+   { NumStraddlers[nd] = (int *)calloc(NumSurfaces, sizeof(int));
+     RegionIsExtended[nd] = (bool *)calloc(NumRegions, sizeof(bool));
+     RegionIsExtended[nd][0] = true; }     // the exterior medium is always extended
+  for (int ns = 0; ns < NumSurfaces; ns++)
+   { RWGSurface *S = Surfaces[ns];
+     int NS[MAXLDIM];
+     S->AddStraddlers(LBasis, NS);
+     const int nr1 = S->RegionIndices[0], nr2 = S->RegionIndices[1];
+     int Total = 0;
+     for (int nd = 0; nd < LDim; nd++)
+      { NumStraddlers[nd][ns] = NS[nd]; Total += NS[nd];
+        if (NS[nd] > 0) { RegionIsExtended[nd][nr1] = true; if (nr2 != -1) RegionIsExtended[nd][nr2] = true; } }
+     TotalBFs += S->NumBFs; TotalPanels += S->NumPanels;
+     S->IsClosed = (Total == S->NumExteriorEdges);      // as written in the reference (PBCSetup.cc:364)
+   }
 }
 
 void RWGGeometry::SyncDeviceGeometry()

@@ -26,7 +26,12 @@ def parse_dump(fn):
     return hdr, regions, S
 
 
-@pytest.mark.parametrize("name", COMPACT)
+# periodic (LATTICE) geometries: straddler vertices / panels / edges appended as RWGSurface::AddStraddlers does
+# (PBCSetup.cc:142-302) -- they define the matrix row/column order of the PBC configurations
+PERIODIC = ["SiSlab_40", "SphereSlabArray", "PECPlate_40"]
+
+
+@pytest.mark.parametrize("name", COMPACT + PERIODIC)
 def test_geometry_matches_reference(ps, name):
     hdr, regions, S = parse_dump(os.path.join(GOLDEN, "geom", name + ".geom.txt"))
     G = ps.RWGGeometry(os.path.join(GEODIR, name + ".scuffgeo"))
