@@ -8,6 +8,9 @@
  *   ref_driver matrix <geo> <wRe> <wIm> <out.bin> [--kbloch kx ky] [--imag] [--repeat n]
  *                     [--cache-in f] [--cache-out f] [--block nsa nsb] [--transfile f --trans n]
  *                     (--trans: apply the n-th transformation of a .trans file first, as scuff-cas3D does)
+ *   ref_driver ssi    <geo> <wRe> <wIm> <nsa> <nsb> <Lx> <Ly> <Lz> <out.bin> [--cache-out f]
+ *        GetSurfaceSurfaceInteractions (SurfaceSurfaceInteractions.cc:426-585) for one surface pair with surface b displaced
+ *        by L (the neighbour-cell blocks of the periodic assembly, AssembleBEMMatrix.cc:72-114), not Symmetric
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
  *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
@@ -108,6 +111,23 @@ int main(int argc, char **argv)
      size_t N=(size_t)M->NR*M->NC;
      if(Imag) fwrite(M->DM,sizeof(double),N,f); else fwrite(M->ZM,sizeof(cdouble),N,f);
      fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"ssi"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); int nsa=atoi(argv[5]), nsb=atoi(argv[6]);
+     double L[3]={atof(argv[7]),atof(argv[8]),atof(argv[9])}; const char *Out=argv[10]; const char *CacheOut=0;
+     for(int n=11;n<argc;n++) if(!strcmp(argv[n],"--cache-out")) CacheOut=argv[++n];
+     G->UpdateCachedEpsMuValues(Omega);
+     HMatrix *B=new HMatrix(G->Surfaces[nsa]->NumBFs,G->Surfaces[nsb]->NumBFs,LHM_COMPLEX);
+     GetSSIArgStruct MyArgs, *Args=&MyArgs; InitGetSSIArgs(Args);
+     Args->G=G; Args->Sa=G->Surfaces[nsa]; Args->Sb=G->Surfaces[nsb]; Args->Omega=Omega;
+     Args->Symmetric=false; Args->B=B; Args->Displacement=L;
+     double t0=Now();
+     GetSurfaceSurfaceInteractions(Args);
+     printf("{\"NR\": %i, \"NC\": %i, \"real\": 0, \"threads\": %i, \"times\": [%.6f]}\n",B->NR,B->NC,omp_get_max_threads(),Now()-t0);
+     if(CacheOut) StoreCache(CacheOut);
+     FILE *f=fopen(Out,"wb"); if(!f) return 1;
+     fwrite(B->ZM,sizeof(cdouble),(size_t)B->NR*B->NC,f); fclose(f); return 0;
    }
 
   if(!strcmp(Cmd,"ppis"))

@@ -80,5 +80,22 @@ def ref_matrix(geo, omega, kbloch=None, imag=False, block=None, cache_in=None, c
     return M, info
 
 
+def ref_ssi(geo, omega, nsa, nsb, L, cache_out=None, tmpdir="/tmp/scuff_ref_cache", env=None):
+    """Reference GetSurfaceSurfaceInteractions for one surface pair with surface b displaced by L (ref_driver ssi)."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
+    os.makedirs(tmpdir, exist_ok=True)
+    key = hashlib.md5(repr(("ssi", geo, complex(omega), nsa, nsb, tuple(L))).encode()).hexdigest()[:16]
+    out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
+    cmd = [REF_DRIVER, "ssi", os.path.basename(geo), repr(float(np.real(omega))), repr(float(np.imag(omega))), str(nsa), str(nsb)]
+    cmd += [repr(float(x)) for x in L] + [out]
+    if cache_out:
+        cmd += ["--cache-out", cache_out]
+    r = subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True,
+                       env=dict(os.environ, **(env or {})))
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    return np.fromfile(out, dtype=np.complex128).reshape(info["NC"], info["NR"]).T, info
+
+
 def rel_fro(A, B):
     return np.linalg.norm(A - B) / np.linalg.norm(B)
