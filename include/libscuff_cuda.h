@@ -66,6 +66,15 @@ int scuffcuda_matrix_symmetrize(scuffcuda_context *ctx, int handle, int offset, 
 /* host <-> device; host buffer is column-major with leading dimension ld (elements)    */
 int scuffcuda_matrix_download(scuffcuda_context *ctx, int handle, void *host, long ld);
 int scuffcuda_matrix_upload(scuffcuda_context *ctx, int handle, const void *host, long ld);
+/* copy-back that overlaps with assembly (what HMatrix *AssembleBEMMatrix returns is a HOST matrix,
+ * AssembleBEMMatrix.cc:684-765): enqueue the D2H copy of rows [row0,row0+nrows) x columns [col0,col0+ncols)
+ * on the context's copy stream, ordered after everything issued on the compute stream so far; `host` is the
+ * base of the full column-major host matrix (page-locked memory for a truly asynchronous copy).
+ * _wait(ctx,0) blocks until all such copies have landed; _wait(ctx,1) instead makes later compute-stream
+ * work wait for them (no host block).                                                   */
+int scuffcuda_matrix_download_region_async(scuffcuda_context *ctx, int handle, void *host, long ld,
+                                           int row0, int nrows, int col0, int ncols);
+int scuffcuda_matrix_download_wait(scuffcuda_context *ctx, int fence_compute);
 /* raw device pointer (for zero-copy consumers such as torch / cuSOLVER callers)        */
 int scuffcuda_matrix_device_ptr(scuffcuda_context *ctx, int handle, void **dptr);
 /* downstream consumer: HMatrix::LUFactorize / LUSolve (libs/libhmat/LBWrappers.cc:150-230)
@@ -95,7 +104,8 @@ typedef struct scuffcuda_ssi_args {
                              * [col_begin, col_end) (and skip the panel pairs that cannot reach them);
                              * col_end == 0: all columns.  Symmetric blocks still fill the upper triangle
                              * only and are NOT mirrored when a range is given (the caller mirrors the
-                             * gathered matrix with scuffcuda_matrix_symmetrize)               */
+                             * gathered matrix with scuffcuda_matrix_symmetrize); without `accumulate`
+                             * only the owned columns of the block are cleared                  */
   int    reserved[5];
 } scuffcuda_ssi_args;
 

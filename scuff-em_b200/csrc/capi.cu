@@ -7,6 +7,7 @@
 #include <cstring>
 #include <algorithm>
 #include "kernels.h"
+#include "sw_kernels.h"
 
 using namespace scuffcuda;
 typedef std::complex<double> cdouble;
@@ -186,6 +187,45 @@ int scuffcuda_matrix_download(scuffcuda_context *ctx, int h, void *host, long ld
   ctx->d2hBytes += (unsigned long long)M->NR * M->NC * es;
   return 0;
 }
+// copy stream for downloads that overlap with assembly (scuffcuda_matrix_download_region_async)
+static cudaStream_t copy_stream(scuffcuda_context *ctx)
+{ static std::map<scuffcuda_context *, cudaStream_t> streams;
+  auto it = streams.find(ctx);
+  if (it != streams.end()) return it->second;
+  cudaStream_t s = nullptr;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); s = ctx->stream; }
+  streams[ctx] = s;
+  return s;
+}
+int scuffcuda_matrix_download_region_async(scuffcuda_context *ctx, int h, void *host, long ld, int row0, int nrows, int col0, int ncols)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  if (ld < M->NR) return fail(ctx, "matrix_download_region: ld < NR");
+  if (row0 < 0 || col0 < 0 || nrows < 0 || ncols < 0 || row0 + nrows > M->NR || col0 + ncols > M->NC)
+   return fail(ctx, "matrix_download_region: region (%d+%d, %d+%d) out of range for %dx%d", row0, nrows, col0, ncols, M->NR, M->NC);
+  if (nrows == 0 || ncols == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  size_t es = (M->isReal ? 1 : 2) * sizeof(double);
+  cudaStream_t cs = copy_stream(ctx);
+  // everything enqueued on the compute stream so far is visible to the copy
+  cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventRecord(e, ctx->stream)); CK(cudaStreamWaitEvent(cs, e, 0)); CK(cudaEventDestroy(e));
+  CK(cudaMemcpy2DAsync((char *)host + ((size_t)row0 + (size_t)col0 * ld) * es, ld * es,
+                       (const char *)M->d + ((size_t)row0 + (size_t)col0 * M->NR) * es, M->NR * es,
+                       (size_t)nrows * es, ncols, cudaMemcpyDeviceToHost, cs));
+  ctx->d2hBytes += (unsigned long long)nrows * ncols * es;
+  return 0;
+}
+int scuffcuda_matrix_download_wait(scuffcuda_context *ctx, int fence_compute)
+{ CK(cudaSetDevice(ctx->device));
+  cudaStream_t cs = copy_stream(ctx);
+  if (fence_compute)
+   { // later work on the compute stream (e.g. the mirror pass) must not overtake the copies in flight
+     cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+     CK(cudaEventRecord(e, cs)); CK(cudaStreamWaitEvent(ctx->stream, e, 0)); CK(cudaEventDestroy(e));
+     return 0; }
+  CK(cudaStreamSynchronize(cs));
+  return 0;
+}
 int scuffcuda_matrix_upload(scuffcuda_context *ctx, int h, const void *host, long ld)
 { Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
   if (ld < M->NR) return fail(ctx, "matrix_upload: ld < NR");
@@ -258,6 +298,25 @@ static cudaStream_t near_stream(scuffcuda_context *ctx)
   return s;
 }
 
+}  // extern "C" (paused)
+namespace scuffcuda {
+void *mapped_host_scratch(scuffcuda_context *ctx, size_t bytes, int slot)
+{ struct Buf { void *p = nullptr; size_t n = 0; };
+  static std::map<std::pair<scuffcuda_context *, int>, Buf> bufs;
+  Buf &B = bufs[std::make_pair(ctx, slot)];
+  if (bytes > B.n)
+   { if (B.p) cudaFreeHost(B.p);
+     B.p = nullptr; B.n = 0;
+     size_t want = std::max<size_t>(bytes, 1 << 16);
+     if (cudaHostAlloc(&B.p, want, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); B.p = nullptr; return nullptr; }
+     B.n = want; }
+  return B.p;
+}
+__global__ void export_counters_kernel(const unsigned long long *src, unsigned long long *dstHost)
+{ dstHost[threadIdx.x] = src[threadIdx.x]; }
+}
+extern "C" {
+
 static cdouble csqrt2(cdouble z)   // libs/libhrutil/libhrutil.cc:692-699
 { cdouble r = std::sqrt(z); return (imag(r) < 0.0) ? -r : r; }
 
@@ -280,7 +339,11 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   M->factored = false;
   ctx->timing[3] = 0.0;
 
-  if (!a->accumulate) launch_zero_block(ctx, *M, a->row_offset, NBFA, a->col_offset, NBFB);
+  if (!a->accumulate)
+   { // a column-range call owns (and clears) only its columns of the block
+     int c0 = a->col_offset, c1 = a->col_offset + NBFB;
+     if (a->col_end > 0 && a->col_end != 0x7fffffff) { c0 = std::max(c0, a->col_begin); c1 = std::min(c1, a->col_end); }
+     launch_zero_block(ctx, *M, a->row_offset, NBFA, c0, c1 - c0); }
 
   cdouble Omega(a->omega[0], a->omega[1]);
   const cdouble II(0.0, 1.0);
@@ -348,8 +411,12 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   CK(cudaEventSynchronize(ev[3]));
   float tot; cudaEventElapsedTime(&tot, ev[0], ev[3]);
   ctx->timing[0] = tot; ctx->timing[1] = farMs; ctx->timing[2] = nearMs;
-  unsigned long long hc[16];
-  CK(cudaMemcpy(hc, ctx->dcounters, sizeof hc, cudaMemcpyDeviceToHost));
+  // counters come back through mapped host memory (no D2H copy-engine transfer: one may be busy with a matrix download)
+  unsigned long long *hc = (unsigned long long *)scuffcuda::mapped_host_scratch(ctx, 16 * sizeof(unsigned long long), 0);
+  if (!hc) return fail(ctx, "assemble_block: cannot allocate mapped host memory");
+  ctx->launches++;
+  scuffcuda::export_counters_kernel<<<1, 16, 0, ctx->stream>>>(ctx->dcounters, hc);
+  CK(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 5; i++) ctx->counts[i] = hc[i];
   ctx->pairCounts[0] = hc[5]; ctx->pairCounts[1] = hc[6];
   for (int i = 0; i < 7; i++) cudaEventDestroy(ev[i]);

@@ -15,4 +15,9 @@ int run_ho(scuffcuda_context *ctx, const NearArgs &A, const int *hoIdx, int n, i
 // items[t] = 36*nearIndex + 18*highk + 9*swapped + 3*i + j  (host memory)
 int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T, const int *items, int nItems);
 
+// Page-locked, device-mapped host memory that kernels write their per-item status words / counters into directly
+// (stores over PCIe from the SMs).  No copy engine is involved, so reading them back never queues behind a bulk
+// device->host matrix download in flight on the copy stream (scuffcuda_matrix_download_region_async).
+void *mapped_host_scratch(scuffcuda_context *ctx, size_t bytes, int slot);
+
 }  // namespace scuffcuda

@@ -473,16 +473,18 @@ int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T,
    { if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
      if (cudaMalloc(&ctx->dscratch, need) != cudaSuccess) { cudaGetLastError(); ctx->err = "Taylor-Duffy scratch allocation failed"; return 1; }
      ctx->scratchBytes = need; }
-  int *dItems = (int *)ctx->dscratch, *dStatus = dItems + batch;
+  int *dItems = (int *)ctx->dscratch;
+  int *hStatus = (int *)mapped_host_scratch(ctx, (size_t)batch * sizeof(int), 1);
+  if (!hStatus) { ctx->err = "Taylor-Duffy: cannot allocate mapped host memory"; return 1; }
   double *scr = (double *)((char *)ctx->dscratch + hdr);
   std::vector<int> status(batch);
   for (int first = 0; first < nItems; first += batch)
    { const int n = std::min(batch, nItems - first);
      cudaMemcpyAsync(dItems, items + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
      ctx->launches++;
-     td_general_kernel<<<(unsigned)(threads / 64), 64, 0, ctx->stream>>>(A, T, dItems, n, scr, dStatus);
-     cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+     td_general_kernel<<<(unsigned)(threads / 64), 64, 0, ctx->stream>>>(A, T, dItems, n, scr, hStatus);
      cudaError_t e = cudaStreamSynchronize(ctx->stream);
+     std::copy(hStatus, hStatus + n, status.begin());
      if (e != cudaSuccess) { ctx->err = std::string("td_general_kernel: ") + cudaGetErrorString(e); return 1; }
      for (int q = 0; q < n; q++)
       if (status[q]) { ctx->err = status[q] == 1 ? "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"

@@ -264,7 +264,9 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
      const int batch = (int)std::min<size_t>(pairs.size(), ((size_t)12 << 30) / perPair);
      const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
      if (td_grow_scratch(ctx, hdr + (size_t)batch * perPair)) return 1;
-     int *dPairs = (int *)ctx->dscratch, *dStatus = dPairs + batch;
+     int *dPairs = (int *)ctx->dscratch;
+     int *hStatus = (int *)mapped_host_scratch(ctx, (size_t)batch * sizeof(int), 1);
+     if (!hStatus) { ctx->err = "Taylor-Duffy: cannot allocate mapped host memory"; return 1; }
      double *scr = (double *)((char *)ctx->dscratch + hdr);
      std::vector<int> status;
      for (size_t first = 0; first < pairs.size(); first += batch)
@@ -272,10 +274,9 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
         cudaMemcpyAsync(dPairs, pairs.data() + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
         ctx->launches++;
         const long threads = (long)n * TD_GROUP;
-        td_ct_pair_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(A, T, dPairs, n, scr, dStatus);
-        status.resize(n);
-        cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        td_ct_pair_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(A, T, dPairs, n, scr, hStatus);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        status.assign(hStatus, hStatus + n);
         if (e != cudaSuccess) { ctx->err = std::string("td_ct_pair_kernel: ") + cudaGetErrorString(e); return 1; }
         for (int q = 0; q < n; q++)
          if (status[q]) { ctx->err = "Taylor-Duffy cubature exceeded the tabulated Clenshaw-Curtis levels"; return 1; }
@@ -295,7 +296,9 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
      const int threads = ((batch + 127) / 128) * 128;
      const size_t hdr = (((size_t)batch * 2 * sizeof(int) + 255) / 256) * 256;
      if (td_grow_scratch(ctx, hdr + (size_t)threads * perItem)) return 1;
-     int *dItems = (int *)ctx->dscratch, *dStatus = dItems + batch;
+     int *dItems = (int *)ctx->dscratch;
+     int *hStatus = (int *)mapped_host_scratch(ctx, (size_t)batch * sizeof(int), 1);
+     if (!hStatus) { ctx->err = "Taylor-Duffy: cannot allocate mapped host memory"; return 1; }
      double *scr = (double *)((char *)ctx->dscratch + hdr);
      std::vector<int> next;
      for (size_t first = 0; first < work.size(); first += batch)
@@ -303,10 +306,9 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
         cudaMemcpyAsync(dItems, work.data() + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
         ctx->launches++;
         // the grid always spans `threads` threads so that the scratch stride is fixed
-        td_ct_kernel<<<threads / 128, 128, 0, ctx->stream>>>(A, T, dItems, n, scr, maxM, dStatus);
-        status.resize(n);
-        cudaMemcpyAsync(status.data(), dStatus, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+        td_ct_kernel<<<threads / 128, 128, 0, ctx->stream>>>(A, T, dItems, n, scr, maxM, hStatus);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        status.assign(hStatus, hStatus + n);
         if (e != cudaSuccess) { ctx->err = std::string("td_ct_kernel: ") + cudaGetErrorString(e); return 1; }
         for (int q = 0; q < n; q++) if (status[q]) next.push_back(work[first + q]);
       }

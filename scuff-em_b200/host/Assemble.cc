@@ -4,6 +4,8 @@
 // Mate reuse, symmetric fill) and GetSurfaceSurfaceInteractions SurfaceSurfaceInteractions.cc:
 // 426-492 (common regions, Eps/Mu/Sign selection, OmitRegion, early returns).
 #include <cstdlib>
+#include <cmath>
+#include <vector>
 #include "host_internal.h"
 
 namespace scuff {
@@ -88,6 +90,48 @@ void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double
   M->SyncToHost();
 }
 
+// The reference hands back a HOST matrix; for large N the copy-back over PCIe (16 N^2 bytes) takes several times longer
+// than the assembly itself.  Overlap the two: assemble the upper triangle in K column blocks (column-block mode of
+// scuffcuda_assemble_block), mirror each block's diagonal square as soon as it is complete and start the download of the
+// finished trapezoid rows [0,c1) x columns [c0,c1) on the copy stream while the next block is assembled; after the last
+// block the whole matrix is mirrored once and the remaining lower parts follow.  Same entries as the one-pass assembly
+// (summation order inside the atomics aside).  SCUFF_CUDA_PIPELINE_BLOCKS=1 disables, =K forces K blocks.
+static int PipelineBlocks(int N)
+{ const char *e = getenv("SCUFF_CUDA_PIPELINE_BLOCKS");
+  if (e && e[0]) { int k = atoi(e); return k < 1 ? 1 : (k > 64 ? 64 : k); }
+  // every column-block call has a latency floor of ~6 ms (the adaptive Taylor-Duffy kernels of its diagonal pairs): the
+  // overlap pays once the copy-back itself takes several times that (16 N^2 bytes at ~50 GB/s: N >~ 16 000)
+  return N >= 16000 ? 4 : 1;
+}
+
+static void AssembleBEMMatrixPipelined(RWGGeometry *G, cdouble Omega, HMatrix *M, int K)
+{ scuffcuda_context *ctx = GetCudaContext();
+  const int N = G->TotalBFs;
+  M->EnsureDevice();
+  void *host = M->RealComplex == LHM_REAL ? (void *)M->DM : (void *)M->ZM;
+  std::vector<int> c(K + 1);
+  for (int j = 0; j <= K; j++) c[j] = (int)(N * sqrt((double)j / K) + 0.5);    // equal upper-triangle area per block
+  c[0] = 0; c[K] = N;
+  unsigned long long Counts[5] = { 0, 0, 0, 0, 0 };
+  for (int j = 0; j < K; j++)
+   { if (c[j + 1] <= c[j]) continue;
+     G->AssembleBEMMatrixDevice(Omega, 0, M, c[j], c[j + 1]);
+     for (int i = 0; i < 5; i++) Counts[i] += G->LastPPICounts[i];
+     if (scuffcuda_matrix_symmetrize(ctx, M->DeviceHandle, c[j], c[j + 1] - c[j])
+         || scuffcuda_matrix_download_region_async(ctx, M->DeviceHandle, host, M->NR, 0, c[j + 1], c[j], c[j + 1] - c[j]))
+      ErrExit("%s", scuffcuda_last_error(ctx)); }
+  // the mirror pass writes below the diagonal squares only what they already hold, but keep it ordered after the copies
+  if (scuffcuda_matrix_download_wait(ctx, 1) || scuffcuda_matrix_symmetrize(ctx, M->DeviceHandle, 0, N))
+   ErrExit("%s", scuffcuda_last_error(ctx));
+  for (int j = 0; j + 1 < K; j++)
+   if (c[j + 1] > c[j]
+       && scuffcuda_matrix_download_region_async(ctx, M->DeviceHandle, host, M->NR, c[j + 1], N - c[j + 1], c[j], c[j + 1] - c[j]))
+    ErrExit("%s", scuffcuda_last_error(ctx));
+  if (scuffcuda_matrix_download_wait(ctx, 0)) ErrExit("%s", scuffcuda_last_error(ctx));
+  for (int i = 0; i < 5; i++) G->LastPPICounts[i] = Counts[i];
+  M->HostStale = false;
+}
+
 HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *M)
 { if (LBasis == 0 && kBloch != 0 && (kBloch[0] != 0.0 || kBloch[1] != 0.0))
    ErrExit("%s:%i: Bloch wavevector is undefined for compact geometries", __FILE__, __LINE__);
@@ -97,8 +141,11 @@ HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *
   else if (M->NR != TotalBFs || M->NC != TotalBFs)
    { Warn("wrong-size matrix passed to AssembleBEMMatrix; reallocating...");
      M = AllocateBEMMatrix(); }
-  AssembleBEMMatrixDevice(Omega, kBloch, M);
-  M->SyncToHost();
+  int K = PipelineBlocks(TotalBFs);
+  if (LBasis == 0 && K > 1 && M->StorageType == LHM_NORMAL) AssembleBEMMatrixPipelined(this, Omega, M, K);
+  else
+   { AssembleBEMMatrixDevice(Omega, kBloch, M);
+     M->SyncToHost(); }
   return M;
 }
 
