@@ -59,7 +59,7 @@ td_ct_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, d
 // contractions), the quadrature sums are reduced with warp shuffles, and every item keeps its own convergence state, so
 // each one stops exactly where the reference's independent pcubature call stops (pcubature.c: RelTol 1e-10 per
 // component, numEval > MaxEval = 1000); only the floating-point summation order of the quadrature sum differs.
-#define TD_GROUP 8
+#define TD_GROUP_DEFAULT 8
 #define TD_COOP_MAXM 9
 #define TD_COOP_NPTS ((1 << (TD_COOP_MAXM + 1)) + 1)
 #define TD_COOP_UDBL 64                                          /* doubles of coefficients per item (60 used) */
@@ -97,12 +97,13 @@ __device__ void td_ct_pair_eval(double A2, double AdB, double B2, cd k, int nLo,
 }
 
 // pairs[g] = 512*nearIndex + 9-bit mask of the (i,j) combinations (bit 3i+j) that feed a matrix entry
+template <int TD_GROUP>
 __global__ void __launch_bounds__(128)
 td_ct_pair_kernel(const NearArgs A, const TDTables T, const int *pairs, int nPairs, double *scratch, int *pairStatus)
 { const int g = (blockIdx.x * blockDim.x + threadIdx.x) / TD_GROUP;
   const int gl = threadIdx.x & (TD_GROUP - 1);
   if (g >= nPairs) return;                                                  // whole groups leave together
-  const unsigned gmask = ((1u << TD_GROUP) - 1u) << ((threadIdx.x & 31) & ~(TD_GROUP - 1));
+  const unsigned gmask = (TD_GROUP == 32 ? 0xffffffffu : ((1u << (TD_GROUP & 31)) - 1u)) << ((threadIdx.x & 31) & ~(TD_GROUP - 1));
   const int code = pairs[g];
   const NearPair N = A.near[code >> 9];
   const PanelRec &Pa = A.pa[N.pa], &Pb = A.pb[N.pb];
@@ -273,8 +274,13 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
       { const int n = (int)std::min<size_t>(batch, pairs.size() - first);
         cudaMemcpyAsync(dPairs, pairs.data() + first, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
         ctx->launches++;
-        const long threads = (long)n * TD_GROUP;
-        td_ct_pair_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->stream>>>(A, T, dPairs, n, scr, hStatus);
+        static const int group = []{ const char *e = getenv("SCUFF_CUDA_TD_GROUP"); int g = e ? atoi(e) : TD_GROUP_DEFAULT;
+                                     return (g == 8 || g == 16 || g == 32) ? g : TD_GROUP_DEFAULT; }();
+        const long threads = (long)n * group;
+        const unsigned grid = (unsigned)((threads + 127) / 128);
+        if (group == 8) td_ct_pair_kernel<8><<<grid, 128, 0, ctx->stream>>>(A, T, dPairs, n, scr, hStatus);
+        else if (group == 16) td_ct_pair_kernel<16><<<grid, 128, 0, ctx->stream>>>(A, T, dPairs, n, scr, hStatus);
+        else td_ct_pair_kernel<32><<<grid, 128, 0, ctx->stream>>>(A, T, dPairs, n, scr, hStatus);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);
         status.assign(hStatus, hStatus + n);
         if (e != cudaSuccess) { ctx->err = std::string("td_ct_pair_kernel: ") + cudaGetErrorString(e); return 1; }
