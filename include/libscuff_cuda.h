@@ -60,6 +60,11 @@ int scuffcuda_matrix_zero(scuffcuda_context *ctx, int handle);
  * within one matrix — the Mate[] diagonal-block reuse of AssembleBEMMatrix.cc:731-737  */
 int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int handle, int dst_row, int dst_col,
                                 int num_rows, int num_cols, int src_row, int src_col);
+/* StampInNeighborBlock (AssembleBEMMatrix.cc:72-114), the Bloch-phase accumulation of one neighbour-cell block of a
+ * periodic geometry: M[row_off+r, col_off+c] += BPF*B[r,c] (+ conj(BPF)*B[c,r] if use_symmetry), BPF = phase[0]+i*phase[1]
+ * = exp(i kBloch.L); `handle_B` is a complex NBFA x NBFB matrix filled by scuffcuda_assemble_block with use_displacement */
+int scuffcuda_matrix_stamp_neighbor_block(scuffcuda_context *ctx, int handle, int row_off, int col_off,
+                                          int handle_B, const double phase[2], int use_symmetry);
 /* upper -> lower triangle copy of the square sub-block at (offset,offset) of size n
  * (AssembleBEMMatrix.cc:753-758, SurfaceSurfaceInteractions.cc:573-583)                */
 int scuffcuda_matrix_symmetrize(scuffcuda_context *ctx, int handle, int offset, int n);

@@ -11,6 +11,10 @@
  *   ref_driver ssi    <geo> <wRe> <wIm> <nsa> <nsb> <Lx> <Ly> <Lz> <out.bin> [--cache-out f]
  *        GetSurfaceSurfaceInteractions (SurfaceSurfaceInteractions.cc:426-585) for one surface pair with surface b displaced
  *        by L (the neighbour-cell blocks of the periodic assembly, AssembleBEMMatrix.cc:72-114), not Symmetric
+ *   ref_driver pbcinner <geo> <wRe> <wIm> <kx> <ky> <nsa> <nsb> <out.bin> [--cache-out f]
+ *        periodic geometry: AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:349-565) MINUS its step 2 (outer cells through the
+ *        GBar tables, :530-560, recomputed here with the reference's own CreateRegionGBA + GetSurfaceSurfaceInteractions):
+ *        what remains is step 1, the Bloch-phased inner-cell blocks.  Also writes <out.bin>.full (the complete block).
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
  *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
@@ -128,6 +132,43 @@ int main(int argc, char **argv)
      if(CacheOut) StoreCache(CacheOut);
      FILE *f=fopen(Out,"wb"); if(!f) return 1;
      fwrite(B->ZM,sizeof(cdouble),(size_t)B->NR*B->NC,f); fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"pbcinner"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); double kBloch[2]={atof(argv[5]),atof(argv[6])};
+     int nsa=atoi(argv[7]), nsb=atoi(argv[8]); const char *Out=argv[9]; const char *CacheOut=0;
+     for(int n=10;n<argc;n++) if(!strcmp(argv[n],"--cache-out")) CacheOut=argv[++n];
+     if (G->LBasis==0) { fprintf(stderr,"pbcinner: geometry is not periodic\n"); return 1; }
+     int NBFA=G->Surfaces[nsa]->NumBFs, NBFB=G->Surfaces[nsb]->NumBFs;
+     HMatrix *Full=new HMatrix(NBFA,NBFB,LHM_COMPLEX), *Outer=new HMatrix(NBFA,NBFB,LHM_COMPLEX);
+     double t0=Now();
+     G->AssembleBEMMatrixBlock(nsa,nsb,Omega,kBloch,Full);
+     double t1=Now();
+     // step 2 alone, as :530-560 does it
+     int CR[2]; double Signs[2];
+     int NCR=CountCommonRegions(G->Surfaces[nsa],G->Surfaces[nsb],CR,Signs);
+     Outer->Zero();
+     if (NCR>0)
+      { int nr1=CR[0], nr2=(NCR==2)?CR[1]:-1;
+        GetSSIArgStruct MyArgs, *Args=&MyArgs; InitGetSSIArgs(Args);
+        Args->G=G; Args->Sa=G->Surfaces[nsa]; Args->Sb=G->Surfaces[nsb]; Args->Omega=Omega;
+        Args->Displacement=0; Args->Symmetric=false; Args->Accumulate=true; Args->B=Outer;
+        Args->OmitRegion1=false; Args->OmitRegion2=(nr2==-1);
+        Args->GBA1=G->CreateRegionGBA(nr1,Omega,kBloch,nsa,nsb);
+        if (Args->GBA1==0) Args->OmitRegion1=true;
+        if (!Args->OmitRegion2) { Args->GBA2=G->CreateRegionGBA(nr2,Omega,kBloch,nsa,nsb); if (Args->GBA2==0) Args->OmitRegion2=true; }
+        else Args->GBA2=0;
+        if (!Args->OmitRegion1 || !Args->OmitRegion2) GetSurfaceSurfaceInteractions(Args);
+      }
+     double nF=0, nO=0;
+     for(size_t i=0;i<(size_t)NBFA*NBFB;i++) { nF+=norm(Full->ZM[i]); nO+=norm(Outer->ZM[i]); }
+     printf("{\"NR\": %i, \"NC\": %i, \"real\": 0, \"threads\": %i, \"times\": [%.6f], \"norm_full\": %.17g, \"norm_outer\": %.17g}\n",
+            NBFA,NBFB,omp_get_max_threads(),t1-t0,sqrt(nF),sqrt(nO));
+     if(CacheOut) StoreCache(CacheOut);
+     char fn[2000]; snprintf(fn,2000,"%s.full",Out);
+     FILE *f=fopen(fn,"wb"); if(!f) return 1; fwrite(Full->ZM,sizeof(cdouble),(size_t)NBFA*NBFB,f); fclose(f);
+     for(size_t i=0;i<(size_t)NBFA*NBFB;i++) Full->ZM[i]-=Outer->ZM[i];
+     f=fopen(Out,"wb"); if(!f) return 1; fwrite(Full->ZM,sizeof(cdouble),(size_t)NBFA*NBFB,f); fclose(f); return 0;
    }
 
   if(!strcmp(Cmd,"ppis"))

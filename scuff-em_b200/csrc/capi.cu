@@ -171,6 +171,16 @@ int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int h, int dr, int dc, i
   CK(cudaSetDevice(ctx->device));
   launch_copy_block(ctx, *M, dr, dc, nr, nc, sr, sc); CK(cudaGetLastError()); return 0;
 }
+int scuffcuda_matrix_stamp_neighbor_block(scuffcuda_context *ctx, int h, int row_off, int col_off, int hB, const double phase[2], int use_symmetry)
+{ Matrix *M = get_matrix(ctx, h), *B = get_matrix(ctx, hB);
+  if (!M || !B) return fail(ctx, "invalid matrix handle %d", !M ? h : hB);
+  if (M->isReal || B->isReal) return fail(ctx, "matrix_stamp_neighbor_block: both matrices must be complex");
+  if (row_off < 0 || col_off < 0 || row_off + B->NR > M->NR || col_off + B->NC > M->NC) return fail(ctx, "matrix_stamp_neighbor_block: block out of range");
+  if (use_symmetry && B->NR != B->NC) return fail(ctx, "matrix_stamp_neighbor_block: use_symmetry needs a square block");
+  CK(cudaSetDevice(ctx->device));
+  launch_stamp_neighbor(ctx, *M, row_off, col_off, *B, phase[0], phase[1], use_symmetry ? 1 : 0); CK(cudaGetLastError());
+  M->factored = false; return 0;
+}
 int scuffcuda_matrix_symmetrize(scuffcuda_context *ctx, int h, int off, int n)
 { Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
   if (off < 0 || off + n > M->NR || off + n > M->NC) return fail(ctx, "matrix_symmetrize: block out of range");

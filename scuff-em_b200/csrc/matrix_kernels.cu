@@ -24,6 +24,39 @@ __global__ void copy_block_kernel(double *M, long ld, int w, int dstRow, int dst
    }
 }
 
+// Bloch-phase stamp of a neighbour-cell block (StampInNeighborBlock, AssembleBEMMatrix.cc:72-114):
+// M[rowOff+r, colOff+c] += BPF * B[r,c]  (+ conj(BPF) * B[c,r] when useSymmetry); both matrices complex, column-major.
+// 32x32 tiles: the transposed read of B goes through shared memory so that both global reads are coalesced.
+__global__ void stamp_neighbor_kernel(double *M, long ldM, int rowOff, int colOff, const double *B, long ldB, int nr, int nc,
+                                      double pr, double pi, int useSymmetry)
+{ __shared__ double tile[32][33 * 2];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  if (useSymmetry)
+   for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    { // element B[c0 + threadIdx.x, r0 + j]: row index runs with threadIdx.x (contiguous)
+      const int rr = c0 + threadIdx.x, cc = r0 + j;
+      double x = 0.0, y = 0.0;
+      if (rr < nr && cc < nc) { const size_t s = ((size_t)rr + (size_t)cc * ldB) * 2; x = B[s]; y = B[s + 1]; }
+      tile[j][2 * threadIdx.x] = x; tile[j][2 * threadIdx.x + 1] = y; }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+   { const int r = r0 + threadIdx.x, c = c0 + j;
+     if (r >= nr || c >= nc) continue;
+     const size_t s = ((size_t)r + (size_t)c * ldB) * 2;
+     const double bx = B[s], by = B[s + 1];
+     double vx = pr * bx - pi * by, vy = pr * by + pi * bx;
+     if (useSymmetry)
+      { const double tx = tile[threadIdx.x][2 * j], ty = tile[threadIdx.x][2 * j + 1];       // B[c, r]
+        vx += pr * tx + pi * ty; vy += pr * ty - pi * tx; }
+     const size_t d = ((size_t)(rowOff + r) + (size_t)(colOff + c) * ldM) * 2;
+     M[d] += vx; M[d + 1] += vy; }
+}
+void launch_stamp_neighbor(scuffcuda_context *ctx, const Matrix &M, int rowOff, int colOff, const Matrix &B, double pr, double pi, int useSymmetry)
+{ dim3 grid((B.NR + 31) / 32, (B.NC + 31) / 32), block(32, 8);
+  ctx->launches++;
+  stamp_neighbor_kernel<<<grid, block, 0, ctx->stream>>>(M.d, M.NR, rowOff, colOff, B.d, B.NR, B.NR, B.NC, pr, pi, useSymmetry);
+}
+
 // lower(r,c) = upper(c,r) for r>c, 32x32 tiles through shared memory so both the read and the
 // write are coalesced (column-major: consecutive rows are contiguous)
 template <int W>

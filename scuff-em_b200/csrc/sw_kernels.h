@@ -15,6 +15,8 @@ int run_ho(scuffcuda_context *ctx, const NearArgs &A, const int *hoIdx, int n, i
 // items[t] = 36*nearIndex + 18*highk + 9*swapped + 3*i + j  (host memory)
 int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T, const int *items, int nItems);
 
+void launch_stamp_neighbor(scuffcuda_context *ctx, const Matrix &M, int rowOff, int colOff, const Matrix &B, double pr, double pi, int useSymmetry);
+
 // Page-locked, device-mapped host memory that kernels write their per-item status words / counters into directly
 // (stores over PCIe from the SMs).  No copy engine is involved, so reading them back never queues behind a bulk
 // device->host matrix download in flight on the copy stream (scuffcuda_matrix_download_region_async).

@@ -187,8 +187,59 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
 
 HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, HMatrix *M) { return AssembleBEMMatrix(Omega, 0, M); }
 
+// Step 1 of the periodic branch of AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:465-519): the kBloch-independent blocks
+// of the innermost lattice cells, each from the displaced-surface assembly on the device and stamped into M with its Bloch
+// phase factor (StampInNeighborBlock, :72-114).  Leaves the block of M in HBM (M->HostStale).
+void RWGGeometry::AssembleInnerCellBlocks(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset, int ColOffset)
+{ if (LBasis == 0) ErrExit("AssembleInnerCellBlocks: geometry is not periodic");
+  if (!kBloch) ErrExit("%s:%i: Bloch wavevector must be specified for PBC geometries", __FILE__, __LINE__);
+  if (M->RealComplex != LHM_COMPLEX) ErrExit("AssembleInnerCellBlocks: the BEM matrix of a periodic geometry is complex");
+  scuffcuda_context *ctx = GetCudaContext();
+  RWGSurface *Sa = Surfaces[nsa], *Sb = Surfaces[nsb];
+  int CR[2]; double Signs[2];
+  int NumCommonRegions = CountCommonRegions(Sa, Sb, CR, Signs);
+  if (NumCommonRegions == 0) return;
+  const int nr1 = CR[0], nr2 = NumCommonRegions == 2 ? CR[1] : -1;
+  const bool UseSymmetry = (nsa == nsb), OneDLattice = (LDim == 1);
+  double LBV[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
+  for (int i = 0; i < 3; i++) { LBV[0][i] = LBasis->GetEntryD(i, 0); if (LDim > 1) LBV[1][i] = LBasis->GetEntryD(i, 1); }
+
+  M->EnsureDevice();
+  // M->ZeroBlock(RowOffset, NBFA, ColOffset, NBFB) on the device: a block assembly with both regions omitted clears it
+  AssembleBlockOnDevice(this, nsa, nsb, Omega, M, RowOffset, ColOffset, false, false, 0, true, true);
+  HMatrix B(Sa->NumBFs, Sb->NumBFs, LHM_COMPLEX);
+  unsigned long long Counts[5] = { 0, 0, 0, 0, 0 };
+  bool done = false;
+  for (int n1 = +1; n1 >= -1 && !done; n1--)
+   for (int n2 = +1; n2 >= -1 && !done; n2--)
+    { if (OneDLattice && n2 != 0) continue;
+      double L[3] = { n1 * LBV[0][0] + n2 * LBV[1][0], n1 * LBV[0][1] + n2 * LBV[1][1], 0.0 };
+      // contributions of regions that do not extend across the cell boundary are omitted (:487-499)
+      bool Omit1, Omit2;
+      if (n1 == 0 && n2 == 0) { Omit1 = false; Omit2 = (nr2 == -1); }
+      else
+       { Omit1 = Omit2 = true;
+         if (n1 != 0 && RegionIsExtended[0][nr1]) Omit1 = false;
+         if (n1 != 0 && nr2 != -1 && RegionIsExtended[0][nr2]) Omit2 = false;
+         if (n2 != 0 && RegionIsExtended[1][nr1]) Omit1 = false;
+         if (n2 != 0 && nr2 != -1 && RegionIsExtended[1][nr2]) Omit2 = false; }
+      const bool Center = (n1 == 0 && n2 == 0);
+      AssembleBlockOnDevice(this, nsa, nsb, Omega, &B, 0, 0, UseSymmetry && Center, false, L, Omit1, Omit2);
+      for (int i = 0; i < 5; i++) Counts[i] += LastPPICounts[i];
+      const double Arg = kBloch[0] * L[0] + kBloch[1] * L[1], BPF[2] = { cos(Arg), sin(Arg) };
+      if (scuffcuda_matrix_stamp_neighbor_block(ctx, M->DeviceHandle, RowOffset, ColOffset, B.DeviceHandle, BPF, UseSymmetry && !Center))
+       ErrExit("%s", scuffcuda_last_error(ctx));
+      if (UseSymmetry && Center) done = true; }
+  for (int i = 0; i < 5; i++) LastPPICounts[i] = Counts[i];
+  M->HostStale = true;
+}
+
 void RWGGeometry::AssembleBEMMatrixBlockPBC(int, int, cdouble, double *, HMatrix *, int, int)
-{ ErrExit("periodic (LATTICE) geometries are not yet supported by the device assembly path"); }
+{ // Step 1 (inner cells: AssembleInnerCellBlocks above) runs on the device; step 2 needs the Ewald-summed periodic Green's
+  // function tables (CreateRegionGBA / GBarVDEwald), which are not built yet.  A matrix without them would be wrong: refuse.
+  ErrExit("periodic (LATTICE) geometries are not yet supported by the device assembly path: the outer-cell contribution "
+          "(Ewald-summed GBar interpolation tables, AssembleBEMMatrix.cc:530-560) is missing");
+}
 
 // PreloadCache / StoreCache (libscuff.h:662-663 -> GlobalFIPPICache.PreLoad/Store)
 void PreloadCache(const char *FileName)

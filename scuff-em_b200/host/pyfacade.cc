@@ -91,6 +91,9 @@ int scuffb200_matrix_symmetrize(void *m)
 int scuffb200_assemble_block(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off)
 { RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
   GUARD(G->AssembleBEMMatrixBlock(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, 0, row_off, col_off); return 0;, 1) }
+int scuffb200_assemble_inner_cells(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off)
+{ RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
+  GUARD(G->AssembleInnerCellBlocks(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, row_off, col_off); M->SyncToHost(); return 0;, 1) }
 int scuffb200_ppi_counts(void *g, unsigned long long *out) { for (int i = 0; i < 5; i++) out[i] = ((RWGGeometry *)g)->LastPPICounts[i]; return 0; }
 int scuffb200_lu_factorize(void *m) { GUARD(return ((HMatrix *)m)->LUFactorize();, 1) }
 int scuffb200_lu_solve(void *m, void *x) { GUARD(return ((HMatrix *)m)->LUSolve((HMatrix *)x);, 1) }

@@ -113,6 +113,8 @@ def host_lib():
         L.scuffb200_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]
         L.scuffb200_assemble_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
         L.scuffb200_matrix_symmetrize.argtypes = [C.c_void_p]
+        L.scuffb200_assemble_inner_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                     C.POINTER(C.c_double), C.c_int, C.c_int]
         L.scuffb200_assemble_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                                C.c_void_p, C.c_int, C.c_int]
         L.scuffb200_ppi_counts.argtypes = [C.c_void_p, C.c_void_p]
@@ -279,6 +281,14 @@ class RWGGeometry:
             kb = (C.c_double * 2)(float(kBloch[0]), float(kBloch[1]))
         _check(host_lib().scuffb200_assemble_block(self.ptr, M.ptr, nsa, nsb, float(np.real(Omega)),
                                                     float(np.imag(Omega)), kb, RowOffset, ColOffset))
+        return M
+
+    def AssembleInnerCellBlocks(self, nsa, nsb, Omega, kBloch, M, RowOffset=0, ColOffset=0):
+        """step 1 of the periodic branch of AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:465-519): neighbour-cell blocks
+        with Bloch phases; the outer-cell (Ewald GBar) part is not included"""
+        kb = (C.c_double * 2)(float(kBloch[0]), float(kBloch[1]))
+        _check(host_lib().scuffb200_assemble_inner_cells(self.ptr, M.ptr, nsa, nsb, float(np.real(Omega)),
+                                                          float(np.imag(Omega)), kb, RowOffset, ColOffset))
         return M
 
     def ppi_counts(self):

@@ -97,5 +97,24 @@ def ref_ssi(geo, omega, nsa, nsb, L, cache_out=None, tmpdir="/tmp/scuff_ref_cach
     return np.fromfile(out, dtype=np.complex128).reshape(info["NC"], info["NR"]).T, info
 
 
+def ref_pbcinner(geo, omega, kbloch, nsa, nsb, cache_out=None, tmpdir="/tmp/scuff_ref_cache", env=None):
+    """Reference AssembleBEMMatrixBlock of a periodic geometry minus its outer-cell (GBar) step, both from the reference's
+    own code (ref_driver pbcinner): the Bloch-phased inner-cell blocks.  Returns (inner, full, info)."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
+    os.makedirs(tmpdir, exist_ok=True)
+    key = hashlib.md5(repr(("pbcinner", geo, complex(omega), tuple(kbloch), nsa, nsb)).encode()).hexdigest()[:16]
+    out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
+    cmd = [REF_DRIVER, "pbcinner", os.path.basename(geo), repr(float(np.real(omega))), repr(float(np.imag(omega))),
+           repr(float(kbloch[0])), repr(float(kbloch[1])), str(nsa), str(nsb), out]
+    if cache_out:
+        cmd += ["--cache-out", cache_out]
+    r = subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True,
+                       env=dict(os.environ, **(env or {})))
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    rd = lambda f: np.fromfile(f, dtype=np.complex128).reshape(info["NC"], info["NR"]).T
+    return rd(out), rd(out + ".full"), info
+
+
 def rel_fro(A, B):
     return np.linalg.norm(A - B) / np.linalg.norm(B)
