@@ -321,19 +321,21 @@ far_kernel(const __grid_constant__ FarArgs A)
      { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
        if (!pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D)) continue; }
      if (A.S.colHi != 0x7fffffff)
-      { // column-block assembly: skip pairs none of whose entries can fall into the owned column range
+      { // column-block assembly: skip pairs none of whose (<= 9) entries falls into the owned column range.  The test is
+        // exact per entry (an interval test on the edge indices is loose: the three edges of a panel next to an icosahedron
+        // face boundary are thousands of indices apart, and such pairs were integrated by every block).
         const int *eb3 = (const int *)(Pb + 34);
-        int loA = 0x7fffffff, hiA = -1, loB = 0x7fffffff, hiB = -1;
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-         { const int e = sEi[m * FAR_THREADS], f = eb3[m];
-           if (e >= 0) { loA = min(loA, e); hiA = max(hiA, e); }
-           if (f >= 0) { loB = min(loB, f); hiB = max(hiB, f); } }
-        if (hiA < 0 || hiB < 0) continue;
-        // symmetric blocks store entry (min(e,f), max(e,f)): its column is max(e,f); otherwise the column is f
         const int w = A.S.bPEC ? 1 : 2;
-        const int lo = A.S.colOff + w * (A.symmetric ? max(loA, loB) : loB), hi = A.S.colOff + w * (A.symmetric ? max(hiA, hiB) : hiB) + w - 1;
-        if (hi < A.S.colLo || lo >= A.S.colHi) continue; }
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+          { const int e = sEi[i * FAR_THREADS], f = eb3[j];
+            // symmetric blocks store entry (min(e,f), max(e,f)): its column is max(e,f); otherwise the column is f
+            const int c0 = A.S.colOff + w * (A.symmetric ? max(e, f) : f);
+            any |= (e >= 0 && f >= 0 && c0 + w - 1 >= A.S.colLo && c0 < A.S.colHi); }
+        if (!any) continue; }
      sCnt[0] += 1;
 
      double r0 = 0.0;

@@ -96,16 +96,16 @@ near_desing_kernel(const NearArgs A)
   bool verySW;
   if (near_algorithm(N.ncv, A.kabs, Pa.R, Pb.R, A.forceTD, verySW) != 4) return;
   if (A.S.colHi != 0x7fffffff)
-   { // column-block assembly: skip pairs none of whose entries can fall into the owned column range
-     int loA = 0x7fffffff, hiA = -1, loB = 0x7fffffff, hiB = -1;
-     for (int m = 0; m < 3; m++)
-      { const int e = Pa.ei[m], f = Pb.ei[m];
-        if (e >= 0) { loA = min(loA, e); hiA = max(hiA, e); }
-        if (f >= 0) { loB = min(loB, f); hiB = max(hiB, f); } }
-     if (hiA < 0 || hiB < 0) return;
+   { // column-block assembly: skip pairs none of whose (<= 9) entries falls into the owned column range (exact per entry,
+     // as in far_kernel)
      const int w = A.S.bPEC ? 1 : 2;
-     const int lo = A.S.colOff + w * (A.S.symmetric ? max(loA, loB) : loB), hi = A.S.colOff + w * (A.S.symmetric ? max(hiA, hiB) : hiB) + w - 1;
-     if (hi < A.S.colLo || lo >= A.S.colHi) return; }
+     bool any = false;
+     for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+       { const int e = Pa.ei[i], f = Pb.ei[j];
+         const int c0 = A.S.colOff + w * (A.S.symmetric ? max(e, f) : f);
+         any |= (e >= 0 && f >= 0 && c0 + w - 1 >= A.S.colLo && c0 < A.S.colHi); }
+     if (!any) return; }
 
   double D[3];
   pair_rrel(Pa.C, Pa.R, Pb.C, Pb.R, A.useDisp != 0, A.L, D);
