@@ -280,6 +280,21 @@ def main():
         return 0
 
     t_far = sum(far_alone_ms) / len(far_alone_ms) * 1e-3
+    # DRAM bytes of one far-kernel launch from the committed `ncu --set full` capture of this same workload (null otherwise)
+    traffic, traffic_src = None, None
+    if a.nu == 26 and not a.material:
+        try:
+            unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+            tot = 0.0
+            fn = os.path.join(ROOT, "profiles", "r01_far_kernel_final_N20280.summary.txt")
+            for ln in open(fn):
+                w = ln.split()
+                if len(w) >= 3 and w[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(w[1]) * unit[w[2]]
+            if tot > 0:
+                traffic, traffic_src = tot, "profiles/r01_far_kernel_final_N20280.summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+        except Exception:
+            traffic = None
     kind = "dielectric" if a.material else "pec"
     fpp = FLOP_PER_POINT_PAIR[kind]
     flops = fpp * POINT_PAIRS * float(far_pairs)
@@ -295,7 +310,7 @@ def main():
                     "d2h_bytes_per_step": (tb1[1] - tb0[1]) // a.e2e_steps, "steps": a.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / a.e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "far_kernel<KMODE_REAL,%s>" % ("PSI" if a.material else "PEC"), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak, "traffic": None,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic": "%d flop/point pair (SURVEY 8d: 97 full, 54 for the PEC variant without the Psi half) x %d point pairs x %d far panel "
                                         "pairs per step (%d launch(es))" % (fpp, POINT_PAIRS, far_pairs, 2 if a.material else 1),
                          "achieved_at_97": 97.0 * POINT_PAIRS * float(far_pairs) / t_far / 1e12,
