@@ -9,11 +9,11 @@ ps = load("pyscuff", "scuff-em_b200/pyscuff.py"); mg = load("meshgen", "scuff-em
 import torch
 nu = int(sys.argv[1]) if len(sys.argv) > 1 else 26
 d = "/tmp/probe"; os.makedirs(d, exist_ok=True)
-geo = mg.write_sphere_geo(d, nu)
+geo = mg.write_sphere_geo(d, nu, sys.argv[2] if len(sys.argv) > 2 else None)
 G = ps.RWGGeometry(geo); N = G.TotalBFs
 M = G.AllocateBEMMatrix()
 G.AssembleBEMMatrix(1.0, M=M, to_host=False)
-for K in (1, 2, 4, 8):
+for K in ((1, 4) if len(sys.argv) > 2 else (1, 2, 4, 8)):
     c = [int(N * np.sqrt(j / K) + 0.5) for j in range(K + 1)]
     tt = []
     for rep in range(2):
