@@ -173,6 +173,8 @@ class RWGSurface
 
    /* internal */
    void *OTGT, *GT;             /* one-time and current rigid transformations */
+   void *SurfaceZeta;           /* SURFACE_IMPEDANCE expression in (w,x,y,z) (RWGSurface.cc:188-210), or 0 */
+   double GetOverlap(int neAlpha, int neBeta);   /* \int f_a . f_b  (OPFT.cc:81-226, Overlaps[0]) */
    char *InitRWGSurface(std::vector<double> &VertexCoordinates, std::vector<int> &PanelVertexIndices);
    char *InitEdgeList();
    void UpdatePanels();

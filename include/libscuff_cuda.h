@@ -60,6 +60,10 @@ int scuffcuda_matrix_zero(scuffcuda_context *ctx, int handle);
  * within one matrix — the Mate[] diagonal-block reuse of AssembleBEMMatrix.cc:731-737  */
 int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int handle, int dst_row, int dst_col,
                                 int num_rows, int num_cols, int src_row, int src_col);
+/* sparse accumulate M[rows[i], cols[i]] += vals[2i] + i*vals[2i+1] (HMatrix::AddEntry; a real matrix takes the real part):
+ * the surface-impedance term of AddSurfaceZetaContributionToBEMMatrix (SurfaceSurfaceInteractions.cc:339-421), whose
+ * O(NumEdges) overlap entries the host computes                                           */
+int scuffcuda_matrix_add_entries(scuffcuda_context *ctx, int handle, int n, const int *rows, const int *cols, const double *vals);
 /* StampInNeighborBlock (AssembleBEMMatrix.cc:72-114), the Bloch-phase accumulation of one neighbour-cell block of a
  * periodic geometry: M[row_off+r, col_off+c] += BPF*B[r,c] (+ conj(BPF)*B[c,r] if use_symmetry), BPF = phase[0]+i*phase[1]
  * = exp(i kBloch.L); `handle_B` is a complex NBFA x NBFB matrix filled by scuffcuda_assemble_block with use_displacement */

@@ -171,6 +171,14 @@ int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int h, int dr, int dc, i
   CK(cudaSetDevice(ctx->device));
   launch_copy_block(ctx, *M, dr, dc, nr, nc, sr, sc); CK(cudaGetLastError()); return 0;
 }
+int scuffcuda_matrix_add_entries(scuffcuda_context *ctx, int h, int n, const int *rows, const int *cols, const double *vals)
+{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+  for (int i = 0; i < n; i++)
+   if (rows[i] < 0 || rows[i] >= M->NR || cols[i] < 0 || cols[i] >= M->NC) return fail(ctx, "matrix_add_entries: entry %d (%d,%d) out of range", i, rows[i], cols[i]);
+  CK(cudaSetDevice(ctx->device));
+  if (launch_add_entries(ctx, *M, n, rows, cols, vals)) return fail(ctx, "matrix_add_entries: device error");
+  M->factored = false; return 0;
+}
 int scuffcuda_matrix_stamp_neighbor_block(scuffcuda_context *ctx, int h, int row_off, int col_off, int hB, const double phase[2], int use_symmetry)
 { Matrix *M = get_matrix(ctx, h), *B = get_matrix(ctx, hB);
   if (!M || !B) return fail(ctx, "invalid matrix handle %d", !M ? h : hB);

@@ -24,6 +24,29 @@ __global__ void copy_block_kernel(double *M, long ld, int w, int dstRow, int dst
    }
 }
 
+// sparse accumulate M[rows[i], cols[i]] += vals[i] (complex values; a real matrix takes the real part, as HMatrix::AddEntry)
+__global__ void add_entries_kernel(double *M, long ld, int w, int n, const int *rows, const int *cols, const double *vals)
+{ int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t d = ((size_t)rows[i] + (size_t)cols[i] * ld) * w;
+  atomicAdd(M + d, vals[2 * i]); if (w == 2) atomicAdd(M + d + 1, vals[2 * i + 1]);
+}
+int launch_add_entries(scuffcuda_context *ctx, const Matrix &M, int n, const int *rows, const int *cols, const double *vals)
+{ if (n <= 0) return 0;
+  int *d = nullptr;
+  const size_t bi = (size_t)n * sizeof(int), bv = (size_t)2 * n * sizeof(double);
+  if (cudaMalloc(&d, 2 * bi + bv + 16) != cudaSuccess) { cudaGetLastError(); return 1; }
+  double *dv = (double *)((char *)d + ((2 * bi + 15) / 16) * 16);
+  cudaMemcpyAsync(d, rows, bi, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(d + n, cols, bi, cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dv, vals, bv, cudaMemcpyHostToDevice, ctx->stream);
+  ctx->launches++;
+  add_entries_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(M.d, M.NR, M.isReal ? 1 : 2, n, d, d + n, dv);
+  cudaStreamSynchronize(ctx->stream);          // the host arrays are the caller's
+  cudaFree(d);
+  return cudaGetLastError() != cudaSuccess;
+}
+
 // Bloch-phase stamp of a neighbour-cell block (StampInNeighborBlock, AssembleBEMMatrix.cc:72-114):
 // M[rowOff+r, colOff+c] += BPF * B[r,c]  (+ conj(BPF) * B[c,r] when useSymmetry); both matrices complex, column-major.
 // 32x32 tiles: the transposed read of B goes through shared memory so that both global reads are coalesced.

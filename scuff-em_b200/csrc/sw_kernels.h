@@ -15,6 +15,7 @@ int run_ho(scuffcuda_context *ctx, const NearArgs &A, const int *hoIdx, int n, i
 // items[t] = 36*nearIndex + 18*highk + 9*swapped + 3*i + j  (host memory)
 int run_td_general(scuffcuda_context *ctx, const NearArgs &A, const TDTables &T, const int *items, int nItems);
 
+int launch_add_entries(scuffcuda_context *ctx, const Matrix &M, int n, const int *rows, const int *cols, const double *vals);
 void launch_stamp_neighbor(scuffcuda_context *ctx, const Matrix &M, int rowOff, int colOff, const Matrix &B, double pr, double pi, int useSymmetry);
 
 // Page-locked, device-mapped host memory that kernels write their per-item status words / counters into directly

@@ -67,6 +67,53 @@ static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omeg
   M->HostStale = true;
 }
 
+// AddSurfaceZetaContributionToBEMMatrix (SurfaceSurfaceInteractions.cc:339-421): a PEC surface with SURFACE_IMPEDANCE Zeta adds
+// -Zeta(w, X) * \int f_a . f_b to the entries of basis functions that share a panel; X = the edge centroid on the diagonal, else
+// the centroid of the (first) shared panel.  Only for the undisplaced diagonal block of a compact geometry.  Entries outside
+// the owned columns [ColBegin,ColEnd) (ColEnd > 0: column-block mode, upper triangle only) are left to their owner.
+static void AddSurfaceZetaContribution(RWGGeometry *G, int ns, cdouble Omega, HMatrix *M, int Offset, int ColBegin, int ColEnd)
+{ RWGSurface *S = G->Surfaces[ns];
+  if (!S->SurfaceZeta || !S->IsPEC) return;
+  const bool Partial = ColEnd > 0;
+  // panel -> edges with a basis function on it
+  std::vector<std::vector<int> > PanelEdges(S->NumPanels);
+  for (int ne = 0; ne < S->NumEdges; ne++)
+   { PanelEdges[S->Edges[ne]->iPPanel].push_back(ne);
+     if (S->Edges[ne]->iMPanel != -1) PanelEdges[S->Edges[ne]->iMPanel].push_back(ne); }
+  std::vector<int> Rows, Cols; std::vector<double> Vals;
+  CExpr *Z = (CExpr *)S->SurfaceZeta;
+  for (int neA = 0; neA < S->NumEdges; neA++)
+   { RWGEdge *EA = S->Edges[neA];
+     // candidates: the edges of the (<= 2) panels of neA, each once, neB >= neA
+     int Cand[8], nCand = 0;
+     for (int side = 0; side < 2; side++)
+      { int np = side == 0 ? EA->iPPanel : EA->iMPanel; if (np == -1) continue;
+        for (int neB : PanelEdges[np])
+         { if (neB < neA) continue;
+           bool seen = false; for (int q = 0; q < nCand; q++) if (Cand[q] == neB) seen = true;
+           if (!seen && nCand < 8) Cand[nCand++] = neB; } }
+     for (int q = 0; q < nCand; q++)
+      { const int neB = Cand[q]; RWGEdge *EB = S->Edges[neB];
+        const double Overlap = S->GetOverlap(neA, neB);
+        if (Overlap == 0.0) continue;
+        const double *X = EA->Centroid;
+        if (neA == neB) X = EA->Centroid;
+        else if (EA->iPPanel == EB->iPPanel || EA->iPPanel == EB->iMPanel) X = S->Panels[EA->iPPanel]->Centroid;
+        else if (EA->iMPanel != -1 && (EA->iMPanel == EB->iPPanel || EA->iMPanel == EB->iMPanel)) X = S->Panels[EA->iMPanel]->Centroid;
+        CExprSetVar(Z, "x", X[0]); CExprSetVar(Z, "y", X[1]); CExprSetVar(Z, "z", X[2]);
+        const cdouble V = -1.0 * CExprEval(Z, Omega * MatProp::FreqUnit) * Overlap;
+        const int r = Offset + neA, c = Offset + neB;
+        if (!Partial || (c >= ColBegin && c < ColEnd)) { Rows.push_back(r); Cols.push_back(c); Vals.push_back(real(V)); Vals.push_back(imag(V)); }
+        if (!Partial && neA != neB) { Rows.push_back(c); Cols.push_back(r); Vals.push_back(real(V)); Vals.push_back(imag(V)); }
+      }
+   }
+  scuffcuda_context *ctx = GetCudaContext();
+  M->EnsureDevice();
+  if (!Rows.empty() && scuffcuda_matrix_add_entries(ctx, M->DeviceHandle, (int)Rows.size(), Rows.data(), Cols.data(), Vals.data()))
+   ErrExit("%s", scuffcuda_last_error(ctx));
+  M->HostStale = true;
+}
+
 void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double *kBloch,
                                          HMatrix *M, HMatrix **GradM, int RowOffset, int ColOffset,
                                          void *Accelerator, bool TransposeAccelerator,
@@ -84,6 +131,9 @@ void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double
   for (int i = 0; i < 5; i++) LastPPICounts[i] = 0;
   if (LBasis == 0)
    { AssembleBlockOnDevice(this, nsa, nsb, Omega, M, RowOffset, ColOffset, nsa == nsb, false, 0, false, false);
+     if (nsa == nsb)
+      { if (RowOffset != ColOffset && Surfaces[nsa]->SurfaceZeta) ErrExit("%s:%i: internal error", __FILE__, __LINE__);
+        AddSurfaceZetaContribution(this, nsa, Omega, M, RowOffset, 0, 0); }
      M->SyncToHost();
      return; }
   AssembleBEMMatrixBlockPBC(nsa, nsb, Omega, kBloch, M, RowOffset, ColOffset);
@@ -176,7 +226,8 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
          if (Partial && ns == nsp && Mate[ns] != -1) nsA = nsB = Mate[ns];
          // the whole matrix is mirrored once at the end: tell the block not to mirror itself (all columns, no mirror)
          const int ce = (!Partial && MatrixIsSymmetric) ? 0x7fffffff : ColEnd;
-         AssembleBlockOnDevice(this, nsA, nsB, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false, ColBegin, ce); }
+         AssembleBlockOnDevice(this, nsA, nsB, Omega, M, BFIndexOffset[ns], BFIndexOffset[nsp], ns == nsp, false, 0, false, false, ColBegin, ce);
+         if (ns == nsp) AddSurfaceZetaContribution(this, nsA, Omega, M, BFIndexOffset[ns], ColBegin, Partial ? ColEnd : 0); }
       else
        AssembleBEMMatrixBlockPBC(ns, nsp, Omega, kBloch, M, BFIndexOffset[ns], BFIndexOffset[nsp]);
     }

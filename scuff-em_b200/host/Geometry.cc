@@ -233,7 +233,15 @@ static char *ParseOBJECTSURFACESection(RWGSurface *S, FILE *f, int *LineNum)
         else { ((GTrans *)S->OTGT)->Transform(NewGT); delete NewGT; }
       }
      else if (!strcasecmp(Tokens[0], "SURFACE_IMPEDANCE"))
-      return strdup("SURFACE_IMPEDANCE is not supported by the device assembly path");
+      { // dimensionless surface impedance Zeta(w,x,y,z): the rest of the line is the expression (RWGSurface.cc:188-210)
+        if (NumTokens < 2) return strdup("no argument specified for SURFACE_IMPEDANCE");
+        char *z = Line; while (*z && strchr(" \t\n", *z)) z++;
+        z += strlen("SURFACE_IMPEDANCE");
+        size_t n = strlen(z); while (n > 0 && (z[n - 1] == '\n' || z[n - 1] == '\r')) z[--n] = 0;
+        char *Err = 0;
+        S->SurfaceZeta = CExprCreate(z, &Err);
+        if (S->SurfaceZeta == 0 || Err) return vstrdup("invalid SURFACE_IMPEDANCE %s", z);
+      }
      else if (!strcasecmp(Tokens[0], "ENDOBJECT") || !strcasecmp(Tokens[0], "ENDSURFACE")) return 0;
      else return vstrdup("unknown keyword %s in %s section", Tokens[0], S->IsObject ? "OBJECT" : "SURFACE");
    }
@@ -245,7 +253,7 @@ static void InitSurfaceFields(RWGSurface *S)
   S->Vertices = 0; S->Panels = 0; S->Edges = 0; S->HalfRWGEdges = 0; S->IsClosed = 0;
   S->IsPEC = true; S->IsObject = true; S->Index = 0; S->RegionIndices[0] = 0; S->RegionIndices[1] = -1;
   S->RegionLabels[0] = S->RegionLabels[1] = 0; S->MaterialName = 0; S->MeshFileName = 0; S->MeshTag = -1;
-  S->Label = 0; S->ErrMsg = 0; S->tolVecClose = 0.0; S->TotalStraddlers = 0; S->OTGT = S->GT = 0;
+  S->Label = 0; S->ErrMsg = 0; S->tolVecClose = 0.0; S->TotalStraddlers = 0; S->OTGT = S->GT = 0; S->SurfaceZeta = 0;
 }
 
 RWGSurface::RWGSurface(FILE *f, const char *pLabel, int *LineNum, char *Keyword)
@@ -809,6 +817,29 @@ void RWGGeometry::SyncDeviceGeometry()
       ErrExit("%s", scuffcuda_last_error(ctx));
      DeviceDirty[ns] = 0;
    }
+}
+
+// \int f_alpha . f_beta over the panels the two RWG functions share (OPFT.cc:81-226, Overlaps[0]).  On a shared panel with
+// source vertices Q_a, Q_b: f_a . f_b = +-(l_a l_b / 4A^2) (X - Q_a).(X - Q_b); with X - Q_a = s L1 + t L2 over the panel
+// (L1 = Q_a' - Q_a, L2 = Q_a'' - Q_a') the integral is (l_a l_b / 2A) [ (L1.L1 + L1.L2)/4 + L1.DQ/3 + L2.L2/12 + L2.DQ/6 ].
+static double PanelOverlap(RWGSurface *S, RWGPanel *P, int iQa, int iQb, double Sign, double LL)
+{ const double *Qa = S->Vertices + 3 * P->VI[iQa], *Qa1 = S->Vertices + 3 * P->VI[(iQa + 1) % 3], *Qa2 = S->Vertices + 3 * P->VI[(iQa + 2) % 3];
+  const double *Qb = S->Vertices + 3 * P->VI[iQb];
+  double L1dL1 = 0, L1dL2 = 0, L1dDQ = 0, L2dL2 = 0, L2dDQ = 0;
+  for (int i = 0; i < 3; i++)
+   { const double l1 = Qa1[i] - Qa[i], l2 = Qa2[i] - Qa1[i], dq = Qa[i] - Qb[i];
+     L1dL1 += l1 * l1; L1dL2 += l1 * l2; L1dDQ += l1 * dq; L2dL2 += l2 * l2; L2dDQ += l2 * dq; }
+  return Sign * LL / (2.0 * P->Area) * ((L1dL1 + L1dL2) / 4.0 + L1dDQ / 3.0 + L2dL2 / 12.0 + L2dDQ / 6.0);
+}
+double RWGSurface::GetOverlap(int neAlpha, int neBeta)
+{ RWGEdge *Ea = Edges[neAlpha], *Eb = Edges[neBeta];
+  const double LL = Ea->Length * Eb->Length;
+  double O = 0.0;
+  if (Ea->iPPanel == Eb->iPPanel) O += PanelOverlap(this, Panels[Ea->iPPanel], Ea->PIndex, Eb->PIndex, 1.0, LL);
+  if (Ea->iPPanel == Eb->iMPanel) O += PanelOverlap(this, Panels[Ea->iPPanel], Ea->PIndex, Eb->MIndex, -1.0, LL);
+  if (Ea->iMPanel != -1 && Ea->iMPanel == Eb->iPPanel) O += PanelOverlap(this, Panels[Ea->iMPanel], Ea->MIndex, Eb->PIndex, -1.0, LL);
+  if (Ea->iMPanel != -1 && Ea->iMPanel == Eb->iMPanel) O += PanelOverlap(this, Panels[Ea->iMPanel], Ea->MIndex, Eb->MIndex, 1.0, LL);
+  return O;
 }
 
 }  // namespace scuff
