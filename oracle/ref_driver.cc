@@ -15,6 +15,8 @@
  *        periodic geometry: AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:349-565) MINUS its step 2 (outer cells through the
  *        GBar tables, :530-560, recomputed here with the reference's own CreateRegionGBA + GetSurfaceSurfaceInteractions):
  *        what remains is step 1, the Bloch-phased inner-cell blocks.  Also writes <out.bin>.full (the complete block).
+ *   ref_driver overlaps <geo> <ns> <out.txt>
+ *        RWGSurface::GetOverlap (OPFT.cc:219-226) for every edge pair neA<=neB with a non-zero overlap: "neA neB value"
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
  *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
@@ -169,6 +171,15 @@ int main(int argc, char **argv)
      FILE *f=fopen(fn,"wb"); if(!f) return 1; fwrite(Full->ZM,sizeof(cdouble),(size_t)NBFA*NBFB,f); fclose(f);
      for(size_t i=0;i<(size_t)NBFA*NBFB;i++) Full->ZM[i]-=Outer->ZM[i];
      f=fopen(Out,"wb"); if(!f) return 1; fwrite(Full->ZM,sizeof(cdouble),(size_t)NBFA*NBFB,f); fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"overlaps"))
+   { int ns=atoi(argv[3]); RWGSurface *S=G->Surfaces[ns];
+     FILE *f=fopen(argv[4],"w"); if(!f) return 1;
+     for(int a=0;a<S->NumEdges;a++)
+      for(int b=a;b<S->NumEdges;b++)
+       { double O=S->GetOverlap(a,b); if (O!=0.0) fprintf(f,"%i %i %.17g\n",a,b,O); }
+     fclose(f); return 0;
    }
 
   if(!strcmp(Cmd,"ppis"))

@@ -94,6 +94,13 @@ int scuffb200_assemble_block(void *g, void *m, int nsa, int nsb, double wr, doub
 int scuffb200_assemble_inner_cells(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off)
 { RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
   GUARD(G->AssembleInnerCellBlocks(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, row_off, col_off); M->SyncToHost(); return 0;, 1) }
+double scuffb200_get_overlap(void *g, int ns, int nea, int neb) { return ((RWGGeometry *)g)->Surfaces[ns]->GetOverlap(nea, neb); }
+int scuffb200_surface_zeta(void *g, int ns, double wr, double wi, const double *X, double *out)
+{ RWGSurface *S = ((RWGGeometry *)g)->Surfaces[ns];
+  if (!S->SurfaceZeta) return 1;
+  GUARD(CExpr *Z = (CExpr *)S->SurfaceZeta;
+        CExprSetVar(Z, "x", X[0]); CExprSetVar(Z, "y", X[1]); CExprSetVar(Z, "z", X[2]);
+        cdouble v = CExprEval(Z, cdouble(wr, wi) * MatProp::FreqUnit); out[0] = real(v); out[1] = imag(v); return 0;, 2) }
 int scuffb200_ppi_counts(void *g, unsigned long long *out) { for (int i = 0; i < 5; i++) out[i] = ((RWGGeometry *)g)->LastPPICounts[i]; return 0; }
 int scuffb200_lu_factorize(void *m) { GUARD(return ((HMatrix *)m)->LUFactorize();, 1) }
 int scuffb200_lu_solve(void *m, void *x) { GUARD(return ((HMatrix *)m)->LUSolve((HMatrix *)x);, 1) }

@@ -113,6 +113,9 @@ def host_lib():
         L.scuffb200_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]
         L.scuffb200_assemble_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
         L.scuffb200_matrix_symmetrize.argtypes = [C.c_void_p]
+        L.scuffb200_get_overlap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.scuffb200_get_overlap.restype = C.c_double
+        L.scuffb200_surface_zeta.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.scuffb200_assemble_inner_cells.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                                      C.POINTER(C.c_double), C.c_int, C.c_int]
         L.scuffb200_assemble_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
@@ -290,6 +293,20 @@ class RWGGeometry:
         _check(host_lib().scuffb200_assemble_inner_cells(self.ptr, M.ptr, nsa, nsb, float(np.real(Omega)),
                                                           float(np.imag(Omega)), kb, RowOffset, ColOffset))
         return M
+
+    def GetOverlap(self, ns, nea, neb):
+        """RWGSurface::GetOverlap: integral of f_a . f_b over the shared panels"""
+        return host_lib().scuffb200_get_overlap(self.ptr, ns, nea, neb)
+
+    def surface_zeta(self, ns, omega, X):
+        """value of the surface's SURFACE_IMPEDANCE expression at angular frequency omega (internal units) and point X, or None"""
+        out = (C.c_double * 2)()
+        x = (C.c_double * 3)(*[float(v) for v in X])
+        rc = host_lib().scuffb200_surface_zeta(self.ptr, ns, float(np.real(omega)), float(np.imag(omega)), x, out)
+        if rc == 1:
+            return None
+        _check(rc)
+        return complex(out[0], out[1])
 
     def ppi_counts(self):
         out = (C.c_ulonglong * 5)()

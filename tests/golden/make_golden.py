@@ -32,6 +32,9 @@ def main():
     os.makedirs(os.path.join(HERE, "geom"), exist_ok=True)
     for n in NAMES:
         run(["geom", n + ".scuffgeo", os.path.join(HERE, "geom", n + ".geom.txt")])
+    # ---- RWG overlap integrals (surface-impedance term) ----
+    for n in ("ZetaSphere_255", "OpenPlate_40"):
+        run(["overlaps", n + ".scuffgeo", "0", os.path.join(HERE, "overlaps_%s.txt" % n)])
     # ---- PPIs ----
     rng = np.random.default_rng(20261017)
     pairs = [(0, 0, 0, 0, 223, 0), (0, 0, 0, 0, 65, 0), (0, 0, 0, 0, 66, 0), (0, 0, 0, 0, 0, 0)]   # unit-test-PPIs.cc cases

@@ -86,3 +86,34 @@ def test_bad_inputs(ps, tmp_path):
     bad.write_text("FOO\n")
     with pytest.raises(ps.ScuffError):
         ps.RWGGeometry(str(bad))
+
+
+@pytest.mark.parametrize("name", ["ZetaSphere_255", "OpenPlate_40"])
+def test_rwg_overlaps_match_reference(ps, name):
+    """RWGSurface::GetOverlap (OPFT.cc:81-226, the basis-function overlap of the surface-impedance term) against the
+    reference's values for every overlapping edge pair (tests/golden/overlaps_*.txt, written by ref_driver overlaps)."""
+    G = ps.RWGGeometry(os.path.join(GEODIR, name + ".scuffgeo"))
+    rows = [l.split() for l in open(os.path.join(GOLDEN, "overlaps_%s.txt" % name))]
+    NE = G.surface(0)["NE"]
+    ref = {(int(a), int(b)): float(v) for a, b, v in rows}
+    assert len(ref) >= NE                                      # at least the diagonal
+    for (a, b), v in ref.items():
+        mine = G.GetOverlap(0, a, b)
+        assert abs(mine - v) <= 1e-14 * max(1.0, abs(v)) and abs(G.GetOverlap(0, b, a) - v) <= 1e-14 * max(1.0, abs(v))
+    # edge pairs without a common panel do not overlap
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        a, b = sorted(int(x) for x in rng.integers(0, NE, 2))
+        if (a, b) not in ref:
+            assert G.GetOverlap(0, a, b) == 0.0
+
+
+def test_surface_impedance_expression(ps):
+    """SURFACE_IMPEDANCE Zeta(w,x,y,z) (RWGSurface.cc:188-210): parsed from the rest of the line, evaluated with
+    w = Omega * MatProp::FreqUnit as AddSurfaceZetaContributionToBEMMatrix does (SurfaceSurfaceInteractions.cc:400-408)."""
+    G = ps.RWGGeometry(os.path.join(GEODIR, "ZetaSphere_255.scuffgeo"))
+    X, omega = (0.3, -0.2, 0.5), 0.7
+    w = omega * 2.99792458e14
+    expect = 0.02 + 0.3j + 0.05 * X[0] * X[1] + (w / 2.99792458e14) * (0.01 - 0.02j * X[2])
+    assert abs(G.surface_zeta(0, omega, X) - expect) <= 1e-15
+    assert ps.RWGGeometry(os.path.join(GEODIR, "PECSphere_255.scuffgeo")).surface_zeta(0, omega, X) is None
