@@ -230,3 +230,42 @@ def far_matrix_single_surface(S, omega, eps_out=1.0, mu_out=1.0, eps_in=None, mu
         M2, _ = stamp_block(S, S, omega, eps_in, mu_in, +1.0, True)
         M = M + M2
     return M, mask
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Bookkeeping steps around the integrals (restated for the checker; the product implements them in
+# scuff-em_b200/host/Assemble.cc and csrc/matrix_kernels.cu)
+# ------------------------------------------------------------------------------------------------------------------
+def rwg_overlap(S, nea, neb):
+    """RWGSurface::GetOverlap, Overlaps[0] = int f_a . f_b (OPFT.cc:81-226): sum over the panels the two basis functions
+    share of  sign * l_a l_b / (2A) * [ (L1.L1 + L1.L2)/4 + L1.DQ/3 + L2.L2/12 + L2.DQ/6 ]  with L1 = Qa' - Qa,
+    L2 = Qa'' - Qa', DQ = Qa - Qb (Qa, Qb: the source/sink vertices of the two functions on that panel)."""
+    Ea, Eb = S["ET"][nea], S["ET"][neb]
+    LL = S["EL"][nea] * S["EL"][neb]
+
+    def panel_term(npanel, iqa, iqb, sign):
+        vi = S["PVI"][npanel]
+        Qa, Qa1, Qa2, Qb = S["V"][vi[iqa]], S["V"][vi[(iqa + 1) % 3]], S["V"][vi[(iqa + 2) % 3]], S["V"][vi[iqb]]
+        L1, L2, DQ = Qa1 - Qa, Qa2 - Qa1, Qa - Qb
+        bullet = (L1 @ L1 + L1 @ L2) / 4.0 + (L1 @ DQ) / 3.0 + (L2 @ L2) / 12.0 + (L2 @ DQ) / 6.0
+        return sign * LL / (2.0 * S["PA"][npanel]) * bullet
+
+    # ET columns: iV1 iV2 iQP iQM iPPanel iMPanel PIndex MIndex
+    O = 0.0
+    if Ea[4] == Eb[4]:
+        O += panel_term(Ea[4], Ea[6], Eb[6], +1.0)
+    if Ea[4] == Eb[5]:
+        O += panel_term(Ea[4], Ea[6], Eb[7], -1.0)
+    if Ea[5] != -1 and Ea[5] == Eb[4]:
+        O += panel_term(Ea[5], Ea[7], Eb[6], -1.0)
+    if Ea[5] != -1 and Ea[5] == Eb[5]:
+        O += panel_term(Ea[5], Ea[7], Eb[7], +1.0)
+    return O
+
+
+def stamp_in_neighbor_block(M, B, row_offset, col_offset, L, kbloch, use_symmetry):
+    """StampInNeighborBlock (AssembleBEMMatrix.cc:72-114): M[block] += BPF * B (+ conj(BPF) * B^T), BPF = exp(i kBloch.L)"""
+    bpf = np.exp(1j * (kbloch[0] * L[0] + kbloch[1] * L[1]))
+    nr, nc = B.shape
+    M[row_offset:row_offset + nr, col_offset:col_offset + nc] += bpf * B + (np.conj(bpf) * B.T if use_symmetry else 0.0)
+    return M

@@ -77,3 +77,30 @@ def test_far_matrix_entries_vs_reference(oracle, name, omega, eps_in):
     assert sel.sum() > 1000
     got, want = M[r, c][sel], val[sel]
     assert np.linalg.norm(got - want) <= 1e-12 * np.linalg.norm(want)
+
+
+@pytest.mark.parametrize("geom,golden", [("PECSphere_255", "ZetaSphere_255"), ("OpenPlate_40", "OpenPlate_40")])
+def test_rwg_overlap_vs_reference_golden(oracle, geom, golden):
+    """the overlap integrals of the surface-impedance term against the reference's RWGSurface::GetOverlap values"""
+    S = surf(oracle, geom)[0]
+    n = 0
+    for l in open(os.path.join(GOLDEN, "overlaps_%s.txt" % golden)):
+        a, b, v = l.split()
+        got = oracle.rwg_overlap(S, int(a), int(b))
+        assert abs(got - float(v)) <= 1e-14 * max(1.0, abs(float(v))), (a, b, got, v)
+        n += 1
+    assert n >= S["NE"]
+
+
+def test_stamp_in_neighbor_block_properties(oracle):
+    """Bloch-phase stamping: kBloch = 0 adds B + B^T; the +L and -L cells of a diagonal block are each other's
+    conjugate-phase transposes, so the stamped block is Hermitian-symmetric in the phase (B real-symmetric => result real)."""
+    rng = np.random.default_rng(5)
+    B = rng.standard_normal((6, 6)) + 1j * rng.standard_normal((6, 6))
+    M = oracle.stamp_in_neighbor_block(np.zeros((8, 8), complex), B, 1, 2, (1.0, 0.0), (0.0, 0.0), True)
+    assert np.allclose(M[1:7, 2:8], B + B.T) and np.all(M[0] == 0) and np.all(M[:, :2] == 0)
+    Br = rng.standard_normal((6, 6)); Br = Br + Br.T
+    M = oracle.stamp_in_neighbor_block(np.zeros((6, 6), complex), Br, 0, 0, (1.0, 0.5), (0.7, -0.3), True)
+    assert np.allclose(M.imag, 0.0) and np.allclose(M.real, 2 * np.cos(0.7 - 0.15) * Br)
+    M1 = oracle.stamp_in_neighbor_block(np.zeros((6, 6), complex), B, 0, 0, (1.0, 0.0), (0.4, 0.0), False)
+    assert np.allclose(M1, np.exp(0.4j) * B)
