@@ -17,6 +17,10 @@
  *        what remains is step 1, the Bloch-phased inner-cell blocks.  Also writes <out.bin>.full (the complete block).
  *   ref_driver overlaps <geo> <ns> <out.txt>
  *        RWGSurface::GetOverlap (OPFT.cc:219-226) for every edge pair neA<=neB with a non-zero overlap: "neA neB value"
+ *   ref_driver gbar <kRe> <kIm> <kBx> <kBy> <LDim> <L1x> <L1y> <L2x> <L2y> <exclude> <npts> <seed> <out.bin>
+ *        GBarVDEwald (GBarVDEwald.cc:931-996, E=-1: automatic Ewald parameter) at npts seeded random points R in
+ *        [-0.5,0.5]^2 x [-1,1]; record = R[3], then GBarVD[8] (value, d/dx, d/dy, d/dz, d2/dxdy, d2/dxdz, d2/dydz, d3/dxdydz)
+ *        as (re,im) pairs: 19 doubles.  No geometry file is read.
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
  *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
@@ -31,6 +35,7 @@
 #include <libhrutil.h>
 #include "libscuff.h"
 #include "libscuffInternals.h"
+#include "GBarAccelerator.h"
 using namespace scuff;
 
 static double Now()
@@ -71,6 +76,19 @@ int main(int argc, char **argv)
 { if(argc<3) { fprintf(stderr,"usage: see header\n"); return 2; }
   const char *Cmd=argv[1];
   SetLogFileName("/dev/null");
+  if(!strcmp(argv[1],"gbar"))
+   { if(argc<15) { fprintf(stderr,"gbar: 13 arguments\n"); return 2; }
+     cdouble k(atof(argv[2]),atof(argv[3])); double kBloch[2]={atof(argv[4]),atof(argv[5])}; int LDim=atoi(argv[6]);
+     double LBV[2][3]={{atof(argv[7]),atof(argv[8]),0.0},{atof(argv[9]),atof(argv[10]),0.0}};
+     bool Exclude=atoi(argv[11])!=0; int npts=atoi(argv[12]); srand48(atol(argv[13]));
+     FILE *f=fopen(argv[14],"wb"); if(!f) return 1;
+     for(int n=0;n<npts;n++)
+      { double R[3]={drand48()-0.5, LDim==2 ? drand48()-0.5 : 0.6*(drand48()-0.5), 2.0*drand48()-1.0};
+        cdouble GBarVD[8];
+        GBarVDEwald(R,k,kBloch,LBV,LDim,-1.0,Exclude,GBarVD);
+        fwrite(R,sizeof(double),3,f); fwrite(GBarVD,sizeof(cdouble),8,f); }
+     fclose(f); return 0;
+   }
   RWGGeometry *G=new RWGGeometry(argv[2]);
 
   if(!strcmp(Cmd,"geom")) return DumpGeom(G,argv[3]);

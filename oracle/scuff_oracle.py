@@ -269,3 +269,28 @@ def stamp_in_neighbor_block(M, B, row_offset, col_offset, L, kbloch, use_symmetr
     nr, nc = B.shape
     M[row_offset:row_offset + nr, col_offset:col_offset + nc] += bpf * B + (np.conj(bpf) * B.T if use_symmetry else 0.0)
     return M
+
+
+def gbar_direct_sum(R, k, kbloch, lbv, exclude_inner=False, ncells=40):
+    """Bloch-periodic scalar Green's function by brute-force lattice summation,
+         GBar(R) = sum_L exp(i kBloch.L) exp(ik|R-L|) / (4 pi |R-L|),   L = n1 L1 (+ n2 L2),
+    the quantity GBarVDEwald (GBarVDEwald.cc:931-996) evaluates by Ewald's method (sign convention R-L: the one that matches the
+    reference's values to 1e-15 on rectangular lattices; on oblique lattices the reference's truncated Ewald sums are themselves
+    ~1 % off this sum, tests/golden/gbar_golden.json keeps such a case flagged).  Only usable as a checker where the sum converges absolutely, i.e.
+    Im k > 0 (exp(-kappa |L|) decay).  exclude_inner drops the cells |n1|,|n2| <= 1 (`ExcludeInnerCells`, the part the
+    periodic assembly integrates directly, AssembleBEMMatrix.cc:465-519).  Returns (GBar, grad GBar[3])."""
+    R = np.asarray(R, float); k = complex(k)
+    lbv = [np.asarray(l, float) for l in lbv]
+    rng = range(-ncells, ncells + 1)
+    G = 0.0j; dG = np.zeros(3, complex)
+    for n1 in rng:
+        for n2 in (rng if len(lbv) == 2 else (0,)):
+            if exclude_inner and abs(n1) <= 1 and abs(n2) <= 1:
+                continue
+            L = n1 * lbv[0] + (n2 * lbv[1] if len(lbv) == 2 else 0.0)
+            X = R - np.array([L[0], L[1], 0.0])
+            r = np.sqrt(X @ X)
+            phi = np.exp(1j * (kbloch[0] * L[0] + kbloch[1] * L[1])) * np.exp(1j * k * r) / (4.0 * np.pi * r)
+            G += phi
+            dG += phi * (1j * k - 1.0 / r) * X / r
+    return G, dG
