@@ -239,9 +239,9 @@ class RWGGeometry
 
    /* internal */
    void InitPBCData();
-   void AssembleBEMMatrixBlockPBC(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset, int ColOffset);
+   void AssembleBEMMatrixBlockPBC(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset, int ColOffset, void *Accelerator = 0);
    /* step 1 of the periodic branch (AssembleBEMMatrix.cc:465-519): inner-cell blocks with Bloch phases, result in HBM */
-   void AssembleInnerCellBlocks(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset=0, int ColOffset=0);
+   void AssembleInnerCellBlocks(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset=0, int ColOffset=0, void *Accelerator = 0);
    std::vector<char> DeviceDirty;
    unsigned long long DeviceId;
    void AddRegion(const char *RegionLabel, const char *MaterialName, int LineNum);

@@ -66,7 +66,8 @@ int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int handle, int dst_row,
 int scuffcuda_matrix_add_entries(scuffcuda_context *ctx, int handle, int n, const int *rows, const int *cols, const double *vals);
 /* StampInNeighborBlock (AssembleBEMMatrix.cc:72-114), the Bloch-phase accumulation of one neighbour-cell block of a
  * periodic geometry: M[row_off+r, col_off+c] += BPF*B[r,c] (+ conj(BPF)*B[c,r] if use_symmetry), BPF = phase[0]+i*phase[1]
- * = exp(i kBloch.L); `handle_B` is a complex NBFA x NBFB matrix filled by scuffcuda_assemble_block with use_displacement */
+ * = exp(i kBloch.L); `handle_B` is an NBFA x NBFB matrix (complex, or real: the
+ * LHM_REAL cache blocks of CreateABMBAccelerator) filled by scuffcuda_assemble_block with use_displacement          */
 int scuffcuda_matrix_stamp_neighbor_block(scuffcuda_context *ctx, int handle, int row_off, int col_off,
                                           int handle_B, const double phase[2], int use_symmetry);
 /* upper -> lower triangle copy of the square sub-block at (offset,offset) of size n
@@ -115,13 +116,39 @@ typedef struct scuffcuda_ssi_args {
                              * only and are NOT mirrored when a range is given (the caller mirrors the
                              * gathered matrix with scuffcuda_matrix_symmetrize); without `accumulate`
                              * only the owned columns of the block are cleared                  */
-  int    reserved[5];
+  int    gba_a, gba_b;      /* Args->GBA1 / GBA2: handles from scuffcuda_gbar_create.  Non-zero = the outer-cell step of a
+                             * periodic geometry (AssembleBEMMatrix.cc:526-557): every panel pair of the block is
+                             * integrated with the 6x6 rule and the periodic Green's function of the region
+                             * (PanelPanelInteractions.cc:124-153,420-424) instead of exp(ikr)/4 pi r; needs symmetric=0,
+                             * no displacement; a region without a table must be passed with eps = 0 (OmitRegion)   */
+  int    reserved[3];
 } scuffcuda_ssi_args;
 
 /* GetSurfaceSurfaceInteractions(Args) on the device: adds the (nsa,nsb) block into the
  * device matrix `handle` at (row_offset,col_offset).                                   */
 int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb,
                              const scuffcuda_ssi_args *args, int handle);
+
+/* ---- periodic Green's function (libs/libscuff/GBarAccelerator.h:45-92, GBarVDEwald.cc:931-996) ------------------ */
+/* CreateGBarAccelerator(LBasis, RhoMin, RhoMax, k, kBloch, RelTol, ExcludeInnerCells) (GBarAccelerator.cc:339-547) on the
+ * device: Ewald sums, grid-spacing probes, table fill and tricubic fit are CUDA kernels; the table stays in HBM.
+ *   k[2] wavenumber in the region (re,im); lbv = {L1x, L1y, L2x, L2y}; ldim must be 2 (1-D lattices: error)
+ *   rho_min > rho_max or force_full_ewald: no table, every lookup is a full Ewald sum (SCUFF_EWALD_FULL, :384-396)
+ *   nmax_grid > 0 caps the grid dimensions (SCUFF_GBAR_NMAX, :532-537)                                                 */
+int scuffcuda_gbar_create(scuffcuda_context *ctx, const double k[2], const double kbloch[2], const double lbv[4], int ldim,
+                          double rho_min, double rho_max, double rel_tol, int exclude_inner_cells, int force_full_ewald,
+                          int nmax_grid, int *handle);
+int scuffcuda_gbar_destroy(scuffcuda_context *ctx, int handle);
+/* table decisions: grid dimensions n[3] (0 if no table), origin xmin[3], spacing dx[3], LMax, full-Ewald flag */
+int scuffcuda_gbar_info(scuffcuda_context *ctx, int handle, int n[3], double xmin[3], double dx[3], double *lmax, int *full_ewald);
+/* tricubic coefficients, 128 doubles per cell (Interp3D::CTable layout, libs/libMDInterp/Interp3D.cc:63-69), host buffer */
+int scuffcuda_gbar_get_table(scuffcuda_context *ctx, int handle, double *coeffs);
+/* GetGBar(R, GBA, dGBar) (GBarAccelerator.cc:983-1005) at npts points R[3*npts] (host): out8 = G, dG/dx, dG/dy, dG/dz as (re,im) */
+int scuffcuda_gbar_eval(scuffcuda_context *ctx, int handle, int npts, const double *R, double *out8);
+/* GBarVDEwald(R, k, kBloch, LBV, LDim, E=-1, ExcludeInnerCells, GBarVD) (GBarVDEwald.cc:931-996) at npts points:
+ * out16 = value, d/dx, d/dy, d/dz, d2/dxdy, d2/dxdz, d2/dydz, d3/dxdydz as (re,im)                                      */
+int scuffcuda_gbar_ewald(scuffcuda_context *ctx, const double k[2], const double kbloch[2], const double lbv[4], int ldim,
+                         int exclude_inner_cells, int npts, const double *R, double *out16);
 
 /* PPI algorithm counters of the last assemble_block call, same order as the reference's
  * log line (SurfaceSurfaceInteractions.cc:550-558; libscuffInternals.h PPIALG_*):

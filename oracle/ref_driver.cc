@@ -21,6 +21,12 @@
  *        GBarVDEwald (GBarVDEwald.cc:931-996, E=-1: automatic Ewald parameter) at npts seeded random points R in
  *        [-0.5,0.5]^2 x [-1,1]; record = R[3], then GBarVD[8] (value, d/dx, d/dy, d/dz, d2/dxdy, d2/dxdz, d2/dydz, d3/dxdydz)
  *        as (re,im) pairs: 19 doubles.  No geometry file is read.
+ *   ref_driver gbarpts <kRe> <kIm> <kBx> <kBy> <L1x> <L1y> <L2x> <L2y> <exclude> <pts.bin> <out.bin>
+ *        GBarVDEwald at the points of pts.bin (raw doubles x,y,z), 2-D lattice; out: 16 doubles per point
+ *   ref_driver gba <geo> <wRe> <wIm> <kx> <ky> <nr> <nsa> <nsb> <pts.bin> <out.bin>
+ *        CreateRegionGBA(nr, Omega, kBloch, nsa, nsb) (GBarAccelerator.cc:1205-1221): prints the table decisions as JSON
+ *        {null | RhoMin, RhoMax, LMax, full, N1, N2, N3, X1Min, DX1, ...}, writes <out.bin>.ctable (the tricubic coefficients)
+ *        and GetGBar (value + gradient, 8 doubles per point) at the points of pts.bin into <out.bin>
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
  *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
@@ -36,6 +42,7 @@
 #include "libscuff.h"
 #include "libscuffInternals.h"
 #include "GBarAccelerator.h"
+#include <libMDInterp.h>
 using namespace scuff;
 
 static double Now()
@@ -88,6 +95,19 @@ int main(int argc, char **argv)
         GBarVDEwald(R,k,kBloch,LBV,LDim,-1.0,Exclude,GBarVD);
         fwrite(R,sizeof(double),3,f); fwrite(GBarVD,sizeof(cdouble),8,f); }
      fclose(f); return 0;
+   }
+  if(!strcmp(argv[1],"gbarpts"))
+   { if(argc<13) { fprintf(stderr,"gbarpts: 11 arguments\n"); return 2; }
+     cdouble k(atof(argv[2]),atof(argv[3])); double kBloch[2]={atof(argv[4]),atof(argv[5])};
+     double LBV[2][3]={{atof(argv[6]),atof(argv[7]),0.0},{atof(argv[8]),atof(argv[9]),0.0}};
+     bool Exclude=atoi(argv[10])!=0;
+     FILE *fi=fopen(argv[11],"rb"), *fo=fopen(argv[12],"wb"); if(!fi||!fo) return 1;
+     double R[3];
+     while(fread(R,sizeof(double),3,fi)==3)
+      { cdouble GBarVD[8];
+        GBarVDEwald(R,k,kBloch,LBV,2,-1.0,Exclude,GBarVD);
+        fwrite(GBarVD,sizeof(cdouble),8,fo); }
+     fclose(fi); fclose(fo); return 0;
    }
   RWGGeometry *G=new RWGGeometry(argv[2]);
 
@@ -189,6 +209,32 @@ int main(int argc, char **argv)
      FILE *f=fopen(fn,"wb"); if(!f) return 1; fwrite(Full->ZM,sizeof(cdouble),(size_t)NBFA*NBFB,f); fclose(f);
      for(size_t i=0;i<(size_t)NBFA*NBFB;i++) Full->ZM[i]-=Outer->ZM[i];
      f=fopen(Out,"wb"); if(!f) return 1; fwrite(Full->ZM,sizeof(cdouble),(size_t)NBFA*NBFB,f); fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"gba"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); double kBloch[2]={atof(argv[5]),atof(argv[6])};
+     int nr=atoi(argv[7]), nsa=atoi(argv[8]), nsb=atoi(argv[9]); const char *Pts=argv[10], *Out=argv[11];
+     G->UpdateCachedEpsMuValues(Omega);
+     GBarAccelerator *GBA=G->CreateRegionGBA(nr,Omega,kBloch,nsa,nsb);
+     if(!GBA) { printf("{\"null\": 1}\n"); return 0; }
+     printf("{\"null\": 0, \"kRe\": %.17g, \"kIm\": %.17g, \"RhoMin\": %.17g, \"RhoMax\": %.17g, \"LMax\": %.17g, \"full\": %i, \"LDim\": %i",
+            real(GBA->k),imag(GBA->k),GBA->RhoMin,GBA->RhoMax,GBA->LMax,(int)GBA->ForceFullEwald,GBA->LDim);
+     if(GBA->I3D)
+      { Interp3D *I=GBA->I3D;
+        printf(", \"N\": [%i, %i, %i], \"XMin\": [%.17g, %.17g, %.17g], \"DX\": [%.17g, %.17g, %.17g]",
+               I->N1,I->N2,I->N3,I->X1Min,I->X2Min,I->X3Min,I->DX1,I->DX2,I->DX3);
+        char fn[2000]; snprintf(fn,2000,"%s.ctable",Out);
+        FILE *f=fopen(fn,"wb"); if(!f) return 1;
+        fwrite(I->CTable,sizeof(double),(size_t)(I->N1-1)*(I->N2-1)*(I->N3-1)*2*64,f); fclose(f);
+      }
+     printf("}\n");
+     FILE *fi=fopen(Pts,"rb"), *fo=fopen(Out,"wb"); if(!fi||!fo) return 1;
+     double R[3];
+     while(fread(R,sizeof(double),3,fi)==3)
+      { cdouble GdG[4];
+        GdG[0]=GetGBar(R,GBA,GdG+1,0,false);
+        fwrite(GdG,sizeof(cdouble),4,fo); }
+     fclose(fi); fclose(fo); return 0;
    }
 
   if(!strcmp(Cmd,"overlaps"))

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include "kernels.h"
 #include "sw_kernels.h"
+#include "pbc.h"
 
 using namespace scuffcuda;
 typedef std::complex<double> cdouble;
@@ -57,6 +58,7 @@ void scuffcuda_destroy(scuffcuda_context *ctx)
   for (auto &s : ctx->surfaces) if (s.dpanels) cudaFree(s.dpanels);
   for (auto &m : ctx->matrices) { if (m.second.d) cudaFree(m.second.d); if (m.second.ipiv) cudaFree(m.second.ipiv); }
   for (auto &p : ctx->plans) if (p.dnear) cudaFree(p.dnear);
+  for (auto &t : ctx->gbarTables) if (t.second.dC) cudaFree(t.second.dC);
   if (ctx->fippi.drec) cudaFree(ctx->fippi.drec);
   if (ctx->dcounters) cudaFree(ctx->dcounters);
   if (ctx->dscratch) cudaFree(ctx->dscratch);
@@ -182,7 +184,7 @@ int scuffcuda_matrix_add_entries(scuffcuda_context *ctx, int h, int n, const int
 int scuffcuda_matrix_stamp_neighbor_block(scuffcuda_context *ctx, int h, int row_off, int col_off, int hB, const double phase[2], int use_symmetry)
 { Matrix *M = get_matrix(ctx, h), *B = get_matrix(ctx, hB);
   if (!M || !B) return fail(ctx, "invalid matrix handle %d", !M ? h : hB);
-  if (M->isReal || B->isReal) return fail(ctx, "matrix_stamp_neighbor_block: both matrices must be complex");
+  if (M->isReal) return fail(ctx, "matrix_stamp_neighbor_block: the target matrix must be complex");
   if (row_off < 0 || col_off < 0 || row_off + B->NR > M->NR || col_off + B->NC > M->NC) return fail(ctx, "matrix_stamp_neighbor_block: block out of range");
   if (use_symmetry && B->NR != B->NC) return fail(ctx, "matrix_stamp_neighbor_block: use_symmetry needs a square block");
   CK(cudaSetDevice(ctx->device));
@@ -348,6 +350,8 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   if (a->row_offset < 0 || a->col_offset < 0 || a->row_offset + NBFA > M->NR || a->col_offset + NBFB > M->NC)
    return fail(ctx, "assemble_block: block (%d+%d, %d+%d) exceeds matrix %dx%d", a->row_offset, NBFA, a->col_offset, NBFB, M->NR, M->NC);
   if (a->symmetric && nsa != nsb) return fail(ctx, "assemble_block: symmetric requires nsa==nsb");
+  if ((a->gba_a || a->gba_b) && (a->symmetric || a->use_displacement || a->col_end > 0 || M->isReal))
+   return fail(ctx, "assemble_block: the periodic outer-cell step needs a complex matrix, symmetric = 0, no displacement and no column range");
   CK(cudaSetDevice(ctx->device));
 
   cudaEvent_t ev[7]; for (int i = 0; i < 7; i++) CK(cudaEventCreate(&ev[i]));
@@ -398,6 +402,19 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
         return fail(ctx, "assemble_block: |Re k| * geometry extent = %g exceeds the supported range %g", std::fabs(real(k)) * ext, SCUFF_MAX_KR);
      }
 
+     if (a->gba_a || a->gba_b)
+      { // outer-cell step of a periodic geometry: all panel pairs through the periodic Green's function of this region
+        GBarTable *T = find_gbar(ctx, region == 0 ? a->gba_a : a->gba_b);
+        if (!T) return fail(ctx, "assemble_block: region %d has material but no periodic Green's function table (pass eps = 0 to omit it)", region);
+        // (the table's k is Omega*sqrt(Eps*Mu) as CreateRegionGBA forms it, GBarAccelerator.cc:1047; prefactors use kA of
+        //  SurfaceSurfaceInteractions.cc:165 — the caller passes both, they are not cross-checked, as in the reference)
+        CK(cudaEventRecord(ev[1], sMain));
+        if (run_pbc_outer(ctx, Sa, Sb, *T, K, SP, ctx->dcounters)) return 1;
+        CK(cudaEventRecord(ev[2], sMain));
+        CK(cudaEventSynchronize(ev[2]));
+        float t; cudaEventElapsedTime(&t, ev[1], ev[2]); farMs += t;
+        continue; }
+
      FarArgs F;
      F.pa = Sa.dpanels; F.NPa = Sa.NP; F.pb = Sb.dpanels; F.NPb = Sb.NP; F.TA = 32;
      F.symmetric = SP.symmetric; F.useDisp = a->use_displacement ? 1 : 0;
@@ -439,6 +456,44 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   ctx->pairCounts[0] = hc[5]; ctx->pairCounts[1] = hc[6];
   for (int i = 0; i < 7; i++) cudaEventDestroy(ev[i]);
   return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// periodic Green's function tables
+// ------------------------------------------------------------------------------------------
+static int make_gbar_params(scuffcuda_context *ctx, const double k[2], const double kb[2], const double lbv[4], int ldim, int excl, GBarParams &P)
+{ if (!k || !kb || !lbv) return fail(ctx, "gbar: null argument");
+  if (ldim != 2) return fail(ctx, "periodic Green's function: only 2-D lattices are supported on the device path (got LDim = %d)", ldim);
+  P.k = mk(k[0], k[1]); P.kBloch[0] = kb[0]; P.kBloch[1] = kb[1];
+  P.LBV[0][0] = lbv[0]; P.LBV[0][1] = lbv[1]; P.LBV[1][0] = lbv[2]; P.LBV[1][1] = lbv[3];
+  P.LDim = ldim; P.excludeInner = excl ? 1 : 0;
+  if (lbv[0] * lbv[3] - lbv[1] * lbv[2] == 0.0) return fail(ctx, "lattice has empty unit cell");
+  return 0;
+}
+int scuffcuda_gbar_create(scuffcuda_context *ctx, const double k[2], const double kb[2], const double lbv[4], int ldim,
+                          double rho_min, double rho_max, double rel_tol, int excl, int force_full, int nmax_grid, int *handle)
+{ GBarParams P; if (make_gbar_params(ctx, k, kb, lbv, ldim, excl, P)) return 1;
+  if (!(rel_tol > 0.0)) return fail(ctx, "gbar_create: invalid interpolation tolerance %g", rel_tol);
+  CK(cudaSetDevice(ctx->device));
+  return gbar_create(ctx, P, rho_min, rho_max, rel_tol, force_full, nmax_grid, handle);
+}
+int scuffcuda_gbar_destroy(scuffcuda_context *ctx, int handle)
+{ CK(cudaSetDevice(ctx->device)); return gbar_destroy(ctx, handle); }
+int scuffcuda_gbar_info(scuffcuda_context *ctx, int handle, int n[3], double xmin[3], double dx[3], double *lmax, int *full)
+{ GBarTable *T = find_gbar(ctx, handle); if (!T) return fail(ctx, "invalid periodic Green's function table handle %d", handle);
+  for (int m = 0; m < 3; m++) { n[m] = T->forceFull ? 0 : T->N[m]; xmin[m] = T->XMin[m]; dx[m] = T->DX[m]; }
+  if (lmax) *lmax = T->LMax; if (full) *full = T->forceFull;
+  return 0;
+}
+int scuffcuda_gbar_get_table(scuffcuda_context *ctx, int handle, double *coeffs)
+{ CK(cudaSetDevice(ctx->device)); return gbar_download_table(ctx, handle, coeffs); }
+int scuffcuda_gbar_eval(scuffcuda_context *ctx, int handle, int npts, const double *R, double *out8)
+{ CK(cudaSetDevice(ctx->device)); return gbar_eval_points(ctx, handle, npts, R, out8); }
+int scuffcuda_gbar_ewald(scuffcuda_context *ctx, const double k[2], const double kb[2], const double lbv[4], int ldim, int excl,
+                         int npts, const double *R, double *out16)
+{ GBarParams P; if (make_gbar_params(ctx, k, kb, lbv, ldim, excl, P)) return 1;
+  CK(cudaSetDevice(ctx->device));
+  return gbar_ewald_points(ctx, P, npts, R, out16);
 }
 
 int scuffcuda_get_ppi_counts(scuffcuda_context *ctx, unsigned long long c[5])

@@ -9,6 +9,7 @@
 #include <stdint.h>
 #include "../../include/libscuff_cuda.h"
 #include "ppi_math.cuh"
+#include "gbar_params.h"
 
 namespace scuffcuda {
 
@@ -92,6 +93,17 @@ struct FIPPITable
   double *drec = nullptr; long dcap = 0; long dcount = 0;  // device copy (resident across the sweep)
 };
 
+// periodic Green's function table (GBarAccelerator, libs/libscuff/GBarAccelerator.h:45-61), resident in HBM
+struct GBarTable
+{ GBarParams P;
+  double RhoMin = 0, RhoMax = 0, LMax = 0;
+  int forceFull = 0;
+  int N[3] = { 0, 0, 0 };
+  double XMin[3] = { 0, 0, 0 }, DX[3] = { 0, 0, 0 };
+  double minDelta[3] = { 0, 0, 0 };   // the probed optimal spacings (diagnostics)
+  double *dC = nullptr;               // 128 doubles per cell
+};
+
 }  // namespace scuffcuda
 
 struct scuffcuda_context
@@ -103,6 +115,7 @@ struct scuffcuda_context
   std::map<int, scuffcuda::Matrix> matrices; int nextHandle = 1;
   std::vector<scuffcuda::Plan> plans;
   scuffcuda::FIPPITable fippi;
+  std::map<int, scuffcuda::GBarTable> gbarTables;   // handles share nextHandle with the matrices
   unsigned long long counts[5] = {0, 0, 0, 0, 0};
   unsigned long long pairCounts[2] = {0, 0};  // far / near panel pairs of the last assemble_block call
   unsigned long long launches = 0;            // kernels launched by this context since creation

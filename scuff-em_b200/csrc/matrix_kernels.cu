@@ -50,7 +50,8 @@ int launch_add_entries(scuffcuda_context *ctx, const Matrix &M, int n, const int
 // Bloch-phase stamp of a neighbour-cell block (StampInNeighborBlock, AssembleBEMMatrix.cc:72-114):
 // M[rowOff+r, colOff+c] += BPF * B[r,c]  (+ conj(BPF) * B[c,r] when useSymmetry); both matrices complex, column-major.
 // 32x32 tiles: the transposed read of B goes through shared memory so that both global reads are coalesced.
-__global__ void stamp_neighbor_kernel(double *M, long ldM, int rowOff, int colOff, const double *B, long ldB, int nr, int nc,
+// bw = 2: B complex; bw = 1: B real (the LHM_REAL cache blocks of CreateABMBAccelerator(..., PureImagFreq = true))
+__global__ void stamp_neighbor_kernel(double *M, long ldM, int rowOff, int colOff, const double *B, long ldB, int bw, int nr, int nc,
                                       double pr, double pi, int useSymmetry)
 { __shared__ double tile[32][33 * 2];
   const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -59,14 +60,14 @@ __global__ void stamp_neighbor_kernel(double *M, long ldM, int rowOff, int colOf
     { // element B[c0 + threadIdx.x, r0 + j]: row index runs with threadIdx.x (contiguous)
       const int rr = c0 + threadIdx.x, cc = r0 + j;
       double x = 0.0, y = 0.0;
-      if (rr < nr && cc < nc) { const size_t s = ((size_t)rr + (size_t)cc * ldB) * 2; x = B[s]; y = B[s + 1]; }
+      if (rr < nr && cc < nc) { const size_t s = ((size_t)rr + (size_t)cc * ldB) * bw; x = B[s]; y = bw == 2 ? B[s + 1] : 0.0; }
       tile[j][2 * threadIdx.x] = x; tile[j][2 * threadIdx.x + 1] = y; }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y)
    { const int r = r0 + threadIdx.x, c = c0 + j;
      if (r >= nr || c >= nc) continue;
-     const size_t s = ((size_t)r + (size_t)c * ldB) * 2;
-     const double bx = B[s], by = B[s + 1];
+     const size_t s = ((size_t)r + (size_t)c * ldB) * bw;
+     const double bx = B[s], by = bw == 2 ? B[s + 1] : 0.0;
      double vx = pr * bx - pi * by, vy = pr * by + pi * bx;
      if (useSymmetry)
       { const double tx = tile[threadIdx.x][2 * j], ty = tile[threadIdx.x][2 * j + 1];       // B[c, r]
@@ -77,7 +78,7 @@ __global__ void stamp_neighbor_kernel(double *M, long ldM, int rowOff, int colOf
 void launch_stamp_neighbor(scuffcuda_context *ctx, const Matrix &M, int rowOff, int colOff, const Matrix &B, double pr, double pi, int useSymmetry)
 { dim3 grid((B.NR + 31) / 32, (B.NC + 31) / 32), block(32, 8);
   ctx->launches++;
-  stamp_neighbor_kernel<<<grid, block, 0, ctx->stream>>>(M.d, M.NR, rowOff, colOff, B.d, B.NR, B.NR, B.NC, pr, pi, useSymmetry);
+  stamp_neighbor_kernel<<<grid, block, 0, ctx->stream>>>(M.d, M.NR, rowOff, colOff, B.d, B.NR, B.isReal ? 1 : 2, B.NR, B.NC, pr, pi, useSymmetry);
 }
 
 // lower(r,c) = upper(c,r) for r>c, 32x32 tiles through shared memory so both the read and the

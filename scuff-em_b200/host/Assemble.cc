@@ -26,14 +26,43 @@ HMatrix *RWGGeometry::AllocateBEMMatrix(bool PureImagFreq, bool Packed)
   return new HMatrix(TotalBFs, TotalBFs, DataType, Storage);
 }
 
-void *RWGGeometry::CreateABMBAccelerator(int, int, bool, bool) { return 0; }   // PBC block cache: not yet on the device path
-void RWGGeometry::DestroyABMBAccelerator(void *) {}
+// KBIMBCache, the 'kBloch-independent matrix-block cache' (AssembleBEMMatrix.cc:250-334): the 2/3/5/9 inner-cell blocks of
+// one surface pair stay resident in HBM across a kBloch sweep at fixed Omega; only the Bloch-phase stamping and the
+// outer-cell step are redone per kBloch.
+struct KBIMBCache
+{ cdouble Omega; int NumMatrices; bool NeedZDerivative; int nsa, nsb;
+  HMatrix *B[9];
+};
+
+void *RWGGeometry::CreateABMBAccelerator(int nsa, int nsb, bool PureImagFreq, bool NeedZDerivative)
+{ if (LBasis == 0) return 0;
+  if (nsa < 0 || nsa >= NumSurfaces || nsb < 0 || nsb >= NumSurfaces) ErrExit("CreateABMBAccelerator: invalid surface indices (%i,%i)", nsa, nsb);
+  if (NeedZDerivative) ErrExit("CreateABMBAccelerator: z-derivative blocks (GradM[2]) are not yet available on the device path");
+  const bool OneDLattice = (LDim == 1), SameSurface = (nsa == nsb);
+  KBIMBCache *Cache = new KBIMBCache;
+  Cache->Omega = -1.0;            // initially dirty
+  Cache->NumMatrices = OneDLattice ? (SameSurface ? 2 : 3) : (SameSurface ? 5 : 9);
+  Cache->NeedZDerivative = NeedZDerivative; Cache->nsa = nsa; Cache->nsb = nsb;
+  for (int nm = 0; nm < 9; nm++) Cache->B[nm] = 0;
+  for (int nm = 0; nm < Cache->NumMatrices; nm++)
+   { Cache->B[nm] = new HMatrix(Surfaces[nsa]->NumBFs, Surfaces[nsb]->NumBFs, PureImagFreq ? LHM_REAL : LHM_COMPLEX);
+     Cache->B[nm]->EnsureDevice(); }
+  return (void *)Cache;
+}
+void RWGGeometry::DestroyABMBAccelerator(void *pCache)
+{ if (pCache == 0) return;
+  KBIMBCache *Cache = (KBIMBCache *)pCache;
+  for (int nm = 0; nm < Cache->NumMatrices; nm++) delete Cache->B[nm];
+  delete Cache;
+}
+static bool EqualFloat(cdouble a, cdouble b)    // libs/libhrutil/Vector.cc:273-276
+{ return float(real(a)) == float(real(b)) && float(imag(a)) == float(imag(b)); }
 
 // device-side GetSurfaceSurfaceInteractions for one block of M (device twin), no host copy-back
 static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omega, HMatrix *M,
                                   int RowOffset, int ColOffset, bool Symmetric, bool Accumulate,
                                   const double *Displacement, bool OmitRegion1, bool OmitRegion2,
-                                  int ColBegin = 0, int ColEnd = 0)
+                                  int ColBegin = 0, int ColEnd = 0, int GBA1 = 0, int GBA2 = 0)
 { scuffcuda_context *ctx = GetCudaContext();
   RWGSurface *Sa = G->Surfaces[nsa], *Sb = G->Surfaces[nsb];
   G->UpdateCachedEpsMuValues(Omega);
@@ -47,6 +76,7 @@ static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omeg
   if (Displacement) { A.use_displacement = 1; for (int i = 0; i < 3; i++) A.displacement[i] = Displacement[i]; }
   A.force_taylor_duffy = RWGGeometry::DisableCache ? 1 : 0;
   A.col_begin = ColBegin; A.col_end = ColEnd;
+  A.gba_a = GBA1; A.gba_b = GBA2;
   const char *fo = getenv("SCUFF_CUDA_FAR_ONLY"); A.far_only = (fo && fo[0] == '1');
 
   double Signs[2]; int CR[2];
@@ -118,7 +148,7 @@ void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double
                                          HMatrix *M, HMatrix **GradM, int RowOffset, int ColOffset,
                                          void *Accelerator, bool TransposeAccelerator,
                                          int NumTorqueAxes, HMatrix **dMdT, double *GammaMatrix)
-{ (void)Accelerator; (void)GammaMatrix; (void)kBloch;
+{ (void)GammaMatrix;
   if (TransposeAccelerator) ErrExit("%s:%i: TransposeAccelerator not implemented", __FILE__, __LINE__);
   if (nsa < 0 || nsa >= NumSurfaces || nsb < 0 || nsb >= NumSurfaces) ErrExit("AssembleBEMMatrixBlock: invalid surface indices (%i,%i)", nsa, nsb);
   if (GradM || (NumTorqueAxes > 0 && dMdT))
@@ -136,7 +166,7 @@ void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double
         AddSurfaceZetaContribution(this, nsa, Omega, M, RowOffset, 0, 0); }
      M->SyncToHost();
      return; }
-  AssembleBEMMatrixBlockPBC(nsa, nsb, Omega, kBloch, M, RowOffset, ColOffset);
+  AssembleBEMMatrixBlockPBC(nsa, nsb, Omega, kBloch, M, RowOffset, ColOffset, Accelerator);
   M->SyncToHost();
 }
 
@@ -241,7 +271,7 @@ HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, HMatrix *M) { return Asse
 // Step 1 of the periodic branch of AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:465-519): the kBloch-independent blocks
 // of the innermost lattice cells, each from the displaced-surface assembly on the device and stamped into M with its Bloch
 // phase factor (StampInNeighborBlock, :72-114).  Leaves the block of M in HBM (M->HostStale).
-void RWGGeometry::AssembleInnerCellBlocks(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset, int ColOffset)
+void RWGGeometry::AssembleInnerCellBlocks(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset, int ColOffset, void *Accelerator)
 { if (LBasis == 0) ErrExit("AssembleInnerCellBlocks: geometry is not periodic");
   if (!kBloch) ErrExit("%s:%i: Bloch wavevector must be specified for PBC geometries", __FILE__, __LINE__);
   if (M->RealComplex != LHM_COMPLEX) ErrExit("AssembleInnerCellBlocks: the BEM matrix of a periodic geometry is complex");
@@ -255,15 +285,23 @@ void RWGGeometry::AssembleInnerCellBlocks(int nsa, int nsb, cdouble Omega, doubl
   double LBV[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };
   for (int i = 0; i < 3; i++) { LBV[0][i] = LBasis->GetEntryD(i, 0); if (LDim > 1) LBV[1][i] = LBasis->GetEntryD(i, 1); }
 
+  KBIMBCache *Cache = (KBIMBCache *)Accelerator;
+  const bool HaveCache = (Cache != 0);
+  if (HaveCache && (Cache->nsa != nsa || Cache->nsb != nsb)) ErrExit("AssembleBEMMatrixBlock: accelerator was created for surfaces (%i,%i), not (%i,%i)", Cache->nsa, Cache->nsb, nsa, nsb);
+  const bool HaveCleanCache = HaveCache && EqualFloat(Cache->Omega, Omega);       // AssembleBEMMatrix.cc:405-408
+  if (HaveCache) Cache->Omega = Omega;
+
   M->EnsureDevice();
   // M->ZeroBlock(RowOffset, NBFA, ColOffset, NBFB) on the device: a block assembly with both regions omitted clears it
   AssembleBlockOnDevice(this, nsa, nsb, Omega, M, RowOffset, ColOffset, false, false, 0, true, true);
-  HMatrix B(Sa->NumBFs, Sb->NumBFs, LHM_COMPLEX);
+  HMatrix *BTemp = HaveCache ? 0 : new HMatrix(Sa->NumBFs, Sb->NumBFs, LHM_COMPLEX);
   unsigned long long Counts[5] = { 0, 0, 0, 0, 0 };
   bool done = false;
+  int nb = 0;
   for (int n1 = +1; n1 >= -1 && !done; n1--)
    for (int n2 = +1; n2 >= -1 && !done; n2--)
     { if (OneDLattice && n2 != 0) continue;
+      HMatrix &B = HaveCache ? *Cache->B[nb++] : *BTemp;
       double L[3] = { n1 * LBV[0][0] + n2 * LBV[1][0], n1 * LBV[0][1] + n2 * LBV[1][1], 0.0 };
       // contributions of regions that do not extend across the cell boundary are omitted (:487-499)
       bool Omit1, Omit2;
@@ -275,21 +313,90 @@ void RWGGeometry::AssembleInnerCellBlocks(int nsa, int nsb, cdouble Omega, doubl
          if (n2 != 0 && RegionIsExtended[1][nr1]) Omit1 = false;
          if (n2 != 0 && nr2 != -1 && RegionIsExtended[1][nr2]) Omit2 = false; }
       const bool Center = (n1 == 0 && n2 == 0);
-      AssembleBlockOnDevice(this, nsa, nsb, Omega, &B, 0, 0, UseSymmetry && Center, false, L, Omit1, Omit2);
-      for (int i = 0; i < 5; i++) Counts[i] += LastPPICounts[i];
+      if (!HaveCleanCache)
+       { AssembleBlockOnDevice(this, nsa, nsb, Omega, &B, 0, 0, UseSymmetry && Center, false, L, Omit1, Omit2);
+         for (int i = 0; i < 5; i++) Counts[i] += LastPPICounts[i]; }
+      else { SyncDeviceGeometry(); B.EnsureDevice(); }
       const double Arg = kBloch[0] * L[0] + kBloch[1] * L[1], BPF[2] = { cos(Arg), sin(Arg) };
       if (scuffcuda_matrix_stamp_neighbor_block(ctx, M->DeviceHandle, RowOffset, ColOffset, B.DeviceHandle, BPF, UseSymmetry && !Center))
        ErrExit("%s", scuffcuda_last_error(ctx));
       if (UseSymmetry && Center) done = true; }
+  delete BTemp;
   for (int i = 0; i < 5; i++) LastPPICounts[i] = Counts[i];
   M->HostStale = true;
 }
 
-void RWGGeometry::AssembleBEMMatrixBlockPBC(int, int, cdouble, double *, HMatrix *, int, int)
-{ // Step 1 (inner cells: AssembleInnerCellBlocks above) runs on the device; step 2 needs the Ewald-summed periodic Green's
-  // function tables (CreateRegionGBA / GBarVDEwald), which are not built yet.  A matrix without them would be wrong: refuse.
-  ErrExit("periodic (LATTICE) geometries are not yet supported by the device assembly path: the outer-cell contribution "
-          "(Ewald-summed GBar interpolation tables, AssembleBEMMatrix.cc:530-560) is missing");
+// CreateRegionGBA(nr, Omega, kBloch, ns1, ns2) (GBarAccelerator.cc:1012-1124,1205-1221): the periodic Green's function of region
+// nr for R = x1 - x2, x1 on surface ns1 and x2 on ns2, as a device table; returns 0 if the region contributes nothing
+static int CreateRegionGBA(RWGGeometry *G, int nr, cdouble Omega, double *kBloch, int ns1, int ns2)
+{ scuffcuda_context *ctx = GetCudaContext();
+  // the lattice with respect to which the region is periodic may be a sublattice of the geometry's
+  int NumExtendedDimensions = 0;
+  if (G->RegionIsExtended[0][nr]) NumExtendedDimensions++;
+  if (G->LDim > 1 && G->RegionIsExtended[1][nr]) NumExtendedDimensions++;
+  if (NumExtendedDimensions == 0) return 0;
+  double lbv[4] = { 0, 0, 0, 0 }; int ldim = G->LDim;
+  if (NumExtendedDimensions == G->LDim)
+   { lbv[0] = G->LBasis->GetEntryD(0, 0); lbv[1] = G->LBasis->GetEntryD(1, 0);
+     if (G->LDim > 1) { lbv[2] = G->LBasis->GetEntryD(0, 1); lbv[3] = G->LBasis->GetEntryD(1, 1); } }
+  else
+   { const int ExtendedDim = G->RegionIsExtended[0][nr] ? 0 : 1;
+     lbv[0] = G->LBasis->GetEntryD(0, ExtendedDim); lbv[1] = G->LBasis->GetEntryD(1, ExtendedDim); ldim = 1; }
+  const cdouble k = Omega * std::sqrt(G->EpsTF[nr] * G->MuTF[nr]);      // Omega * RegionMPs[nr]->GetRefractiveIndex(Omega)
+  // no table where GBar is exponentially tiny at all evaluation points
+  if (imag(k) > 0.0)
+   { double minL = 2.0 * sqrt(lbv[0] * lbv[0] + lbv[1] * lbv[1]);
+     if (ldim > 1) minL = fmin(minL, 2.0 * sqrt(lbv[2] * lbv[2] + lbv[3] * lbv[3]));
+     if (imag(k) * minL > 14.0) return 0; }
+  // range of the transverse coordinate Rho = |z| of R = x1 - x2 (from the surfaces' bounding boxes as the reference keeps them)
+  double RMin[3], RMax[3], AbsRMin[3], AbsRMax[3];
+  for (int Mu = 0; Mu < 3; Mu++)
+   { RMax[Mu] = G->Surfaces[ns1]->RMax[Mu] - G->Surfaces[ns2]->RMin[Mu];
+     RMin[Mu] = G->Surfaces[ns1]->RMin[Mu] - G->Surfaces[ns2]->RMax[Mu]; }
+  double RhoMin, RhoMax;
+  if (RMin[0] > RMax[0]) { RhoMin = 1.0; RhoMax = 0.0; }
+  else
+   { for (int Mu = 0; Mu < 3; Mu++)
+      { if (RMin[Mu] >= 0.0) { AbsRMin[Mu] = fabs(RMin[Mu]); AbsRMax[Mu] = fabs(RMax[Mu]); }
+        else if (RMin[Mu] < 0.0 && RMax[Mu] > 0.0) { AbsRMin[Mu] = 0.0; AbsRMax[Mu] = fmax(fabs(RMax[Mu]), fabs(RMin[Mu])); }
+        else { AbsRMin[Mu] = fabs(RMax[Mu]); AbsRMax[Mu] = fabs(RMin[Mu]); } }
+     if (ldim == 1) { RhoMin = sqrt(AbsRMin[1] * AbsRMin[1] + AbsRMin[2] * AbsRMin[2]); RhoMax = sqrt(AbsRMax[1] * AbsRMax[1] + AbsRMax[2] * AbsRMax[2]); }
+     else { RhoMin = AbsRMin[2]; RhoMax = AbsRMax[2]; } }
+  double RelTol = 1.0e-3;
+  if (const char *str = getenv("SCUFF_INTERPOLATION_TOLERANCE")) { sscanf(str, "%le", &RelTol); Log("Setting interpolation tolerance to %e.", RelTol); }
+  int ForceFull = 0, NMax = 0;
+  if (const char *str = getenv("SCUFF_EWALD_FULL")) if (str[0] == '1') { Log("Forcing full Ewald summation."); ForceFull = 1; }
+  if (const char *str = getenv("SCUFF_GBAR_NMAX")) NMax = atoi(str);
+  if (getenv("SCUFF_GBAR_NDINTERP")) ErrExit("SCUFF_GBAR_NDINTERP (InterpND tables) is not supported by the device assembly path");
+  const double kk[2] = { real(k), imag(k) };
+  int Handle = 0;
+  if (scuffcuda_gbar_create(ctx, kk, kBloch, lbv, ldim, RhoMin, RhoMax, RelTol, 1, ForceFull, NMax, &Handle)) ErrExit("%s", scuffcuda_last_error(ctx));
+  return Handle;
+}
+
+void RWGGeometry::AssembleBEMMatrixBlockPBC(int nsa, int nsb, cdouble Omega, double *kBloch, HMatrix *M, int RowOffset, int ColOffset, void *Accelerator)
+{ scuffcuda_context *ctx = GetCudaContext();
+  int CR[2]; double Signs[2];
+  const int NumCommonRegions = CountCommonRegions(Surfaces[nsa], Surfaces[nsb], CR, Signs);
+  if (NumCommonRegions == 0) return;                                    // AssembleBEMMatrix.cc:413-414 (the block is left as it is)
+  const int nr1 = CR[0], nr2 = NumCommonRegions == 2 ? CR[1] : -1;
+  // step 1: innermost grid cells, Bloch-phased (:462-521)
+  AssembleInnerCellBlocks(nsa, nsb, Omega, kBloch, M, RowOffset, ColOffset, Accelerator);
+  unsigned long long Counts[5]; for (int i = 0; i < 5; i++) Counts[i] = LastPPICounts[i];
+  // step 2: outer grid cells through the periodic Green's function of each common region (:526-560)
+  UpdateCachedEpsMuValues(Omega);
+  bool OmitRegion1 = false, OmitRegion2 = (nr2 == -1);
+  const int GBA1 = CreateRegionGBA(this, nr1, Omega, kBloch, nsa, nsb);
+  if (GBA1 == 0) OmitRegion1 = true;
+  int GBA2 = 0;
+  if (!OmitRegion2) { GBA2 = CreateRegionGBA(this, nr2, Omega, kBloch, nsa, nsb); if (GBA2 == 0) OmitRegion2 = true; }
+  if (!OmitRegion1 || !OmitRegion2)
+   { AssembleBlockOnDevice(this, nsa, nsb, Omega, M, RowOffset, ColOffset, false, true, 0, OmitRegion1, OmitRegion2, 0, 0, GBA1, GBA2);
+     for (int i = 0; i < 5; i++) Counts[i] += LastPPICounts[i]; }
+  if (GBA1) scuffcuda_gbar_destroy(ctx, GBA1);
+  if (GBA2) scuffcuda_gbar_destroy(ctx, GBA2);
+  for (int i = 0; i < 5; i++) LastPPICounts[i] = Counts[i];
+  M->HostStale = true;
 }
 
 // PreloadCache / StoreCache (libscuff.h:662-663 -> GlobalFIPPICache.PreLoad/Store)

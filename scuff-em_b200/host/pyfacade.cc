@@ -91,6 +91,11 @@ int scuffb200_matrix_symmetrize(void *m)
 int scuffb200_assemble_block(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off)
 { RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
   GUARD(G->AssembleBEMMatrixBlock(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, 0, row_off, col_off); return 0;, 1) }
+void *scuffb200_create_abmb(void *g, int nsa, int nsb, int pure_imag) { GUARD(return ((RWGGeometry *)g)->CreateABMBAccelerator(nsa, nsb, pure_imag != 0, false);, 0) }
+void scuffb200_destroy_abmb(void *g, void *acc) { ((RWGGeometry *)g)->DestroyABMBAccelerator(acc); }
+int scuffb200_assemble_block_acc(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off, void *acc)
+{ RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
+  GUARD(G->AssembleBEMMatrixBlock(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, 0, row_off, col_off, acc); return 0;, 1) }
 int scuffb200_assemble_inner_cells(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off)
 { RWGGeometry *G = (RWGGeometry *)g; HMatrix *M = (HMatrix *)m;
   GUARD(G->AssembleInnerCellBlocks(nsa, nsb, cdouble(wr, wi), (double *)kBloch, M, row_off, col_off); M->SyncToHost(); return 0;, 1) }

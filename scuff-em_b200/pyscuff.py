@@ -29,7 +29,7 @@ class SSIArgs(C.Structure):
                 ("row_offset", C.c_int), ("col_offset", C.c_int),
                 ("use_displacement", C.c_int), ("displacement", C.c_double * 3),
                 ("force_taylor_duffy", C.c_int), ("far_only", C.c_int),
-                ("col_begin", C.c_int), ("col_end", C.c_int), ("reserved", C.c_int * 5)]
+                ("col_begin", C.c_int), ("col_end", C.c_int), ("gba_a", C.c_int), ("gba_b", C.c_int), ("reserved", C.c_int * 3)]
 
 
 _cuda = None
@@ -74,6 +74,13 @@ def cuda_lib():
         L.scuffcuda_host_free.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffcuda_selftest_math.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.scuffcuda_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.scuffcuda_gbar_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double,
+                                            C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.scuffcuda_gbar_destroy.argtypes = [C.c_void_p, C.c_int]
+        L.scuffcuda_gbar_info.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
+        L.scuffcuda_gbar_get_table.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.scuffcuda_gbar_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.scuffcuda_gbar_ewald.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _cuda = L
     return _cuda
 
@@ -121,6 +128,11 @@ def host_lib():
         L.scuffb200_assemble_block.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                                C.c_void_p, C.c_int, C.c_int]
         L.scuffb200_ppi_counts.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_create_abmb.restype = C.c_void_p
+        L.scuffb200_create_abmb.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.scuffb200_destroy_abmb.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_assemble_block_acc.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                   C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.scuffb200_lu_factorize.argtypes = [C.c_void_p]
         L.scuffb200_lu_solve.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffb200_preload_cache.argtypes = [C.c_char_p]
@@ -278,13 +290,23 @@ class RWGGeometry:
         _check(host_lib().scuffb200_assemble_columns(self.ptr, M.ptr, float(np.real(Omega)), float(np.imag(Omega)), int(c0), int(c1)))
         return M
 
-    def AssembleBEMMatrixBlock(self, nsa, nsb, Omega, M, kBloch=None, RowOffset=0, ColOffset=0):
+    def AssembleBEMMatrixBlock(self, nsa, nsb, Omega, M, kBloch=None, RowOffset=0, ColOffset=0, ABMBCache=None):
         kb = None
         if kBloch is not None:
             kb = (C.c_double * 2)(float(kBloch[0]), float(kBloch[1]))
-        _check(host_lib().scuffb200_assemble_block(self.ptr, M.ptr, nsa, nsb, float(np.real(Omega)),
-                                                    float(np.imag(Omega)), kb, RowOffset, ColOffset))
+        _check(host_lib().scuffb200_assemble_block_acc(self.ptr, M.ptr, nsa, nsb, float(np.real(Omega)),
+                                                        float(np.imag(Omega)), kb, RowOffset, ColOffset, ABMBCache))
         return M
+
+    def CreateABMBAccelerator(self, nsa, nsb, PureImagFreq=False):
+        """kBloch-independent matrix-block cache of one surface pair (AssembleBEMMatrix.cc:260-318); None for compact geometries"""
+        p = host_lib().scuffb200_create_abmb(self.ptr, nsa, nsb, int(PureImagFreq))
+        if not p and self.LDim:
+            raise ScuffError(host_lib().scuffb200_last_error().decode())
+        return p
+
+    def DestroyABMBAccelerator(self, acc):
+        host_lib().scuffb200_destroy_abmb(self.ptr, acc)
 
     def AssembleInnerCellBlocks(self, nsa, nsb, Omega, kBloch, M, RowOffset=0, ColOffset=0):
         """step 1 of the periodic branch of AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:465-519): neighbour-cell blocks
@@ -360,6 +382,58 @@ def transfer_bytes():
     b = (C.c_ulonglong * 2)()
     cuda_lib().scuffcuda_get_transfer_bytes(context(), b)
     return list(b)
+
+
+def _cuda_check(rc):
+    if rc:
+        raise ScuffError(cuda_lib().scuffcuda_last_error(context()).decode())
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def gbar_ewald(k, kBloch, lbv, R, exclude_inner=False, ldim=2):
+    """GBarVDEwald (GBarVDEwald.cc:931-996) on the device at points R[n,3]: complex array [n,8]"""
+    R = _d(R).reshape(-1, 3)
+    out = np.zeros((len(R), 16))
+    kk = _d([np.real(k), np.imag(k)]); kb = _d(kBloch); lb = _d(lbv).ravel()
+    _cuda_check(cuda_lib().scuffcuda_gbar_ewald(context(), kk.ctypes.data, kb.ctypes.data, lb.ctypes.data, ldim, int(exclude_inner),
+                                                len(R), R.ctypes.data, out.ctypes.data))
+    return out[:, 0::2] + 1j * out[:, 1::2]
+
+
+class GBarAccelerator:
+    """device table of the periodic Green's function (CreateGBarAccelerator, GBarAccelerator.cc:339-547)"""
+
+    def __init__(self, k, kBloch, lbv, rho_min, rho_max, rel_tol=1e-3, exclude_inner=True, force_full=False, nmax=0, ldim=2):
+        kk = _d([np.real(k), np.imag(k)]); kb = _d(kBloch); lb = _d(lbv).ravel()
+        h = C.c_int()
+        _cuda_check(cuda_lib().scuffcuda_gbar_create(context(), kk.ctypes.data, kb.ctypes.data, lb.ctypes.data, ldim, float(rho_min), float(rho_max),
+                                                     float(rel_tol), int(exclude_inner), int(force_full), int(nmax), C.byref(h)))
+        self.handle = h.value
+        n = (C.c_int * 3)(); xmin = (C.c_double * 3)(); dx = (C.c_double * 3)(); lmax = C.c_double(); full = C.c_int()
+        _cuda_check(cuda_lib().scuffcuda_gbar_info(context(), self.handle, n, xmin, dx, C.byref(lmax), C.byref(full)))
+        self.N, self.XMin, self.DX, self.LMax, self.full = list(n), list(xmin), list(dx), lmax.value, bool(full.value)
+
+    def table(self):
+        ncell = (self.N[0] - 1) * (self.N[1] - 1) * (self.N[2] - 1)
+        out = np.zeros(max(ncell, 0) * 128)
+        if ncell > 0:
+            _cuda_check(cuda_lib().scuffcuda_gbar_get_table(context(), self.handle, out.ctypes.data))
+        return out
+
+    def eval(self, R):
+        """GetGBar: complex array [n,4] = G, dG/dx, dG/dy, dG/dz"""
+        R = _d(R).reshape(-1, 3)
+        out = np.zeros((len(R), 8))
+        _cuda_check(cuda_lib().scuffcuda_gbar_eval(context(), self.handle, len(R), R.ctypes.data, out.ctypes.data))
+        return out[:, 0::2] + 1j * out[:, 1::2]
+
+    def close(self):
+        if self.handle:
+            cuda_lib().scuffcuda_gbar_destroy(context(), self.handle)
+            self.handle = 0
 
 
 def measure_fp64_peak():

@@ -104,3 +104,65 @@ extern "C" int hh_fippi(const double *V, int ncv, double *out36, int *nregions)
   (void)nregions;
   return st;
 }
+
+// ---- periodic Green's function (Ewald) check: host build of csrc/gbar.cuh ----
+#include "../scuff-em_b200/csrc/gbar.cuh"
+extern "C" int hh_gbar(double kr, double ki, const double *kBloch, const double *LBV4, int exclude, int npts, const double *R, double *out16)
+{ GBarParams P; P.k = mk(kr, ki); P.kBloch[0] = kBloch[0]; P.kBloch[1] = kBloch[1];
+  P.LBV[0][0] = LBV4[0]; P.LBV[0][1] = LBV4[1]; P.LBV[1][0] = LBV4[2]; P.LBV[1][1] = LBV4[3];
+  P.LDim = 2; P.excludeInner = exclude;
+  for (int n = 0; n < npts; n++)
+   { cd G[8]; gbar_vd_ewald(R + 3 * n, P, G);
+     for (int i = 0; i < 8; i++) { out16[16 * n + 2 * i] = G[i].x; out16[16 * n + 2 * i + 1] = G[i].y; } }
+  return 0;
+}
+extern "C" void hh_faddeeva(int n, const double *z, double *w)
+{ for (int i = 0; i < n; i++) { cd r = faddeeva_w(mk(z[2 * i], z[2 * i + 1])); w[2 * i] = r.x; w[2 * i + 1] = r.y; } }
+
+// ---- whole table chain on the host (same inline source as gbar.cu): decisions, coefficients, GetGBar ----
+#include "../scuff-em_b200/csrc/gbar_table.cuh"
+// info[0..2] = N, info[3..5] = XMin, info[6..8] = DX, info[9] = LMax, info[10] = full; coeffs (may be null) receives 128 doubles per cell
+extern "C" int hh_gbar_table(double kr, double ki, const double *kBloch, const double *LBV4, double RhoMin, double RhoMax, double RelTol,
+                             double *info, double *coeffs, int maxCoeffs, int npts, const double *R, double *out8)
+{ GBarParams P; P.k = mk(kr, ki); P.kBloch[0] = kBloch[0]; P.kBloch[1] = kBloch[1];
+  P.LBV[0][0] = LBV4[0]; P.LBV[0][1] = LBV4[1]; P.LBV[1][0] = LBV4[2]; P.LBV[1][1] = LBV4[3];
+  P.LDim = 2; P.excludeInner = 1;
+  GBarGrid Gr; gbar_grid_lmax(P, RhoMin, Gr);
+  GBarTableView T; T.P = P; T.RhoMin = RhoMin; T.RhoMax = RhoMax; T.LMax = Gr.LMax; T.forceFull = RhoMin > RhoMax; T.C = 0;
+  std::vector<double> C;
+  if (!T.forceFull)
+   { double probes[8][3], MinDelta[3] = { 1e300, 1e300, 1e300 };
+     const int nProbe = gbar_grid_probes(Gr, RhoMin, RhoMax, probes);
+     for (int i = 0; i < nProbe; i++)
+      { double Delta[3], DX[3], Pts[11][3], Opt[3]; cd V[11][SC_GB_NSUM];
+        spacing_probe_setup(P, RhoMin, RhoMax, probes[i], Delta, DX, Pts);
+        for (int n = 0; n < 11; n++) gbar_vd_ewald(Pts[n], P, V[n]);
+        spacing_probe_finish(probes[i], Delta, DX, V, RelTol, Opt);
+        for (int m = 0; m < 3; m++) MinDelta[m] = fmin(MinDelta[m], Opt[m]); }
+     gbar_grid_dims(Gr, RhoMin, RhoMax, MinDelta, 0);
+     const int N1 = Gr.N[0], N2 = Gr.N[1], N3 = Gr.N[2];
+     std::vector<double> Phi((size_t)N1 * N2 * N3 * 16);
+     for (int n1 = 0; n1 < N1; n1++) for (int n2 = 0; n2 < N2; n2++) for (int n3 = 0; n3 < N3; n3++)
+      { const double X[3] = { Gr.XMin[0] + n1 * Gr.DX[0], Gr.XMin[1] + n2 * Gr.DX[1], Gr.XMin[2] + n3 * Gr.DX[2] };
+        cd V[SC_GB_NSUM]; gbar_vd_ewald(X, P, V);
+        const size_t i = n3 + (size_t)N3 * (n2 + (size_t)N2 * n1);
+        for (int s = 0; s < 8; s++) { Phi[16 * i + s] = V[s].x; Phi[16 * i + 8 + s] = V[s].y; } }
+     const int nCells = (N1 - 1) * (N2 - 1) * (N3 - 1);
+     C.resize((size_t)nCells * 128);
+     for (int cell = 0; cell < nCells; cell++) for (int nf = 0; nf < 2; nf++)
+      { const int n3 = cell % (N3 - 1), n2 = (cell / (N3 - 1)) % (N2 - 1), n1 = cell / ((N3 - 1) * (N2 - 1));
+        double D[8][8];
+        for (int c = 0; c < 8; c++)
+         { const size_t p = (n3 + (c & 1)) + (size_t)N3 * ((n2 + ((c >> 1) & 1)) + (size_t)N2 * (n1 + (c >> 2)));
+           for (int d = 0; d < 8; d++) D[c][d] = Phi[16 * p + 8 * nf + d]; }
+        tricubic_fit(D, Gr.DX, &C[(size_t)64 * (2 * cell + nf)]); }
+     for (int m = 0; m < 3; m++) { T.N[m] = Gr.N[m]; T.XMin[m] = Gr.XMin[m]; T.DX[m] = Gr.DX[m]; info[m] = Gr.N[m]; info[3 + m] = Gr.XMin[m]; info[6 + m] = Gr.DX[m]; }
+     T.C = C.data();
+     if (coeffs) for (size_t i = 0; i < C.size() && (int)i < maxCoeffs; i++) coeffs[i] = C[i]; }
+  info[9] = Gr.LMax; info[10] = T.forceFull;
+  for (int n = 0; n < npts; n++)
+   { cd G, dG[3]; gbar_get(T, R + 3 * n, G, dG);
+     out8[8 * n] = G.x; out8[8 * n + 1] = G.y;
+     for (int m = 0; m < 3; m++) { out8[8 * n + 2 + 2 * m] = dG[m].x; out8[8 * n + 3 + 2 * m] = dG[m].y; } }
+  return 0;
+}

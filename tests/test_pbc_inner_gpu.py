@@ -2,8 +2,7 @@
 innermost lattice cells (displaced-surface assembly, region omission by RegionIsExtended, straddler edges) stamped with
 their Bloch phase factors (StampInNeighborBlock, :72-114).  The checker is the reference's full periodic block minus the
 outer-cell contribution it computes from its GBar tables (oracle/ref_driver.cc pbcinner), tolerance 1e-10 relative
-Frobenius.  The outer-cell (Ewald) step itself is not on the device path yet: AssembleBEMMatrix still refuses LATTICE
-geometries (tests/test_errors_gpu.py)."""
+Frobenius.  The outer-cell (Ewald) step is checked in tests/test_pbc_outer_gpu.py."""
 import os
 import numpy as np
 import pytest
