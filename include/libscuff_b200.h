@@ -74,9 +74,12 @@ class HMatrix
     * refreshed by SyncToHost() (AssembleBEMMatrix does it before returning)                */
    int  DeviceHandle;         /* 0 = none                                                     */
    bool HostStale;            /* device copy is newer than DM/ZM                              */
+   bool DeviceStale;          /* DM/ZM is newer than the device copy (host-side edits)        */
    void SyncToHost();
    void SyncToDevice();
    void EnsureDevice();
+   void PrepareDevice();      /* make the device copy current (uploads if it is missing or stale)            */
+   void MarkHostDirty();      /* call after writing DM/ZM directly (SetEntry/AddEntry/... do it themselves)  */
 
    int NR, NC;
    int RealComplex;

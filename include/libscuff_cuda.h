@@ -60,6 +60,10 @@ int scuffcuda_matrix_zero(scuffcuda_context *ctx, int handle);
  * within one matrix — the Mate[] diagonal-block reuse of AssembleBEMMatrix.cc:731-737  */
 int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int handle, int dst_row, int dst_col,
                                 int num_rows, int num_cols, int src_row, int src_col);
+/* HMatrix::InsertBlock between two device matrices of the same type (libs/libhmat/HMatrix.cc InsertBlock): the T/U-block stamping
+ * of scuff-cas3D's Factorize (CasimirIntegrand.cc:159-196) without a round trip through the host                          */
+int scuffcuda_matrix_insert_block(scuffcuda_context *ctx, int handle_dst, int dst_row, int dst_col,
+                                  int handle_src, int src_row, int src_col, int num_rows, int num_cols);
 /* sparse accumulate M[rows[i], cols[i]] += vals[2i] + i*vals[2i+1] (HMatrix::AddEntry; a real matrix takes the real part):
  * the surface-impedance term of AddSurfaceZetaContributionToBEMMatrix (SurfaceSurfaceInteractions.cc:339-421), whose
  * O(NumEdges) overlap entries the host computes                                           */

@@ -48,6 +48,10 @@ int scuffcuda_create(int device, scuffcuda_context **out)
   CKS(cusolverDnSetStream(ctx->solver, ctx->stream));
   CK(cudaMalloc(&ctx->dcounters, 16 * sizeof(unsigned long long)));
   CK(cudaMemset(ctx->dcounters, 0, 16 * sizeof(unsigned long long)));
+  { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CK(cudaStreamCreateWithPriority(&ctx->nearStream, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    for (int i = 0; i < 7; i++) CK(cudaEventCreate(&ctx->ev[i])); }
   *out = ctx;
   return 0;
 }
@@ -62,6 +66,11 @@ void scuffcuda_destroy(scuffcuda_context *ctx)
   if (ctx->fippi.drec) cudaFree(ctx->fippi.drec);
   if (ctx->dcounters) cudaFree(ctx->dcounters);
   if (ctx->dscratch) cudaFree(ctx->dscratch);
+  if (ctx->dHoIdx) cudaFree(ctx->dHoIdx);
+  for (auto &b : ctx->mapped) if (b.second.p) cudaFreeHost(b.second.p);
+  for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+  if (ctx->nearStream) cudaStreamDestroy(ctx->nearStream);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -173,6 +182,20 @@ int scuffcuda_matrix_copy_block(scuffcuda_context *ctx, int h, int dr, int dc, i
   CK(cudaSetDevice(ctx->device));
   launch_copy_block(ctx, *M, dr, dc, nr, nc, sr, sc); CK(cudaGetLastError()); return 0;
 }
+int scuffcuda_matrix_insert_block(scuffcuda_context *ctx, int hd, int dr, int dc, int hs, int sr, int sc, int nr, int nc)
+{ Matrix *D = get_matrix(ctx, hd), *S = get_matrix(ctx, hs);
+  if (!D || !S) return fail(ctx, "invalid matrix handle %d", !D ? hd : hs);
+  if (D->isReal != S->isReal) return fail(ctx, "matrix_insert_block: matrices differ in type");
+  if (dr < 0 || dc < 0 || sr < 0 || sc < 0 || nr < 0 || nc < 0 || dr + nr > D->NR || dc + nc > D->NC || sr + nr > S->NR || sc + nc > S->NC)
+   return fail(ctx, "matrix_insert_block: block out of range");
+  if (nr == 0 || nc == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const size_t es = (D->isReal ? 1 : 2) * sizeof(double);
+  CK(cudaMemcpy2DAsync((char *)D->d + ((size_t)dr + (size_t)dc * D->NR) * es, (size_t)D->NR * es,
+                       (const char *)S->d + ((size_t)sr + (size_t)sc * S->NR) * es, (size_t)S->NR * es,
+                       (size_t)nr * es, nc, cudaMemcpyDeviceToDevice, ctx->stream));
+  D->factored = false; return 0;
+}
 int scuffcuda_matrix_add_entries(scuffcuda_context *ctx, int h, int n, const int *rows, const int *cols, const double *vals)
 { Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
   for (int i = 0; i < n; i++)
@@ -207,16 +230,7 @@ int scuffcuda_matrix_download(scuffcuda_context *ctx, int h, void *host, long ld
   ctx->d2hBytes += (unsigned long long)M->NR * M->NC * es;
   return 0;
 }
-// copy stream for downloads that overlap with assembly (scuffcuda_matrix_download_region_async)
-static cudaStream_t copy_stream(scuffcuda_context *ctx)
-{ static std::map<scuffcuda_context *, cudaStream_t> streams;
-  auto it = streams.find(ctx);
-  if (it != streams.end()) return it->second;
-  cudaStream_t s = nullptr;
-  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); s = ctx->stream; }
-  streams[ctx] = s;
-  return s;
-}
+static cudaStream_t copy_stream(scuffcuda_context *ctx) { return ctx->copyStream; }
 int scuffcuda_matrix_download_region_async(scuffcuda_context *ctx, int h, void *host, long ld, int row0, int nrows, int col0, int ncols)
 { Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
   if (ld < M->NR) return fail(ctx, "matrix_download_region: ld < NR");
@@ -307,23 +321,12 @@ int scuffcuda_lu_solve(scuffcuda_context *ctx, int h, void *rhs, int nrhs)
 // ------------------------------------------------------------------------------------------
 // second, high-priority stream per context for the near/singular kernels: they are latency-bound (one thread per
 // adaptive cubature) and overlap with the FP64-bound far kernel; both scatter with atomics into the same matrix
-static cudaStream_t near_stream(scuffcuda_context *ctx)
-{ static std::map<scuffcuda_context *, cudaStream_t> streams;
-  auto it = streams.find(ctx);
-  if (it != streams.end()) return it->second;
-  int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
-  cudaStream_t s = nullptr;
-  if (cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); s = ctx->stream; }
-  streams[ctx] = s;
-  return s;
-}
+static cudaStream_t near_stream(scuffcuda_context *ctx) { return ctx->nearStream; }
 
 }  // extern "C" (paused)
 namespace scuffcuda {
 void *mapped_host_scratch(scuffcuda_context *ctx, size_t bytes, int slot)
-{ struct Buf { void *p = nullptr; size_t n = 0; };
-  static std::map<std::pair<scuffcuda_context *, int>, Buf> bufs;
-  Buf &B = bufs[std::make_pair(ctx, slot)];
+{ scuffcuda_context::MappedBuf &B = ctx->mapped[slot];
   if (bytes > B.n)
    { if (B.p) cudaFreeHost(B.p);
      B.p = nullptr; B.n = 0;
@@ -350,12 +353,33 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   if (a->row_offset < 0 || a->col_offset < 0 || a->row_offset + NBFA > M->NR || a->col_offset + NBFB > M->NC)
    return fail(ctx, "assemble_block: block (%d+%d, %d+%d) exceeds matrix %dx%d", a->row_offset, NBFA, a->col_offset, NBFB, M->NR, M->NC);
   if (a->symmetric && nsa != nsb) return fail(ctx, "assemble_block: symmetric requires nsa==nsb");
+  for (const char *v : { "SCUFF_TAYLORDUFFY_ABSTOL", "SCUFF_TAYLORDUFFY_RELTOL", "SCUFF_TAYLORDUFFY_MAXEVAL" })
+   if (getenv(v)) return fail(ctx, "assemble_block: %s is set, but the device Taylor-Duffy kernels compile in the reference's defaults "
+                                   "(AbsTol 0, RelTol 1e-10, MaxEval 1000; TaylorDuffy.cc:263-273,294-296) and cannot honour overrides", v);
   if ((a->gba_a || a->gba_b) && (a->symmetric || a->use_displacement || a->col_end > 0 || M->isReal))
    return fail(ctx, "assemble_block: the periodic outer-cell step needs a complex matrix, symmetric = 0, no displacement and no column range");
   CK(cudaSetDevice(ctx->device));
 
-  cudaEvent_t ev[7]; for (int i = 0; i < 7; i++) CK(cudaEventCreate(&ev[i]));
+  // validate the wavenumber range of both regions before anything is written: the FP64 sincos range reduction of the
+  // far kernel is exact for |Re k| * distance < 1e5
+  { double ext = 0.0;
+    for (const Surface *S : { &Sa, &Sb })
+     for (const PanelRec &P : S->hpanels)
+      ext = std::max(ext, std::sqrt(P.C[0] * P.C[0] + P.C[1] * P.C[1] + P.C[2] * P.C[2]) + P.R);
+    ext = 2.0 * ext + (a->use_displacement ? std::sqrt(a->displacement[0] * a->displacement[0] + a->displacement[1] * a->displacement[1]
+                                                       + a->displacement[2] * a->displacement[2]) : 0.0);
+    for (int region = 0; region < 2; region++)
+     { std::complex<double> Eps = region == 0 ? std::complex<double>(a->eps_a[0], a->eps_a[1]) : std::complex<double>(a->eps_b[0], a->eps_b[1]);
+       std::complex<double> Mu = region == 0 ? std::complex<double>(a->mu_a[0], a->mu_a[1]) : std::complex<double>(a->mu_b[0], a->mu_b[1]);
+       if (Eps == 0.0 || (region == 1 && (Sa.isPEC || Sb.isPEC))) continue;
+       std::complex<double> r = std::sqrt(Eps * Mu); if (imag(r) < 0.0) r = -r;
+       const double kre = std::fabs(real(r * std::complex<double>(a->omega[0], a->omega[1])));
+       if (kre * ext >= SCUFF_MAX_KR)
+        return fail(ctx, "assemble_block: |Re k| * geometry extent = %g exceeds the supported range %g", kre * ext, SCUFF_MAX_KR); } }
+
+  cudaEvent_t *ev = ctx->ev;                     // owned by the context: nothing to release on the error paths below
   cudaStream_t sMain = ctx->stream, sNear = near_stream(ctx);
+  struct StreamGuard { scuffcuda_context *c; cudaStream_t s; ~StreamGuard() { c->stream = s; } } restoreStream{ ctx, sMain };
   CK(cudaEventRecord(ev[0], ctx->stream));
   CK(cudaMemsetAsync(ctx->dcounters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   M->factored = false;
@@ -391,17 +415,6 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      SP.c3 = mk(real(PreFac3), imag(PreFac3));
      SP.colLo = a->col_end > 0 ? a->col_begin : 0; SP.colHi = a->col_end > 0 ? a->col_end : 0x7fffffff;
      int kmode = (imag(k) == 0.0) ? KMODE_REAL : ((real(k) == 0.0) ? KMODE_IMAG : KMODE_CPLX);
-     { // the FP64 sincos range reduction of the far kernel is exact for |Re k| * distance < 1e5
-       double ext = 0.0;
-       for (const Surface *S : { &Sa, &Sb })
-        for (const PanelRec &P : S->hpanels)
-         ext = std::max(ext, std::sqrt(P.C[0] * P.C[0] + P.C[1] * P.C[1] + P.C[2] * P.C[2]) + P.R);
-       ext = 2.0 * ext + (a->use_displacement ? std::sqrt(a->displacement[0] * a->displacement[0] + a->displacement[1] * a->displacement[1]
-                                                          + a->displacement[2] * a->displacement[2]) : 0.0);
-       if (std::fabs(real(k)) * ext >= SCUFF_MAX_KR)
-        return fail(ctx, "assemble_block: |Re k| * geometry extent = %g exceeds the supported range %g", std::fabs(real(k)) * ext, SCUFF_MAX_KR);
-     }
-
      if (a->gba_a || a->gba_b)
       { // outer-cell step of a periodic geometry: all panel pairs through the periodic Green's function of this region
         GBarTable *T = find_gbar(ctx, region == 0 ? a->gba_a : a->gba_b);
@@ -454,7 +467,6 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   CK(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 5; i++) ctx->counts[i] = hc[i];
   ctx->pairCounts[0] = hc[5]; ctx->pairCounts[1] = hc[6];
-  for (int i = 0; i < 7; i++) cudaEventDestroy(ev[i]);
   return 0;
 }
 

@@ -124,4 +124,11 @@ struct scuffcuda_context
   unsigned long long *dcounters = nullptr;   // device counters (near-list length, algorithm counts)
   void *dscratch = nullptr; size_t scratchBytes = 0;
   int smCount = 148;
+  // per-context helper streams, events and mapped host buffers (created with the context, destroyed with it)
+  cudaStream_t nearStream = nullptr;          // high priority: near/singular kernels, concurrent with the far kernel
+  cudaStream_t copyStream = nullptr;          // downloads overlapping with assembly
+  cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
+  struct MappedBuf { void *p = nullptr; size_t n = 0; };
+  std::map<int, MappedBuf> mapped;            // slot -> page-locked, device-mapped scratch
+  int *dHoIdx = nullptr; size_t hoIdxCap = 0; // index list of the high-order cubature kernel
 };

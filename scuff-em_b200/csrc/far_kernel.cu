@@ -521,17 +521,20 @@ int run_ho(scuffcuda_context *ctx, const NearArgs &A, const int *hoIdx, int n, i
   double *&T = dtcr[ctx->device & 63];
   if (!T)
    { if (cudaMalloc(&T, sizeof SC_TCR20_H) != cudaSuccess) { ctx->err = "high-order cubature table allocation failed"; return 1; }
-     cudaMemcpy(T, SC_TCR20_H, sizeof SC_TCR20_H, cudaMemcpyHostToDevice); }
-  int *didx = nullptr;
-  if (cudaMalloc(&didx, (size_t)n * sizeof(int)) != cudaSuccess) { ctx->err = "high-order cubature index allocation failed"; return 1; }
+     cudaMemcpy(T, SC_TCR20_H, sizeof SC_TCR20_H, cudaMemcpyHostToDevice); cudaDeviceSynchronize(); }
+  if ((size_t)n > ctx->hoIdxCap)
+   { if (ctx->dHoIdx) { cudaDeviceSynchronize(); cudaFree(ctx->dHoIdx); ctx->dHoIdx = nullptr; ctx->hoIdxCap = 0; }
+     const size_t cap = std::max<size_t>(2 * (size_t)n, 4096);
+     if (cudaMalloc(&ctx->dHoIdx, cap * sizeof(int)) != cudaSuccess) { ctx->err = "high-order cubature index allocation failed"; return 1; }
+     ctx->hoIdxCap = cap; }
+  int *didx = ctx->dHoIdx;                                      // persistent per context, grown on demand
   cudaMemcpyAsync(didx, hoIdx, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
   const bool psi = !(A.S.aPEC && A.S.bPEC);
   ctx->launches++;
   if (kmode == KMODE_REAL) launch_ho_mode<KMODE_REAL>(ctx, A, didx, n, T, psi);
   else if (kmode == KMODE_IMAG) launch_ho_mode<KMODE_IMAG>(ctx, A, didx, n, T, psi);
   else launch_ho_mode<KMODE_CPLX>(ctx, A, didx, n, T, psi);
-  cudaError_t e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(didx);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);           // hoIdx is the caller's; the index buffer may be reused next call
   if (e != cudaSuccess) { ctx->err = std::string("ho_kernel: ") + cudaGetErrorString(e); return 1; }
   return 0;
 }

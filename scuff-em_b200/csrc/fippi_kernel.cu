@@ -34,6 +34,7 @@ static int fippi_tables(scuffcuda_context *ctx, FIPPITables &T)
      cudaMemcpy(G.cePC, SC_CE_PC_H, sizeof SC_CE_PC_H, cudaMemcpyHostToDevice);
      cudaMemcpy(G.cvPX, SC_CV_PX_H, sizeof SC_CV_PX_H, cudaMemcpyHostToDevice);
      cudaMemcpy(G.cvPC, SC_CV_PC_H, sizeof SC_CV_PC_H, cudaMemcpyHostToDevice);
+     cudaDeviceSynchronize();   // pageable H2D copies may return before the DMA lands; the kernels run on non-blocking streams
    }
   T.cePX = G.cePX; T.cePXn = SC_CE_PX_N; T.cePC = G.cePC; T.cePCn = SC_CE_PC_N;
   T.cvPX = G.cvPX; T.cvPXn = SC_CV_PX_N; T.cvPC = G.cvPC; T.cvPCn = SC_CV_PC_N;
@@ -53,6 +54,7 @@ int fippi_compute_records(scuffcuda_context *ctx, const std::vector<int> &recIds
    { ctx->err = "FIPPI builder allocation failed"; cleanup(); return 1; }
   cudaMemcpy(dverts, verts.data(), (size_t)n * 18 * sizeof(double), cudaMemcpyHostToDevice);
   cudaMemcpy(dncv, ncvs.data(), n * sizeof(int), cudaMemcpyHostToDevice);
+  cudaDeviceSynchronize();     // the builder kernels run on their own non-blocking streams
 
   // integration case of every record: 0 no common vertex (3-D), 1 common edge (1-D), 2 common vertex (2-D); the
   // common-edge test is the float comparison of V2 and V2' that the integrand setup makes (fippi_integrands.cuh)

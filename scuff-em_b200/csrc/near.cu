@@ -182,12 +182,14 @@ static int fippi_sync_device(scuffcuda_context *ctx)
   if (n > T.dcap)
    { long cap = std::max(n * 2, 1024L);
      double *d; CKN(cudaMalloc(&d, (size_t)cap * FIPPI_REC_DOUBLES * sizeof(double)));
-     if (T.drec) { CKN(cudaMemcpy(d, T.drec, (size_t)T.dcount * FIPPI_REC_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice)); cudaFree(T.drec); }
+     if (T.drec) { CKN(cudaDeviceSynchronize()); CKN(cudaMemcpy(d, T.drec, (size_t)T.dcount * FIPPI_REC_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice)); CKN(cudaDeviceSynchronize()); cudaFree(T.drec); }
      T.drec = d; T.dcap = cap;
    }
   if (n > T.dcount)
-   { CKN(cudaMemcpy(T.drec + (size_t)T.dcount * FIPPI_REC_DOUBLES, T.hrec.data() + (size_t)T.dcount * FIPPI_REC_DOUBLES,
-                    (size_t)(n - T.dcount) * FIPPI_REC_DOUBLES * sizeof(double), cudaMemcpyHostToDevice));
+   { // stream-ordered (and waited for): the consumers run on non-blocking streams, which the legacy stream does not order
+     CKN(cudaMemcpyAsync(T.drec + (size_t)T.dcount * FIPPI_REC_DOUBLES, T.hrec.data() + (size_t)T.dcount * FIPPI_REC_DOUBLES,
+                         (size_t)(n - T.dcount) * FIPPI_REC_DOUBLES * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+     CKN(cudaDeviceSynchronize());
      T.dcount = n; }
   return 0;
 }
@@ -236,7 +238,7 @@ static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, 
      std::vector<int2> hl(count);
      cudaMemcpy(hl.data(), dlist, count * sizeof(int2), cudaMemcpyDeviceToHost);
      std::sort(hl.begin(), hl.end(), [](const int2 &u, const int2 &v) { return u.x != v.x ? u.x < v.x : u.y < v.y; });
-     cudaMemcpy(dlist, hl.data(), count * sizeof(int2), cudaMemcpyHostToDevice);
+     cudaMemcpyAsync(dlist, hl.data(), count * sizeof(int2), cudaMemcpyHostToDevice, ctx->stream);   // ordered before near_assess_kernel on the same stream
      float *dkeys = nullptr;
      if (cudaMalloc(&P.dnear, count * sizeof(NearPair)) != cudaSuccess || cudaMalloc(&dkeys, 2 * count * 15 * sizeof(float)) != cudaSuccess)
       { status = failc(ctx, "near plan alloc", cudaGetLastError()); cudaFree(dlist); return nullptr; }
@@ -295,7 +297,8 @@ static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, 
          }
         if (N.rec < 0) N.rec = N.rec2;   // forward order never evaluated: keep a valid index
       }
-     cudaMemcpy(P.dnear, P.hnear.data(), count * sizeof(NearPair), cudaMemcpyHostToDevice);
+     cudaMemcpyAsync(P.dnear, P.hnear.data(), count * sizeof(NearPair), cudaMemcpyHostToDevice, ctx->stream);
+     cudaStreamSynchronize(ctx->stream);          // consumers run on the near stream as well as on this one
      if (!newIds.empty())
       { if (fippi_compute_records(ctx, newIds, newVerts, newNcv)) { cudaFree(dlist); status = 1; return nullptr; } }
      if (fippi_sync_device(ctx)) { cudaFree(dlist); status = 1; return nullptr; }

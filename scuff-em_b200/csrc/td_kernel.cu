@@ -26,6 +26,7 @@ static int td_tables(scuffcuda_context *ctx, TDTables &T)
      cudaMemcpy(G.ccx, SC_CC_X_H, sizeof SC_CC_X_H, cudaMemcpyHostToDevice);
      cudaMemcpy(G.ccw, SC_CC_W_H, sizeof SC_CC_W_H, cudaMemcpyHostToDevice);
      cudaMemcpy(G.ups, SC_UPS_H, sizeof SC_UPS_H, cudaMemcpyHostToDevice);
+     cudaDeviceSynchronize();   // pageable H2D copies may return before the DMA lands; the kernels run on non-blocking streams
    }
   T.ccx = G.ccx; T.ccw = G.ccw; T.ups = G.ups;
   for (int i = 0; i < 5; i++) T.upsStart[i] = SC_UPS_START_H[i];

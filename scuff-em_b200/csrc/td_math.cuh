@@ -8,9 +8,9 @@
 // to the previous level, per-component convergence test converged.h, stop when numEval > MaxEval).
 // The polynomial coefficient maps (CMVStoUpsilon) come from generated_tables.h as data.
 //
-// Implemented here: the common-triangle case (ncv == 3, 1-D integral), which the reference uses at
-// every frequency; the common-edge / common-vertex cases are only reached in the short-wavelength
-// regime (|k| R > pi) and are reported as unsupported by the dispatcher.
+// Here: the shared integrand machinery and the common-triangle case (ncv == 3, 1-D integral), which the reference
+// uses at every frequency (td_kernel.cu); the common-edge / common-vertex cases (2-D / 3-D, reached in the
+// short-wavelength regime |k| R > pi or with SCUFF_DISABLE_CACHE) and the high-k kernels are in td_general.cu.
 #pragma once
 #include "ppi_math.cuh"
 #include "fippi_math.cuh"

@@ -67,7 +67,7 @@ static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omeg
   RWGSurface *Sa = G->Surfaces[nsa], *Sb = G->Surfaces[nsb];
   G->UpdateCachedEpsMuValues(Omega);
   G->SyncDeviceGeometry();
-  M->EnsureDevice();
+  M->PrepareDevice();            // host-side edits of other parts of M reach the device before the block is written
 
   scuffcuda_ssi_args A; memset(&A, 0, sizeof A);
   A.omega[0] = real(Omega); A.omega[1] = imag(Omega);
@@ -155,9 +155,7 @@ void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double
    ErrExit("AssembleBEMMatrixBlock: GradM / dMdT derivative blocks are not yet available on the device path");
   if (getenv("SCUFF_TBLOCK_PATH")) Warn("SCUFF_TBLOCK_PATH is ignored by the device assembly path");
   // the caller may have written into M on the host (e.g. other blocks): keep both sides coherent
-  bool fresh = (M->DeviceHandle == 0);
-  M->EnsureDevice();
-  if (fresh) M->SyncToDevice();
+  M->PrepareDevice();
   for (int i = 0; i < 5; i++) LastPPICounts[i] = 0;
   if (LBasis == 0)
    { AssembleBlockOnDevice(this, nsa, nsb, Omega, M, RowOffset, ColOffset, nsa == nsb, false, 0, false, false);
@@ -187,6 +185,7 @@ static int PipelineBlocks(int N)
 static void AssembleBEMMatrixPipelined(RWGGeometry *G, cdouble Omega, HMatrix *M, int K)
 { scuffcuda_context *ctx = GetCudaContext();
   const int N = G->TotalBFs;
+  M->DeviceStale = false;        // every entry is rewritten
   M->EnsureDevice();
   void *host = M->RealComplex == LHM_REAL ? (void *)M->DM : (void *)M->ZM;
   std::vector<int> c(K + 1);
@@ -234,7 +233,9 @@ HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *
 void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M, int ColBegin, int ColEnd)
 { scuffcuda_context *ctx = GetCudaContext();
   const bool Partial = ColEnd > 0;
-  M->EnsureDevice();
+  // a compact-geometry assembly rewrites every entry (of the owned columns): host-side edits need not be uploaded first
+  if (LBasis == 0 && !Partial) M->DeviceStale = false;
+  if (M->DeviceStale) M->SyncToDevice(); else M->EnsureDevice();
   for (int i = 0; i < 5; i++) LastPPICounts[i] = 0;
   bool MatrixIsSymmetric = (!kBloch || (kBloch[0] == 0.0 && kBloch[1] == 0.0));
   int nspStart = MatrixIsSymmetric ? 1 : 0;

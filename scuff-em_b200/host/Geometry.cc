@@ -398,7 +398,7 @@ void RWGSurface::Transform(const char *format, ...)
   GTrans D; char *Err = 0; int pos = 0;
   while (pos < NumTokens)
    { GTrans One; int used = 0; One.Parse(Tokens + pos, NumTokens - pos, &Err, &used);
-     if (Err) ErrExit(Err);
+     if (Err) ErrExit("%s", Err);
      D.Transform(&One); pos += used; }
   ApplyGT(this, &D);
 }
@@ -665,7 +665,8 @@ void RWGGeometry::UpdateCachedEpsMuValues(cdouble Omega)
 
 // "TRANS name SURFACE label DISP x y z ROT t ABOUT x y z SURFACE label2 ..."
 void RWGGeometry::Transform(const char *TransLine)
-{ char buf[MAXSTR]; strncpy(buf, TransLine, MAXSTR - 1); buf[MAXSTR - 1] = 0;
+{ if (strlen(TransLine) >= MAXSTR) ErrExit("Transform: line longer than %i characters", MAXSTR - 1);
+  char buf[MAXSTR]; strncpy(buf, TransLine, MAXSTR - 1); buf[MAXSTR - 1] = 0;
   char *Tokens[MAXTOK]; int n = Tokenize(buf, Tokens, MAXTOK);
   int pos = 0;
   if (n >= 2 && (!strcasecmp(Tokens[0], "TRANS") || !strcasecmp(Tokens[0], "TRANSFORMATION"))) pos = 2;
@@ -795,6 +796,8 @@ void RWGGeometry::SyncDeviceGeometry()
   // the device context holds ONE geometry at a time; a process-unique id (not the object address,
   // which the allocator may recycle) tells whether it is ours
   static unsigned long long deviceOwner = 0, nextId = 0;
+  static scuffcuda_context *ownerCtx = 0;
+  if (ownerCtx != ctx) { ownerCtx = ctx; deviceOwner = 0; }        // a new context (SetCudaDevice) holds no geometry yet
   if (DeviceId == 0) DeviceId = ++nextId;
   if (deviceOwner != DeviceId)
    { if (scuffcuda_set_num_surfaces(ctx, 0) || scuffcuda_set_num_surfaces(ctx, NumSurfaces)) ErrExit("%s", scuffcuda_last_error(ctx));

@@ -6,11 +6,12 @@
 #include <strings.h>
 #include "../../include/libscuff_b200.h"
 
-#define MAXSTR 1000
-#define MAXTOK 50
+#define MAXSTR 10000   /* long TRANS lines (many surfaces) must fit: the reference tolerates them */
+#define MAXTOK 1000
 
 namespace scuff {
 
+void AddLiveDeviceObject(int delta);   // bookkeeping for SetCudaDevice (util.cc)
 int Tokenize(char *s, char **Tokens, int MaxTokens, const char *Separators = " \t\r\n");
 char *vstrdup(const char *fmt, ...);
 

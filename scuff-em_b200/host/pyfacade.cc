@@ -65,6 +65,16 @@ void *scuffb200_matrix_new(int nr, int nc, int is_real) { GUARD(return (void *)n
 void scuffb200_matrix_free(void *m) { delete (HMatrix *)m; }
 void *scuffb200_matrix_data(void *m) { HMatrix *M = (HMatrix *)m; return M->RealComplex == LHM_REAL ? (void *)M->DM : (void *)M->ZM; }
 int scuffb200_matrix_shape(void *m, int *out) { HMatrix *M = (HMatrix *)m; out[0] = M->NR; out[1] = M->NC; out[2] = (M->RealComplex == LHM_REAL); return 0; }
+int scuffb200_matrix_set_entry(void *m, int r, int c, double re, double im) { GUARD(((HMatrix *)m)->SetEntry(r, c, cdouble(re, im)); return 0;, 1) }
+int scuffb200_matrix_add_entry(void *m, int r, int c, double re, double im) { GUARD(((HMatrix *)m)->AddEntry(r, c, cdouble(re, im)); return 0;, 1) }
+int scuffb200_matrix_get_entry(void *m, int r, int c, double *out) { GUARD(cdouble v = ((HMatrix *)m)->GetEntry(r, c); out[0] = real(v); out[1] = imag(v); return 0;, 1) }
+int scuffb200_matrix_zero(void *m) { GUARD(((HMatrix *)m)->Zero(); return 0;, 1) }
+int scuffb200_matrix_zero_block(void *m, int ro, int nr, int co, int nc) { GUARD(((HMatrix *)m)->ZeroBlock(ro, nr, co, nc); return 0;, 1) }
+int scuffb200_matrix_insert_block(void *m, void *b, int ro, int co, int nrb, int ncb, int bro, int bco)
+{ GUARD(((HMatrix *)m)->InsertBlock((HMatrix *)b, ro, co, nrb, ncb, bro, bco); return 0;, 1) }
+int scuffb200_matrix_mark_host_dirty(void *m) { GUARD(((HMatrix *)m)->MarkHostDirty(); return 0;, 1) }
+// state[0] = HostStale, state[1] = DeviceStale, state[2] = DeviceHandle != 0
+int scuffb200_matrix_state(void *m, int *state) { HMatrix *M = (HMatrix *)m; state[0] = M->HostStale; state[1] = M->DeviceStale; state[2] = M->DeviceHandle != 0; return 0; }
 int scuffb200_matrix_sync_host(void *m) { GUARD(((HMatrix *)m)->SyncToHost(); return 0;, 1) }
 int scuffb200_matrix_device_handle(void *m) { return ((HMatrix *)m)->DeviceHandle; }
 

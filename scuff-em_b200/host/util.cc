@@ -38,8 +38,16 @@ void Log(const char *fmt, ...)
   fprintf(f, "%s: %s\n", ts, buf); fclose(f);
 }
 
+// number of live objects that hold handles into the context (device matrices, uploaded geometries)
+static int g_liveDeviceObjects = 0;
+void AddLiveDeviceObject(int delta) { g_liveDeviceObjects += delta; }
+
 void SetCudaDevice(int device)
-{ if (g_ctx && device != g_device) { scuffcuda_destroy(g_ctx); g_ctx = 0; }
+{ if (g_ctx && device != g_device)
+   { // matrices / geometries hold handles into the old context: switching under them would leave them dangling
+     if (g_liveDeviceObjects > 0)
+      ErrExit("SetCudaDevice(%i): %i device-resident matrices/geometries are still alive on device %i; destroy them first", device, g_liveDeviceObjects, g_device);
+     scuffcuda_destroy(g_ctx); g_ctx = 0; }
   g_device = device;
 }
 
@@ -59,7 +67,8 @@ scuffcuda_context *GetCudaContext()
 int Tokenize(char *s, char **Tokens, int MaxTokens, const char *Separators)
 { int n = 0; char *save = 0;
   for (char *t = strtok_r(s, Separators, &save); t; t = strtok_r(0, Separators, &save))
-   { if (n < MaxTokens) Tokens[n] = t; n++; }
+   { if (n >= MaxTokens) ErrExit("line has more than %i tokens (near '%s')", MaxTokens, t);     // never hand back more tokens than were stored
+     Tokens[n++] = t; }
   return n;
 }
 

@@ -116,6 +116,14 @@ def host_lib():
         L.scuffb200_matrix_data.argtypes = [C.c_void_p]
         L.scuffb200_matrix_shape.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffb200_matrix_sync_host.argtypes = [C.c_void_p]
+        L.scuffb200_matrix_set_entry.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.scuffb200_matrix_add_entry.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.scuffb200_matrix_get_entry.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.scuffb200_matrix_zero.argtypes = [C.c_void_p]
+        L.scuffb200_matrix_zero_block.argtypes = [C.c_void_p] + [C.c_int] * 4
+        L.scuffb200_matrix_insert_block.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 6
+        L.scuffb200_matrix_mark_host_dirty.argtypes = [C.c_void_p]
+        L.scuffb200_matrix_state.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.scuffb200_matrix_device_handle.argtypes = [C.c_void_p]
         L.scuffb200_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int]
         L.scuffb200_assemble_columns.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int]
@@ -189,6 +197,42 @@ class HMatrix:
             buf = (C.c_double * (2 * n)).from_address(data)
             a = np.frombuffer(buf, dtype=np.complex128)
         return np.array(a.reshape(self.NC, self.NR).T)   # column-major storage; copy (the HMatrix may be freed)
+
+    def SetEntry(self, r, c, v):
+        _check(host_lib().scuffb200_matrix_set_entry(self.ptr, r, c, float(np.real(v)), float(np.imag(v))))
+
+    def AddEntry(self, r, c, v):
+        _check(host_lib().scuffb200_matrix_add_entry(self.ptr, r, c, float(np.real(v)), float(np.imag(v))))
+
+    def GetEntry(self, r, c):
+        out = (C.c_double * 2)()
+        _check(host_lib().scuffb200_matrix_get_entry(self.ptr, r, c, out))
+        return complex(out[0], out[1])
+
+    def Zero(self):
+        _check(host_lib().scuffb200_matrix_zero(self.ptr))
+
+    def ZeroBlock(self, ro, nr, co, nc):
+        _check(host_lib().scuffb200_matrix_zero_block(self.ptr, ro, nr, co, nc))
+
+    def InsertBlock(self, B, RowOffset, ColOffset, NRB=None, NCB=None, BRowOffset=0, BColOffset=0):
+        _check(host_lib().scuffb200_matrix_insert_block(self.ptr, B.ptr, RowOffset, ColOffset, B.NR if NRB is None else NRB,
+                                                         B.NC if NCB is None else NCB, BRowOffset, BColOffset))
+
+    def host_view(self):
+        """writable numpy view of the HOST array (column-major: index [col, row]); call MarkHostDirty() after writing"""
+        data = host_lib().scuffb200_matrix_data(self.ptr)
+        n = self.NR * self.NC
+        buf = (C.c_double * (n if self.is_real else 2 * n)).from_address(data)
+        return np.frombuffer(buf, dtype=np.float64 if self.is_real else np.complex128).reshape(self.NC, self.NR)
+
+    def MarkHostDirty(self):
+        _check(host_lib().scuffb200_matrix_mark_host_dirty(self.ptr))
+
+    def state(self):
+        st = (C.c_int * 3)()
+        host_lib().scuffb200_matrix_state(self.ptr, st)
+        return dict(HostStale=bool(st[0]), DeviceStale=bool(st[1]), OnDevice=bool(st[2]))
 
     @property
     def device_handle(self):
