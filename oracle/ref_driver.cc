@@ -29,7 +29,9 @@
  *        and GetGBar (value + gradient, 8 doubles per point) at the points of pts.bin into <out.bin>
  *   ref_driver ppis   <geo> <kRe> <kIm> <pairs.txt> <out.bin>    (lines: nsa npa iQa nsb npb iQb)
  *   ref_driver fippi  <geo> <pairs.txt> <out.bin>                (lines: nsa npa nsb npb)
- *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep]
+ *   ref_driver eeisample <geo> <wRe> <wIm> <npairs> <seed> <out.bin> [--repeat n] [--sweep] [--patch m] [--cache-out f]
+ *        (--patch m: after the random pairs, ALL pairs nea<=neb<m — a compact patch of the mesh, mostly near/singular pairs;
+ *         --cache-out: StoreCache after the last pass, whose values then all come from the stored records)
  *        GetEdgeEdgeInteractions (EdgeEdgeInteractions.cc:50-217) on a seeded random sample of edge pairs
  *        of surface 0 in the exterior medium (k=Omega): the per-element work of AssembleBEMMatrix on a
  *        bounded sample of a large mesh.  out.bin: records {nea, neb, Re GC0, Im GC0, Re GC1, Im GC1}.
@@ -281,18 +283,23 @@ int main(int argc, char **argv)
 
   if(!strcmp(Cmd,"eeisample"))
    { cdouble Omega(atof(argv[3]),atof(argv[4])); long NPairs=atol(argv[5]); unsigned long long Seed=strtoull(argv[6],0,10);
-     const char *Out=argv[7]; int Repeat=1;
+     const char *Out=argv[7]; int Repeat=1; long Patch=0; const char *CacheOut=0;
      bool Sweep=false;   // --sweep: pass r runs at Omega*(1+0.01 r), the frequency points of a sweep (FIPPI cache stays warm)
      for(int n=8;n<argc;n++)
       { if(!strcmp(argv[n],"--repeat")) Repeat=atoi(argv[++n]);
-        else if(!strcmp(argv[n],"--sweep")) Sweep=true; }
+        else if(!strcmp(argv[n],"--sweep")) Sweep=true;
+        else if(!strcmp(argv[n],"--patch")) Patch=atol(argv[++n]);
+        else if(!strcmp(argv[n],"--cache-out")) CacheOut=argv[++n]; }
      RWGSurface *S=G->Surfaces[0]; int NE=S->NumEdges;
+     if(Patch>NE) Patch=NE;
+     const long NRandom=NPairs; NPairs+=Patch*(Patch+1)/2;
      int *ea=(int *)malloc(NPairs*sizeof(int)), *eb=(int *)malloc(NPairs*sizeof(int));
      double *Rec=(double *)malloc(NPairs*6*sizeof(double));
      unsigned long long x=Seed*2862933555777941757ULL+3037000493ULL;   // 64-bit LCG (Knuth MMIX constants below)
-     for(long n=0;n<NPairs;n++)
+     for(long n=0;n<NRandom;n++)
       { x=x*6364136223846793005ULL+1442695040888963407ULL; ea[n]=(int)((x>>33)%(unsigned long long)NE);
         x=x*6364136223846793005ULL+1442695040888963407ULL; eb[n]=(int)((x>>33)%(unsigned long long)NE); }
+     { long n=NRandom; for(int a=0;a<Patch;a++) for(int b=a;b<Patch;b++,n++) { ea[n]=a; eb[n]=b; } }
      printf("{\"n\": %li, \"NE\": %i, \"threads\": %i, \"times\": [",NPairs,NE,omp_get_max_threads());
      for(int r=0;r<Repeat;r++)
       { cdouble OmegaR = Sweep ? Omega*(1.0+0.01*r) : Omega;
@@ -307,7 +314,8 @@ int main(int argc, char **argv)
          }
         printf("%s%.6f",r?", ":"",Now()-t0);
       }
-     printf("]}\n");
+     printf("], \"n_random\": %li, \"n_patch\": %li}\n",NRandom,NPairs-NRandom);
+     if(CacheOut) StoreCache(CacheOut);
      FILE *f=fopen(Out,"wb"); if(!f) return 1;
      fwrite(Rec,sizeof(double),6*NPairs,f); fclose(f); return 0;
    }

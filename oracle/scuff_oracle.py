@@ -294,3 +294,46 @@ def gbar_direct_sum(R, k, kbloch, lbv, exclude_inner=False, ncells=40):
             G += phi
             dG += phi * (1j * k - 1.0 / r) * X / r
     return G, dG
+
+
+def far_edge_pairs_gc0_extended(S, nea, neb, k):
+    """GC[0] = l_a l_b (H++ - H+- - H-+ + H--)[0] (EdgeEdgeInteractions.cc:154-188) of a batch of FAR edge pairs of one surface in
+    80-bit extended precision (np.longdouble), in the reference's formulation (6x6 rule, hPlus = F.F' + 4/(ik)^2): the
+    yardstick for how much of a double-precision difference is rounding noise of the ill-conditioned sum (for k h << 1 the
+    four panel-pair terms cancel to ~ (k h)^2 of their size).  Returns (GC0 [complex longdouble], far mask): entries whose
+    four panel pairs are not all far (rRel > 4) are flagged False and must be ignored.
+    S: dict with V, PVI, PC, PR, ET, EL as returned by pyscuff RWGGeometry.surface() / parse_geom_dump."""
+    LD, CLD = np.longdouble, np.clongdouble
+    nea = np.asarray(nea); neb = np.asarray(neb)
+    V = S["V"].astype(LD); T = TCR4.astype(LD)
+    ik = CLD(1j) * CLD(k)
+    c4 = CLD(4.0) / (ik * ik)
+    ET = S["ET"]
+    out = np.zeros(len(nea), dtype=CLD)
+    far = np.ones(len(nea), dtype=bool)
+    fourpi = LD(4.0) * np.arccos(LD(-1.0))
+    for sa, (ipa, iqa) in enumerate(((4, 2), (5, 3))):          # P panel / Q = iQP ; M panel / Q = iQM
+        for sb, (ipb, iqb) in enumerate(((4, 2), (5, 3))):
+            pa, pb = ET[nea, ipa], ET[neb, ipb]
+            ok = (pa >= 0) & (pb >= 0)
+            pa_, pb_ = np.where(ok, pa, 0), np.where(ok, pb, 0)
+            D = S["PC"][pa_] - S["PC"][pb_]
+            rrel = np.sqrt((D * D).sum(1)) / np.maximum(S["PR"][pa_], S["PR"][pb_])
+            far &= (~ok) | (rrel > DESING_RADIUS)
+            Qa, Qb = V[ET[nea, iqa]], V[ET[neb, iqb]]
+            Va, Vb = V[S["PVI"][pa_]], V[S["PVI"][pb_]]                      # (m,3,3)
+            A, B = Va[:, 1] - Va[:, 0], Va[:, 2] - Va[:, 0]
+            AP, BP = Vb[:, 1] - Vb[:, 0], Vb[:, 2] - Vb[:, 0]
+            X = Va[:, None, 0, :] + T[None, :, 0, None] * A[:, None, :] + T[None, :, 1, None] * B[:, None, :]      # (m,6,3)
+            XP = Vb[:, None, 0, :] + T[None, :, 0, None] * AP[:, None, :] + T[None, :, 1, None] * BP[:, None, :]
+            F, FP = X - Qa[:, None, :], XP - Qb[:, None, :]
+            R = X[:, :, None, :] - XP[:, None, :, :]
+            r = np.sqrt((R * R).sum(-1))
+            with np.errstate(divide="ignore", invalid="ignore"):
+                Phi = np.exp(ik * r.astype(CLD)) / (fourpi * r)
+            hPlus = (F[:, :, None, :] * FP[:, None, :, :]).sum(-1).astype(CLD) + c4
+            ww = (T[:, 2][:, None] * T[:, 2][None, :])[None]
+            H0 = (hPlus * Phi * ww).sum((1, 2))
+            sign = (1 if sa == 0 else -1) * (1 if sb == 0 else -1)
+            out += np.where(ok, sign * H0, 0)
+    return S["EL"][nea].astype(LD) * S["EL"][neb].astype(LD) * out, far
