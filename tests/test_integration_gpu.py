@@ -1,0 +1,89 @@
+"""The drop-in boundary, for real: the REFERENCE's own libscuff compiled with the binding of INTEGRATION.md section B
+(integration/AssembleBEMMatrixCUDA.cc + a hook in RWGGeometry::AssembleBEMMatrixBlock; oracle/Makefile target `cuda`) runs its
+block assembly through libscuff_cuda.so when SCUFF_CUDA=1.  Checked here on the B200:
+  * the reference's AssembleBEMMatrix through the hooked library against the plain reference library, on the compact
+    cases of unitTests/unit-test-BEMMatrix.cc:108-150 (PEC, dielectric, two-body with Mate reuse; real, small and imaginary
+    frequency), <= 1e-10 relative Frobenius (north_star tolerance);
+  * the reference's own scuff-scatter application (applications/scuff-scatter, built from the reference's sources against
+    the hooked library) on the tests/Mie geometry: absorbed / scattered power, force and torque equal to the CPU run's to
+    the precision the application prints.
+The binaries are built where /root/reference exists and travel to the GPU box (oracle/_ref is git-ignored, not gpurun-ignored)."""
+import os
+import subprocess
+import numpy as np
+import pytest
+from conftest import GEODIR, ROOT, rel_fro
+
+pytestmark = pytest.mark.gpu
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _need(*names):
+    for n in names:
+        if not os.path.exists(os.path.join(REFDIR, n)):
+            pytest.skip("oracle/_ref/%s not built (make -C oracle cuda where /root/reference exists)" % n)
+
+
+def _matrix(binary, geo, omega, imag, tmp, cuda):
+    out = os.path.join(tmp, ("cuda" if cuda else "cpu") + ".bin")
+    cmd = [os.path.join(REFDIR, binary), "matrix", os.path.basename(geo), repr(float(np.real(omega))), repr(float(np.imag(omega))), out]
+    if imag:
+        cmd.append("--imag")
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    env.pop("SCUFF_CUDA", None)
+    if cuda:
+        env.update(SCUFF_CUDA="1", SCUFF_CUDA_VERBOSE="1")
+    r = subprocess.run(cmd, cwd=os.path.dirname(geo), capture_output=True, text=True, env=env, stdin=subprocess.DEVNULL, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    M = np.fromfile(out, dtype=np.float64 if imag else np.complex128)
+    n = int(round(np.sqrt(M.size)))
+    return M.reshape(n, n).T, r.stderr
+
+
+CASES = [("PECSphere_255.scuffgeo", 0.01, False), ("PECSphere_255.scuffgeo", 1.0, False), ("PECSphere_255.scuffgeo", 0.1j, True),
+         ("SiSphere_255.scuffgeo", 1.0, False), ("SiSphere_255.scuffgeo", 0.1j, True), ("SiSpheres_255.scuffgeo", 0.1, False),
+         ("ZetaSphere_255.scuffgeo", 0.7, False)]
+
+
+@pytest.mark.parametrize("geo,omega,imag", CASES)
+def test_reference_library_through_the_binding(tmp_path, geo, omega, imag):
+    _need("ref_driver", "ref_driver_cuda", "libscuff_ref_cuda.so")
+    path = os.path.join(GEODIR, geo)
+    ref, _ = _matrix("ref_driver", path, omega, imag, str(tmp_path), False)
+    # the hooked library with SCUFF_CUDA unset IS the reference
+    same, _ = _matrix("ref_driver_cuda", path, omega, imag, str(tmp_path), False)
+    assert rel_fro(same, ref) <= 1e-12
+    got, log = _matrix("ref_driver_cuda", path, omega, imag, str(tmp_path), True)
+    assert "blocks assembled on the device" in log and " 0 BEM" not in log, log[-500:]
+    err = rel_fro(got, ref)
+    print(geo, omega, "reference API through libscuff_cuda: rel_fro", err, "|", log.strip().splitlines()[-1])
+    assert err <= 1e-10
+
+
+def test_scuff_scatter_through_the_binding(tmp_path):
+    """the reference's scuff-scatter on tests/Mie/LossySphere_327 at two frequencies: EMTPFT output (absorbed and scattered
+    power, force, torque) with SCUFF_CUDA=1 against the unmodified CPU run"""
+    _need("scuff-scatter", "scuff-scatter_cuda")
+    rows = {}
+    for tag, binary, cuda in (("cpu", "scuff-scatter", False), ("cuda", "scuff-scatter_cuda", True)):
+        d = tmp_path / tag; d.mkdir()
+        for f in ("LossySphere_327.scuffgeo", "Sphere_327.msh"):
+            os.symlink(os.path.join(GEODIR, f), str(d / f))
+        env = dict(os.environ, OMP_NUM_THREADS="4")
+        env.pop("SCUFF_CUDA", None)
+        if cuda:
+            env.update(SCUFF_CUDA="1", SCUFF_CUDA_VERBOSE="1")
+        cmd = [os.path.join(REFDIR, binary), "--geometry", "LossySphere_327.scuffgeo", "--Omega", "0.4", "--Omega", "1.0", "--PWDirection", "0", "0", "1",
+               "--PWPolarization", "0.70710678", "0.70710678i", "0", "--EMTPFTFile", "out.EMTPFT"]
+        # (the reference's ProcessOptions also reads options from stdin when it is not a terminal: give it an empty one)
+        r = subprocess.run(cmd, cwd=str(d), capture_output=True, text=True, env=env, stdin=subprocess.DEVNULL, timeout=300)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+        if cuda:
+            assert "blocks assembled on the device" in r.stderr and " 0 BEM" not in r.stderr, r.stderr[-500:]
+        rows[tag] = np.array([[float(x) for x in l.split()[2:]] for l in open(d / "out.EMTPFT") if not l.startswith("#")])
+    assert rows["cpu"].shape == rows["cuda"].shape and rows["cpu"].shape[0] == 2
+    scale = np.abs(rows["cpu"]).max(axis=1, keepdims=True)
+    err = np.abs(rows["cuda"] - rows["cpu"]) / scale
+    print("scuff-scatter EMTPFT (PAbs, PScat, F, T) cpu vs cuda, max deviation relative to the row's largest entry:", err.max())
+    print(rows["cpu"][1], rows["cuda"][1])
+    assert err.max() <= 2e-6          # the application prints 7 significant digits
