@@ -23,6 +23,7 @@ static int fail(scuffcuda_context *ctx, const char *fmt, ...)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 #define CKS(call) do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(ctx, "%s:%d: %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
 
+namespace scuffcuda { void far_slots_release(scuffcuda_context *ctx); }   // far_kernel.cu: window/slot tables of the staged scatter
 extern "C" {
 
 int scuffcuda_device_count(void)
@@ -59,6 +60,7 @@ int scuffcuda_create(int device, scuffcuda_context **out)
 void scuffcuda_destroy(scuffcuda_context *ctx)
 { if (!ctx) return;
   cudaSetDevice(ctx->device);
+  scuffcuda::far_slots_release(ctx);
   for (auto &s : ctx->surfaces) if (s.dpanels) cudaFree(s.dpanels);
   for (auto &m : ctx->matrices) { if (m.second.d) cudaFree(m.second.d); if (m.second.ipiv) cudaFree(m.second.ipiv); }
   for (auto &p : ctx->plans) if (p.dnear) cudaFree(p.dnear);

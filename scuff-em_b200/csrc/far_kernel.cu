@@ -21,6 +21,9 @@
 #include <stdint.h>
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <vector>
 #include "context.h"
 #include "classify.cuh"
 #include "stamp.cuh"
@@ -102,60 +105,75 @@ __device__ __forceinline__ void helm_fast<KMODE_CPLX, true, cd>(double r2, doubl
 // |delta| <= R_a + R_b.  When |k| (R_a + R_b) <= 1/8 for all panels (the launcher checks), exp(ik r) = exp(ik r0) exp(ik delta):
 // the pair factor is applied ONCE to the accumulated moments (they are linear in Phi and Psi), and exp(ik delta) needs no
 // range reduction, no quadrant logic and only degree-9/10 Taylor polynomials (truncation < 3e-18 at |t| <= 1/8).
-template <int KMODE, bool PSI, typename S>
-__device__ __forceinline__ void helm_small(double r2, double cw, const KParams &K, double r0, S &Phi, S &Psi);
+template <int KMODE, bool PSI, int DEG, typename S> struct HelmSmall;
 
+// DEG = 1: |t| <= 1/8 (sin to t^9, cos to t^10; truncation < 3e-18), DEG = 2: |t| <= 1/16 (sin to t^7, cos to t^8; < 4e-17)
+template <int DEG>
 __device__ __forceinline__ void sincos_small(double t, double &s, double &c)
 { const double z = t * t;
-  double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);       // 1/9!, -1/7!
-  ps = fma(z, ps, 8.3333333333333332e-03); ps = fma(z, ps, -1.6666666666666666e-01);
-  s = fma(t * z, ps, t);
-  double pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);        // -1/10!, 1/8!
-  pc = fma(z, pc, -1.3888888888888889e-03); pc = fma(z, pc, 4.1666666666666664e-02); pc = fma(z, pc, -0.5);
-  c = fma(z, pc, 1.0);
+  if (DEG == 1)
+   { double ps = fma(z, 2.7557319223985893e-06, -1.9841269841269841e-04);       // 1/9!, -1/7!
+     ps = fma(z, ps, 8.3333333333333332e-03); ps = fma(z, ps, -1.6666666666666666e-01);
+     s = fma(t * z, ps, t);
+     double pc = fma(z, -2.7557319223985888e-07, 2.4801587301587302e-05);        // -1/10!, 1/8!
+     pc = fma(z, pc, -1.3888888888888889e-03); pc = fma(z, pc, 4.1666666666666664e-02); pc = fma(z, pc, -0.5);
+     c = fma(z, pc, 1.0); }
+  else
+   { double ps = fma(z, -1.9841269841269841e-04, 8.3333333333333332e-03);        // -1/7!, 1/5!
+     ps = fma(z, ps, -1.6666666666666666e-01);
+     s = fma(t * z, ps, t);
+     double pc = fma(z, 2.4801587301587302e-05, -1.3888888888888889e-03);        // 1/8!, -1/6!
+     pc = fma(z, pc, 4.1666666666666664e-02); pc = fma(z, pc, -0.5);
+     c = fma(z, pc, 1.0); }
 }
-__device__ __forceinline__ double exp_small(double s)                          // |s| <= 1/8, Taylor to s^10
-{ double p = 2.7557319223985888e-07;
-  p = fma(p, s, 2.7557319223985893e-06); p = fma(p, s, 2.4801587301587302e-05); p = fma(p, s, 1.9841269841269841e-04);
+template <int DEG>
+__device__ __forceinline__ double exp_small(double s)                          // DEG 1: |s| <= 1/8, Taylor to s^10; DEG 2: |s| <= 1/16, to s^8
+{ double p;
+  if (DEG == 1)
+   { p = 2.7557319223985888e-07;
+     p = fma(p, s, 2.7557319223985893e-06); p = fma(p, s, 2.4801587301587302e-05); }
+  else p = 2.4801587301587302e-05;
+  p = fma(p, s, 1.9841269841269841e-04);
   p = fma(p, s, 1.3888888888888889e-03); p = fma(p, s, 8.3333333333333332e-03); p = fma(p, s, 4.1666666666666664e-02);
   p = fma(p, s, 1.6666666666666666e-01); p = fma(p, s, 0.5); p = fma(p, s, 1.0);
   return fma(p, s, 1.0);
 }
-template <>
-__device__ __forceinline__ void helm_small<KMODE_REAL, false, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
-{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
-  double s, c; sincos_small(K.kr * (r - r0), s, c);
+template <int DEG> struct HelmSmall<KMODE_REAL, false, DEG, cd>
+{ static __device__ __forceinline__ void eval(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+  { const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  double s, c; sincos_small<DEG>(K.kr * (r - r0), s, c);
   const double f = cw * rinv;
   Phi = mk(f * c, f * s);
-}
-template <>
-__device__ __forceinline__ void helm_small<KMODE_REAL, true, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
-{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
-  double s, c; sincos_small(K.kr * (r - r0), s, c);
+  } };
+template <int DEG> struct HelmSmall<KMODE_REAL, true, DEG, cd>
+{ static __device__ __forceinline__ void eval(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+  { const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  double s, c; sincos_small<DEG>(K.kr * (r - r0), s, c);
   const double f = cw * rinv;
   Phi = mk(f * c, f * s);
   const double a = -rinv * rinv, b = K.kr * rinv;
   Psi = mk(fma(Phi.x, a, -Phi.y * b), fma(Phi.x, b, Phi.y * a));
-}
-template <>
-__device__ __forceinline__ void helm_small<KMODE_IMAG, false, double>(double r2, double cw, const KParams &K, double r0, double &Phi, double &Psi)
-{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
-  Phi = cw * rinv * exp_small(-K.ki * (r - r0));
-}
-template <>
-__device__ __forceinline__ void helm_small<KMODE_IMAG, true, double>(double r2, double cw, const KParams &K, double r0, double &Phi, double &Psi)
-{ const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
-  Phi = cw * rinv * exp_small(-K.ki * (r - r0));
+  } };
+template <int DEG> struct HelmSmall<KMODE_IMAG, false, DEG, double>
+{ static __device__ __forceinline__ void eval(double r2, double cw, const KParams &K, double r0, double &Phi, double &Psi)
+  { const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  Phi = cw * rinv * exp_small<DEG>(-K.ki * (r - r0));
+  } };
+template <int DEG> struct HelmSmall<KMODE_IMAG, true, DEG, double>
+{ static __device__ __forceinline__ void eval(double r2, double cw, const KParams &K, double r0, double &Phi, double &Psi)
+  { const double rinv = rsqrt_fast<false>(r2), r = r2 * rinv;
+  Phi = cw * rinv * exp_small<DEG>(-K.ki * (r - r0));
   Psi = Phi * (-K.ki - rinv) * rinv;
-}
+  } };
 // general complex k never takes the small-phase path (the launcher does not select it)
-template <>
-__device__ __forceinline__ void helm_small<KMODE_CPLX, false, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
-{ helm_fast<KMODE_CPLX, false, cd>(r2, cw, K, Phi, Psi); }
-template <>
-__device__ __forceinline__ void helm_small<KMODE_CPLX, true, cd>(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
-{ helm_fast<KMODE_CPLX, true, cd>(r2, cw, K, Phi, Psi); }
+template <int DEG> struct HelmSmall<KMODE_CPLX, false, DEG, cd>
+{ static __device__ __forceinline__ void eval(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+  { helm_fast<KMODE_CPLX, false, cd>(r2, cw, K, Phi, Psi); } };
+template <int DEG> struct HelmSmall<KMODE_CPLX, true, DEG, cd>
+{ static __device__ __forceinline__ void eval(double r2, double cw, const KParams &K, double r0, cd &Phi, cd &Psi)
+  { helm_fast<KMODE_CPLX, true, cd>(r2, cw, K, Phi, Psi); } };
 
+// (the small-phase pair factor)
 __device__ __forceinline__ void smul(double &a, double f) { a *= f; }
 __device__ __forceinline__ void smul(cd &a, cd f) { a = mk(fma(a.x, f.x, -a.y * f.y), fma(a.x, f.y, a.y * f.x)); }
 
@@ -195,12 +213,22 @@ __device__ __forceinline__ void contract_scatter(const S (&mPhi)[3][3], const S 
 #pragma unroll
   for (int m = 0; m < 3; m++) E00[m] = Va0[m] - Vb0[m];
   const double dAA = dot3(Aa, Ab), dAB = dot3(Aa, Bb), dBA = dot3(Ba, Ab), dBB = dot3(Ba, Bb);
-  // rows of the a-side shifted moments: row 1 ~ (u - [i==1]), row 2 ~ (v - [i==2])
-  S r1s[3], r2s[3], q1s[3], q2s[3];
+  // H0_ij = sum_{al,be} d_{al be} <(x_al - [i==al]) (y_be - [j==be]) Phi> + c4 <Phi>
+  //       = T - [j>0] P_j - [i>0] Q_i + [i>0][j>0] d_ij m00 + c4 m00 ,   T = sum d_{al be} m_{al be} (common to all nine),
+  //         P_j = sum_al d_{al j} m_{al 0} ,  Q_i = sum_be d_{i be} m_{0 be}
+  S T0, P1, P2, Q1, Q2;
+  szero(T0); szero(P1); szero(P2); szero(Q1); szero(Q2);
+  fma_acc(T0, dAA, mPhi[1][1]); fma_acc(T0, dAB, mPhi[1][2]); fma_acc(T0, dBA, mPhi[2][1]); fma_acc(T0, dBB, mPhi[2][2]);
+  fma_acc(P1, dAA, mPhi[1][0]); fma_acc(P1, dBA, mPhi[2][0]);
+  fma_acc(P2, dAB, mPhi[1][0]); fma_acc(P2, dBB, mPhi[2][0]);
+  fma_acc(Q1, dAA, mPhi[0][1]); fma_acc(Q1, dAB, mPhi[0][2]);
+  fma_acc(Q2, dBA, mPhi[0][1]); fma_acc(Q2, dBB, mPhi[0][2]);
+  // rows of the a-side shifted Psi moments: row 1 ~ (u - [i==1]), row 2 ~ (v - [i==2])
+  S q1s[3], q2s[3];
+  if (PSI)
+   {
 #pragma unroll
-  for (int n = 0; n < 3; n++)
-   { r1s[n] = ssub(mPhi[1][n], mPhi[0][n]); r2s[n] = ssub(mPhi[2][n], mPhi[0][n]);
-     if (PSI) { q1s[n] = ssub(mPsi[1][n], mPsi[0][n]); q2s[n] = ssub(mPsi[2][n], mPsi[0][n]); } }
+     for (int n = 0; n < 3; n++) { q1s[n] = ssub(mPsi[1][n], mPsi[0][n]); q2s[n] = ssub(mPsi[2][n], mPsi[0][n]); } }
   const cd c4m = K.c4 * tocd(mPhi[0][0]);
   // triple products for H1
   double tAA = 0, tAB = 0, tBA = 0, tBB = 0, AbN = 0, BbN = 0, AaNp = 0, BaNp = 0;
@@ -211,21 +239,63 @@ __device__ __forceinline__ void contract_scatter(const S (&mPhi)[3][3], const S 
      tAA = dot3(Ab, eA); tAB = dot3(Bb, eA); tBA = dot3(Ab, eB); tBB = dot3(Bb, eB);
      AbN = dot3(Ab, Na); BbN = dot3(Bb, Na); AaNp = dot3(Aa, Nb); BaNp = dot3(Ba, Nb); }
 
+  if (!PSI)
+   { // PEC/PEC blocks (one entry per edge pair, SurfaceSurfaceInteractions.cc:205-217).  Two phases: first ALL nine values and
+     // addresses into their own registers, then the atomics back to back.  Interleaving value computation and RED made every
+     // entry wait for the previous RED to release its operand registers (ncu: half of all stall samples were scoreboard
+     // waits in this epilogue, the kernel time did not move when the cubature loop lost 27 % of its instructions).
+     cd val[9]; long idx[9];
+#pragma unroll
+     for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+       { const int n = 3 * i + j;
+         int ea = eia[i], eb = eib[j];
+         idx[n] = -1;
+         S h0 = T0;
+         if (j == 1) h0 = ssub(h0, P1); else if (j == 2) h0 = ssub(h0, P2);
+         if (i == 1) h0 = ssub(h0, Q1); else if (i == 2) h0 = ssub(h0, Q2);
+         if (i > 0 && j > 0) fma_acc(h0, (i == 1) ? (j == 1 ? dAA : dAB) : (j == 1 ? dBA : dBB), mPhi[0][0]);
+         double sc = sla3[i] * slb[j];
+         bool ok = (ea >= 0 && eb >= 0);
+         if (SP.symmetric)
+          { if (pa == pb) ok = ok && (ea <= eb);
+            else if (ea == eb) sc *= 2.0;
+            else if (ea > eb) { const int t = ea; ea = eb; eb = t; } }
+         const int col = SP.colOff + eb;
+         ok = ok && col >= SP.colLo && col < SP.colHi;
+         val[n] = SP.c1 * (sc * (tocd(h0) + c4m));
+         if (ok) { idx[n] = (long)(SP.rowOff + ea) + (long)col * SP.ld; nPPI += (symmetric && pa != pb && eia[i] == eib[j]) ? 2 : 1; } }
+     // materialise the nine addresses in nine register pairs BEFORE the first RED (the compiler otherwise recomputes each address
+     // into the same pair just in time, which serialises the REDs on that pair)
+     double *ptr[9];
+#pragma unroll
+     for (int n = 0; n < 9; n++) ptr[n] = SP.M + (SP.isReal ? 1 : 2) * (idx[n] >= 0 ? idx[n] : 0);
+     asm volatile("" : "+l"(ptr[0]), "+l"(ptr[1]), "+l"(ptr[2]), "+l"(ptr[3]), "+l"(ptr[4]), "+l"(ptr[5]), "+l"(ptr[6]), "+l"(ptr[7]), "+l"(ptr[8]));
+     asm volatile("" : "+d"(val[0].x), "+d"(val[1].x), "+d"(val[2].x), "+d"(val[3].x), "+d"(val[4].x), "+d"(val[5].x), "+d"(val[6].x), "+d"(val[7].x), "+d"(val[8].x));
+     if (SP.isReal)
+      {
+#pragma unroll
+        for (int n = 0; n < 9; n++) if (idx[n] >= 0) atomicAdd(ptr[n], val[n].x); }
+     else
+      { asm volatile("" : "+d"(val[0].y), "+d"(val[1].y), "+d"(val[2].y), "+d"(val[3].y), "+d"(val[4].y), "+d"(val[5].y), "+d"(val[6].y), "+d"(val[7].y), "+d"(val[8].y));
+#pragma unroll
+        for (int n = 0; n < 9; n++) if (idx[n] >= 0) { atomicAdd(ptr[n], val[n].x); atomicAdd(ptr[n] + 1, val[n].y); } }
+     return; }
+
 #pragma unroll
   for (int i = 0; i < 3; i++)
    { const int ea = eia[i];
      if (ea < 0) continue;
      const double sla = sla3[i];
-     const S *U = (i == 1) ? r1s : mPhi[1], *V = (i == 2) ? r2s : mPhi[2];
      const S *UQ = (i == 1) ? q1s : mPsi[1], *VQ = (i == 2) ? q2s : mPsi[2];
 #pragma unroll
      for (int j = 0; j < 3; j++)
       { if (eib[j] < 0) continue;
-        // b-side shift: column 1 ~ (u' - [j==1]), column 2 ~ (v' - [j==2])
-        const S Uu = (j == 1) ? ssub(U[1], U[0]) : U[1], Uv = (j == 2) ? ssub(U[2], U[0]) : U[2];
-        const S Vu = (j == 1) ? ssub(V[1], V[0]) : V[1], Vv = (j == 2) ? ssub(V[2], V[0]) : V[2];
-        S h0; szero(h0);
-        fma_acc(h0, dAA, Uu); fma_acc(h0, dAB, Uv); fma_acc(h0, dBA, Vu); fma_acc(h0, dBB, Vv);
+        S h0 = T0;
+        if (j == 1) h0 = ssub(h0, P1); else if (j == 2) h0 = ssub(h0, P2);
+        if (i == 1) h0 = ssub(h0, Q1); else if (i == 2) h0 = ssub(h0, Q2);
+        if (i > 0 && j > 0) fma_acc(h0, (i == 1) ? (j == 1 ? dAA : dAB) : (j == 1 ? dBA : dBB), mPhi[0][0]);
         cd H0 = tocd(h0) + c4m, H1 = mk(0.0, 0.0);
         if (PSI)
          { const S Pu = (j == 1) ? ssub(UQ[1], UQ[0]) : UQ[1], Pv = (j == 2) ? ssub(UQ[2], UQ[0]) : UQ[2];
@@ -261,13 +331,81 @@ __device__ __forceinline__ bool pair_is_far(const double *Ca, double Ra, const d
   return sqrt(r2) / Rm > SCUFF_DESING_RADIUS;
 }
 
+// ---- 3x3 barycentric moments of one far panel pair: m[m over a (outer loop: this lane's points, thread-private shared-memory
+//      column sXa)][n over b (inner loop: the tile panel's points Pb, broadcast shared-memory reads)] ----
+template <int KMODE, bool PSI, int SMALL, typename S>
+__device__ __forceinline__ void far_moments(const double *sXa, const double *Pb, const double (&D)[3], const KParams &K, double r0,
+                                            S (&mPhi)[3][3], S (&mPsi)[3][3])
+{
+     // ---- 3x3 barycentric moments m[m over a (outer loop: this lane's points)][n over b (inner loop: tile panel's points,
+     //      broadcast shared-memory reads)] ----
+#pragma unroll
+     for (int m = 0; m < 3; m++)
+#pragma unroll
+      for (int n = 0; n < 3; n++) { szero(mPhi[m][n]); szero(mPsi[m][n]); }
+
+#pragma unroll 1
+     for (int p = 0; p < 6; p += 2)
+      { // two outer points per iteration share the broadcast loads of the tile panel's points and give the scheduler two
+        // independent dependency chains per inner point.  R = X_a - X_b = (x_a(lane) + D) - x_b(tile)
+        const double y0 = sXa[(3 * p) * FAR_THREADS] + D[0], y1 = sXa[(3 * p + 1) * FAR_THREADS] + D[1], y2 = sXa[(3 * p + 2) * FAR_THREADS] + D[2];
+        const double z0 = sXa[(3 * p + 3) * FAR_THREADS] + D[0], z1 = sXa[(3 * p + 4) * FAR_THREADS] + D[1], z2 = sXa[(3 * p + 5) * FAR_THREADS] + D[2];
+        S a0_, au, av, b0_, bu, bv, c0_, cu, cv, d0_, du, dv;
+        szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
+        szero(c0_); szero(cu); szero(cv); szero(d0_); szero(du); szero(dv);
+#pragma unroll
+        for (int pp = 0; pp < 6; pp++)
+         { const double xb0 = Pb[13 + 3 * pp], xb1 = Pb[14 + 3 * pp], xb2 = Pb[15 + 3 * pp];
+           const double R0 = y0 - xb0, R1 = y1 - xb1, R2 = y2 - xb2;
+           const double Q0 = z0 - xb0, Q1 = z1 - xb1, Q2 = z2 - xb2;
+           const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
+           const double q2 = fma(Q2, Q2, fma(Q1, Q1, Q0 * Q0));
+           S Phi, Psi, Phj, Psj;
+           if (SMALL) { HelmSmall<KMODE, PSI, (SMALL > 0 ? SMALL : 1), S>::eval(r2, SCUFF_OO4PI * tcr_w(pp), K, r0, Phi, Psi);
+                        HelmSmall<KMODE, PSI, (SMALL > 0 ? SMALL : 1), S>::eval(q2, SCUFF_OO4PI * tcr_w(pp), K, r0, Phj, Psj); }
+           else { helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), K, Phi, Psi);
+                  helm_fast<KMODE, PSI, S>(q2, SCUFF_OO4PI * tcr_w(pp), K, Phj, Psj); }
+           sadd(a0_, Phi); fma_acc(au, tcr_u(pp), Phi); fma_acc(av, tcr_v(pp), Phi);
+           sadd(c0_, Phj); fma_acc(cu, tcr_u(pp), Phj); fma_acc(cv, tcr_v(pp), Phj);
+           if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi);
+                      sadd(d0_, Psj); fma_acc(du, tcr_u(pp), Psj); fma_acc(dv, tcr_v(pp), Psj); }
+         }
+        { const double w0 = c_far_wm[p][0], w1 = c_far_wm[p][1], w2 = c_far_wm[p][2];
+          fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
+          fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
+          fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
+          if (PSI)
+           { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
+             fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
+             fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); } }
+        { const double w0 = c_far_wm[p + 1][0], w1 = c_far_wm[p + 1][1], w2 = c_far_wm[p + 1][2];
+          fma_acc(mPhi[0][0], w0, c0_); fma_acc(mPhi[0][1], w0, cu); fma_acc(mPhi[0][2], w0, cv);
+          fma_acc(mPhi[1][0], w1, c0_); fma_acc(mPhi[1][1], w1, cu); fma_acc(mPhi[1][2], w1, cv);
+          fma_acc(mPhi[2][0], w2, c0_); fma_acc(mPhi[2][1], w2, cu); fma_acc(mPhi[2][2], w2, cv);
+          if (PSI)
+           { fma_acc(mPsi[0][0], w0, d0_); fma_acc(mPsi[0][1], w0, du); fma_acc(mPsi[0][2], w0, dv);
+             fma_acc(mPsi[1][0], w1, d0_); fma_acc(mPsi[1][1], w1, du); fma_acc(mPsi[1][2], w1, dv);
+             fma_acc(mPsi[2][0], w2, d0_); fma_acc(mPsi[2][1], w2, du); fma_acc(mPsi[2][2], w2, dv); } }
+      }
+
+}
+
+// the small-phase pair factor exp(ik r0)
+template <int KMODE, typename S>
+__device__ __forceinline__ S far_pair_factor(const KParams &K, double r0)
+{ S E0;
+  if (KMODE == KMODE_IMAG) { const double e = exp_neg_fast(-K.ki * r0); E0 = *reinterpret_cast<const S *>(&e); }
+  else { double s0, c0; sincos_fast(K.kr * r0, s0, c0); const cd e = mk(c0, s0); E0 = *reinterpret_cast<const S *>(&e); }
+  return E0;
+}
+
 // shared-memory layout (doubles): b-tile [TB][36] | lane (a) cubature points [18][128] | lane stash [16][128] | lane edge ids (int)[3][128]
 #define FAR_SMEM_BYTES(TA) ((size_t)((TA) * 36 + 34 * FAR_THREADS) * sizeof(double) + 6 * FAR_THREADS * sizeof(int))
 
 // Thread mapping: lane <-> a-panel (matrix ROW side), tile <-> b-panels (column side).  The matrix is column-major, so
 // the RED.ADD.F64 of one warp for entry (e_a(lane), e_b) go to neighbouring rows of ONE column (edges of consecutive
 // panels are nearly consecutive) instead of 32 different columns: ~4-8x fewer L2 atomic sectors per warp instruction.
-template <int KMODE, bool PSI, int MINB, bool SMALL>
+template <int KMODE, bool PSI, int MINB, int SMALL>
 __global__ void __launch_bounds__(FAR_THREADS, MINB)
 far_kernel(const __grid_constant__ FarArgs A)
 { extern __shared__ __align__(128) double sm[];
@@ -340,63 +478,11 @@ far_kernel(const __grid_constant__ FarArgs A)
 
      double r0 = 0.0;
      if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
-     // ---- 3x3 barycentric moments m[m over a (outer loop: this lane's points)][n over b (inner loop: tile panel's points,
-     //      broadcast shared-memory reads)] ----
      S mPhi[3][3], mPsi[3][3];
-#pragma unroll
-     for (int m = 0; m < 3; m++)
-#pragma unroll
-      for (int n = 0; n < 3; n++) { szero(mPhi[m][n]); szero(mPsi[m][n]); }
-
-#pragma unroll 1
-     for (int p = 0; p < 6; p += 2)
-      { // two outer points per iteration share the broadcast loads of the tile panel's points and give the scheduler two
-        // independent dependency chains per inner point.  R = X_a - X_b = (x_a(lane) + D) - x_b(tile)
-        const double y0 = sXa[(3 * p) * FAR_THREADS] + D[0], y1 = sXa[(3 * p + 1) * FAR_THREADS] + D[1], y2 = sXa[(3 * p + 2) * FAR_THREADS] + D[2];
-        const double z0 = sXa[(3 * p + 3) * FAR_THREADS] + D[0], z1 = sXa[(3 * p + 4) * FAR_THREADS] + D[1], z2 = sXa[(3 * p + 5) * FAR_THREADS] + D[2];
-        S a0_, au, av, b0_, bu, bv, c0_, cu, cv, d0_, du, dv;
-        szero(a0_); szero(au); szero(av); szero(b0_); szero(bu); szero(bv);
-        szero(c0_); szero(cu); szero(cv); szero(d0_); szero(du); szero(dv);
-#pragma unroll
-        for (int pp = 0; pp < 6; pp++)
-         { const double xb0 = Pb[13 + 3 * pp], xb1 = Pb[14 + 3 * pp], xb2 = Pb[15 + 3 * pp];
-           const double R0 = y0 - xb0, R1 = y1 - xb1, R2 = y2 - xb2;
-           const double Q0 = z0 - xb0, Q1 = z1 - xb1, Q2 = z2 - xb2;
-           const double r2 = fma(R2, R2, fma(R1, R1, R0 * R0));
-           const double q2 = fma(Q2, Q2, fma(Q1, Q1, Q0 * Q0));
-           S Phi, Psi, Phj, Psj;
-           if (SMALL) { helm_small<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, r0, Phi, Psi);
-                        helm_small<KMODE, PSI, S>(q2, SCUFF_OO4PI * tcr_w(pp), A.K, r0, Phj, Psj); }
-           else { helm_fast<KMODE, PSI, S>(r2, SCUFF_OO4PI * tcr_w(pp), A.K, Phi, Psi);
-                  helm_fast<KMODE, PSI, S>(q2, SCUFF_OO4PI * tcr_w(pp), A.K, Phj, Psj); }
-           sadd(a0_, Phi); fma_acc(au, tcr_u(pp), Phi); fma_acc(av, tcr_v(pp), Phi);
-           sadd(c0_, Phj); fma_acc(cu, tcr_u(pp), Phj); fma_acc(cv, tcr_v(pp), Phj);
-           if (PSI) { sadd(b0_, Psi); fma_acc(bu, tcr_u(pp), Psi); fma_acc(bv, tcr_v(pp), Psi);
-                      sadd(d0_, Psj); fma_acc(du, tcr_u(pp), Psj); fma_acc(dv, tcr_v(pp), Psj); }
-         }
-        { const double w0 = c_far_wm[p][0], w1 = c_far_wm[p][1], w2 = c_far_wm[p][2];
-          fma_acc(mPhi[0][0], w0, a0_); fma_acc(mPhi[0][1], w0, au); fma_acc(mPhi[0][2], w0, av);
-          fma_acc(mPhi[1][0], w1, a0_); fma_acc(mPhi[1][1], w1, au); fma_acc(mPhi[1][2], w1, av);
-          fma_acc(mPhi[2][0], w2, a0_); fma_acc(mPhi[2][1], w2, au); fma_acc(mPhi[2][2], w2, av);
-          if (PSI)
-           { fma_acc(mPsi[0][0], w0, b0_); fma_acc(mPsi[0][1], w0, bu); fma_acc(mPsi[0][2], w0, bv);
-             fma_acc(mPsi[1][0], w1, b0_); fma_acc(mPsi[1][1], w1, bu); fma_acc(mPsi[1][2], w1, bv);
-             fma_acc(mPsi[2][0], w2, b0_); fma_acc(mPsi[2][1], w2, bu); fma_acc(mPsi[2][2], w2, bv); } }
-        { const double w0 = c_far_wm[p + 1][0], w1 = c_far_wm[p + 1][1], w2 = c_far_wm[p + 1][2];
-          fma_acc(mPhi[0][0], w0, c0_); fma_acc(mPhi[0][1], w0, cu); fma_acc(mPhi[0][2], w0, cv);
-          fma_acc(mPhi[1][0], w1, c0_); fma_acc(mPhi[1][1], w1, cu); fma_acc(mPhi[1][2], w1, cv);
-          fma_acc(mPhi[2][0], w2, c0_); fma_acc(mPhi[2][1], w2, cu); fma_acc(mPhi[2][2], w2, cv);
-          if (PSI)
-           { fma_acc(mPsi[0][0], w0, d0_); fma_acc(mPsi[0][1], w0, du); fma_acc(mPsi[0][2], w0, dv);
-             fma_acc(mPsi[1][0], w1, d0_); fma_acc(mPsi[1][1], w1, du); fma_acc(mPsi[1][2], w1, dv);
-             fma_acc(mPsi[2][0], w2, d0_); fma_acc(mPsi[2][1], w2, du); fma_acc(mPsi[2][2], w2, dv); } }
-      }
-
+     far_moments<KMODE, PSI, SMALL, S>(sXa, Pb, D, A.K, r0, mPhi, mPsi);
      if (SMALL)
       { // the pair factor exp(ik r0), once for all moments
-        S E0;
-        if (KMODE == KMODE_IMAG) { const double e = exp_neg_fast(-A.K.ki * r0); E0 = *reinterpret_cast<const S *>(&e); }
-        else { double s0, c0; sincos_fast(A.K.kr * r0, s0, c0); const cd e = mk(c0, s0); E0 = *reinterpret_cast<const S *>(&e); }
+        const S E0 = far_pair_factor<KMODE, S>(A.K, r0);
 #pragma unroll
         for (int m = 0; m < 3; m++)
 #pragma unroll
@@ -417,6 +503,279 @@ far_kernel(const __grid_constant__ FarArgs A)
        sCnt[FAR_THREADS] += (unsigned int)nPPI;
      }
    }
+  // algorithm counters (reference log line SurfaceSurfaceInteractions.cc:550-558)
+  if (sCnt[FAR_THREADS]) atomicAdd(A.counters, (unsigned long long)sCnt[FAR_THREADS]);
+  if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Staged scatter for PEC/PEC blocks.  Round-1 profile: the nine complex RED.ADD.F64 pairs per panel pair (1.64 G scalar
+// atomics at N = 20 280) occupy the LSU for as long as the cubature occupies the FP64 pipe (measured alone: 8.4 ms,
+// tools/probes/bulkred_probe.cu), and the shared-memory loads of the cubature loop queue behind them, so the two phases
+// did not overlap.  Here a warp (32 consecutive a-panels x one b-panel) first adds its <= 96 x 3 contributions inside a
+// dense shared-memory window [rows rowLo .. rowLo+span) x [3 columns = the b-panel's edges]: the edges of 32 consecutive
+// panels lie within ~60-90 consecutive matrix rows (the reference numbers an edge when it meets it the second time,
+// InitEdgeList.cc:129-204), and the two panels of an interior edge that sit in the same warp are summed there.  One lane then
+// sends each column of the window with ONE bulk reduction (cp.reduce.async.bulk .add.f64, SASS UBLKRED: the TMA unit
+// streams the window to the L2 atomic units; nothing goes through the LSU).  Edges outside the window (5 % of the
+// slots), columns at the diagonal of a symmetric block (where the (min,max) swap applies) and pruned columns keep the scalar
+// RED path.  The window of every 32-panel group and the slot of every (panel, edge) are computed once per surface on the
+// host (far_slots()).
+// ------------------------------------------------------------------------------------------------------------------
+#define FAR_SPAN 96
+#define FAR_SLOT_SECOND 0x4000   /* the other panel of this edge sits in a lower lane of the same warp: add to its value */
+#define FAR_SLOT_NONE (-1)       /* exterior edge: no basis function */
+#define FAR_SLOT_OUTLIER (-2)    /* edge outside the warp's window: scalar RED */
+#define FAR_STAGE_BYTES 4736     /* per warp: complex 3 x 96 x 16 = 4608 B; real 2 parities x 3 x 98 x 8 = 4704 B */
+struct __align__(16) FarSlot { short s[3]; short span; int rowLo; int pad; };
+struct FarArgsX { FarArgs A; const FarSlot *slots; long nElem; };
+
+__device__ __forceinline__ void bulk_red_f64(double *dst, const void *srcSmem, uint32_t bytes)
+{ asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+               ::"l"(dst), "r"(smem_u32(srcSmem)), "r"(bytes) : "memory"); }
+
+__device__ __forceinline__ cd cscale(cd c, double a) { return mk(c.x * a, c.y * a); }
+__device__ __forceinline__ cd cscale(cd c, cd a) { return c * a; }
+
+// the nine PEC/PEC values  c1 l_a l_b [ <(F.F') Phi> + 4/(ik)^2 <Phi> ]  from the 3x3 moments:
+//   H0_ij = T - [j>0] P_j - [i>0] Q_i + [i>0][j>0] d_ij m00 + c4 m00 ,  T = sum_{al,be} d_{al be} m_{al be} (common to all nine),
+//   P_j = sum_al d_{al j} m_{al 0} ,  Q_i = sum_be d_{i be} m_{0 be} ,  d = {A,B}.{A',B'}
+template <typename S>
+__device__ __forceinline__ void contract_pec(const S (&m)[3][3], const double *Aa, const double *Ba, const double *Ab, const double *Bb,
+                                             const double *sla, const double *slb, cd c1, cd c4, cd (&val)[9])
+{ const double dAA = dot3(Aa, Ab), dAB = dot3(Aa, Bb), dBA = dot3(Ba, Ab), dBB = dot3(Ba, Bb);
+  S T0, P1, P2, Q1, Q2;
+  szero(T0); szero(P1); szero(P2); szero(Q1); szero(Q2);
+  fma_acc(T0, dAA, m[1][1]); fma_acc(T0, dAB, m[1][2]); fma_acc(T0, dBA, m[2][1]); fma_acc(T0, dBB, m[2][2]);
+  fma_acc(P1, dAA, m[1][0]); fma_acc(P1, dBA, m[2][0]);
+  fma_acc(P2, dAB, m[1][0]); fma_acc(P2, dBB, m[2][0]);
+  fma_acc(Q1, dAA, m[0][1]); fma_acc(Q1, dAB, m[0][2]);
+  fma_acc(Q2, dBA, m[0][1]); fma_acc(Q2, dBB, m[0][2]);
+  const cd m00 = cscale(c1, m[0][0]);
+  const cd cT = cscale(c1, T0) + c4 * m00;
+  const cd cP1 = cscale(c1, P1), cP2 = cscale(c1, P2), cQ1 = cscale(c1, Q1), cQ2 = cscale(c1, Q2);
+  const cd TP[3] = { cT, cT - cP1, cT - cP2 };
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+   for (int j = 0; j < 3; j++)
+    { cd h = TP[j];
+      if (i > 0)
+       { h = h - (i == 1 ? cQ1 : cQ2);
+         if (j > 0) { const double d = (i == 1) ? (j == 1 ? dAA : dAB) : (j == 1 ? dBA : dBB); h.x = fma(d, m00.x, h.x); h.y = fma(d, m00.y, h.y); } }
+      val[3 * i + j] = (sla[i] * slb[j]) * h; }
+}
+
+#define FAR_STAGED_SMEM_BYTES(TA) (FAR_SMEM_BYTES(TA) + (FAR_THREADS / 32) * FAR_STAGE_BYTES)
+
+template <int KMODE, int SMALL>
+__global__ void __launch_bounds__(FAR_THREADS, 3)
+far_staged_kernel(const __grid_constant__ FarArgsX X)
+{ const FarArgs &A = X.A;
+  extern __shared__ __align__(128) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  typedef typename KScalar<KMODE>::type S;
+  const int TB = A.TA;
+  const int b0 = blockIdx.y * TB;
+  const int aBase = blockIdx.x * FAR_THREADS;
+  const int nB = min(TB, A.NPb - b0);
+  if (A.symmetric && b0 + nB - 1 < aBase) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double *sXa = sm + TB * 36 + tid;                    // element k at sXa[k * FAR_THREADS]
+  double *sSt = sm + TB * 36 + 18 * FAR_THREADS + tid;
+  int *sEi = (int *)(sm + TB * 36 + 34 * FAR_THREADS) + tid;
+  unsigned int *sCnt = (unsigned int *)sEi + 3 * FAR_THREADS;
+  char *stage = (char *)(sm + TB * 36 + 34 * FAR_THREADS) + 6 * FAR_THREADS * sizeof(int) + warp * FAR_STAGE_BYTES;
+  sCnt[0] = 0; sCnt[FAR_THREADS] = 0;
+
+  if (tid == 0)
+   { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (tid == 0) tma_load_1d(sm, A.pb + b0, (uint32_t)(nB * sizeof(PanelRec)), &bar);
+
+  const int pa = aBase + tid;
+  const bool live = pa < A.NPa && !(A.symmetric && pa > b0 + nB - 1);
+  const PanelRec *Pa = A.pa + (pa < A.NPa ? pa : 0);
+#pragma unroll
+  for (int i = 0; i < 18; i++) sXa[i * FAR_THREADS] = Pa->x[i];
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+   { const double v0 = Pa->V[m];
+     sSt[(3 + m) * FAR_THREADS] = Pa->V[3 + m] - v0;                 // A
+     sSt[(6 + m) * FAR_THREADS] = Pa->V[6 + m] - v0;                 // B
+     sSt[(9 + m) * FAR_THREADS] = Pa->sl[m];
+     sSt[(12 + m) * FAR_THREADS] = Pa->C[m];
+     sEi[m * FAR_THREADS] = (pa < A.NPa) ? Pa->ei[m] : -1; }
+  sSt[15 * FAR_THREADS] = Pa->R;
+  // this lane's slots in the warp's window (the table is padded to a multiple of FAR_THREADS panels; every lane of a
+  // warp, live or not, takes part in the staging so that a slot's first writer always refreshes it)
+  const FarSlot fs = X.slots[pa];
+  const int sl0 = fs.s[0], sl1 = fs.s[1], sl2 = fs.s[2];
+  const int rowLo = fs.rowLo, span = fs.span;              // warp-uniform
+  const int nIn = (sl0 >= 0) + (sl1 >= 0) + (sl2 >= 0);
+  for (int i = lane; i < FAR_STAGE_BYTES / 16; i += 32) reinterpret_cast<double2 *>(stage)[i] = make_double2(0.0, 0.0);
+  __syncwarp();
+
+  mbar_wait(&bar, 0);
+  if (!__any_sync(0xffffffffu, live)) return;
+
+  const long rowBase = (long)A.S.rowOff + rowLo;
+  bool pending = false;                                    // warp-uniform: a bulk group of this warp may still read the stage
+  for (int ib = 0; ib < nB; ib++)
+   { const int pb = b0 + ib;
+     const double *Pb = sm + ib * 36;
+     double D[3];
+     bool valid = live && !(A.symmetric && pb < pa);
+     { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
+       valid = pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D) && valid; }
+     const int *eb3 = (const int *)(Pb + 34);
+     const int eb0 = eb3[0], eb1 = eb3[1], eb2 = eb3[2];
+     if (A.S.colHi != 0x7fffffff && valid)
+      { // column-block assembly: skip pairs none of whose (<= 9) entries falls into the owned column range (exact per entry)
+        bool any = false;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+          { const int e = sEi[i * FAR_THREADS], f = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+            const int c0 = A.S.colOff + (A.symmetric ? max(e, f) : f);
+            any |= (e >= 0 && f >= 0 && c0 >= A.S.colLo && c0 < A.S.colHi); }
+        valid = any; }
+     if (!__any_sync(0xffffffffu, valid)) continue;
+
+     cd val[9];
+#pragma unroll
+     for (int n = 0; n < 9; n++) val[n] = mk(0.0, 0.0);
+     if (valid)
+      { sCnt[0] += 1;
+        double r0 = 0.0;
+        if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
+        S mPhi[3][3], mPsi[3][3];
+        far_moments<KMODE, false, SMALL, S>(sXa, Pb, D, A.K, r0, mPhi, mPsi);
+        cd c1 = A.S.c1;
+        if (SMALL) c1 = cscale(c1, far_pair_factor<KMODE, S>(A.K, r0));   // the pair factor exp(ik r0) rides on the prefactor
+        double sla[3], Aa[3], Ba[3], Ab[3], Bb[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+         { sla[m] = sSt[(9 + m) * FAR_THREADS]; Aa[m] = sSt[(3 + m) * FAR_THREADS]; Ba[m] = sSt[(6 + m) * FAR_THREADS];
+           Ab[m] = Pb[7 + m] - Pb[4 + m]; Bb[m] = Pb[10 + m] - Pb[4 + m]; }
+        contract_pec<S>(mPhi, Aa, Ba, Ab, Bb, sla, Pb + 31, c1, A.K.c4, val); }
+
+     // ---- dense part: window rows x the b-panel's three columns ----
+     bool dense[3]; int par[3];
+#pragma unroll
+     for (int j = 0; j < 3; j++)
+      { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+        const int col = A.S.colOff + eb;
+        dense[j] = span > 0 && eb >= 0 && col >= A.S.colLo && col < A.S.colHi && (!A.symmetric || rowLo + span - 1 < eb);
+        par[j] = 0;
+        if (A.S.isReal)
+         { // 8-byte entries: the bulk reduction needs 16-byte aligned ends, so the window is widened to even element indices
+           // (the extra elements are zero padding of the stage) and must stay inside the matrix
+           const long g = rowBase + (long)col * A.S.ld;
+           par[j] = (int)(g & 1);
+           dense[j] = dense[j] && (g - par[j] + ((par[j] + span + 1) & ~1) <= X.nElem); } }
+     if (dense[0] || dense[1] || dense[2])
+      { if (pending) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
+        if (!A.S.isReal)
+         { cd *st = reinterpret_cast<cd *>(stage);
+#pragma unroll
+           for (int i = 0; i < 3; i++)
+            { const int s = (i == 0) ? sl0 : (i == 1 ? sl1 : sl2);
+              if (s >= 0 && !(s & FAR_SLOT_SECOND))
+               {
+#pragma unroll
+                 for (int j = 0; j < 3; j++) if (dense[j]) *reinterpret_cast<double2 *>(st + j * FAR_SPAN + s) = make_double2(val[3 * i + j].x, val[3 * i + j].y); } }
+           __syncwarp();
+#pragma unroll
+           for (int i = 0; i < 3; i++)
+            { const int s = (i == 0) ? sl0 : (i == 1 ? sl1 : sl2);
+              if (s >= 0 && (s & FAR_SLOT_SECOND))
+               { const int s2 = s & (FAR_SLOT_SECOND - 1);
+#pragma unroll
+                 for (int j = 0; j < 3; j++)
+                  if (dense[j])
+                   { double2 *q = reinterpret_cast<double2 *>(st + j * FAR_SPAN + s2);
+                     double2 t = *q; t.x += val[3 * i + j].x; t.y += val[3 * i + j].y; *q = t; } } }
+           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+           __syncwarp();
+           if (lane == 0)
+            {
+#pragma unroll
+              for (int j = 0; j < 3; j++)
+               if (dense[j])
+                { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+                  bulk_red_f64(A.S.M + 2 * (rowBase + (long)(A.S.colOff + eb) * A.S.ld), st + j * FAR_SPAN, (uint32_t)span * 16u); }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory"); } }
+        else
+         { double *st = reinterpret_cast<double *>(stage);    // [parity][column][FAR_SPAN + 2], element of slot s at index parity + s
+#pragma unroll
+           for (int i = 0; i < 3; i++)
+            { const int s = (i == 0) ? sl0 : (i == 1 ? sl1 : sl2);
+              if (s >= 0 && !(s & FAR_SLOT_SECOND))
+               {
+#pragma unroll
+                 for (int j = 0; j < 3; j++) if (dense[j]) st[(par[j] * 3 + j) * (FAR_SPAN + 2) + par[j] + s] = val[3 * i + j].x; } }
+           __syncwarp();
+#pragma unroll
+           for (int i = 0; i < 3; i++)
+            { const int s = (i == 0) ? sl0 : (i == 1 ? sl1 : sl2);
+              if (s >= 0 && (s & FAR_SLOT_SECOND))
+               { const int s2 = s & (FAR_SLOT_SECOND - 1);
+#pragma unroll
+                 for (int j = 0; j < 3; j++) if (dense[j]) st[(par[j] * 3 + j) * (FAR_SPAN + 2) + par[j] + s2] += val[3 * i + j].x; } }
+           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+           __syncwarp();
+           if (lane == 0)
+            {
+#pragma unroll
+              for (int j = 0; j < 3; j++)
+               if (dense[j])
+                { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+                  const long g = rowBase + (long)(A.S.colOff + eb) * A.S.ld;
+                  bulk_red_f64(A.S.M + (g - par[j]), st + (par[j] * 3 + j) * (FAR_SPAN + 2), (uint32_t)((par[j] + span + 1) & ~1) * 8u); }
+              asm volatile("cp.async.bulk.commit_group;" ::: "memory"); } }
+        pending = true; }
+
+     // ---- the rest through scalar atomics: outlier rows, columns at the diagonal of a symmetric block ----
+     unsigned int nPPI = 0;
+     bool need = false;
+     if (valid)
+      {
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+         { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+           if (dense[j]) { nPPI += nIn; need = need || (sl0 == FAR_SLOT_OUTLIER || sl1 == FAR_SLOT_OUTLIER || sl2 == FAR_SLOT_OUTLIER); }
+           else need = need || (eb >= 0 && (sl0 != FAR_SLOT_NONE || sl1 != FAR_SLOT_NONE || sl2 != FAR_SLOT_NONE)); } }
+     if (__any_sync(0xffffffffu, need))
+      { if (need)
+         {
+#pragma unroll
+           for (int i = 0; i < 3; i++)
+            { const int s = (i == 0) ? sl0 : (i == 1 ? sl1 : sl2);
+              const int ea0 = sEi[i * FAR_THREADS];
+              if (ea0 < 0) continue;
+#pragma unroll
+              for (int j = 0; j < 3; j++)
+               { int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+                 if (eb < 0 || (dense[j] && s != FAR_SLOT_OUTLIER)) continue;
+                 int ea = ea0;
+                 cd v = val[3 * i + j];
+                 bool ok = true; unsigned int cnt = 1;
+                 if (A.S.symmetric)
+                  { if (pa == pb) ok = (ea <= eb);
+                    else if (ea == eb) { v = 2.0 * v; cnt = 2; }
+                    else if (ea > eb) { const int t = ea; ea = eb; eb = t; } }
+                 const int col = A.S.colOff + eb;
+                 if (!ok || col < A.S.colLo || col >= A.S.colHi) continue;
+                 const size_t idx = (size_t)(A.S.rowOff + ea) + (size_t)col * (size_t)A.S.ld;
+                 if (A.S.isReal) atomicAdd(A.S.M + idx, v.x);
+                 else { atomicAdd(A.S.M + 2 * idx, v.x); atomicAdd(A.S.M + 2 * idx + 1, v.y); }
+                 nPPI += cnt; } } } }
+     sCnt[FAR_THREADS] += nPPI;
+   }
+  if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   // algorithm counters (reference log line SurfaceSurfaceInteractions.cc:550-558)
   if (sCnt[FAR_THREADS]) atomicAdd(A.counters, (unsigned long long)sCnt[FAR_THREADS]);
   if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
@@ -563,27 +922,31 @@ int run_fastmath_selftest(scuffcuda_context *ctx, int n, const double *xh, doubl
   return 0;
 }
 
-template <int KMODE, bool PSI, int MINB, bool SMALL>
+template <int KMODE, bool PSI, int MINB, int SMALL>
 static void launch_far_inst(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem)
 { // ask for the shared-memory carve-out that lets MINB CTAs (~46 KB each) share an SM
   cudaFuncSetAttribute(far_kernel<KMODE, PSI, MINB, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   far_kernel<KMODE, PSI, MINB, SMALL><<<grid, FAR_THREADS, smem, ctx->stream>>>(A);
 }
-// resident CTAs per SM: 4 (128 registers) for the PEC variant, 3 (168) with the Psi half — measured best (3 / 4 / 5 tried)
-template <int KMODE>
-static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi, bool small)
-{ static int psiMinb = -1;
-  if (psiMinb < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB_PSI"); psiMinb = e ? atoi(e) : 2; }   // 2 CTAs/SM (242 registers, no spills) measured 5 % faster than 3
+// resident CTAs per SM and small-phase degree: measured defaults, overridable for experiments with SCUFF_CUDA_FAR_MINB (PEC: 3|4),
+// SCUFF_CUDA_FAR_MINB_PSI (2|3)
+template <int KMODE, int SMALL>
+static void launch_far_small(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi)
+{ static int psiMinb = -1, pecMinb = -1;
+  if (psiMinb < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB_PSI"); psiMinb = e ? atoi(e) : (SMALL ? 3 : 2); }
+  if (pecMinb < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB"); pecMinb = e ? atoi(e) : (SMALL ? 4 : 3); }
   if (psi)
-   { if (small) launch_far_inst<KMODE, true, 3, true>(ctx, A, grid, smem);
-     else if (psiMinb == 2) launch_far_inst<KMODE, true, 2, false>(ctx, A, grid, smem);
-     else launch_far_inst<KMODE, true, 3, false>(ctx, A, grid, smem); }
+   { if (psiMinb == 2) launch_far_inst<KMODE, true, 2, SMALL>(ctx, A, grid, smem);
+     else launch_far_inst<KMODE, true, 3, SMALL>(ctx, A, grid, smem); }
   else
-   { static int pecMinb = -1;
-     if (pecMinb < 0) { const char *e = getenv("SCUFF_CUDA_FAR_MINB"); pecMinb = e ? atoi(e) : 3; }   // 3 CTAs/SM (165 registers, no spills) measured 2-4 % faster than 4 with the two-point loop
-     if (small) launch_far_inst<KMODE, false, 4, true>(ctx, A, grid, smem);
-     else if (pecMinb == 3) launch_far_inst<KMODE, false, 3, false>(ctx, A, grid, smem);
-     else launch_far_inst<KMODE, false, 4, false>(ctx, A, grid, smem); }
+   { if (pecMinb == 3) launch_far_inst<KMODE, false, 3, SMALL>(ctx, A, grid, smem);
+     else launch_far_inst<KMODE, false, 4, SMALL>(ctx, A, grid, smem); }
+}
+template <int KMODE>
+static void launch_far_mode(scuffcuda_context *ctx, const FarArgs &A, dim3 grid, size_t smem, bool psi, int small)
+{ if (small == 2) launch_far_small<KMODE, 2>(ctx, A, grid, smem, psi);
+  else if (small == 1) launch_far_small<KMODE, 1>(ctx, A, grid, smem, psi);
+  else launch_far_small<KMODE, 0>(ctx, A, grid, smem, psi);
 }
 
 // largest panel radius of the surface whose device panels are `d`
@@ -591,6 +954,72 @@ static double surface_rmax(scuffcuda_context *ctx, const PanelRec *d)
 { for (const Surface &S : ctx->surfaces)
    if (S.dpanels == d) { double r = 0.0; for (const PanelRec &P : S.hpanels) r = std::max(r, P.R); return r; }
   return 1.0e300;
+}
+
+// ---- host side of the staged scatter: window and slots of every 32-panel group of a surface ----
+struct FarSlotTable { uint64_t generation = 0; int NP = 0; FarSlot *d = nullptr; };
+static std::map<std::pair<scuffcuda_context *, const PanelRec *>, FarSlotTable> g_farSlots;
+static std::mutex g_farSlotsLock;
+
+void build_far_slots(const std::vector<PanelRec> &P, std::vector<FarSlot> &T)
+{ const int NP = (int)P.size(), NPpad = (NP + FAR_THREADS - 1) / FAR_THREADS * FAR_THREADS;
+  T.assign(NPpad, FarSlot{ { FAR_SLOT_NONE, FAR_SLOT_NONE, FAR_SLOT_NONE }, 0, 0, 0 });
+  for (int g0 = 0; g0 < NP; g0 += 32)
+   { const int g1 = std::min(NP, g0 + 32);
+     // the window [lo, lo + FAR_SPAN) that holds most of the group's (panel, edge) slots
+     std::vector<int> e;
+     for (int p = g0; p < g1; p++) for (int i = 0; i < 3; i++) if (P[p].ei[i] >= 0) e.push_back(P[p].ei[i]);
+     std::sort(e.begin(), e.end());
+     int bestLo = 0, bestCnt = 0, bestHi = 0;
+     for (size_t a = 0, b = 0; a < e.size(); a++)
+      { if (a > 0 && e[a] == e[a - 1]) continue;
+        while (b < e.size() && e[b] < e[a] + FAR_SPAN) b++;
+        if ((int)(b - a) > bestCnt) { bestCnt = (int)(b - a); bestLo = e[a]; bestHi = e[b - 1]; } }
+     const int span = bestCnt ? bestHi - bestLo + 1 : 0;
+     for (int p = g0; p < std::min(NPpad, g0 + 32); p++) { T[p].rowLo = bestLo; T[p].span = (short)span; }
+     for (int p = g0; p < g1; p++)
+      for (int i = 0; i < 3; i++)
+       { const int ed = P[p].ei[i];
+         if (ed < 0) continue;
+         if (ed < bestLo || ed >= bestLo + span) { T[p].s[i] = FAR_SLOT_OUTLIER; continue; }
+         bool second = false;
+         for (int q = g0; q < p && !second; q++) for (int k = 0; k < 3; k++) if (P[q].ei[k] == ed) second = true;
+         T[p].s[i] = (short)((ed - bestLo) | (second ? FAR_SLOT_SECOND : 0)); } }
+}
+
+static const FarSlot *far_slots(scuffcuda_context *ctx, const PanelRec *d)
+{ const Surface *S = nullptr;
+  for (const Surface &Q : ctx->surfaces) if (Q.dpanels == d) S = &Q;
+  if (!S) return nullptr;
+  std::lock_guard<std::mutex> lock(g_farSlotsLock);
+  FarSlotTable &T = g_farSlots[std::make_pair(ctx, d)];
+  if (T.d && T.generation == S->generation && T.NP == S->NP) return T.d;
+  std::vector<FarSlot> h;
+  build_far_slots(S->hpanels, h);
+  if (T.d) { cudaStreamSynchronize(ctx->stream); cudaFree(T.d); T.d = nullptr; }
+  if (cudaMalloc(&T.d, h.size() * sizeof(FarSlot)) != cudaSuccess) { T.d = nullptr; return nullptr; }
+  cudaMemcpyAsync(T.d, h.data(), h.size() * sizeof(FarSlot), cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);                   // h is a local
+  T.generation = S->generation; T.NP = S->NP;
+  return T.d;
+}
+void far_slots_release(scuffcuda_context *ctx)
+{ std::lock_guard<std::mutex> lock(g_farSlotsLock);
+  for (auto it = g_farSlots.begin(); it != g_farSlots.end();)
+   if (it->first.first == ctx) { if (it->second.d) cudaFree(it->second.d); it = g_farSlots.erase(it); } else ++it;
+}
+
+template <int KMODE, int SMALL>
+static void launch_far_staged_inst(scuffcuda_context *ctx, const FarArgsX &X, dim3 grid, size_t smem)
+{ cudaFuncSetAttribute(far_staged_kernel<KMODE, SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(far_staged_kernel<KMODE, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  far_staged_kernel<KMODE, SMALL><<<grid, FAR_THREADS, smem, ctx->stream>>>(X);
+}
+template <int KMODE>
+static void launch_far_staged(scuffcuda_context *ctx, const FarArgsX &X, dim3 grid, size_t smem, int small)
+{ if (small == 2) launch_far_staged_inst<KMODE, 2>(ctx, X, grid, smem);
+  else if (small == 1) launch_far_staged_inst<KMODE, 1>(ctx, X, grid, smem);
+  else launch_far_staged_inst<KMODE, 0>(ctx, X, grid, smem);
 }
 
 void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
@@ -604,14 +1033,30 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   A.TA = TB;
   dim3 grid(aTiles, (A.NPb + TB - 1) / TB);
   size_t smem = FAR_SMEM_BYTES(TB);
-  // small-phase variant when |k| (R_a + R_b) <= 1/8 for every panel pair (fine meshes).  It executes 22 % fewer
-  // instructions but measured the same duration on B200 (the kernel is latency-, not issue-bound at 4 CTAs/SM), so it is
-  // opt-in: SCUFF_CUDA_FAR_SMALL=1
-  static int smallEnv = -1;
-  if (smallEnv < 0) { const char *e = getenv("SCUFF_CUDA_FAR_SMALL"); smallEnv = e ? atoi(e) : 0; }
+  // small-phase variant when |k| (R_a + R_b) <= 1/8 (or 1/16: two polynomial degrees less) for every panel pair — fine meshes,
+  // i.e. every large problem: exp(ik r) = exp(ik r0) exp(ik (r - r0)) with the pair factor applied once per panel pair and a
+  // short Taylor polynomial, no range reduction and no quadrant logic, for the point-pair factor.  SCUFF_CUDA_FAR_SMALL=0
+  // forces the general path.
+  // (read at every launch: the tests toggle them inside one process)
+  int smallEnv = -1, stagedEnv = 1;
+  { const char *e = getenv("SCUFF_CUDA_FAR_SMALL"); if (e) smallEnv = atoi(e); }
+  { const char *e = getenv("SCUFF_CUDA_FAR_STAGED"); if (e) stagedEnv = atoi(e); }
   const double kk = (kmode == KMODE_REAL) ? fabs(A.K.kr) : fabs(A.K.ki);
-  const bool small = smallEnv && kmode != KMODE_CPLX && kk * (surface_rmax(ctx, A.pa) + surface_rmax(ctx, A.pb)) <= 0.125;
+  const double span = kk * (surface_rmax(ctx, A.pa) + surface_rmax(ctx, A.pb));
+  int small = 0;
+  if (smallEnv != 0 && kmode != KMODE_CPLX) { if (span <= 0.0625) small = 2; else if (span <= 0.125) small = 1; }
+  if (smallEnv == 1 && small == 2) small = 1;
   ctx->launches++;
+  if (!psi && stagedEnv)
+   { // PEC/PEC: staged scatter (dense shared-memory window + bulk reductions)
+     FarArgsX X; X.A = A; X.slots = far_slots(ctx, A.pa); X.nElem = 0;
+     for (const auto &kv : ctx->matrices) if (kv.second.d == A.S.M) X.nElem = (long)kv.second.NR * kv.second.NC;
+     if (X.slots && X.nElem > 0)
+      { smem = FAR_STAGED_SMEM_BYTES(TB);
+        if (kmode == KMODE_REAL) launch_far_staged<KMODE_REAL>(ctx, X, grid, smem, small);
+        else if (kmode == KMODE_IMAG) launch_far_staged<KMODE_IMAG>(ctx, X, grid, smem, small);
+        else launch_far_staged<KMODE_CPLX>(ctx, X, grid, smem, 0);
+        return; } }
   if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi, small);
   else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi, small);
   else launch_far_mode<KMODE_CPLX>(ctx, A, grid, smem, psi, small);
