@@ -23,7 +23,11 @@ static int fail(scuffcuda_context *ctx, const char *fmt, ...)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 #define CKS(call) do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(ctx, "%s:%d: %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
 
-namespace scuffcuda { void far_slots_release(scuffcuda_context *ctx); }   // far_kernel.cu: window/slot tables of the staged scatter
+namespace scuffcuda {   // far_kernel.cu
+void far_slots_release(scuffcuda_context *ctx);     // window/slot tables of the staged scatter
+void far_twopass_release(scuffcuda_context *ctx);   // panel-pair array and edge tables of the two-pass path
+int launch_far_gather(scuffcuda_context *ctx, double *ms);   // second pass (no-op unless launch_far chose the two-pass path)
+}
 extern "C" {
 
 int scuffcuda_device_count(void)
@@ -61,6 +65,7 @@ void scuffcuda_destroy(scuffcuda_context *ctx)
 { if (!ctx) return;
   cudaSetDevice(ctx->device);
   scuffcuda::far_slots_release(ctx);
+  scuffcuda::far_twopass_release(ctx);
   for (auto &s : ctx->surfaces) if (s.dpanels) cudaFree(s.dpanels);
   for (auto &m : ctx->matrices) { if (m.second.d) cudaFree(m.second.d); if (m.second.ipiv) cudaFree(m.second.ipiv); }
   for (auto &p : ctx->plans) if (p.dnear) cudaFree(p.dnear);
@@ -395,7 +400,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
 
   cdouble Omega(a->omega[0], a->omega[1]);
   const cdouble II(0.0, 1.0);
-  double farMs = 0, nearMs = 0;
+  double farMs = 0, nearMs = 0, gatherMs = 0; bool mirrored = false;
   for (int region = 0; region < 2; region++)
    { cdouble Eps = region == 0 ? cdouble(a->eps_a[0], a->eps_a[1]) : cdouble(a->eps_b[0], a->eps_b[1]);
      cdouble Mu = region == 0 ? cdouble(a->mu_a[0], a->mu_a[1]) : cdouble(a->mu_b[0], a->mu_b[1]);
@@ -449,18 +454,21 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
         if (rc) return 1;
         CK(cudaEventRecord(ev[5], sNear));
         CK(cudaStreamWaitEvent(sMain, ev[5], 0)); }
+     // two-pass far path: the gather adds the panel-pair values to what the near kernels stamped (and mirrors a symmetric block)
+     if (launch_far_gather(ctx, &gatherMs)) mirrored = true;
+     CK(cudaGetLastError());
      CK(cudaEventRecord(ev[3], sMain));
      CK(cudaEventSynchronize(ev[3]));
      float t; cudaEventElapsedTime(&t, ev[1], ev[2]); farMs += t;
      if (!a->far_only) { cudaEventElapsedTime(&t, ev[4], ev[5]); nearMs += t; }
    }
-  if (a->symmetric && a->col_end <= 0)
+  if (a->symmetric && a->col_end <= 0 && !mirrored)
    launch_symmetrize(ctx, *M, a->row_offset, NBFA);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev[3], ctx->stream));
   CK(cudaEventSynchronize(ev[3]));
   float tot; cudaEventElapsedTime(&tot, ev[0], ev[3]);
-  ctx->timing[0] = tot; ctx->timing[1] = farMs; ctx->timing[2] = nearMs;
+  ctx->timing[0] = tot; ctx->timing[1] = farMs; ctx->timing[2] = nearMs; ctx->timing[4] = gatherMs;
   // counters come back through mapped host memory (no D2H copy-engine transfer: one may be busy with a matrix download)
   unsigned long long *hc = (unsigned long long *)scuffcuda::mapped_host_scratch(ctx, 16 * sizeof(unsigned long long), 0);
   if (!hc) return fail(ctx, "assemble_block: cannot allocate mapped host memory");

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <algorithm>
 #include <cstdlib>
+#include <cstdio>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -525,14 +526,20 @@ far_kernel(const __grid_constant__ FarArgs A)
 #define FAR_SPAN 96
 #define FAR_SLOT_SECOND 0x4000   /* the other panel of this edge sits in a lower lane of the same warp: add to its value */
 #define FAR_SLOT_NONE (-1)       /* exterior edge: no basis function */
-#define FAR_SLOT_OUTLIER (-2)    /* edge outside the warp's window: scalar RED */
-#define FAR_STAGE_BYTES 4736     /* per warp: complex 3 x 96 x 16 = 4608 B; real 2 parities x 3 x 98 x 8 = 4704 B */
-struct __align__(16) FarSlot { short s[3]; short span; int rowLo; int pad; };
-struct FarArgsX { FarArgs A; const FarSlot *slots; long nElem; };
+#define FAR_SLOT_OUTLIER (-2)    /* -2 - r: edge outside the warp's window, r = its rank among the warp's outlier slots */
+#define FAR_EX_ROWS 16           /* outlier slots handled per flush round */
+#define FAR_WIN_BYTES 4736       /* per warp: complex 3 x 96 x 16 = 4608 B; real 2 parities x 3 x 98 x 8 = 4704 B */
+#define FAR_STAGE_BYTES (FAR_WIN_BYTES + FAR_EX_ROWS * 64)
+struct __align__(16) FarSlot { short s[3]; short span; int rowLo; int nOut; };
+struct __align__(16) FarExRow { cd v[3]; int edge; int pad[3]; };    // one outlier slot: its three column values and its edge (-1: nothing)
+struct FarArgsX { FarArgs A; const FarSlot *slots; long nElem; int dbg; };
 
-__device__ __forceinline__ void bulk_red_f64(double *dst, const void *srcSmem, uint32_t bytes)
+__device__ __forceinline__ void bulk_red_f64(double *dst, uint32_t srcSmem, uint32_t bytes)
 { asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
-               ::"l"(dst), "r"(smem_u32(srcSmem)), "r"(bytes) : "memory"); }
+               ::"l"(dst), "r"(srcSmem), "r"(bytes) : "memory"); }
+// a warp-uniform value as the compiler can prove it (lane 0's copy): operands of the bulk reduction live in uniform registers,
+// per-lane copies made ptxas wrap every UBLKRED in a waterfall loop
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 
 __device__ __forceinline__ cd cscale(cd c, double a) { return mk(c.x * a, c.y * a); }
 __device__ __forceinline__ cd cscale(cd c, cd a) { return c * a; }
@@ -566,6 +573,22 @@ __device__ __forceinline__ void contract_pec(const S (&m)[3][3], const double *A
       val[3 * i + j] = (sla[i] * slb[j]) * h; }
 }
 
+// one entry through the scalar path, with the upper-triangle convention of Symmetric blocks (stamp.cuh scatter_ppi); returns
+// the number of reference PPIs it stands for
+__device__ __forceinline__ unsigned int far_scalar_entry(const StampParams &SP, int pa, int pb, int ea, int eb, cd v)
+{ unsigned int cnt = 1;
+  if (SP.symmetric)
+   { if (pa == pb) { if (ea > eb) return 0; }
+     else if (ea == eb) { v = 2.0 * v; cnt = 2; }
+     else if (ea > eb) { const int t = ea; ea = eb; eb = t; } }
+  const int col = SP.colOff + eb;
+  if (col < SP.colLo || col >= SP.colHi) return 0;
+  const size_t idx = (size_t)(SP.rowOff + ea) + (size_t)col * (size_t)SP.ld;
+  if (SP.isReal) atomicAdd(SP.M + idx, v.x);
+  else { atomicAdd(SP.M + 2 * idx, v.x); atomicAdd(SP.M + 2 * idx + 1, v.y); }
+  return cnt;
+}
+
 #define FAR_STAGED_SMEM_BYTES(TA) (FAR_SMEM_BYTES(TA) + (FAR_THREADS / 32) * FAR_STAGE_BYTES)
 
 template <int KMODE, int SMALL>
@@ -580,12 +603,14 @@ far_staged_kernel(const __grid_constant__ FarArgsX X)
   const int aBase = blockIdx.x * FAR_THREADS;
   const int nB = min(TB, A.NPb - b0);
   if (A.symmetric && b0 + nB - 1 < aBase) return;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = uni(tid >> 5);
   double *sXa = sm + TB * 36 + tid;                    // element k at sXa[k * FAR_THREADS]
   double *sSt = sm + TB * 36 + 18 * FAR_THREADS + tid;
   int *sEi = (int *)(sm + TB * 36 + 34 * FAR_THREADS) + tid;
   unsigned int *sCnt = (unsigned int *)sEi + 3 * FAR_THREADS;
   char *stage = (char *)(sm + TB * 36 + 34 * FAR_THREADS) + 6 * FAR_THREADS * sizeof(int) + warp * FAR_STAGE_BYTES;
+  FarExRow *ex = reinterpret_cast<FarExRow *>(stage + FAR_WIN_BYTES);
+  const uint32_t stageU = smem_u32(stage);
   sCnt[0] = 0; sCnt[FAR_THREADS] = 0;
 
   if (tid == 0)
@@ -612,8 +637,9 @@ far_staged_kernel(const __grid_constant__ FarArgsX X)
   // warp, live or not, takes part in the staging so that a slot's first writer always refreshes it)
   const FarSlot fs = X.slots[pa];
   const int sl0 = fs.s[0], sl1 = fs.s[1], sl2 = fs.s[2];
-  const int rowLo = fs.rowLo, span = fs.span;              // warp-uniform
+  const int rowLo = uni(fs.rowLo), span = uni(fs.span), nOut = uni(fs.nOut);
   const int nIn = (sl0 >= 0) + (sl1 >= 0) + (sl2 >= 0);
+  const bool hasOut = (sl0 <= FAR_SLOT_OUTLIER) || (sl1 <= FAR_SLOT_OUTLIER) || (sl2 <= FAR_SLOT_OUTLIER);
   for (int i = lane; i < FAR_STAGE_BYTES / 16; i += 32) reinterpret_cast<double2 *>(stage)[i] = make_double2(0.0, 0.0);
   __syncwarp();
 
@@ -622,15 +648,24 @@ far_staged_kernel(const __grid_constant__ FarArgsX X)
 
   const long rowBase = (long)A.S.rowOff + rowLo;
   bool pending = false;                                    // warp-uniform: a bulk group of this warp may still read the stage
-  for (int ib = 0; ib < nB; ib++)
-   { const int pb = b0 + ib;
+  // SCUFF_CUDA_FAR_DBG & 16: cycle counts of the phases of an iteration (lane 0 of every warp), summed into counters[8..13]
+  const bool prof = (X.dbg & 16) != 0;
+  long long tc[6] = { 0, 0, 0, 0, 0, 0 }, tPrev = prof ? clock64() : 0;
+#define FAR_TICK(k) do { if (prof) { const long long t_ = clock64(); tc[k] += t_ - tPrev; tPrev = t_; } } while (0)
+  // every warp walks the tile's b-panels from its own starting point: warps (and CTAs of one grid row) that march through the
+  // same b-panels in step would send their windows — overlapping row ranges of the same three columns — to the same L2
+  // sectors at the same moment, and same-address atomics serialise in the L2
+  const int ibRot = (X.dbg & 8) ? 0 : (int)((blockIdx.x * 4u + (unsigned)warp) * 7u) % nB;
+  for (int it = 0; it < nB; it++)
+   { int ib = it + ibRot; if (ib >= nB) ib -= nB;
+     const int pb = b0 + ib;
      const double *Pb = sm + ib * 36;
      double D[3];
      bool valid = live && !(A.symmetric && pb < pa);
      { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
        valid = pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D) && valid; }
      const int *eb3 = (const int *)(Pb + 34);
-     const int eb0 = eb3[0], eb1 = eb3[1], eb2 = eb3[2];
+     const int eb0 = uni(eb3[0]), eb1 = uni(eb3[1]), eb2 = uni(eb3[2]);
      if (A.S.colHi != 0x7fffffff && valid)
       { // column-block assembly: skip pairs none of whose (<= 9) entries falls into the owned column range (exact per entry)
         bool any = false;
@@ -647,7 +682,11 @@ far_staged_kernel(const __grid_constant__ FarArgsX X)
      cd val[9];
 #pragma unroll
      for (int n = 0; n < 9; n++) val[n] = mk(0.0, 0.0);
-     if (valid)
+     if (valid && (X.dbg & 32))
+      { sCnt[0] += 1;
+#pragma unroll
+        for (int n = 0; n < 9; n++) val[n] = mk(D[0] + n, D[1] - n); }      // timing experiment: scatter only, no cubature
+     else if (valid)
       { sCnt[0] += 1;
         double r0 = 0.0;
         if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
@@ -662,23 +701,27 @@ far_staged_kernel(const __grid_constant__ FarArgsX X)
            Ab[m] = Pb[7 + m] - Pb[4 + m]; Bb[m] = Pb[10 + m] - Pb[4 + m]; }
         contract_pec<S>(mPhi, Aa, Ba, Ab, Bb, sla, Pb + 31, c1, A.K.c4, val); }
 
-     // ---- dense part: window rows x the b-panel's three columns ----
-     bool dense[3]; int par[3];
+     // ---- dense part: window rows x the b-panel's three columns (all decisions warp-uniform) ----
+     bool dense[3]; int par[3]; long gcol[3];
 #pragma unroll
      for (int j = 0; j < 3; j++)
       { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
         const int col = A.S.colOff + eb;
         dense[j] = span > 0 && eb >= 0 && col >= A.S.colLo && col < A.S.colHi && (!A.symmetric || rowLo + span - 1 < eb);
+        gcol[j] = rowBase + (long)col * A.S.ld;           // element index of the window's first row in this column
         par[j] = 0;
         if (A.S.isReal)
          { // 8-byte entries: the bulk reduction needs 16-byte aligned ends, so the window is widened to even element indices
            // (the extra elements are zero padding of the stage) and must stay inside the matrix
-           const long g = rowBase + (long)col * A.S.ld;
-           par[j] = (int)(g & 1);
-           dense[j] = dense[j] && (g - par[j] + ((par[j] + span + 1) & ~1) <= X.nElem); } }
-     if (dense[0] || dense[1] || dense[2])
-      { if (pending) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
-        if (!A.S.isReal)
+           par[j] = (int)(gcol[j] & 1);
+           dense[j] = dense[j] && (gcol[j] - par[j] + ((par[j] + span + 1) & ~1) <= X.nElem); } }
+     const bool anyDense = dense[0] || dense[1] || dense[2];
+     const bool flushOut = nOut > 0 && (eb0 >= 0 || eb1 >= 0 || eb2 >= 0) && !(X.dbg & 64);
+     FAR_TICK(0);                                          // far test, cubature, contraction
+     if (anyDense && pending) { if (lane < 3) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); pending = false; }
+     FAR_TICK(1);                                          // wait for the previous bulk group's reads
+     if (anyDense)
+      { if (!A.S.isReal)
          { cd *st = reinterpret_cast<cd *>(stage);
 #pragma unroll
            for (int i = 0; i < 3; i++)
@@ -700,13 +743,20 @@ far_staged_kernel(const __grid_constant__ FarArgsX X)
                      double2 t = *q; t.x += val[3 * i + j].x; t.y += val[3 * i + j].y; *q = t; } } }
            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
            __syncwarp();
-           if (lane == 0)
+           FAR_TICK(2);                                    // stage writes, fence
+           if (X.dbg & 4)
+            { if (lane < 3)
+               { const int j = lane;
+                 if (dense[j]) bulk_red_f64(A.S.M + 2 * gcol[j], stageU + (uint32_t)(j * FAR_SPAN * 16), (uint32_t)span * 16u);
+                 asm volatile("cp.async.bulk.commit_group;" ::: "memory"); } }
+           else if (lane == 0 && !(X.dbg & 1))
             {
 #pragma unroll
               for (int j = 0; j < 3; j++)
                if (dense[j])
-                { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
-                  bulk_red_f64(A.S.M + 2 * (rowBase + (long)(A.S.colOff + eb) * A.S.ld), st + j * FAR_SPAN, (uint32_t)span * 16u); }
+                { if (X.dbg & 2) asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                                              ::"l"(A.S.M + 2 * gcol[j]), "r"(stageU + (uint32_t)(j * FAR_SPAN * 16)), "r"((uint32_t)span * 16u) : "memory");
+                  else bulk_red_f64(A.S.M + 2 * gcol[j], stageU + (uint32_t)(j * FAR_SPAN * 16), (uint32_t)span * 16u); }
               asm volatile("cp.async.bulk.commit_group;" ::: "memory"); } }
         else
          { double *st = reinterpret_cast<double *>(stage);    // [parity][column][FAR_SPAN + 2], element of slot s at index parity + s
@@ -731,51 +781,60 @@ far_staged_kernel(const __grid_constant__ FarArgsX X)
             {
 #pragma unroll
               for (int j = 0; j < 3; j++)
-               if (dense[j])
-                { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
-                  const long g = rowBase + (long)(A.S.colOff + eb) * A.S.ld;
-                  bulk_red_f64(A.S.M + (g - par[j]), st + (par[j] * 3 + j) * (FAR_SPAN + 2), (uint32_t)((par[j] + span + 1) & ~1) * 8u); }
+               if (dense[j]) bulk_red_f64(A.S.M + (gcol[j] - par[j]), stageU + (uint32_t)((par[j] * 3 + j) * (FAR_SPAN + 2) * 8),
+                                          (uint32_t)((par[j] + span + 1) & ~1) * 8u);
               asm volatile("cp.async.bulk.commit_group;" ::: "memory"); } }
         pending = true; }
 
-     // ---- the rest through scalar atomics: outlier rows, columns at the diagonal of a symmetric block ----
+     FAR_TICK(3);                                          // bulk reductions issued
      unsigned int nPPI = 0;
-     bool need = false;
-     if (valid)
-      {
+     if (valid) nPPI = (unsigned int)nIn * ((unsigned int)dense[0] + (unsigned int)dense[1] + (unsigned int)dense[2]);
+     // ---- outlier slots (edges outside the window): their values are collected in the warp's extra rows and flushed with all
+     //      lanes busy, FAR_EX_ROWS slots per round (one lane per (slot, column) record) ----
+     if (flushOut)
+      { for (int r0 = 0; r0 < nOut; r0 += FAR_EX_ROWS)
+         { if (hasOut)
+            {
 #pragma unroll
-        for (int j = 0; j < 3; j++)
-         { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
-           if (dense[j]) { nPPI += nIn; need = need || (sl0 == FAR_SLOT_OUTLIER || sl1 == FAR_SLOT_OUTLIER || sl2 == FAR_SLOT_OUTLIER); }
-           else need = need || (eb >= 0 && (sl0 != FAR_SLOT_NONE || sl1 != FAR_SLOT_NONE || sl2 != FAR_SLOT_NONE)); } }
-     if (__any_sync(0xffffffffu, need))
-      { if (need)
+              for (int i = 0; i < 3; i++)
+               { const int s = (i == 0) ? sl0 : (i == 1 ? sl1 : sl2);
+                 const int r = FAR_SLOT_OUTLIER - s - r0;                  // rank of this slot inside the round
+                 if (s <= FAR_SLOT_OUTLIER && r >= 0 && r < FAR_EX_ROWS)
+                  { FarExRow *E = ex + r;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) *reinterpret_cast<double2 *>(&E->v[j]) = make_double2(val[3 * i + j].x, val[3 * i + j].y);
+                    E->edge = valid ? sEi[i * FAR_THREADS] : -1; } } }
+           __syncwarp();
+           const int nRec = 3 * min(FAR_EX_ROWS, nOut - r0);
+           for (int t = lane; t < nRec; t += 32)
+            { const int r = t / 3, j = t - 3 * r;
+              const int ea = ex[r].edge, eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+              if (ea < 0 || eb < 0) continue;
+              const double2 v = *reinterpret_cast<const double2 *>(&ex[r].v[j]);
+              // the pair's own panel indices only matter for pa == pb, which is never a far pair
+              nPPI += far_scalar_entry(A.S, 0, 1, ea, eb, mk(v.x, v.y)); }
+           __syncwarp(); } }
+     // ---- columns that cannot take the dense path (at the diagonal of a symmetric block, the last rows of a real matrix):
+     //      in-window slots through scalar atomics ----
+     if ((eb0 >= 0 && !dense[0]) || (eb1 >= 0 && !dense[1]) || (eb2 >= 0 && !dense[2]))
+      { if (valid)
          {
 #pragma unroll
            for (int i = 0; i < 3; i++)
             { const int s = (i == 0) ? sl0 : (i == 1 ? sl1 : sl2);
-              const int ea0 = sEi[i * FAR_THREADS];
-              if (ea0 < 0) continue;
+              if (s < 0) continue;
+              const int ea = sEi[i * FAR_THREADS];
 #pragma unroll
               for (int j = 0; j < 3; j++)
-               { int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
-                 if (eb < 0 || (dense[j] && s != FAR_SLOT_OUTLIER)) continue;
-                 int ea = ea0;
-                 cd v = val[3 * i + j];
-                 bool ok = true; unsigned int cnt = 1;
-                 if (A.S.symmetric)
-                  { if (pa == pb) ok = (ea <= eb);
-                    else if (ea == eb) { v = 2.0 * v; cnt = 2; }
-                    else if (ea > eb) { const int t = ea; ea = eb; eb = t; } }
-                 const int col = A.S.colOff + eb;
-                 if (!ok || col < A.S.colLo || col >= A.S.colHi) continue;
-                 const size_t idx = (size_t)(A.S.rowOff + ea) + (size_t)col * (size_t)A.S.ld;
-                 if (A.S.isReal) atomicAdd(A.S.M + idx, v.x);
-                 else { atomicAdd(A.S.M + 2 * idx, v.x); atomicAdd(A.S.M + 2 * idx + 1, v.y); }
-                 nPPI += cnt; } } } }
+               { const int eb = (j == 0) ? eb0 : (j == 1 ? eb1 : eb2);
+                 if (eb < 0 || dense[j]) continue;
+                 nPPI += far_scalar_entry(A.S, pa, pb, ea, eb, val[3 * i + j]); } } } }
      sCnt[FAR_THREADS] += nPPI;
+     FAR_TICK(4);                                          // outlier flush, scalar leftovers
    }
-  if (pending && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (pending && lane < 3) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  FAR_TICK(5);
+  if (prof && lane == 0) for (int k = 0; k < 6; k++) atomicAdd(A.counters + 8 + k, (unsigned long long)tc[k]);
   // algorithm counters (reference log line SurfaceSurfaceInteractions.cc:550-558)
   if (sCnt[FAR_THREADS]) atomicAdd(A.counters, (unsigned long long)sCnt[FAR_THREADS]);
   if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
@@ -956,6 +1015,159 @@ static double surface_rmax(scuffcuda_context *ctx, const PanelRec *d)
   return 1.0e300;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Two-pass far assembly (PEC/PEC blocks).  Measured (tools/far_dbg_probe.sh, profiles/r02_far_scatter_experiments.txt): whatever
+// the scatter mechanism — 18 scalar RED per pair, or the staged windows above — 1.2-1.6 G FP64 atomics into a matrix that does
+// not fit the L2 keep the far kernel at 14-17 ms; with the atomics replaced by plain stores the same kernel takes 10 ms.  So:
+//   pass 1  far_pass1_kernel: every panel pair pa<pb (pa, pb any for a non-symmetric block) writes its nine contributions
+//           (zeros when the pair is not far) with plain 16-byte stores to the panel-pair array Q[pb][j][pa][i] — no atomics, no
+//           fences, nothing the cubature loop can queue behind;
+//   pass 2  far_gather_kernel: one thread per matrix entry (e_a, e_b) adds the <= 4 panel-pair values of its two x two panels
+//           (coalesced: consecutive edges <-> consecutive panels), adds them to what the near/singular kernels have stamped, and
+//           writes the entry AND its mirror image (32 x 32 tiles through shared memory) — it replaces the symmetrize pass.
+// HBM traffic of the detour: 9 x 16 B per panel pair written and read once (13.4 GB at N = 20 280: ~4 ms at 6.5 TB/s, the write
+// half hidden under the FP64-bound pass 1).  Q is sized NP^2/2 x 144 B for a symmetric block; when it does not fit the budget
+// (SCUFF_CUDA_FAR_QMAX_GB, default 40) the staged-atomic kernel is used instead.
+// ------------------------------------------------------------------------------------------------------------------
+struct FarQ { cd *Q; int symmetric; int NApad; };
+// offset (in complex elements) of the row of b-panel pb and its a-extent NA; element (pb, j, pa, i) = row + (j * NA + pa) * 3 + i
+__device__ __forceinline__ long farq_row(const FarQ &L, int pb, int &NA)
+{ if (L.symmetric)
+   { const long t = pb >> 7; NA = (int)((t + 1) << 7);
+     return 9L * 128 * 128 * (t * (t + 1) / 2) + (long)(pb - (int)(t << 7)) * 9 * NA; }
+  NA = L.NApad; return (long)pb * 9 * L.NApad;
+}
+struct FarArgsQ { FarArgs A; FarQ L; };
+
+template <int KMODE, int SMALL>
+__global__ void __launch_bounds__(FAR_THREADS, 3)
+far_pass1_kernel(const __grid_constant__ FarArgsQ X)
+{ const FarArgs &A = X.A;
+  extern __shared__ __align__(128) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  typedef typename KScalar<KMODE>::type S;
+  const int TB = A.TA;
+  const int b0 = blockIdx.y * TB;
+  const int aBase = blockIdx.x * FAR_THREADS;
+  const int nB = min(TB, A.NPb - b0);
+  if (A.symmetric && b0 + nB - 1 < aBase) return;
+  const int tid = threadIdx.x;
+  double *sXa = sm + TB * 36 + tid;                    // element k at sXa[k * FAR_THREADS]
+  double *sSt = sm + TB * 36 + 18 * FAR_THREADS + tid;
+  int *sEi = (int *)(sm + TB * 36 + 34 * FAR_THREADS) + tid;
+  unsigned int *sCnt = (unsigned int *)sEi + 3 * FAR_THREADS;
+  sCnt[0] = 0; sCnt[FAR_THREADS] = 0;
+
+  if (tid == 0)
+   { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (tid == 0) tma_load_1d(sm, A.pb + b0, (uint32_t)(nB * sizeof(PanelRec)), &bar);
+
+  const int pa = aBase + tid;
+  const bool live = pa < A.NPa && !(A.symmetric && pa >= b0 + nB - 1);
+  const PanelRec *Pa = A.pa + (pa < A.NPa ? pa : 0);
+#pragma unroll
+  for (int i = 0; i < 18; i++) sXa[i * FAR_THREADS] = Pa->x[i];
+  int na = 0;
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+   { const double v0 = Pa->V[m];
+     sSt[(3 + m) * FAR_THREADS] = Pa->V[3 + m] - v0;                 // A
+     sSt[(6 + m) * FAR_THREADS] = Pa->V[6 + m] - v0;                 // B
+     sSt[(9 + m) * FAR_THREADS] = Pa->sl[m];
+     sSt[(12 + m) * FAR_THREADS] = Pa->C[m];
+     na += (Pa->ei[m] >= 0); }
+  sSt[15 * FAR_THREADS] = Pa->R;
+  mbar_wait(&bar, 0);
+  if (!live) return;
+
+  for (int ib = 0; ib < nB; ib++)
+   { const int pb = b0 + ib;
+     if (A.symmetric && pb <= pa) continue;            // the gather reads pairs pa < pb only
+     const double *Pb = sm + ib * 36;
+     double D[3];
+     bool far;
+     { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
+       far = pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D); }
+     cd val[9];
+#pragma unroll
+     for (int n = 0; n < 9; n++) val[n] = mk(0.0, 0.0);
+     if (far)
+      { const int *eb3 = (const int *)(Pb + 34);
+        sCnt[0] += 1;
+        sCnt[FAR_THREADS] += (unsigned int)(na * ((eb3[0] >= 0) + (eb3[1] >= 0) + (eb3[2] >= 0)));
+        double r0 = 0.0;
+        if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
+        S mPhi[3][3], mPsi[3][3];
+        far_moments<KMODE, false, SMALL, S>(sXa, Pb, D, A.K, r0, mPhi, mPsi);
+        cd c1 = A.S.c1;
+        if (SMALL) c1 = cscale(c1, far_pair_factor<KMODE, S>(A.K, r0));   // the pair factor exp(ik r0) rides on the prefactor
+        double sla[3], Aa[3], Ba[3], Ab[3], Bb[3];
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+         { sla[m] = sSt[(9 + m) * FAR_THREADS]; Aa[m] = sSt[(3 + m) * FAR_THREADS]; Ba[m] = sSt[(6 + m) * FAR_THREADS];
+           Ab[m] = Pb[7 + m] - Pb[4 + m]; Bb[m] = Pb[10 + m] - Pb[4 + m]; }
+        contract_pec<S>(mPhi, Aa, Ba, Ab, Bb, sla, Pb + 31, c1, A.K.c4, val); }
+     int NA; const long row = farq_row(X.L, pb, NA);
+     double2 *q = reinterpret_cast<double2 *>(X.L.Q + row + (long)pa * 3);
+#pragma unroll
+     for (int j = 0; j < 3; j++)
+#pragma unroll
+      for (int i = 0; i < 3; i++) q[(long)j * NA * 3 + i] = make_double2(val[3 * i + j].x, val[3 * i + j].y);
+   }
+  // algorithm counters (reference log line SurfaceSurfaceInteractions.cc:550-558)
+  if (sCnt[FAR_THREADS]) atomicAdd(A.counters, (unsigned long long)sCnt[FAR_THREADS]);
+  if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
+}
+
+// edge -> its two panels and the local index of the edge in each: {pP, iP, pM, iM}, -1 where there is none
+struct GatherArgs
+{ FarQ L; const int4 *edgeA, *edgeB; int NEa, NEb;
+  double *M; long ld; int rowOff, colOff; };
+
+template <int W, bool SYM>
+__global__ void __launch_bounds__(256)
+far_gather_kernel(const GatherArgs G)
+{ __shared__ double tile[32][33 * W];
+  const int bx = blockIdx.x, by = blockIdx.y;      // tile: rows (a-edges) by*32.., columns (b-edges) bx*32..
+  if (SYM && by > bx) return;
+  const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
+  const int ea = by * 32 + tx;
+  int4 Ea = make_int4(-1, 0, -1, 0);
+  if (ea < G.NEa) Ea = G.edgeA[ea];
+  for (int j = ty; j < 32; j += 8)
+   { const int eb = bx * 32 + j;
+     if (ea >= G.NEa || eb >= G.NEb || (SYM && ea >= eb)) continue;
+     const int4 Eb = G.edgeB[eb];
+     double sx = 0.0, sy = 0.0;
+#pragma unroll
+     for (int u = 0; u < 2; u++)
+#pragma unroll
+      for (int v = 0; v < 2; v++)
+       { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = v ? Eb.z : Eb.x, jb = v ? Eb.w : Eb.y;
+         if (pa < 0 || pb < 0) continue;
+         if (SYM)
+          { if (pa == pb) continue;
+            if (pa > pb) { int t = pa; pa = pb; pb = t; t = ia; ia = jb; jb = t; } }   // the pair is stored once, with the lower panel as 'a'
+         int NA; const long row = farq_row(G.L, pb, NA);
+         const double2 q = *reinterpret_cast<const double2 *>(G.L.Q + row + ((long)jb * NA + pa) * 3 + ia);
+         sx += q.x; sy += q.y; }
+     const size_t idx = ((size_t)(G.rowOff + ea) + (size_t)(G.colOff + eb) * (size_t)G.ld) * W;
+     if (W == 2)
+      { double2 m = *reinterpret_cast<double2 *>(G.M + idx); m.x += sx; m.y += sy;
+        *reinterpret_cast<double2 *>(G.M + idx) = m; tile[j][2 * tx] = m.x; tile[j][2 * tx + 1] = m.y; }
+     else { const double m = G.M[idx] + sx; G.M[idx] = m; tile[j][tx] = m; }
+   }
+  if (!SYM) return;
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8)
+   { const int r = bx * 32 + tx, c = by * 32 + j;   // mirror image: lower(r, c) = upper(c, r)
+     if (r < G.NEa && c < G.NEa && r > c)
+      { const size_t idx = ((size_t)(G.rowOff + r) + (size_t)(G.colOff + c) * (size_t)G.ld) * W;
+        for (int q = 0; q < W; q++) G.M[idx + q] = tile[tx][j * W + q]; } }
+}
+
 // ---- host side of the staged scatter: window and slots of every 32-panel group of a surface ----
 struct FarSlotTable { uint64_t generation = 0; int NP = 0; FarSlot *d = nullptr; };
 static std::map<std::pair<scuffcuda_context *, const PanelRec *>, FarSlotTable> g_farSlots;
@@ -963,7 +1175,7 @@ static std::mutex g_farSlotsLock;
 
 void build_far_slots(const std::vector<PanelRec> &P, std::vector<FarSlot> &T)
 { const int NP = (int)P.size(), NPpad = (NP + FAR_THREADS - 1) / FAR_THREADS * FAR_THREADS;
-  T.assign(NPpad, FarSlot{ { FAR_SLOT_NONE, FAR_SLOT_NONE, FAR_SLOT_NONE }, 0, 0, 0 });
+  T.assign(NPpad, FarSlot{ { FAR_SLOT_NONE, FAR_SLOT_NONE, FAR_SLOT_NONE }, 0, 0, 0 });   // s[3], span, rowLo, nOut
   for (int g0 = 0; g0 < NP; g0 += 32)
    { const int g1 = std::min(NP, g0 + 32);
      // the window [lo, lo + FAR_SPAN) that holds most of the group's (panel, edge) slots
@@ -977,14 +1189,16 @@ void build_far_slots(const std::vector<PanelRec> &P, std::vector<FarSlot> &T)
         if ((int)(b - a) > bestCnt) { bestCnt = (int)(b - a); bestLo = e[a]; bestHi = e[b - 1]; } }
      const int span = bestCnt ? bestHi - bestLo + 1 : 0;
      for (int p = g0; p < std::min(NPpad, g0 + 32); p++) { T[p].rowLo = bestLo; T[p].span = (short)span; }
+     int nOut = 0;
      for (int p = g0; p < g1; p++)
       for (int i = 0; i < 3; i++)
        { const int ed = P[p].ei[i];
          if (ed < 0) continue;
-         if (ed < bestLo || ed >= bestLo + span) { T[p].s[i] = FAR_SLOT_OUTLIER; continue; }
+         if (ed < bestLo || ed >= bestLo + span) { T[p].s[i] = (short)(FAR_SLOT_OUTLIER - nOut++); continue; }
          bool second = false;
          for (int q = g0; q < p && !second; q++) for (int k = 0; k < 3; k++) if (P[q].ei[k] == ed) second = true;
-         T[p].s[i] = (short)((ed - bestLo) | (second ? FAR_SLOT_SECOND : 0)); } }
+         T[p].s[i] = (short)((ed - bestLo) | (second ? FAR_SLOT_SECOND : 0)); }
+     for (int p = g0; p < std::min(NPpad, g0 + 32); p++) T[p].nOut = nOut; }
 }
 
 static const FarSlot *far_slots(scuffcuda_context *ctx, const PanelRec *d)
@@ -1007,6 +1221,75 @@ void far_slots_release(scuffcuda_context *ctx)
 { std::lock_guard<std::mutex> lock(g_farSlotsLock);
   for (auto it = g_farSlots.begin(); it != g_farSlots.end();)
    if (it->first.first == ctx) { if (it->second.d) cudaFree(it->second.d); it = g_farSlots.erase(it); } else ++it;
+}
+
+// ---- host side of the two-pass path ----
+struct FarTwoPassState
+{ cd *Q = nullptr; size_t qBytes = 0;                       // panel-pair array, grown on demand, kept for the life of the context
+  std::map<const PanelRec *, std::pair<uint64_t, int4 *> > edges;   // surface -> (generation, device edge table)
+  bool pending = false; GatherArgs G; bool sym = false; int isReal = 0; int NEa = 0, NEb = 0; };
+static std::map<scuffcuda_context *, FarTwoPassState> g_twoPass;
+
+static const int4 *far_edge_table(scuffcuda_context *ctx, FarTwoPassState &T, const PanelRec *d, int &NE)
+{ const Surface *S = nullptr;
+  for (const Surface &Q : ctx->surfaces) if (Q.dpanels == d) S = &Q;
+  if (!S) return nullptr;
+  NE = S->NE;
+  auto &slot = T.edges[d];
+  if (slot.second && slot.first == S->generation) return slot.second;
+  std::vector<int4> h(std::max(S->NE, 1), make_int4(-1, 0, -1, 0));
+  for (int p = 0; p < S->NP; p++)
+   for (int i = 0; i < 3; i++)
+    { const int e = S->hpanels[p].ei[i];
+      if (e < 0 || e >= S->NE) continue;
+      if (S->hpanels[p].sl[i] >= 0.0) { h[e].x = p; h[e].y = i; } else { h[e].z = p; h[e].w = i; } }
+  if (slot.second) { cudaStreamSynchronize(ctx->stream); cudaFree(slot.second); slot.second = nullptr; }
+  if (cudaMalloc(&slot.second, h.size() * sizeof(int4)) != cudaSuccess) { slot.second = nullptr; return nullptr; }
+  cudaMemcpyAsync(slot.second, h.data(), h.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  slot.first = S->generation;
+  return slot.second;
+}
+void far_twopass_release(scuffcuda_context *ctx)
+{ std::lock_guard<std::mutex> lock(g_farSlotsLock);
+  auto it = g_twoPass.find(ctx);
+  if (it == g_twoPass.end()) return;
+  if (it->second.Q) cudaFree(it->second.Q);
+  for (auto &e : it->second.edges) if (e.second.second) cudaFree(e.second.second);
+  g_twoPass.erase(it);
+}
+
+template <int KMODE, int SMALL>
+static void launch_far_pass1_inst(scuffcuda_context *ctx, const FarArgsQ &X, dim3 grid, size_t smem)
+{ cudaFuncSetAttribute(far_pass1_kernel<KMODE, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  far_pass1_kernel<KMODE, SMALL><<<grid, FAR_THREADS, smem, ctx->stream>>>(X);
+}
+template <int KMODE>
+static void launch_far_pass1(scuffcuda_context *ctx, const FarArgsQ &X, dim3 grid, size_t smem, int small)
+{ if (small == 2) launch_far_pass1_inst<KMODE, 2>(ctx, X, grid, smem);
+  else if (small == 1) launch_far_pass1_inst<KMODE, 1>(ctx, X, grid, smem);
+  else launch_far_pass1_inst<KMODE, 0>(ctx, X, grid, smem);
+}
+
+// Second pass of the two-pass path: called by assemble_block once the near/singular kernels of this region pass have finished
+// stamping (the gather adds to their entries without atomics).  Returns 1 if it also wrote the mirror image of a symmetric block.
+int launch_far_gather(scuffcuda_context *ctx, double *ms)
+{ FarTwoPassState *T;
+  { std::lock_guard<std::mutex> lock(g_farSlotsLock);
+    auto it = g_twoPass.find(ctx);
+    if (it == g_twoPass.end() || !it->second.pending) return 0;
+    T = &it->second; }
+  T->pending = false;
+  dim3 grid((T->NEb + 31) / 32, (T->NEa + 31) / 32), block(32, 8);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, ctx->stream);
+  ctx->launches++;
+  if (T->sym) { if (T->isReal) far_gather_kernel<1, true><<<grid, block, 0, ctx->stream>>>(T->G); else far_gather_kernel<2, true><<<grid, block, 0, ctx->stream>>>(T->G); }
+  else { if (T->isReal) far_gather_kernel<1, false><<<grid, block, 0, ctx->stream>>>(T->G); else far_gather_kernel<2, false><<<grid, block, 0, ctx->stream>>>(T->G); }
+  cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
+  float t = 0; cudaEventElapsedTime(&t, e0, e1); if (ms) *ms += t;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return T->sym ? 1 : 0;
 }
 
 template <int KMODE, int SMALL>
@@ -1047,15 +1330,51 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   if (smallEnv != 0 && kmode != KMODE_CPLX) { if (span <= 0.0625) small = 2; else if (span <= 0.125) small = 1; }
   if (smallEnv == 1 && small == 2) small = 1;
   ctx->launches++;
+  int twoPassEnv = 1;
+  { const char *e = getenv("SCUFF_CUDA_FAR_TWOPASS"); if (e) twoPassEnv = atoi(e); }
+  if (!psi && twoPassEnv && A.S.colHi == 0x7fffffff)
+   { // PEC/PEC, whole block: two-pass path (plain stores to the panel-pair array, gathered after the near kernels)
+     std::unique_lock<std::mutex> lock(g_farSlotsLock);
+     FarTwoPassState &T = g_twoPass[ctx];
+     lock.unlock();
+     const long NApad = (long)aTiles * FAR_THREADS;
+     const long tiles = (A.NPb + 127) / 128;
+     const size_t need = sizeof(cd) * (size_t)(A.symmetric ? 9L * 128 * 128 * (tiles * (tiles + 1) / 2) : (long)A.NPb * 9 * NApad);
+     double qmaxGB = 40.0;
+     { const char *e = getenv("SCUFF_CUDA_FAR_QMAX_GB"); if (e) qmaxGB = atof(e); }
+     bool ok = (double)need <= qmaxGB * 1073741824.0;
+     if (ok && need > T.qBytes)
+      { if (T.Q) { cudaStreamSynchronize(ctx->stream); cudaFree(T.Q); T.Q = nullptr; T.qBytes = 0; }
+        size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
+        if (need + (size_t)(2ull << 30) > freeB || cudaMalloc(&T.Q, need) != cudaSuccess) { cudaGetLastError(); T.Q = nullptr; ok = false; }
+        else T.qBytes = need; }
+     int NEa = 0, NEb = 0;
+     const int4 *ea = ok ? far_edge_table(ctx, T, A.pa, NEa) : nullptr, *eb = ok ? far_edge_table(ctx, T, A.pb, NEb) : nullptr;
+     if (ok && ea && eb)
+      { FarArgsQ X; X.A = A; X.L.Q = T.Q; X.L.symmetric = A.symmetric; X.L.NApad = (int)NApad;
+        if (kmode == KMODE_REAL) launch_far_pass1<KMODE_REAL>(ctx, X, grid, smem, small);
+        else if (kmode == KMODE_IMAG) launch_far_pass1<KMODE_IMAG>(ctx, X, grid, smem, small);
+        else launch_far_pass1<KMODE_CPLX>(ctx, X, grid, smem, 0);
+        T.G.L = X.L; T.G.edgeA = ea; T.G.edgeB = eb; T.G.NEa = NEa; T.G.NEb = NEb;
+        T.G.M = A.S.M; T.G.ld = A.S.ld; T.G.rowOff = A.S.rowOff; T.G.colOff = A.S.colOff;
+        T.sym = A.symmetric != 0; T.isReal = A.S.isReal; T.NEa = NEa; T.NEb = NEb; T.pending = true;
+        return; } }
   if (!psi && stagedEnv)
    { // PEC/PEC: staged scatter (dense shared-memory window + bulk reductions)
-     FarArgsX X; X.A = A; X.slots = far_slots(ctx, A.pa); X.nElem = 0;
+     FarArgsX X; X.A = A; X.slots = far_slots(ctx, A.pa); X.nElem = 0; X.dbg = 0;
+     { const char *e = getenv("SCUFF_CUDA_FAR_DBG"); if (e) X.dbg = atoi(e); }      // timing experiments only (1: no bulk ops, 2: plain stores: wrong results)
      for (const auto &kv : ctx->matrices) if (kv.second.d == A.S.M) X.nElem = (long)kv.second.NR * kv.second.NC;
      if (X.slots && X.nElem > 0)
       { smem = FAR_STAGED_SMEM_BYTES(TB);
         if (kmode == KMODE_REAL) launch_far_staged<KMODE_REAL>(ctx, X, grid, smem, small);
         else if (kmode == KMODE_IMAG) launch_far_staged<KMODE_IMAG>(ctx, X, grid, smem, small);
         else launch_far_staged<KMODE_CPLX>(ctx, X, grid, smem, 0);
+        if (X.dbg & 16)
+         { unsigned long long h[16]; cudaStreamSynchronize(ctx->stream);
+           cudaMemcpy(h, A.counters, sizeof h, cudaMemcpyDeviceToHost);
+           const double tot = (double)(h[8] + h[9] + h[10] + h[11] + h[12] + h[13]);
+           fprintf(stderr, "far_staged phases (warp cycles, %% of total): compute %.1f  wait-read %.1f  stage %.1f  bulk-issue %.1f  outliers %.1f  drain %.1f   [total %.3g cycles, pairs %llu]\n",
+                   100 * h[8] / tot, 100 * h[9] / tot, 100 * h[10] / tot, 100 * h[11] / tot, 100 * h[12] / tot, 100 * h[13] / tot, tot, h[5]); }
         return; } }
   if (kmode == KMODE_REAL) launch_far_mode<KMODE_REAL>(ctx, A, grid, smem, psi, small);
   else if (kmode == KMODE_IMAG) launch_far_mode<KMODE_IMAG>(ctx, A, grid, smem, psi, small);

@@ -1,6 +1,8 @@
-"""Staged scatter of the far kernel (shared-memory window + cp.reduce.async.bulk, far_kernel.cu far_staged_kernel) against the
-scalar-atomic scatter it replaces: same far-pair matrices, same reference PPI counts, for complex and real (imaginary-frequency)
-matrices, symmetric diagonal blocks, off-diagonal blocks of a two-body geometry and column-block assembly."""
+"""The three scatter paths of the far kernel (far_kernel.cu) against each other: "scalar" (18 RED.ADD.F64 per panel pair),
+"staged" (shared-memory window per warp + cp.reduce.async.bulk, far_staged_kernel; used for column-block assembly) and
+"twopass" (plain stores to the panel-pair array + far_gather_kernel, the default for whole PEC/PEC blocks): same far-pair
+matrices, same reference PPI counts, for complex and real (imaginary-frequency) matrices, symmetric diagonal blocks,
+off-diagonal blocks of a two-body geometry and column-block assembly."""
 import os
 import sys
 import numpy as np
@@ -10,9 +12,11 @@ from conftest import GEODIR, ROOT
 pytestmark = pytest.mark.gpu
 
 
-def far_matrix(ps, geo, omega, staged, monkeypatch, small=None, real=False):
+def far_matrix(ps, geo, omega, mode, monkeypatch, small=None, real=False):
+    mode = {False: "scalar", True: "staged"}.get(mode, mode)
     monkeypatch.setenv("SCUFF_CUDA_FAR_ONLY", "1")
-    monkeypatch.setenv("SCUFF_CUDA_FAR_STAGED", "1" if staged else "0")
+    monkeypatch.setenv("SCUFF_CUDA_FAR_TWOPASS", "1" if mode == "twopass" else "0")
+    monkeypatch.setenv("SCUFF_CUDA_FAR_STAGED", "0" if mode == "scalar" else "1")
     if small is not None:
         monkeypatch.setenv("SCUFF_CUDA_FAR_SMALL", str(small))
     G = ps.RWGGeometry(geo)
@@ -26,24 +30,27 @@ def far_matrix(ps, geo, omega, staged, monkeypatch, small=None, real=False):
 def test_staged_equals_scalar(ps, name, omega, monkeypatch):
     geo = os.path.join(GEODIR, name + ".scuffgeo")
     for real in ((False, True) if np.real(omega) == 0 else (False,)):      # LHM_REAL matrices at imaginary frequency (8-byte entries)
-        M0, c0, p0 = far_matrix(ps, geo, omega, False, monkeypatch, real=real)
-        M1, c1, p1 = far_matrix(ps, geo, omega, True, monkeypatch, real=real)
-        err = np.linalg.norm(M1 - M0) / np.linalg.norm(M0)
-        print(name, omega, M0.dtype, "staged vs scalar rel diff", err, "counts", c1, "pairs", p1)
-        assert M0.dtype == M1.dtype and (M0.dtype == np.float64) == real
-        assert err <= 1e-13
-        assert list(c0) == list(c1) and list(p0) == list(p1)
+        M0, c0, p0 = far_matrix(ps, geo, omega, "scalar", monkeypatch, real=real)
+        for mode in ("staged", "twopass"):
+            M1, c1, p1 = far_matrix(ps, geo, omega, mode, monkeypatch, real=real)
+            err = np.linalg.norm(M1 - M0) / np.linalg.norm(M0)
+            print(name, omega, M0.dtype, mode, "vs scalar rel diff", err, "counts", c1, "pairs", p1)
+            assert M0.dtype == M1.dtype and (M0.dtype == np.float64) == real
+            assert err <= 1e-13
+            assert list(c0) == list(c1) and list(p0) == list(p1)
+            assert np.array_equal(M1, M1.T) == np.array_equal(M0, M0.T)
 
 
 def test_staged_small_phase_variants(ps, monkeypatch):
     """the small-phase polynomial variants (|k| (R_a+R_b) <= 1/8, 1/16) against the general range-reduced path"""
     geo = os.path.join(GEODIR, "PECSphere_501.scuffgeo")
     for omega in (0.05, 0.15, 0.05j, 0.15j):
-        Mg, _, _ = far_matrix(ps, geo, omega, True, monkeypatch, small=0)
-        Ms, _, _ = far_matrix(ps, geo, omega, True, monkeypatch, small=-1)
-        err = np.linalg.norm(Ms - Mg) / np.linalg.norm(Mg)
-        print("omega", omega, "small-phase vs general rel diff", err)
-        assert err <= 2e-14
+        for mode in ("staged", "twopass"):
+            Mg, _, _ = far_matrix(ps, geo, omega, mode, monkeypatch, small=0)
+            Ms, _, _ = far_matrix(ps, geo, omega, mode, monkeypatch, small=-1)
+            err = np.linalg.norm(Ms - Mg) / np.linalg.norm(Mg)
+            print("omega", omega, mode, "small-phase vs general rel diff", err)
+            assert err <= 2e-14
 
 
 def test_staged_icosphere_tiles_and_columns(ps, monkeypatch, tmp_path):
@@ -52,12 +59,13 @@ def test_staged_icosphere_tiles_and_columns(ps, monkeypatch, tmp_path):
     import meshgen
     geo = meshgen.write_sphere_geo(str(tmp_path), 16, None)
     omega = 0.8
-    M0, c0, _ = far_matrix(ps, geo, omega, False, monkeypatch)
-    M1, c1, _ = far_matrix(ps, geo, omega, True, monkeypatch)
-    err = np.linalg.norm(M1 - M0) / np.linalg.norm(M0)
-    print("icosphere nu=16 N", M0.shape[0], "staged vs scalar", err, c1)
-    assert err <= 1e-13 and list(c0) == list(c1)
-    assert np.array_equal(M1, M1.T)
+    M0, c0, _ = far_matrix(ps, geo, omega, "scalar", monkeypatch)
+    for mode in ("staged", "twopass"):
+        M1, c1, _ = far_matrix(ps, geo, omega, mode, monkeypatch)
+        err = np.linalg.norm(M1 - M0) / np.linalg.norm(M0)
+        print("icosphere nu=16 N", M0.shape[0], mode, "vs scalar", err, c1, ps.last_timing())
+        assert err <= 1e-13 and list(c0) == list(c1)
+        assert np.array_equal(M1, M1.T)
     G = ps.RWGGeometry(geo)
     N = G.TotalBFs
     cut = N // 3 + 1

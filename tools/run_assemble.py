@@ -28,6 +28,6 @@ for r in range(a.reps):
     wall = time.time() - t0
     t = ps.last_timing()
     farflop = 3492.0 * P * (P + 1) / 2
-    print(json.dumps(dict(N=G.TotalBFs, panels=P, wall_s=wall, ms_total=t[0], ms_far=t[1], ms_near=t[2],
+    print(json.dumps(dict(N=G.TotalBFs, panels=P, wall_s=wall, ms_total=t[0], ms_far=t[1], ms_near=t[2], ms_gather=t[4],
                           far_tflops=farflop / (t[1] * 1e-3) / 1e12, fp64_peak=peak, counts=G.ppi_counts(),
                           gelem_s=G.TotalBFs ** 2 / (t[0] * 1e-3) / 1e9)))
