@@ -26,7 +26,11 @@ static int fail(scuffcuda_context *ctx, const char *fmt, ...)
 namespace scuffcuda {   // far_kernel.cu
 void far_slots_release(scuffcuda_context *ctx);     // window/slot tables of the staged scatter
 void far_twopass_release(scuffcuda_context *ctx);   // panel-pair array and edge tables of the two-pass path
-int launch_far_gather(scuffcuda_context *ctx, double *ms);   // second pass (no-op unless launch_far chose the two-pass path)
+int launch_far_gather(scuffcuda_context *ctx);      // second pass (no-op unless launch_far chose the two-pass path); 1 = it mirrored
+double far_gather_elapsed_ms(scuffcuda_context *ctx);
+void far_set_zero_event(scuffcuda_context *ctx, cudaEvent_t ev);
+int far_gather_red();                               // gather with atomic adds (runs beside the near kernels) or read-modify-write after them
+int far_twopass_pending(scuffcuda_context *ctx);    // launch_far took the two-pass path: a gather is due   // 'matrix block cleared' event of the current assemble_block call
 }
 extern "C" {
 
@@ -392,11 +396,18 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   M->factored = false;
   ctx->timing[3] = 0.0;
 
+  // The block is cleared on the NEAR stream: the near/singular kernels follow it there, and a far pass that does not touch the
+  // matrix (two-pass path: it writes the panel-pair array) starts at once on the main stream; every other consumer on the
+  // main stream waits for ev[6] first.
+  CK(cudaStreamWaitEvent(sNear, ev[0], 0));
   if (!a->accumulate)
    { // a column-range call owns (and clears) only its columns of the block
      int c0 = a->col_offset, c1 = a->col_offset + NBFB;
      if (a->col_end > 0 && a->col_end != 0x7fffffff) { c0 = std::max(c0, a->col_begin); c1 = std::min(c1, a->col_end); }
-     launch_zero_block(ctx, *M, a->row_offset, NBFA, c0, c1 - c0); }
+     ctx->stream = sNear;
+     launch_zero_block(ctx, *M, a->row_offset, NBFA, c0, c1 - c0);
+     ctx->stream = sMain; }
+  CK(cudaEventRecord(ev[6], sNear));
 
   cdouble Omega(a->omega[0], a->omega[1]);
   const cdouble II(0.0, 1.0);
@@ -428,6 +439,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
         if (!T) return fail(ctx, "assemble_block: region %d has material but no periodic Green's function table (pass eps = 0 to omit it)", region);
         // (the table's k is Omega*sqrt(Eps*Mu) as CreateRegionGBA forms it, GBarAccelerator.cc:1047; prefactors use kA of
         //  SurfaceSurfaceInteractions.cc:165 — the caller passes both, they are not cross-checked, as in the reference)
+        CK(cudaStreamWaitEvent(sMain, ev[6], 0));
         CK(cudaEventRecord(ev[1], sMain));
         if (run_pbc_outer(ctx, Sa, Sb, *T, K, SP, ctx->dcounters)) return 1;
         CK(cudaEventRecord(ev[2], sMain));
@@ -440,13 +452,20 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      F.symmetric = SP.symmetric; F.useDisp = a->use_displacement ? 1 : 0;
      for (int i = 0; i < 3; i++) F.L[i] = a->use_displacement ? a->displacement[i] : 0.0;
      F.K = K; F.S = SP; F.counters = ctx->dcounters;
-     CK(cudaEventRecord(ev[1], sMain));           // also: the block is zeroed, the counters reset
+     far_set_zero_event(ctx, ev[6]);              // launch_far waits for it unless it takes the two-pass path
+     CK(cudaEventRecord(ev[1], sMain));           // the counters are reset
      launch_far(ctx, F, kmode);
      CK(cudaGetLastError());
      CK(cudaEventRecord(ev[2], sMain));
+     // Two-pass path with the atomic gather: the FP64-bound first pass has the SMs to itself, then the HBM-bound gather
+     // runs beside the latency-bound near/singular kernels.  Otherwise the near kernels run beside the far kernel.
+     const bool gatherBesideNear = far_twopass_pending(ctx) && far_gather_red();
+     if (gatherBesideNear)
+      { CK(cudaStreamWaitEvent(sMain, ev[6], 0));
+        launch_far_gather(ctx); CK(cudaGetLastError()); }
      if (!a->far_only)
-      { // near/singular work on the second stream, concurrently with the far kernel
-        CK(cudaStreamWaitEvent(sNear, ev[1], 0));
+      { // near/singular work on the second stream
+        CK(cudaStreamWaitEvent(sNear, gatherBesideNear ? ev[2] : ev[1], 0));  // (the counters are reset; the block was cleared on this stream)
         CK(cudaEventRecord(ev[4], sNear));
         ctx->stream = sNear;
         int rc = run_near(ctx, nsa, nsb, a, K, SP, kmode, std::abs(k));
@@ -455,13 +474,16 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
         CK(cudaEventRecord(ev[5], sNear));
         CK(cudaStreamWaitEvent(sMain, ev[5], 0)); }
      // two-pass far path: the gather adds the panel-pair values to what the near kernels stamped (and mirrors a symmetric block)
-     if (launch_far_gather(ctx, &gatherMs)) mirrored = true;
+     CK(cudaStreamWaitEvent(sMain, ev[6], 0));
+     if (launch_far_gather(ctx)) mirrored = true;
      CK(cudaGetLastError());
      CK(cudaEventRecord(ev[3], sMain));
      CK(cudaEventSynchronize(ev[3]));
      float t; cudaEventElapsedTime(&t, ev[1], ev[2]); farMs += t;
+     gatherMs += far_gather_elapsed_ms(ctx);
      if (!a->far_only) { cudaEventElapsedTime(&t, ev[4], ev[5]); nearMs += t; }
    }
+  CK(cudaStreamWaitEvent(sMain, ev[6], 0));
   if (a->symmetric && a->col_end <= 0 && !mirrored)
    launch_symmetrize(ctx, *M, a->row_offset, NBFA);
   CK(cudaGetLastError());

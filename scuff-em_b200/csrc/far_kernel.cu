@@ -1029,13 +1029,13 @@ static double surface_rmax(scuffcuda_context *ctx, const PanelRec *d)
 // half hidden under the FP64-bound pass 1).  Q is sized NP^2/2 x 144 B for a symmetric block; when it does not fit the budget
 // (SCUFF_CUDA_FAR_QMAX_GB, default 40) the staged-atomic kernel is used instead.
 // ------------------------------------------------------------------------------------------------------------------
-struct FarQ { cd *Q; int symmetric; int NApad; };
-// offset (in complex elements) of the row of b-panel pb and its a-extent NA; element (pb, j, pa, i) = row + (j * NA + pa) * 3 + i
+struct FarQ { cd *Q; int symmetric; int NApad; int nc; };   // nc complex values per (Q_a,Q_b) combination: 1 (PEC/PEC: g0), 2 (g0, g1)
+// offset (in complex elements) of the row of b-panel pb and its a-extent NA; element (pb, j, pa, i, c) = row + ((j * NA + pa) * 3 + i) * nc + c
 __device__ __forceinline__ long farq_row(const FarQ &L, int pb, int &NA)
 { if (L.symmetric)
    { const long t = pb >> 7; NA = (int)((t + 1) << 7);
-     return 9L * 128 * 128 * (t * (t + 1) / 2) + (long)(pb - (int)(t << 7)) * 9 * NA; }
-  NA = L.NApad; return (long)pb * 9 * L.NApad;
+     return L.nc * (9L * 128 * 128 * (t * (t + 1) / 2) + (long)(pb - (int)(t << 7)) * 9 * NA); }
+  NA = L.NApad; return (long)L.nc * pb * 9 * L.NApad;
 }
 struct FarArgsQ { FarArgs A; FarQ L; };
 
@@ -1121,51 +1121,279 @@ far_pass1_kernel(const __grid_constant__ FarArgsQ X)
   if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
 }
 
+// Pass 1 for blocks with a dielectric side: per (Q_a,Q_b) combination the two values the stamps need,
+//   g0 = l_a l_b H0 ,  g1 = l_a l_b H1 / (ik)      (EdgeEdgeInteractions.cc:183-188, SurfaceSurfaceInteractions.cc:219-327)
+// (the region prefactors c1, c2, c3 are applied by the gather).
+template <int KMODE, int SMALL>
+__global__ void __launch_bounds__(FAR_THREADS, 2)
+far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
+{ const FarArgs &A = X.A;
+  extern __shared__ __align__(128) double sm[];
+  __shared__ __align__(8) uint64_t bar;
+  typedef typename KScalar<KMODE>::type S;
+  const int TB = A.TA;
+  const int b0 = blockIdx.y * TB;
+  const int aBase = blockIdx.x * FAR_THREADS;
+  const int nB = min(TB, A.NPb - b0);
+  if (A.symmetric && b0 + nB - 1 < aBase) return;
+  const int tid = threadIdx.x;
+  double *sXa = sm + TB * 36 + tid;                    // element k at sXa[k * FAR_THREADS]
+  double *sSt = sm + TB * 36 + 18 * FAR_THREADS + tid;
+  int *sEi = (int *)(sm + TB * 36 + 34 * FAR_THREADS) + tid;
+  unsigned int *sCnt = (unsigned int *)sEi + 3 * FAR_THREADS;
+  sCnt[0] = 0; sCnt[FAR_THREADS] = 0;
+
+  if (tid == 0)
+   { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)) : "memory");
+     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  __syncthreads();
+  if (tid == 0) tma_load_1d(sm, A.pb + b0, (uint32_t)(nB * sizeof(PanelRec)), &bar);
+
+  const int pa = aBase + tid;
+  const bool live = pa < A.NPa && !(A.symmetric && pa >= b0 + nB - 1);
+  const PanelRec *Pa = A.pa + (pa < A.NPa ? pa : 0);
+#pragma unroll
+  for (int i = 0; i < 18; i++) sXa[i * FAR_THREADS] = Pa->x[i];
+  int na = 0;
+#pragma unroll
+  for (int m = 0; m < 3; m++)
+   { const double v0 = Pa->V[m];
+     sSt[m * FAR_THREADS] = v0;                                      // V_0
+     sSt[(3 + m) * FAR_THREADS] = Pa->V[3 + m] - v0;                 // A
+     sSt[(6 + m) * FAR_THREADS] = Pa->V[6 + m] - v0;                 // B
+     sSt[(9 + m) * FAR_THREADS] = Pa->sl[m];
+     sSt[(12 + m) * FAR_THREADS] = Pa->C[m];
+     na += (Pa->ei[m] >= 0); }
+  sSt[15 * FAR_THREADS] = Pa->R;
+  mbar_wait(&bar, 0);
+  if (!live) return;
+
+  for (int ib = 0; ib < nB; ib++)
+   { const int pb = b0 + ib;
+     if (A.symmetric && pb <= pa) continue;            // the gather reads pairs pa < pb only
+     const double *Pb = sm + ib * 36;
+     double D[3];
+     bool far;
+     { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
+       far = pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D); }
+     int NA; const long row = farq_row(X.L, pb, NA);
+     double2 *q = reinterpret_cast<double2 *>(X.L.Q + row + (long)pa * 6);
+     if (!far)
+      {
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+         for (int n = 0; n < 6; n++) q[(long)j * NA * 6 + n] = make_double2(0.0, 0.0);
+        continue; }
+     const int *eb3 = (const int *)(Pb + 34);
+     sCnt[0] += 1;
+     sCnt[FAR_THREADS] += (unsigned int)(na * ((eb3[0] >= 0) + (eb3[1] >= 0) + (eb3[2] >= 0)));
+     double r0 = 0.0;
+     if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
+     S mPhi[3][3], mPsi[3][3];
+     far_moments<KMODE, true, SMALL, S>(sXa, Pb, D, A.K, r0, mPhi, mPsi);
+     cd e0 = mk(1.0, 0.0), ooik = A.K.ooik;
+     if (SMALL) { e0 = tocd(far_pair_factor<KMODE, S>(A.K, r0)); ooik = ooik * e0; }      // the pair factor rides on the two prefactors
+     double Aa[3], Ba[3], Ab[3], Bb[3], E00[3];
+#pragma unroll
+     for (int m = 0; m < 3; m++)
+      { Aa[m] = sSt[(3 + m) * FAR_THREADS]; Ba[m] = sSt[(6 + m) * FAR_THREADS];
+        Ab[m] = Pb[7 + m] - Pb[4 + m]; Bb[m] = Pb[10 + m] - Pb[4 + m];
+        E00[m] = sSt[m * FAR_THREADS] - (Pb[4 + m] + (A.useDisp ? A.L[m] : 0.0)); }
+     const double dAA = dot3(Aa, Ab), dAB = dot3(Aa, Bb), dBA = dot3(Ba, Ab), dBB = dot3(Ba, Bb);
+     // H0_ij = T - [j>0] P_j - [i>0] Q_i + [i>0][j>0] d_ij m00 + c4 m00  (see contract_pec)
+     S T0, P1, P2, Q1, Q2;
+     szero(T0); szero(P1); szero(P2); szero(Q1); szero(Q2);
+     fma_acc(T0, dAA, mPhi[1][1]); fma_acc(T0, dAB, mPhi[1][2]); fma_acc(T0, dBA, mPhi[2][1]); fma_acc(T0, dBB, mPhi[2][2]);
+     fma_acc(P1, dAA, mPhi[1][0]); fma_acc(P1, dBA, mPhi[2][0]);
+     fma_acc(P2, dAB, mPhi[1][0]); fma_acc(P2, dBB, mPhi[2][0]);
+     fma_acc(Q1, dAA, mPhi[0][1]); fma_acc(Q1, dAB, mPhi[0][2]);
+     fma_acc(Q2, dBA, mPhi[0][1]); fma_acc(Q2, dBB, mPhi[0][2]);
+     const cd m00 = cscale(e0, mPhi[0][0]);
+     const cd cT = cscale(e0, T0) + A.K.c4 * m00;
+     const cd cP1 = cscale(e0, P1), cP2 = cscale(e0, P2), cQ1 = cscale(e0, Q1), cQ2 = cscale(e0, Q2);
+     // H1_ij = sum_{X in {A,B}, Y in {A',B'}} ((X x Y).E_ij) <(x - d_i)(y - d_j) Psi> ,  E_ij = E00 + {0,A,B}_i - {0,A',B'}_j
+     double tAA, tAB, tBA, tBB, AbN, BbN, AaNp, BaNp;
+     { double Na[3], Nb[3], eA[3], eB[3];
+       cross3(Aa, Ba, Na); cross3(Ab, Bb, Nb);
+       cross3(E00, Aa, eA); cross3(E00, Ba, eB);         // (X x Y).E = Y.(E x X)
+       tAA = dot3(Ab, eA); tAB = dot3(Bb, eA); tBA = dot3(Ab, eB); tBB = dot3(Bb, eB);
+       AbN = dot3(Ab, Na); BbN = dot3(Bb, Na); AaNp = dot3(Aa, Nb); BaNp = dot3(Ba, Nb); }
+     S q1s[3], q2s[3];
+#pragma unroll
+     for (int n = 0; n < 3; n++) { q1s[n] = ssub(mPsi[1][n], mPsi[0][n]); q2s[n] = ssub(mPsi[2][n], mPsi[0][n]); }
+#pragma unroll
+     for (int i = 0; i < 3; i++)
+      { const double sla = sSt[(9 + i) * FAR_THREADS];
+        const S *UQ = (i == 1) ? q1s : mPsi[1], *VQ = (i == 2) ? q2s : mPsi[2];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+         { cd h0 = (j == 0) ? cT : (j == 1 ? cT - cP1 : cT - cP2);
+           if (i > 0)
+            { h0 = h0 - (i == 1 ? cQ1 : cQ2);
+              if (j > 0) { const double d = (i == 1) ? (j == 1 ? dAA : dAB) : (j == 1 ? dBA : dBB); h0.x = fma(d, m00.x, h0.x); h0.y = fma(d, m00.y, h0.y); } }
+           const S Pu = (j == 1) ? ssub(UQ[1], UQ[0]) : UQ[1], Pv = (j == 2) ? ssub(UQ[2], UQ[0]) : UQ[2];
+           const S Qu = (j == 1) ? ssub(VQ[1], VQ[0]) : VQ[1], Qv = (j == 2) ? ssub(VQ[2], VQ[0]) : VQ[2];
+           const double cAA = tAA - (i == 2 ? AbN : 0.0) - (j == 2 ? AaNp : 0.0);
+           const double cAB = tAB - (i == 2 ? BbN : 0.0) + (j == 1 ? AaNp : 0.0);
+           const double cBA = tBA + (i == 1 ? AbN : 0.0) - (j == 2 ? BaNp : 0.0);
+           const double cBB = tBB + (i == 1 ? BbN : 0.0) + (j == 1 ? BaNp : 0.0);
+           S h1; szero(h1);
+           fma_acc(h1, cAA, Pu); fma_acc(h1, cAB, Pv); fma_acc(h1, cBA, Qu); fma_acc(h1, cBB, Qv);
+           const double sc = sla * Pb[31 + j];
+           const cd g0 = sc * h0, g1 = sc * cscale(ooik, h1);
+           q[(long)j * NA * 6 + 2 * i] = make_double2(g0.x, g0.y);
+           q[(long)j * NA * 6 + 2 * i + 1] = make_double2(g1.x, g1.y); } }
+   }
+  if (sCnt[FAR_THREADS]) atomicAdd(A.counters, (unsigned long long)sCnt[FAR_THREADS]);
+  if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
+}
+
 // edge -> its two panels and the local index of the edge in each: {pP, iP, pM, iM}, -1 where there is none
 struct GatherArgs
 { FarQ L; const int4 *edgeA, *edgeB; int NEa, NEb;
-  double *M; long ld; int rowOff, colOff; };
+  double *M; long ld; int rowOff, colOff;
+  int aPEC, bPEC; cd c1, c2, c3; };
 
-template <int W, bool SYM>
+// Tile = 32 columns (b-edges) x GR*32 rows (a-edges); blockIdx.x walks DOWN the rows of one column tile so that CTAs in flight
+// at the same time read neighbouring pieces of the same Q rows (DRAM pages, shared sectors) and write neighbouring
+// segments of the same 32 matrix columns.  Q is read once (streaming loads), the matrix written once per triangle.
+#define FAR_GATHER_GR 2
+// RED = true: the sums are ADDED with atomics instead of read-modify-written, so the gather may run while the near/singular
+// kernels are still stamping (it then overlaps the latency-bound Taylor-Duffy work with its HBM-bound streaming); the mirror
+// image is left to the symmetrize pass.
+template <int W, bool SYM, bool RED>
 __global__ void __launch_bounds__(256)
 far_gather_kernel(const GatherArgs G)
-{ __shared__ double tile[32][33 * W];
-  const int bx = blockIdx.x, by = blockIdx.y;      // tile: rows (a-edges) by*32.., columns (b-edges) bx*32..
-  if (SYM && by > bx) return;
+{ __shared__ double tile[RED ? 1 : 32][RED ? 1 : 33 * W];
+  const int bx = blockIdx.y;                       // column tile
   const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
-  const int ea = by * 32 + tx;
-  int4 Ea = make_int4(-1, 0, -1, 0);
-  if (ea < G.NEa) Ea = G.edgeA[ea];
-  for (int j = ty; j < 32; j += 8)
-   { const int eb = bx * 32 + j;
-     if (ea >= G.NEa || eb >= G.NEb || (SYM && ea >= eb)) continue;
-     const int4 Eb = G.edgeB[eb];
-     double sx = 0.0, sy = 0.0;
+  for (int g = 0; g < FAR_GATHER_GR; g++)
+   { const int by = blockIdx.x * FAR_GATHER_GR + g;     // row tile
+     if (by * 32 >= G.NEa || (SYM && by > bx)) break;
+     const int ea = by * 32 + tx;
+     int4 Ea = make_int4(-1, 0, -1, 0);
+     if (ea < G.NEa) Ea = G.edgeA[ea];
+     for (int j = ty; j < 32; j += 8)
+      { const int eb = bx * 32 + j;
+        if (ea >= G.NEa || eb >= G.NEb || (SYM && ea >= eb)) continue;
+        const int4 Eb = G.edgeB[eb];
+        double sx = 0.0, sy = 0.0;
 #pragma unroll
-     for (int u = 0; u < 2; u++)
+        for (int u = 0; u < 2; u++)
 #pragma unroll
-      for (int v = 0; v < 2; v++)
-       { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = v ? Eb.z : Eb.x, jb = v ? Eb.w : Eb.y;
-         if (pa < 0 || pb < 0) continue;
-         if (SYM)
-          { if (pa == pb) continue;
-            if (pa > pb) { int t = pa; pa = pb; pb = t; t = ia; ia = jb; jb = t; } }   // the pair is stored once, with the lower panel as 'a'
-         int NA; const long row = farq_row(G.L, pb, NA);
-         const double2 q = *reinterpret_cast<const double2 *>(G.L.Q + row + ((long)jb * NA + pa) * 3 + ia);
-         sx += q.x; sy += q.y; }
-     const size_t idx = ((size_t)(G.rowOff + ea) + (size_t)(G.colOff + eb) * (size_t)G.ld) * W;
-     if (W == 2)
-      { double2 m = *reinterpret_cast<double2 *>(G.M + idx); m.x += sx; m.y += sy;
-        *reinterpret_cast<double2 *>(G.M + idx) = m; tile[j][2 * tx] = m.x; tile[j][2 * tx + 1] = m.y; }
-     else { const double m = G.M[idx] + sx; G.M[idx] = m; tile[j][tx] = m; }
+         for (int v = 0; v < 2; v++)
+          { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = v ? Eb.z : Eb.x, jb = v ? Eb.w : Eb.y;
+            if (pa < 0 || pb < 0) continue;
+            if (SYM)
+             { if (pa == pb) continue;
+               if (pa > pb) { int t = pa; pa = pb; pb = t; t = ia; ia = jb; jb = t; } }   // the pair is stored once, with the lower panel as 'a'
+            int NA; const long row = farq_row(G.L, pb, NA);
+            const double2 q = __ldcs(reinterpret_cast<const double2 *>(G.L.Q + row + ((long)jb * NA + pa) * 3 + ia));
+            sx += q.x; sy += q.y; }
+        const size_t idx = ((size_t)(G.rowOff + ea) + (size_t)(G.colOff + eb) * (size_t)G.ld) * W;
+        if (RED)
+         { if (sx != 0.0) atomicAdd(G.M + idx, sx);
+           if (W == 2 && sy != 0.0) atomicAdd(G.M + idx + 1, sy); }
+        else if (W == 2)
+         { double2 m = *reinterpret_cast<double2 *>(G.M + idx); m.x += sx; m.y += sy;
+           __stcs(reinterpret_cast<double2 *>(G.M + idx), m); tile[j][2 * tx] = m.x; tile[j][2 * tx + 1] = m.y; }
+        else { const double m = G.M[idx] + sx; __stcs(G.M + idx, m); tile[j][tx] = m; }
+      }
+     if (!SYM || RED) continue;
+     __syncthreads();
+     for (int j = ty; j < 32; j += 8)
+      { const int r = bx * 32 + tx, c = by * 32 + j;   // mirror image: lower(r, c) = upper(c, r)
+        if (r < G.NEa && c < G.NEa && r > c)
+         { const size_t idx = ((size_t)(G.rowOff + r) + (size_t)(G.colOff + c) * (size_t)G.ld) * W;
+           if (W == 2) __stcs(reinterpret_cast<double2 *>(G.M + idx), make_double2(tile[tx][2 * j], tile[tx][2 * j + 1]));
+           else __stcs(G.M + idx, tile[tx][j]); } }
+     __syncthreads();
    }
-  if (!SYM) return;
-  __syncthreads();
-  for (int j = ty; j < 32; j += 8)
-   { const int r = bx * 32 + tx, c = by * 32 + j;   // mirror image: lower(r, c) = upper(c, r)
-     if (r < G.NEa && c < G.NEa && r > c)
-      { const size_t idx = ((size_t)(G.rowOff + r) + (size_t)(G.colOff + c) * (size_t)G.ld) * W;
-        for (int q = 0; q < W; q++) G.M[idx + q] = tile[tx][j * W + q]; } }
+}
+
+// Gather for blocks with a dielectric side: G0 = sum g0, G1 = sum g1 over the <= 4 panel pairs of the edge pair, stamped as
+//   dielectric/dielectric: [ c1 G0  c2 G1 ; c2 G1  c3 G0 ] at (2 e_a, 2 e_b);  PEC/dielectric: [ c1 G0  c2 G1 ] at (e_a, 2 e_b);
+//   dielectric/PEC: [ c1 G0 ; c2 G1 ] at (2 e_a, e_b)     (SurfaceSurfaceInteractions.cc:219-327).  The matrix is complex or real
+// (W doubles per entry; a real matrix keeps the real parts, HMatrix.cc:419-447).  SYM (same dielectric surface): entries e_a < e_b,
+// and the mirror image of each of the four component planes through shared memory.
+template <int W, bool SYM, bool RED>
+__global__ void __launch_bounds__(256)
+far_gather_psi_kernel(const GatherArgs G)
+{ __shared__ double tile[RED ? 1 : 32][RED ? 1 : 33 * W];
+  const int bx = blockIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
+  const int wa = G.aPEC ? 1 : 2, wb = G.bPEC ? 1 : 2;
+  for (int g = 0; g < FAR_GATHER_GR; g++)
+   { const int by = blockIdx.x * FAR_GATHER_GR + g;
+     if (by * 32 >= G.NEa || (SYM && by > bx)) break;
+     const int ea = by * 32 + tx;
+     int4 Ea = make_int4(-1, 0, -1, 0);
+     if (ea < G.NEa) Ea = G.edgeA[ea];
+     cd v[4][4];                                   // [column j of this thread: ty, ty+8, ..][component plane]
+#pragma unroll
+     for (int jj = 0; jj < 4; jj++)
+      { const int j = ty + 8 * jj, eb = bx * 32 + j;
+#pragma unroll
+        for (int c = 0; c < 4; c++) v[jj][c] = mk(0.0, 0.0);
+        if (ea >= G.NEa || eb >= G.NEb || (SYM && ea >= eb)) continue;
+        const int4 Eb = G.edgeB[eb];
+        double g0x = 0, g0y = 0, g1x = 0, g1y = 0;
+#pragma unroll
+        for (int u = 0; u < 2; u++)
+#pragma unroll
+         for (int w = 0; w < 2; w++)
+          { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = w ? Eb.z : Eb.x, jb = w ? Eb.w : Eb.y;
+            if (pa < 0 || pb < 0) continue;
+            if (SYM)
+             { if (pa == pb) continue;
+               if (pa > pb) { int t = pa; pa = pb; pb = t; t = ia; ia = jb; jb = t; } }
+            int NA; const long row = farq_row(G.L, pb, NA);
+            const double2 *q = reinterpret_cast<const double2 *>(G.L.Q + row + (((long)jb * NA + pa) * 3 + ia) * 2);
+            const double2 a = __ldcs(q), b = __ldcs(q + 1);
+            g0x += a.x; g0y += a.y; g1x += b.x; g1y += b.y; }
+        const cd G0 = mk(g0x, g0y), G1 = mk(g1x, g1y);
+        const cd v11 = G.c1 * G0, v12 = G.c2 * G1, v22 = G.c3 * G0;
+        // component planes: 0 (X,Y), 1 (X,Y+1), 2 (X+1,Y), 3 (X+1,Y+1)
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+         { const int dr = c >> 1, dc = c & 1;
+           if (dr >= wa || dc >= wb) continue;
+           const cd val = (c == 0) ? v11 : (c == 3 ? v22 : v12);
+           const size_t idx = ((size_t)(G.rowOff + wa * ea + dr) + (size_t)(G.colOff + wb * eb + dc) * (size_t)G.ld) * W;
+           if (RED)
+            { if (val.x != 0.0) atomicAdd(G.M + idx, val.x);
+              if (W == 2 && val.y != 0.0) atomicAdd(G.M + idx + 1, val.y); }
+           else if (W == 2)
+            { double2 m = *reinterpret_cast<double2 *>(G.M + idx); m.x += val.x; m.y += val.y;
+              __stcs(reinterpret_cast<double2 *>(G.M + idx), m); v[jj][c] = mk(m.x, m.y); }
+           else { const double m = G.M[idx] + val.x; __stcs(G.M + idx, m); v[jj][c] = mk(m, 0.0); } } }
+     if (!SYM || RED) continue;
+     // inside the 2x2 block of an edge with itself (near contributions only): (2e+1, 2e) = (2e, 2e+1)
+     if (bx == by && ty == 0 && ea < G.NEa)
+      { const size_t up = ((size_t)(G.rowOff + 2 * ea) + (size_t)(G.colOff + 2 * ea + 1) * (size_t)G.ld) * W;
+        const size_t lo = ((size_t)(G.rowOff + 2 * ea + 1) + (size_t)(G.colOff + 2 * ea) * (size_t)G.ld) * W;
+        for (int q = 0; q < W; q++) G.M[lo + q] = G.M[up + q]; }
+     // mirror image, one component plane at a time: lower(2 e_b + q, 2 e_a + p) = upper(2 e_a + p, 2 e_b + q)
+#pragma unroll
+     for (int c = 0; c < 4; c++)
+      { __syncthreads();
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++)
+         { const int j = ty + 8 * jj;
+           if (W == 2) { tile[j][2 * tx] = v[jj][c].x; tile[j][2 * tx + 1] = v[jj][c].y; } else tile[j][tx] = v[jj][c].x; }
+        __syncthreads();
+        const int dr = c >> 1, dc = c & 1;
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++)
+         { const int j = ty + 8 * jj;
+           const int eb = bx * 32 + tx, eA = by * 32 + j;      // this thread now writes the image of (e_a = eA, e_b = eb)
+           if (eb < G.NEa && eA < G.NEa && eb > eA)
+            { const size_t idx = ((size_t)(G.rowOff + 2 * eb + dc) + (size_t)(G.colOff + 2 * eA + dr) * (size_t)G.ld) * W;
+              if (W == 2) __stcs(reinterpret_cast<double2 *>(G.M + idx), make_double2(tile[tx][2 * j], tile[tx][2 * j + 1]));
+              else __stcs(G.M + idx, tile[tx][j]); } } }
+     __syncthreads();
+   }
 }
 
 // ---- host side of the staged scatter: window and slots of every 32-panel group of a surface ----
@@ -1227,7 +1455,9 @@ void far_slots_release(scuffcuda_context *ctx)
 struct FarTwoPassState
 { cd *Q = nullptr; size_t qBytes = 0;                       // panel-pair array, grown on demand, kept for the life of the context
   std::map<const PanelRec *, std::pair<uint64_t, int4 *> > edges;   // surface -> (generation, device edge table)
-  bool pending = false; GatherArgs G; bool sym = false; int isReal = 0; int NEa = 0, NEb = 0; };
+  bool pending = false; GatherArgs G; bool sym = false; int isReal = 0; int NEa = 0, NEb = 0;
+  cudaEvent_t zeroEvent = nullptr;
+  cudaEvent_t g0 = nullptr, g1 = nullptr; bool timed = false; };   // gather start / end
 static std::map<scuffcuda_context *, FarTwoPassState> g_twoPass;
 
 static const int4 *far_edge_table(scuffcuda_context *ctx, FarTwoPassState &T, const PanelRec *d, int &NE)
@@ -1250,11 +1480,16 @@ static const int4 *far_edge_table(scuffcuda_context *ctx, FarTwoPassState &T, co
   slot.first = S->generation;
   return slot.second;
 }
+void far_set_zero_event(scuffcuda_context *ctx, cudaEvent_t ev)
+{ std::lock_guard<std::mutex> lock(g_farSlotsLock);
+  g_twoPass[ctx].zeroEvent = ev;
+}
 void far_twopass_release(scuffcuda_context *ctx)
 { std::lock_guard<std::mutex> lock(g_farSlotsLock);
   auto it = g_twoPass.find(ctx);
   if (it == g_twoPass.end()) return;
   if (it->second.Q) cudaFree(it->second.Q);
+  if (it->second.g0) { cudaEventDestroy(it->second.g0); cudaEventDestroy(it->second.g1); }
   for (auto &e : it->second.edges) if (e.second.second) cudaFree(e.second.second);
   g_twoPass.erase(it);
 }
@@ -1271,25 +1506,60 @@ static void launch_far_pass1(scuffcuda_context *ctx, const FarArgsQ &X, dim3 gri
   else launch_far_pass1_inst<KMODE, 0>(ctx, X, grid, smem);
 }
 
+template <int KMODE, int SMALL>
+static void launch_far_pass1_psi_inst(scuffcuda_context *ctx, const FarArgsQ &X, dim3 grid, size_t smem)
+{ cudaFuncSetAttribute(far_pass1_psi_kernel<KMODE, SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  far_pass1_psi_kernel<KMODE, SMALL><<<grid, FAR_THREADS, smem, ctx->stream>>>(X);
+}
+template <int KMODE>
+static void launch_far_pass1_psi(scuffcuda_context *ctx, const FarArgsQ &X, dim3 grid, size_t smem, int small)
+{ if (small == 2) launch_far_pass1_psi_inst<KMODE, 2>(ctx, X, grid, smem);
+  else if (small == 1) launch_far_pass1_psi_inst<KMODE, 1>(ctx, X, grid, smem);
+  else launch_far_pass1_psi_inst<KMODE, 0>(ctx, X, grid, smem);
+}
+
 // Second pass of the two-pass path: called by assemble_block once the near/singular kernels of this region pass have finished
 // stamping (the gather adds to their entries without atomics).  Returns 1 if it also wrote the mirror image of a symmetric block.
-int launch_far_gather(scuffcuda_context *ctx, double *ms)
-{ FarTwoPassState *T;
+// gather mode: 1 = atomic adds, concurrent with the near kernels, mirror left to symmetrize (default); 0 = read-modify-write after
+// the near kernels, mirror included (SCUFF_CUDA_FAR_GATHER_RED=0)
+int far_gather_red()
+{ const char *e = getenv("SCUFF_CUDA_FAR_GATHER_RED"); return e ? atoi(e) : 1; }
+int far_twopass_pending(scuffcuda_context *ctx)
+{ std::lock_guard<std::mutex> lock(g_farSlotsLock);
+  auto it = g_twoPass.find(ctx);
+  return it != g_twoPass.end() && it->second.pending;
+}
+int launch_far_gather(scuffcuda_context *ctx)
+{ const bool red = far_gather_red() != 0;
+  FarTwoPassState *T;
   { std::lock_guard<std::mutex> lock(g_farSlotsLock);
     auto it = g_twoPass.find(ctx);
     if (it == g_twoPass.end() || !it->second.pending) return 0;
     T = &it->second; }
   T->pending = false;
-  dim3 grid((T->NEb + 31) / 32, (T->NEa + 31) / 32), block(32, 8);
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  cudaEventRecord(e0, ctx->stream);
+  dim3 grid(((T->NEa + 31) / 32 + FAR_GATHER_GR - 1) / FAR_GATHER_GR, (T->NEb + 31) / 32), block(32, 8);
+  if (!T->g0) { cudaEventCreate(&T->g0); cudaEventCreate(&T->g1); }
+  cudaEventRecord(T->g0, ctx->stream);
   ctx->launches++;
-  if (T->sym) { if (T->isReal) far_gather_kernel<1, true><<<grid, block, 0, ctx->stream>>>(T->G); else far_gather_kernel<2, true><<<grid, block, 0, ctx->stream>>>(T->G); }
-  else { if (T->isReal) far_gather_kernel<1, false><<<grid, block, 0, ctx->stream>>>(T->G); else far_gather_kernel<2, false><<<grid, block, 0, ctx->stream>>>(T->G); }
-  cudaEventRecord(e1, ctx->stream); cudaEventSynchronize(e1);
-  float t = 0; cudaEventElapsedTime(&t, e0, e1); if (ms) *ms += t;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  return T->sym ? 1 : 0;
+#define FAR_GATHER_LAUNCH(K, W, SYM, RED) K<W, SYM, RED><<<grid, block, 0, ctx->stream>>>(T->G)
+#define FAR_GATHER_PICK(K) do { \
+    if (T->sym) { if (T->isReal) { if (red) FAR_GATHER_LAUNCH(K, 1, true, true); else FAR_GATHER_LAUNCH(K, 1, true, false); } \
+                  else { if (red) FAR_GATHER_LAUNCH(K, 2, true, true); else FAR_GATHER_LAUNCH(K, 2, true, false); } } \
+    else { if (T->isReal) { if (red) FAR_GATHER_LAUNCH(K, 1, false, true); else FAR_GATHER_LAUNCH(K, 1, false, false); } \
+           else { if (red) FAR_GATHER_LAUNCH(K, 2, false, true); else FAR_GATHER_LAUNCH(K, 2, false, false); } } } while (0)
+  if (T->G.L.nc == 2) FAR_GATHER_PICK(far_gather_psi_kernel); else FAR_GATHER_PICK(far_gather_kernel);
+  cudaEventRecord(T->g1, ctx->stream); T->timed = true;
+  return (T->sym && !red) ? 1 : 0;
+}
+// duration of the last gather (blocks until it has finished)
+double far_gather_elapsed_ms(scuffcuda_context *ctx)
+{ std::lock_guard<std::mutex> lock(g_farSlotsLock);
+  auto it = g_twoPass.find(ctx);
+  if (it == g_twoPass.end() || !it->second.timed) return 0.0;
+  it->second.timed = false;
+  cudaEventSynchronize(it->second.g1);
+  float t = 0; cudaEventElapsedTime(&t, it->second.g0, it->second.g1);
+  return t;
 }
 
 template <int KMODE, int SMALL>
@@ -1332,14 +1602,14 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   ctx->launches++;
   int twoPassEnv = 1;
   { const char *e = getenv("SCUFF_CUDA_FAR_TWOPASS"); if (e) twoPassEnv = atoi(e); }
-  if (!psi && twoPassEnv && A.S.colHi == 0x7fffffff)
-   { // PEC/PEC, whole block: two-pass path (plain stores to the panel-pair array, gathered after the near kernels)
+  if (twoPassEnv && A.S.colHi == 0x7fffffff)
+   { // whole block: two-pass path (plain stores to the panel-pair array, gathered after the near kernels)
      std::unique_lock<std::mutex> lock(g_farSlotsLock);
      FarTwoPassState &T = g_twoPass[ctx];
      lock.unlock();
      const long NApad = (long)aTiles * FAR_THREADS;
      const long tiles = (A.NPb + 127) / 128;
-     const size_t need = sizeof(cd) * (size_t)(A.symmetric ? 9L * 128 * 128 * (tiles * (tiles + 1) / 2) : (long)A.NPb * 9 * NApad);
+     const size_t need = sizeof(cd) * (size_t)(psi ? 2 : 1) * (size_t)(A.symmetric ? 9L * 128 * 128 * (tiles * (tiles + 1) / 2) : (long)A.NPb * 9 * NApad);
      double qmaxGB = 40.0;
      { const char *e = getenv("SCUFF_CUDA_FAR_QMAX_GB"); if (e) qmaxGB = atof(e); }
      bool ok = (double)need <= qmaxGB * 1073741824.0;
@@ -1351,14 +1621,23 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
      int NEa = 0, NEb = 0;
      const int4 *ea = ok ? far_edge_table(ctx, T, A.pa, NEa) : nullptr, *eb = ok ? far_edge_table(ctx, T, A.pb, NEb) : nullptr;
      if (ok && ea && eb)
-      { FarArgsQ X; X.A = A; X.L.Q = T.Q; X.L.symmetric = A.symmetric; X.L.NApad = (int)NApad;
-        if (kmode == KMODE_REAL) launch_far_pass1<KMODE_REAL>(ctx, X, grid, smem, small);
+      { FarArgsQ X; X.A = A; X.L.Q = T.Q; X.L.symmetric = A.symmetric; X.L.NApad = (int)NApad; X.L.nc = psi ? 2 : 1;
+        if (psi)
+         { if (kmode == KMODE_REAL) launch_far_pass1_psi<KMODE_REAL>(ctx, X, grid, smem, small);
+           else if (kmode == KMODE_IMAG) launch_far_pass1_psi<KMODE_IMAG>(ctx, X, grid, smem, small);
+           else launch_far_pass1_psi<KMODE_CPLX>(ctx, X, grid, smem, 0); }
+        else if (kmode == KMODE_REAL) launch_far_pass1<KMODE_REAL>(ctx, X, grid, smem, small);
         else if (kmode == KMODE_IMAG) launch_far_pass1<KMODE_IMAG>(ctx, X, grid, smem, small);
         else launch_far_pass1<KMODE_CPLX>(ctx, X, grid, smem, 0);
         T.G.L = X.L; T.G.edgeA = ea; T.G.edgeB = eb; T.G.NEa = NEa; T.G.NEb = NEb;
         T.G.M = A.S.M; T.G.ld = A.S.ld; T.G.rowOff = A.S.rowOff; T.G.colOff = A.S.colOff;
+        T.G.aPEC = A.S.aPEC; T.G.bPEC = A.S.bPEC; T.G.c1 = A.S.c1; T.G.c2 = A.S.c2; T.G.c3 = A.S.c3;
         T.sym = A.symmetric != 0; T.isReal = A.S.isReal; T.NEa = NEa; T.NEb = NEb; T.pending = true;
         return; } }
+  { // every other path accumulates into the matrix with atomics: the block must have been cleared
+    cudaEvent_t zev = nullptr;
+    { std::lock_guard<std::mutex> lock(g_farSlotsLock); auto it = g_twoPass.find(ctx); if (it != g_twoPass.end()) zev = it->second.zeroEvent; }
+    if (zev) cudaStreamWaitEvent(ctx->stream, zev, 0); }
   if (!psi && stagedEnv)
    { // PEC/PEC: staged scatter (dense shared-memory window + bulk reductions)
      FarArgsX X; X.A = A; X.slots = far_slots(ctx, A.pa); X.nElem = 0; X.dbg = 0;

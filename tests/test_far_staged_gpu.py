@@ -78,3 +78,44 @@ def test_staged_icosphere_tiles_and_columns(ps, monkeypatch, tmp_path):
         e = np.linalg.norm(np.triu(A)[:, a:b] - U0) / np.linalg.norm(U0)
         print("columns", a, b, "rel diff", e)
         assert e <= 1e-13
+
+
+MIXED_GEO = """OBJECT PECBall
+	MESHFILE SSphere_255.msh
+ENDOBJECT
+
+OBJECT GlassBall
+	MESHFILE Sphere_327.msh
+	DISPLACED 0 0 3
+	MATERIAL CONST_EPS_10
+ENDOBJECT
+
+OBJECT LossyBall
+	MESHFILE SSphere_R0P25_255.msh
+	DISPLACED 2.5 0 0
+	MATERIAL CONST_EPS_10_SIGMA_1
+ENDOBJECT
+"""
+
+
+@pytest.mark.parametrize("name,omega", [("SiO2Sphere_501", 1.0), ("E10Spheres_327", 0.3), ("SiSpheres_255", 0.25j), ("LossySphere_327", 0.8),
+                                        ("GoldSphere_501", 0.05), ("MIXED", 0.7), ("MIXED", 0.4j)])
+def test_twopass_dielectric(ps, name, omega, monkeypatch, tmp_path):
+    """blocks with a dielectric side (two values per (Q_a,Q_b) combination, 2x2 / 1x2 / 2x1 stamps, two region passes, complex k):
+    the two-pass path against the scalar-atomic scatter, incl. a geometry that mixes a PEC body with two dielectrics"""
+    if name == "MIXED":
+        import shutil
+        for f in ("SSphere_255.msh", "Sphere_327.msh", "SSphere_R0P25_255.msh"):
+            shutil.copy(os.path.join(GEODIR, f), tmp_path)
+        geo = str(tmp_path / "Mixed.scuffgeo")
+        open(geo, "w").write(MIXED_GEO)
+    else:
+        geo = os.path.join(GEODIR, name + ".scuffgeo")
+    for real in ((False, True) if np.real(omega) == 0 else (False,)):
+        M0, c0, p0 = far_matrix(ps, geo, omega, "scalar", monkeypatch, real=real)
+        M1, c1, p1 = far_matrix(ps, geo, omega, "twopass", monkeypatch, real=real)
+        err = np.linalg.norm(M1 - M0) / np.linalg.norm(M0)
+        print(name, omega, M0.dtype, "twopass vs scalar rel diff", err, "counts", c1, "pairs", p1, ps.last_timing())
+        assert err <= 1e-13
+        assert list(c0) == list(c1) and list(p0) == list(p1)
+        assert np.array_equal(M1, M1.T) == np.array_equal(M0, M0.T)
