@@ -369,13 +369,13 @@ def main():
         sampler.start()
         time.sleep(0.3)
     launches0 = ps.launch_count()
-    far_ms, near_ms, tot_ms = [], [], []
+    far_ms, near_ms, tot_ms, gather_ms = [], [], [], []
     barrier()
     t0 = time.perf_counter()
     for s in range(a.steps):
         G.AssembleBEMMatrix(mine[s], M=M, to_host=False)   # returns after the stream has drained
         t = ps.last_timing()
-        tot_ms.append(t[0]); far_ms.append(t[1]); near_ms.append(t[2])
+        tot_ms.append(t[0]); far_ms.append(t[1]); near_ms.append(t[2]); gather_ms.append(t[4])
     barrier()
     elapsed = time.perf_counter() - t0
     launches = ps.launch_count() - launches0
@@ -389,12 +389,12 @@ def main():
     # the dominant kernel timed ALONE for the roofline (in a full step the latency-bound near/singular kernels share the
     # SMs with it on a second stream): far-pairs-only assemblies, CUDA events on the kernel's stream
     os.environ["SCUFF_CUDA_FAR_ONLY"] = "1"
-    far_alone_ms = []
+    far_alone_ms, gather_alone_ms = [], []
     for s in range(4):
         G.AssembleBEMMatrix(mine[s % len(mine)], M=M, to_host=False)
-        far_alone_ms.append(ps.last_timing()[1])
+        far_alone_ms.append(ps.last_timing()[1]); gather_alone_ms.append(ps.last_timing()[4])
     del os.environ["SCUFF_CUDA_FAR_ONLY"]
-    far_alone_ms = far_alone_ms[1:]
+    far_alone_ms = far_alone_ms[1:]; gather_alone_ms = gather_alone_ms[1:]
     value = world * a.steps * float(N) * N / elapsed / 1e9
 
     # ---- end to end through the reference-facing call with host buffers ----
@@ -455,13 +455,13 @@ def main():
         try:
             unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
             tot = 0.0
-            fn = os.path.join(ROOT, "profiles", "r01_far_kernel_final_N20280.summary.txt")
+            fn = os.path.join(ROOT, "profiles", "r02_far_pass1_N20280.summary.txt")
             for ln in open(fn):
                 w = ln.split()
                 if len(w) >= 3 and w[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     tot += float(w[1]) * unit[w[2]]
             if tot > 0:
-                traffic, traffic_src = tot, "profiles/r01_far_kernel_final_N20280.summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+                traffic, traffic_src = tot, "profiles/r02_far_pass1_N20280.summary.txt (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
         except Exception:
             traffic = None
     kind = "dielectric" if a.material else "pec"
@@ -478,7 +478,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (tb1[0] - tb0[0]) // a.e2e_steps,
                     "d2h_bytes_per_step": (tb1[1] - tb0[1]) // a.e2e_steps, "steps": a.e2e_steps, "ms_per_step": 1e3 * e2e_elapsed / a.e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "far_kernel<KMODE_REAL,%s>" % ("PSI" if a.material else "PEC"), "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "far_pass1%s_kernel<KMODE_REAL> (first pass of the two-pass far path; far_kernel.cu)" % ("_psi" if a.material else ""),
+                         "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic": "%d flop/point pair (SURVEY 8d: 97 full, 54 for the PEC variant without the Psi half) x %d point pairs x %d far panel "
                                         "pairs per step (%d launch(es))" % (fpp, POINT_PAIRS, far_pairs, 2 if a.material else 1),
@@ -486,6 +487,7 @@ def main():
                          "kernel_ms": 1e3 * t_far,
                          "peak_source": "in-run DFMA microkernel (scuffcuda_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry"},
             "breakdown_ms": {"total_device": sum(tot_ms) / len(tot_ms), "far_kernel_alone": 1e3 * t_far, "far_kernel_in_step": sum(far_ms) / len(far_ms),
+                             "gather_in_step_beside_near": sum(gather_ms) / len(gather_ms), "gather_alone": sum(gather_alone_ms) / len(gather_alone_ms),
                              "near_singular_in_step_concurrent": sum(near_ms) / len(near_ms),
                              "cold_first_assembly_s": cold_s, "cold_fippi_build_ms": cold_t[3]},
             "pairs": {"far": int(far_pairs), "near": int(near_pairs), "reference_ppi_counts": [int(c) for c in ppi_counts]},
@@ -499,6 +501,16 @@ def main():
         pass
     line["store_phase"] = {"bytes": 16.0 * N * N, "min_ms_at_measured_hbm": (16.0 * N * N / (hbm * 1e9) * 1e3) if hbm else None,
                            "hbm_gbs": hbm, "source": "measured" if hbm else "absent"}
+    # second kernel of the two-pass far path: HBM-bound.  Algorithmic bytes: the panel-pair array read once (9 combinations x
+    # 16 B (x2 with the Psi half) per panel pair pa<pb, both region passes) + the upper triangle updated (atomic adds: written once)
+    npairs = float(P) * (P - 1) / 2.0
+    q_bytes = npairs * 9 * 16.0 * (2 if a.material else 1) * (2 if a.material else 1)
+    g_bytes = q_bytes + 16.0 * N * N / 2.0 * (2 if a.material else 1)
+    g_ms = sum(gather_alone_ms) / len(gather_alone_ms)
+    line["gather"] = {"kernel": "far_gather%s_kernel (second pass: panel-pair array -> matrix entries)" % ("_psi" if a.material else ""), "bound": "hbm",
+                      "algorithmic_bytes": g_bytes, "panel_pair_array_bytes": q_bytes, "ms_alone": g_ms,
+                      "achieved": (g_bytes / (g_ms * 1e-3) / 1e9) if g_ms > 0 else None, "peak": hbm, "unit": "GB/s",
+                      "frac": (g_bytes / (g_ms * 1e-3) / 1e9 / hbm) if (hbm and g_ms > 0) else None}
 
     # ---- downstream consumer (timed separately, not the optimisation target): on-device LU + solve ----
     if not a.no_lu and world == 1:

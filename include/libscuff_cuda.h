@@ -89,6 +89,11 @@ int scuffcuda_matrix_upload(scuffcuda_context *ctx, int handle, const void *host
 int scuffcuda_matrix_download_region_async(scuffcuda_context *ctx, int handle, void *host, long ld,
                                            int row0, int nrows, int col0, int ncols);
 int scuffcuda_matrix_download_wait(scuffcuda_context *ctx, int fence_compute);
+/* a marker in the copy stream: _mark returns a ticket for "every region copy enqueued so far", _wait_ticket blocks the host until
+ * those copies have landed (and releases the ticket).  Lets a caller consume the first regions (e.g. mirror the upper triangle on
+ * the host) while later regions are still crossing PCIe.                                  */
+int scuffcuda_matrix_download_mark(scuffcuda_context *ctx, int *ticket);
+int scuffcuda_matrix_download_wait_ticket(scuffcuda_context *ctx, int ticket);
 /* raw device pointer (for zero-copy consumers such as torch / cuSOLVER callers)        */
 int scuffcuda_matrix_device_ptr(scuffcuda_context *ctx, int handle, void **dptr);
 /* downstream consumer: HMatrix::LUFactorize / LUSolve (libs/libhmat/LBWrappers.cc:150-230)

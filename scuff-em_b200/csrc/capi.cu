@@ -2,6 +2,7 @@
 // integrals run in the CUDA kernels of this directory.  No CPU fallback exists: every entry
 // point that computes needs a live CUDA context.
 #include <complex>
+#include <mutex>
 #include <cstdio>
 #include <cstdarg>
 #include <cstring>
@@ -269,6 +270,30 @@ int scuffcuda_matrix_download_wait(scuffcuda_context *ctx, int fence_compute)
      CK(cudaEventRecord(e, cs)); CK(cudaStreamWaitEvent(ctx->stream, e, 0)); CK(cudaEventDestroy(e));
      return 0; }
   CK(cudaStreamSynchronize(cs));
+  return 0;
+}
+static std::map<std::pair<scuffcuda_context *, int>, cudaEvent_t> g_downloadTickets;
+static std::mutex g_downloadTicketsLock;
+static int g_nextTicket = 1;
+int scuffcuda_matrix_download_mark(scuffcuda_context *ctx, int *ticket)
+{ if (!ticket) return fail(ctx, "matrix_download_mark: null ticket");
+  CK(cudaSetDevice(ctx->device));
+  cudaEvent_t e; CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CK(cudaEventRecord(e, copy_stream(ctx)));
+  std::lock_guard<std::mutex> lock(g_downloadTicketsLock);
+  *ticket = g_nextTicket++;
+  g_downloadTickets[std::make_pair(ctx, *ticket)] = e;
+  return 0;
+}
+int scuffcuda_matrix_download_wait_ticket(scuffcuda_context *ctx, int ticket)
+{ cudaEvent_t e;
+  { std::lock_guard<std::mutex> lock(g_downloadTicketsLock);
+    auto it = g_downloadTickets.find(std::make_pair(ctx, ticket));
+    if (it == g_downloadTickets.end()) return fail(ctx, "matrix_download_wait_ticket: unknown ticket %d", ticket);
+    e = it->second; g_downloadTickets.erase(it); }
+  cudaError_t rc = cudaEventSynchronize(e);
+  cudaEventDestroy(e);
+  if (rc != cudaSuccess) return fail(ctx, "matrix_download_wait_ticket: %s", cudaGetErrorString(rc));
   return 0;
 }
 int scuffcuda_matrix_upload(scuffcuda_context *ctx, int h, const void *host, long ld)

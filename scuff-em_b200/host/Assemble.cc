@@ -6,6 +6,13 @@
 #include <cstdlib>
 #include <cmath>
 #include <vector>
+#include <atomic>
+#include <thread>
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <emmintrin.h>
 #include "host_internal.h"
 
 namespace scuff {
@@ -211,6 +218,88 @@ static void AssembleBEMMatrixPipelined(RWGGeometry *G, cdouble Omega, HMatrix *M
   M->HostStale = false;
 }
 
+// Copy-back of a symmetric matrix: only the upper triangle crosses PCIe (half the bytes); the lower triangle is written by
+// host threads while the later column chunks are still in flight.  The matrix is assembled in ONE pass (the two-pass far path
+// needs whole blocks), the K chunk copies [0,c1) x [c0,c1) are enqueued at once, and the host mirrors chunk j as soon as
+// its ticket completes.  SCUFF_CUDA_PIPELINE_MODE=columns selects the older scheme above (assembly in column blocks overlapped
+// with full-matrix downloads).
+static inline void StreamStore(cdouble *dst, const cdouble &v) { _mm_stream_pd(reinterpret_cast<double *>(dst), _mm_loadu_pd(reinterpret_cast<const double *>(&v))); }
+static inline void StreamStore(double *dst, const double &v) { long long b; memcpy(&b, &v, 8); _mm_stream_si64(reinterpret_cast<long long *>(dst), b); }
+
+template <typename T>
+static void MirrorChunkOnHost(T *A, long ld, int c0, int c1, int nThreads)
+{ // lower(r, c) = upper(c, r) for columns c in [0, c0), rows r in [c0, c1): read the chunk's part above its diagonal square
+  // (columns [c0,c1), rows [0,c0)) in 64 x 64 tiles, write them transposed with streaming stores (no read-for-ownership)
+  const int TS = 64;
+  const long tilesR = (c0 + TS - 1) / TS, tilesC = (c1 - c0 + TS - 1) / TS, nTiles = tilesR * tilesC;
+  if (nTiles <= 0) return;
+  std::atomic<long> next(0);
+  auto work = [&]()
+   { T buf[TS][TS + 1];
+     for (;;)
+      { const long t = next.fetch_add(1);
+        if (t >= nTiles) break;
+        const int r0 = (int)(t % tilesR) * TS, q0 = c0 + (int)(t / tilesR) * TS;
+        const int nr = std::min(TS, c0 - r0), nc = std::min(TS, c1 - q0);
+        for (int q = 0; q < nc; q++) { const T *src = A + (size_t)r0 + (size_t)(q0 + q) * ld; for (int r = 0; r < nr; r++) buf[q][r] = src[r]; }
+        for (int r = 0; r < nr; r++) { T *dst = A + (size_t)q0 + (size_t)(r0 + r) * ld; for (int q = 0; q < nc; q++) StreamStore(dst + q, buf[q][r]); } }
+     _mm_sfence(); };
+  std::vector<std::thread> pool;
+  for (int i = 1; i < nThreads; i++) pool.emplace_back(work);
+  work();
+  for (auto &th : pool) th.join();
+}
+
+static void AssembleBEMMatrixUpperCopyBack(RWGGeometry *G, cdouble Omega, HMatrix *M, int K)
+{ scuffcuda_context *ctx = GetCudaContext();
+  const int N = G->TotalBFs;
+  G->AssembleBEMMatrixDevice(Omega, 0, M);                 // whole matrix (both triangles) resident in HBM
+  void *host = M->RealComplex == LHM_REAL ? (void *)M->DM : (void *)M->ZM;
+  std::vector<int> c(K + 1), ticket(K, 0);
+  for (int j = 0; j <= K; j++) c[j] = (int)(N * sqrt((double)j / K) + 0.5);    // equal upper-triangle area per chunk
+  c[0] = 0; c[K] = N;
+  for (int j = 0; j < K; j++)
+   { if (c[j + 1] > c[j] && scuffcuda_matrix_download_region_async(ctx, M->DeviceHandle, host, M->NR, 0, c[j + 1], c[j], c[j + 1] - c[j]))
+      ErrExit("%s", scuffcuda_last_error(ctx));
+     if (scuffcuda_matrix_download_mark(ctx, &ticket[j])) ErrExit("%s", scuffcuda_last_error(ctx)); }
+  int nThreads = (int)std::thread::hardware_concurrency();
+  if (const char *e = getenv("SCUFF_CUDA_MIRROR_THREADS")) nThreads = atoi(e);
+  nThreads = nThreads < 1 ? 1 : (nThreads > 64 ? 64 : nThreads);
+  // The lower triangle is produced from both ends: host threads mirror the chunks in ascending order (as their upper parts land),
+  // the copy engine — idle once the upper triangle is through — downloads the lower parts in descending order, until they meet.
+  std::mutex claimLock; int lo = 0, hi = K - 1;            // chunks [lo, hi] are not yet claimed
+  auto claim = [&](bool fromTop) -> int
+   { std::lock_guard<std::mutex> g(claimLock);
+     if (lo > hi) return -1;
+     return fromTop ? hi-- : lo++; };
+  std::string mirrorErr;
+  std::thread mirror([&]()
+   { for (;;)
+      { const int j = claim(false);
+        if (j < 0) break;
+        if (scuffcuda_matrix_download_wait_ticket(ctx, ticket[j])) { mirrorErr = scuffcuda_last_error(ctx); break; }
+        ticket[j] = 0;
+        if (c[j + 1] <= c[j]) continue;
+        if (M->RealComplex == LHM_REAL) MirrorChunkOnHost<double>(M->DM, M->NR, c[j], c[j + 1], nThreads > 1 ? nThreads - 1 : 1);
+        else MirrorChunkOnHost<cdouble>(M->ZM, M->NR, c[j], c[j + 1], nThreads > 1 ? nThreads - 1 : 1); } });
+  const bool dmaHelps = !(getenv("SCUFF_CUDA_MIRROR_DMA") && getenv("SCUFF_CUDA_MIRROR_DMA")[0] == '0');
+  std::string dmaErr;
+  while (dmaHelps)
+   { // one lower part at a time, so that the claim reflects what the copy engine has really reached
+     const int j = claim(true);
+     if (j < 0) break;
+     int t = 0;
+     if ((c[j + 1] > c[j] && c[j] > 0 && scuffcuda_matrix_download_region_async(ctx, M->DeviceHandle, host, M->NR, c[j], c[j + 1] - c[j], 0, c[j]))
+         || scuffcuda_matrix_download_mark(ctx, &t) || scuffcuda_matrix_download_wait_ticket(ctx, t))
+      { dmaErr = scuffcuda_last_error(ctx); break; } }
+  mirror.join();
+  for (int j = 0; j < K; j++) if (ticket[j]) scuffcuda_matrix_download_wait_ticket(ctx, ticket[j]);   // upper parts of chunks the copy engine took
+  if (!mirrorErr.empty()) ErrExit("%s", mirrorErr.c_str());
+  if (!dmaErr.empty()) ErrExit("%s", dmaErr.c_str());
+  if (scuffcuda_matrix_download_wait(ctx, 0)) ErrExit("%s", scuffcuda_last_error(ctx));
+  M->HostStale = false;
+}
+
 HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *M)
 { if (LBasis == 0 && kBloch != 0 && (kBloch[0] != 0.0 || kBloch[1] != 0.0))
    ErrExit("%s:%i: Bloch wavevector is undefined for compact geometries", __FILE__, __LINE__);
@@ -221,7 +310,9 @@ HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *
    { Warn("wrong-size matrix passed to AssembleBEMMatrix; reallocating...");
      M = AllocateBEMMatrix(); }
   int K = PipelineBlocks(TotalBFs);
-  if (LBasis == 0 && K > 1 && M->StorageType == LHM_NORMAL) AssembleBEMMatrixPipelined(this, Omega, M, K);
+  const char *mode = getenv("SCUFF_CUDA_PIPELINE_MODE");
+  if (LBasis == 0 && K > 1 && M->StorageType == LHM_NORMAL && mode && !strcmp(mode, "columns")) AssembleBEMMatrixPipelined(this, Omega, M, K);
+  else if (LBasis == 0 && K > 1 && M->StorageType == LHM_NORMAL) AssembleBEMMatrixUpperCopyBack(this, Omega, M, 2 * K);
   else
    { AssembleBEMMatrixDevice(Omega, kBloch, M);
      M->SyncToHost(); }

@@ -46,14 +46,28 @@ def test_pipelined_copy_back(ps, monkeypatch, name, omega, K):
     M1 = G.AllocateBEMMatrix(imag)
     G.AssembleBEMMatrix(omega, M=M1); A1 = M1.array.copy(); c1 = G.ppi_counts()
     monkeypatch.setenv("SCUFF_CUDA_PIPELINE_BLOCKS", str(K))
-    M2 = G.AllocateBEMMatrix(imag)
-    G.AssembleBEMMatrix(omega, M=M2); A2 = M2.array.copy(); c2 = G.ppi_counts()
-    assert A1.dtype == A2.dtype and (A1.dtype == np.float64) == bool(imag)
-    err = np.linalg.norm(A2 - A1) / np.linalg.norm(A1)
-    print(name, omega, K, "pipelined vs one-pass rel err", err)
-    assert err <= 1e-14
-    assert np.array_equal(A2, A2.T)                        # mirrored exactly
-    # the HBM copy is the same matrix (LU consumers read it)
-    D = M2.device_tensor().cpu().numpy().view(A2.dtype).reshape(A2.shape[1], A2.shape[0]).T
-    assert np.array_equal(D, A2)
-    assert all(b >= a for a, b in zip(c1, c2))            # pairs straddling a block boundary are visited by both blocks
+    # "upper" (default): one-pass assembly, only the upper triangle crosses PCIe in 2K chunks, host threads write the mirror image;
+    # "columns": assembly in K column blocks overlapped with full-matrix downloads
+    for mode in ("upper", "columns"):
+        monkeypatch.setenv("SCUFF_CUDA_PIPELINE_MODE", mode)
+        for threads in ((1, 5, -5) if mode == "upper" else (0,)):
+            if threads:
+                monkeypatch.setenv("SCUFF_CUDA_MIRROR_THREADS", str(abs(threads)))
+                monkeypatch.setenv("SCUFF_CUDA_MIRROR_DMA", "0" if threads < 0 else "1")   # host threads only / host threads + copy engine
+            M2 = G.AllocateBEMMatrix(imag)
+            d0 = ps.transfer_bytes()[1]
+            G.AssembleBEMMatrix(omega, M=M2); A2 = M2.array.copy(); c2 = G.ppi_counts()
+            d2h = ps.transfer_bytes()[1] - d0
+            assert A1.dtype == A2.dtype and (A1.dtype == np.float64) == bool(imag)
+            err = np.linalg.norm(A2 - A1) / np.linalg.norm(A1)
+            print(name, omega, K, mode, threads, "pipelined vs one-pass rel err", err, "D2H bytes", d2h, "of", A2.nbytes)
+            assert err <= 1e-14
+            assert np.array_equal(A2, A2.T)                        # mirrored exactly
+            # the HBM copy is the same matrix (LU consumers read it)
+            D = M2.device_tensor().cpu().numpy().view(A2.dtype).reshape(A2.shape[1], A2.shape[0]).T
+            assert np.array_equal(D, A2)
+            assert all(b >= a for a, b in zip(c1, c2))            # pairs straddling a block boundary are visited by both blocks
+            if mode == "upper":
+                assert list(c1) == list(c2)
+                if threads < 0:
+                    assert d2h < 0.7 * A2.nbytes                   # host-only mirror: about half the matrix crosses PCIe
