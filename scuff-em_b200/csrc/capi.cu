@@ -24,7 +24,9 @@ static int fail(scuffcuda_context *ctx, const char *fmt, ...)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ctx, "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 #define CKS(call) do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(ctx, "%s:%d: %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
 
-namespace scuffcuda {   // far_kernel.cu
+namespace scuffcuda {
+int run_td_div_selftest(scuffcuda_context *ctx, int n, const double *x, double *out);   // td_kernel.cu
+// far_kernel.cu
 void far_slots_release(scuffcuda_context *ctx);     // window/slot tables of the staged scatter
 void far_twopass_release(scuffcuda_context *ctx);   // panel-pair array and edge tables of the two-pass path
 int launch_far_gather(scuffcuda_context *ctx);      // second pass (no-op unless launch_far chose the two-pass path); 1 = it mirrored
@@ -582,7 +584,9 @@ int scuffcuda_host_free(scuffcuda_context *ctx, void *p)
 { CK(cudaSetDevice(ctx->device)); CK(cudaFreeHost(p)); return 0; }
 
 int scuffcuda_selftest_math(scuffcuda_context *ctx, int n, const double *x, double *out)
-{ CK(cudaSetDevice(ctx->device)); return run_fastmath_selftest(ctx, n, x, out); }
+{ CK(cudaSetDevice(ctx->device));
+  if (run_fastmath_selftest(ctx, n, x, out)) return 1;
+  return scuffcuda::run_td_div_selftest(ctx, n, x, out); }
 
 int scuffcuda_measure_fp64_peak(scuffcuda_context *ctx, double *tflops)
 { CK(cudaSetDevice(ctx->device)); *tflops = run_fp64_peak(ctx); CK(cudaGetLastError()); return 0; }

@@ -965,7 +965,7 @@ __global__ void fastmath_selftest_kernel(int n, const double *x, double *out)
   double s, c; sincos_fast(x[i], s, c);
   out[6 * i + 0] = rsqrt_fast<true>(a); out[6 * i + 1] = rsqrt_fast<false>(a);
   out[6 * i + 2] = s; out[6 * i + 3] = c;
-  out[6 * i + 4] = exp_neg_fast(-fabs(x[i])); out[6 * i + 5] = 0.0;
+  out[6 * i + 4] = exp_neg_fast(-fabs(x[i])); out[6 * i + 5] = 0.0;   // column 5: td_div_selftest_kernel (td_kernel.cu)
 }
 int run_fastmath_selftest(scuffcuda_context *ctx, int n, const double *xh, double *outh)
 { double *dx = nullptr, *dout = nullptr;
@@ -1029,13 +1029,18 @@ static double surface_rmax(scuffcuda_context *ctx, const PanelRec *d)
 // half hidden under the FP64-bound pass 1).  Q is sized NP^2/2 x 144 B for a symmetric block; when it does not fit the budget
 // (SCUFF_CUDA_FAR_QMAX_GB, default 40) the staged-atomic kernel is used instead.
 // ------------------------------------------------------------------------------------------------------------------
-struct FarQ { cd *Q; int symmetric; int NApad; int nc; };   // nc complex values per (Q_a,Q_b) combination: 1 (PEC/PEC: g0), 2 (g0, g1)
-// offset (in complex elements) of the row of b-panel pb and its a-extent NA; element (pb, j, pa, i, c) = row + ((j * NA + pa) * 3 + i) * nc + c
-__device__ __forceinline__ long farq_row(const FarQ &L, int pb, int &NA)
-{ if (L.symmetric)
-   { const long t = pb >> 7; NA = (int)((t + 1) << 7);
-     return L.nc * (9L * 128 * 128 * (t * (t + 1) / 2) + (long)(pb - (int)(t << 7)) * 9 * NA); }
-  NA = L.NApad; return (long)L.nc * pb * 9 * L.NApad;
+// Layout of the panel-pair array.  The values of a-panel pa for b-panel pb and local b-index j sit at the SLOTS of pa's edges,
+//   element (pb, j, slot, c) = row(pb) + (j * EX + slot) * nc + c ,   slot = 2 * edge + (0: pa is the edge's P panel, 1: its M panel),
+// so that the gather thread of entry (e_a, e_b) finds both panels of e_a in ONE contiguous 2 * nc * 16 B piece and a warp
+// (consecutive e_a) reads contiguous memory: every sector is fetched once (with a panel-indexed layout the three values of a panel
+// were split between the warps of its M-role and P-role edges and every sector crossed HBM -> L2 more than twice).  The stores of
+// pass 1 stay dense: the 32 consecutive panels of a warp cover ~50 consecutive edges in both roles.
+// A symmetric block stores pa < pb only: row pb extends over EX = ext[pb / 128] slots (all edges of the panels below the end of
+// pb's 128-tile), rows are packed with the prefix sums base[].
+struct FarQ { cd *Q; const long *base; const int *ext; int symmetric; int extFull; int nc; };   // nc complex values per combination: 1 (PEC/PEC: g0), 2 (g0, g1)
+__device__ __forceinline__ long farq_row(const FarQ &L, int pb, int &EX)
+{ if (L.symmetric) { const int t = pb >> 7; EX = L.ext[t]; return L.nc * (L.base[t] + (long)(pb - (t << 7)) * 3 * EX); }
+  EX = L.extFull; return (long)L.nc * pb * 3 * L.extFull;
 }
 struct FarArgsQ { FarArgs A; FarQ L; };
 
@@ -1069,7 +1074,7 @@ far_pass1_kernel(const __grid_constant__ FarArgsQ X)
   const PanelRec *Pa = A.pa + (pa < A.NPa ? pa : 0);
 #pragma unroll
   for (int i = 0; i < 18; i++) sXa[i * FAR_THREADS] = Pa->x[i];
-  int na = 0;
+  int na = 0, slot[3];
 #pragma unroll
   for (int m = 0; m < 3; m++)
    { const double v0 = Pa->V[m];
@@ -1077,6 +1082,7 @@ far_pass1_kernel(const __grid_constant__ FarArgsQ X)
      sSt[(6 + m) * FAR_THREADS] = Pa->V[6 + m] - v0;                 // B
      sSt[(9 + m) * FAR_THREADS] = Pa->sl[m];
      sSt[(12 + m) * FAR_THREADS] = Pa->C[m];
+     slot[m] = (Pa->ei[m] >= 0) ? 2 * Pa->ei[m] + (Pa->sl[m] < 0.0 ? 1 : 0) : -1;
      na += (Pa->ei[m] >= 0); }
   sSt[15 * FAR_THREADS] = Pa->R;
   mbar_wait(&bar, 0);
@@ -1109,12 +1115,14 @@ far_pass1_kernel(const __grid_constant__ FarArgsQ X)
          { sla[m] = sSt[(9 + m) * FAR_THREADS]; Aa[m] = sSt[(3 + m) * FAR_THREADS]; Ba[m] = sSt[(6 + m) * FAR_THREADS];
            Ab[m] = Pb[7 + m] - Pb[4 + m]; Bb[m] = Pb[10 + m] - Pb[4 + m]; }
         contract_pec<S>(mPhi, Aa, Ba, Ab, Bb, sla, Pb + 31, c1, A.K.c4, val); }
-     int NA; const long row = farq_row(X.L, pb, NA);
-     double2 *q = reinterpret_cast<double2 *>(X.L.Q + row + (long)pa * 3);
+     int EX; const long row = farq_row(X.L, pb, EX);
+     double2 *q = reinterpret_cast<double2 *>(X.L.Q + row);
 #pragma unroll
-     for (int j = 0; j < 3; j++)
+     for (int i = 0; i < 3; i++)
+      if (slot[i] >= 0)
+       {
 #pragma unroll
-      for (int i = 0; i < 3; i++) q[(long)j * NA * 3 + i] = make_double2(val[3 * i + j].x, val[3 * i + j].y);
+         for (int j = 0; j < 3; j++) q[(long)j * EX + slot[i]] = make_double2(val[3 * i + j].x, val[3 * i + j].y); }
    }
   // algorithm counters (reference log line SurfaceSurfaceInteractions.cc:550-558)
   if (sCnt[FAR_THREADS]) atomicAdd(A.counters, (unsigned long long)sCnt[FAR_THREADS]);
@@ -1163,6 +1171,7 @@ far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
      sSt[(6 + m) * FAR_THREADS] = Pa->V[6 + m] - v0;                 // B
      sSt[(9 + m) * FAR_THREADS] = Pa->sl[m];
      sSt[(12 + m) * FAR_THREADS] = Pa->C[m];
+     sEi[m * FAR_THREADS] = (Pa->ei[m] >= 0) ? 2 * Pa->ei[m] + (Pa->sl[m] < 0.0 ? 1 : 0) : -1;     // slot of this panel in the edge's piece
      na += (Pa->ei[m] >= 0); }
   sSt[15 * FAR_THREADS] = Pa->R;
   mbar_wait(&bar, 0);
@@ -1176,14 +1185,16 @@ far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
      bool far;
      { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
        far = pair_is_far(Ca, sSt[15 * FAR_THREADS], Pb, Pb[3], A.useDisp != 0, A.L, D); }
-     int NA; const long row = farq_row(X.L, pb, NA);
-     double2 *q = reinterpret_cast<double2 *>(X.L.Q + row + (long)pa * 6);
+     int EX; const long row = farq_row(X.L, pb, EX);
+     double2 *q = reinterpret_cast<double2 *>(X.L.Q + row);
      if (!far)
       {
 #pragma unroll
-        for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++)
+         { const int sl = sEi[i * FAR_THREADS];
+           if (sl < 0) continue;
 #pragma unroll
-         for (int n = 0; n < 6; n++) q[(long)j * NA * 6 + n] = make_double2(0.0, 0.0);
+           for (int j = 0; j < 3; j++) { q[((long)j * EX + sl) * 2] = make_double2(0.0, 0.0); q[((long)j * EX + sl) * 2 + 1] = make_double2(0.0, 0.0); } }
         continue; }
      const int *eb3 = (const int *)(Pb + 34);
      sCnt[0] += 1;
@@ -1242,8 +1253,10 @@ far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
            fma_acc(h1, cAA, Pu); fma_acc(h1, cAB, Pv); fma_acc(h1, cBA, Qu); fma_acc(h1, cBB, Qv);
            const double sc = sla * Pb[31 + j];
            const cd g0 = sc * h0, g1 = sc * cscale(ooik, h1);
-           q[(long)j * NA * 6 + 2 * i] = make_double2(g0.x, g0.y);
-           q[(long)j * NA * 6 + 2 * i + 1] = make_double2(g1.x, g1.y); } }
+           const int sl = sEi[i * FAR_THREADS];
+           if (sl >= 0)
+            { q[((long)j * EX + sl) * 2] = make_double2(g0.x, g0.y);
+              q[((long)j * EX + sl) * 2 + 1] = make_double2(g1.x, g1.y); } } }
    }
   if (sCnt[FAR_THREADS]) atomicAdd(A.counters, (unsigned long long)sCnt[FAR_THREADS]);
   if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
@@ -1285,11 +1298,12 @@ far_gather_kernel(const GatherArgs G)
          for (int v = 0; v < 2; v++)
           { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = v ? Eb.z : Eb.x, jb = v ? Eb.w : Eb.y;
             if (pa < 0 || pb < 0) continue;
+            int slot = 2 * ea + u;
             if (SYM)
              { if (pa == pb) continue;
-               if (pa > pb) { int t = pa; pa = pb; pb = t; t = ia; ia = jb; jb = t; } }   // the pair is stored once, with the lower panel as 'a'
-            int NA; const long row = farq_row(G.L, pb, NA);
-            const double2 q = __ldcs(reinterpret_cast<const double2 *>(G.L.Q + row + ((long)jb * NA + pa) * 3 + ia));
+               if (pa > pb) { pb = pa; jb = ia; slot = 2 * eb + v; } }   // the pair is stored once, in the row of its higher panel
+            int EX; const long row = farq_row(G.L, pb, EX);
+            const double2 q = __ldcs(reinterpret_cast<const double2 *>(G.L.Q + row + (long)jb * EX + slot));
             sx += q.x; sy += q.y; }
         const size_t idx = ((size_t)(G.rowOff + ea) + (size_t)(G.colOff + eb) * (size_t)G.ld) * W;
         if (RED)
@@ -1345,11 +1359,12 @@ far_gather_psi_kernel(const GatherArgs G)
          for (int w = 0; w < 2; w++)
           { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = w ? Eb.z : Eb.x, jb = w ? Eb.w : Eb.y;
             if (pa < 0 || pb < 0) continue;
+            int slot = 2 * ea + u;
             if (SYM)
              { if (pa == pb) continue;
-               if (pa > pb) { int t = pa; pa = pb; pb = t; t = ia; ia = jb; jb = t; } }
-            int NA; const long row = farq_row(G.L, pb, NA);
-            const double2 *q = reinterpret_cast<const double2 *>(G.L.Q + row + (((long)jb * NA + pa) * 3 + ia) * 2);
+               if (pa > pb) { pb = pa; jb = ia; slot = 2 * eb + w; } }
+            int EX; const long row = farq_row(G.L, pb, EX);
+            const double2 *q = reinterpret_cast<const double2 *>(G.L.Q + row + ((long)jb * EX + slot) * 2);
             const double2 a = __ldcs(q), b = __ldcs(q + 1);
             g0x += a.x; g0y += a.y; g1x += b.x; g1y += b.y; }
         const cd G0 = mk(g0x, g0y), G1 = mk(g1x, g1y);
@@ -1454,31 +1469,41 @@ void far_slots_release(scuffcuda_context *ctx)
 // ---- host side of the two-pass path ----
 struct FarTwoPassState
 { cd *Q = nullptr; size_t qBytes = 0;                       // panel-pair array, grown on demand, kept for the life of the context
-  std::map<const PanelRec *, std::pair<uint64_t, int4 *> > edges;   // surface -> (generation, device edge table)
+  struct SurfTab { uint64_t generation = 0; int4 *edges = nullptr; long *base = nullptr; int *ext = nullptr; long symElems = 0; int extFull = 0; int NE = 0; };
+  std::map<const PanelRec *, SurfTab> edges;                // surface -> edge table and row layout of the panel-pair array
   bool pending = false; GatherArgs G; bool sym = false; int isReal = 0; int NEa = 0, NEb = 0;
   cudaEvent_t zeroEvent = nullptr;
   cudaEvent_t g0 = nullptr, g1 = nullptr; bool timed = false; };   // gather start / end
 static std::map<scuffcuda_context *, FarTwoPassState> g_twoPass;
 
-static const int4 *far_edge_table(scuffcuda_context *ctx, FarTwoPassState &T, const PanelRec *d, int &NE)
+static const FarTwoPassState::SurfTab *far_surface_tables(scuffcuda_context *ctx, FarTwoPassState &T, const PanelRec *d)
 { const Surface *S = nullptr;
   for (const Surface &Q : ctx->surfaces) if (Q.dpanels == d) S = &Q;
   if (!S) return nullptr;
-  NE = S->NE;
-  auto &slot = T.edges[d];
-  if (slot.second && slot.first == S->generation) return slot.second;
+  FarTwoPassState::SurfTab &slot = T.edges[d];
+  if (slot.edges && slot.generation == S->generation) return &slot;
   std::vector<int4> h(std::max(S->NE, 1), make_int4(-1, 0, -1, 0));
+  const int tiles = (S->NP + 127) / 128;
+  std::vector<int> ext(tiles, 0); std::vector<long> base(tiles + 1, 0);
+  int maxEdge = -1;
   for (int p = 0; p < S->NP; p++)
-   for (int i = 0; i < 3; i++)
-    { const int e = S->hpanels[p].ei[i];
-      if (e < 0 || e >= S->NE) continue;
-      if (S->hpanels[p].sl[i] >= 0.0) { h[e].x = p; h[e].y = i; } else { h[e].z = p; h[e].w = i; } }
-  if (slot.second) { cudaStreamSynchronize(ctx->stream); cudaFree(slot.second); slot.second = nullptr; }
-  if (cudaMalloc(&slot.second, h.size() * sizeof(int4)) != cudaSuccess) { slot.second = nullptr; return nullptr; }
-  cudaMemcpyAsync(slot.second, h.data(), h.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream);
-  cudaStreamSynchronize(ctx->stream);
-  slot.first = S->generation;
-  return slot.second;
+   { for (int i = 0; i < 3; i++)
+      { const int e = S->hpanels[p].ei[i];
+        if (e < 0 || e >= S->NE) continue;
+        maxEdge = std::max(maxEdge, e);
+        if (S->hpanels[p].sl[i] >= 0.0) { h[e].x = p; h[e].y = i; } else { h[e].z = p; h[e].w = i; } }
+     // row extent of the 128-tile this panel ends: all slots of the edges met so far, rounded to whole 128-byte lines
+     if ((p & 127) == 127 || p == S->NP - 1) ext[p >> 7] = ((2 * (maxEdge + 1) + 7) / 8) * 8; }
+  for (int t = 0; t < tiles; t++) base[t + 1] = base[t] + 128L * 3 * ext[t];
+  if (slot.edges) { cudaStreamSynchronize(ctx->stream); cudaFree(slot.edges); cudaFree(slot.base); cudaFree(slot.ext); slot.edges = nullptr; }
+  if (cudaMalloc(&slot.edges, h.size() * sizeof(int4)) != cudaSuccess || cudaMalloc(&slot.base, base.size() * sizeof(long)) != cudaSuccess
+      || cudaMalloc(&slot.ext, ext.size() * sizeof(int)) != cudaSuccess) { cudaGetLastError(); slot.edges = nullptr; return nullptr; }
+  cudaMemcpyAsync(slot.edges, h.data(), h.size() * sizeof(int4), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(slot.base, base.data(), base.size() * sizeof(long), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(slot.ext, ext.data(), ext.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);                   // the vectors are locals
+  slot.generation = S->generation; slot.symElems = base[tiles]; slot.extFull = ((2 * std::max(S->NE, 1) + 7) / 8) * 8; slot.NE = S->NE;
+  return &slot;
 }
 void far_set_zero_event(scuffcuda_context *ctx, cudaEvent_t ev)
 { std::lock_guard<std::mutex> lock(g_farSlotsLock);
@@ -1490,7 +1515,7 @@ void far_twopass_release(scuffcuda_context *ctx)
   if (it == g_twoPass.end()) return;
   if (it->second.Q) cudaFree(it->second.Q);
   if (it->second.g0) { cudaEventDestroy(it->second.g0); cudaEventDestroy(it->second.g1); }
-  for (auto &e : it->second.edges) if (e.second.second) cudaFree(e.second.second);
+  for (auto &e : it->second.edges) if (e.second.edges) { cudaFree(e.second.edges); cudaFree(e.second.base); cudaFree(e.second.ext); }
   g_twoPass.erase(it);
 }
 
@@ -1607,21 +1632,20 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
      std::unique_lock<std::mutex> lock(g_farSlotsLock);
      FarTwoPassState &T = g_twoPass[ctx];
      lock.unlock();
-     const long NApad = (long)aTiles * FAR_THREADS;
-     const long tiles = (A.NPb + 127) / 128;
-     const size_t need = sizeof(cd) * (size_t)(psi ? 2 : 1) * (size_t)(A.symmetric ? 9L * 128 * 128 * (tiles * (tiles + 1) / 2) : (long)A.NPb * 9 * NApad);
+     const FarTwoPassState::SurfTab *ta = far_surface_tables(ctx, T, A.pa), *tb = far_surface_tables(ctx, T, A.pb);
+     bool ok = ta && tb;
+     const size_t need = !ok ? 0 : sizeof(cd) * (size_t)(psi ? 2 : 1) * (size_t)(A.symmetric ? ta->symElems : (long)A.NPb * 3 * ta->extFull);
      double qmaxGB = 40.0;
      { const char *e = getenv("SCUFF_CUDA_FAR_QMAX_GB"); if (e) qmaxGB = atof(e); }
-     bool ok = (double)need <= qmaxGB * 1073741824.0;
+     ok = ok && (double)need <= qmaxGB * 1073741824.0;
      if (ok && need > T.qBytes)
       { if (T.Q) { cudaStreamSynchronize(ctx->stream); cudaFree(T.Q); T.Q = nullptr; T.qBytes = 0; }
         size_t freeB = 0, totalB = 0; cudaMemGetInfo(&freeB, &totalB);
         if (need + (size_t)(2ull << 30) > freeB || cudaMalloc(&T.Q, need) != cudaSuccess) { cudaGetLastError(); T.Q = nullptr; ok = false; }
         else T.qBytes = need; }
-     int NEa = 0, NEb = 0;
-     const int4 *ea = ok ? far_edge_table(ctx, T, A.pa, NEa) : nullptr, *eb = ok ? far_edge_table(ctx, T, A.pb, NEb) : nullptr;
-     if (ok && ea && eb)
-      { FarArgsQ X; X.A = A; X.L.Q = T.Q; X.L.symmetric = A.symmetric; X.L.NApad = (int)NApad; X.L.nc = psi ? 2 : 1;
+     if (ok)
+      { FarArgsQ X; X.A = A; X.L.Q = T.Q; X.L.symmetric = A.symmetric; X.L.base = ta->base; X.L.ext = ta->ext; X.L.extFull = ta->extFull; X.L.nc = psi ? 2 : 1;
+        const int4 *ea = ta->edges, *eb = tb->edges; const int NEa = ta->NE, NEb = tb->NE;
         if (psi)
          { if (kmode == KMODE_REAL) launch_far_pass1_psi<KMODE_REAL>(ctx, X, grid, smem, small);
            else if (kmode == KMODE_IMAG) launch_far_pass1_psi<KMODE_IMAG>(ctx, X, grid, smem, small);

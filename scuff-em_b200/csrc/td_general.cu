@@ -273,7 +273,7 @@ __device__ void tdg_integrand(const TDGen &W, const double *y, double f[TDG_FDIM
          const int nn = n + nOff;
          cd Kv;
          if (npk < 2)      // TD_HELMHOLTZ: e^{ikX} ExpRel(n,-ikX) / (n X)
-          { cd t = eIKXv[d] * E[d][nn]; const double dn = nn * X[d]; Kv = mk(t.x / dn, t.y / dn); }
+          { cd t = eIKXv[d] * E[d][nn]; const double dn = nn * X[d], rdn = 1.0 / dn; Kv = mk(td_div_rcp(t.x, dn, rdn), td_div_rcp(t.y, dn, rdn)); }
          else              // TD_GRADHELMHOLTZ
           { cd t1 = IK * E[d][nn - 1]; const double d1 = (double)nn - 1.0; t1 = mk(t1.x / d1, t1.y / d1);
             const double d2 = ((double)nn - 2.0) * X[d]; cd t2 = mk(E[d][nn - 2].x / d2, E[d][nn - 2].y / d2);

@@ -81,7 +81,7 @@ __device__ void td_ct_pair_eval(double A2, double AdB, double B2, cd k, int nLo,
      cd emIKX = mk(0.0, 0.0);
      if (!small) emIKX = (mIKX.y == 0.0) ? mk(exp(mIKX.x), 0.0) : cexp_(mIKX);
      for (int n = nLo + 1; n <= nHi + 1; n++)
-      { cd t = eIKX * exprel_v3p0_pre(n, mIKX, emIKX, small); double dn = n * X[d]; K[d][n] = mk(t.x / dn, t.y / dn); }
+      { cd t = eIKX * exprel_v3p0_pre(n, mIKX, emIKX, small); const double dn = n * X[d], rdn = 1.0 / dn; K[d][n] = mk(td_div_rcp(t.x, dn, rdn), td_div_rcp(t.y, dn, rdn)); }
    }
   const double s = 1.0 / (4.0 * M_PI);
   for (int it = 0; it < nIt; it++)
@@ -188,6 +188,26 @@ td_ct_pair_kernel(const NearArgs A, const TDTables T, const int *pairs, int nPai
      scatter_ppi(A.S, A.K, N.pa, N.pb, ea, eb, Pa.sl[i], Pb.sl[j], H0, H1);
      atomicAdd(A.counters + 2, (A.S.symmetric && N.pa != N.pb && ea == eb) ? 2ull : 1ull);
    }
+}
+
+// ---- self-test of td_math.cuh td_div_int (tests/test_fastmath_gpu.py): out[6 i + 5] = x[i] / ((i % 127) + 1) ----
+__global__ void td_div_selftest_kernel(int n, const double *x, double *out)
+{ const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[6 * i + 5] = td_div_int(x[i], (i % 127) + 1);
+}
+int run_td_div_selftest(scuffcuda_context *ctx, int n, const double *xh, double *outh)
+{ double *dx = nullptr, *dout = nullptr;
+  if (cudaMalloc(&dx, n * sizeof(double)) != cudaSuccess || cudaMalloc(&dout, 6 * (size_t)n * sizeof(double)) != cudaSuccess)
+   { cudaFree(dx); ctx->err = "selftest allocation failed"; return 1; }
+  cudaMemcpyAsync(dx, xh, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(dout, outh, 6 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  ctx->launches++;
+  td_div_selftest_kernel<<<(n + 127) / 128, 128, 0, ctx->stream>>>(n, dx, dout);
+  cudaMemcpyAsync(outh, dout, 6 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dx); cudaFree(dout);
+  if (e != cudaSuccess) { ctx->err = std::string("td_div selftest: ") + cudaGetErrorString(e); return 1; }
+  return 0;
 }
 
 static int td_grow_scratch(scuffcuda_context *ctx, size_t need)

@@ -31,6 +31,36 @@ struct TDTables
 SCUFF_HD cd cexp_(cd z) { double e = exp(z.x), s, c; sincos(z.y, &s, &c); return mk(e * c, e * s); }
 SCUFF_HD double cabs_(cd z) { return hypot(z.x, z.y); }
 
+
+// x / d for a small positive integer d (the divisors m + n of the ExpRel series).  The reference divides; an IEEE division costs
+// ~25 instructions on the device (MUFU.RCP64H seed, Newton steps, range checks, slow-path call) and these divisions were half of
+// the Taylor-Duffy kernels' issue slots.  With y = RN(1/d) tabulated, q0 = RN(x y), r = x - q0 d (exact in one FMA) and
+// q = RN(q0 + r y) is the correctly rounded quotient (Markstein's division step: q0 is a faithful estimate) — three FP64
+// instructions, same bits.  The host build (formula checks without a GPU) keeps the plain division.
+#if defined(__CUDACC__)
+static __constant__ double c_td_rcp[128] = { 0.0, 1.0, 0.5, 0.3333333333333333, 0.25, 0.2, 0.16666666666666666, 0.14285714285714285, 0.125, 0.1111111111111111, 0.1, 0.09090909090909091, 0.08333333333333333, 0.07692307692307693, 0.07142857142857142, 0.06666666666666667, 0.0625, 0.058823529411764705, 0.05555555555555555, 0.05263157894736842, 0.05, 0.047619047619047616, 0.045454545454545456, 0.043478260869565216, 0.041666666666666664, 0.04, 0.038461538461538464, 0.037037037037037035, 0.03571428571428571, 0.034482758620689655, 0.03333333333333333, 0.03225806451612903, 0.03125, 0.030303030303030304, 0.029411764705882353, 0.02857142857142857, 0.027777777777777776, 0.02702702702702703, 0.02631578947368421, 0.02564102564102564, 0.025, 0.024390243902439025, 0.023809523809523808, 0.023255813953488372, 0.022727272727272728, 0.022222222222222223, 0.021739130434782608, 0.02127659574468085, 0.020833333333333332, 0.02040816326530612, 0.02, 0.0196078431372549, 0.019230769230769232, 0.018867924528301886, 0.018518518518518517, 0.01818181818181818, 0.017857142857142856, 0.017543859649122806, 0.017241379310344827, 0.01694915254237288, 0.016666666666666666, 0.01639344262295082, 0.016129032258064516, 0.015873015873015872, 0.015625, 0.015384615384615385, 0.015151515151515152, 0.014925373134328358, 0.014705882352941176, 0.014492753623188406, 0.014285714285714285, 0.014084507042253521, 0.013888888888888888, 0.0136986301369863, 0.013513513513513514, 0.013333333333333334, 0.013157894736842105, 0.012987012987012988, 0.01282051282051282, 0.012658227848101266, 0.0125, 0.012345679012345678, 0.012195121951219513, 0.012048192771084338, 0.011904761904761904, 0.011764705882352941, 0.011627906976744186, 0.011494252873563218, 0.011363636363636364, 0.011235955056179775, 0.011111111111111112, 0.01098901098901099, 0.010869565217391304, 0.010752688172043012, 0.010638297872340425, 0.010526315789473684, 0.010416666666666666, 0.010309278350515464, 0.01020408163265306, 0.010101010101010102, 0.01, 0.009900990099009901, 0.00980392156862745, 0.009708737864077669, 0.009615384615384616, 0.009523809523809525, 0.009433962264150943, 0.009345794392523364, 0.009259259259259259, 0.009174311926605505, 0.00909090909090909, 0.009009009009009009, 0.008928571428571428, 0.008849557522123894, 0.008771929824561403, 0.008695652173913044, 0.008620689655172414, 0.008547008547008548, 0.00847457627118644, 0.008403361344537815, 0.008333333333333333, 0.008264462809917356, 0.00819672131147541, 0.008130081300813009, 0.008064516129032258, 0.008, 0.007936507936507936, 0.007874015748031496 };
+#endif
+SCUFF_HD double td_div_int(double x, int d)
+{
+#if defined(__CUDA_ARCH__)
+  const double y = c_td_rcp[d], dv = (double)d;
+  const double q0 = x * y, r = fma(-q0, dv, x);
+  return fma(r, y, q0);
+#else
+  return x / ((double)d);
+#endif
+}
+// x / d given y = RN(1/d) (one IEEE division shared by several quotients)
+SCUFF_HD double td_div_rcp(double x, double d, double y)
+{
+#if defined(__CUDA_ARCH__)
+  const double q0 = x * y, r = fma(-q0, d, x);
+  return fma(r, y, q0);
+#else
+  (void)y; return x / d;
+#endif
+}
+
 // ExpRel(n,Z) = (e^Z - first n Taylor terms) / (Z^n/n!)   (TaylorDuffy.cc:829-891)
 SCUFF_HD cd exprel_v3p0(int n, cd Z)
 { if (Z.y == 0.0)
@@ -38,25 +68,24 @@ SCUFF_HD cd exprel_v3p0(int n, cd Z)
      if (fabs(X) < 0.1)
       { double Sum = 1.0, Term = 1.0;
         for (int m = 1; m < 100; m++)
-         { Term *= X / ((double)(m + n)); Sum += Term;
+         { Term *= td_div_int(X, m + n); Sum += Term;
            if (fabs(Term) < 1.0e-8 * fabs(Sum)) break; }
         return mk(Sum, 0.0);
       }
      double Sum = exp(X), Term = 1.0;
-     for (int m = 0; m < n; m++) { Sum -= Term; Term *= X / ((double)(m + 1)); }
+     for (int m = 0; m < n; m++) { Sum -= Term; Term *= td_div_int(X, m + 1); }
      return mk(Sum / Term, 0.0);
    }
   if (cabs_(Z) < 0.1)
    { cd Sum = mk(1.0, 0.0), Term = mk(1.0, 0.0);
      for (int m = 1; m < 100; m++)
-      { double dv = (double)(m + n);
-        Term = Term * mk(Z.x / dv, Z.y / dv); Sum += Term;
+      { Term = Term * mk(td_div_int(Z.x, m + n), td_div_int(Z.y, m + n)); Sum += Term;
         if (norm2(Term) < 1.0e-16 * norm2(Sum)) break; }
      return Sum;
    }
   cd Sum = cexp_(Z), Term = mk(1.0, 0.0);
   for (int m = 0; m < n; m++)
-   { Sum -= Term; double dv = (double)(m + 1); Term = Term * mk(Z.x / dv, Z.y / dv); }
+   { Sum -= Term; Term = Term * mk(td_div_int(Z.x, m + 1), td_div_int(Z.y, m + 1)); }
   return cdiv(Sum, Term);
 }
 
@@ -107,12 +136,12 @@ SCUFF_HD cd exprel_v3p0_pre(int n, cd Z, cd expZ, bool small)
 { if (small) return exprel_v3p0(n, Z);
   if (Z.y == 0.0)
    { double X = Z.x, Sum = expZ.x, Term = 1.0;
-     for (int m = 0; m < n; m++) { Sum -= Term; Term *= X / ((double)(m + 1)); }
+     for (int m = 0; m < n; m++) { Sum -= Term; Term *= td_div_int(X, m + 1); }
      return mk(Sum / Term, 0.0);
    }
   cd Sum = expZ, Term = mk(1.0, 0.0);
   for (int m = 0; m < n; m++)
-   { Sum -= Term; double dv = (double)(m + 1); Term = Term * mk(Z.x / dv, Z.y / dv); }
+   { Sum -= Term; Term = Term * mk(td_div_int(Z.x, m + 1), td_div_int(Z.y, m + 1)); }
   return cdiv(Sum, Term);
 }
 
@@ -134,7 +163,7 @@ SCUFF_HD void td_ct_integrand(const TDCommonTriangle &W, double y, double f[4])
      cd emIKX = mk(0.0, 0.0);
      if (!small) emIKX = (mIKX.y == 0.0) ? mk(exp(mIKX.x), 0.0) : cexp_(mIKX);
      for (int n = nLo + 1; n <= nHi + 1; n++)
-      { cd t = eIKX * exprel_v3p0_pre(n, mIKX, emIKX, small); double dn = n * X[d]; K[d][n] = mk(t.x / dn, t.y / dn); }
+      { cd t = eIKX * exprel_v3p0_pre(n, mIKX, emIKX, small); const double dn = n * X[d], rdn = 1.0 / dn; K[d][n] = mk(td_div_rcp(t.x, dn, rdn), td_div_rcp(t.y, dn, rdn)); }
    }
   for (int np = 0; np < 2; np++)
    { cd Sum = mk(0.0, 0.0);

@@ -49,3 +49,17 @@ def test_exp_neg(ps):
     print("exp(-x) max rel err %.3e" % rel.max())
     assert rel.max() <= 4e-16
     assert np.all(out[x > 700.0, 4] == 0.0)
+
+
+def test_small_integer_division_is_exact(ps):
+    """td_math.cuh td_div_int (tabulated reciprocal + one Markstein correction step, used by the Taylor-Duffy ExpRel series in
+    place of an IEEE division) returns the correctly rounded quotient: bit-identical to x / d"""
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-1, 1, 400000), 10.0 ** rng.uniform(-30, 30, 200000) * rng.choice([-1.0, 1.0], 200000),
+                        rng.uniform(-0.1, 0.1, 400000), np.arange(1, 2001, dtype=float), [0.0]])
+    out = run(ps, x)
+    d = (np.arange(len(x)) % 127) + 1.0
+    want = x / d
+    bad = np.nonzero(out[:, 5] != want)[0]
+    print("x / d: %d of %d quotients differ from the IEEE division" % (len(bad), len(x)))
+    assert len(bad) == 0
