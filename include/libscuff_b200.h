@@ -139,6 +139,9 @@ typedef struct RWGEdge
    RWGEdge *Next;
  } RWGEdge;
 
+/* EdgeEdgeInteractions.cc:241-270 (libscuff.h: CreateGammaMatrix) */
+void CreateGammaMatrix(double *TorqueAxis, double *GammaMatrix);
+
 class RWGGeometry;
 
 class RWGSurface

@@ -138,6 +138,17 @@ typedef struct scuffcuda_ssi_args {
 int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb,
                              const scuffcuda_ssi_args *args, int handle);
 
+/* Derivative blocks of the same surface pair — the GradM[3] / dMdT[NumTorqueAxes] arguments of AssembleBEMMatrixBlock
+ * (AssembleBEMMatrix.cc:349-391 -> GetSurfaceSurfaceInteractions GradB / dBdTheta, SurfaceSurfaceInteractions.cc:205-327;
+ * integrands PanelPanelInteractions.cc:176-199, 6x6 rule for far pairs, 78x78 without desingularisation otherwise, zero for
+ * Taylor-Duffy pairs :484-486, :504-510).  grad_handles[Mu] / dmdt_handles[n]: matrices of the block's shape or 0 to skip a
+ * component; gamma_matrix: 9 doubles per torque axis as CreateGammaMatrix writes them (EdgeEdgeInteractions.cc:241-270).
+ * args as for scuffcuda_assemble_block (symmetric must be 0: the reference's callers ask for derivatives of blocks between
+ * different surfaces; gba_a/gba_b and column ranges are not available).  The value block itself is NOT computed here.   */
+int scuffcuda_assemble_block_gradients(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args *args,
+                                       const int grad_handles[3], int num_torque_axes, const double *gamma_matrix,
+                                       const int dmdt_handles[3]);
+
 /* ---- periodic Green's function (libs/libscuff/GBarAccelerator.h:45-92, GBarVDEwald.cc:931-996) ------------------ */
 /* CreateGBarAccelerator(LBasis, RhoMin, RhoMax, k, kBloch, RelTol, ExcludeInnerCells) (GBarAccelerator.cc:339-547) on the
  * device: Ewald sums, grid-spacing probes, table fill and tricubic fit are CUDA kernels; the table stays in HBM.

@@ -8,6 +8,10 @@
  *   ref_driver matrix <geo> <wRe> <wIm> <out.bin> [--kbloch kx ky] [--imag] [--repeat n]
  *                     [--cache-in f] [--cache-out f] [--block nsa nsb] [--transfile f --trans n]
  *                     (--trans: apply the n-th transformation of a .trans file first, as scuff-cas3D does)
+ *   ref_driver gradblock <geo> <wRe> <wIm> <nsa> <nsb> <out.bin> [--imag] [--transfile f --trans n] [--torque ax ay az]...
+ *        AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:349-391) with GradM[3] and dMdT[NumTorqueAxes] (CreateGammaMatrix,
+ *        EdgeEdgeInteractions.cc:241-270): writes the value block, the three gradient blocks and the torque blocks one after
+ *        the other (complex, or real with --imag as scuff-cas3D allocates them)
  *   ref_driver ssi    <geo> <wRe> <wIm> <nsa> <nsb> <Lx> <Ly> <Lz> <out.bin> [--cache-out f]
  *        GetSurfaceSurfaceInteractions (SurfaceSurfaceInteractions.cc:426-585) for one surface pair with surface b displaced
  *        by L (the neighbour-cell blocks of the periodic assembly, AssembleBEMMatrix.cc:72-114), not Symmetric
@@ -156,6 +160,34 @@ int main(int argc, char **argv)
      FILE *f=fopen(Out,"wb"); if(!f) return 1;
      size_t N=(size_t)M->NR*M->NC;
      if(Imag) fwrite(M->DM,sizeof(double),N,f); else fwrite(M->ZM,sizeof(cdouble),N,f);
+     fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"gradblock"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); int nsa=atoi(argv[5]), nsb=atoi(argv[6]); const char *Out=argv[7];
+     bool Imag=false; const char *TransFile=0; int nTrans=0; int NTA=0; double Axes[9];
+     for(int n=8;n<argc;n++)
+      { if(!strcmp(argv[n],"--imag")) Imag=true;
+        else if(!strcmp(argv[n],"--transfile")) TransFile=argv[++n];
+        else if(!strcmp(argv[n],"--trans")) nTrans=atoi(argv[++n]);
+        else if(!strcmp(argv[n],"--torque") && NTA<3) { Axes[3*NTA]=atof(argv[n+1]); Axes[3*NTA+1]=atof(argv[n+2]); Axes[3*NTA+2]=atof(argv[n+3]); NTA++; n+=3; } }
+     if (TransFile)
+      { GTCList GTCs=ReadTransFile(TransFile);
+        if(nTrans<0||nTrans>=(int)GTCs.size()) { fprintf(stderr,"no transformation %i in %s\n",nTrans,TransFile); return 2; }
+        G->Transform(GTCs[nTrans]); }
+     int NBFA=G->Surfaces[nsa]->NumBFs, NBFB=G->Surfaces[nsb]->NumBFs, RC=Imag?LHM_REAL:LHM_COMPLEX;
+     HMatrix *M=new HMatrix(NBFA,NBFB,RC), *GradM[3], *dMdT[3]={0,0,0};
+     for(int m=0;m<3;m++) GradM[m]=new HMatrix(NBFA,NBFB,RC);
+     for(int m=0;m<NTA;m++) dMdT[m]=new HMatrix(NBFA,NBFB,RC);
+     double Gamma[27];
+     for(int m=0;m<NTA;m++) CreateGammaMatrix(Axes+3*m,Gamma+9*m);
+     double t0=Now();
+     G->AssembleBEMMatrixBlock(nsa,nsb,Omega,0,M,GradM,0,0,0,false,NTA,NTA?dMdT:0,NTA?Gamma:0);
+     printf("{\"NR\": %i, \"NC\": %i, \"real\": %i, \"ntorque\": %i, \"threads\": %i, \"times\": [%.6f]}\n",NBFA,NBFB,(int)Imag,NTA,omp_get_max_threads(),Now()-t0);
+     FILE *f=fopen(Out,"wb"); if(!f) return 1;
+     size_t N=(size_t)NBFA*NBFB;
+     HMatrix *All[7]={M,GradM[0],GradM[1],GradM[2],dMdT[0],dMdT[1],dMdT[2]};
+     for(int q=0;q<4+NTA;q++) { if(Imag) fwrite(All[q]->DM,sizeof(double),N,f); else fwrite(All[q]->ZM,sizeof(cdouble),N,f); }
      fclose(f); return 0;
    }
 

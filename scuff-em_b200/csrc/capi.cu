@@ -25,6 +25,8 @@ static int fail(scuffcuda_context *ctx, const char *fmt, ...)
 #define CKS(call) do { cusolverStatus_t s_ = (call); if (s_ != CUSOLVER_STATUS_SUCCESS) return fail(ctx, "%s:%d: %s: cusolver status %d", __FILE__, __LINE__, #call, (int)s_); } while (0)
 
 namespace scuffcuda {
+int run_gradients(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args *a, const KParams &K, const StampParams &SP, double kabs,
+                  double *const GM[3], int nTorque, double *const TM[3], const double *gamma);   // grad_kernel.cu
 int run_td_div_selftest(scuffcuda_context *ctx, int n, const double *x, double *out);   // td_kernel.cu
 // far_kernel.cu
 void far_slots_release(scuffcuda_context *ctx);     // window/slot tables of the staged scatter
@@ -526,6 +528,57 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   CK(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 5; i++) ctx->counts[i] = hc[i];
   ctx->pairCounts[0] = hc[5]; ctx->pairCounts[1] = hc[6];
+  return 0;
+}
+
+int scuffcuda_assemble_block_gradients(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args *a,
+                                       const int grad_handles[3], int num_torque_axes, const double *gamma_matrix, const int dmdt_handles[3])
+{ int NS = (int)ctx->surfaces.size();
+  if (nsa < 0 || nsa >= NS || nsb < 0 || nsb >= NS) return fail(ctx, "assemble_block_gradients: invalid surface index");
+  Surface &Sa = ctx->surfaces[nsa], &Sb = ctx->surfaces[nsb];
+  if (!Sa.dpanels || !Sb.dpanels) return fail(ctx, "assemble_block_gradients: surface not set");
+  if (a->symmetric || nsa == nsb) return fail(ctx, "assemble_block_gradients: derivative blocks of a surface with itself are not available on the device path");
+  if (a->gba_a || a->gba_b || a->col_end > 0) return fail(ctx, "assemble_block_gradients: periodic tables and column ranges are not available for derivative blocks");
+  if (num_torque_axes < 0 || num_torque_axes > 3 || (num_torque_axes > 0 && (!gamma_matrix || !dmdt_handles)))
+   return fail(ctx, "assemble_block_gradients: invalid torque-axis arguments");
+  const int NBFA = Sa.isPEC ? Sa.NE : 2 * Sa.NE, NBFB = Sb.isPEC ? Sb.NE : 2 * Sb.NE;
+  Matrix *GM[3] = { nullptr, nullptr, nullptr }, *TM[3] = { nullptr, nullptr, nullptr }, *first = nullptr;
+  for (int m = 0; m < 3; m++)
+   { if (grad_handles && grad_handles[m]) { GM[m] = get_matrix(ctx, grad_handles[m]); if (!GM[m]) return fail(ctx, "invalid matrix handle %d", grad_handles[m]); }
+     if (m < num_torque_axes && dmdt_handles[m]) { TM[m] = get_matrix(ctx, dmdt_handles[m]); if (!TM[m]) return fail(ctx, "invalid matrix handle %d", dmdt_handles[m]); } }
+  for (Matrix *M : { GM[0], GM[1], GM[2], TM[0], TM[1], TM[2] })
+   { if (!M) continue;
+     if (!first) first = M;
+     if (M->NR != first->NR || M->NC != first->NC || M->isReal != first->isReal) return fail(ctx, "assemble_block_gradients: derivative matrices differ in shape or type");
+     if (a->row_offset < 0 || a->col_offset < 0 || a->row_offset + NBFA > M->NR || a->col_offset + NBFB > M->NC)
+      return fail(ctx, "assemble_block_gradients: block (%d+%d, %d+%d) exceeds matrix %dx%d", a->row_offset, NBFA, a->col_offset, NBFB, M->NR, M->NC); }
+  if (!first) return 0;
+  CK(cudaSetDevice(ctx->device));
+  if (!a->accumulate)
+   for (Matrix *M : { GM[0], GM[1], GM[2], TM[0], TM[1], TM[2] })
+    if (M) { launch_zero_block(ctx, *M, a->row_offset, NBFA, a->col_offset, NBFB); M->factored = false; }
+  cdouble Omega(a->omega[0], a->omega[1]);
+  const cdouble II(0.0, 1.0);
+  for (int region = 0; region < 2; region++)
+   { cdouble Eps = region == 0 ? cdouble(a->eps_a[0], a->eps_a[1]) : cdouble(a->eps_b[0], a->eps_b[1]);
+     cdouble Mu = region == 0 ? cdouble(a->mu_a[0], a->mu_a[1]) : cdouble(a->mu_b[0], a->mu_b[1]);
+     double Sign = region == 0 ? a->sign_a : a->sign_b;
+     if (Eps == 0.0) continue;
+     if (region == 1 && (Sa.isPEC || Sb.isPEC)) continue;
+     cdouble k = csqrt2(Eps * Mu) * Omega;
+     if (real(k) == 0.0 && imag(k) == 0.0) continue;
+     cdouble PreFac1 = Sign * II * Mu * Omega, PreFac2 = -Sign * II * k, PreFac3 = -Sign * II * Eps * Omega;
+     KParams K = make_kparams(real(k), imag(k));
+     StampParams SP;
+     SP.M = nullptr; SP.ld = first->NR; SP.isReal = first->isReal ? 1 : 0;
+     SP.rowOff = a->row_offset; SP.colOff = a->col_offset;
+     SP.aPEC = Sa.isPEC; SP.bPEC = Sb.isPEC; SP.symmetric = 0;
+     SP.c1 = mk(real(PreFac1), imag(PreFac1)); SP.c2 = mk(real(PreFac2), imag(PreFac2)); SP.c3 = mk(real(PreFac3), imag(PreFac3));
+     SP.colLo = 0; SP.colHi = 0x7fffffff;
+     double *gm[3] = { GM[0] ? GM[0]->d : nullptr, GM[1] ? GM[1]->d : nullptr, GM[2] ? GM[2]->d : nullptr };
+     double *tm[3] = { TM[0] ? TM[0]->d : nullptr, TM[1] ? TM[1]->d : nullptr, TM[2] ? TM[2]->d : nullptr };
+     if (run_gradients(ctx, nsa, nsb, a, K, SP, std::abs(k), gm, num_torque_axes, tm, gamma_matrix)) return 1; }
+  CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 

@@ -309,6 +309,10 @@ static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, 
 }
 
 
+// the pair plan of a surface pair for other translation units (grad_kernel.cu)
+Plan *near_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, bool useDisp, const double *L, int &status)
+{ return get_plan(ctx, nsa, nsb, symmetric, useDisp, L, status); }
+
 int run_near(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args *a,
              const KParams &K, const StampParams &SP, int kmode, double kabs)
 { int status = 0;

@@ -104,6 +104,34 @@ static void AssembleBlockOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omeg
   M->HostStale = true;
 }
 
+// GradM[3] / dMdT[NumTorqueAxes] of a block between two different surfaces (scuffcuda_assemble_block_gradients)
+static void AssembleDerivativeBlocksOnDevice(RWGGeometry *G, int nsa, int nsb, cdouble Omega, HMatrix **GradM, int RowOffset, int ColOffset,
+                                             int NumTorqueAxes, HMatrix **dMdT, double *GammaMatrix)
+{ scuffcuda_context *ctx = GetCudaContext();
+  RWGSurface *Sa = G->Surfaces[nsa], *Sb = G->Surfaces[nsb];
+  G->UpdateCachedEpsMuValues(Omega);
+  G->SyncDeviceGeometry();
+  int gh[3] = { 0, 0, 0 }, th[3] = { 0, 0, 0 };
+  for (int m = 0; m < 3; m++)
+   { if (GradM && GradM[m]) { GradM[m]->PrepareDevice(); gh[m] = GradM[m]->DeviceHandle; }
+     if (dMdT && m < NumTorqueAxes && dMdT[m]) { dMdT[m]->PrepareDevice(); th[m] = dMdT[m]->DeviceHandle; } }
+  scuffcuda_ssi_args A; memset(&A, 0, sizeof A);
+  A.omega[0] = real(Omega); A.omega[1] = imag(Omega);
+  A.row_offset = RowOffset; A.col_offset = ColOffset;
+  A.force_taylor_duffy = RWGGeometry::DisableCache ? 1 : 0;
+  double Signs[2]; int CR[2];
+  int NumCommonRegions = CountCommonRegions(Sa, Sb, CR, Signs);
+  cdouble EpsA = 0.0, MuA = 0.0, EpsB = 0.0, MuB = 0.0; double SignA = 0.0, SignB = 0.0;
+  if (NumCommonRegions >= 1) { EpsA = G->EpsTF[CR[0]]; MuA = G->MuTF[CR[0]]; SignA = Signs[0]; }
+  if (NumCommonRegions == 2) { EpsB = G->EpsTF[CR[1]]; MuB = G->MuTF[CR[1]]; SignB = Signs[1]; }
+  A.eps_a[0] = real(EpsA); A.eps_a[1] = imag(EpsA); A.mu_a[0] = real(MuA); A.mu_a[1] = imag(MuA); A.sign_a = SignA;
+  A.eps_b[0] = real(EpsB); A.eps_b[1] = imag(EpsB); A.mu_b[0] = real(MuB); A.mu_b[1] = imag(MuB); A.sign_b = SignB;
+  if (scuffcuda_assemble_block_gradients(ctx, nsa, nsb, &A, gh, dMdT ? NumTorqueAxes : 0, GammaMatrix, th)) ErrExit("%s", scuffcuda_last_error(ctx));
+  for (int m = 0; m < 3; m++)
+   { if (GradM && GradM[m]) { GradM[m]->HostStale = true; GradM[m]->SyncToHost(); }
+     if (dMdT && m < NumTorqueAxes && dMdT[m]) { dMdT[m]->HostStale = true; dMdT[m]->SyncToHost(); } }
+}
+
 // AddSurfaceZetaContributionToBEMMatrix (SurfaceSurfaceInteractions.cc:339-421): a PEC surface with SURFACE_IMPEDANCE Zeta adds
 // -Zeta(w, X) * \int f_a . f_b to the entries of basis functions that share a panel; X = the edge centroid on the diagonal, else
 // the centroid of the (first) shared panel.  Only for the undisplaced diagonal block of a compact geometry.  Entries outside
@@ -158,14 +186,19 @@ void RWGGeometry::AssembleBEMMatrixBlock(int nsa, int nsb, cdouble Omega, double
 { (void)GammaMatrix;
   if (TransposeAccelerator) ErrExit("%s:%i: TransposeAccelerator not implemented", __FILE__, __LINE__);
   if (nsa < 0 || nsa >= NumSurfaces || nsb < 0 || nsb >= NumSurfaces) ErrExit("AssembleBEMMatrixBlock: invalid surface indices (%i,%i)", nsa, nsb);
-  if (GradM || (NumTorqueAxes > 0 && dMdT))
-   ErrExit("AssembleBEMMatrixBlock: GradM / dMdT derivative blocks are not yet available on the device path");
+  const bool WantDerivatives = GradM || (NumTorqueAxes > 0 && dMdT);
+  if (WantDerivatives && (LBasis != 0 || nsa == nsb))
+   ErrExit("AssembleBEMMatrixBlock: GradM / dMdT derivative blocks are available on the device path for blocks between two different "
+           "surfaces of a compact geometry only");
+  if (WantDerivatives && NumTorqueAxes > 0 && (NumTorqueAxes > 3 || GammaMatrix == 0))
+   ErrExit("AssembleBEMMatrixBlock: NumTorqueAxes must be 1..3 with a GammaMatrix");
   if (getenv("SCUFF_TBLOCK_PATH")) Warn("SCUFF_TBLOCK_PATH is ignored by the device assembly path");
   // the caller may have written into M on the host (e.g. other blocks): keep both sides coherent
   M->PrepareDevice();
   for (int i = 0; i < 5; i++) LastPPICounts[i] = 0;
   if (LBasis == 0)
    { AssembleBlockOnDevice(this, nsa, nsb, Omega, M, RowOffset, ColOffset, nsa == nsb, false, 0, false, false);
+     if (WantDerivatives) AssembleDerivativeBlocksOnDevice(this, nsa, nsb, Omega, GradM, RowOffset, ColOffset, NumTorqueAxes, dMdT, GammaMatrix);
      if (nsa == nsb)
       { if (RowOffset != ColOffset && Surfaces[nsa]->SurfaceZeta) ErrExit("%s:%i: internal error", __FILE__, __LINE__);
         AddSurfaceZetaContribution(this, nsa, Omega, M, RowOffset, 0, 0); }
@@ -500,3 +533,19 @@ void StoreCache(const char *FileName)
   if (scuffcuda_fippi_store(ctx, FileName)) Warn("%s", scuffcuda_last_error(ctx)); }
 
 }  // namespace scuff
+
+// CreateGammaMatrix (EdgeEdgeInteractions.cc:241-270): Gamma = Lambda^T Gamma0 Lambda, the generator of rotations about TorqueAxis
+namespace scuff {
+void CreateGammaMatrix(double *TorqueAxis, double *GammaMatrix)
+{ double ax[3] = { TorqueAxis[0], TorqueAxis[1], TorqueAxis[2] };
+  const double n = sqrt(ax[0] * ax[0] + ax[1] * ax[1] + ax[2] * ax[2]);
+  for (int i = 0; i < 3; i++) ax[i] /= n;
+  const double ct = ax[2], st = sqrt(1.0 - ct * ct);
+  const double cp = (st < 1.0e-8) ? 1.0 : ax[0] / st, sp = (st < 1.0e-8) ? 0.0 : ax[1] / st;
+  const double Lambda[3][3] = { { ct * cp, ct * sp, -st }, { -sp, cp, 0.0 }, { st * cp, st * sp, ct } };
+  const double Gamma0[3][3] = { { 0.0, -1.0, 0.0 }, { 1.0, 0.0, 0.0 }, { 0.0, 0.0, 0.0 } };
+  memset(GammaMatrix, 0, 9 * sizeof(double));
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++)
+   GammaMatrix[i + 3 * j] += Lambda[k][i] * Gamma0[k][l] * Lambda[l][j];
+}
+}

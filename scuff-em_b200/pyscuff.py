@@ -342,6 +342,19 @@ class RWGGeometry:
                                                         float(np.imag(Omega)), kb, RowOffset, ColOffset, ABMBCache))
         return M
 
+    def AssembleBEMMatrixBlockGrad(self, nsa, nsb, Omega, M, GradM=None, TorqueAxes=None, dMdT=None):
+        """AssembleBEMMatrixBlock with its GradM[3] / dMdT[NumTorqueAxes] arguments (entries may be None); TorqueAxes: list of 3-vectors"""
+        L = host_lib()
+        gp = (C.c_void_p * 3)(*[(h.ptr if h is not None else None) for h in (GradM or [None] * 3)])
+        nt = len(TorqueAxes) if TorqueAxes else 0
+        ax = (C.c_double * max(3 * nt, 1))(*[float(x) for a in (TorqueAxes or []) for x in a])
+        tp = (C.c_void_p * 3)(*([(h.ptr if h is not None else None) for h in (dMdT or [])] + [None] * 3)[:3])
+        L.scuffb200_assemble_block_grad.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                    C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_void_p)]
+        _check(L.scuffb200_assemble_block_grad(self.ptr, M.ptr, nsa, nsb, float(np.real(Omega)), float(np.imag(Omega)),
+                                               gp if GradM else None, nt, ax, tp if dMdT else None))
+        return M
+
     def CreateABMBAccelerator(self, nsa, nsb, PureImagFreq=False):
         """kBloch-independent matrix-block cache of one surface pair (AssembleBEMMatrix.cc:260-318); None for compact geometries"""
         p = host_lib().scuffb200_create_abmb(self.ptr, nsa, nsb, int(PureImagFreq))

@@ -97,6 +97,28 @@ def ref_ssi(geo, omega, nsa, nsb, L, cache_out=None, tmpdir="/tmp/scuff_ref_cach
     return np.fromfile(out, dtype=np.complex128).reshape(info["NC"], info["NR"]).T, info
 
 
+def ref_gradblock(geo, omega, nsa, nsb, imag=False, torque_axes=(), trans=None, tmpdir="/tmp/scuff_ref_cache", env=None):
+    """Reference AssembleBEMMatrixBlock with GradM[3] and dMdT (ref_driver gradblock): returns [M, dM/dx, dM/dy, dM/dz, dM/dT_0, ...]"""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
+    os.makedirs(tmpdir, exist_ok=True)
+    key = hashlib.md5(repr(("grad", geo, complex(omega), nsa, nsb, imag, tuple(map(tuple, torque_axes)), trans)).encode()).hexdigest()[:16]
+    out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
+    cmd = [REF_DRIVER, "gradblock", os.path.basename(geo), repr(float(np.real(omega))), repr(float(np.imag(omega))), str(nsa), str(nsb), out]
+    if imag:
+        cmd += ["--imag"]
+    if trans is not None:
+        cmd += ["--transfile", trans[0], "--trans", str(trans[1])]
+    for ax in torque_axes:
+        cmd += ["--torque"] + [repr(float(x)) for x in ax]
+    r = subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True,
+                       env=dict(os.environ, **(env or {})))
+    info = json.loads(r.stdout.strip().splitlines()[-1])
+    dt = np.float64 if info["real"] else np.complex128
+    A = np.fromfile(out, dtype=dt).reshape(4 + info["ntorque"], info["NC"], info["NR"])
+    return [A[q].T for q in range(A.shape[0])], info
+
+
 def ref_pbcinner(geo, omega, kbloch, nsa, nsb, cache_out=None, tmpdir="/tmp/scuff_ref_cache", env=None):
     """Reference AssembleBEMMatrixBlock of a periodic geometry minus its outer-cell (GBar) step, both from the reference's
     own code (ref_driver pbcinner): the Bloch-phased inner-cell blocks.  Returns (inner, full, info)."""
