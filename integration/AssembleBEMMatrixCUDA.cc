@@ -6,8 +6,9 @@
 // file, and a three-line hook inserted at the top of the compact branch of AssembleBEMMatrixBlock, AssembleBEMMatrix.cc:371),
 // uses only the reference's own types (RWGGeometry, RWGSurface, HMatrix, GetSSIArgStruct) and links with -lscuff_cuda.
 // Opt-in at run time: SCUFF_CUDA=1 (device: SCUFF_CUDA_DEVICE, default 0).  Anything the device path does not cover
-// (GradM / dMdT derivative blocks, packed HMatrix storage, periodic lattices in this shim) returns false and the
-// reference's CPU path runs, unchanged.
+// (derivative blocks of a surface with itself, packed HMatrix storage, periodic lattices in this shim) returns false and the
+// reference's CPU path runs, unchanged.  GradM / dMdT of blocks between different surfaces (what scuff-cas3D asks for,
+// CasimirIntegrand.cc:443-447) go through scuffcuda_assemble_block_gradients.
 //
 // What it replaces: GetSurfaceSurfaceInteractions for Args->B = M at (RowOffset, ColOffset) with Symmetric = (nsa == nsb)
 // (AssembleBEMMatrix.cc:373-387, SurfaceSurfaceInteractions.cc:426-585): material values are evaluated on the host exactly
@@ -62,10 +63,12 @@ static void SendSurface(scuffcuda_context *ctx, int ns, RWGSurface *S)
 
 // returns true if the block was assembled on the device
 bool AssembleBEMMatrixBlockCUDA(RWGGeometry *G, int nsa, int nsb, cdouble Omega, HMatrix *M, HMatrix **GradM,
-                                int RowOffset, int ColOffset, int NumTorqueAxes, HMatrix **dMdT)
+                                int RowOffset, int ColOffset, int NumTorqueAxes, HMatrix **dMdT, double *GammaMatrix)
 { const char *Env=getenv("SCUFF_CUDA");
   if (!Env || Env[0]!='1') return false;
-  if (G->LBasis!=0 || GradM!=0 || (NumTorqueAxes>0 && dMdT!=0) || M->StorageType!=LHM_NORMAL) return false;
+  const bool WantDerivatives = GradM!=0 || (NumTorqueAxes>0 && dMdT!=0);
+  if (G->LBasis!=0 || M->StorageType!=LHM_NORMAL) return false;
+  if (WantDerivatives && (nsa==nsb || NumTorqueAxes>3 || (NumTorqueAxes>0 && GammaMatrix==0))) return false;
   if (RWGGeometry::UseHRWGFunctions) return false;          // half-RWG basis functions: not on the device path
 
   scuffcuda_context *ctx=CudaContext();
@@ -111,6 +114,25 @@ bool AssembleBEMMatrixBlockCUDA(RWGGeometry *G, int nsa, int nsb, cdouble Omega,
   void *dst = IsReal ? (void *)(M->DM + RowOffset + (size_t)ColOffset*M->NR)
                      : (void *)(M->ZM + RowOffset + (size_t)ColOffset*M->NR);
   if (scuffcuda_matrix_download(ctx,h,dst,M->NR)) ErrExit("%s",scuffcuda_last_error(ctx));
+
+  // derivative blocks: same arguments, one scratch matrix per requested component, copied into the caller's matrices
+  if (WantDerivatives)
+   { int gh[3]={0,0,0}, th[3]={0,0,0};
+     static std::map<std::vector<int>, std::vector<int> > GradScratch;
+     std::vector<int> &hs=GradScratch[Key];
+     while (hs.size()<6) { int hh=0; if (scuffcuda_matrix_create(ctx,NBFA,NBFB,IsReal,&hh)) ErrExit("%s",scuffcuda_last_error(ctx)); hs.push_back(hh); }
+     for(int m=0; m<3; m++)
+      { if (GradM && GradM[m]) gh[m]=hs[m];
+        if (dMdT && m<NumTorqueAxes && dMdT[m]) th[m]=hs[3+m]; }
+     if (scuffcuda_assemble_block_gradients(ctx,nsa,nsb,&A,gh,dMdT ? NumTorqueAxes : 0,GammaMatrix,th)) ErrExit("%s",scuffcuda_last_error(ctx));
+     for(int m=0; m<3; m++)
+      for(int which=0; which<2; which++)
+       { HMatrix *D = which==0 ? ((GradM && GradM[m]) ? GradM[m] : 0) : ((dMdT && m<NumTorqueAxes && dMdT[m]) ? dMdT[m] : 0);
+         if (!D) continue;
+         if (D->NR!=M->NR || D->NC!=M->NC || D->RealComplex!=M->RealComplex) ErrExit("%s:%i: derivative matrices must have the shape and type of M",__FILE__,__LINE__);
+         void *dd = IsReal ? (void *)(D->DM + RowOffset + (size_t)ColOffset*D->NR) : (void *)(D->ZM + RowOffset + (size_t)ColOffset*D->NR);
+         if (scuffcuda_matrix_download(ctx,which==0 ? gh[m] : th[m],dd,D->NR)) ErrExit("%s",scuffcuda_last_error(ctx)); }
+   }
 
   // SURFACE_IMPEDANCE term: the reference's own routine on the host matrix (SurfaceSurfaceInteractions.cc:339-421,563-564)
   if (nsa==nsb && Sa->SurfaceZeta!=0)

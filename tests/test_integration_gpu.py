@@ -87,3 +87,26 @@ def test_scuff_scatter_through_the_binding(tmp_path):
     print("scuff-scatter EMTPFT (PAbs, PScat, F, T) cpu vs cuda, max deviation relative to the row's largest entry:", err.max())
     print(rows["cpu"][1], rows["cuda"][1])
     assert err.max() <= 2e-6          # the application prints 7 significant digits
+
+
+def test_derivative_blocks_through_the_binding(tmp_path):
+    """AssembleBEMMatrixBlock(GradM, dMdT) of the hooked reference library: SCUFF_CUDA=1 vs the same binary with it unset"""
+    _need("ref_driver_cuda", "libscuff_ref_cuda.so")
+    geo = os.path.join(GEODIR, "PECSpheres_327.scuffgeo")
+    outs = []
+    for cuda in (False, True):
+        out = os.path.join(str(tmp_path), "g%d.bin" % cuda)
+        cmd = [os.path.join(REFDIR, "ref_driver_cuda"), "gradblock", os.path.basename(geo), "0.0", "0.5", "0", "1", out, "--imag",
+               "--torque", "0", "0", "1", "--torque", "1", "0", "0"]
+        env = dict(os.environ, OMP_NUM_THREADS="8")
+        env.pop("SCUFF_CUDA", None)
+        if cuda:
+            env.update(SCUFF_CUDA="1", SCUFF_CUDA_VERBOSE="1")
+        r = subprocess.run(cmd, cwd=GEODIR, capture_output=True, text=True, check=True, env=env)
+        if cuda:
+            assert "blocks assembled on the device" in r.stderr
+        outs.append(np.fromfile(out, dtype=np.float64).reshape(6, 327, 327))
+    for q, lab in enumerate(["M", "dM/dx", "dM/dy", "dM/dz", "dM/dT0", "dM/dT1"]):
+        err = np.linalg.norm(outs[1][q] - outs[0][q]) / np.linalg.norm(outs[0][q])
+        print("hooked reference", lab, "rel err %.3e" % err)
+        assert err <= 1e-10
