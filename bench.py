@@ -356,7 +356,15 @@ def main():
     sweep = _load("sweep", os.path.join(PKG, "sweep.py"))
     mine = [w for _, w in sweep.points_for_rank([omega_of(j) for j in range(world * a.steps)], rank, world)]   # point j -> rank j % world
 
-    # cold pass: builds the frequency-independent FIPPI table on the device (kept resident for the sweep)
+    # cold pass: builds the frequency-independent FIPPI table on the device (kept resident for the sweep).  With several ranks
+    # the table is built ONCE: rank r computes the records with index = r (mod world), one all-reduce sums the shares
+    fippi_share = None
+    if world > 1:
+        barrier()
+        t0 = time.perf_counter()
+        nrec = sweep.share_fippi_table(ps, G, rank, world, device=torch.device("cuda", local))
+        torch.cuda.synchronize()
+        fippi_share = {"records": int(nrec), "seconds_this_rank": time.perf_counter() - t0}
     t0 = time.perf_counter()
     G.AssembleBEMMatrix(omega_of(rank), M=M, to_host=False)
     cold_s = time.perf_counter() - t0
@@ -494,6 +502,8 @@ def main():
             "clocks": clocks}
     if split:
         line["matrix_split"] = split
+    if fippi_share:
+        line["fippi_table_shared_build"] = fippi_share
     hbm = None
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]

@@ -241,7 +241,8 @@ class RWGGeometry
     * (M->HostStale) for the on-device LU consumer and the sweep drivers                   */
    /* ColBegin/ColEnd (ColEnd > 0): column-block assembly across GPUs — fill only the global columns [ColBegin, ColEnd)
     * of the UPPER triangle (symmetric case) and do not mirror; the caller gathers the column blocks and mirrors once   */
-   void AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M, int ColBegin = 0, int ColEnd = 0);
+   void PrepareNearPlans();   /* device path: pair plans + FIPPI records of all blocks, no assembly (sweeps that share the table) */
+  void AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix *M, int ColBegin = 0, int ColEnd = 0);
 
    /* internal */
    void InitPBCData();

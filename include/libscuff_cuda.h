@@ -201,6 +201,15 @@ int scuffcuda_fippi_store(scuffcuda_context *ctx, const char *filename);
 int scuffcuda_fippi_num_records(scuffcuda_context *ctx, long *n);
 /* drop every record (and the pair plans that index them); next assembly rebuilds the table on the device */
 int scuffcuda_fippi_clear(scuffcuda_context *ctx);
+/* FIPPI table built ONCE by all ranks of a sweep instead of once per rank: after _set_partition(rank, world) a pair
+ * plan computes only the records with index = rank (mod world); _prepare_block builds the plan of a surface pair (pair
+ * classification + its share of the records) without assembling anything; _host_records exposes the table (36 doubles per record,
+ * zeros where another rank computes) so that the caller can sum it over the ranks in place — record indices are identical on
+ * every rank because the geometry is; _commit sends the completed table to the device.  Reset with _set_partition(0, 1).   */
+int scuffcuda_fippi_set_partition(scuffcuda_context *ctx, int rank, int world);
+int scuffcuda_prepare_block(scuffcuda_context *ctx, int nsa, int nsb, int symmetric, int use_displacement, const double *displacement);
+int scuffcuda_fippi_host_records(scuffcuda_context *ctx, double **records, long *count);
+int scuffcuda_fippi_commit(scuffcuda_context *ctx);
 
 /* ---- self-test of the kernels' FP64 elementary functions (csrc/fastmath.cuh): for each x[i] writes
  *      out[6i..] = { rsqrt(|x|), rsqrt one-step variant, sin x, cos x, exp(-|x|), 0 }; host buffers          */

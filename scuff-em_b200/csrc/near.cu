@@ -194,6 +194,10 @@ static int fippi_sync_device(scuffcuda_context *ctx)
   return 0;
 }
 
+// FIPPI build partitioned over the ranks of a sweep: with partition (rank, world) set, a plan computes
+// only the records whose index is congruent to rank mod world; the others stay zero until the caller has summed the
+// tables of all ranks (identical geometry => identical record indices on every rank) and called scuffcuda_fippi_commit.
+static std::map<scuffcuda_context *, std::pair<int, int> > g_fippiPartition;
 static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, bool useDisp, const double *L, int &status)
 { status = 0;
   Surface &Sa = ctx->surfaces[nsa], &Sb = ctx->surfaces[nsb];
@@ -300,7 +304,14 @@ static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, 
      cudaMemcpyAsync(P.dnear, P.hnear.data(), count * sizeof(NearPair), cudaMemcpyHostToDevice, ctx->stream);
      cudaStreamSynchronize(ctx->stream);          // consumers run on the near stream as well as on this one
      if (!newIds.empty())
-      { if (fippi_compute_records(ctx, newIds, newVerts, newNcv)) { cudaFree(dlist); status = 1; return nullptr; } }
+      { auto part = g_fippiPartition.find(ctx);
+        if (part != g_fippiPartition.end() && part->second.second > 1)
+         { std::vector<int> ids, ncv; std::vector<double> verts;
+           for (size_t q = 0; q < newIds.size(); q++)
+            if (newIds[q] % part->second.second == part->second.first)
+             { ids.push_back(newIds[q]); ncv.push_back(newNcv[q]); verts.insert(verts.end(), newVerts.begin() + 18 * q, newVerts.begin() + 18 * (q + 1)); }
+           newIds.swap(ids); newNcv.swap(ncv); newVerts.swap(verts); }
+        if (fippi_compute_records(ctx, newIds, newVerts, newNcv)) { cudaFree(dlist); status = 1; return nullptr; } }
      if (fippi_sync_device(ctx)) { cudaFree(dlist); status = 1; return nullptr; }
    }
   if (dlist) cudaFree(dlist);
@@ -386,6 +397,31 @@ int scuffcuda_fippi_store(scuffcuda_context *ctx, const char *filename)
 
 int scuffcuda_fippi_num_records(scuffcuda_context *ctx, long *n) { *n = (long)ctx->fippi.keys.size(); return 0; }
 
+int scuffcuda_fippi_set_partition(scuffcuda_context *ctx, int rank, int world)
+{ if (world < 1 || rank < 0 || rank >= world) { ctx->err = "fippi_set_partition: need 0 <= rank < world"; return 1; }
+  if (world == 1) g_fippiPartition.erase(ctx); else g_fippiPartition[ctx] = std::make_pair(rank, world);
+  return 0;
+}
+int scuffcuda_prepare_block(scuffcuda_context *ctx, int nsa, int nsb, int symmetric, int use_displacement, const double *displacement)
+{ const int NS = (int)ctx->surfaces.size();
+  if (nsa < 0 || nsa >= NS || nsb < 0 || nsb >= NS || !ctx->surfaces[nsa].dpanels || !ctx->surfaces[nsb].dpanels)
+   { ctx->err = "prepare_block: invalid surface index or surface not set"; return 1; }
+  if (symmetric && nsa != nsb) { ctx->err = "prepare_block: symmetric requires nsa==nsb"; return 1; }
+  cudaSetDevice(ctx->device);
+  int status = 0; const double zero[3] = { 0, 0, 0 };
+  Plan *P = get_plan(ctx, nsa, nsb, symmetric != 0, use_displacement != 0, (use_displacement && displacement) ? displacement : zero, status);
+  return P ? 0 : (status ? status : 1);
+}
+int scuffcuda_fippi_host_records(scuffcuda_context *ctx, double **records, long *count)
+{ if (!records || !count) { ctx->err = "fippi_host_records: null argument"; return 1; }
+  *records = ctx->fippi.hrec.data(); *count = (long)ctx->fippi.keys.size();
+  return 0;
+}
+int scuffcuda_fippi_commit(scuffcuda_context *ctx)
+{ cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
+  ctx->fippi.dcount = 0;                       // every record travels to the device again
+  return fippi_sync_device(ctx);
+}
 int scuffcuda_fippi_clear(scuffcuda_context *ctx)
 { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream);
   for (auto &p : ctx->plans) if (p.dnear) cudaFree(p.dnear);

@@ -393,6 +393,18 @@ void RWGGeometry::AssembleBEMMatrixDevice(cdouble Omega, double *kBloch, HMatrix
 
 HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, HMatrix *M) { return AssembleBEMMatrix(Omega, 0, M); }
 
+// pair plans (and FIPPI records) of every block AssembleBEMMatrix will visit, without assembling: the loop of
+// AssembleBEMMatrixDevice over surface pairs with its Mate shortcut
+void RWGGeometry::PrepareNearPlans()
+{ scuffcuda_context *ctx = GetCudaContext();
+  if (LBasis != 0) return;                   // displaced blocks of periodic geometries are planned when first assembled
+  SyncDeviceGeometry();
+  for (int ns = 0; ns < NumSurfaces; ns++)
+   for (int nsp = ns; nsp < NumSurfaces; nsp++)
+    { if (ns == nsp && Mate[ns] != -1) continue;
+      if (scuffcuda_prepare_block(ctx, ns, nsp, ns == nsp, 0, 0)) ErrExit("%s", scuffcuda_last_error(ctx)); }
+}
+
 // Step 1 of the periodic branch of AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:465-519): the kBloch-independent blocks
 // of the innermost lattice cells, each from the displaced-surface assembly on the device and stamped into M with its Bloch
 // phase factor (StampInNeighborBlock, :72-114).  Leaves the block of M in HBM (M->HostStale).

@@ -107,6 +107,7 @@ int scuffb200_assemble_block_grad(void *g, void *m, int nsa, int nsb, double wr,
   double Gamma[27];
   for (int n = 0; n < ntorque && n < 3; n++) { double ax[3]; ax[0] = axes[3 * n]; ax[1] = axes[3 * n + 1]; ax[2] = axes[3 * n + 2]; CreateGammaMatrix(ax, Gamma + 9 * n); }
   GUARD(G->AssembleBEMMatrixBlock(nsa, nsb, cdouble(wr, wi), 0, M, (HMatrix **)grad, 0, 0, 0, false, ntorque, (HMatrix **)dmdt, Gamma); return 0;, 1) }
+int scuffb200_prepare_plans(void *g) { GUARD(((RWGGeometry *)g)->PrepareNearPlans(); return 0;, 1) }
 void *scuffb200_create_abmb(void *g, int nsa, int nsb, int pure_imag) { GUARD(return ((RWGGeometry *)g)->CreateABMBAccelerator(nsa, nsb, pure_imag != 0, false);, 0) }
 void scuffb200_destroy_abmb(void *g, void *acc) { ((RWGGeometry *)g)->DestroyABMBAccelerator(acc); }
 int scuffb200_assemble_block_acc(void *g, void *m, int nsa, int nsb, double wr, double wi, const double *kBloch, int row_off, int col_off, void *acc)

@@ -387,6 +387,10 @@ class RWGGeometry:
         _check(rc)
         return complex(out[0], out[1])
 
+    def PrepareNearPlans(self):
+        """pair plans + FIPPI records of every block AssembleBEMMatrix visits, without assembling"""
+        _check(host_lib().scuffb200_prepare_plans(self.ptr))
+
     def ppi_counts(self):
         out = (C.c_ulonglong * 5)()
         host_lib().scuffb200_ppi_counts(self.ptr, out)
@@ -399,6 +403,27 @@ class RWGGeometry:
 
     def __del__(self):
         self.close()
+
+
+def fippi_set_partition(rank, world):
+    """this context computes only the FIPPI records with index = rank (mod world) until reset with (0, 1)"""
+    _cuda_check(cuda_lib().scuffcuda_fippi_set_partition(context(), int(rank), int(world)))
+
+
+def fippi_host_records():
+    """zero-copy numpy view [count, 36] of the context's FIPPI table on the host (valid until the table grows)"""
+    L = cuda_lib()
+    L.scuffcuda_fippi_host_records.argtypes = [C.c_void_p, C.POINTER(C.POINTER(C.c_double)), C.POINTER(C.c_long)]
+    p = C.POINTER(C.c_double)(); n = C.c_long()
+    _cuda_check(L.scuffcuda_fippi_host_records(context(), C.byref(p), C.byref(n)))
+    if n.value == 0:
+        return np.zeros((0, 36))
+    return np.ctypeslib.as_array(p, shape=(n.value, 36))
+
+
+def fippi_commit():
+    """send the (completed) host table to the device"""
+    _cuda_check(cuda_lib().scuffcuda_fippi_commit(context()))
 
 
 def PreloadCache(fn):

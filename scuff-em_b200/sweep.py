@@ -41,6 +41,44 @@ def run_sweep(points, evaluate, rank=0, world=1):
     return gather_results(local, len(points), rank, world)
 
 
+# ---- the frequency-independent FIPPI table, built once by all ranks together (third row) ------------
+def allreduce_records(rec, world, device=None):
+    """rec: this rank's [count, 36] float64 table with zeros where other ranks computed; summed over the ranks IN PLACE
+    (the table is the union: every record is computed by exactly one rank).  NCCL needs the data on the device."""
+    if world == 1 or rec.size == 0:
+        return rec
+    import numpy as np
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(rec))
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    rec[...] = t.cpu().numpy()
+    return rec
+
+
+def share_fippi_table(ps, G, rank, world, device=None):
+    """Cold start of a sweep: instead of every rank building the whole FIPPI table of G (seconds), rank r builds the records
+    with index = r (mod world) and the tables are summed with one all-reduce (36 doubles per record: 90 MB at N = 20 280).
+    Every rank classifies the pairs itself (milliseconds), so the record indices agree without any exchange."""
+    if world == 1:
+        G.PrepareNearPlans()
+        return ps.cache_records()
+    ps.fippi_set_partition(rank, world)
+    try:
+        G.PrepareNearPlans()
+    finally:
+        ps.fippi_set_partition(0, 1)
+    rec = ps.fippi_host_records()
+    counts = [None] * world
+    dist.all_gather_object(counts, int(rec.shape[0]))
+    if len(set(counts)) != 1:
+        raise RuntimeError("FIPPI tables of the ranks differ in size (%s): the ranks do not hold the same geometry" % counts)
+    allreduce_records(rec, world, device)
+    ps.fippi_commit()
+    return rec.shape[0]
+
+
 # ---- one very large matrix across GPUs (SURVEY.md §8e, second row) ----------------------------------------------
 def column_ranges(n, world):
     """Column blocks [c_r, c_{r+1}) of an n x n SYMMETRIC matrix with equal upper-triangle area (work ~ c_{r+1}^2 - c_r^2):

@@ -112,3 +112,58 @@ def test_column_ranges_balance_upper_triangle():
     rs = sweep.column_ranges(20280, 8)
     areas = [c1 * c1 - c0 * c0 for c0, c1 in rs]
     assert max(areas) / min(areas) < 1.01
+
+
+class _FakePS:
+    """stands in for pyscuff in the CPU test of share_fippi_table: a 'table' of nrec records of which this rank fills its share"""
+    def __init__(self, nrec):
+        import numpy as np
+        self.np = np; self.nrec = nrec; self.part = (0, 1); self.rec = None; self.committed = None
+    def fippi_set_partition(self, rank, world): self.part = (rank, world)
+    def fippi_host_records(self): return self.rec
+    def fippi_commit(self): self.committed = self.rec.copy()
+    def cache_records(self): return self.nrec
+
+
+class _FakeG:
+    def __init__(self, ps): self.ps = ps
+    def PrepareNearPlans(self):
+        np = self.ps.np; r, w = self.ps.part
+        full = np.arange(self.ps.nrec * 36, dtype=np.float64).reshape(self.ps.nrec, 36) + 1.0
+        self.ps.rec = np.where((np.arange(self.ps.nrec) % w == r)[:, None], full, 0.0)
+
+
+def _fippi_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sweep = _load()
+    ps = _FakePS(1001)
+    n = sweep.share_fippi_table(ps, _FakeG(ps), rank, world)
+    mismatch = None
+    try:
+        bad = _FakePS(1001 + rank)                       # ranks that do not hold the same geometry are detected
+        sweep.share_fippi_table(bad, _FakeG(bad), rank, world)
+    except RuntimeError as e:
+        mismatch = str(e)
+    q.put((rank, n, ps.part, float(ps.committed.sum()), bool((ps.committed > 0).all()), mismatch))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fippi_table_built_once_by_all_ranks_world2():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fippi_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = float(sum(range(1, 1001 * 36 + 1)))
+    for rank, n, part, total, complete, mismatch in got:
+        assert n == 1001 and part == (0, 1)              # partition reset after the build
+        assert total == want and complete                # every rank ends with the union of the shares
+        assert mismatch and "differ in size" in mismatch
