@@ -343,8 +343,14 @@ HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *
    { Warn("wrong-size matrix passed to AssembleBEMMatrix; reallocating...");
      M = AllocateBEMMatrix(); }
   int K = PipelineBlocks(TotalBFs);
+  // "upper" halves the PCIe bytes but spends host memory bandwidth on the mirror (a read and a write per byte against one write
+  // for a DMA copy): right for one process per host, wrong when several ranks share the host's memory system (measured on a
+  // 2-GPU box: 460 ms per step and rank against 213 ms with DMA only) — those default to the all-DMA "columns" scheme
   const char *mode = getenv("SCUFF_CUDA_PIPELINE_MODE");
-  if (LBasis == 0 && K > 1 && M->StorageType == LHM_NORMAL && mode && !strcmp(mode, "columns")) AssembleBEMMatrixPipelined(this, Omega, M, K);
+  if (!mode)
+   { const char *lw = getenv("LOCAL_WORLD_SIZE"), *ww = getenv("WORLD_SIZE");
+     mode = ((lw && atoi(lw) > 1) || (!lw && ww && atoi(ww) > 1)) ? "columns" : "upper"; }
+  if (LBasis == 0 && K > 1 && M->StorageType == LHM_NORMAL && !strcmp(mode, "columns")) AssembleBEMMatrixPipelined(this, Omega, M, K);
   else if (LBasis == 0 && K > 1 && M->StorageType == LHM_NORMAL) AssembleBEMMatrixUpperCopyBack(this, Omega, M, 2 * K);
   else
    { AssembleBEMMatrixDevice(Omega, kBloch, M);
