@@ -44,10 +44,11 @@ void SetLogFileName(const char *name);
 typedef void (*ErrExitHandler)(const char *msg);
 void SetErrExitHandler(ErrExitHandler h);
 
-/* the device context used by all geometries of this process (created lazily on device
- * SCUFF_CUDA_DEVICE, default 0, or LOCAL_RANK when launched by torchrun)                   */
+/* the device context of the calling HOST THREAD (created lazily on device SCUFF_CUDA_DEVICE, default 0, or LOCAL_RANK when
+ * launched by torchrun; SetCudaDevice picks another one).  One context per thread: see SweepDriver below.                  */
 scuffcuda_context *GetCudaContext();
 void SetCudaDevice(int device);
+void ReleaseCudaContext();      /* destroys the calling thread's context (worker threads call it before they end) */
 
 /*--------------------------------------------------------------------------------------*/
 class HMatrix
@@ -258,6 +259,34 @@ class RWGGeometry
 
 void PreloadCache(const char *FileName);
 void StoreCache(const char *FileName);
+
+
+/*--------------------------------------------------------------------------------------*/
+/* Sweep sharding from C++: the frequency / imaginary-frequency / Bloch-vector points of a sweep are    */
+/* independent, so point j goes to device j mod NumDevices — one host thread and one device context per GPU inside ONE */
+/* process, each with its own copy of the geometry and its own matrix; the FIPPI table is built once, the devices      */
+/* computing disjoint shares of the records (as sweep.share_fippi_table does across processes).  This is what the      */
+/* frequency loops of the reference applications (scuff-scatter.cc:373-472, scuff-cas3D SumsIntegrals.cc) map onto.    */
+/*--------------------------------------------------------------------------------------*/
+class SweepDriver
+ {
+  public:
+   /* Devices == 0: devices 0 .. NumDevices-1; NumDevices == 0: every visible device.  The same device may be listed more than once */
+   SweepDriver(const char *GeoFileName, int NumDevices = 0, const int *Devices = 0);
+   ~SweepDriver();
+
+   /* called on the worker thread that owns G and M, after AssembleBEMMatrix(Omega, kBloch) has filled M in HBM (M->HostStale) */
+   typedef void (*PointFunction)(RWGGeometry *G, HMatrix *M, cdouble Omega, double *kBloch, int PointIndex, int Worker, void *UserData);
+
+   /* kBlochs: 2 doubles per point, or 0 for compact geometries */
+   void Run(int NumPoints, const cdouble *Omegas, const double *kBlochs, PointFunction F, void *UserData, bool ShareFIPPITable = true);
+
+   int NumWorkers;
+   std::vector<int> DeviceOf;            /* device of worker w */
+   std::vector<RWGGeometry *> Geometries;
+   std::vector<HMatrix *> Matrices;      /* created by the workers on first use */
+   std::vector<double> ColdSeconds;      /* per worker: plans + its share of the FIPPI table */
+ };
 
 }  /* namespace scuff */
 

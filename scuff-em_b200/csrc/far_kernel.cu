@@ -936,10 +936,13 @@ static void launch_ho_mode(scuffcuda_context *ctx, const NearArgs &A, const int 
 int run_ho(scuffcuda_context *ctx, const NearArgs &A, const int *hoIdx, int n, int kmode)
 { if (n <= 0) return 0;
   static double *dtcr[64] = { nullptr };
+  static std::mutex dtcrLock;
+  std::unique_lock<std::mutex> tlock(dtcrLock);
   double *&T = dtcr[ctx->device & 63];
   if (!T)
    { if (cudaMalloc(&T, sizeof SC_TCR20_H) != cudaSuccess) { ctx->err = "high-order cubature table allocation failed"; return 1; }
      cudaMemcpy(T, SC_TCR20_H, sizeof SC_TCR20_H, cudaMemcpyHostToDevice); cudaDeviceSynchronize(); }
+  tlock.unlock();
   if ((size_t)n > ctx->hoIdxCap)
    { if (ctx->dHoIdx) { cudaDeviceSynchronize(); cudaFree(ctx->dHoIdx); ctx->dHoIdx = nullptr; ctx->hoIdxCap = 0; }
      const size_t cap = std::max<size_t>(2 * (size_t)n, 4096);

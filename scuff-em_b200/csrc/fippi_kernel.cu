@@ -12,6 +12,7 @@
 #include <string>
 #include "kernels.h"
 #include "fippi_build.cuh"
+#include <mutex>
 #include "generated_tables.h"
 
 namespace scuffcuda {
@@ -23,9 +24,11 @@ static_assert(sizeof(SCPXEntry) == sizeof(PXEntry) && sizeof(SCPCEntry) == sizeo
 
 struct FIPPIDeviceTables { PXEntry *cePX = nullptr, *cvPX = nullptr; PCEntry *cePC = nullptr, *cvPC = nullptr; };
 static FIPPIDeviceTables g_ft[64];
+static std::mutex g_ftLock;          // several contexts (one host thread each) may reach the first use together
 
 static int fippi_tables(scuffcuda_context *ctx, FIPPITables &T)
-{ FIPPIDeviceTables &G = g_ft[ctx->device & 63];
+{ std::lock_guard<std::mutex> lock(g_ftLock);
+  FIPPIDeviceTables &G = g_ft[ctx->device & 63];
   if (!G.cePX)
    { if (cudaMalloc(&G.cePX, sizeof SC_CE_PX_H) != cudaSuccess || cudaMalloc(&G.cePC, sizeof SC_CE_PC_H) != cudaSuccess
          || cudaMalloc(&G.cvPX, sizeof SC_CV_PX_H) != cudaSuccess || cudaMalloc(&G.cvPC, sizeof SC_CV_PC_H) != cudaSuccess)

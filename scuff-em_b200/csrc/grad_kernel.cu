@@ -19,6 +19,7 @@
 // (from the pair plan of near.cu): one warp per combination, lanes split the 78 outer points.
 #include <vector>
 #include <complex>
+#include <mutex>
 #include "kernels.h"
 #include "classify.cuh"
 #include "stamp.cuh"
@@ -151,6 +152,8 @@ int run_gradients(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_
   Plan *P = near_plan(ctx, nsa, nsb, false, a->use_displacement != 0, L, status);
   if (!P) return status ? status : 1;
   static double *dtcr[64] = { nullptr };
+  static std::mutex dtcrLock;
+  std::lock_guard<std::mutex> tlock(dtcrLock);
   double *&T = dtcr[ctx->device & 63];
   if (!T)
    { if (cudaMalloc(&T, sizeof SC_TCR20_H) != cudaSuccess) { ctx->err = "derivative blocks: cubature table allocation failed"; return 1; }

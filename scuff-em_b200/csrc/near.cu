@@ -4,6 +4,8 @@
 // in td_kernel.cu, FIPPI records are built on the device in fippi_kernel.cu.
 #include <algorithm>
 #include <numeric>
+#include <map>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include "kernels.h"
@@ -198,6 +200,7 @@ static int fippi_sync_device(scuffcuda_context *ctx)
 // only the records whose index is congruent to rank mod world; the others stay zero until the caller has summed the
 // tables of all ranks (identical geometry => identical record indices on every rank) and called scuffcuda_fippi_commit.
 static std::map<scuffcuda_context *, std::pair<int, int> > g_fippiPartition;
+static std::mutex g_fippiPartitionLock;
 static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, bool useDisp, const double *L, int &status)
 { status = 0;
   Surface &Sa = ctx->surfaces[nsa], &Sb = ctx->surfaces[nsb];
@@ -304,11 +307,12 @@ static Plan *get_plan(scuffcuda_context *ctx, int nsa, int nsb, bool symmetric, 
      cudaMemcpyAsync(P.dnear, P.hnear.data(), count * sizeof(NearPair), cudaMemcpyHostToDevice, ctx->stream);
      cudaStreamSynchronize(ctx->stream);          // consumers run on the near stream as well as on this one
      if (!newIds.empty())
-      { auto part = g_fippiPartition.find(ctx);
-        if (part != g_fippiPartition.end() && part->second.second > 1)
+      { std::pair<int, int> part(0, 1);
+        { std::lock_guard<std::mutex> lock(g_fippiPartitionLock); auto it = g_fippiPartition.find(ctx); if (it != g_fippiPartition.end()) part = it->second; }
+        if (part.second > 1)
          { std::vector<int> ids, ncv; std::vector<double> verts;
            for (size_t q = 0; q < newIds.size(); q++)
-            if (newIds[q] % part->second.second == part->second.first)
+            if (newIds[q] % part.second == part.first)
              { ids.push_back(newIds[q]); ncv.push_back(newNcv[q]); verts.insert(verts.end(), newVerts.begin() + 18 * q, newVerts.begin() + 18 * (q + 1)); }
            newIds.swap(ids); newNcv.swap(ncv); newVerts.swap(verts); }
         if (fippi_compute_records(ctx, newIds, newVerts, newNcv)) { cudaFree(dlist); status = 1; return nullptr; } }
@@ -399,6 +403,7 @@ int scuffcuda_fippi_num_records(scuffcuda_context *ctx, long *n) { *n = (long)ct
 
 int scuffcuda_fippi_set_partition(scuffcuda_context *ctx, int rank, int world)
 { if (world < 1 || rank < 0 || rank >= world) { ctx->err = "fippi_set_partition: need 0 <= rank < world"; return 1; }
+  std::lock_guard<std::mutex> lock(g_fippiPartitionLock);
   if (world == 1) g_fippiPartition.erase(ctx); else g_fippiPartition[ctx] = std::make_pair(rank, world);
   return 0;
 }

@@ -4,6 +4,8 @@
 // reference's tolerances (RelTol 1e-10, MaxEval 1000), its function-value cache living in a strided
 // HBM scratch block.
 #include <vector>
+#include <map>
+#include <mutex>
 #include <cstdlib>
 #include "kernels.h"
 #include "stamp.cuh"
@@ -17,9 +19,11 @@ static_assert(sizeof(SCUpsEntry) == sizeof(UpsEntry), "generated table layout");
 
 struct TDDeviceTables { double *ccx = nullptr, *ccw = nullptr; UpsEntry *ups = nullptr; int device = -1; };
 static TDDeviceTables g_tables[64];
+static std::mutex g_tablesLock;      // several contexts (one host thread each) may reach the first use together
 
 static int td_tables(scuffcuda_context *ctx, TDTables &T)
-{ TDDeviceTables &G = g_tables[ctx->device & 63];
+{ std::lock_guard<std::mutex> lock(g_tablesLock);
+  TDDeviceTables &G = g_tables[ctx->device & 63];
   if (!G.ccx)
    { if (cudaMalloc(&G.ccx, sizeof SC_CC_X_H) != cudaSuccess || cudaMalloc(&G.ccw, sizeof SC_CC_W_H) != cudaSuccess
          || cudaMalloc(&G.ups, sizeof SC_UPS_H) != cudaSuccess) { ctx->err = "Taylor-Duffy table allocation failed"; return 1; }
@@ -226,8 +230,9 @@ int run_td(scuffcuda_context *ctx, const Plan &P, const NearArgs &A, int kmode)
   // frequency point of the sweep are reused (they are O(#near pairs) host work otherwise).
   struct ListCache { bool valid = false; uint64_t genA = 0, genB = 0; int nsa = -1, nsb = -1, forceTD = 0, nNear = 0; bool symmetric = false, useDisp = false;
                      double L[3] = { 0, 0, 0 }; std::vector<int> items, hoIdx, genItems; int colLo = 0, colHi = 0; };
-  static ListCache g_cache[64];
-  ListCache &C = g_cache[ctx->device & 63];
+  static std::map<scuffcuda_context *, ListCache> g_cache;     // per context (a device may carry several contexts)
+  static std::mutex g_cacheLock;
+  g_cacheLock.lock(); ListCache &C = g_cache[ctx]; g_cacheLock.unlock();
   double Rmax = 0.0;
   for (const PanelRec &Q : Sa.hpanels) Rmax = std::max(Rmax, Q.R);
   for (const PanelRec &Q : Sb.hpanels) Rmax = std::max(Rmax, Q.R);

@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include "host_internal.h"
 
 namespace scuff {
@@ -795,8 +796,9 @@ void RWGGeometry::SyncDeviceGeometry()
 { scuffcuda_context *ctx = GetCudaContext();
   // the device context holds ONE geometry at a time; a process-unique id (not the object address,
   // which the allocator may recycle) tells whether it is ours
-  static unsigned long long deviceOwner = 0, nextId = 0;
-  static scuffcuda_context *ownerCtx = 0;
+  static thread_local unsigned long long deviceOwner = 0;
+  static std::atomic<unsigned long long> nextId(0);
+  static thread_local scuffcuda_context *ownerCtx = 0;
   if (ownerCtx != ctx) { ownerCtx = ctx; deviceOwner = 0; }        // a new context (SetCudaDevice) holds no geometry yet
   if (DeviceId == 0) DeviceId = ++nextId;
   if (deviceOwner != DeviceId)

@@ -11,8 +11,11 @@ namespace scuff {
 
 static ErrExitHandler g_handler = 0;
 static std::string g_logFile;
-static scuffcuda_context *g_ctx = 0;
-static int g_device = -1;
+// one device context per HOST THREAD (thread_local): the main thread's context serves ordinary single-GPU use; a SweepDriver
+// worker thread calls SetCudaDevice(d) and gets its own context on device d.  Objects that hold device handles (HMatrix,
+// RWGGeometry after its first assembly) belong to the thread that created their device twin.
+static thread_local scuffcuda_context *g_ctx = 0;
+static thread_local int g_device = -1;
 
 void SetErrExitHandler(ErrExitHandler h) { g_handler = h; }
 void SetLogFileName(const char *name) { g_logFile = name ? name : ""; }
@@ -39,7 +42,7 @@ void Log(const char *fmt, ...)
 }
 
 // number of live objects that hold handles into the context (device matrices, uploaded geometries)
-static int g_liveDeviceObjects = 0;
+static thread_local int g_liveDeviceObjects = 0;
 void AddLiveDeviceObject(int delta) { g_liveDeviceObjects += delta; }
 
 void SetCudaDevice(int device)
@@ -50,6 +53,9 @@ void SetCudaDevice(int device)
      scuffcuda_destroy(g_ctx); g_ctx = 0; }
   g_device = device;
 }
+
+void ReleaseCudaContext()
+{ if (g_ctx) { scuffcuda_destroy(g_ctx); g_ctx = 0; } }
 
 scuffcuda_context *GetCudaContext()
 { if (g_ctx) return g_ctx;
