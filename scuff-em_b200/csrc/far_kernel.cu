@@ -1265,6 +1265,10 @@ far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
   if (sCnt[0]) atomicAdd(A.counters + 5, (unsigned long long)sCnt[0]);
 }
 
+// 32-byte streaming load (sm_100 LDG.E.EF.ENL2.256): both role slots of an edge in one request
+__device__ __forceinline__ void ld256_cs(const void *p, double &a, double &b, double &c, double &d)
+{ asm volatile("ld.global.cs.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p)); }
+
 // edge -> its two panels and the local index of the edge in each: {pP, iP, pM, iM}, -1 where there is none
 struct GatherArgs
 { FarQ L; const int4 *edgeA, *edgeB; int NEa, NEb;
@@ -1296,18 +1300,26 @@ far_gather_kernel(const GatherArgs G)
         const int4 Eb = G.edgeB[eb];
         double sx = 0.0, sy = 0.0;
 #pragma unroll
-        for (int u = 0; u < 2; u++)
+        for (int v = 0; v < 2; v++)
+         { const int pb = v ? Eb.z : Eb.x, jb = v ? Eb.w : Eb.y;
+           if (pb < 0) continue;
+           // the two panels of e_a that lie below pb (any, in a non-symmetric block): their slots 2 e_a, 2 e_a + 1 of row pb are
+           // one aligned 32-byte piece; a slot whose panel does not qualify is loaded but not used (it may never have been written)
+           const bool okP = Ea.x >= 0 && (!SYM || Ea.x < pb), okM = Ea.z >= 0 && (!SYM || Ea.z < pb);
+           if (okP || okM)
+            { int EX; const long row = farq_row(G.L, pb, EX);
+              double a, b, c, d; ld256_cs(G.L.Q + row + (long)jb * EX + 2 * ea, a, b, c, d);
+              if (okP) { sx += a; sy += b; }
+              if (okM) { sx += c; sy += d; } }
+           if (SYM)
+            { // a panel of e_a ABOVE pb: the pair is stored in that panel's row, at the slot of (e_b, role v)
 #pragma unroll
-         for (int v = 0; v < 2; v++)
-          { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = v ? Eb.z : Eb.x, jb = v ? Eb.w : Eb.y;
-            if (pa < 0 || pb < 0) continue;
-            int slot = 2 * ea + u;
-            if (SYM)
-             { if (pa == pb) continue;
-               if (pa > pb) { pb = pa; jb = ia; slot = 2 * eb + v; } }   // the pair is stored once, in the row of its higher panel
-            int EX; const long row = farq_row(G.L, pb, EX);
-            const double2 q = __ldcs(reinterpret_cast<const double2 *>(G.L.Q + row + (long)jb * EX + slot));
-            sx += q.x; sy += q.y; }
+              for (int u = 0; u < 2; u++)
+               { const int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y;
+                 if (pa <= pb) continue;                  // (pa == pb: same panel, never a far pair)
+                 int EX; const long row = farq_row(G.L, pa, EX);
+                 const double2 q = __ldcs(reinterpret_cast<const double2 *>(G.L.Q + row + (long)ia * EX + 2 * eb + v));
+                 sx += q.x; sy += q.y; } } }
         const size_t idx = ((size_t)(G.rowOff + ea) + (size_t)(G.colOff + eb) * (size_t)G.ld) * W;
         if (RED)
          { if (sx != 0.0) atomicAdd(G.M + idx, sx);
@@ -1357,19 +1369,25 @@ far_gather_psi_kernel(const GatherArgs G)
         const int4 Eb = G.edgeB[eb];
         double g0x = 0, g0y = 0, g1x = 0, g1y = 0;
 #pragma unroll
-        for (int u = 0; u < 2; u++)
+        for (int w = 0; w < 2; w++)
+         { const int pb = w ? Eb.z : Eb.x, jb = w ? Eb.w : Eb.y;
+           if (pb < 0) continue;
+           const bool okP = Ea.x >= 0 && (!SYM || Ea.x < pb), okM = Ea.z >= 0 && (!SYM || Ea.z < pb);
+           if (okP || okM)
+            { int EX; const long row = farq_row(G.L, pb, EX);
+              const cd *q = G.L.Q + row + ((long)jb * EX + 2 * ea) * 2;          // {g0, g1} of role P, {g0, g1} of role M: 64 bytes
+              double a, b, c, d;
+              if (okP) { ld256_cs(q, a, b, c, d); g0x += a; g0y += b; g1x += c; g1y += d; }
+              if (okM) { ld256_cs(q + 2, a, b, c, d); g0x += a; g0y += b; g1x += c; g1y += d; } }
+           if (SYM)
+            {
 #pragma unroll
-         for (int w = 0; w < 2; w++)
-          { int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y, pb = w ? Eb.z : Eb.x, jb = w ? Eb.w : Eb.y;
-            if (pa < 0 || pb < 0) continue;
-            int slot = 2 * ea + u;
-            if (SYM)
-             { if (pa == pb) continue;
-               if (pa > pb) { pb = pa; jb = ia; slot = 2 * eb + w; } }
-            int EX; const long row = farq_row(G.L, pb, EX);
-            const double2 *q = reinterpret_cast<const double2 *>(G.L.Q + row + ((long)jb * EX + slot) * 2);
-            const double2 a = __ldcs(q), b = __ldcs(q + 1);
-            g0x += a.x; g0y += a.y; g1x += b.x; g1y += b.y; }
+              for (int u = 0; u < 2; u++)
+               { const int pa = u ? Ea.z : Ea.x, ia = u ? Ea.w : Ea.y;
+                 if (pa <= pb) continue;
+                 int EX; const long row = farq_row(G.L, pa, EX);
+                 double a, b, c, d; ld256_cs(G.L.Q + row + ((long)ia * EX + 2 * eb + w) * 2, a, b, c, d);
+                 g0x += a; g0y += b; g1x += c; g1y += d; } } }
         const cd G0 = mk(g0x, g0y), G1 = mk(g1x, g1y);
         const cd v11 = G.c1 * G0, v12 = G.c2 * G1, v22 = G.c3 * G0;
         // component planes: 0 (X,Y), 1 (X,Y+1), 2 (X+1,Y), 3 (X+1,Y+1)

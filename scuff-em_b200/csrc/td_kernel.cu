@@ -64,6 +64,11 @@ td_ct_kernel(const NearArgs A, const TDTables T, const int *items, int nItems, d
 // contractions), the quadrature sums are reduced with warp shuffles, and every item keeps its own convergence state, so
 // each one stops exactly where the reference's independent pcubature call stops (pcubature.c: RelTol 1e-10 per
 // component, numEval > MaxEval = 1000); only the floating-point summation order of the quadrature sum differs.
+#ifndef TD_CT_MINB
+#define TD_CT_MINB 8      /* register cap asked of ptxas: 65536 / (128 * MINB) = 64: the kernel is latency-bound and shares the SMs with the
+                             HBM-bound gather, so resident warps count for more than spills.  Measured in the step (gather and Taylor-Duffy side by side,
+                             N = 20 280): 168 regs 16.7 ms, 96 regs 16.2 ms, 64 regs 15.95 ms with 2.4 KB of local memory per thread */
+#endif
 #define TD_GROUP_DEFAULT 8
 #define TD_COOP_MAXM 9
 #define TD_COOP_NPTS ((1 << (TD_COOP_MAXM + 1)) + 1)
@@ -103,7 +108,7 @@ __device__ void td_ct_pair_eval(double A2, double AdB, double B2, cd k, int nLo,
 
 // pairs[g] = 512*nearIndex + 9-bit mask of the (i,j) combinations (bit 3i+j) that feed a matrix entry
 template <int TD_GROUP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TD_CT_MINB)
 td_ct_pair_kernel(const NearArgs A, const TDTables T, const int *pairs, int nPairs, double *scratch, int *pairStatus)
 { const int g = (blockIdx.x * blockDim.x + threadIdx.x) / TD_GROUP;
   const int gl = threadIdx.x & (TD_GROUP - 1);
@@ -117,6 +122,7 @@ td_ct_pair_kernel(const NearArgs A, const TDTables T, const int *pairs, int nPai
   double Va[9], Vb[9];
   for (int q = 0; q < 9; q++) { Va[q] = Pa.V[q]; Vb[q] = A.useDisp ? (Pb.V[q] + 1.0 * A.L[q % 3]) : Pb.V[q]; }
   const cd k = mk(A.K.kr, A.K.ki);
+  // (the per-item coefficients were tried in shared memory, 72 KB per CTA: the occupancy loss made the kernel slower)
   double *Uc = scratch + (size_t)g * TD_COOP_PAIR_DBL;                      // [it][64]
   double *cache = Uc + 9 * TD_COOP_UDBL;                                    // [point][nIt][4]
   __shared__ int s_nmm[128 / TD_GROUP][36];                                 // nMin/nMax per item and polynomial
