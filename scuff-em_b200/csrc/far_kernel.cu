@@ -1095,6 +1095,20 @@ far_pass1_kernel(const __grid_constant__ FarArgsQ X)
    { const int pb = b0 + ib;
      if (A.symmetric && pb <= pa) continue;            // the gather reads pairs pa < pb only
      const double *Pb = sm + ib * 36;
+     const int *eb3 = (const int *)(Pb + 34);
+     int nEnt = na * ((eb3[0] >= 0) + (eb3[1] >= 0) + (eb3[2] >= 0));
+     if (A.S.colHi != 0x7fffffff)
+      { // column-block assembly: a pair none of whose (<= 9) entries lies in the owned columns is neither computed nor stored
+        // (the gather of the owned columns never reads it); exact per entry
+        nEnt = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+          { const int e = slot[i] >> 1, f = eb3[j];
+            const int c0 = A.S.colOff + (A.symmetric ? max(e, f) : f);
+            nEnt += (slot[i] >= 0 && f >= 0 && c0 >= A.S.colLo && c0 < A.S.colHi); }
+        if (nEnt == 0) continue; }
      double D[3];
      bool far;
      { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
@@ -1103,9 +1117,8 @@ far_pass1_kernel(const __grid_constant__ FarArgsQ X)
 #pragma unroll
      for (int n = 0; n < 9; n++) val[n] = mk(0.0, 0.0);
      if (far)
-      { const int *eb3 = (const int *)(Pb + 34);
-        sCnt[0] += 1;
-        sCnt[FAR_THREADS] += (unsigned int)(na * ((eb3[0] >= 0) + (eb3[1] >= 0) + (eb3[2] >= 0)));
+      { sCnt[0] += 1;
+        sCnt[FAR_THREADS] += (unsigned int)nEnt;
         double r0 = 0.0;
         if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
         S mPhi[3][3], mPsi[3][3];
@@ -1184,6 +1197,20 @@ far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
    { const int pb = b0 + ib;
      if (A.symmetric && pb <= pa) continue;            // the gather reads pairs pa < pb only
      const double *Pb = sm + ib * 36;
+     const int *eb3 = (const int *)(Pb + 34);
+     int nEnt = na * ((eb3[0] >= 0) + (eb3[1] >= 0) + (eb3[2] >= 0));
+     if (A.S.colHi != 0x7fffffff)
+      { // column-block assembly (see far_pass1_kernel); a dielectric b side owns two columns per edge
+        const int wb = A.S.bPEC ? 1 : 2;
+        nEnt = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+         for (int j = 0; j < 3; j++)
+          { const int sl = sEi[i * FAR_THREADS], e = sl >> 1, f = eb3[j];
+            const int c0 = A.S.colOff + wb * (A.symmetric ? max(e, f) : f);
+            nEnt += (sl >= 0 && f >= 0 && c0 + wb - 1 >= A.S.colLo && c0 < A.S.colHi); }
+        if (nEnt == 0) continue; }
      double D[3];
      bool far;
      { const double Ca[3] = { sSt[12 * FAR_THREADS], sSt[13 * FAR_THREADS], sSt[14 * FAR_THREADS] };
@@ -1199,9 +1226,8 @@ far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
 #pragma unroll
            for (int j = 0; j < 3; j++) { q[((long)j * EX + sl) * 2] = make_double2(0.0, 0.0); q[((long)j * EX + sl) * 2 + 1] = make_double2(0.0, 0.0); } }
         continue; }
-     const int *eb3 = (const int *)(Pb + 34);
      sCnt[0] += 1;
-     sCnt[FAR_THREADS] += (unsigned int)(na * ((eb3[0] >= 0) + (eb3[1] >= 0) + (eb3[2] >= 0)));
+     sCnt[FAR_THREADS] += (unsigned int)nEnt;
      double r0 = 0.0;
      if (SMALL) { const double d2 = fma(D[2], D[2], fma(D[1], D[1], D[0] * D[0])); r0 = d2 * rsqrt_fast<true>(d2); }
      S mPhi[3][3], mPsi[3][3];
@@ -1273,7 +1299,9 @@ __device__ __forceinline__ void ld256_cs(const void *p, double &a, double &b, do
 struct GatherArgs
 { FarQ L; const int4 *edgeA, *edgeB; int NEa, NEb;
   double *M; long ld; int rowOff, colOff;
-  int aPEC, bPEC; cd c1, c2, c3; };
+  int aPEC, bPEC; cd c1, c2, c3;
+  int colLo, colHi;          // owned matrix columns (column-block assembly); 0, INT_MAX = all
+  int bxOff; };              // first column tile of the launch
 
 // Tile = 32 columns (b-edges) x GR*32 rows (a-edges); blockIdx.x walks DOWN the rows of one column tile so that CTAs in flight
 // at the same time read neighbouring pieces of the same Q rows (DRAM pages, shared sectors) and write neighbouring
@@ -1286,7 +1314,7 @@ template <int W, bool SYM, bool RED>
 __global__ void __launch_bounds__(256)
 far_gather_kernel(const GatherArgs G)
 { __shared__ double tile[RED ? 1 : 32][RED ? 1 : 33 * W];
-  const int bx = blockIdx.y;                       // column tile
+  const int bx = blockIdx.y + G.bxOff;             // column tile
   const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
   for (int g = 0; g < FAR_GATHER_GR; g++)
    { const int by = blockIdx.x * FAR_GATHER_GR + g;     // row tile
@@ -1297,6 +1325,7 @@ far_gather_kernel(const GatherArgs G)
      for (int j = ty; j < 32; j += 8)
       { const int eb = bx * 32 + j;
         if (ea >= G.NEa || eb >= G.NEb || (SYM && ea >= eb)) continue;
+        if (G.colOff + eb < G.colLo || G.colOff + eb >= G.colHi) continue;
         const int4 Eb = G.edgeB[eb];
         double sx = 0.0, sy = 0.0;
 #pragma unroll
@@ -1350,7 +1379,7 @@ template <int W, bool SYM, bool RED>
 __global__ void __launch_bounds__(256)
 far_gather_psi_kernel(const GatherArgs G)
 { __shared__ double tile[RED ? 1 : 32][RED ? 1 : 33 * W];
-  const int bx = blockIdx.y;
+  const int bx = blockIdx.y + G.bxOff;
   const int tx = threadIdx.x, ty = threadIdx.y;    // 32 x 8
   const int wa = G.aPEC ? 1 : 2, wb = G.bPEC ? 1 : 2;
   for (int g = 0; g < FAR_GATHER_GR; g++)
@@ -1395,6 +1424,7 @@ far_gather_psi_kernel(const GatherArgs G)
         for (int c = 0; c < 4; c++)
          { const int dr = c >> 1, dc = c & 1;
            if (dr >= wa || dc >= wb) continue;
+           { const int col = G.colOff + wb * eb + dc; if (col < G.colLo || col >= G.colHi) continue; }
            const cd val = (c == 0) ? v11 : (c == 3 ? v22 : v12);
            const size_t idx = ((size_t)(G.rowOff + wa * ea + dr) + (size_t)(G.colOff + wb * eb + dc) * (size_t)G.ld) * W;
            if (RED)
@@ -1576,14 +1606,23 @@ int far_twopass_pending(scuffcuda_context *ctx)
   return it != g_twoPass.end() && it->second.pending;
 }
 int launch_far_gather(scuffcuda_context *ctx)
-{ const bool red = far_gather_red() != 0;
+{ bool red = far_gather_red() != 0;
   FarTwoPassState *T;
   { std::lock_guard<std::mutex> lock(g_farSlotsLock);
     auto it = g_twoPass.find(ctx);
     if (it == g_twoPass.end() || !it->second.pending) return 0;
     T = &it->second; }
   T->pending = false;
-  dim3 grid(((T->NEa + 31) / 32 + FAR_GATHER_GR - 1) / FAR_GATHER_GR, (T->NEb + 31) / 32), block(32, 8);
+  if (T->G.colHi != 0x7fffffff) red = true;         // column blocks are never mirrored: the read-modify-write variant writes mirror images
+  // column tiles that intersect the owned columns (b-edges wb * eb + dc in [colLo - colOff, colHi - colOff))
+  int bx0 = 0, bx1 = (T->NEb + 31) / 32;
+  if (T->G.colHi != 0x7fffffff)
+   { const int wb = (T->G.L.nc == 2 && !T->G.bPEC) ? 2 : 1;
+     const int e0 = std::max(0, (T->G.colLo - T->G.colOff) / wb), e1 = std::min(T->NEb, (T->G.colHi - T->G.colOff + wb - 1) / wb);
+     bx0 = e0 / 32; bx1 = std::max(bx0, (e1 + 31) / 32); }
+  T->G.bxOff = bx0;
+  if (bx1 <= bx0) { T->timed = false; return 0; }
+  dim3 grid(((T->NEa + 31) / 32 + FAR_GATHER_GR - 1) / FAR_GATHER_GR, bx1 - bx0), block(32, 8);
   if (!T->g0) { cudaEventCreate(&T->g0); cudaEventCreate(&T->g1); }
   cudaEventRecord(T->g0, ctx->stream);
   ctx->launches++;
@@ -1648,8 +1687,9 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
   ctx->launches++;
   int twoPassEnv = 1;
   { const char *e = getenv("SCUFF_CUDA_FAR_TWOPASS"); if (e) twoPassEnv = atoi(e); }
-  if (twoPassEnv && A.S.colHi == 0x7fffffff)
-   { // whole block: two-pass path (plain stores to the panel-pair array, gathered after the near kernels)
+  if (twoPassEnv)
+   { // two-pass path (plain stores to the panel-pair array, gathered beside / after the near kernels); with a column range only the
+     // pairs and entries of the owned columns
      std::unique_lock<std::mutex> lock(g_farSlotsLock);
      FarTwoPassState &T = g_twoPass[ctx];
      lock.unlock();
@@ -1677,6 +1717,7 @@ void launch_far(scuffcuda_context *ctx, const FarArgs &Ain, int kmode)
         T.G.L = X.L; T.G.edgeA = ea; T.G.edgeB = eb; T.G.NEa = NEa; T.G.NEb = NEb;
         T.G.M = A.S.M; T.G.ld = A.S.ld; T.G.rowOff = A.S.rowOff; T.G.colOff = A.S.colOff;
         T.G.aPEC = A.S.aPEC; T.G.bPEC = A.S.bPEC; T.G.c1 = A.S.c1; T.G.c2 = A.S.c2; T.G.c3 = A.S.c3;
+        T.G.colLo = A.S.colLo; T.G.colHi = A.S.colHi; T.G.bxOff = 0;
         T.sym = A.symmetric != 0; T.isReal = A.S.isReal; T.NEa = NEa; T.NEb = NEb; T.pending = true;
         return; } }
   { // every other path accumulates into the matrix with atomics: the block must have been cleared
