@@ -165,6 +165,7 @@ static void AddSurfaceZetaContribution(RWGGeometry *G, int ns, cdouble Omega, HM
         if (neA == neB) X = EA->Centroid;
         else if (EA->iPPanel == EB->iPPanel || EA->iPPanel == EB->iMPanel) X = S->Panels[EA->iPPanel]->Centroid;
         else if (EA->iMPanel != -1 && (EA->iMPanel == EB->iPPanel || EA->iMPanel == EB->iMPanel)) X = S->Panels[EA->iMPanel]->Centroid;
+        std::lock_guard<std::recursive_mutex> exprLock(CExprMutex());
         CExprSetVar(Z, "x", X[0]); CExprSetVar(Z, "y", X[1]); CExprSetVar(Z, "z", X[2]);
         const cdouble V = -1.0 * CExprEval(Z, Omega * MatProp::FreqUnit) * Overlap;
         const int r = Offset + neA, c = Offset + neB;

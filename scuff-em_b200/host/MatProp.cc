@@ -4,6 +4,7 @@
 // sections with constants and Eps(w)/Mu(w) expressions).  The reference evaluates expressions with
 // its bundled cmatheval; here a small recursive-descent complex evaluator stands in for it.
 // Tabulated (FILE_...) materials are not supported.
+#include <mutex>
 #include <cctype>
 #include <cstdlib>
 #include <map>
@@ -108,8 +109,15 @@ CExpr *CExprCreate(const char *text, char **ErrMsg)
   return e;
 }
 void CExprSetVar(CExpr *e, const char *name, cdouble value) { e->vars[name] = value; }
+// Parsed expressions are shared between the geometries of a process (a MATERIAL section is kept once in the material data base, as in
+// the reference) and evaluation mutates the expression object (parser position, error state): worker threads of a SweepDriver evaluating
+// Eps(w) for different frequencies at the same time raced here.  One lock for all expression objects; callers that set variables and then
+// evaluate (SURFACE_IMPEDANCE) hold it across the sequence.
+std::recursive_mutex &CExprMutex() { static std::recursive_mutex m; return m; }
+
 cdouble CExprEval(CExpr *e, cdouble w)
-{ cdouble v = e->eval(w);
+{ std::lock_guard<std::recursive_mutex> lock(CExprMutex());
+  cdouble v = e->eval(w);
   if (!e->ok) ErrExit("invalid material expression '%s': %s", e->text.c_str(), e->err.c_str());
   return v;
 }

@@ -1,6 +1,7 @@
 // internal helpers of the host-side mirror (not installed)
 #pragma once
 #include <cmath>
+#include <mutex>
 #include <cstdio>
 #include <cstring>
 #include <strings.h>
@@ -20,6 +21,7 @@ struct CExpr;
 CExpr *CExprCreate(const char *text, char **ErrMsg);
 void CExprSetVar(CExpr *e, const char *name, cdouble value);
 cdouble CExprEval(CExpr *e, cdouble w);
+std::recursive_mutex &CExprMutex();        // held by CExprEval; hold it across CExprSetVar ... CExprEval sequences
 
 inline double VecDistance(const double *a, const double *b)
 { double d = 0.0; for (int n = 0; n < 3; n++) d += (a[n] - b[n]) * (a[n] - b[n]); return sqrt(d); }
