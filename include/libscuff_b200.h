@@ -51,6 +51,7 @@ void SetCudaDevice(int device);
 void ReleaseCudaContext();      /* destroys the calling thread's context (worker threads call it before they end) */
 
 /*--------------------------------------------------------------------------------------*/
+class HVector;
 class HMatrix
  {
   public:
@@ -70,6 +71,7 @@ class HMatrix
    /* downstream consumer, on the device (cuSOLVER getrf/getrs); LBWrappers.cc:150-230 */
    int LUFactorize();
    int LUSolve(HMatrix *X);
+   int LUSolve(HVector *X);        /* the vector's device copy is solved in place (no copy through the host) */
 
    /* device residency: the assembled matrix lives in HBM (DeviceHandle); host DM/ZM is
     * refreshed by SyncToHost() (AssembleBEMMatrix does it before returning)                */
@@ -91,6 +93,25 @@ class HMatrix
    bool ownsM;
    char *ErrMsg;
    bool Pinned;               /* DM/ZM is page-locked memory from scuffcuda_host_alloc        */
+ };
+
+/*--------------------------------------------------------------------------------------*/
+/* HVector (libs/libhmat/libhmat.h:95-160): here an N x 1 HMatrix, so that it has the same device twin and host/device    */
+/* coherence rules; N, DV, ZV as in the reference.  RHS and solution vectors of a scattering run stay in HBM.             */
+class HVector : public HMatrix
+ {
+  public:
+   HVector(int N, int RealComplex = LHM_REAL, void *data = NULL);
+   cdouble GetEntry(int n);
+   double GetEntryD(int n);
+   void SetEntry(int n, cdouble Entry);
+   void SetEntry(int n, double Entry);
+   void AddEntry(int n, cdouble Entry);
+   void AddEntry(int n, double Entry);
+   void Copy(HVector *V);          /* device-to-device when V lives in HBM */
+   int N;
+   double *DV;
+   cdouble *ZV;
  };
 
 /*--------------------------------------------------------------------------------------*/
@@ -143,6 +164,86 @@ typedef struct RWGEdge
 /* EdgeEdgeInteractions.cc:241-270 (libscuff.h: CreateGammaMatrix) */
 void CreateGammaMatrix(double *TorqueAxis, double *GammaMatrix);
 
+/*--------------------------------------------------------------------------------------*/
+/* incident fields (libs/libIncField/libIncField.h:45-160)                                */
+/*--------------------------------------------------------------------------------------*/
+#define LIF_ELECTRIC_DIPOLE 0
+#define LIF_MAGNETIC_DIPOLE 1
+class IncField
+ {
+  public:
+   cdouble Omega, Eps, Mu;
+   IncField *Next;
+   char *RegionLabel;
+   int RegionIndex;
+   IncField();
+   virtual ~IncField();
+   void SetFrequency(cdouble Omega, bool Traverse = true);
+   void SetFrequencyAndEpsMu(cdouble Omega, cdouble Eps, cdouble Mu, bool Traverse = true);
+   void SetRegionLabel(const char *Label = 0);
+   virtual bool GetSourcePoint(double X[3]) const { (void)X; return false; }
+   virtual void GetFields(const double X[3], cdouble EH[6]) = 0;
+   void GetTotalFields(const double X[3], cdouble EH[6]);
+   virtual void GetFieldGradients(const double X[3], cdouble dEH[3][6]);   /* finite differences unless overridden */
+ };
+void DeleteIncFieldChain(IncField *IF);
+/* evaluated ON THE DEVICE by AssembleRHSVector / GetPFT; every other IncField subclass is evaluated by its own GetFields  */
+/* at the device's cubature points and contracted there                                                                   */
+class PlaneWave : public IncField
+ {
+  public:
+   cdouble E0[3];
+   double nHat[3];
+   PlaneWave(const cdouble E0[3], const double nHat[3], const char *Label = 0);
+   void SetE0(cdouble pE0[3]);
+   void SetnHat(double pnHat[3]);
+   void GetFields(const double X[3], cdouble EH[6]);
+   void GetFieldGradients(const double X[3], cdouble dEH[3][6]);
+ };
+class PointSource : public IncField      /* compact geometries only */
+ {
+  public:
+   double X0[3];
+   cdouble P[3];
+   int Type;
+   PointSource(const double X0[3], const cdouble P[3], int Type = LIF_ELECTRIC_DIPOLE, const char *Label = 0);
+   bool GetSourcePoint(double X[3]) const;
+   void GetFields(const double X[3], cdouble EH[6]);
+ };
+
+/* power / force / torque (libs/libscuff/PFTOptions.h)                                    */
+#define PFT_PABS 0
+#define PFT_PSCAT 1
+#define PFT_XFORCE 2
+#define PFT_YFORCE 3
+#define PFT_ZFORCE 4
+#define PFT_XTORQUE 5
+#define PFT_YTORQUE 6
+#define PFT_ZTORQUE 7
+#define NUMPFT 8
+#define SCUFF_PFT_OVERLAP 0
+#define SCUFF_PFT_DSI 1
+#define SCUFF_PFT_EMT 5
+#define SCUFF_PFT_EMT_EXTERIOR 5
+#define SCUFF_PFT_EMT_INTERIOR 6
+#define SCUFF_PFT_MOMENTS 7
+#define SCUFF_PFT_DEFAULT SCUFF_PFT_EMT_EXTERIOR
+#define SCUFF_EMTPFTI_EHDERIVATIVES1 0
+#define SCUFF_EMTPFTI_EHDERIVATIVES2 1
+#define SCUFF_EMTPFTI_DEFAULT SCUFF_EMTPFTI_EHDERIVATIVES2
+typedef struct PFTOptions
+ { int PFTMethod;
+   IncField *IF;
+   HMatrix *DRMatrix;
+   double *kBloch;
+   HVector *RHSVector;
+   bool Interior;
+   int EMTPFTIMethod;
+   bool Itemize;
+   bool GetRegionPFTs;
+ } PFTOptions;
+PFTOptions *InitPFTOptions(PFTOptions *Options = 0);
+
 class RWGGeometry;
 
 class RWGSurface
@@ -173,6 +274,7 @@ class RWGSurface
    char *Label;
    char *ErrMsg;
    double RMax[3], RMin[3];
+   double Origin[3];            /* torque centre, moves with the surface (RWGSurface.cc:423-429, :609, :657) */
    double tolVecClose;
    int TotalStraddlers;
    /* PBCSetup.cc:142-302: promote exterior edges that have a lattice-translated partner to full RWG edges */
@@ -205,6 +307,15 @@ class RWGGeometry
                                int NumTorqueAxes = 0, HMatrix **dMdT = 0, double *GammaMatrix = 0);
    void *CreateABMBAccelerator(int nsa, int nsb, bool PureImagFreq = false, bool NeedZDerivative = false);
    void DestroyABMBAccelerator(void *Accelerator);
+
+   /* scattering run on the device: libscuff.h:367-372, :409-418 */
+   HVector *AllocateRHSVector(bool PureImagFreq = false);
+   HVector *AssembleRHSVector(cdouble Omega, double *kBloch, IncField *IF, HVector *RHS = NULL);
+   HVector *AssembleRHSVector(cdouble Omega, IncField *IF, HVector *RHS = NULL);
+   int UpdateIncFields(IncField *IF, cdouble Omega, double *kBloch = 0);
+   void GetPFT(int SurfaceIndex, HVector *KN, cdouble Omega, double PFT[NUMPFT], PFTOptions *Options = 0);
+   HMatrix *GetPFTMatrix(HVector *KN, cdouble Omega, PFTOptions *Options = 0, HMatrix *PFTMatrix = 0);
+   int GetRegionIndex(const double X[3]);
 
    void UpdateCachedEpsMuValues(cdouble Omega);
    int GetRegionByLabel(const char *Label);
@@ -256,6 +367,12 @@ class RWGGeometry
    bool PointInRegion(int nr, const double X[3]);
    unsigned long long LastPPICounts[5];
  };
+
+/* EMTPFT.cc:533-905 on the device.  Only the cubature integrals SCUFF_EMTPFTI_EHDERIVATIVES1 (Options->EMTPFTIMethod = 0 or
+ * SCUFF_EMTPFTI_METHOD=0 in the environment) are available; the reference's default (EHDERIVATIVES2, which goes through
+ * GetGCMatrixElements and the FIBBI cache of the 2018 assembler) is refused with a message.                              */
+HMatrix *GetEMTPFTMatrix(RWGGeometry *G, cdouble Omega, IncField *IF, HVector *KNVector, HMatrix *DRMatrix = 0,
+                         HMatrix *PFTMatrix = 0, bool Interior = false, int EMTPFTIMethod = SCUFF_EMTPFTI_DEFAULT, bool Itemize = false);
 
 void PreloadCache(const char *FileName);
 void StoreCache(const char *FileName);

@@ -170,6 +170,57 @@ int scuffcuda_gbar_eval(scuffcuda_context *ctx, int handle, int npts, const doub
 int scuffcuda_gbar_ewald(scuffcuda_context *ctx, const double k[2], const double kbloch[2], const double lbv[4], int ldim,
                          int exclude_inner_cells, int npts, const double *R, double *out16);
 
+/* ---- right-hand side, solve and power / force / torque on the device ---------------------------
+ * One frequency point of a scattering run (applications/scuff-scatter/scuff-scatter.cc:402-520) without the matrix or the
+ * vectors leaving HBM.  Device vectors are N x 1 device matrices (scuffcuda_matrix_create(ctx, N, 1, is_real, &h)).     */
+/* PlaneWave (libs/libIncField/libIncField.h:106-125) as UpdateIncFields prepared it (AssembleRHSVector.cc:62-118)      */
+typedef struct scuffcuda_planewave {
+  double e0[6];             /* PlaneWave::E0, (re,im) x 3                                                             */
+  double nhat[3];           /* PlaneWave::nHat                                                                        */
+  double eps[2], mu[2];     /* IncField::Eps, Mu of the region that holds the sources                                 */
+  double sign;              /* +1: sources in the surface's interior region (PositiveIFs), -1: exterior (NegativeIFs),
+                             * AssembleRHSVector.cc:297-306; ignored by scuffcuda_emtpft                              */
+} scuffcuda_planewave;
+/* cubature points of the RHS inner products of surface ns: for edge ne, panel pm (0 positive, 1 negative), point np of the
+ * 78-point rule: X[3*((ne*2+pm)*78+np)...] (host buffer; X may be NULL to query *npts = 2*78*NumEdges).  Incident fields the
+ * device does not know (any IncField subclass) are evaluated there by the caller and passed as `tabulated_eh`.            */
+int scuffcuda_rhs_points(scuffcuda_context *ctx, int ns, double *X, long *npts);
+/* AssembleRHSVector for one surface (AssembleRHSVector.cc:282-345, GetInnerProducts :172-229): writes the entries
+ * [offset, offset+NumBFs) of the device vector.  Fields = sum of the plane waves (each with its sign) + tabulated_eh
+ * (12 doubles per point of scuffcuda_rhs_points: E then H as (re,im), signs already applied; or NULL).  A real vector takes
+ * the real parts (AllocateRHSVector(PureImagFreq), :438-447).                                                            */
+int scuffcuda_assemble_rhs(scuffcuda_context *ctx, int ns, const double omega[2], int num_pw, const scuffcuda_planewave *pw,
+                           const double *tabulated_eh, int vec_handle, int offset);
+/* HMatrix::LUSolve(HVector *) (libs/libhmat/LBWrappers.cc:196-230) with the vector resident on the device                */
+int scuffcuda_lu_solve_device(scuffcuda_context *ctx, int handle, int vec_handle);
+/* device vector / matrix element-wise copy dst <- src (HVector::Copy): same shape and type                                */
+int scuffcuda_matrix_copy(scuffcuda_context *ctx, int handle_dst, int handle_src);
+
+/* GetEMTPFTMatrix (libs/libscuff/EMTPFT.cc:533-905) with the cubature integrals SCUFF_EMTPFTI_EHDERIVATIVES1 (:82-176,
+ * :308-334): the energy/momentum-transfer sums over all pairs of basis functions and the extinction sums over all basis
+ * functions (GetExtinctionPFTT :466-531), on the device.                                                                 */
+typedef struct scuffcuda_pft_args {
+  double omega[2];              /* real, positive frequency                                                           */
+  int    interior;              /* PFTOptions::Interior                                                               */
+  int    num_surfaces;
+  const int    *region_indices; /* RWGSurface::RegionIndices, 2 per surface                                           */
+  const int    *bf_offsets;     /* RWGGeometry::BFIndexOffset                                                         */
+  const double *origins;        /* RWGSurface::Origin (torque centres), 3 per surface                                 */
+  int    num_regions;
+  const double *eps_mu;         /* per region: eps (re,im), mu (re,im), relative (RegionMPs[nr]->GetEpsMu(Omega))      */
+  int    if_region;             /* IncField::RegionIndex of the head of the incident-field chain; -1: no incident field */
+  int    num_pw;                /* 1: the incident field is the plane wave *pw; 0: it is tabulated                     */
+  const scuffcuda_planewave *pw;
+  const double *tabulated_ehd;  /* or NULL; 48 doubles per point of scuffcuda_pft_points, surfaces one after the other:
+                                 * EH[6] then dEH[3][6] (IncField::GetFields / GetFieldGradients) as (re,im)           */
+} scuffcuda_pft_args;
+/* the 21-point rule of every panel of surface ns in the panel's vertex order (PanelCubature.cc:155-236): X[3*(np*21+p)...] */
+int scuffcuda_pft_points(scuffcuda_context *ctx, int ns, double *X, long *npts);
+/* scattered[(nsa*NS + nsb)*11 + nq] = contribution of surface b to quantity nq on surface a (DeltaPFTT, EMTPFT.cc:604-625;
+ * nq: 0 PAbs (unused), 1 PScat, 2-4 force, 5-7 first torque term, 8-10 second torque term); extinction[ns*11 + nq] as
+ * GetExtinctionPFTT returns it.  Host buffers.                                                                           */
+int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_args *args, double *scattered, double *extinction);
+
 /* PPI algorithm counters of the last assemble_block call, same order as the reference's
  * log line (SurfaceSurfaceInteractions.cc:550-558; libscuffInternals.h PPIALG_*):
  * [0] low-order cubature, [1] high-order cubature, [2] Taylor-Duffy, [3] high-k TD,

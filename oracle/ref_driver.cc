@@ -12,6 +12,12 @@
  *        AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:349-391) with GradM[3] and dMdT[NumTorqueAxes] (CreateGammaMatrix,
  *        EdgeEdgeInteractions.cc:241-270): writes the value block, the three gradient blocks and the torque blocks one after
  *        the other (complex, or real with --imag as scuff-cas3D allocates them)
+ *   ref_driver scatter <geo> <wRe> <wIm> <out.bin> --pw E0xr E0xi E0yr E0yi E0zr E0zi nx ny nz [--ps x y z Pxr Pxi Pyr Pyi Pzr Pzi]
+ *                      [--interior] [--method m] [--transfile f --trans n] [--nopft]
+ *        one frequency point of scuff-scatter (scuff-scatter.cc:402-520): AssembleBEMMatrix, AssembleRHSVector with the given
+ *        incident-field chain (plane wave first, then an optional point source), LUFactorize, LUSolve, GetPFTMatrix by the
+ *        energy/momentum-transfer method with integral method m (default 0 = SCUFF_EMTPFTI_EHDERIVATIVES1).  Writes RHS
+ *        (TotalBFs complex), the solution KN (TotalBFs complex) and the PFT matrix (NumSurfaces x 8 doubles, row-major).
  *   ref_driver ssi    <geo> <wRe> <wIm> <nsa> <nsb> <Lx> <Ly> <Lz> <out.bin> [--cache-out f]
  *        GetSurfaceSurfaceInteractions (SurfaceSurfaceInteractions.cc:426-585) for one surface pair with surface b displaced
  *        by L (the neighbour-cell blocks of the periodic assembly, AssembleBEMMatrix.cc:72-114), not Symmetric
@@ -188,6 +194,51 @@ int main(int argc, char **argv)
      size_t N=(size_t)NBFA*NBFB;
      HMatrix *All[7]={M,GradM[0],GradM[1],GradM[2],dMdT[0],dMdT[1],dMdT[2]};
      for(int q=0;q<4+NTA;q++) { if(Imag) fwrite(All[q]->DM,sizeof(double),N,f); else fwrite(All[q]->ZM,sizeof(cdouble),N,f); }
+     fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"scatter"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); const char *Out=argv[5];
+     IncField *IFList=0, *Tail=0; bool Interior=false, NoPFT=false; int Method=0; const char *TransFile=0; int nTrans=0;
+     for(int n=6;n<argc;n++)
+      { IncField *New=0;
+        if(!strcmp(argv[n],"--pw") && n+9<argc)
+         { cdouble E0[3]; double nHat[3];
+           for(int m=0;m<3;m++) { E0[m]=cdouble(atof(argv[n+1+2*m]),atof(argv[n+2+2*m])); nHat[m]=atof(argv[n+7+m]); }
+           New=new PlaneWave(E0,nHat); n+=9; }
+        else if(!strcmp(argv[n],"--ps") && n+9<argc)
+         { double X0[3]; cdouble P[3];
+           for(int m=0;m<3;m++) { X0[m]=atof(argv[n+1+m]); P[m]=cdouble(atof(argv[n+4+2*m]),atof(argv[n+5+2*m])); }
+           New=new PointSource(X0,P); n+=9; }
+        else if(!strcmp(argv[n],"--interior")) Interior=true;
+        else if(!strcmp(argv[n],"--nopft")) NoPFT=true;
+        else if(!strcmp(argv[n],"--method")) Method=atoi(argv[++n]);
+        else if(!strcmp(argv[n],"--transfile")) TransFile=argv[++n];
+        else if(!strcmp(argv[n],"--trans")) nTrans=atoi(argv[++n]);
+        if(New) { if(Tail) Tail->Next=New; else IFList=New; Tail=New; } }
+     if(!IFList) { fprintf(stderr,"scatter: no incident field\n"); return 2; }
+     if (TransFile)
+      { GTCList GTCs=ReadTransFile(TransFile);
+        if(nTrans<0||nTrans>=(int)GTCs.size()) { fprintf(stderr,"no transformation %i in %s\n",nTrans,TransFile); return 2; }
+        G->Transform(GTCs[nTrans]); }
+     double t0=Now();
+     HMatrix *M=G->AssembleBEMMatrix(Omega,(HMatrix *)0);
+     double t1=Now();
+     HVector *KN=G->AssembleRHSVector(Omega,IFList,0), *RHS=new HVector(KN->N,LHM_COMPLEX);
+     RHS->Copy(KN);
+     double t2=Now();
+     M->LUFactorize(); M->LUSolve(KN);
+     double t3=Now();
+     HMatrix *PFT=new HMatrix(G->NumSurfaces,NUMPFT);
+     if(!NoPFT)
+      { PFTOptions Opts; InitPFTOptions(&Opts); Opts.PFTMethod=SCUFF_PFT_EMT; Opts.IF=IFList; Opts.Interior=Interior; Opts.EMTPFTIMethod=Method;
+        G->GetPFTMatrix(KN,Omega,&Opts,PFT); }
+     double t4=Now();
+     printf("{\"N\": %i, \"NS\": %i, \"threads\": %i, \"assemble_s\": %.6f, \"rhs_s\": %.6f, \"lu_solve_s\": %.6f, \"pft_s\": %.6f}\n",
+            KN->N,G->NumSurfaces,omp_get_max_threads(),t1-t0,t2-t1,t3-t2,t4-t3);
+     FILE *f=fopen(Out,"wb"); if(!f) return 1;
+     fwrite(RHS->ZV,sizeof(cdouble),RHS->N,f); fwrite(KN->ZV,sizeof(cdouble),KN->N,f);
+     for(int ns=0;ns<G->NumSurfaces;ns++) for(int nq=0;nq<NUMPFT;nq++) { double v=PFT->GetEntryD(ns,nq); fwrite(&v,sizeof(double),1,f); }
      fclose(f); return 0;
    }
 

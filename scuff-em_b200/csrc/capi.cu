@@ -31,6 +31,7 @@ int run_td_div_selftest(scuffcuda_context *ctx, int n, const double *x, double *
 // far_kernel.cu
 void far_slots_release(scuffcuda_context *ctx);     // window/slot tables of the staged scatter
 void far_twopass_release(scuffcuda_context *ctx);   // panel-pair array and edge tables of the two-pass path
+void pft_release(scuffcuda_context *ctx);           // rhs_pft.cu: cubature tables and near basis-function pair lists
 int launch_far_gather(scuffcuda_context *ctx);      // second pass (no-op unless launch_far chose the two-pass path); 1 = it mirrored
 double far_gather_elapsed_ms(scuffcuda_context *ctx);
 void far_set_zero_event(scuffcuda_context *ctx, cudaEvent_t ev);
@@ -75,7 +76,8 @@ void scuffcuda_destroy(scuffcuda_context *ctx)
   cudaSetDevice(ctx->device);
   scuffcuda::far_slots_release(ctx);
   scuffcuda::far_twopass_release(ctx);
-  for (auto &s : ctx->surfaces) if (s.dpanels) cudaFree(s.dpanels);
+  scuffcuda::pft_release(ctx);
+  for (auto &s : ctx->surfaces) { if (s.dpanels) cudaFree(s.dpanels); if (s.dedges) cudaFree(s.dedges); }
   for (auto &m : ctx->matrices) { if (m.second.d) cudaFree(m.second.d); if (m.second.ipiv) cudaFree(m.second.ipiv); }
   for (auto &p : ctx->plans) if (p.dnear) cudaFree(p.dnear);
   for (auto &t : ctx->gbarTables) if (t.second.dC) cudaFree(t.second.dC);
@@ -101,7 +103,9 @@ int scuffcuda_synchronize(scuffcuda_context *ctx)
 int scuffcuda_set_num_surfaces(scuffcuda_context *ctx, int n)
 { if (n < 0) return fail(ctx, "invalid number of surfaces %d", n);
   CK(cudaSetDevice(ctx->device));
-  for (size_t i = n; i < ctx->surfaces.size(); i++) if (ctx->surfaces[i].dpanels) cudaFree(ctx->surfaces[i].dpanels);
+  for (size_t i = n; i < ctx->surfaces.size(); i++)
+   { if (ctx->surfaces[i].dpanels) cudaFree(ctx->surfaces[i].dpanels);
+     if (ctx->surfaces[i].dedges) cudaFree(ctx->surfaces[i].dedges); }
   ctx->surfaces.resize(n);
   return 0;
 }
@@ -118,6 +122,7 @@ int scuffcuda_set_surface(scuffcuda_context *ctx, int ns, int NV, const double *
   const bool sameShape = (S.NV == NV && S.NP == NP && S.NE == NE && S.isPEC == (isPEC != 0) && S.dpanels);
   S.NV = NV; S.NP = NP; S.NE = NE; S.isPEC = (isPEC != 0);
   S.V.assign(V, V + 3 * (size_t)NV);
+  S.edgeTopo.assign(ET, ET + 8 * (size_t)NE); S.edgeLen.assign(EL, EL + NE); S.edgesGen = 0;
   S.hpanels.assign(NP, PanelRec());
   for (int np = 0; np < NP; np++)
    { PanelRec &P = S.hpanels[np];
@@ -353,6 +358,32 @@ int scuffcuda_lu_solve(scuffcuda_context *ctx, int h, void *rhs, int nrhs)
   else CKS(cusolverDnZgetrs(ctx->solver, CUBLAS_OP_N, n, nrhs, (cuDoubleComplex *)M->d, n, M->ipiv, (cuDoubleComplex *)dB, n, dinfo));
   CK(cudaMemcpyAsync(rhs, dB, (size_t)n * nrhs * es, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// the right-hand side stays on the device (scuffcuda_assemble_rhs wrote it there): solve in place
+int scuffcuda_lu_solve_device(scuffcuda_context *ctx, int h, int hv)
+{ Matrix *M = get_matrix(ctx, h), *X = get_matrix(ctx, hv);
+  if (!M || !X) return fail(ctx, "lu_solve_device: invalid handle");
+  if (!M->factored) return fail(ctx, "lu_solve_device: matrix has not been factored");
+  if (X->NR != M->NR || X->isReal != M->isReal) return fail(ctx, "lu_solve_device: vector does not match the matrix (%d x %d %s vs %d %s)",
+                                                            X->NR, X->NC, X->isReal ? "real" : "complex", M->NR, M->isReal ? "real" : "complex");
+  CK(cudaSetDevice(ctx->device));
+  if (256 > ctx->scratchBytes)
+   { if (ctx->dscratch) cudaFree(ctx->dscratch); ctx->dscratch = nullptr; ctx->scratchBytes = 0;
+     CK(cudaMalloc(&ctx->dscratch, 256)); ctx->scratchBytes = 256; }
+  int *dinfo = (int *)ctx->dscratch; const int n = M->NR;
+  if (M->isReal) CKS(cusolverDnDgetrs(ctx->solver, CUBLAS_OP_N, n, X->NC, M->d, n, M->ipiv, X->d, n, dinfo));
+  else CKS(cusolverDnZgetrs(ctx->solver, CUBLAS_OP_N, n, X->NC, (cuDoubleComplex *)M->d, n, M->ipiv, (cuDoubleComplex *)X->d, n, dinfo));
+  return 0;
+}
+int scuffcuda_matrix_copy(scuffcuda_context *ctx, int hd, int hs)
+{ Matrix *D = get_matrix(ctx, hd), *S = get_matrix(ctx, hs);
+  if (!D || !S) return fail(ctx, "matrix_copy: invalid handle");
+  if (D->NR != S->NR || D->NC != S->NC || D->isReal != S->isReal) return fail(ctx, "matrix_copy: shapes differ");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(D->d, S->d, (size_t)S->NR * S->NC * (S->isReal ? 1 : 2) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  D->factored = false;
   return 0;
 }
 

@@ -32,6 +32,10 @@ struct Surface
   std::vector<PanelRec> hpanels;
   PanelRec *dpanels = nullptr;
   uint64_t generation = 0;         // bumped on every set_surface (invalidates plans)
+  // edge topology as scuffcuda_set_surface received it (8 ints per edge) + lengths: the per-edge kernels of rhs_pft.cu
+  // (RHS vector, PFT near pairs) build their device edge records from these
+  std::vector<int> edgeTopo; std::vector<double> edgeLen;
+  void *dedges = nullptr; uint64_t edgesGen = 0;
 };
 
 struct Matrix
@@ -131,4 +135,5 @@ struct scuffcuda_context
   struct MappedBuf { void *p = nullptr; size_t n = 0; };
   std::map<int, MappedBuf> mapped;            // slot -> page-locked, device-mapped scratch
   int *dHoIdx = nullptr; size_t hoIdxCap = 0; // index list of the high-order cubature kernel
+  void *pftState = nullptr;                   // rhs_pft.cu: cubature tables, near basis-function pair lists (freed by pft_release)
 };

@@ -1046,6 +1046,9 @@ __device__ __forceinline__ long farq_row(const FarQ &L, int pb, int &EX)
   EX = L.extFull; return (long)L.nc * pb * 3 * L.extFull;
 }
 struct FarArgsQ { FarArgs A; FarQ L; };
+#ifndef FAR_PSI_MINB
+#define FAR_PSI_MINB 2          /* resident CTAs per SM of the Phi + Psi first pass */
+#endif
 
 template <int KMODE, int SMALL>
 __global__ void __launch_bounds__(FAR_THREADS, 3)
@@ -1149,7 +1152,7 @@ far_pass1_kernel(const __grid_constant__ FarArgsQ X)
 //   g0 = l_a l_b H0 ,  g1 = l_a l_b H1 / (ik)      (EdgeEdgeInteractions.cc:183-188, SurfaceSurfaceInteractions.cc:219-327)
 // (the region prefactors c1, c2, c3 are applied by the gather).
 template <int KMODE, int SMALL>
-__global__ void __launch_bounds__(FAR_THREADS, 2)
+__global__ void __launch_bounds__(FAR_THREADS, FAR_PSI_MINB)
 far_pass1_psi_kernel(const __grid_constant__ FarArgsQ X)
 { const FarArgs &A = X.A;
   extern __shared__ __align__(128) double sm[];

@@ -1,0 +1,721 @@
+// Right-hand-side vector and power / force / torque of a scattering problem on the device: with the
+// BEM matrix assembled and factored in HBM, the incident-field projections, the solve and the energy/momentum-transfer
+// sums run on the same device, so that one frequency point of a scuff-scatter run (scuff-scatter.cc:402-520) ends with
+// 8 doubles per surface crossing PCIe instead of the matrix.
+//
+// What the reference computes, restated:
+//   * AssembleRHSVector (AssembleRHSVector.cc:365-428): RHS[edge] = -+ <f_edge, E_inc>/ZVAC (and -+ <f_edge, H_inc> for a
+//     dielectric surface), each inner product by the 78-point order-20 rule over the edge's positive panel (vertices QP, V1,
+//     V2) minus the same over its negative panel (V1, V2, QM) (GetInnerProducts :172-229, TriIntFixed libTriInt.cc:279-322);
+//     fields whose sources lie in the surface's exterior region enter with -, interior region with + (:297-306).
+//   * GetEMTPFTMatrix (EMTPFT.cc:533-905) with the cubature integrals of SCUFF_EMTPFTI_EHDERIVATIVES1 (:82-176, :308-334):
+//     for every ordered pair of basis functions (a, b) that act on each other, sums over the Order x Order points of the
+//     four panel pairs (GetBFBFCubature2, PanelCubature.cc:791-893; Order = 9 if the two functions share a vertex
+//     (AssessBFPair), else 4) of kernels Phi, Psi, Zeta times polynomial factors, contracted with the bilinears
+//     conj(k_a) k_b, ... of the solution (GetKNBilinears, GetPFT.cc:95-132).  On one surface only the imaginary parts of the
+//     kernels enter (:103-121).  Plus the extinction terms (GetExtinctionPFTT :466-531): the 21-point rule of every panel
+//     with the incident field and its gradient.
+//
+// B200 formulation (not the reference's): the sums are bilinear in the expansion coefficients, so the surface currents
+//   K(x) = sum_e k_e f_e(x),  N(x) = sum_e n_e f_e(x)  are tabulated once at the cubature points of every panel
+// (pft_currents_kernel) and ONE pass over all ordered pairs of cubature points (pft_pair_kernel, an N-body style tile loop:
+// a thread owns one point of surface a, a CTA stages tiles of the points of surface b in shared memory) accumulates
+// power, force and both torque terms — 36 point pairs per panel pair instead of 9 basis-function pairs x 4 x 36.  The basis
+// function pairs that share a vertex (O(N) of them, listed on the host by the reference's VecClose test) get the difference
+// "order 9 minus order 4" from pft_near_kernel, one warp per pair.  All reductions are fixed-order (per-CTA partial sums,
+// summed on the host), so results are reproducible run to run.
+#include <vector>
+#include <map>
+#include <algorithm>
+#include <complex>
+#include <string>
+#include "kernels.h"
+#include "generated_tcr20.h"
+#include "generated_tcr9.h"
+
+#define ZVAC 376.73031346177      /* libscuff.h:78 */
+#define TENTHIRDS 3.33333333333333333333333   /* PFTOptions.h:64 */
+#define CVTHRESHOLD 1.0e-6        /* AssessPanelPair.cc:39 */
+#define PFT_NQ 10                 /* PScat, F[3], T1[3], T2[3] (PAbs comes from the extinction pass) */
+#define PFT_MAXPW 8
+
+namespace scuffcuda {
+
+struct EdgeRec { double QP[3], V1[3], V2[3], QM[3]; double len; int hasM; int pad; };   // 112 B
+
+// one cubature point of a panel with the surface currents there (160 B)
+struct __align__(16) CurPt
+{ double x[3]; double w;            // position; weight = 2 A w_p
+  double Kr[3], Ki[3];              // K(x)
+  double Nr[3], Ni[3];              // N(x) = sum -ZVAC KN[2e+1] f_e(x)
+  double dKr, dKi, dNr, dNi;        // surface divergences
+};
+static_assert(sizeof(CurPt) == 160, "CurPt layout");
+
+struct PlaneWaveDev { cd E0[3]; double n[3]; cd K; cd invZ; double sign; };
+
+struct NearBF { int ea, eb; };
+
+struct PftNearList { uint64_t genA = 0, genB = 0; int n = 0; NearBF *d = nullptr; };
+
+struct PftState
+{ double *dtcr20 = nullptr, *dtcr9 = nullptr, *dtcr4 = nullptr;
+  std::map<std::pair<int, int>, PftNearList> nearLists;
+  CurPt *dcur = nullptr; size_t curCap = 0;          // current points of all surfaces (order 4, then order 9)
+  double *dpart = nullptr; size_t partCap = 0;       // per-CTA partial sums
+  double *dtab = nullptr; size_t tabCap = 0;         // tabulated incident fields
+};
+
+#define PCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string("rhs/pft: ") + #call + ": " + cudaGetErrorString(e_); return 1; } } while (0)
+static int pfail(scuffcuda_context *ctx, const std::string &msg) { ctx->err = msg; return 1; }
+
+static PftState *pft_state(scuffcuda_context *ctx)
+{ if (!ctx->pftState) ctx->pftState = new PftState();
+  return (PftState *)ctx->pftState;
+}
+void pft_release(scuffcuda_context *ctx)
+{ PftState *P = (PftState *)ctx->pftState; if (!P) return;
+  if (P->dtcr20) cudaFree(P->dtcr20); if (P->dtcr9) cudaFree(P->dtcr9); if (P->dtcr4) cudaFree(P->dtcr4);
+  for (auto &l : P->nearLists) if (l.second.d) cudaFree(l.second.d);
+  if (P->dcur) cudaFree(P->dcur); if (P->dpart) cudaFree(P->dpart); if (P->dtab) cudaFree(P->dtab);
+  delete P; ctx->pftState = nullptr;
+}
+static int pft_tables(scuffcuda_context *ctx)
+{ PftState *P = pft_state(ctx);
+  if (P->dtcr20) return 0;
+  static const double U4[6] = SCUFF_TCR4_U, V4[6] = SCUFF_TCR4_V, W4[6] = SCUFF_TCR4_W;
+  double T4[18]; for (int p = 0; p < 6; p++) { T4[3 * p] = U4[p]; T4[3 * p + 1] = V4[p]; T4[3 * p + 2] = W4[p]; }
+  PCK(cudaMalloc(&P->dtcr4, sizeof T4)); PCK(cudaMalloc(&P->dtcr9, sizeof SC_TCR9_H)); PCK(cudaMalloc(&P->dtcr20, sizeof SC_TCR20_H));
+  PCK(cudaMemcpyAsync(P->dtcr4, T4, sizeof T4, cudaMemcpyHostToDevice, ctx->stream));
+  PCK(cudaMemcpyAsync(P->dtcr9, SC_TCR9_H, sizeof SC_TCR9_H, cudaMemcpyHostToDevice, ctx->stream));
+  PCK(cudaMemcpyAsync(P->dtcr20, SC_TCR20_H, sizeof SC_TCR20_H, cudaMemcpyHostToDevice, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+template <class T> static int grow(scuffcuda_context *ctx, T *&p, size_t &cap, size_t need)
+{ if (need <= cap) return 0;
+  if (p) cudaFree(p); p = nullptr; cap = 0;
+  PCK(cudaMalloc(&p, need * sizeof(T))); cap = need; return 0;
+}
+
+static void host_edge(const Surface &S, int ne, EdgeRec &E)
+{ const int *t = &S.edgeTopo[8 * (size_t)ne];
+  for (int m = 0; m < 3; m++)
+   { E.V1[m] = S.V[3 * (size_t)t[0] + m]; E.V2[m] = S.V[3 * (size_t)t[1] + m]; E.QP[m] = S.V[3 * (size_t)t[2] + m];
+     E.QM[m] = t[3] >= 0 ? S.V[3 * (size_t)t[3] + m] : 0.0; }
+  E.len = S.edgeLen[ne]; E.hasM = (t[3] >= 0 && t[5] >= 0); E.pad = 0;
+}
+static int ensure_edges(scuffcuda_context *ctx, Surface &S)
+{ if (S.dedges && S.edgesGen == S.generation && S.generation != 0) return 0;
+  if ((int)S.edgeLen.size() != S.NE) return pfail(ctx, "rhs/pft: surface has no edge table");
+  std::vector<EdgeRec> E(S.NE);
+  for (int ne = 0; ne < S.NE; ne++) host_edge(S, ne, E[ne]);
+  if (S.dedges) { cudaFree(S.dedges); S.dedges = nullptr; }
+  PCK(cudaMalloc(&S.dedges, std::max<size_t>(1, S.NE) * sizeof(EdgeRec)));
+  PCK(cudaMemcpyAsync(S.dedges, E.data(), (size_t)S.NE * sizeof(EdgeRec), cudaMemcpyHostToDevice, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  ctx->h2dBytes += (unsigned long long)S.NE * sizeof(EdgeRec);
+  S.edgesGen = S.generation;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// right-hand side
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ cd cexp_i(cd z)    // exp(i z)
+{ double s, c; sincos(z.x, &s, &c); const double e = (z.y == 0.0) ? 1.0 : exp(-z.y); return mk(e * c, e * s); }
+
+// sum of the plane waves' fields at X, each with its sign (PlaneWave::GetFields, libIncField/PlaneWave.cc:75-88)
+__device__ __forceinline__ void planewave_fields(const PlaneWaveDev *pw, int npw, const double X[3], cd E[3], cd H[3])
+{ for (int m = 0; m < 3; m++) { E[m] = mk(0.0, 0.0); H[m] = mk(0.0, 0.0); }
+  for (int i = 0; i < npw; i++)
+   { const PlaneWaveDev &W = pw[i];
+     const double nx = W.n[0] * X[0] + W.n[1] * X[1] + W.n[2] * X[2];
+     const cd ef = cexp_i(W.K * nx) * W.sign;
+     cd e[3]; for (int m = 0; m < 3; m++) e[m] = W.E0[m] * ef;
+     for (int m = 0; m < 3; m++) E[m] += e[m];
+     H[0] += (W.n[1] * e[2] - W.n[2] * e[1]) * W.invZ;
+     H[1] += (W.n[2] * e[0] - W.n[0] * e[2]) * W.invZ;
+     H[2] += (W.n[0] * e[1] - W.n[1] * e[0]) * W.invZ; }
+}
+
+struct RhsArgs
+{ const EdgeRec *edges; int NE; const double *tcr20; int npw; PlaneWaveDev pw[PFT_MAXPW];
+  const double *tab;              // 12 doubles per point ((ne*2 + pm)*78 + np), already signed and summed; or null
+  double *vec; int isReal; int offset; int isPEC;
+};
+
+__global__ void __launch_bounds__(128) rhs_points_kernel(const EdgeRec *edges, int NE, const double *tcr20, double *X)
+{ const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long)NE * 2 * SC_TCR20_NPTS) return;
+  const int np = (int)(i % SC_TCR20_NPTS), pm = (int)((i / SC_TCR20_NPTS) & 1), ne = (int)(i / (2 * SC_TCR20_NPTS));
+  const EdgeRec &E = edges[ne];
+  const double u = tcr20[3 * np], v = tcr20[3 * np + 1];
+  const double *A0 = pm ? E.V1 : E.QP, *A1 = pm ? E.V2 : E.V1, *A2 = pm ? E.QM : E.V2;
+  for (int m = 0; m < 3; m++) X[3 * i + m] = (pm && !E.hasM) ? E.QP[m] : A0[m] + u * (A1[m] - A0[m]) + v * (A2[m] - A0[m]);
+}
+
+// one warp per edge, lanes over the 2 x 78 cubature points
+__global__ void __launch_bounds__(128) rhs_kernel(const __grid_constant__ RhsArgs A)
+{ const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= A.NE) return;
+  const EdgeRec &E = A.edges[warp];
+  double acc[4] = { 0.0, 0.0, 0.0, 0.0 };      // Re/Im <f,E>, Re/Im <f,H>
+  for (int idx = lane; idx < 2 * SC_TCR20_NPTS; idx += 32)
+   { const int pm = idx / SC_TCR20_NPTS, np = idx - pm * SC_TCR20_NPTS;
+     if (pm && !E.hasM) continue;
+     const double u = A.tcr20[3 * np], v = A.tcr20[3 * np + 1], w = A.tcr20[3 * np + 2];
+     // TriIntFixed(.., QP, V1, V2) on the positive panel, TriIntFixed(.., V1, V2, QM) on the negative one
+     const double *A0 = pm ? E.V1 : E.QP, *A1 = pm ? E.V2 : E.V1, *A2 = pm ? E.QM : E.V2, *Q = pm ? E.QM : E.QP;
+     double X[3], f[3];
+     for (int m = 0; m < 3; m++) { X[m] = A0[m] + u * (A1[m] - A0[m]) + v * (A2[m] - A0[m]); f[m] = X[m] - Q[m]; }
+     cd Ef[3], Hf[3];
+     planewave_fields(A.pw, A.npw, X, Ef, Hf);
+     if (A.tab)
+      { const double *t = A.tab + 12 * ((size_t)(warp * 2 + pm) * SC_TCR20_NPTS + np);
+        for (int m = 0; m < 3; m++) { Ef[m] += mk(t[2 * m], t[2 * m + 1]); Hf[m] += mk(t[6 + 2 * m], t[7 + 2 * m]); } }
+     // PreFac * Jacobian * w = (l / 2A)(2A) w = l w; the negative panel enters with a minus sign
+     const double s = (pm ? -w : w) * E.len;
+     acc[0] += s * (f[0] * Ef[0].x + f[1] * Ef[1].x + f[2] * Ef[2].x);
+     acc[1] += s * (f[0] * Ef[0].y + f[1] * Ef[1].y + f[2] * Ef[2].y);
+     acc[2] += s * (f[0] * Hf[0].x + f[1] * Hf[1].x + f[2] * Hf[2].x);
+     acc[3] += s * (f[0] * Hf[0].y + f[1] * Hf[1].y + f[2] * Hf[2].y); }
+  for (int q = 0; q < 4; q++)
+   for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+  if (lane) return;
+  const int row = A.offset + (A.isPEC ? warp : 2 * warp);
+  if (A.isReal)
+   { A.vec[row] = acc[0] / ZVAC; if (!A.isPEC) A.vec[row + 1] = acc[2]; }
+  else
+   { A.vec[2 * row] = acc[0] / ZVAC; A.vec[2 * row + 1] = acc[1] / ZVAC;
+     if (!A.isPEC) { A.vec[2 * row + 2] = acc[2]; A.vec[2 * row + 3] = acc[3]; } }
+}
+
+static int make_pw(scuffcuda_context *ctx, const double omega[2], int n, const scuffcuda_planewave *pw, PlaneWaveDev *out)
+{ if (n < 0 || n > PFT_MAXPW) return pfail(ctx, "rhs/pft: at most 8 plane waves per call");
+  typedef std::complex<double> cx;
+  for (int i = 0; i < n; i++)
+   { const cx Om(omega[0], omega[1]), eps(pw[i].eps[0], pw[i].eps[1]), mu(pw[i].mu[0], pw[i].mu[1]);
+     const cx K = std::sqrt(eps * mu) * Om, Z = ZVAC * std::sqrt(mu / eps), iZ = 1.0 / Z;
+     for (int m = 0; m < 3; m++) { out[i].E0[m] = mk(pw[i].e0[2 * m], pw[i].e0[2 * m + 1]); out[i].n[m] = pw[i].nhat[m]; }
+     out[i].K = mk(K.real(), K.imag()); out[i].invZ = mk(iZ.real(), iZ.imag()); out[i].sign = pw[i].sign; }
+  return 0;
+}
+
+static Matrix *find_matrix(scuffcuda_context *ctx, int h)
+{ auto it = ctx->matrices.find(h); return it == ctx->matrices.end() ? nullptr : &it->second; }
+
+// ------------------------------------------------------------------------------------------------------------------
+// power / force / torque
+// ------------------------------------------------------------------------------------------------------------------
+struct PftParams
+{ double k, omega;             // real wavenumber in the region, real frequency
+  double zmu, eoz;             // ZVAC * MuRel, EpsRel / ZVAC
+  double ook2;                 // 1 / k^2
+  double origin[3];            // torque centre of the surface the force acts on (RWGSurface::Origin)
+};
+
+// surface currents at the cubature points of every panel of one surface (panel vertex order: GetPanelCubature,
+// PanelCubature.cc:155-236; coefficients as GetKNCoefficients reads them, RWGGeometry.cc:957-980)
+__global__ void __launch_bounds__(128)
+pft_currents_kernel(const PanelRec *panels, int NP, const double *tcr, int npts, const double *kn, int offset, int isPEC, int useN, CurPt *out)
+{ const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NP * npts) return;
+  const int np = i / npts, p = i - np * npts;
+  const PanelRec &P = panels[np];
+  const double u = tcr[3 * p], v = tcr[3 * p + 1], w = tcr[3 * p + 2];
+  double A[3], B[3], X[3];
+  for (int m = 0; m < 3; m++) { A[m] = P.V[3 + m] - P.V[m]; B[m] = P.V[6 + m] - P.V[m]; X[m] = P.V[m] + u * A[m] + v * B[m]; }
+  const double cx = A[1] * B[2] - A[2] * B[1], cy = A[2] * B[0] - A[0] * B[2], cz = A[0] * B[1] - A[1] * B[0];
+  const double twoA = sqrt(cx * cx + cy * cy + cz * cz);
+  CurPt C;
+  for (int m = 0; m < 3; m++) { C.x[m] = X[m]; C.Kr[m] = C.Ki[m] = C.Nr[m] = C.Ni[m] = 0.0; }
+  C.dKr = C.dKi = C.dNr = C.dNi = 0.0; C.w = twoA * w;
+  for (int e = 0; e < 3; e++)
+   { const int ne = P.ei[e]; if (ne < 0) continue;
+     const double pre = P.sl[e] / twoA;                       // +-l/(2A)
+     const int row = offset + (isPEC ? ne : 2 * ne);
+     const double kr = kn[2 * row], ki = kn[2 * row + 1];
+     double nr = 0.0, ni = 0.0;
+     if (!isPEC && useN) { nr = -ZVAC * kn[2 * row + 2]; ni = -ZVAC * kn[2 * row + 3]; }
+     for (int m = 0; m < 3; m++)
+      { const double f = pre * (X[m] - P.V[3 * e + m]);
+        C.Kr[m] += kr * f; C.Ki[m] += ki * f; C.Nr[m] += nr * f; C.Ni[m] += ni * f; }
+     C.dKr += 2.0 * pre * kr; C.dKi += 2.0 * pre * ki; C.dNr += 2.0 * pre * nr; C.dNi += 2.0 * pre * ni; }
+  out[i] = C;
+}
+
+__device__ __forceinline__ cd cmul_helper(cd a, cd b, double s) { const cd p = a * b; return mk(p.x * s, p.y * s); }
+
+// Phi, Psi, Zeta of ScatteredPFTIntegrand1 (EMTPFT.cc:98-128).  SAME: imaginary parts only, with the reference's
+// small-argument series; otherwise the complex kernels.
+template <bool SAME>
+__device__ __forceinline__ void pft_kernels(double k, double r2, cd &Phi, cd &Psi, cd &Zeta)
+{ const double r = sqrt(r2), kr = k * r, kr2 = kr * kr, k2 = k * k;
+  if (SAME)
+   { double iPhi, iPsi, iZeta;
+     if (fabs(kr) < 1.0e-3)
+      { const double k3 = k2 * k, k5 = k3 * k2;
+        iPhi = (1.0 - kr2 / 6.0) * k / (4.0 * M_PI);
+        iPsi = -(1.0 - kr2 / 10.0) * k3 / (12.0 * M_PI);
+        iZeta = (1.0 - kr2 / 14.0) * k5 / (60.0 * M_PI); }
+     else
+      { double s, c; sincos(kr, &s, &c);
+        const double r3 = r * r2, r5 = r3 * r2;
+        iPhi = s / (4.0 * M_PI * r);
+        iPsi = (kr * c - s) / (4.0 * M_PI * r3);
+        iZeta = (-3.0 * kr * c + (3.0 - kr2) * s) / (4.0 * M_PI * r5); }
+     Phi = mk(0.0, iPhi); Psi = mk(0.0, iPsi); Zeta = mk(0.0, iZeta); }
+  else
+   { double s, c; sincos(kr, &s, &c);
+     const double g = 1.0 / (4.0 * M_PI * r);
+     Phi = mk(c * g, s * g);
+     Psi = cmul_helper(Phi, mk(-1.0, kr), 1.0 / r2);
+     Zeta = cmul_helper(Phi, mk(3.0 - kr2, -3.0 * kr), 1.0 / (r2 * r2)); }
+}
+
+// one cubature point pair: a* = conjugated currents at the point of surface a, b = currents at the point of surface b;
+// acc[0] PScat, acc[1..3] force density, acc[4..6] first torque term — all without the weights of point a.
+// HASN: both surfaces carry magnetic currents (if either is PEC the reference drops every N bilinear, GetPFT.cc:103-109)
+template <bool HASN, bool SAME>
+__device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double xa[3],
+                                               const double aKr[3], const double aKi[3], const double aNr[3], const double aNi[3],
+                                               double adKr, double adKi, double adNr, double adNi,
+                                               const CurPt &b, double acc[7])
+{ double R[3]; for (int m = 0; m < 3; m++) R[m] = xa[m] - b.x[m];
+  const double r2 = R[0] * R[0] + R[1] * R[1] + R[2] * R[2];
+  cd Phi, Psi, Zeta;
+  pft_kernels<SAME>(Q.k, r2, Phi, Psi, Zeta);
+  // conj(K_a) = (aKr, -aKi) etc. are passed already conjugated
+  cd kk = mk(0.0, 0.0), nn = mk(0.0, 0.0), kn = mk(0.0, 0.0), nk = mk(0.0, 0.0), aR = mk(0.0, 0.0), nR = mk(0.0, 0.0);
+  for (int m = 0; m < 3; m++)
+   { kk += mk(aKr[m], aKi[m]) * mk(b.Kr[m], b.Ki[m]);
+     aR += mk(aKr[m] * R[m], aKi[m] * R[m]);
+     if (HASN)
+      { nn += mk(aNr[m], aNi[m]) * mk(b.Nr[m], b.Ni[m]);
+        kn += mk(aKr[m], aKi[m]) * mk(b.Nr[m], b.Ni[m]);
+        nk += mk(aNr[m], aNi[m]) * mk(b.Kr[m], b.Ki[m]);
+        nR += mk(aNr[m] * R[m], aNi[m] * R[m]); } }
+  const cd ddk = mk(adKr, adKi) * mk(b.dKr, b.dKi);
+  cd S1p = (kk - ddk * Q.ook2) * Q.zmu;
+  if (HASN) { const cd ddn = mk(adNr, adNi) * mk(b.dNr, b.dNi); S1p += (nn - ddn * Q.ook2) * Q.eoz; }
+  // V1 = zmu (a x b) + eoz (n x m);  C = a x m - n x b
+  cd V1[3], C[3], D[3];
+  for (int m = 0; m < 3; m++)
+   { const int m1 = (m + 1) % 3, m2 = (m + 2) % 3;
+     const cd a1 = mk(aKr[m1], aKi[m1]), a2 = mk(aKr[m2], aKi[m2]), b1 = mk(b.Kr[m1], b.Ki[m1]), b2 = mk(b.Kr[m2], b.Ki[m2]);
+     V1[m] = (a1 * b2 - a2 * b1) * Q.zmu;
+     if (HASN)
+      { const cd n1 = mk(aNr[m1], aNi[m1]), n2 = mk(aNr[m2], aNi[m2]), q1 = mk(b.Nr[m1], b.Ni[m1]), q2 = mk(b.Nr[m2], b.Ni[m2]);
+        V1[m] += (n1 * q2 - n2 * q1) * Q.eoz;
+        C[m] = (a1 * q2 - a2 * q1) - (n1 * b2 - n2 * b1);
+        D[m] = aR * mk(b.Nr[m], b.Ni[m]) - nR * mk(b.Kr[m], b.Ki[m]) - (kn - nk) * R[m]; }
+     else { C[m] = mk(0.0, 0.0); D[m] = mk(0.0, 0.0); } }
+  const double w = b.w, ft = TENTHIRDS * w, oow = 1.0 / Q.omega;
+  // PScat: -Re( i omega S1p Phi + PM Psi ) = omega Im(S1p Phi) - Re(PM Psi)
+  const cd sPhi = S1p * Phi, sPsi = S1p * Psi;
+  double p = Q.omega * sPhi.y;
+  cd PM = mk(0.0, 0.0);
+  if (HASN) { PM = C[0] * R[0] + C[1] * R[1] + C[2] * R[2]; p -= (PM * Psi).x; }
+  acc[0] += w * p;
+  const cd pmZ = PM * Zeta;
+  for (int m = 0; m < 3; m++)
+   { // force: -Im( i S1p R Psi - (C Psi + PM R Zeta)/omega ) = -R Re(S1p Psi) + Im(C Psi + PM R Zeta)/omega
+     double f = -R[m] * sPsi.x;
+     // first torque term: -Im( i V1 Phi - D Psi/omega ) = -Re(V1 Phi) + Im(D Psi)/omega
+     double t = -(V1[m] * Phi).x;
+     if (HASN) { f += ((C[m] * Psi).y + pmZ.y * R[m]) * oow; t += (D[m] * Psi).y * oow; }
+     acc[1 + m] += ft * f; acc[4 + m] += ft * t; }
+}
+
+#define PFT_TILE 64
+#define PFT_THREADS 128
+
+struct PairArgs
+{ const CurPt *A; int nA; const CurPt *B; int nB; int bChunk;    // blockIdx.y covers points [y*bChunk, (y+1)*bChunk) of B
+  PftParams Q; double *part;                                      // PFT_NQ doubles per CTA
+};
+
+__device__ __forceinline__ void block_reduce_store(double v[PFT_NQ], double *out)
+{ __shared__ double red[PFT_THREADS / 32][PFT_NQ];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < PFT_NQ; q++)
+   for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  if (lane == 0) for (int q = 0; q < PFT_NQ; q++) red[warp][q] = v[q];
+  __syncthreads();
+  if (threadIdx.x < PFT_NQ)
+   { double s = 0.0; for (int wq = 0; wq < PFT_THREADS / 32; wq++) s += red[wq][threadIdx.x];
+     out[threadIdx.x] = s; }
+}
+
+template <bool HASN, bool SAME>
+__global__ void __launch_bounds__(PFT_THREADS) pft_pair_kernel(const __grid_constant__ PairArgs X)
+{ __shared__ CurPt tile[PFT_TILE];
+  const int ia = blockIdx.x * PFT_THREADS + threadIdx.x;
+  const bool live = ia < X.nA;
+  CurPt a = X.A[live ? ia : 0];
+  double aKi[3], aNi[3];
+  for (int m = 0; m < 3; m++) { aKi[m] = -a.Ki[m]; aNi[m] = -a.Ni[m]; }
+  double acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
+  const int b0 = blockIdx.y * X.bChunk, b1 = min(X.nB, b0 + X.bChunk);
+  for (int t0 = b0; t0 < b1; t0 += PFT_TILE)
+   { const int nt = min(PFT_TILE, b1 - t0);
+     __syncthreads();
+     // cooperative copy of the tile (20 doubles per point)
+     { const double *src = (const double *)(X.B + t0); double *dst = (double *)tile;
+       for (int i = threadIdx.x; i < nt * 20; i += PFT_THREADS) dst[i] = src[i]; }
+     __syncthreads();
+     if (live)
+      for (int j = 0; j < nt; j++)
+       pft_point_pair<HASN, SAME>(X.Q, a.x, a.Kr, aKi, a.Nr, aNi, a.dKr, -a.dKi, a.dNr, -a.dNi, tile[j], acc);
+   }
+  double v[PFT_NQ];
+  const double wa = live ? a.w : 0.0;
+  for (int q = 0; q < 7; q++) v[q] = wa * acc[q];
+  // second torque term: (x_a - origin) x force density (EMTPFT.cc:166-168)
+  const double xt[3] = { a.x[0] - X.Q.origin[0], a.x[1] - X.Q.origin[1], a.x[2] - X.Q.origin[2] };
+  v[7] = xt[1] * v[3] - xt[2] * v[2]; v[8] = xt[2] * v[1] - xt[0] * v[3]; v[9] = xt[0] * v[2] - xt[1] * v[1];
+  block_reduce_store(v, X.part + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * PFT_NQ);
+}
+
+// basis-function pairs that share a vertex: (order 9) - (order 4) of the pair's four panel combinations; one warp per pair
+struct NearPftArgs
+{ const NearBF *list; int n; const EdgeRec *ea, *eb; const double *kn; int offA, offB, pecA, pecB;
+  const double *tcr9, *tcr4; PftParams Q; double *part; };
+
+__device__ __forceinline__ void bf_point(const EdgeRec &E, int pm, double u, double v, double X[3], double f[3], double &div, double &jac)
+{ const double *Q = pm ? E.QM : E.QP;
+  double A[3], B[3];
+  for (int m = 0; m < 3; m++) { A[m] = E.V1[m] - Q[m]; B[m] = E.V2[m] - Q[m]; }
+  const double cx = A[1] * B[2] - A[2] * B[1], cy = A[2] * B[0] - A[0] * B[2], cz = A[0] * B[1] - A[1] * B[0];
+  jac = sqrt(cx * cx + cy * cy + cz * cz);                    // 2 A
+  const double pre = (pm ? -E.len : E.len) / jac;             // +- l/(2A)
+  for (int m = 0; m < 3; m++) { const double d = u * A[m] + v * B[m]; X[m] = d + Q[m]; f[m] = pre * d; }
+  div = 2.0 * pre;
+}
+
+template <bool HASN, bool SAME>
+__global__ void __launch_bounds__(PFT_THREADS) pft_near_kernel(const __grid_constant__ NearPftArgs X)
+{ const int lane = threadIdx.x & 31, wid = blockIdx.x * (PFT_THREADS / 32) + (threadIdx.x >> 5);
+  double v[PFT_NQ]; for (int q = 0; q < PFT_NQ; q++) v[q] = 0.0;
+  if (wid < X.n)
+   { const NearBF P = X.list[wid];
+     const EdgeRec &EA = X.ea[P.ea], &EB = X.eb[P.eb];
+     const int rowA = X.offA + (X.pecA ? P.ea : 2 * P.ea), rowB = X.offB + (X.pecB ? P.eb : 2 * P.eb);
+     const double kar = X.kn[2 * rowA], kai = -X.kn[2 * rowA + 1];          // conj(k_a)
+     const double kbr = X.kn[2 * rowB], kbi = X.kn[2 * rowB + 1];
+     double nar = 0, nai = 0, nbr = 0, nbi = 0;
+     if (HASN) { nar = -ZVAC * X.kn[2 * rowA + 2]; nai = ZVAC * X.kn[2 * rowA + 3]; nbr = -ZVAC * X.kn[2 * rowB + 2]; nbi = -ZVAC * X.kn[2 * rowB + 3]; }
+     const int nPMa = EA.hasM ? 2 : 1, nPMb = EB.hasM ? 2 : 1;
+     for (int pass = 0; pass < 2; pass++)
+      { const double *tcr = pass ? X.tcr4 : X.tcr9; const int npts = pass ? 6 : SC_TCR9_NPTS; const double sgn = pass ? -1.0 : 1.0;
+        const int total = nPMa * nPMb * npts * npts;
+        for (int idx = lane; idx < total; idx += 32)
+         { int t = idx; const int pb = t % npts; t /= npts; const int pa = t % npts; t /= npts; const int pmb = t % nPMb; const int pma = t / nPMb;
+           double xa[3], fa[3], da, ja, xb[3], fb[3], db, jb;
+           bf_point(EA, pma, tcr[3 * pa], tcr[3 * pa + 1], xa, fa, da, ja);
+           bf_point(EB, pmb, tcr[3 * pb], tcr[3 * pb + 1], xb, fb, db, jb);
+           CurPt b; double aKr[3], aKi[3], aNr[3], aNi[3];
+           for (int m = 0; m < 3; m++)
+            { b.x[m] = xb[m]; b.Kr[m] = kbr * fb[m]; b.Ki[m] = kbi * fb[m]; b.Nr[m] = nbr * fb[m]; b.Ni[m] = nbi * fb[m];
+              aKr[m] = kar * fa[m]; aKi[m] = kai * fa[m]; aNr[m] = nar * fa[m]; aNi[m] = nai * fa[m]; }
+           b.dKr = kbr * db; b.dKi = kbi * db; b.dNr = nbr * db; b.dNi = nbi * db;
+           b.w = jb * tcr[3 * pb + 2];
+           double acc[7] = { 0, 0, 0, 0, 0, 0, 0 };
+           pft_point_pair<HASN, SAME>(X.Q, xa, aKr, aKi, aNr, aNi, kar * da, kai * da, nar * da, nai * da, b, acc);
+           const double wa = sgn * ja * tcr[3 * pa + 2];
+           for (int q = 0; q < 7; q++) { acc[q] *= wa; v[q] += acc[q]; }
+           const double xt[3] = { xa[0] - X.Q.origin[0], xa[1] - X.Q.origin[1], xa[2] - X.Q.origin[2] };
+           v[7] += xt[1] * acc[3] - xt[2] * acc[2]; v[8] += xt[2] * acc[1] - xt[0] * acc[3]; v[9] += xt[0] * acc[2] - xt[1] * acc[1]; } } }
+  block_reduce_store(v, X.part + (size_t)blockIdx.x * PFT_NQ);
+}
+
+// extinction (GetExtinctionPFTT, EMTPFT.cc:389-531): one thread per 21-point-rule point of a panel
+struct ExtArgs
+{ const CurPt *A; int nA; PlaneWaveDev pw; int havePW; const double *tab;   // tab: 48 doubles per point (EH[6], dEH[3][6]) or null
+  double origin[3]; double *part; };
+
+__global__ void __launch_bounds__(PFT_THREADS) pft_ext_kernel(const __grid_constant__ ExtArgs X)
+{ const int i = blockIdx.x * PFT_THREADS + threadIdx.x;
+  double v[PFT_NQ]; for (int q = 0; q < PFT_NQ; q++) v[q] = 0.0;
+  if (i < X.nA)
+   { const CurPt a = X.A[i];
+     cd EH[6], dEH[3][6];
+     for (int q = 0; q < 6; q++) { EH[q] = mk(0.0, 0.0); for (int m = 0; m < 3; m++) dEH[m][q] = mk(0.0, 0.0); }
+     if (X.havePW)
+      { cd E[3], H[3]; planewave_fields(&X.pw, 1, a.x, E, H);
+        for (int m = 0; m < 3; m++) { EH[m] = E[m]; EH[3 + m] = H[m]; }
+        // dEH[i][j] = i K nHat[i] EH[j] (PlaneWave::GetFieldGradients, PlaneWave.cc:94-103)
+        const cd iK = mk(-X.pw.K.y, X.pw.K.x);
+        for (int m = 0; m < 3; m++) for (int q = 0; q < 6; q++) dEH[m][q] = iK * EH[q] * X.pw.n[m]; }
+     if (X.tab)
+      { const double *t = X.tab + 48 * (size_t)i;
+        for (int q = 0; q < 6; q++) EH[q] += mk(t[2 * q], t[2 * q + 1]);
+        for (int m = 0; m < 3; m++) for (int q = 0; q < 6; q++) dEH[m][q] += mk(t[12 + 12 * m + 2 * q], t[13 + 12 * m + 2 * q]); }
+     cd Ks[3], Ns[3];                     // conj(K), conj(N)
+     for (int m = 0; m < 3; m++) { Ks[m] = mk(a.Kr[m], -a.Ki[m]); Ns[m] = mk(a.Nr[m], -a.Ni[m]); }
+     cd pabs = mk(0.0, 0.0);
+     for (int m = 0; m < 3; m++) pabs += Ks[m] * EH[m] + Ns[m] * EH[3 + m];
+     v[0] = a.w * pabs.x;
+     double F[3];
+     for (int mu = 0; mu < 3; mu++)
+      { cd f = mk(0.0, 0.0);
+        for (int m = 0; m < 3; m++) f += Ks[m] * dEH[mu][m] + Ns[m] * dEH[mu][3 + m];
+        F[mu] = a.w * f.y; v[1 + mu] = F[mu];
+        const int m1 = (mu + 1) % 3, m2 = (mu + 2) % 3;
+        const cd t = (Ks[m1] * EH[m2] - Ks[m2] * EH[m1]) + (Ns[m1] * EH[3 + m2] - Ns[m2] * EH[3 + m1]);
+        v[4 + mu] = a.w * t.y; }
+     const double xt[3] = { a.x[0] - X.origin[0], a.x[1] - X.origin[1], a.x[2] - X.origin[2] };
+     v[7] = xt[1] * F[2] - xt[2] * F[1]; v[8] = xt[2] * F[0] - xt[0] * F[2]; v[9] = xt[0] * F[1] - xt[1] * F[0]; }
+  block_reduce_store(v, X.part + (size_t)blockIdx.x * PFT_NQ);
+}
+
+// ---- host side: near basis-function pairs of a surface pair (AssessBFPair, AssessPanelPair.cc:200-241) -----------
+static int build_near_list(scuffcuda_context *ctx, int nsa, int nsb, PftNearList &L)
+{ Surface &SA = ctx->surfaces[nsa], &SB = ctx->surfaces[nsb];
+  if (L.d && L.genA == SA.generation && L.genB == SB.generation) return 0;
+  auto radius = [](const Surface &S, int ne)
+   { const int *t = &S.edgeTopo[8 * (size_t)ne]; double c[3], r = 0.0;
+     for (int m = 0; m < 3; m++) c[m] = 0.5 * (S.V[3 * (size_t)t[0] + m] + S.V[3 * (size_t)t[1] + m]);
+     for (int q = 0; q < 4; q++)
+      { const int vi = t[q]; if (vi < 0) continue; double d = 0.0;
+        for (int m = 0; m < 3; m++) { const double dd = S.V[3 * (size_t)vi + m] - c[m]; d += dd * dd; }
+        r = fmax(r, sqrt(d)); }
+     return r; };
+  std::vector<double> ra(SA.NE), rb(SB.NE); double rmax = 0.0;
+  for (int ne = 0; ne < SA.NE; ne++) { ra[ne] = radius(SA, ne); rmax = fmax(rmax, ra[ne]); }
+  for (int ne = 0; ne < SB.NE; ne++) { rb[ne] = radius(SB, ne); rmax = fmax(rmax, rb[ne]); }
+  const double tolMax = 3.0 * CVTHRESHOLD * rmax;
+  // vertices of b sorted by x; edges of b touching each vertex of b
+  std::vector<int> order(SB.NV); for (int i = 0; i < SB.NV; i++) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](int p, int q) { return SB.V[3 * (size_t)p] < SB.V[3 * (size_t)q]; });
+  std::vector<double> xs(SB.NV); for (int i = 0; i < SB.NV; i++) xs[i] = SB.V[3 * (size_t)order[i]];
+  std::vector<std::vector<int>> vedges(SB.NV);
+  for (int ne = 0; ne < SB.NE; ne++)
+   { const int *t = &SB.edgeTopo[8 * (size_t)ne];
+     for (int q = 0; q < 4; q++) if (t[q] >= 0 && (q < 3 || t[5] >= 0)) vedges[t[q]].push_back(ne); }
+  std::vector<NearBF> list; std::vector<int> stamp(SB.NE, -1);
+  for (int nea = 0; nea < SA.NE; nea++)
+   { const int *ta = &SA.edgeTopo[8 * (size_t)nea];
+     const int iVa[4] = { ta[2], ta[0], ta[1], ta[3] }; const int NVA = (ta[3] == -1 ? 3 : 4);
+     for (int qa = 0; qa < NVA; qa++)
+      { const double *va = &SA.V[3 * (size_t)iVa[qa]];
+        auto lo = std::lower_bound(xs.begin(), xs.end(), va[0] - tolMax), hi = std::upper_bound(xs.begin(), xs.end(), va[0] + tolMax);
+        for (auto it = lo; it != hi; ++it)
+         { const int vb = order[it - xs.begin()];
+           const double *pb = &SB.V[3 * (size_t)vb];
+           if (fabs(va[0] - pb[0]) + fabs(va[1] - pb[1]) + fabs(va[2] - pb[2]) > tolMax) continue;
+           for (int neb : vedges[vb])
+            { if (stamp[neb] == nea) continue;
+              stamp[neb] = nea;
+              // the reference's count with the pair's own threshold
+              const int *tb = &SB.edgeTopo[8 * (size_t)neb];
+              const int iVb[4] = { tb[2], tb[0], tb[1], tb[3] }; const int NVB = (tb[3] == -1 ? 3 : 4);
+              const double thr = 3.0 * fabs(CVTHRESHOLD * fmin(ra[nea], rb[neb]));
+              int ncv = 0;
+              for (int i = 0; i < NVA; i++) for (int j = 0; j < NVB; j++)
+               { const double *p = &SA.V[3 * (size_t)iVa[i]], *q = &SB.V[3 * (size_t)iVb[j]];
+                 if (fabs(p[0] - q[0]) + fabs(p[1] - q[1]) + fabs(p[2] - q[2]) <= thr) ncv++; }
+              if (ncv > 0) { NearBF P; P.ea = nea; P.eb = neb; list.push_back(P); } } } } }
+  if (L.d) { cudaFree(L.d); L.d = nullptr; }
+  L.n = (int)list.size();
+  PCK(cudaMalloc(&L.d, std::max<size_t>(1, list.size()) * sizeof(NearBF)));
+  if (L.n) PCK(cudaMemcpyAsync(L.d, list.data(), list.size() * sizeof(NearBF), cudaMemcpyHostToDevice, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  ctx->h2dBytes += (unsigned long long)list.size() * sizeof(NearBF);
+  L.genA = SA.generation; L.genB = SB.generation;
+  return 0;
+}
+
+static int sum_partials(scuffcuda_context *ctx, const double *dpart, size_t nblocks, double out[PFT_NQ])
+{ std::vector<double> h(nblocks * PFT_NQ);
+  PCK(cudaMemcpyAsync(h.data(), dpart, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2hBytes += h.size() * sizeof(double);
+  for (int q = 0; q < PFT_NQ; q++) { double s = 0.0; for (size_t b = 0; b < nblocks; b++) s += h[b * PFT_NQ + q]; out[q] = s; }
+  return 0;
+}
+
+}  // namespace scuffcuda
+
+using namespace scuffcuda;
+
+extern "C" {
+
+int scuffcuda_rhs_points(scuffcuda_context *ctx, int ns, double *X, long *npts)
+{ if (ns < 0 || ns >= (int)ctx->surfaces.size()) return pfail(ctx, "rhs_points: invalid surface index");
+  Surface &S = ctx->surfaces[ns];
+  const long n = (long)S.NE * 2 * SC_TCR20_NPTS;
+  if (npts) *npts = n;
+  if (!X || n == 0) return 0;
+  PCK(cudaSetDevice(ctx->device));
+  if (pft_tables(ctx) || ensure_edges(ctx, S)) return 1;
+  PftState *P = pft_state(ctx);
+  if (grow(ctx, P->dtab, P->tabCap, (size_t)3 * n)) return 1;
+  rhs_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const EdgeRec *)S.dedges, S.NE, P->dtcr20, P->dtab);
+  ctx->launches++;
+  PCK(cudaMemcpyAsync(X, P->dtab, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2hBytes += (size_t)3 * n * sizeof(double);
+  return 0;
+}
+
+int scuffcuda_assemble_rhs(scuffcuda_context *ctx, int ns, const double omega[2], int num_pw, const scuffcuda_planewave *pw,
+                           const double *tabulated_eh, int vec_handle, int offset)
+{ if (ns < 0 || ns >= (int)ctx->surfaces.size()) return pfail(ctx, "assemble_rhs: invalid surface index");
+  Matrix *V = find_matrix(ctx, vec_handle);
+  if (!V || V->NC != 1) return pfail(ctx, "assemble_rhs: invalid vector handle");
+  Surface &S = ctx->surfaces[ns];
+  const int nbf = S.isPEC ? S.NE : 2 * S.NE;
+  if (offset < 0 || offset + nbf > V->NR) return pfail(ctx, "assemble_rhs: surface does not fit the vector");
+  if (S.NE == 0) return 0;
+  PCK(cudaSetDevice(ctx->device));
+  if (pft_tables(ctx) || ensure_edges(ctx, S)) return 1;
+  PftState *P = pft_state(ctx);
+  RhsArgs A;
+  A.edges = (const EdgeRec *)S.dedges; A.NE = S.NE; A.tcr20 = P->dtcr20; A.npw = num_pw;
+  if (make_pw(ctx, omega, num_pw, pw, A.pw)) return 1;
+  A.tab = nullptr;
+  if (tabulated_eh)
+   { const size_t n = (size_t)S.NE * 2 * SC_TCR20_NPTS * 12;
+     if (grow(ctx, P->dtab, P->tabCap, n)) return 1;
+     PCK(cudaMemcpyAsync(P->dtab, tabulated_eh, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+     ctx->h2dBytes += n * sizeof(double);
+     A.tab = P->dtab; }
+  A.vec = V->d; A.isReal = V->isReal; A.offset = offset; A.isPEC = S.isPEC;
+  rhs_kernel<<<(S.NE + 3) / 4, 128, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  PCK(cudaGetLastError());
+  if (tabulated_eh) PCK(cudaStreamSynchronize(ctx->stream));    // the caller may reuse its host buffer
+  return 0;
+}
+
+int scuffcuda_pft_points(scuffcuda_context *ctx, int ns, double *X, long *npts)
+{ if (ns < 0 || ns >= (int)ctx->surfaces.size()) return pfail(ctx, "pft_points: invalid surface index");
+  Surface &S = ctx->surfaces[ns];
+  const long n = (long)S.NP * SC_TCR9_NPTS;
+  if (npts) *npts = n;
+  if (!X) return 0;
+  // the 21-point rule in the panel's own vertex order (GetPanelCubature, PanelCubature.cc:155-236)
+  for (int np = 0; np < S.NP; np++)
+   { const PanelRec &P = S.hpanels[np];
+     for (int p = 0; p < SC_TCR9_NPTS; p++)
+      for (int m = 0; m < 3; m++)
+       X[3 * ((size_t)np * SC_TCR9_NPTS + p) + m] = P.V[m] + SC_TCR9_H[3 * p] * (P.V[3 + m] - P.V[m]) + SC_TCR9_H[3 * p + 1] * (P.V[6 + m] - P.V[m]); }
+  return 0;
+}
+
+int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_args *a, double *scattered, double *extinction)
+{ const int NS = (int)ctx->surfaces.size();
+  if (!a || a->num_surfaces != NS) return pfail(ctx, "emtpft: num_surfaces does not match the device geometry");
+  Matrix *KN = find_matrix(ctx, kn_handle);
+  if (!KN || KN->NC != 1 || KN->isReal) return pfail(ctx, "emtpft: the solution vector must be a complex device vector");
+  if (a->omega[1] != 0.0 || !(a->omega[0] > 0.0)) return pfail(ctx, "emtpft: power/force/torque needs a real positive frequency (EMTPFT.cc:86-89 takes real parts)");
+  PCK(cudaSetDevice(ctx->device));
+  if (pft_tables(ctx)) return 1;
+  PftState *P = pft_state(ctx);
+  const int which = a->interior ? 1 : 0;
+  for (int i = 0; i < NS * NS * 11; i++) scattered[i] = 0.0;
+  for (int i = 0; i < NS * 11; i++) extinction[i] = 0.0;
+  // current points: order 4 (all surfaces), then order 9 (extinction)
+  std::vector<size_t> off4(NS + 1, 0), off9(NS + 1, 0);
+  for (int ns = 0; ns < NS; ns++) { off4[ns + 1] = off4[ns] + (size_t)ctx->surfaces[ns].NP * 6; off9[ns + 1] = off9[ns] + (size_t)ctx->surfaces[ns].NP * SC_TCR9_NPTS; }
+  if (grow(ctx, P->dcur, P->curCap, 2 * off4[NS] + off9[NS])) return 1;
+  for (int ns = 0; ns < NS; ns++)
+   { Surface &S = ctx->surfaces[ns];
+     const int nbf = S.isPEC ? S.NE : 2 * S.NE;
+     if (a->bf_offsets[ns] < 0 || a->bf_offsets[ns] + nbf > KN->NR) return pfail(ctx, "emtpft: basis-function offsets do not fit the vector");
+     if (ensure_edges(ctx, S)) return 1; }
+  CurPt *cur4 = P->dcur, *cur4k = P->dcur + off4[NS], *cur9 = P->dcur + 2 * off4[NS];
+  for (int ns = 0; ns < NS; ns++)
+   { Surface &S = ctx->surfaces[ns]; const int n4 = S.NP * 6, n9 = S.NP * SC_TCR9_NPTS;
+     // with N (pairs of two dielectric surfaces, extinction) and without (pairs involving a PEC surface: GetKNBilinears drops N)
+     pft_currents_kernel<<<(n4 + 127) / 128, 128, 0, ctx->stream>>>(S.dpanels, S.NP, P->dtcr4, 6, KN->d, a->bf_offsets[ns], S.isPEC, 1, cur4 + off4[ns]);
+     pft_currents_kernel<<<(n4 + 127) / 128, 128, 0, ctx->stream>>>(S.dpanels, S.NP, P->dtcr4, 6, KN->d, a->bf_offsets[ns], S.isPEC, 0, cur4k + off4[ns]);
+     pft_currents_kernel<<<(n9 + 127) / 128, 128, 0, ctx->stream>>>(S.dpanels, S.NP, P->dtcr9, SC_TCR9_NPTS, KN->d, a->bf_offsets[ns], S.isPEC, 1, cur9 + off9[ns]);
+     ctx->launches += 3; }
+  PCK(cudaGetLastError());
+  // ---- scattered part: ordered surface pairs (sa, sb) gated as the reference's loop over nea <= neb does (EMTPFT.cc:640-668)
+  for (int sa = 0; sa < NS; sa++)
+   for (int sb = 0; sb < NS; sb++)
+    { const int lo = std::min(sa, sb), hi = std::max(sa, sb);
+      const int *rl = a->region_indices + 2 * lo, *rh = a->region_indices + 2 * hi;
+      const int region = rl[which];
+      if (region == -1) continue;                       // no interior PFT for PEC bodies
+      double sign = 0.0;
+      if (lo == hi) sign = 1.0;
+      else if (rl[0] == rh[0]) sign = a->interior ? 0.0 : 1.0;
+      else if (rl[0] == rh[1]) sign = a->interior ? 0.0 : -1.0;
+      else if (rl[1] == rh[0]) sign = a->interior ? 1.0 : 0.0;
+      if (sign == 0.0) continue;
+      if (region < 0 || region >= a->num_regions) return pfail(ctx, "emtpft: invalid region index");
+      Surface &SA = ctx->surfaces[sa], &SB = ctx->surfaces[sb];
+      if (SA.NE == 0 || SB.NE == 0) continue;
+      typedef std::complex<double> cx;
+      const cx eps(a->eps_mu[4 * region], a->eps_mu[4 * region + 1]), mu(a->eps_mu[4 * region + 2], a->eps_mu[4 * region + 3]);
+      const cx kc = a->omega[0] * std::sqrt(eps * mu);
+      PftParams Q;
+      Q.k = kc.real(); Q.omega = a->omega[0]; Q.zmu = ZVAC * mu.real(); Q.eoz = eps.real() / ZVAC; Q.ook2 = 1.0 / (Q.k * Q.k);
+      for (int m = 0; m < 3; m++) Q.origin[m] = a->origins[3 * sa + m];
+      const bool hasN = !SA.isPEC && !SB.isPEC, same = (sa == sb);
+      const CurPt *CA = (hasN ? cur4 : cur4k) + off4[sa], *CB = (hasN ? cur4 : cur4k) + off4[sb];
+      const int nA = SA.NP * 6, nB = SB.NP * 6;
+      PftNearList &L = P->nearLists[std::make_pair(sa, sb)];
+      if (build_near_list(ctx, sa, sb, L)) return 1;
+      const int gx = (nA + PFT_THREADS - 1) / PFT_THREADS;
+      int gy = std::max(1, std::min((4 * ctx->smCount + gx - 1) / gx, (nB + PFT_TILE - 1) / PFT_TILE));
+      int chunk = (nB + gy - 1) / gy; chunk = ((chunk + PFT_TILE - 1) / PFT_TILE) * PFT_TILE; gy = (nB + chunk - 1) / chunk;
+      const int nearBlocks = (L.n + PFT_THREADS / 32 - 1) / (PFT_THREADS / 32);
+      const size_t nblocks = (size_t)gx * gy + nearBlocks;
+      if (grow(ctx, P->dpart, P->partCap, nblocks * PFT_NQ)) return 1;
+      PairArgs X; X.A = CA; X.nA = nA; X.B = CB; X.nB = nB; X.bChunk = chunk; X.Q = Q; X.part = P->dpart;
+      const dim3 grid(gx, gy);
+      if (hasN) { if (same) pft_pair_kernel<true, true><<<grid, PFT_THREADS, 0, ctx->stream>>>(X); else pft_pair_kernel<true, false><<<grid, PFT_THREADS, 0, ctx->stream>>>(X); }
+      else      { if (same) pft_pair_kernel<false, true><<<grid, PFT_THREADS, 0, ctx->stream>>>(X); else pft_pair_kernel<false, false><<<grid, PFT_THREADS, 0, ctx->stream>>>(X); }
+      ctx->launches++;
+      if (nearBlocks)
+       { NearPftArgs Y; Y.list = L.d; Y.n = L.n; Y.ea = (const EdgeRec *)SA.dedges; Y.eb = (const EdgeRec *)SB.dedges; Y.kn = KN->d;
+         Y.offA = a->bf_offsets[sa]; Y.offB = a->bf_offsets[sb]; Y.pecA = SA.isPEC; Y.pecB = SB.isPEC;
+         Y.tcr9 = P->dtcr9; Y.tcr4 = P->dtcr4; Y.Q = Q; Y.part = P->dpart + (size_t)gx * gy * PFT_NQ;
+         if (hasN) { if (same) pft_near_kernel<true, true><<<nearBlocks, PFT_THREADS, 0, ctx->stream>>>(Y); else pft_near_kernel<true, false><<<nearBlocks, PFT_THREADS, 0, ctx->stream>>>(Y); }
+         else      { if (same) pft_near_kernel<false, true><<<nearBlocks, PFT_THREADS, 0, ctx->stream>>>(Y); else pft_near_kernel<false, false><<<nearBlocks, PFT_THREADS, 0, ctx->stream>>>(Y); }
+         ctx->launches++; }
+      PCK(cudaGetLastError());
+      double q[PFT_NQ];
+      if (sum_partials(ctx, P->dpart, nblocks, q)) return 1;
+      // DeltaPFTT[sa][sb] += 0.5 Sign dPFTT, dPFTT itself carrying Sign (EMTPFT.cc:689-725): Sign^2 = 1
+      double *out = scattered + ((size_t)sa * NS + sb) * 11;
+      out[1] = 0.5 * q[0];
+      for (int m = 0; m < 9; m++) out[2 + m] = 0.5 * q[1 + m]; }
+  // ---- extinction (only the head of the incident-field chain, EMTPFT.cc:499-511)
+  if (a->if_region >= 0 && (a->num_pw > 0 || a->tabulated_ehd))
+   { ExtArgs E; E.havePW = 0;
+     if (a->num_pw > 0) { if (make_pw(ctx, a->omega, 1, a->pw, &E.pw)) return 1; E.pw.sign = 1.0; E.havePW = 1; }
+     size_t tabOff = 0;
+     for (int ns = 0; ns < NS; ns++)
+      { Surface &S = ctx->surfaces[ns]; const int nA = S.NP * SC_TCR9_NPTS;
+        const size_t myTab = tabOff; tabOff += (size_t)nA * 48;
+        if (a->if_region != a->region_indices[2 * ns + which] || nA == 0) continue;
+        E.A = cur9 + off9[ns]; E.nA = nA; E.tab = nullptr;
+        if (a->tabulated_ehd)
+         { if (grow(ctx, P->dtab, P->tabCap, (size_t)nA * 48)) return 1;
+           PCK(cudaMemcpyAsync(P->dtab, a->tabulated_ehd + myTab, (size_t)nA * 48 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+           ctx->h2dBytes += (size_t)nA * 48 * sizeof(double);
+           E.tab = P->dtab; }
+        for (int m = 0; m < 3; m++) E.origin[m] = a->origins[3 * ns + m];
+        const int nb = (nA + PFT_THREADS - 1) / PFT_THREADS;
+        if (grow(ctx, P->dpart, P->partCap, (size_t)nb * PFT_NQ)) return 1;
+        E.part = P->dpart;
+        pft_ext_kernel<<<nb, PFT_THREADS, 0, ctx->stream>>>(E);
+        ctx->launches++;
+        PCK(cudaGetLastError());
+        double q[PFT_NQ];
+        if (sum_partials(ctx, P->dpart, nb, q)) return 1;
+        const double PFactor = 0.5, FTFactor = 0.5 * TENTHIRDS / a->omega[0];
+        double *out = extinction + (size_t)ns * 11;
+        out[0] = PFactor * q[0];
+        for (int m = 0; m < 9; m++) out[2 + m] = FTFactor * q[1 + m]; } }
+  return 0;
+}
+
+}  // extern "C"

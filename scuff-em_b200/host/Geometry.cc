@@ -304,7 +304,8 @@ char *RWGSurface::InitRWGSurface(std::vector<double> &VC, std::vector<int> &PVI)
   if (NumVertices == 0 || PVI.empty()) return vstrdup("%s: mesh has no vertices or no triangles", MeshFileName);
   Vertices = (double *)malloc(3 * NumVertices * sizeof(double));
   memcpy(Vertices, &VC[0], 3 * NumVertices * sizeof(double));
-  if (OTGT) ((GTrans *)OTGT)->Apply(Vertices, NumVertices);
+  Origin[0] = Origin[1] = Origin[2] = 0.0;
+  if (OTGT) { ((GTrans *)OTGT)->Apply(Vertices, NumVertices); ((GTrans *)OTGT)->Apply(Origin, 1); }
   NumPanels = PVI.size() / 3;
   Panels = (RWGPanel **)malloc(NumPanels * sizeof(RWGPanel *));
   for (int np = 0; np < NumPanels; np++)
@@ -389,6 +390,7 @@ static void ApplyGT(RWGSurface *S, const GTrans *D)
 { D->Apply(S->Vertices, S->NumVertices);
   for (int ne = 0; ne < S->NumEdges; ne++) D->Apply(S->Edges[ne]->Centroid, 1);
   for (int ne = 0; ne < S->NumHalfRWGEdges; ne++) D->Apply(S->HalfRWGEdges[ne]->Centroid, 1);
+  D->Apply(S->Origin, 1);
   S->UpdatePanels();
   if (!S->GT) S->GT = new GTrans(*D); else ((GTrans *)S->GT)->Transform(D);
 }
@@ -410,6 +412,7 @@ void RWGSurface::UnTransform()
   G->UnApply(Vertices, NumVertices);
   for (int ne = 0; ne < NumEdges; ne++) G->UnApply(Edges[ne]->Centroid, 1);
   for (int ne = 0; ne < NumHalfRWGEdges; ne++) G->UnApply(HalfRWGEdges[ne]->Centroid, 1);
+  G->UnApply(Origin, 1);
   G->Reset();
   UpdatePanels();
 }

@@ -1,0 +1,302 @@
+// One frequency point of a scattering run on the device: HVector, the incident-field classes,
+// AssembleRHSVector, LUSolve on a device-resident vector and GetPFT / GetPFTMatrix / GetEMTPFTMatrix — the calls
+// scuff-scatter makes after AssembleBEMMatrix (applications/scuff-scatter/scuff-scatter.cc:466-520).  Same names, argument
+// meaning and error behaviour as the reference (libs/libhmat/libhmat.h:95-160, libs/libIncField/libIncField.h,
+// libs/libscuff/AssembleRHSVector.cc, GetPFT.cc, EMTPFT.cc); the arithmetic runs in csrc/rhs_pft.cu through the C ABI.
+// Host work here is O(number of surfaces): which fields act on which surface with which sign, material values, and the
+// final combination of the 11 sums per surface pair into the 8 PFT numbers per surface (EMTPFT.cc:826-856).
+#include <cstdlib>
+#include <vector>
+#include <thread>
+#include <functional>
+#include "host_internal.h"
+
+#define ZVAC 376.73031346177
+#define II cdouble(0.0, 1.0)
+
+namespace scuff {
+
+// user-supplied incident fields are evaluated on host threads (IncField::GetFields is the caller's code)
+static void ParallelFor(long n, const std::function<void(long)> &f)
+{ int nt = (int)std::thread::hardware_concurrency(); if (nt < 1) nt = 1; if (nt > 32) nt = 32;
+  if (n < 4096 || nt == 1) { for (long i = 0; i < n; i++) f(i); return; }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; t++) pool.emplace_back([=, &f]() { for (long i = t; i < n; i += nt) f(i); });
+  for (auto &th : pool) th.join();
+}
+
+// ---- HVector -------------------------------------------------------------------------------------------------------------
+HVector::HVector(int pN, int pRealComplex, void *data) : HMatrix(pN, 1, pRealComplex, LHM_NORMAL, data)
+{ N = pN; DV = DM; ZV = ZM; }
+cdouble HVector::GetEntry(int n) { return HMatrix::GetEntry((size_t)n, 0); }
+double HVector::GetEntryD(int n) { return HMatrix::GetEntryD((size_t)n, 0); }
+void HVector::SetEntry(int n, cdouble Entry) { HMatrix::SetEntry((size_t)n, 0, Entry); }
+void HVector::SetEntry(int n, double Entry) { HMatrix::SetEntry((size_t)n, 0, Entry); }
+void HVector::AddEntry(int n, cdouble Entry) { HMatrix::AddEntry((size_t)n, 0, Entry); }
+void HVector::AddEntry(int n, double Entry) { HMatrix::AddEntry((size_t)n, 0, Entry); }
+void HVector::Copy(HVector *V)
+{ if (V->N != N || V->RealComplex != RealComplex) ErrExit("HVector::Copy: size/type mismatch");
+  if (V->DeviceHandle && V->HostStale)                 // the source lives in HBM: copy there
+   { scuffcuda_context *ctx = GetCudaContext();
+     EnsureDevice();
+     if (scuffcuda_matrix_copy(ctx, DeviceHandle, V->DeviceHandle)) ErrExit("%s", scuffcuda_last_error(ctx));
+     HostStale = true; DeviceStale = false;
+     return; }
+  MarkHostDirty();
+  if (RealComplex == LHM_REAL) memcpy(DV, V->DV, N * sizeof(double)); else memcpy(ZV, V->ZV, N * sizeof(cdouble));
+}
+
+int HMatrix::LUSolve(HVector *X)
+{ scuffcuda_context *ctx = GetCudaContext();
+  if (!DeviceHandle) ErrExit("LUSolve: matrix has not been LU-factorized");
+  if (DeviceStale) ErrExit("LUSolve: the matrix was modified on the host after LUFactorize()");
+  if (X->NR != NR || X->RealComplex != RealComplex) ErrExit("LUSolve: dimension/type mismatch");
+  X->PrepareDevice();
+  if (scuffcuda_lu_solve_device(ctx, DeviceHandle, X->DeviceHandle)) ErrExit("%s", scuffcuda_last_error(ctx));
+  X->HostStale = true;
+  return 0;
+}
+
+// ---- incident fields -----------------------------------------------------------------------------------------------------
+IncField::IncField()
+{ Eps = cdouble(1.0, 0.0); Mu = cdouble(1.0, 0.0); Omega = -1.0; RegionLabel = 0; RegionIndex = 0; Next = 0; }
+IncField::~IncField() { if (RegionLabel) free(RegionLabel); }
+void DeleteIncFieldChain(IncField *IF)
+{ while (IF) { IncField *N = IF->Next; delete IF; IF = N; } }
+void IncField::SetFrequency(cdouble pOmega, bool Traverse)
+{ Omega = pOmega;
+  if (Traverse) for (IncField *I = Next; I; I = I->Next) I->Omega = pOmega; }
+void IncField::SetFrequencyAndEpsMu(cdouble pOmega, cdouble pEps, cdouble pMu, bool Traverse)
+{ Omega = pOmega; Eps = pEps; Mu = pMu;
+  if (Traverse) for (IncField *I = Next; I; I = I->Next) { I->Omega = pOmega; I->Eps = pEps; I->Mu = pMu; } }
+void IncField::SetRegionLabel(const char *Label)
+{ if (RegionLabel) free(RegionLabel);
+  RegionLabel = Label ? strdup(Label) : 0;
+  if (!Label) RegionIndex = 0; }
+void IncField::GetTotalFields(const double X[3], cdouble EH[6])
+{ for (int n = 0; n < 6; n++) EH[n] = 0.0;
+  for (IncField *I = this; I; I = I->Next)
+   { cdouble P[6]; I->GetFields(X, P); for (int n = 0; n < 6; n++) EH[n] += P[n]; } }
+// central differences with the reference's step (IncField.cc:178-198)
+void IncField::GetFieldGradients(const double X[3], cdouble dEH[3][6])
+{ cdouble EHP[6], EHM[6];
+  for (int i = 0; i < 3; i++)
+   { double x[3] = { X[0], X[1], X[2] };
+     const double Delta = (X[i] == 0.0 ? 1.0e-4 : 1.0e-4 * fabs(X[i]));
+     x[i] += Delta; GetFields(x, EHP);
+     x[i] -= 2.0 * Delta; GetFields(x, EHM);
+     for (int j = 0; j < 6; j++) dEH[i][j] = (EHP[j] - EHM[j]) / (2.0 * Delta); } }
+
+PlaneWave::PlaneWave(const cdouble pE0[3], const double pnHat[3], const char *Label)
+{ memcpy(E0, pE0, 3 * sizeof(cdouble)); memcpy(nHat, pnHat, 3 * sizeof(double)); SetRegionLabel(Label); }
+void PlaneWave::SetE0(cdouble pE0[3]) { memcpy(E0, pE0, 3 * sizeof(cdouble)); }
+void PlaneWave::SetnHat(double pnHat[3]) { memcpy(nHat, pnHat, 3 * sizeof(double)); }
+// host evaluation for callers that ask for the field itself (the device evaluates the same formula in rhs_pft.cu)
+void PlaneWave::GetFields(const double X[3], cdouble EH[6])
+{ const cdouble K = sqrt(Eps * Mu) * Omega, Z = ZVAC * sqrt(Mu / Eps);
+  const cdouble ExpFac = exp(II * K * (nHat[0] * X[0] + nHat[1] * X[1] + nHat[2] * X[2]));
+  for (int m = 0; m < 3; m++) EH[m] = E0[m] * ExpFac;
+  EH[3] = (nHat[1] * EH[2] - nHat[2] * EH[1]) / Z;
+  EH[4] = (nHat[2] * EH[0] - nHat[0] * EH[2]) / Z;
+  EH[5] = (nHat[0] * EH[1] - nHat[1] * EH[0]) / Z; }
+void PlaneWave::GetFieldGradients(const double X[3], cdouble dEH[3][6])
+{ cdouble EH[6]; GetFields(X, EH);
+  const cdouble K = sqrt(Eps * Mu) * Omega;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 6; j++) dEH[i][j] = II * K * nHat[i] * EH[j]; }
+
+PointSource::PointSource(const double pX0[3], const cdouble pP[3], int pType, const char *Label)
+{ memcpy(X0, pX0, 3 * sizeof(double)); memcpy(P, pP, 3 * sizeof(cdouble)); Type = pType; SetRegionLabel(Label); }
+bool PointSource::GetSourcePoint(double X[3]) const { memcpy(X, X0, 3 * sizeof(double)); return true; }
+// fields of a point dipole in a homogeneous medium (PointSource.cc:118-175); P = dipole moment / eps_0
+void PointSource::GetFields(const double X[3], cdouble EH[6])
+{ double RHat[3] = { X[0] - X0[0], X[1] - X0[1], X[2] - X0[2] };
+  const double R = sqrt(RHat[0] * RHat[0] + RHat[1] * RHat[1] + RHat[2] * RHat[2]);
+  for (int m = 0; m < 3; m++) RHat[m] /= R;
+  const cdouble PDotR = P[0] * RHat[0] + P[1] * RHat[1] + P[2] * RHat[2];
+  const cdouble RCrossP[3] = { RHat[1] * P[2] - RHat[2] * P[1], RHat[2] * P[0] - RHat[0] * P[2], RHat[0] * P[1] - RHat[1] * P[0] };
+  const cdouble k = Omega * sqrt(Eps * Mu), ikr = II * k * R, ikr2 = ikr * ikr;
+  cdouble ExpFac = k * k * exp(ikr) / (4.0 * M_PI * R);
+  const cdouble Z = ZVAC * sqrt(Mu / Eps);
+  const cdouble Term1 = 1.0 - 1.0 / ikr + 1.0 / ikr2, Term2 = (-1.0 + 3.0 / ikr - 3.0 / ikr2) * PDotR, Term3 = (1.0 - 1.0 / ikr);
+  if (Type == LIF_ELECTRIC_DIPOLE)
+   { ExpFac /= Eps;
+     for (int m = 0; m < 3; m++) { EH[m] = ExpFac * (Term1 * P[m] + Term2 * RHat[m]); EH[3 + m] = ExpFac * Term3 * RCrossP[m] / Z; } }
+  else
+   { ExpFac /= Mu;
+     for (int m = 0; m < 3; m++) { EH[m] = -1.0 * Z * ExpFac * Term3 * RCrossP[m]; EH[3 + m] = ExpFac * (Term1 * P[m] + Term2 * RHat[m]); } }
+}
+
+// ---- right-hand side ---------------------------------------------------------------------------------------------------
+int RWGGeometry::GetRegionIndex(const double X[3])
+{ if (LBasis) ErrExit("GetRegionIndex: point sources in periodic geometries are not supported on the device path");
+  if (!AllSurfacesClosed) ErrExit("GetRegionIndex: geometries with open surfaces need an explicit region label for the incident field");
+  for (int i = NumSurfaces - 1; i >= 0; --i) if (Surfaces[i]->Contains(X)) return Surfaces[i]->RegionIndices[1];
+  return 0;
+}
+
+// AssembleRHSVector.cc:62-118
+int RWGGeometry::UpdateIncFields(IncField *IFList, cdouble Omega, double *kBloch)
+{ if (IFList == 0) return 0;
+  if ((LBasis == 0 && kBloch != 0) || (LBasis != 0 && kBloch == 0)) ErrExit("%s:%i: internal error", __FILE__, __LINE__);
+  if (LBasis) ErrExit("AssembleRHSVector: incident fields in periodic geometries are not on the device path yet (Bloch-periodic sources)");
+  UpdateCachedEpsMuValues(Omega);
+  int NIF = 0;
+  for (IncField *IF = IFList; IF; NIF++, IF = IF->Next)
+   { double X[3];
+     if (IF->GetSourcePoint(X)) IF->RegionIndex = GetRegionIndex(X);
+     else if (IF->RegionLabel) IF->RegionIndex = GetRegionByLabel(IF->RegionLabel);
+     else IF->RegionIndex = 0;
+     if (IF->RegionIndex < 0 || IF->RegionIndex > NumRegions) ErrExit("invalid region index %i", IF->RegionIndex);
+     IF->SetFrequencyAndEpsMu(Omega, EpsTF[IF->RegionIndex], MuTF[IF->RegionIndex], false); }
+  return NIF;
+}
+
+HVector *RWGGeometry::AllocateRHSVector(bool PureImagFreq)
+{ return new HVector(TotalBFs, (PureImagFreq && LBasis == 0) ? LHM_REAL : LHM_COMPLEX); }
+
+static void FillPlaneWave(scuffcuda_planewave &W, PlaneWave *PW, double Sign)
+{ for (int m = 0; m < 3; m++) { W.e0[2 * m] = real(PW->E0[m]); W.e0[2 * m + 1] = imag(PW->E0[m]); W.nhat[m] = PW->nHat[m]; }
+  W.eps[0] = real(PW->Eps); W.eps[1] = imag(PW->Eps); W.mu[0] = real(PW->Mu); W.mu[1] = imag(PW->Mu); W.sign = Sign; }
+
+HVector *RWGGeometry::AssembleRHSVector(cdouble Omega, double *kBloch, IncField *IFList, HVector *RHS)
+{ if (RHS == NULL) RHS = AllocateRHSVector();
+  if (RHS->N != TotalBFs) ErrExit("AssembleRHSVector: wrong-size RHS vector");
+  RHS->Zero();
+  UpdateIncFields(IFList, Omega, kBloch);
+  SyncDeviceGeometry();
+  scuffcuda_context *ctx = GetCudaContext();
+  RHS->PrepareDevice();
+  const double omega[2] = { real(Omega), imag(Omega) };
+  for (int ns = 0; ns < NumSurfaces; ns++)
+   { RWGSurface *S = Surfaces[ns];
+     if (S->NumEdges == 0) continue;
+     // fields with sources in the surface's exterior region enter with a minus sign, interior region with a plus sign
+     // (AssembleRHSVector.cc:297-306); plane waves go to the device as parameters, everything else as values at its points
+     std::vector<scuffcuda_planewave> PWs; std::vector<std::pair<IncField *, double> > Others;
+     for (IncField *IF = IFList; IF; IF = IF->Next)
+      { double Sign = 0.0;
+        if (S->RegionIndices[0] == IF->RegionIndex) Sign = -1.0;
+        else if (S->RegionIndices[1] == IF->RegionIndex) Sign = +1.0;
+        else continue;
+        PlaneWave *PW = dynamic_cast<PlaneWave *>(IF);
+        if (PW && PWs.size() < 8) { scuffcuda_planewave W; FillPlaneWave(W, PW, Sign); PWs.push_back(W); }
+        else Others.push_back(std::make_pair(IF, Sign)); }
+     if (PWs.empty() && Others.empty()) continue;
+     std::vector<double> Tab;
+     if (!Others.empty())
+      { long npts = 0;
+        if (scuffcuda_rhs_points(ctx, ns, 0, &npts)) ErrExit("%s", scuffcuda_last_error(ctx));
+        std::vector<double> X(3 * (size_t)npts); Tab.assign(12 * (size_t)npts, 0.0);
+        if (scuffcuda_rhs_points(ctx, ns, X.data(), &npts)) ErrExit("%s", scuffcuda_last_error(ctx));
+        ParallelFor(npts, [&](long n)
+         { for (size_t i = 0; i < Others.size(); i++)
+            { cdouble EH[6]; Others[i].first->GetFields(&X[3 * n], EH);
+              for (int q = 0; q < 6; q++) { Tab[12 * n + 2 * q] += Others[i].second * real(EH[q]); Tab[12 * n + 2 * q + 1] += Others[i].second * imag(EH[q]); } } }); }
+     if (scuffcuda_assemble_rhs(ctx, ns, omega, (int)PWs.size(), PWs.data(), Tab.empty() ? 0 : Tab.data(), RHS->DeviceHandle, BFIndexOffset[ns]))
+      ErrExit("%s", scuffcuda_last_error(ctx)); }
+  RHS->HostStale = true; RHS->DeviceStale = false;
+  if (UseHRWGFunctions) ErrExit("AssembleRHSVector: half-RWG basis functions are not supported on the device path");
+  return RHS;
+}
+HVector *RWGGeometry::AssembleRHSVector(cdouble Omega, IncField *IF, HVector *RHS) { return AssembleRHSVector(Omega, 0, IF, RHS); }
+
+// ---- power, force, torque ------------------------------------------------------------------------------------------------
+PFTOptions *InitPFTOptions(PFTOptions *Options)
+{ if (Options == 0) Options = (PFTOptions *)calloc(1, sizeof(PFTOptions));
+  Options->PFTMethod = SCUFF_PFT_DEFAULT; Options->IF = 0; Options->DRMatrix = 0; Options->kBloch = 0; Options->RHSVector = 0;
+  Options->Interior = false; Options->EMTPFTIMethod = SCUFF_EMTPFTI_DEFAULT; Options->Itemize = false; Options->GetRegionPFTs = false;
+  return Options;
+}
+
+#define NUMPFTT 11
+HMatrix *GetEMTPFTMatrix(RWGGeometry *G, cdouble Omega, IncField *IF, HVector *KN, HMatrix *DRMatrix, HMatrix *PFTMatrix,
+                         bool Interior, int EMTPFTIMethod, bool Itemize)
+{ const char *sss = getenv("SCUFF_EMTPFTI_METHOD");
+  if (sss) sscanf(sss, "%i", &EMTPFTIMethod);
+  const int NS = G->NumSurfaces;
+  if (PFTMatrix == 0 || PFTMatrix->NR != NS || PFTMatrix->NC != NUMPFT) ErrExit("invalid PFTMatrix in GetEMTPFT");
+  if (EMTPFTIMethod != SCUFF_EMTPFTI_EHDERIVATIVES1)
+   ErrExit("GetEMTPFTMatrix: only the cubature integrals (EMTPFTIMethod = SCUFF_EMTPFTI_EHDERIVATIVES1 = 0, or SCUFF_EMTPFTI_METHOD=0) are "
+           "available on the device path; method %i (GetGCMatrixElements + FIBBI cache) is not", EMTPFTIMethod);
+  if (DRMatrix) ErrExit("GetEMTPFTMatrix: the Rytov-matrix (non-equilibrium) form is not available on the device path");
+  if (KN == 0) ErrExit("GetEMTPFTMatrix: no solution vector");
+  if (Itemize || (getenv("SCUFF_ITEMIZE_PFT") && getenv("SCUFF_ITEMIZE_PFT")[0] == '1')) Warn("GetEMTPFTMatrix: itemized output files are not written by the device path");
+  if (G->LBasis) ErrExit("GetEMTPFTMatrix: periodic geometries are not supported");
+  G->SyncDeviceGeometry();
+  scuffcuda_context *ctx = GetCudaContext();
+  KN->PrepareDevice();
+  G->UpdateCachedEpsMuValues(Omega);
+  std::vector<int> Regions(2 * NS), Offsets(NS); std::vector<double> Origins(3 * NS), EpsMu(4 * G->NumRegions);
+  for (int ns = 0; ns < NS; ns++)
+   { Regions[2 * ns] = G->Surfaces[ns]->RegionIndices[0]; Regions[2 * ns + 1] = G->Surfaces[ns]->RegionIndices[1];
+     Offsets[ns] = G->BFIndexOffset[ns];
+     for (int m = 0; m < 3; m++) Origins[3 * ns + m] = G->Surfaces[ns]->Origin[m]; }
+  for (int nr = 0; nr < G->NumRegions; nr++)
+   { cdouble Eps, Mu; G->RegionMPs[nr]->GetEpsMu(Omega, &Eps, &Mu);
+     EpsMu[4 * nr] = real(Eps); EpsMu[4 * nr + 1] = imag(Eps); EpsMu[4 * nr + 2] = real(Mu); EpsMu[4 * nr + 3] = imag(Mu); }
+  scuffcuda_pft_args A; memset(&A, 0, sizeof A);
+  A.omega[0] = real(Omega); A.omega[1] = imag(Omega); A.interior = Interior ? 1 : 0; A.num_surfaces = NS;
+  A.region_indices = Regions.data(); A.bf_offsets = Offsets.data(); A.origins = Origins.data();
+  A.num_regions = G->NumRegions; A.eps_mu = EpsMu.data(); A.if_region = -1;
+  scuffcuda_planewave W; std::vector<double> Tab;
+  if (IF)
+   { A.if_region = IF->RegionIndex;
+     PlaneWave *PW = dynamic_cast<PlaneWave *>(IF);
+     if (PW) { FillPlaneWave(W, PW, 1.0); A.num_pw = 1; A.pw = &W; }
+     else
+      { // any other incident field: its own GetFields / GetFieldGradients at the device's cubature points (EMTPFT.cc:389-436)
+        size_t total = 0; std::vector<size_t> first(NS);
+        for (int ns = 0; ns < NS; ns++) { long n = 0; if (scuffcuda_pft_points(ctx, ns, 0, &n)) ErrExit("%s", scuffcuda_last_error(ctx)); first[ns] = total; total += (size_t)n; }
+        std::vector<double> X(3 * total); Tab.assign(48 * total, 0.0);
+        for (int ns = 0; ns < NS; ns++) { long n = 0; if (scuffcuda_pft_points(ctx, ns, &X[3 * first[ns]], &n)) ErrExit("%s", scuffcuda_last_error(ctx)); }
+        ParallelFor((long)total, [&](long n)
+         { cdouble EH[6], dEH[3][6]; IF->GetFields(&X[3 * n], EH); IF->GetFieldGradients(&X[3 * n], dEH);
+           double *t = &Tab[48 * n];
+           for (int q = 0; q < 6; q++) { t[2 * q] = real(EH[q]); t[2 * q + 1] = imag(EH[q]); }
+           for (int m = 0; m < 3; m++) for (int q = 0; q < 6; q++) { t[12 + 12 * m + 2 * q] = real(dEH[m][q]); t[13 + 12 * m + 2 * q] = imag(dEH[m][q]); } });
+        A.tabulated_ehd = Tab.data(); } }
+  std::vector<double> Scat((size_t)NS * NS * NUMPFTT), Ext((size_t)NS * NUMPFTT);
+  if (scuffcuda_emtpft(ctx, KN->DeviceHandle, &A, Scat.data(), Ext.data())) ErrExit("%s", scuffcuda_last_error(ctx));
+  // Q_full = Q_extinction - Q_scattered (except the scattered power itself); the two torque terms add (EMTPFT.cc:826-856)
+  PFTMatrix->Zero();
+  for (int nsa = 0; nsa < NS; nsa++)
+   for (int nq = 0; nq < NUMPFT; nq++)
+    { double v = Ext[nsa * NUMPFTT + nq];
+      for (int nsb = 0; nsb < NS; nsb++)
+       { const double *s = &Scat[((size_t)nsa * NS + nsb) * NUMPFTT];
+         if (nq == PFT_PABS) v += -1.0 * s[PFT_PSCAT];
+         else if (nq == PFT_PSCAT) v += s[PFT_PSCAT];
+         else v += -1.0 * s[nq]; }
+      if (PFT_XTORQUE <= nq && nq <= PFT_ZTORQUE)
+       { v += Ext[nsa * NUMPFTT + nq + 3];
+         for (int nsb = 0; nsb < NS; nsb++) v += -1.0 * Scat[((size_t)nsa * NS + nsb) * NUMPFTT + nq + 3]; }
+      PFTMatrix->SetEntry(nsa, nq, v); }
+  if (Interior) for (int ns = 0; ns < NS; ns++) PFTMatrix->SetEntry(ns, PFT_PSCAT, 0.0);
+  return PFTMatrix;
+}
+
+void RWGGeometry::GetPFT(int SurfaceIndex, HVector *KN, cdouble Omega, double PFT[NUMPFT], PFTOptions *Options)
+{ PFTOptions Default; if (Options == 0) { Options = &Default; InitPFTOptions(Options); }
+  if (SurfaceIndex < 0 || SurfaceIndex >= NumSurfaces) ErrExit("GetPFT: invalid surface index %i", SurfaceIndex);
+  if (Options->PFTMethod == SCUFF_PFT_EMT_EXTERIOR || Options->PFTMethod == SCUFF_PFT_EMT_INTERIOR)
+   { HMatrix *PFTMatrix = new HMatrix(NumSurfaces, NUMPFT);
+     GetEMTPFTMatrix(this, Omega, Options->IF, KN, Options->DRMatrix, PFTMatrix,
+                     Options->Interior || Options->PFTMethod == SCUFF_PFT_EMT_INTERIOR, Options->EMTPFTIMethod);
+     for (int nq = 0; nq < NUMPFT; nq++) PFT[nq] = PFTMatrix->GetEntryD(SurfaceIndex, nq);
+     delete PFTMatrix; }
+  else ErrExit("GetPFT: PFT method %i is not available on the device path (only the energy/momentum-transfer method, SCUFF_PFT_EMT)", Options->PFTMethod);
+}
+
+HMatrix *RWGGeometry::GetPFTMatrix(HVector *KN, cdouble Omega, PFTOptions *Options, HMatrix *PFTMatrix)
+{ PFTOptions Default; if (Options == 0) { Options = &Default; InitPFTOptions(Options); }
+  if (PFTMatrix && (PFTMatrix->NR != NumSurfaces || PFTMatrix->NC != NUMPFT))
+   { Warn("wrong-size PFTMatrix in GetPFTMatrix (reallocating...)"); delete PFTMatrix; PFTMatrix = 0; }
+  if (PFTMatrix == 0) PFTMatrix = new HMatrix(NumSurfaces, NUMPFT);
+  if (Options->PFTMethod == SCUFF_PFT_EMT_EXTERIOR || Options->PFTMethod == SCUFF_PFT_EMT_INTERIOR)
+   GetEMTPFTMatrix(this, Omega, Options->IF, KN, Options->DRMatrix, PFTMatrix,
+                   Options->Interior || Options->PFTMethod == SCUFF_PFT_EMT_INTERIOR, Options->EMTPFTIMethod);
+  else ErrExit("GetPFTMatrix: PFT method %i is not available on the device path (only SCUFF_PFT_EMT)", Options->PFTMethod);
+  return PFTMatrix;
+}
+
+}  // namespace scuff

@@ -132,4 +132,28 @@ int scuffb200_clear_cache() { GUARD(if (scuffcuda_fippi_clear(GetCudaContext()))
 long scuffb200_cache_records() { long n = 0; GUARD(scuffcuda_fippi_num_records(GetCudaContext(), &n); return n;, -1) }
 int scuffb200_set_disable_cache(int v) { RWGGeometry::DisableCache = (v != 0); return 0; }
 
+/* ---- scattering run (Scatter.cc): vectors, incident fields, RHS, solve, PFT ---- */
+void *scuffb200_vector_new(int n, int is_real) { GUARD(return (void *)(HMatrix *)new HVector(n, is_real ? LHM_REAL : LHM_COMPLEX);, 0) }
+void scuffb200_vector_free(void *v) { delete (HVector *)(HMatrix *)v; }
+void *scuffb200_planewave_new(const double *e0, const double *nhat, const char *label)
+{ cdouble E0[3]; for (int m = 0; m < 3; m++) E0[m] = cdouble(e0[2 * m], e0[2 * m + 1]);
+  GUARD(return (void *)(IncField *)new PlaneWave(E0, nhat, (label && label[0]) ? label : 0);, 0) }
+void *scuffb200_pointsource_new(const double *x0, const double *p, int type, const char *label)
+{ cdouble P[3]; for (int m = 0; m < 3; m++) P[m] = cdouble(p[2 * m], p[2 * m + 1]);
+  GUARD(return (void *)(IncField *)new PointSource(x0, P, type, (label && label[0]) ? label : 0);, 0) }
+void scuffb200_incfield_set_next(void *a, void *b) { ((IncField *)a)->Next = (IncField *)b; }
+void scuffb200_incfield_free(void *a) { delete (IncField *)a; }
+int scuffb200_assemble_rhs(void *g, double wr, double wi, void *incfield, void *vec)
+{ GUARD(((RWGGeometry *)g)->AssembleRHSVector(cdouble(wr, wi), (IncField *)incfield, (HVector *)(HMatrix *)vec); return 0;, 1) }
+int scuffb200_lu_solve_vector(void *m, void *vec) { GUARD(return ((HMatrix *)m)->LUSolve((HVector *)(HMatrix *)vec);, 1) }
+int scuffb200_vector_copy(void *dst, void *src) { GUARD(((HVector *)(HMatrix *)dst)->Copy((HVector *)(HMatrix *)src); return 0;, 1) }
+/* out: NumSurfaces x 8, row-major */
+int scuffb200_get_pft_matrix(void *g, void *kn, double wr, double wi, void *incfield, int interior, int method, double *out)
+{ GUARD(RWGGeometry *G = (RWGGeometry *)g;
+        PFTOptions Opts; InitPFTOptions(&Opts); Opts.IF = (IncField *)incfield; Opts.Interior = (interior != 0); Opts.EMTPFTIMethod = method;
+        HMatrix *P = G->GetPFTMatrix((HVector *)(HMatrix *)kn, cdouble(wr, wi), &Opts, 0);
+        for (int ns = 0; ns < G->NumSurfaces; ns++) for (int nq = 0; nq < NUMPFT; nq++) out[ns * NUMPFT + nq] = P->GetEntryD(ns, nq);
+        delete P; return 0;, 1) }
+int scuffb200_surface_origin(void *g, int ns, double *out) { for (int m = 0; m < 3; m++) out[m] = ((RWGGeometry *)g)->Surfaces[ns]->Origin[m]; return 0; }
+
 }  // extern "C"

@@ -147,6 +147,20 @@ def host_lib():
         L.scuffb200_store_cache.argtypes = [C.c_char_p]
         L.scuffb200_set_device.argtypes = [C.c_int]
         L.scuffb200_cache_records.restype = C.c_long
+        L.scuffb200_vector_new.restype = C.c_void_p
+        L.scuffb200_vector_new.argtypes = [C.c_int, C.c_int]
+        L.scuffb200_vector_free.argtypes = [C.c_void_p]
+        L.scuffb200_planewave_new.restype = C.c_void_p
+        L.scuffb200_planewave_new.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        L.scuffb200_pointsource_new.restype = C.c_void_p
+        L.scuffb200_pointsource_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_char_p]
+        L.scuffb200_incfield_set_next.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_incfield_free.argtypes = [C.c_void_p]
+        L.scuffb200_assemble_rhs.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.scuffb200_lu_solve_vector.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_vector_copy.argtypes = [C.c_void_p, C.c_void_p]
+        L.scuffb200_get_pft_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.scuffb200_surface_origin.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         _host = L
     return _host
 
@@ -258,14 +272,101 @@ class HMatrix:
     def lu_solve(self, X):
         _check(host_lib().scuffb200_lu_solve(self.ptr, X.ptr))
 
+    def lu_solve_vector(self, X):
+        """HMatrix::LUSolve(HVector *): solves in HBM, the vector is not copied through the host"""
+        _check(host_lib().scuffb200_lu_solve_vector(self.ptr, X.ptr))
+
     def __del__(self):
         if getattr(self, "owner", False) and self.ptr and _host is not None:
             _host.scuffb200_matrix_free(self.ptr)
             self.ptr = None
 
 
+class HVector(HMatrix):
+    """scuff::HVector (an N x 1 HMatrix with the same device twin); .array has shape (N,)"""
+
+    @classmethod
+    def new(cls, n, is_real=False):
+        p = host_lib().scuffb200_vector_new(int(n), int(is_real))
+        if not p:
+            raise ScuffError(host_lib().scuffb200_last_error().decode())
+        return cls(p)
+
+    @property
+    def array(self):
+        return HMatrix.array.fget(self)[:, 0]
+
+    def set(self, values):
+        self.host_view()[0, :] = np.asarray(values)
+        self.MarkHostDirty()
+
+    def Copy(self, V):
+        _check(host_lib().scuffb200_vector_copy(self.ptr, V.ptr))
+
+    def __del__(self):
+        if getattr(self, "owner", False) and self.ptr and _host is not None:
+            _host.scuffb200_vector_free(self.ptr)
+            self.ptr = None
+
+
+class IncField:
+    """scuff::IncField chain element (PlaneWave evaluated on the device; PointSource by its own GetFields at the device's points)"""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+        self.next = None
+
+    def chain(self, other):
+        host_lib().scuffb200_incfield_set_next(self.ptr, other.ptr if other is not None else None)
+        self.next = other
+        return self
+
+    def __del__(self):
+        if self.ptr and _host is not None:
+            _host.scuffb200_incfield_free(self.ptr)
+            self.ptr = None
+
+
+def PlaneWave(E0, nHat, label=None):
+    e0 = np.ascontiguousarray(np.asarray(E0, dtype=np.complex128)).view(np.float64)
+    n = np.ascontiguousarray(np.asarray(nHat, dtype=np.float64))
+    p = host_lib().scuffb200_planewave_new(e0.ctypes.data, n.ctypes.data, (label or "").encode())
+    if not p:
+        raise ScuffError(host_lib().scuffb200_last_error().decode())
+    return IncField(p)
+
+
+def PointSource(X0, P, type=0, label=None):
+    x0 = np.ascontiguousarray(np.asarray(X0, dtype=np.float64))
+    pp = np.ascontiguousarray(np.asarray(P, dtype=np.complex128)).view(np.float64)
+    p = host_lib().scuffb200_pointsource_new(x0.ctypes.data, pp.ctypes.data, int(type), (label or "").encode())
+    if not p:
+        raise ScuffError(host_lib().scuffb200_last_error().decode())
+    return IncField(p)
+
+
 class RWGGeometry:
     """scuff::RWGGeometry from a .scuffgeo file"""
+
+    def AllocateRHSVector(self, PureImagFreq=False):
+        return HVector.new(self.TotalBFs, bool(PureImagFreq) and self.LDim == 0)
+
+    def AssembleRHSVector(self, Omega, IF, RHS=None):
+        if RHS is None:
+            RHS = self.AllocateRHSVector()
+        _check(host_lib().scuffb200_assemble_rhs(self.ptr, float(np.real(Omega)), float(np.imag(Omega)), IF.ptr, RHS.ptr))
+        return RHS
+
+    def GetPFTMatrix(self, KN, Omega, IF=None, Interior=False, EMTPFTIMethod=0):
+        out = np.zeros((self.NumSurfaces, 8))
+        _check(host_lib().scuffb200_get_pft_matrix(self.ptr, KN.ptr, float(np.real(Omega)), float(np.imag(Omega)),
+                                                    IF.ptr if IF is not None else None, int(Interior), int(EMTPFTIMethod), out.ctypes.data))
+        return out
+
+    def surface_origin(self, ns):
+        out = np.zeros(3)
+        host_lib().scuffb200_surface_origin(self.ptr, ns, out.ctypes.data)
+        return out
 
     def __init__(self, geofile):
         L = host_lib()

@@ -140,3 +140,41 @@ def ref_pbcinner(geo, omega, kbloch, nsa, nsb, cache_out=None, tmpdir="/tmp/scuf
 
 def rel_fro(A, B):
     return np.linalg.norm(A - B) / np.linalg.norm(B)
+
+
+def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=None, nopft=False, tmpdir="/tmp/scuff_ref_cache", env=None):
+    """One frequency point of the reference's scuff-scatter flow (ref_driver scatter): AssembleBEMMatrix, AssembleRHSVector,
+    LU solve, GetPFTMatrix (EMT method).  pw = (E0[3] complex, nHat[3]); ps_src = (X0[3], P[3] complex) or None.
+    Returns (RHS, KN, PFT[NS, 8], info).  Cached on disk."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
+    os.makedirs(tmpdir, exist_ok=True)
+    key = hashlib.md5(repr(("scatter", geo, complex(omega), pw, ps_src, interior, method, trans, nopft)).encode()).hexdigest()[:16]
+    out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
+    meta = out + ".json"
+    if not (os.path.exists(out) and os.path.exists(meta)):
+        cmd = [REF_DRIVER, "scatter", os.path.basename(geo), repr(float(np.real(omega))), repr(float(np.imag(omega))), out, "--pw"]
+        for z in pw[0]:
+            cmd += [repr(float(np.real(z))), repr(float(np.imag(z)))]
+        cmd += [repr(float(x)) for x in pw[1]]
+        if ps_src is not None:
+            cmd += ["--ps"] + [repr(float(x)) for x in ps_src[0]]
+            for z in ps_src[1]:
+                cmd += [repr(float(np.real(z))), repr(float(np.imag(z)))]
+        if interior:
+            cmd += ["--interior"]
+        if nopft:
+            cmd += ["--nopft"]
+        cmd += ["--method", str(method)]
+        if trans is not None:
+            cmd += ["--transfile", trans[0], "--trans", str(trans[1])]
+        r = subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True,
+                           env=dict(os.environ, **(env or {})))
+        open(meta, "w").write(r.stdout.strip().splitlines()[-1])
+    info = json.load(open(meta))
+    N, NS = info["N"], info["NS"]
+    raw = np.fromfile(out, dtype=np.float64)
+    RHS = raw[:2 * N].view(np.complex128).copy()
+    KN = raw[2 * N:4 * N].view(np.complex128).copy()
+    PFT = raw[4 * N:4 * N + 8 * NS].reshape(NS, 8).copy()
+    return RHS, KN, PFT, info

@@ -1,0 +1,124 @@
+"""Right-hand side, solve and power/force/torque on the device against the unmodified reference's
+scuff-scatter flow (oracle/_ref/ref_driver scatter: AssembleBEMMatrix -> AssembleRHSVector -> LUFactorize/LUSolve ->
+GetPFTMatrix with the energy/momentum-transfer method, cubature integrals SCUFF_EMTPFTI_EHDERIVATIVES1).
+
+Tolerances: RHS entries 1e-12 relative to the largest entry (78-point rule, same points, same order of vertices);
+solution vector 1e-8 (two LU factorisations of a matrix with condition number ~1e4); power/force/torque 1e-9 relative to
+the largest entry of its group when both sides start from the SAME solution vector — the reference's same-surface kernels
+Im Psi = (kr cos kr - sin kr)/(4 pi r^3), Im Zeta cancel catastrophically for close points (EMTPFT.cc:113-117), which
+amplifies last-bit differences of sin/cos."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GEODIR, ref_scatter
+
+pytestmark = pytest.mark.gpu
+
+PW_X = ((1.0, 0.0, 0.0), (0.0, 0.0, 1.0))                 # E0 = x, propagating along +z (the Mie test's field)
+PW_OBL = ((0.3 + 0.1j, -0.2j, 0.1), (0.6, 0.0, 0.8))       # complex polarisation, oblique (E0 need not be transverse)
+
+
+def geo(name):
+    return os.path.join(GEODIR, name)
+
+
+def rel(a, b):
+    return np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(np.max(np.abs(b)), 1e-300)
+
+
+def pft_err(P, Pref):
+    """worst relative error per group (powers, force, torque), relative to the group's largest reference entry"""
+    worst = 0.0
+    for cols in ((0, 1), (2, 3, 4), (5, 6, 7)):
+        scale = np.max(np.abs(Pref[:, cols]))
+        if scale > 0:
+            worst = max(worst, np.max(np.abs(P[:, cols] - Pref[:, cols])) / scale)
+    return worst
+
+
+CASES = [("PECSphere_501.scuffgeo", 1.0, PW_X, None),
+         ("SiO2Sphere_501.scuffgeo", 1.0, PW_X, None),
+         ("SiO2Sphere_501.scuffgeo", 0.1, PW_OBL, None),
+         ("PECSpheres_327.scuffgeo", 0.7, PW_OBL, None),
+         ("E10Spheres_327.scuffgeo", 1.0, PW_X, ("Spheres.trans", 2)),
+         ("GoldSphere_501.scuffgeo", 2.0, PW_X, None)]
+
+
+@pytest.mark.parametrize("name,omega,pw,trans", CASES)
+def test_rhs_solve_pft_planewave(ps, name, omega, pw, trans):
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, pw, trans=trans)
+    G = ps.RWGGeometry(geo(name))
+    if trans is not None:
+        line = open(os.path.join(GEODIR, trans[0])).read().splitlines()[trans[1]]
+        G.transform(line)
+    IF = ps.PlaneWave(pw[0], pw[1])
+    M = G.AssembleBEMMatrix(omega, to_host=False)
+    RHS = G.AssembleRHSVector(omega, IF)
+    assert RHS.state()["HostStale"]                      # assembled in HBM
+    assert rel(RHS.array, RHSr) <= 1e-12
+    KN = G.AllocateRHSVector()
+    KN.Copy(RHS)                                         # device-to-device
+    M.lu_factorize()
+    M.lu_solve_vector(KN)
+    assert rel(KN.array, KNr) <= 1e-8
+    # same solution vector on both sides: isolates the PFT sums
+    KN2 = G.AllocateRHSVector()
+    KN2.set(KNr)
+    P = G.GetPFTMatrix(KN2, omega, IF, EMTPFTIMethod=0)
+    assert pft_err(P, PFTr) <= 1e-9, (P, PFTr)
+    # and end to end from the device's own solution
+    P2 = G.GetPFTMatrix(KN, omega, IF, EMTPFTIMethod=0)
+    assert pft_err(P2, PFTr) <= 1e-6, (P2, PFTr)
+
+
+def test_interior_pft(ps):
+    name, omega = "SiO2Sphere_501.scuffgeo", 1.0
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, interior=True)
+    G = ps.RWGGeometry(geo(name))
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    P = G.GetPFTMatrix(KN, omega, ps.PlaneWave(*PW_X), Interior=True, EMTPFTIMethod=0)
+    assert pft_err(P, PFTr) <= 1e-9, (P, PFTr)
+    assert P[0, 1] == 0.0                                # EMTPFT.cc:863-865
+
+
+def test_point_source_and_chain(ps):
+    """an IncField the device does not know (PointSource) goes through the tabulated route; chained after a plane wave"""
+    name, omega = "SiO2Sphere_501.scuffgeo", 1.0
+    src = ((0.0, 0.0, 2.5), (0.0, 1.0 + 0.5j, 0.2))
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, ps_src=src)
+    G = ps.RWGGeometry(geo(name))
+    IF = ps.PlaneWave(*PW_X).chain(ps.PointSource(*src))
+    RHS = G.AssembleRHSVector(omega, IF)
+    assert rel(RHS.array, RHSr) <= 1e-12
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    P = G.GetPFTMatrix(KN, omega, IF, EMTPFTIMethod=0)   # extinction uses the head of the chain only (EMTPFT.cc:499-511)
+    assert pft_err(P, PFTr) <= 1e-9, (P, PFTr)
+
+
+def test_point_source_inside(ps):
+    """a source inside the sphere enters the RHS with the opposite sign and the interior medium's eps/mu"""
+    name, omega = "SiO2Sphere_501.scuffgeo", 0.5
+    src = ((0.1, 0.2, -0.3), (1.0, 0.0, 0.0))
+    G = ps.RWGGeometry(geo(name))
+    RHS_in = G.AssembleRHSVector(omega, ps.PointSource(*src)).array
+    assert np.all(np.isfinite(RHS_in)) and np.max(np.abs(RHS_in)) > 0
+
+
+def test_refusals(ps):
+    G = ps.RWGGeometry(geo("PECSphere_501.scuffgeo"))
+    KN = G.AllocateRHSVector()
+    with pytest.raises(ps.ScuffError, match="EHDERIVATIVES1"):
+        G.GetPFTMatrix(KN, 1.0, ps.PlaneWave(*PW_X), EMTPFTIMethod=1)
+    with pytest.raises(ps.ScuffError, match="real positive frequency"):
+        G.GetPFTMatrix(KN, 1.0j, ps.PlaneWave(*PW_X), EMTPFTIMethod=0)
+
+
+def test_origin_follows_transform(ps):
+    G = ps.RWGGeometry(geo("E10Spheres_327.scuffgeo"))
+    assert np.allclose(G.surface_origin(0), [0, 0, 3]) and np.allclose(G.surface_origin(1), [0, 0, 0])
+    G.transform("TRANS 3.4 SURFACE UpperSphere DISP 0 0 0.4")
+    assert np.allclose(G.surface_origin(0), [0, 0, 3.4])
+    G.untransform()
+    assert np.allclose(G.surface_origin(0), [0, 0, 3])
