@@ -165,9 +165,22 @@ def other_configs(ps, np, a, peak, with_ref):
         G.AssembleBEMMatrix(points[0], M=M, to_host=False)            # cold: FIPPI table
         t_asm = timed(lambda j: G.AssembleBEMMatrix(points[j % len(points)], M=M, to_host=False), len(points))
 
+        # real frequencies: the whole scuff-scatter point (scuff-scatter.cc:402-520) on the device — RHS of a plane wave, LU, solve
+        # and the energy/momentum-transfer power/force/torque; only 8 doubles per surface are read back
+        scatter = lu and not imag
+        IF = ps.PlaneWave((1.0, 0.0, 0.0), (0.0, 0.0, 1.0)) if scatter else None
+        KN = G.AllocateRHSVector() if scatter else None
+        pft = []
+
         def point(j):
-            G.AssembleBEMMatrix(points[j % len(points)], M=M, to_host=False)
-            if lu:
+            om = points[j % len(points)]
+            G.AssembleBEMMatrix(om, M=M, to_host=False)
+            if scatter:
+                G.AssembleRHSVector(om, IF, KN)
+                M.lu_factorize()
+                M.lu_solve_vector(KN)
+                pft.append(G.GetPFTMatrix(KN, om, IF, EMTPFTIMethod=0))
+            elif lu:
                 M.lu_factorize()
                 X.host_view()[0, :] = rhs; X.MarkHostDirty()
                 M.lu_solve(X)
@@ -175,8 +188,12 @@ def other_configs(ps, np, a, peak, with_ref):
         t_pt = timed(point, len(points))
         r = {"workload": what, "matrix": "%dx%d %s" % (N, N, "float64" if imag else "complex128"), "points": len(points),
              "value": float(N) * N / t_asm / 1e9, "unit": UNIT, "assemble_ms": 1e3 * t_asm,
-             "points_per_s": 1.0 / t_pt, "point": "assemble + LU + solve, matrix never leaves HBM" if lu else "assemble",
+             "points_per_s": 1.0 / t_pt,
+             "point": ("assemble + RHS (plane wave) + LU + solve + EMTPFT power/force/torque on the device; 8 doubles per surface read back" if scatter
+                       else "assemble + LU + solve, matrix never leaves HBM" if lu else "assemble"),
              "reference_ppi_counts": [int(c) for c in G.ppi_counts()]}
+        if scatter:
+            r["pft_last_point"] = [float(v) for v in pft[-1][0]]
         ref = ref_warm(geo, points[len(points) // 2], imag=imag)
         if ref:
             ref["value"] = float(N) * N / ref["assemble_s_warm"] / 1e9
@@ -531,9 +548,27 @@ def main():
             for i in range(64):
                 W.SetEntry(i, i, 1.0)
             W.lu_factorize(); del W
-            t0 = time.perf_counter(); M.lu_factorize(); t_lu = time.perf_counter() - t0
+            sync = lambda: (ps.cuda_lib().scuffcuda_synchronize(ps.context()), torch.cuda.synchronize())
+            G.AssembleBEMMatrix(mine[-1], M=M, to_host=False)    # the kernel-by-kernel timings above may have left a partial matrix
+            sync()
+            t0 = time.perf_counter(); M.lu_factorize(); sync(); t_lu = time.perf_counter() - t0
             t0 = time.perf_counter(); M.lu_solve(X); t_sv = time.perf_counter() - t0
             line["lu"] = {"factor_s": t_lu, "solve_s": t_sv, "omega_points_per_s": 1.0 / (elapsed / a.steps + t_lu + t_sv)}
+            # the rest of a scuff-scatter frequency point on the device: plane-wave RHS, solve in HBM,
+            # energy/momentum-transfer power/force/torque (O(N^2) cubature sums).  First calls untimed (table uploads, near lists).
+            if not a.material:
+                om_pt = mine[-1]                       # the frequency M was last assembled at
+                IF = ps.PlaneWave((1.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+                KN = G.AssembleRHSVector(om_pt, IF); M.lu_solve_vector(KN); P0 = G.GetPFTMatrix(KN, om_pt, IF, EMTPFTIMethod=0); sync()
+                t0 = time.perf_counter(); G.AssembleRHSVector(om_pt, IF, KN); sync(); t_rhs = time.perf_counter() - t0
+                t0 = time.perf_counter(); M.lu_solve_vector(KN); sync(); t_sv2 = time.perf_counter() - t0
+                t0 = time.perf_counter(); P1 = G.GetPFTMatrix(KN, om_pt, IF, EMTPFTIMethod=0); t_pft = time.perf_counter() - t0
+                NPt = 6.0 * (2 * N // 3)
+                line["scatter_point"] = {"what": "AssembleRHSVector (plane wave) + LUSolve on the device vector + GetPFTMatrix (EMT, cubature integrals): only 8 doubles per surface leave the GPU",
+                                         "rhs_ms": 1e3 * t_rhs, "solve_ms": 1e3 * t_sv2, "pft_ms": 1e3 * t_pft,
+                                         "pft_point_pairs": NPt * NPt, "pft_gpairs_per_s": NPt * NPt / t_pft / 1e9,
+                                         "pft": [float(v) for v in P1[0]],
+                                         "omega_points_per_s": 1.0 / (elapsed / a.steps + t_lu + t_rhs + t_sv2 + t_pft)}
         except Exception as e:  # noqa
             line["lu"] = {"error": str(e)[:200]}
 

@@ -221,6 +221,17 @@ int scuffcuda_pft_points(scuffcuda_context *ctx, int ns, double *X, long *npts);
  * GetExtinctionPFTT returns it.  Host buffers.                                                                           */
 int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_args *args, double *scattered, double *extinction);
 
+/* ---- scattered fields at evaluation points: RWGGeometry::GetRFMatrix / GetFields (libs/libscuff/GetFields.cc:141-395) --
+ * Contribution of surface ns to the fields at npts points X[3*npts] (host) that all lie in ONE region bounded by the surface:
+ * k, zrel = wavenumber and relative wave impedance of that region, sign = +1 if it is the surface's exterior region, -1 if interior
+ * (GetFields.cc:262-270).  kn_handle != 0: F[12*npts] (host; E then H as (re,im)) += sum over the surface's basis functions of
+ * (reduced fields) x (solution entries).  rf_handle != 0: the reduced-field matrix entries RFMatrix[bf_offset + .., 6*rf_columns[i] + mu]
+ * are stored in that device matrix (TotalBFs x 6 NX complex).  16-point rule beyond 4 basis-function radii, 78-point rule beyond 1
+ * (:171-181, :284-295); pairs closer than that need GetReducedFields_Nearby, which is not on the device path: *near_pairs counts them
+ * (their contribution is NOT included; callers treat a non-zero count as an error).                                      */
+int scuffcuda_get_fields(scuffcuda_context *ctx, int ns, const double k[2], const double zrel[2], double sign, int npts, const double *X,
+                         int kn_handle, int bf_offset, double *F, int rf_handle, const int *rf_columns, long *near_pairs);
+
 /* PPI algorithm counters of the last assemble_block call, same order as the reference's
  * log line (SurfaceSurfaceInteractions.cc:550-558; libscuffInternals.h PPIALG_*):
  * [0] low-order cubature, [1] high-order cubature, [2] Taylor-Duffy, [3] high-k TD,

@@ -13,11 +13,13 @@
  *        EdgeEdgeInteractions.cc:241-270): writes the value block, the three gradient blocks and the torque blocks one after
  *        the other (complex, or real with --imag as scuff-cas3D allocates them)
  *   ref_driver scatter <geo> <wRe> <wIm> <out.bin> --pw E0xr E0xi E0yr E0yi E0zr E0zi nx ny nz [--ps x y z Pxr Pxi Pyr Pyi Pzr Pzi]
- *                      [--interior] [--method m] [--transfile f --trans n] [--nopft]
+ *                      [--interior] [--method m] [--transfile f --trans n] [--nopft] [--fields pts.bin [--rf]]
  *        one frequency point of scuff-scatter (scuff-scatter.cc:402-520): AssembleBEMMatrix, AssembleRHSVector with the given
  *        incident-field chain (plane wave first, then an optional point source), LUFactorize, LUSolve, GetPFTMatrix by the
  *        energy/momentum-transfer method with integral method m (default 0 = SCUFF_EMTPFTI_EHDERIVATIVES1).  Writes RHS
  *        (TotalBFs complex), the solution KN (TotalBFs complex) and the PFT matrix (NumSurfaces x 8 doubles, row-major).
+ *        --fields: then GetFields (GetFields.cc:336-395) at the points of pts.bin (raw doubles x,y,z): NX x 6 complex, row-major,
+ *        appended; --rf: then GetRFMatrix (:141-330), TotalBFs x 6NX complex column-major, appended.
  *   ref_driver ssi    <geo> <wRe> <wIm> <nsa> <nsb> <Lx> <Ly> <Lz> <out.bin> [--cache-out f]
  *        GetSurfaceSurfaceInteractions (SurfaceSurfaceInteractions.cc:426-585) for one surface pair with surface b displaced
  *        by L (the neighbour-cell blocks of the periodic assembly, AssembleBEMMatrix.cc:72-114), not Symmetric
@@ -199,7 +201,7 @@ int main(int argc, char **argv)
 
   if(!strcmp(Cmd,"scatter"))
    { cdouble Omega(atof(argv[3]),atof(argv[4])); const char *Out=argv[5];
-     IncField *IFList=0, *Tail=0; bool Interior=false, NoPFT=false; int Method=0; const char *TransFile=0; int nTrans=0;
+     IncField *IFList=0, *Tail=0; bool Interior=false, NoPFT=false, WantRF=false; int Method=0; const char *TransFile=0, *PtsFile=0; int nTrans=0;
      for(int n=6;n<argc;n++)
       { IncField *New=0;
         if(!strcmp(argv[n],"--pw") && n+9<argc)
@@ -212,6 +214,8 @@ int main(int argc, char **argv)
            New=new PointSource(X0,P); n+=9; }
         else if(!strcmp(argv[n],"--interior")) Interior=true;
         else if(!strcmp(argv[n],"--nopft")) NoPFT=true;
+        else if(!strcmp(argv[n],"--rf")) WantRF=true;
+        else if(!strcmp(argv[n],"--fields")) PtsFile=argv[++n];
         else if(!strcmp(argv[n],"--method")) Method=atoi(argv[++n]);
         else if(!strcmp(argv[n],"--transfile")) TransFile=argv[++n];
         else if(!strcmp(argv[n],"--trans")) nTrans=atoi(argv[++n]);
@@ -239,6 +243,15 @@ int main(int argc, char **argv)
      FILE *f=fopen(Out,"wb"); if(!f) return 1;
      fwrite(RHS->ZV,sizeof(cdouble),RHS->N,f); fwrite(KN->ZV,sizeof(cdouble),KN->N,f);
      for(int ns=0;ns<G->NumSurfaces;ns++) for(int nq=0;nq<NUMPFT;nq++) { double v=PFT->GetEntryD(ns,nq); fwrite(&v,sizeof(double),1,f); }
+     if(PtsFile)
+      { FILE *fp=fopen(PtsFile,"rb"); if(!fp) return 1;
+        fseek(fp,0,SEEK_END); long NX=ftell(fp)/(3*sizeof(double)); fseek(fp,0,SEEK_SET);
+        HMatrix *XM=new HMatrix(NX,3);
+        for(long nx=0;nx<NX;nx++) { double X[3]; if(fread(X,sizeof(double),3,fp)!=3) return 1; for(int m=0;m<3;m++) XM->SetEntry(nx,m,X[m]); }
+        fclose(fp);
+        HMatrix *FM=G->GetFields(IFList,KN,Omega,XM);
+        for(long nx=0;nx<NX;nx++) for(int q=0;q<6;q++) { cdouble v=FM->GetEntry(nx,q); fwrite(&v,sizeof(cdouble),1,f); }
+        if(WantRF) { HMatrix *RF=G->GetRFMatrix(Omega,0,XM,0); fwrite(RF->ZM,sizeof(cdouble),(size_t)RF->NR*RF->NC,f); } }
      fclose(f); return 0;
    }
 

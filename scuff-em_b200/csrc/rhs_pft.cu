@@ -32,6 +32,7 @@
 #include "kernels.h"
 #include "generated_tcr20.h"
 #include "generated_tcr9.h"
+#include "generated_tcr7.h"
 
 #define ZVAC 376.73031346177      /* libscuff.h:78 */
 #define TENTHIRDS 3.33333333333333333333333   /* PFTOptions.h:64 */
@@ -59,7 +60,8 @@ struct NearBF { int ea, eb; };
 struct PftNearList { uint64_t genA = 0, genB = 0; int n = 0; NearBF *d = nullptr; };
 
 struct PftState
-{ double *dtcr20 = nullptr, *dtcr9 = nullptr, *dtcr4 = nullptr;
+{ double *dtcr20 = nullptr, *dtcr9 = nullptr, *dtcr4 = nullptr, *dtcr7 = nullptr;
+  double *dfx = nullptr; size_t fxCap = 0;          // evaluation points + field sums of scuffcuda_get_fields
   std::map<std::pair<int, int>, PftNearList> nearLists;
   CurPt *dcur = nullptr; size_t curCap = 0;          // current points of all surfaces (order 4, then order 9)
   double *dpart = nullptr; size_t partCap = 0;       // per-CTA partial sums
@@ -75,7 +77,7 @@ static PftState *pft_state(scuffcuda_context *ctx)
 }
 void pft_release(scuffcuda_context *ctx)
 { PftState *P = (PftState *)ctx->pftState; if (!P) return;
-  if (P->dtcr20) cudaFree(P->dtcr20); if (P->dtcr9) cudaFree(P->dtcr9); if (P->dtcr4) cudaFree(P->dtcr4);
+  if (P->dtcr20) cudaFree(P->dtcr20); if (P->dtcr9) cudaFree(P->dtcr9); if (P->dtcr4) cudaFree(P->dtcr4); if (P->dtcr7) cudaFree(P->dtcr7); if (P->dfx) cudaFree(P->dfx);
   for (auto &l : P->nearLists) if (l.second.d) cudaFree(l.second.d);
   if (P->dcur) cudaFree(P->dcur); if (P->dpart) cudaFree(P->dpart); if (P->dtab) cudaFree(P->dtab);
   delete P; ctx->pftState = nullptr;
@@ -86,6 +88,8 @@ static int pft_tables(scuffcuda_context *ctx)
   static const double U4[6] = SCUFF_TCR4_U, V4[6] = SCUFF_TCR4_V, W4[6] = SCUFF_TCR4_W;
   double T4[18]; for (int p = 0; p < 6; p++) { T4[3 * p] = U4[p]; T4[3 * p + 1] = V4[p]; T4[3 * p + 2] = W4[p]; }
   PCK(cudaMalloc(&P->dtcr4, sizeof T4)); PCK(cudaMalloc(&P->dtcr9, sizeof SC_TCR9_H)); PCK(cudaMalloc(&P->dtcr20, sizeof SC_TCR20_H));
+  PCK(cudaMalloc(&P->dtcr7, sizeof SC_TCR7_H));
+  PCK(cudaMemcpyAsync(P->dtcr7, SC_TCR7_H, sizeof SC_TCR7_H, cudaMemcpyHostToDevice, ctx->stream));
   PCK(cudaMemcpyAsync(P->dtcr4, T4, sizeof T4, cudaMemcpyHostToDevice, ctx->stream));
   PCK(cudaMemcpyAsync(P->dtcr9, SC_TCR9_H, sizeof SC_TCR9_H, cudaMemcpyHostToDevice, ctx->stream));
   PCK(cudaMemcpyAsync(P->dtcr20, SC_TCR20_H, sizeof SC_TCR20_H, cudaMemcpyHostToDevice, ctx->stream));
@@ -470,6 +474,86 @@ __global__ void __launch_bounds__(PFT_THREADS) pft_ext_kernel(const __grid_const
   block_reduce_store(v, X.part + (size_t)blockIdx.x * PFT_NQ);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// scattered fields at evaluation points (GetRFMatrix / GetFields, GetFields.cc:141-330, 336-395)
+// ------------------------------------------------------------------------------------------------------------------
+// One CTA per evaluation point, threads stride over the edges of one surface.  Per (edge, point): the reduced fields
+//   g = int f G - div f grad G / k^2 ,   c = int f x grad G / (-ik)        (RFIntegrand :86-105, GetG CalcGC.cc:194-240)
+// by the 16-point rule if the point is >= 4 basis-function radii from the edge centroid, the 78-point rule if >= 1
+// (GetBFCubature2, PanelCubature.cc:713-787: points Q + u(V1-Q) + v(V2-Q) on both panels); closer points need the
+// reference's desingularised near-field integrals, which are not on the device: they are counted and reported.
+// KN != null: contract with the solution on the fly (E, H accumulate into F); RF != null: also store the reduced-field
+// matrix entries (RFMatrix[bf, 6 nx + mu], :307-325).
+struct FieldArgs
+{ const EdgeRec *edges; int NE; const double *X; int NX; const double *tcr7, *tcr20;
+  cd k, zrel; double sign;
+  const double *kn; int offset, isPEC;
+  double *F;                       // 12 doubles per point, accumulated
+  double *RF; long ldRF; const int *colOf;   // RFMatrix (complex, column-major, leading dimension ldRF), column block 6*colOf[nx]
+  unsigned long long *nearCount;
+};
+
+__global__ void __launch_bounds__(PFT_THREADS) fields_kernel(const __grid_constant__ FieldArgs A)
+{ __shared__ double red[PFT_THREADS / 32][12];
+  const int nx = blockIdx.x;
+  const double X0[3] = { A.X[3 * nx], A.X[3 * nx + 1], A.X[3 * nx + 2] };
+  const cd ik = mk(-A.k.y, A.k.x), k2 = A.k * A.k, ook2 = cinv(k2), oomik = cinv(mk(A.k.y, -A.k.x));   // 1/(-ik)
+  const cd ikz = ik * A.sign;
+  const cd EK = ikz * A.zrel * ZVAC, HK = -ikz, EN = -(ikz * ZVAC), HN = -cdiv(ikz, A.zrel);
+  cd acc[6]; for (int q = 0; q < 6; q++) acc[q] = mk(0.0, 0.0);
+  for (int ne = threadIdx.x; ne < A.NE; ne += PFT_THREADS)
+   { const EdgeRec &E = A.edges[ne];
+     double c[3], rad = 0.0, d2 = 0.0;
+     for (int m = 0; m < 3; m++) { c[m] = (E.V1[m] + E.V2[m]) / 2.0; d2 += (X0[m] - c[m]) * (X0[m] - c[m]); }
+     { double a = 0, b = 0, q = 0, qm = 0;
+       for (int m = 0; m < 3; m++) { a += (E.QP[m] - c[m]) * (E.QP[m] - c[m]); b += (E.V1[m] - c[m]) * (E.V1[m] - c[m]); q += (E.V2[m] - c[m]) * (E.V2[m] - c[m]); qm += (E.QM[m] - c[m]) * (E.QM[m] - c[m]); }
+       rad = fmax(sqrt(a), fmax(sqrt(b), sqrt(q))); if (E.hasM) rad = fmax(rad, sqrt(qm)); }
+     const double rRel = sqrt(d2) / rad;
+     if (rRel < 1.0) { atomicAdd(A.nearCount, 1ull); continue; }
+     const double *tcr = rRel >= 4.0 ? A.tcr7 : A.tcr20; const int npts = rRel >= 4.0 ? SC_TCR7_NPTS : SC_TCR20_NPTS;
+     cd GC[6]; for (int q = 0; q < 6; q++) GC[q] = mk(0.0, 0.0);
+     for (int np = 0; np < npts; np++)
+      { const double u = tcr[3 * np], v = tcr[3 * np + 1], w = tcr[3 * np + 2];
+        for (int pm = 0; pm < (E.hasM ? 2 : 1); pm++)
+         { double Xs[3], b[3], div, jac;
+           bf_point(E, pm, u, v, Xs, b, div, jac);
+           const double W = jac * w;
+           double R[3]; for (int m = 0; m < 3; m++) R[m] = Xs[m] - X0[m];
+           const double r2 = R[0] * R[0] + R[1] * R[1] + R[2] * R[2], r = sqrt(r2);
+           // Phi = exp(ikr)/(4 pi r), Psi = Phi (ikr - 1)/r^2, dG = R Psi
+           double sn, cs; sincos(A.k.x * r, &sn, &cs);
+           const double e = (A.k.y == 0.0 ? 1.0 : exp(-A.k.y * r)) / (4.0 * M_PI * r);
+           const cd Phi = mk(e * cs, e * sn);
+           const cd Psi = cmul_helper(Phi, mk(ik.x * r - 1.0, ik.y * r), 1.0 / r2);
+           const cd dco = Psi * ook2 * div;                 // Divb dG / k^2 = R (Divb Psi / k^2)
+           for (int m = 0; m < 3; m++) GC[m] += (Phi * b[m] - dco * R[m]) * W;
+           const double bxR[3] = { b[1] * R[2] - b[2] * R[1], b[2] * R[0] - b[0] * R[2], b[0] * R[1] - b[1] * R[0] };
+           const cd pc = Psi * oomik * W;
+           for (int m = 0; m < 3; m++) GC[3 + m] += pc * bxR[m]; } }
+     const int row = A.offset + (A.isPEC ? ne : 2 * ne);
+     cd rf[12];
+     for (int m = 0; m < 3; m++) { rf[m] = EK * GC[m]; rf[3 + m] = HK * GC[3 + m]; rf[6 + m] = EN * GC[3 + m]; rf[9 + m] = HN * GC[m]; }
+     if (A.RF)
+      { double *col = A.RF + 2 * ((size_t)6 * A.colOf[nx] * A.ldRF);
+        for (int q = 0; q < 6; q++)
+         { double *p = col + 2 * ((size_t)q * A.ldRF + row);
+           p[0] = rf[q].x; p[1] = rf[q].y;
+           if (!A.isPEC) { p[2] = rf[6 + q].x; p[3] = rf[6 + q].y; } } }
+     if (A.kn)
+      { const cd kc = mk(A.kn[2 * row], A.kn[2 * row + 1]);
+        for (int q = 0; q < 6; q++) acc[q] += kc * rf[q];
+        if (!A.isPEC) { const cd nc = mk(A.kn[2 * row + 2], A.kn[2 * row + 3]); for (int q = 0; q < 6; q++) acc[q] += nc * rf[6 + q]; } } }
+  if (!A.kn) return;
+  double v[12]; for (int q = 0; q < 6; q++) { v[2 * q] = acc[q].x; v[2 * q + 1] = acc[q].y; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < 12; q++) for (int o = 16; o > 0; o >>= 1) v[q] += __shfl_xor_sync(0xffffffffu, v[q], o);
+  if (lane == 0) for (int q = 0; q < 12; q++) red[warp][q] = v[q];
+  __syncthreads();
+  if (threadIdx.x < 12)
+   { double sum = 0.0; for (int wq = 0; wq < PFT_THREADS / 32; wq++) sum += red[wq][threadIdx.x];
+     A.F[12 * (size_t)nx + threadIdx.x] += sum; }
+}
+
 // ---- host side: near basis-function pairs of a surface pair (AssessBFPair, AssessPanelPair.cc:200-241) -----------
 static int build_near_list(scuffcuda_context *ctx, int nsa, int nsb, PftNearList &L)
 { Surface &SA = ctx->surfaces[nsa], &SB = ctx->surfaces[nsb];
@@ -715,6 +799,53 @@ int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_
         double *out = extinction + (size_t)ns * 11;
         out[0] = PFactor * q[0];
         for (int m = 0; m < 9; m++) out[2 + m] = FTFactor * q[1 + m]; } }
+  return 0;
+}
+
+int scuffcuda_get_fields(scuffcuda_context *ctx, int ns, const double k[2], const double zrel[2], double sign, int npts, const double *X,
+                         int kn_handle, int bf_offset, double *F, int rf_handle, const int *rf_columns, long *near_pairs)
+{ if (ns < 0 || ns >= (int)ctx->surfaces.size()) return pfail(ctx, "get_fields: invalid surface index");
+  if (near_pairs) *near_pairs = 0;
+  if (npts <= 0) return 0;
+  Surface &S = ctx->surfaces[ns];
+  if (S.NE == 0) return 0;
+  Matrix *KN = kn_handle ? find_matrix(ctx, kn_handle) : nullptr, *RF = rf_handle ? find_matrix(ctx, rf_handle) : nullptr;
+  if (kn_handle && (!KN || KN->NC != 1 || KN->isReal)) return pfail(ctx, "get_fields: the solution vector must be a complex device vector");
+  if (rf_handle && (!RF || RF->isReal || !rf_columns)) return pfail(ctx, "get_fields: the reduced-field matrix must be a complex device matrix");
+  const int nbf = S.isPEC ? S.NE : 2 * S.NE;
+  if (KN && (bf_offset < 0 || bf_offset + nbf > KN->NR)) return pfail(ctx, "get_fields: basis-function offset does not fit the vector");
+  if (RF && (bf_offset < 0 || bf_offset + nbf > RF->NR)) return pfail(ctx, "get_fields: basis-function offset does not fit the reduced-field matrix");
+  if (RF) for (int i = 0; i < npts; i++) if (rf_columns[i] < 0 || 6 * (rf_columns[i] + 1) > RF->NC) return pfail(ctx, "get_fields: reduced-field matrix has too few columns");
+  if (!KN && !RF) return pfail(ctx, "get_fields: nothing to compute");
+  PCK(cudaSetDevice(ctx->device));
+  if (pft_tables(ctx) || ensure_edges(ctx, S)) return 1;
+  PftState *P = pft_state(ctx);
+  // layout of the scratch: X[3 npts] | F[12 npts] | counter (8 B) | columns (npts ints)
+  const size_t need = (size_t)15 * npts + 1 + ((size_t)npts + 1) / 2 + 1;
+  if (grow(ctx, P->dfx, P->fxCap, need)) return 1;
+  double *dX = P->dfx, *dF = dX + (size_t)3 * npts; unsigned long long *dcnt = (unsigned long long *)(dF + (size_t)12 * npts); int *dcol = (int *)(dcnt + 1);
+  PCK(cudaMemcpyAsync(dX, X, (size_t)3 * npts * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  PCK(cudaMemsetAsync(dF, 0, ((size_t)12 * npts + 1) * sizeof(double), ctx->stream));
+  if (RF) PCK(cudaMemcpyAsync(dcol, rf_columns, (size_t)npts * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->h2dBytes += (size_t)3 * npts * sizeof(double);
+  FieldArgs A;
+  A.edges = (const EdgeRec *)S.dedges; A.NE = S.NE; A.X = dX; A.NX = npts; A.tcr7 = P->dtcr7; A.tcr20 = P->dtcr20;
+  A.k = mk(k[0], k[1]); A.zrel = mk(zrel[0], zrel[1]); A.sign = sign;
+  A.kn = KN ? KN->d : nullptr; A.offset = bf_offset; A.isPEC = S.isPEC; A.F = dF;
+  A.RF = RF ? RF->d : nullptr; A.ldRF = RF ? RF->NR : 0; A.colOf = dcol; A.nearCount = dcnt;
+  fields_kernel<<<npts, PFT_THREADS, 0, ctx->stream>>>(A);
+  ctx->launches++;
+  PCK(cudaGetLastError());
+  unsigned long long cnt = 0;
+  PCK(cudaMemcpyAsync(&cnt, dcnt, sizeof cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  if (KN && F)
+   { std::vector<double> h((size_t)12 * npts);
+     PCK(cudaMemcpyAsync(h.data(), dF, h.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+     PCK(cudaStreamSynchronize(ctx->stream));
+     ctx->d2hBytes += h.size() * sizeof(double);
+     for (size_t i = 0; i < h.size(); i++) F[i] += h[i]; }
+  else PCK(cudaStreamSynchronize(ctx->stream));
+  if (near_pairs) *near_pairs = (long)cnt;
   return 0;
 }
 

@@ -299,4 +299,79 @@ HMatrix *RWGGeometry::GetPFTMatrix(HVector *KN, cdouble Omega, PFTOptions *Optio
   return PFTMatrix;
 }
 
+// ---- scattered fields at evaluation points -----------------------------------------------------------
+// shared by GetFields (contracted with KN on the device) and GetRFMatrix (entries stored in a device matrix)
+static void ReducedFieldsOnDevice(RWGGeometry *G, cdouble Omega, HMatrix *XMatrix, int ColumnOffset, HVector *KN, double *F, HMatrix *RFMatrix)
+{ const int NX = XMatrix->NR;
+  G->SyncDeviceGeometry();
+  scuffcuda_context *ctx = GetCudaContext();
+  if (KN) KN->PrepareDevice();
+  if (RFMatrix) RFMatrix->PrepareDevice();
+  std::vector<int> Region(NX);
+  std::vector<double> XAll(3 * (size_t)NX);
+  for (int nx = 0; nx < NX; nx++)
+   { for (int m = 0; m < 3; m++) XAll[3 * (size_t)nx + m] = XMatrix->GetEntryD(nx, ColumnOffset + m);
+     Region[nx] = G->GetRegionIndex(&XAll[3 * (size_t)nx]); }
+  for (int nr = 0; nr < G->NumRegions; nr++)
+   { std::vector<int> Idx; std::vector<double> X;
+     for (int nx = 0; nx < NX; nx++) if (Region[nx] == nr) { Idx.push_back(nx); for (int m = 0; m < 3; m++) X.push_back(XAll[3 * (size_t)nx + m]); }
+     if (Idx.empty()) continue;
+     cdouble EpsRel, MuRel; G->RegionMPs[nr]->GetEpsMu(Omega, &EpsRel, &MuRel);
+     const cdouble ZRel = sqrt(MuRel / EpsRel), k = sqrt(MuRel * EpsRel) * Omega;
+     const double kk[2] = { real(k), imag(k) }, zz[2] = { real(ZRel), imag(ZRel) };
+     std::vector<double> Fr(KN ? 12 * Idx.size() : 0, 0.0);
+     for (int ns = 0; ns < G->NumSurfaces; ns++)
+      { RWGSurface *S = G->Surfaces[ns];
+        double Sign = 0.0;
+        if (S->RegionIndices[0] == nr) Sign = +1.0; else if (S->RegionIndices[1] == nr) Sign = -1.0; else continue;
+        long Near = 0;
+        if (scuffcuda_get_fields(ctx, ns, kk, zz, Sign, (int)Idx.size(), X.data(), KN ? KN->DeviceHandle : 0, G->BFIndexOffset[ns],
+                                 KN ? Fr.data() : 0, RFMatrix ? RFMatrix->DeviceHandle : 0, RFMatrix ? Idx.data() : 0, &Near))
+         ErrExit("%s", scuffcuda_last_error(ctx));
+        if (Near) ErrExit("GetFields: %li (basis function, evaluation point) pairs are closer than one basis-function radius; the reference's "
+                          "desingularised near-field integrals (GetReducedFields_Nearby) are not available on the device path", Near); }
+     if (KN) for (size_t i = 0; i < Idx.size(); i++) for (int q = 0; q < 12; q++) F[12 * (size_t)Idx[i] + q] += Fr[12 * i + q]; }
+  if (RFMatrix) { RFMatrix->HostStale = true; RFMatrix->DeviceStale = false; }
+}
+
+HMatrix *RWGGeometry::GetRFMatrix(cdouble Omega, double *kBloch, HMatrix *XMatrix, HMatrix *RFMatrix, bool MinuskBloch, int ColumnOffset)
+{ (void)MinuskBloch;
+  if (LBasis || kBloch) ErrExit("GetRFMatrix: periodic geometries are not supported on the device path");
+  const int NX = XMatrix->NR;
+  if (RFMatrix == 0 || RFMatrix->NR != TotalBFs || RFMatrix->NC != 6 * NX)
+   { if (RFMatrix) { Warn("wrong-size RFMatrix passed to GetRFMatrix; reallocating"); delete RFMatrix; }
+     RFMatrix = new HMatrix(TotalBFs, 6 * NX, LHM_COMPLEX); }
+  RFMatrix->Zero();
+  ReducedFieldsOnDevice(this, Omega, XMatrix, ColumnOffset, 0, 0, RFMatrix);
+  return RFMatrix;
+}
+
+HMatrix *RWGGeometry::GetFields(IncField *IFList, HVector *KN, cdouble Omega, double *kBloch, HMatrix *XMatrix, HMatrix *FMatrix)
+{ if (XMatrix == 0 || XMatrix->NC < 3 || XMatrix->NR == 0) ErrExit("wrong-size XMatrix (%ix%i) passed to GetFields", XMatrix ? XMatrix->NR : 0, XMatrix ? XMatrix->NC : 0);
+  if (LBasis || kBloch) ErrExit("GetFields: periodic geometries are not supported on the device path");
+  const int NX = XMatrix->NR;
+  if (FMatrix == 0 || FMatrix->NR != NX || FMatrix->NC != 6)
+   { if (FMatrix) { Warn(" ** warning: wrong-size FMatrix passed to GetFields(); reallocating"); delete FMatrix; }
+     FMatrix = new HMatrix(NX, 6, LHM_COMPLEX); }
+  FMatrix->Zero();
+  if (IFList) UpdateIncFields(IFList, Omega, kBloch);
+  std::vector<double> F(12 * (size_t)NX, 0.0);
+  if (KN) ReducedFieldsOnDevice(this, Omega, XMatrix, 0, KN, F.data(), 0);
+  for (int nx = 0; nx < NX; nx++)
+   { cdouble EH[6]; for (int q = 0; q < 6; q++) EH[q] = cdouble(F[12 * (size_t)nx + 2 * q], F[12 * (size_t)nx + 2 * q + 1]);
+     if (IFList)
+      { double X[3] = { XMatrix->GetEntryD(nx, 0), XMatrix->GetEntryD(nx, 1), XMatrix->GetEntryD(nx, 2) };
+        const int RegionIndex = GetRegionIndex(X);
+        if (RegionIndex != -1)
+         for (IncField *IF = IFList; IF; IF = IF->Next)
+          if (IF->RegionIndex == RegionIndex) { cdouble P[6]; IF->GetFields(X, P); for (int q = 0; q < 6; q++) EH[q] += P[q]; } }
+     for (int q = 0; q < 6; q++) FMatrix->SetEntry(nx, q, EH[q]); }
+  return FMatrix;
+}
+HMatrix *RWGGeometry::GetFields(IncField *IF, HVector *KN, cdouble Omega, HMatrix *XMatrix, HMatrix *FMatrix)
+{ return GetFields(IF, KN, Omega, 0, XMatrix, FMatrix); }
+void RWGGeometry::GetFields(IncField *IF, HVector *KN, cdouble Omega, double *X, cdouble *EH)
+{ HMatrix XMatrix(1, 3, LHM_REAL, LHM_NORMAL, (void *)X), FMatrix(1, 6, LHM_COMPLEX, LHM_NORMAL, (void *)EH);
+  GetFields(IF, KN, Omega, 0, &XMatrix, &FMatrix); }
+
 }  // namespace scuff

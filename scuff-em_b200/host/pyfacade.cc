@@ -154,6 +154,17 @@ int scuffb200_get_pft_matrix(void *g, void *kn, double wr, double wi, void *incf
         HMatrix *P = G->GetPFTMatrix((HVector *)(HMatrix *)kn, cdouble(wr, wi), &Opts, 0);
         for (int ns = 0; ns < G->NumSurfaces; ns++) for (int nq = 0; nq < NUMPFT; nq++) out[ns * NUMPFT + nq] = P->GetEntryD(ns, nq);
         delete P; return 0;, 1) }
+/* X: NX x 3 row-major; out: NX x 6 complex row-major (E, H) */
+int scuffb200_get_fields(void *g, void *incfield, void *kn, double wr, double wi, int nx, const double *X, double *out)
+{ GUARD(RWGGeometry *G = (RWGGeometry *)g;
+        HMatrix XM(nx, 3, LHM_REAL); for (int i = 0; i < nx; i++) for (int m = 0; m < 3; m++) XM.SetEntry(i, m, X[3 * i + m]);
+        HMatrix *F = G->GetFields((IncField *)incfield, (HVector *)(HMatrix *)kn, cdouble(wr, wi), &XM, 0);
+        for (int i = 0; i < nx; i++) for (int q = 0; q < 6; q++) { cdouble v = F->GetEntry(i, q); out[12 * i + 2 * q] = real(v); out[12 * i + 2 * q + 1] = imag(v); }
+        delete F; return 0;, 1) }
+void *scuffb200_get_rf_matrix(void *g, double wr, double wi, int nx, const double *X)
+{ GUARD(RWGGeometry *G = (RWGGeometry *)g;
+        HMatrix XM(nx, 3, LHM_REAL); for (int i = 0; i < nx; i++) for (int m = 0; m < 3; m++) XM.SetEntry(i, m, X[3 * i + m]);
+        return (void *)G->GetRFMatrix(cdouble(wr, wi), 0, &XM, 0);, 0) }
 int scuffb200_surface_origin(void *g, int ns, double *out) { for (int m = 0; m < 3; m++) out[m] = ((RWGGeometry *)g)->Surfaces[ns]->Origin[m]; return 0; }
 
 }  // extern "C"

@@ -161,6 +161,9 @@ def host_lib():
         L.scuffb200_vector_copy.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffb200_get_pft_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.scuffb200_surface_origin.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.scuffb200_get_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.scuffb200_get_rf_matrix.restype = C.c_void_p
+        L.scuffb200_get_rf_matrix.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
         _host = L
     return _host
 
@@ -362,6 +365,21 @@ class RWGGeometry:
         _check(host_lib().scuffb200_get_pft_matrix(self.ptr, KN.ptr, float(np.real(Omega)), float(np.imag(Omega)),
                                                     IF.ptr if IF is not None else None, int(Interior), int(EMTPFTIMethod), out.ctypes.data))
         return out
+
+    def GetFields(self, IF, KN, Omega, X):
+        """total (scattered + incident) E, H at the rows of X (NX x 3): NX x 6 complex"""
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1, 3))
+        out = np.zeros((X.shape[0], 6), dtype=np.complex128)
+        _check(host_lib().scuffb200_get_fields(self.ptr, IF.ptr if IF is not None else None, KN.ptr if KN is not None else None,
+                                                float(np.real(Omega)), float(np.imag(Omega)), X.shape[0], X.ctypes.data, out.ctypes.data))
+        return out
+
+    def GetRFMatrix(self, Omega, X):
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1, 3))
+        p = host_lib().scuffb200_get_rf_matrix(self.ptr, float(np.real(Omega)), float(np.imag(Omega)), X.shape[0], X.ctypes.data)
+        if not p:
+            raise ScuffError(host_lib().scuffb200_last_error().decode())
+        return HMatrix(p)
 
     def surface_origin(self, ns):
         out = np.zeros(3)

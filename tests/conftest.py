@@ -142,14 +142,16 @@ def rel_fro(A, B):
     return np.linalg.norm(A - B) / np.linalg.norm(B)
 
 
-def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=None, nopft=False, tmpdir="/tmp/scuff_ref_cache", env=None):
+def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=None, nopft=False, tmpdir="/tmp/scuff_ref_cache", env=None,
+                points=None, rf=False):
     """One frequency point of the reference's scuff-scatter flow (ref_driver scatter): AssembleBEMMatrix, AssembleRHSVector,
     LU solve, GetPFTMatrix (EMT method).  pw = (E0[3] complex, nHat[3]); ps_src = (X0[3], P[3] complex) or None.
     Returns (RHS, KN, PFT[NS, 8], info).  Cached on disk."""
     if not have_ref():
         pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
     os.makedirs(tmpdir, exist_ok=True)
-    key = hashlib.md5(repr(("scatter", geo, complex(omega), pw, ps_src, interior, method, trans, nopft)).encode()).hexdigest()[:16]
+    pkey = None if points is None else hashlib.md5(np.ascontiguousarray(points, dtype=np.float64).tobytes()).hexdigest()
+    key = hashlib.md5(repr(("scatter", geo, complex(omega), pw, ps_src, interior, method, trans, nopft, pkey, rf)).encode()).hexdigest()[:16]
     out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
     meta = out + ".json"
     if not (os.path.exists(out) and os.path.exists(meta)):
@@ -168,6 +170,9 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
         cmd += ["--method", str(method)]
         if trans is not None:
             cmd += ["--transfile", trans[0], "--trans", str(trans[1])]
+        if points is not None:
+            np.ascontiguousarray(points, dtype=np.float64).tofile(out + ".pts")
+            cmd += ["--fields", out + ".pts"] + (["--rf"] if rf else [])
         r = subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True,
                            env=dict(os.environ, **(env or {})))
         open(meta, "w").write(r.stdout.strip().splitlines()[-1])
@@ -177,4 +182,11 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
     RHS = raw[:2 * N].view(np.complex128).copy()
     KN = raw[2 * N:4 * N].view(np.complex128).copy()
     PFT = raw[4 * N:4 * N + 8 * NS].reshape(NS, 8).copy()
+    if points is not None:
+        NX = np.asarray(points).reshape(-1, 3).shape[0]
+        o = 4 * N + 8 * NS
+        info["fields"] = raw[o:o + 12 * NX].view(np.complex128).reshape(NX, 6).copy()
+        if rf:
+            o += 12 * NX
+            info["rf"] = raw[o:o + 2 * N * 6 * NX].view(np.complex128).reshape(6 * NX, N).T.copy()
     return RHS, KN, PFT, info

