@@ -31,8 +31,8 @@ def rel(a, b):
 
 @pytest.mark.parametrize("name,omega", [("PECSphere_501.scuffgeo", 1.0), ("SiO2Sphere_501.scuffgeo", 1.0), ("GoldSphere_501.scuffgeo", 2.0)])
 def test_fields_outside_and_inside(ps, name, omega):
-    # outside: from 1.3 radii (78-point rule for the closest basis functions) to 6 radii; inside (dielectrics): |x| < 0.55
-    X = np.vstack([points_outside(24, 1, 1.3, 6.0), [[0.1, 0.2, 0.3], [1.3, -1.9, 0.7]]])       # + the two points of tests/Mie/EPFile
+    # outside: from 1.5 radii (78-point rule for the closest basis functions) to 6 radii; inside (dielectrics): |x| < 0.55
+    X = np.vstack([points_outside(24, 1, 1.5, 6.0), [[0.1, 0.2, 0.3], [1.3, -1.9, 0.7]]])       # + the two points of tests/Mie/EPFile
     if "PEC" not in name:
         X = np.vstack([X, points_outside(10, 2, 0.0, 0.55)])
     RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, points=X)
@@ -49,7 +49,7 @@ def test_fields_outside_and_inside(ps, name, omega):
 
 def test_two_bodies_and_rf_matrix(ps):
     name, omega = "E10Spheres_327.scuffgeo", 1.0
-    X = np.vstack([points_outside(12, 3, 1.4, 3.0, (0, 0, 1.5)) + [[3.0, 0, 0]], points_outside(4, 4, 0.0, 0.5, (0, 0, 3.0)), points_outside(4, 5, 0.0, 0.5)])
+    X = np.vstack([points_outside(12, 3, 1.5, 3.0, (0, 0, 1.5)) + [[3.0, 0, 0]], points_outside(4, 4, 0.0, 0.5, (0, 0, 3.0)), points_outside(4, 5, 0.0, 0.5)])
     RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, points=X, rf=True)
     G = ps.RWGGeometry(geo(name))
     KN = G.AllocateRHSVector(); KN.set(KNr)
