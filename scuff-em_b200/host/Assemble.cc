@@ -343,6 +343,12 @@ HMatrix *RWGGeometry::AssembleBEMMatrix(cdouble Omega, double *kBloch, HMatrix *
   else if (M->NR != TotalBFs || M->NC != TotalBFs)
    { Warn("wrong-size matrix passed to AssembleBEMMatrix; reallocating...");
      M = AllocateBEMMatrix(); }
+  // SCUFF_CUDA_LAZY_HOST=1: return with the matrix in HBM only (M->HostStale).  LUFactorize / LUSolve / InsertBlock / the RHS,
+  // PFT and field routines work on the device copy; the HMatrix accessors (GetEntry, SetEntry, ...) fetch it on first use.  For
+  // callers that never read M->ZM / M->DM directly — the assemble -> LUFactorize -> LUSolve flow of scuff-scatter
+  // (scuff-scatter.cc:402-472) — nothing else changes and the 16 N^2 bytes never cross PCIe.
+  { const char *lazy = getenv("SCUFF_CUDA_LAZY_HOST");
+    if (lazy && lazy[0] == '1') { AssembleBEMMatrixDevice(Omega, kBloch, M); return M; } }
   int K = PipelineBlocks(TotalBFs);
   // "upper" halves the PCIe bytes but spends host memory bandwidth on the mirror (a read and a write per byte against one write
   // for a DMA copy): right for one process per host, wrong when several ranks share the host's memory system (measured on a

@@ -110,3 +110,31 @@ def test_derivative_blocks_through_the_binding(tmp_path):
         err = np.linalg.norm(outs[1][q] - outs[0][q]) / np.linalg.norm(outs[0][q])
         print("hooked reference", lab, "rel err %.3e" % err)
         assert err <= 1e-10
+
+
+def test_scuff_scatter_rhs_and_pft_through_the_binding(tmp_path):
+    """SURVEY 8 row f2 through the reference's own application: with the cubature integrals selected (SCUFF_EMTPFTI_METHOD=0) the hooked
+    scuff-scatter also assembles its right-hand side and evaluates the EMTPFT sums on the device (hooks in AssembleRHSVector and
+    GetEMTPFTMatrix); output file against the unmodified CPU run with the same setting.  Two spheres: every surface-pair branch."""
+    _need("scuff-scatter", "scuff-scatter_cuda")
+    rows = {}
+    for tag, binary, cuda in (("cpu", "scuff-scatter", False), ("cuda", "scuff-scatter_cuda", True)):
+        d = tmp_path / tag; d.mkdir()
+        for f in ("E10Spheres_327.scuffgeo", "Sphere_327.msh"):
+            os.symlink(os.path.join(GEODIR, f), str(d / f))
+        env = dict(os.environ, OMP_NUM_THREADS="8", SCUFF_EMTPFTI_METHOD="0")
+        env.pop("SCUFF_CUDA", None)
+        if cuda:
+            env.update(SCUFF_CUDA="1", SCUFF_CUDA_VERBOSE="1")
+        cmd = [os.path.join(REFDIR, binary), "--geometry", "E10Spheres_327.scuffgeo", "--Omega", "0.8", "--PWDirection", "0", "0", "1",
+               "--PWPolarization", "1", "0", "0", "--EMTPFTFile", "out.EMTPFT"]
+        r = subprocess.run(cmd, cwd=str(d), capture_output=True, text=True, env=env, stdin=subprocess.DEVNULL, timeout=600)
+        assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+        if cuda:
+            assert "1 right-hand sides, 1 EMTPFT evaluations on the device" in r.stderr, r.stderr[-500:]
+        rows[tag] = np.array([[float(x) for x in l.split()[2:]] for l in open(d / "out.EMTPFT") if not l.startswith("#")])
+    assert rows["cpu"].shape == rows["cuda"].shape and rows["cpu"].shape[0] == 2      # one row per sphere
+    scale = np.abs(rows["cpu"]).max(axis=1, keepdims=True)
+    err = np.abs(rows["cuda"] - rows["cpu"]) / scale
+    print("scuff-scatter (RHS + EMTPFT on the device) cpu vs cuda:", err.max()); print(rows["cpu"], rows["cuda"])
+    assert err.max() <= 2e-6          # the application prints 7 significant digits

@@ -123,3 +123,25 @@ def test_origin_follows_transform(ps):
     assert np.allclose(G.surface_origin(0), [0, 0, 3.4])
     G.untransform()
     assert np.allclose(G.surface_origin(0), [0, 0, 3])
+
+
+def test_lazy_host_mode(ps, monkeypatch):
+    """SCUFF_CUDA_LAZY_HOST=1: AssembleBEMMatrix (the reference-facing call) leaves the matrix in HBM; accessors fetch on demand"""
+    name, omega = "PECSphere_501.scuffgeo", 1.0
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X)
+    G = ps.RWGGeometry(geo(name))
+    ctx = ps.context(); nbytes = (ps.C.c_ulonglong * 2)()
+    ps.cuda_lib().scuffcuda_get_transfer_bytes(ctx, nbytes); d2h0 = nbytes[1]
+    monkeypatch.setenv("SCUFF_CUDA_LAZY_HOST", "1")
+    M = G.AssembleBEMMatrix(omega)                        # to_host=True path
+    monkeypatch.delenv("SCUFF_CUDA_LAZY_HOST")
+    assert M.state()["HostStale"]
+    IF = ps.PlaneWave(*PW_X)
+    KN = G.AssembleRHSVector(omega, IF)
+    M.lu_factorize(); M.lu_solve_vector(KN)
+    P = G.GetPFTMatrix(KN, omega, IF, EMTPFTIMethod=0)
+    ps.cuda_lib().scuffcuda_get_transfer_bytes(ctx, nbytes)
+    assert nbytes[1] - d2h0 < 64 * 1024                   # the matrix (4 MB) and the vectors never crossed PCIe
+    assert pft_err(P, PFTr) <= 1e-6
+    M2 = G.AssembleBEMMatrix(omega)                       # default mode: host copy current
+    assert not M2.state()["HostStale"]
