@@ -280,7 +280,18 @@ __device__ __forceinline__ void pft_kernels(double k, double r2, cd &Phi, cd &Ps
 
 // one cubature point pair: a* = conjugated currents at the point of surface a, b = currents at the point of surface b;
 // acc[0] PScat, acc[1..3] force density, acc[4..6] first torque term — all without the weights of point a.
-// HASN: both surfaces carry magnetic currents (if either is PEC the reference drops every N bilinear, GetPFT.cc:103-109)
+// HASN: both surfaces carry magnetic currents (if either is PEC the reference drops every N bilinear, GetPFT.cc:103-109).
+// With S1p = ZVAC mu (K*.K' - div K* div K'/k^2) + (eps/ZVAC)(N*.N' - ...), V1 = ZVAC mu K* x K' + (eps/ZVAC) N* x N',
+// C = K* x N' - N* x K', PM = C.R, D = (K*.R) N' - (N*.R) K' - R (K*.N' - N*.K'), the integrands of EMTPFT.cc:131-175 are
+//   PScat  = -Re( i w S1p Phi + PM Psi )                 = w Im(S1p Phi) - Re(PM Psi)
+//   F_m    = -Im( i S1p R_m Psi - (C_m Psi + PM R_m Zeta)/w ) = -R_m Re(S1p Psi) + Im(C_m Psi + PM R_m Zeta)/w
+//   T1_m   = -Im( i V1_m Phi - D_m Psi/w )               = -Re(V1_m Phi) + Im(D_m Psi)/w
+// SAME (one surface): Phi = i phi, Psi = i psi, Zeta = i zeta are purely imaginary (:103-121), so only
+//   PScat = w phi Re S1p + psi Im PM,  F_m = R_m psi Im S1p + (psi Re C_m + R_m zeta Re PM)/w,  T1_m = phi Im V1_m + psi Re D_m/w
+// are formed (half of the complex arithmetic; no Zeta at all without magnetic currents).
+__device__ __forceinline__ double cre(double ar, double ai, double br, double bi) { return ar * br - ai * bi; }
+__device__ __forceinline__ double cim(double ar, double ai, double br, double bi) { return ar * bi + ai * br; }
+
 template <bool HASN, bool SAME>
 __device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double xa[3],
                                                const double aKr[3], const double aKi[3], const double aNr[3], const double aNi[3],
@@ -288,8 +299,55 @@ __device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double 
                                                const CurPt &b, double acc[7])
 { double R[3]; for (int m = 0; m < 3; m++) R[m] = xa[m] - b.x[m];
   const double r2 = R[0] * R[0] + R[1] * R[1] + R[2] * R[2];
+  const double w = b.w, ft = TENTHIRDS * w, oow = 1.0 / Q.omega;
+  if (SAME)
+   { // imaginary parts of the kernels with the reference's small-argument series
+     const double k = Q.k, r = sqrt(r2), kr = k * r, kr2 = kr * kr, k2 = k * k;
+     double phi, psi, zeta = 0.0;
+     if (fabs(kr) < 1.0e-3)
+      { const double k3 = k2 * k;
+        phi = (1.0 - kr2 / 6.0) * k / (4.0 * M_PI);
+        psi = -(1.0 - kr2 / 10.0) * k3 / (12.0 * M_PI);
+        if (HASN) zeta = (1.0 - kr2 / 14.0) * (k3 * k2) / (60.0 * M_PI); }
+     else
+      { double sn, cs; sincos(kr, &sn, &cs);
+        const double r3 = r * r2;
+        phi = sn / (4.0 * M_PI * r);
+        psi = (kr * cs - sn) / (4.0 * M_PI * r3);
+        if (HASN) zeta = (-3.0 * kr * cs + (3.0 - kr2) * sn) / (4.0 * M_PI * (r3 * r2)); }
+     double kkr = 0, kki = 0, nnr = 0, nni = 0, knr = 0, nkr = 0, aRr = 0, nRr = 0, aRi = 0, nRi = 0, kni = 0, nki = 0;
+     for (int m = 0; m < 3; m++)
+      { kkr += cre(aKr[m], aKi[m], b.Kr[m], b.Ki[m]); kki += cim(aKr[m], aKi[m], b.Kr[m], b.Ki[m]);
+        if (HASN)
+         { nnr += cre(aNr[m], aNi[m], b.Nr[m], b.Ni[m]); nni += cim(aNr[m], aNi[m], b.Nr[m], b.Ni[m]);
+           knr += cre(aKr[m], aKi[m], b.Nr[m], b.Ni[m]); kni += cim(aKr[m], aKi[m], b.Nr[m], b.Ni[m]);
+           nkr += cre(aNr[m], aNi[m], b.Kr[m], b.Ki[m]); nki += cim(aNr[m], aNi[m], b.Kr[m], b.Ki[m]);
+           aRr += aKr[m] * R[m]; aRi += aKi[m] * R[m]; nRr += aNr[m] * R[m]; nRi += aNi[m] * R[m]; } }
+     double s1r = (kkr - cre(adKr, adKi, b.dKr, b.dKi) * Q.ook2) * Q.zmu, s1i = (kki - cim(adKr, adKi, b.dKr, b.dKi) * Q.ook2) * Q.zmu;
+     if (HASN) { s1r += (nnr - cre(adNr, adNi, b.dNr, b.dNi) * Q.ook2) * Q.eoz; s1i += (nni - cim(adNr, adNi, b.dNr, b.dNi) * Q.ook2) * Q.eoz; }
+     double Cr[3], Ci[3], V1i[3], Dr[3];
+     for (int m = 0; m < 3; m++)
+      { const int m1 = (m + 1) % 3, m2 = (m + 2) % 3;
+        V1i[m] = (cim(aKr[m1], aKi[m1], b.Kr[m2], b.Ki[m2]) - cim(aKr[m2], aKi[m2], b.Kr[m1], b.Ki[m1])) * Q.zmu;
+        if (HASN)
+         { V1i[m] += (cim(aNr[m1], aNi[m1], b.Nr[m2], b.Ni[m2]) - cim(aNr[m2], aNi[m2], b.Nr[m1], b.Ni[m1])) * Q.eoz;
+           Cr[m] = (cre(aKr[m1], aKi[m1], b.Nr[m2], b.Ni[m2]) - cre(aKr[m2], aKi[m2], b.Nr[m1], b.Ni[m1]))
+                 - (cre(aNr[m1], aNi[m1], b.Kr[m2], b.Ki[m2]) - cre(aNr[m2], aNi[m2], b.Kr[m1], b.Ki[m1]));
+           Ci[m] = (cim(aKr[m1], aKi[m1], b.Nr[m2], b.Ni[m2]) - cim(aKr[m2], aKi[m2], b.Nr[m1], b.Ni[m1]))
+                 - (cim(aNr[m1], aNi[m1], b.Kr[m2], b.Ki[m2]) - cim(aNr[m2], aNi[m2], b.Kr[m1], b.Ki[m1]));
+           Dr[m] = cre(aRr, aRi, b.Nr[m], b.Ni[m]) - cre(nRr, nRi, b.Kr[m], b.Ki[m]) - (knr - nkr) * R[m]; } }
+     double p = Q.omega * phi * s1r, pmr = 0.0;
+     if (HASN) { pmr = Cr[0] * R[0] + Cr[1] * R[1] + Cr[2] * R[2]; p += psi * (Ci[0] * R[0] + Ci[1] * R[1] + Ci[2] * R[2]); }
+     acc[0] += w * p;
+     const double psis1 = psi * s1i;
+     for (int m = 0; m < 3; m++)
+      { double f = R[m] * psis1, t = phi * V1i[m];
+        if (HASN) { f += (psi * Cr[m] + R[m] * zeta * pmr) * oow; t += psi * Dr[m] * oow; }
+        acc[1 + m] += ft * f; acc[4 + m] += ft * t; }
+     (void)kni; (void)nki;
+     return; }
   cd Phi, Psi, Zeta;
-  pft_kernels<SAME>(Q.k, r2, Phi, Psi, Zeta);
+  pft_kernels<false>(Q.k, r2, Phi, Psi, Zeta);
   // conj(K_a) = (aKr, -aKi) etc. are passed already conjugated
   cd kk = mk(0.0, 0.0), nn = mk(0.0, 0.0), kn = mk(0.0, 0.0), nk = mk(0.0, 0.0), aR = mk(0.0, 0.0), nR = mk(0.0, 0.0);
   for (int m = 0; m < 3; m++)
@@ -315,8 +373,6 @@ __device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double 
         C[m] = (a1 * q2 - a2 * q1) - (n1 * b2 - n2 * b1);
         D[m] = aR * mk(b.Nr[m], b.Ni[m]) - nR * mk(b.Kr[m], b.Ki[m]) - (kn - nk) * R[m]; }
      else { C[m] = mk(0.0, 0.0); D[m] = mk(0.0, 0.0); } }
-  const double w = b.w, ft = TENTHIRDS * w, oow = 1.0 / Q.omega;
-  // PScat: -Re( i omega S1p Phi + PM Psi ) = omega Im(S1p Phi) - Re(PM Psi)
   const cd sPhi = S1p * Phi, sPsi = S1p * Psi;
   double p = Q.omega * sPhi.y;
   cd PM = mk(0.0, 0.0);
@@ -324,9 +380,7 @@ __device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double 
   acc[0] += w * p;
   const cd pmZ = PM * Zeta;
   for (int m = 0; m < 3; m++)
-   { // force: -Im( i S1p R Psi - (C Psi + PM R Zeta)/omega ) = -R Re(S1p Psi) + Im(C Psi + PM R Zeta)/omega
-     double f = -R[m] * sPsi.x;
-     // first torque term: -Im( i V1 Phi - D Psi/omega ) = -Re(V1 Phi) + Im(D Psi)/omega
+   { double f = -R[m] * sPsi.x;
      double t = -(V1[m] * Phi).x;
      if (HASN) { f += ((C[m] * Psi).y + pmZ.y * R[m]) * oow; t += (D[m] * Psi).y * oow; }
      acc[1 + m] += ft * f; acc[4 + m] += ft * t; }
@@ -400,9 +454,10 @@ __device__ __forceinline__ void bf_point(const EdgeRec &E, int pm, double u, dou
 
 template <bool HASN, bool SAME>
 __global__ void __launch_bounds__(PFT_THREADS) pft_near_kernel(const __grid_constant__ NearPftArgs X)
-{ const int lane = threadIdx.x & 31, wid = blockIdx.x * (PFT_THREADS / 32) + (threadIdx.x >> 5);
+{ const int lane = threadIdx.x & 31;
   double v[PFT_NQ]; for (int q = 0; q < PFT_NQ; q++) v[q] = 0.0;
-  if (wid < X.n)
+  // grid-stride over the pairs: a fixed number of CTAs (and partial sums), one warp per pair at a time
+  for (int wid = blockIdx.x * (PFT_THREADS / 32) + (threadIdx.x >> 5); wid < X.n; wid += gridDim.x * (PFT_THREADS / 32))
    { const NearBF P = X.list[wid];
      const EdgeRec &EA = X.ea[P.ea], &EB = X.eb[P.eb];
      const int rowA = X.offA + (X.pecA ? P.ea : 2 * P.ea), rowB = X.offB + (X.pecB ? P.eb : 2 * P.eb);
@@ -749,7 +804,7 @@ int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_
       const int gx = (nA + PFT_THREADS - 1) / PFT_THREADS;
       int gy = std::max(1, std::min((4 * ctx->smCount + gx - 1) / gx, (nB + PFT_TILE - 1) / PFT_TILE));
       int chunk = (nB + gy - 1) / gy; chunk = ((chunk + PFT_TILE - 1) / PFT_TILE) * PFT_TILE; gy = (nB + chunk - 1) / chunk;
-      const int nearBlocks = (L.n + PFT_THREADS / 32 - 1) / (PFT_THREADS / 32);
+      const int nearBlocks = std::min((L.n + PFT_THREADS / 32 - 1) / (PFT_THREADS / 32), 8 * ctx->smCount);
       const size_t nblocks = (size_t)gx * gy + nearBlocks;
       if (grow(ctx, P->dpart, P->partCap, nblocks * PFT_NQ)) return 1;
       PairArgs X; X.A = CA; X.nA = nA; X.B = CB; X.nB = nB; X.bChunk = chunk; X.Q = Q; X.part = P->dpart;

@@ -141,7 +141,7 @@ def test_lazy_host_mode(ps, monkeypatch):
     M.lu_factorize(); M.lu_solve_vector(KN)
     P = G.GetPFTMatrix(KN, omega, IF, EMTPFTIMethod=0)
     ps.cuda_lib().scuffcuda_get_transfer_bytes(ctx, nbytes)
-    assert nbytes[1] - d2h0 < 64 * 1024                   # the matrix (4 MB) and the vectors never crossed PCIe
+    assert nbytes[1] - d2h0 < 512 * 1024                  # per-CTA partial sums only: the matrix (4 MB) never crossed PCIe
     assert pft_err(P, PFTr) <= 1e-6
     M2 = G.AssembleBEMMatrix(omega)                       # default mode: host copy current
     assert not M2.state()["HostStale"]
