@@ -585,7 +585,7 @@ def main():
         warm = info["times"][1]
         npairs = len(rec)
         line["cpu_baseline"] = {"value": 2.0 * npairs / warm / 1e9, "unit": UNIT, "cores": info["threads"], "kind": "reference",
-                                "sample": "%d seeded random edge pairs + all %d pairs of a %d-edge patch of the same mesh through the reference's "
+                                "sample": "%d seeded random edge pairs (each in the order nea<=neb in which the reference's assembly evaluates it) + all %d pairs of a %d-edge patch of the same mesh through the reference's "
                                           "GetEdgeEdgeInteractions (OpenMP, pinned, warm FIPPI cache %.2f s; cold pass %.2f s); full-matrix elements = "
                                           "2 x unique edge pairs" % (info.get("n_random", a.ref_pairs), info.get("n_patch", 0), a.parity_patch, warm, info["times"][0])}
         # parity at full size: M[nea,neb] = i*omega*GC0 (PEC in vacuum, SurfaceSurfaceInteractions.cc:165-176,205-217)

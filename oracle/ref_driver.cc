@@ -394,7 +394,10 @@ int main(int argc, char **argv)
      unsigned long long x=Seed*2862933555777941757ULL+3037000493ULL;   // 64-bit LCG (Knuth MMIX constants below)
      for(long n=0;n<NRandom;n++)
       { x=x*6364136223846793005ULL+1442695040888963407ULL; ea[n]=(int)((x>>33)%(unsigned long long)NE);
-        x=x*6364136223846793005ULL+1442695040888963407ULL; eb[n]=(int)((x>>33)%(unsigned long long)NE); }
+        x=x*6364136223846793005ULL+1442695040888963407ULL; eb[n]=(int)((x>>33)%(unsigned long long)NE);
+        // the reference's assembly evaluates a pair in the order nea<=neb and mirrors (SurfaceSurfaceInteractions.cc:140-150,573-583); its
+        // near-singular integrals are not symmetric under exchanging the panels, so the sample must ask for the same order
+        if(ea[n]>eb[n]) { int t=ea[n]; ea[n]=eb[n]; eb[n]=t; } }
      { long n=NRandom; for(int a=0;a<Patch;a++) for(int b=a;b<Patch;b++,n++) { ea[n]=a; eb[n]=b; } }
      printf("{\"n\": %li, \"NE\": %i, \"threads\": %i, \"times\": [",NPairs,NE,omp_get_max_threads());
      for(int r=0;r<Repeat;r++)

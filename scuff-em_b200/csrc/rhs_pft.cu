@@ -30,6 +30,7 @@
 #include <complex>
 #include <string>
 #include "kernels.h"
+#include "fastmath.cuh"
 #include "generated_tcr20.h"
 #include "generated_tcr9.h"
 #include "generated_tcr7.h"
@@ -251,31 +252,15 @@ pft_currents_kernel(const PanelRec *panels, int NP, const double *tcr, int npts,
 
 __device__ __forceinline__ cd cmul_helper(cd a, cd b, double s) { const cd p = a * b; return mk(p.x * s, p.y * s); }
 
-// Phi, Psi, Zeta of ScatteredPFTIntegrand1 (EMTPFT.cc:98-128).  SAME: imaginary parts only, with the reference's
-// small-argument series; otherwise the complex kernels.
-template <bool SAME>
-__device__ __forceinline__ void pft_kernels(double k, double r2, cd &Phi, cd &Psi, cd &Zeta)
-{ const double r = sqrt(r2), kr = k * r, kr2 = kr * kr, k2 = k * k;
-  if (SAME)
-   { double iPhi, iPsi, iZeta;
-     if (fabs(kr) < 1.0e-3)
-      { const double k3 = k2 * k, k5 = k3 * k2;
-        iPhi = (1.0 - kr2 / 6.0) * k / (4.0 * M_PI);
-        iPsi = -(1.0 - kr2 / 10.0) * k3 / (12.0 * M_PI);
-        iZeta = (1.0 - kr2 / 14.0) * k5 / (60.0 * M_PI); }
-     else
-      { double s, c; sincos(kr, &s, &c);
-        const double r3 = r * r2, r5 = r3 * r2;
-        iPhi = s / (4.0 * M_PI * r);
-        iPsi = (kr * c - s) / (4.0 * M_PI * r3);
-        iZeta = (-3.0 * kr * c + (3.0 - kr2) * s) / (4.0 * M_PI * r5); }
-     Phi = mk(0.0, iPhi); Psi = mk(0.0, iPsi); Zeta = mk(0.0, iZeta); }
-  else
-   { double s, c; sincos(kr, &s, &c);
-     const double g = 1.0 / (4.0 * M_PI * r);
-     Phi = mk(c * g, s * g);
-     Psi = cmul_helper(Phi, mk(-1.0, kr), 1.0 / r2);
-     Zeta = cmul_helper(Phi, mk(3.0 - kr2, -3.0 * kr), 1.0 / (r2 * r2)); }
+// complex Phi, Psi, Zeta of ScatteredPFTIntegrand1 for two different surfaces (EMTPFT.cc:122-128); the same-surface
+// (imaginary parts only) variant is inlined in pft_point_pair
+__device__ __forceinline__ void pft_kernels_complex(double k, double r2, cd &Phi, cd &Psi, cd &Zeta)
+{ const double rinv = rsqrt_fast(r2), r = r2 * rinv, kr = k * r, kr2 = kr * kr;
+  double s, c; sincos_fast(kr, s, c);
+  const double g = rinv * (1.0 / (4.0 * M_PI)), rinv2 = rinv * rinv;
+  Phi = mk(c * g, s * g);
+  Psi = cmul_helper(Phi, mk(-1.0, kr), rinv2);
+  Zeta = cmul_helper(Phi, mk(3.0 - kr2, -3.0 * kr), rinv2 * rinv2);
 }
 
 // one cubature point pair: a* = conjugated currents at the point of surface a, b = currents at the point of surface b;
@@ -302,7 +287,9 @@ __device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double 
   const double w = b.w, ft = TENTHIRDS * w, oow = 1.0 / Q.omega;
   if (SAME)
    { // imaginary parts of the kernels with the reference's small-argument series
-     const double k = Q.k, r = sqrt(r2), kr = k * r, kr2 = kr * kr, k2 = k * k;
+     // r = r2/sqrt(r2) and 1/r from one branch-free rsqrt, sin/cos by the far kernel's branch-free FP64 routines (fastmath.cuh);
+     // the reference's expressions (kr cos kr - sin kr) etc. are kept as they are (their cancellation is part of its answer)
+     const double k = Q.k, rinv = rsqrt_fast(fmax(r2, 1.0e-300)), r = r2 * rinv, kr = k * r, kr2 = kr * kr, k2 = k * k;
      double phi, psi, zeta = 0.0;
      if (fabs(kr) < 1.0e-3)
       { const double k3 = k2 * k;
@@ -310,11 +297,11 @@ __device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double 
         psi = -(1.0 - kr2 / 10.0) * k3 / (12.0 * M_PI);
         if (HASN) zeta = (1.0 - kr2 / 14.0) * (k3 * k2) / (60.0 * M_PI); }
      else
-      { double sn, cs; sincos(kr, &sn, &cs);
-        const double r3 = r * r2;
-        phi = sn / (4.0 * M_PI * r);
-        psi = (kr * cs - sn) / (4.0 * M_PI * r3);
-        if (HASN) zeta = (-3.0 * kr * cs + (3.0 - kr2) * sn) / (4.0 * M_PI * (r3 * r2)); }
+      { double sn, cs; sincos_fast(kr, sn, cs);
+        const double g = rinv * (1.0 / (4.0 * M_PI)), rinv2 = rinv * rinv, g3 = g * rinv2;
+        phi = sn * g;
+        psi = (kr * cs - sn) * g3;
+        if (HASN) zeta = (-3.0 * kr * cs + (3.0 - kr2) * sn) * (g3 * rinv2); }
      double kkr = 0, kki = 0, nnr = 0, nni = 0, knr = 0, nkr = 0, aRr = 0, nRr = 0, aRi = 0, nRi = 0, kni = 0, nki = 0;
      for (int m = 0; m < 3; m++)
       { kkr += cre(aKr[m], aKi[m], b.Kr[m], b.Ki[m]); kki += cim(aKr[m], aKi[m], b.Kr[m], b.Ki[m]);
@@ -347,7 +334,7 @@ __device__ __forceinline__ void pft_point_pair(const PftParams &Q, const double 
      (void)kni; (void)nki;
      return; }
   cd Phi, Psi, Zeta;
-  pft_kernels<false>(Q.k, r2, Phi, Psi, Zeta);
+  pft_kernels_complex(Q.k, r2, Phi, Psi, Zeta);
   // conj(K_a) = (aKr, -aKi) etc. are passed already conjugated
   cd kk = mk(0.0, 0.0), nn = mk(0.0, 0.0), kn = mk(0.0, 0.0), nk = mk(0.0, 0.0), aR = mk(0.0, 0.0), nR = mk(0.0, 0.0);
   for (int m = 0; m < 3; m++)
@@ -765,6 +752,11 @@ int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_
      const int nbf = S.isPEC ? S.NE : 2 * S.NE;
      if (a->bf_offsets[ns] < 0 || a->bf_offsets[ns] + nbf > KN->NR) return pfail(ctx, "emtpft: basis-function offsets do not fit the vector");
      if (ensure_edges(ctx, S)) return 1; }
+  double extent = 0.0;
+  { double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+    for (int ns = 0; ns < NS; ns++) { const Surface &S = ctx->surfaces[ns]; for (int v = 0; v < S.NV; v++) for (int m = 0; m < 3; m++) { lo[m] = fmin(lo[m], S.V[3 * (size_t)v + m]); hi[m] = fmax(hi[m], S.V[3 * (size_t)v + m]); } }
+    for (int m = 0; m < 3; m++) extent += (hi[m] - lo[m]) * (hi[m] - lo[m]);
+    extent = sqrt(extent); }
   CurPt *cur4 = P->dcur, *cur4k = P->dcur + off4[NS], *cur9 = P->dcur + 2 * off4[NS];
   for (int ns = 0; ns < NS; ns++)
    { Surface &S = ctx->surfaces[ns]; const int n4 = S.NP * 6, n9 = S.NP * SC_TCR9_NPTS;
@@ -794,6 +786,7 @@ int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_
       const cx eps(a->eps_mu[4 * region], a->eps_mu[4 * region + 1]), mu(a->eps_mu[4 * region + 2], a->eps_mu[4 * region + 3]);
       const cx kc = a->omega[0] * std::sqrt(eps * mu);
       PftParams Q;
+      if (fabs(kc.real()) * extent >= SCUFF_MAX_KR) return pfail(ctx, "emtpft: |k| x (extent of the geometry) exceeds the range of the device sin/cos (1e5)");
       Q.k = kc.real(); Q.omega = a->omega[0]; Q.zmu = ZVAC * mu.real(); Q.eoz = eps.real() / ZVAC; Q.ook2 = 1.0 / (Q.k * Q.k);
       for (int m = 0; m < 3; m++) Q.origin[m] = a->origins[3 * sa + m];
       const bool hasN = !SA.isPEC && !SB.isPEC, same = (sa == sb);

@@ -9,7 +9,7 @@
 #include "libscuff_b200.h"
 using namespace scuff;
 
-struct Result { double fro, trRe, trIm, x0Re, x0Im; int worker; };
+struct Result { double fro, trRe, trIm, x0Re, x0Im; double pabs, pscat, fz; int worker; };
 
 static void Point(RWGGeometry *G, HMatrix *M, cdouble Omega, double *kBloch, int j, int w, void *ud)
 { (void)G; (void)Omega; (void)kBloch;
@@ -23,6 +23,16 @@ static void Point(RWGGeometry *G, HMatrix *M, cdouble Omega, double *kBloch, int
   for (int r = 0; r < M->NR; r++) X.SetEntry(r, 0, cdouble(1.0 + 0.001 * r, 0.5));
   M->LUFactorize(); M->LUSolve(&X);
   R->x0Re = real(X.GetEntry(0, 0)); R->x0Im = imag(X.GetEntry(0, 0));
+  // the rest of a scuff-scatter frequency point on the worker's device: plane-wave right-hand side, solve on the
+  // device-resident vector, energy/momentum-transfer power and force — the loop body of scuff-scatter.cc:466-520
+  cdouble E0[3] = { 1.0, 0.0, 0.0 }; double nHat[3] = { 0.0, 0.0, 1.0 };
+  PlaneWave PW(E0, nHat);
+  HVector *KN = G->AssembleRHSVector(Omega, &PW, 0);
+  M->LUSolve(KN);
+  PFTOptions Opts; InitPFTOptions(&Opts); Opts.IF = &PW; Opts.EMTPFTIMethod = SCUFF_EMTPFTI_EHDERIVATIVES1;
+  HMatrix *PFT = G->GetPFTMatrix(KN, Omega, &Opts, 0);
+  R->pabs = PFT->GetEntryD(0, PFT_PABS); R->pscat = PFT->GetEntryD(0, PFT_PSCAT); R->fz = PFT->GetEntryD(0, PFT_ZFORCE);
+  delete PFT; delete KN;
 }
 
 int main(int argc, char **argv)
@@ -44,9 +54,13 @@ int main(int argc, char **argv)
    { worst = fmax(worst, fabs(many[j].fro - one[j].fro) / one[j].fro);
      worst = fmax(worst, hypot(many[j].trRe - one[j].trRe, many[j].trIm - one[j].trIm) / hypot(one[j].trRe, one[j].trIm));
      worst = fmax(worst, hypot(many[j].x0Re - one[j].x0Re, many[j].x0Im - one[j].x0Im) / hypot(one[j].x0Re, one[j].x0Im));
+     worst = fmax(worst, fabs(many[j].pscat - one[j].pscat) / fabs(one[j].pscat));
+     worst = fmax(worst, fabs(many[j].pabs - one[j].pabs) / fabs(one[j].pscat));
+     worst = fmax(worst, fabs(many[j].fz - one[j].fz) / fabs(one[j].fz));
      if (many[j].worker != j % W) { printf("{\"error\": \"point %d ran on worker %d\"}\n", j, many[j].worker); return 1; }
      counts[many[j].worker & 15]++; }
-  printf("{\"points\": %d, \"workers\": %d, \"worst_rel_diff\": %.3e, \"cold_s_one_worker\": %.3f, \"cold_s_first\": %.3f, \"cold_s_last\": %.3f, \"points_worker0\": %d}\n",
+  printf("{\"pscat_first\": %.6e, \"pscat_last\": %.6e, ", many[0].pscat, many[NP - 1].pscat);
+  printf("\"points\": %d, \"workers\": %d, \"worst_rel_diff\": %.3e, \"cold_s_one_worker\": %.3f, \"cold_s_first\": %.3f, \"cold_s_last\": %.3f, \"points_worker0\": %d}\n",
          NP, W, worst, cold1, coldW0, coldW1, counts[0]);
   return worst <= 1e-9 ? 0 : 1;
 }

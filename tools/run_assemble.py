@@ -14,6 +14,7 @@ ap.add_argument("--far-only", action="store_true")
 ap.add_argument("--material", default=None)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--imag", action="store_true")
+ap.add_argument("--pft", action="store_true", help="skip the assembly: RHS of a plane wave + EMTPFT sums with that vector as the solution (kernel timing only)")
 a = ap.parse_args()
 if a.far_only:
     os.environ["SCUFF_CUDA_FAR_ONLY"] = "1"
@@ -22,6 +23,15 @@ G = ps.RWGGeometry(geo)
 M = G.AllocateBEMMatrix(a.imag)
 peak = ps.measure_fp64_peak()
 P = G.TotalPanels
+if a.pft:
+    import numpy as np
+    IF = ps.PlaneWave((1.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+    KN = G.AssembleRHSVector(a.omega, IF)
+    for r in range(a.reps):
+        t0 = time.time(); Pm = G.GetPFTMatrix(KN, a.omega, IF, EMTPFTIMethod=0); wall = time.time() - t0
+        npt = 6.0 * P
+        print(json.dumps(dict(N=G.TotalBFs, panels=P, pft_wall_s=wall, point_pairs=npt * npt, gpairs_per_s=npt * npt / wall / 1e9, pft=[float(v) for v in Pm[0]])))
+    sys.exit(0)
 for r in range(a.reps):
     t0 = time.time()
     G.AssembleBEMMatrix(a.omega, M=M, to_host=False)
