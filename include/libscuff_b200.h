@@ -241,6 +241,13 @@ typedef struct PFTOptions
    int EMTPFTIMethod;
    bool Itemize;
    bool GetRegionPFTs;
+   /* displaced-surface-integral method (SCUFF_PFT_DSI): bounding mesh, or a Lebedev rule of DSIPoints points on a sphere of
+    * DSIRadius (0 = 1.5 x the surface's extent about its origin, GetPFT.cc:73-86)                                           */
+   char *DSIMesh;
+   double DSIRadius;
+   int DSIPoints;
+   bool DSIFarField;
+   char *FluxFileName;
  } PFTOptions;
 PFTOptions *InitPFTOptions(PFTOptions *Options = 0);
 
@@ -374,6 +381,11 @@ class RWGGeometry
    bool PointInRegion(int nr, const double X[3]);
    unsigned long long LastPPICounts[5];
  };
+
+/* GetDSIPFT (DSIPFT.cc:449-590): Poynting vector and Maxwell stress tensor integrated over a surface that encloses the body; the
+ * fields at its cubature points come from GetFields on the device.  GT-transformed like the surface (OTGT, then GT).       */
+void GetDSIPFT(RWGGeometry *G, cdouble Omega, double *kBloch, HVector *KN, IncField *IF, double PFT[NUMPFT],
+               char *DSIMesh, double DSIRadius, int DSIPoints, bool FarField, char *PlotFileName, void *GT1, void *GT2);
 
 /* EMTPFT.cc:533-905 on the device.  Only the cubature integrals SCUFF_EMTPFTI_EHDERIVATIVES1 (Options->EMTPFTIMethod = 0 or
  * SCUFF_EMTPFTI_METHOD=0 in the environment) are available; the reference's default (EHDERIVATIVES2, which goes through

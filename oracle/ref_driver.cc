@@ -13,11 +13,12 @@
  *        EdgeEdgeInteractions.cc:241-270): writes the value block, the three gradient blocks and the torque blocks one after
  *        the other (complex, or real with --imag as scuff-cas3D allocates them)
  *   ref_driver scatter <geo> <wRe> <wIm> <out.bin> --pw E0xr E0xi E0yr E0yi E0zr E0zi nx ny nz [--ps x y z Pxr Pxi Pyr Pyi Pzr Pzi]
- *                      [--interior] [--method m] [--transfile f --trans n] [--nopft] [--fields pts.bin [--rf]]
+ *                      [--interior] [--method m] [--transfile f --trans n] [--nopft] [--dsi radius npoints] [--fields pts.bin [--rf]]
  *        one frequency point of scuff-scatter (scuff-scatter.cc:402-520): AssembleBEMMatrix, AssembleRHSVector with the given
  *        incident-field chain (plane wave first, then an optional point source), LUFactorize, LUSolve, GetPFTMatrix by the
  *        energy/momentum-transfer method with integral method m (default 0 = SCUFF_EMTPFTI_EHDERIVATIVES1).  Writes RHS
  *        (TotalBFs complex), the solution KN (TotalBFs complex) and the PFT matrix (NumSurfaces x 8 doubles, row-major).
+ *        --dsi: then the PFT matrix by the displaced-surface-integral method (GetDSIPFT, DSIPFT.cc:449-590; radius 0 = automatic), NS x 8.
  *        --fields: then GetFields (GetFields.cc:336-395) at the points of pts.bin (raw doubles x,y,z): NX x 6 complex, row-major,
  *        appended; --rf: then GetRFMatrix (:141-330), TotalBFs x 6NX complex column-major, appended.
  *   ref_driver ssi    <geo> <wRe> <wIm> <nsa> <nsb> <Lx> <Ly> <Lz> <out.bin> [--cache-out f]
@@ -201,7 +202,7 @@ int main(int argc, char **argv)
 
   if(!strcmp(Cmd,"scatter"))
    { cdouble Omega(atof(argv[3]),atof(argv[4])); const char *Out=argv[5];
-     IncField *IFList=0, *Tail=0; bool Interior=false, NoPFT=false, WantRF=false; int Method=0; const char *TransFile=0, *PtsFile=0; int nTrans=0;
+     IncField *IFList=0, *Tail=0; bool Interior=false, NoPFT=false, WantRF=false, WantDSI=false; double DSIRadius=0.0; int DSIPoints=302; int Method=0; const char *TransFile=0, *PtsFile=0; int nTrans=0;
      for(int n=6;n<argc;n++)
       { IncField *New=0;
         if(!strcmp(argv[n],"--pw") && n+9<argc)
@@ -215,6 +216,7 @@ int main(int argc, char **argv)
         else if(!strcmp(argv[n],"--interior")) Interior=true;
         else if(!strcmp(argv[n],"--nopft")) NoPFT=true;
         else if(!strcmp(argv[n],"--rf")) WantRF=true;
+        else if(!strcmp(argv[n],"--dsi")) { WantDSI=true; DSIRadius=atof(argv[n+1]); DSIPoints=atoi(argv[n+2]); n+=2; }
         else if(!strcmp(argv[n],"--fields")) PtsFile=argv[++n];
         else if(!strcmp(argv[n],"--method")) Method=atoi(argv[++n]);
         else if(!strcmp(argv[n],"--transfile")) TransFile=argv[++n];
@@ -243,6 +245,10 @@ int main(int argc, char **argv)
      FILE *f=fopen(Out,"wb"); if(!f) return 1;
      fwrite(RHS->ZV,sizeof(cdouble),RHS->N,f); fwrite(KN->ZV,sizeof(cdouble),KN->N,f);
      for(int ns=0;ns<G->NumSurfaces;ns++) for(int nq=0;nq<NUMPFT;nq++) { double v=PFT->GetEntryD(ns,nq); fwrite(&v,sizeof(double),1,f); }
+     if(WantDSI)
+      { PFTOptions Opts; InitPFTOptions(&Opts); Opts.PFTMethod=SCUFF_PFT_DSI; Opts.IF=IFList; Opts.DSIRadius=DSIRadius; Opts.DSIPoints=DSIPoints;
+        HMatrix *P2=G->GetPFTMatrix(KN,Omega,&Opts,0);
+        for(int ns=0;ns<G->NumSurfaces;ns++) for(int nq=0;nq<NUMPFT;nq++) { double v=P2->GetEntryD(ns,nq); fwrite(&v,sizeof(double),1,f); } }
      if(PtsFile)
       { FILE *fp=fopen(PtsFile,"rb"); if(!fp) return 1;
         fseek(fp,0,SEEK_END); long NX=ftell(fp)/(3*sizeof(double)); fseek(fp,0,SEEK_SET);

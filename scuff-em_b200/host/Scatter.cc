@@ -10,6 +10,7 @@
 #include <thread>
 #include <functional>
 #include "host_internal.h"
+#include "generated_lebedev.h"
 
 #define ZVAC 376.73031346177
 #define II cdouble(0.0, 1.0)
@@ -205,6 +206,7 @@ PFTOptions *InitPFTOptions(PFTOptions *Options)
 { if (Options == 0) Options = (PFTOptions *)calloc(1, sizeof(PFTOptions));
   Options->PFTMethod = SCUFF_PFT_DEFAULT; Options->IF = 0; Options->DRMatrix = 0; Options->kBloch = 0; Options->RHSVector = 0;
   Options->Interior = false; Options->EMTPFTIMethod = SCUFF_EMTPFTI_DEFAULT; Options->Itemize = false; Options->GetRegionPFTs = false;
+  Options->DSIMesh = 0; Options->DSIRadius = 0.0; Options->DSIPoints = 302; Options->DSIFarField = false; Options->FluxFileName = 0;
   return Options;
 }
 
@@ -275,6 +277,104 @@ HMatrix *GetEMTPFTMatrix(RWGGeometry *G, cdouble Omega, IncField *IF, HVector *K
   return PFTMatrix;
 }
 
+// ---- displaced-surface-integral PFT (DSIPFT.cc:261-590) ---------------------------------------------------------------------
+// cubature rule over the bounding surface: rows (x, y, z, nx, ny, nz, w) (GetSCRMatrix :261-347)
+static std::vector<double> GetSCRMatrix(const char *DSIMesh, double DSIRadius, int DSIPoints, const GTrans *GT1, const GTrans *GT2)
+{ std::vector<double> SCR;
+  if (DSIMesh)
+   { RWGSurface *BS = new RWGSurface(DSIMesh);
+     if (BS->ErrMsg) ErrExit("%s", BS->ErrMsg);
+     for (int np = 0; np < BS->NumPanels; np++)
+      { const double *X0 = BS->Panels[np]->Centroid, *ZHat = BS->Panels[np]->ZHat;
+        double Sign = 1.0, XP[3];
+        for (int m = 0; m < 3; m++) XP[m] = X0[m] + 0.1 * BS->Panels[np]->Radius * ZHat[m];
+        if (BS->Contains(XP)) Sign = -1.0;                  // Sign*ZHat is the outward normal
+        for (int m = 0; m < 3; m++) SCR.push_back(X0[m]);
+        for (int m = 0; m < 3; m++) SCR.push_back(Sign * ZHat[m]);
+        SCR.push_back(BS->Panels[np]->Area); }
+     delete BS; }
+  else
+   { const double *LRule = ScLebedevRule(DSIPoints);
+     if (LRule == 0) ErrExit("no Lebedev rule with %i points", DSIPoints);
+     const double R = DSIRadius, R2 = R * R;
+     for (int np = 0; np < DSIPoints; np++)
+      { for (int m = 0; m < 3; m++) SCR.push_back(R * LRule[4 * np + m]);
+        for (int m = 0; m < 3; m++) SCR.push_back(LRule[4 * np + m]);
+        SCR.push_back(R2 * LRule[4 * np + 3]); } }
+  const GTrans *GTs[2] = { GT1, GT2 };
+  for (int n = 0; n < 2; n++)
+   { if (!GTs[n]) continue;
+     for (size_t nr = 0; nr < SCR.size() / 7; nr++)
+      { double *X = &SCR[7 * nr], *nHat = X + 3, XP[3];
+        for (int m = 0; m < 3; m++) XP[m] = X[m] + nHat[m];
+        GTs[n]->Apply(X, 1); GTs[n]->Apply(XP, 1);
+        for (int m = 0; m < 3; m++) nHat[m] = XP[m] - X[m]; } }
+  return SCR;
+}
+
+// the 3x3 matrices sandwiched between the field vectors: Poynting flux, Maxwell stress, torque (GetNMatrices :358-428)
+static void GetNMatrices(const double nHat[3], const double X[3], const double XTorque[3], double NMatrix[NUMPFT][3][3])
+{ static const double LeviCivita[3][3][3] = { { { 0, 0, 0 }, { 0, 0, 1 }, { 0, -1, 0 } }, { { 0, 0, -1 }, { 0, 0, 0 }, { 1, 0, 0 } }, { { 0, 1, 0 }, { -1, 0, 0 }, { 0, 0, 0 } } };
+  memset(NMatrix, 0, NUMPFT * 9 * sizeof(double));
+  double (*P)[3] = NMatrix[PFT_PABS];
+  P[1][2] = nHat[0]; P[2][1] = -nHat[0]; P[2][0] = nHat[1]; P[0][2] = -nHat[1]; P[0][1] = nHat[2]; P[1][0] = -nHat[2];
+  for (int i = 0; i < 3; i++)
+   { double (*F)[3] = NMatrix[PFT_XFORCE + i];
+     for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++)
+       F[a][b] = (a == b ? -nHat[i] : 0.0) + (a == i ? nHat[b] : 0.0) + (b == i ? nHat[a] : 0.0);   // n_a d_ib + n_b d_ia - n_i d_ab
+   }
+  double D[3], DxN[3];
+  for (int m = 0; m < 3; m++) D[m] = X[m] - XTorque[m];
+  DxN[0] = D[1] * nHat[2] - D[2] * nHat[1]; DxN[1] = D[2] * nHat[0] - D[0] * nHat[2]; DxN[2] = D[0] * nHat[1] - D[1] * nHat[0];
+  for (int i = 0; i < 3; i++)
+   for (int a = 0; a < 3; a++)
+    for (int b = 0; b < 3; b++)
+     { double v = (a == b) ? -DxN[i] : 0.0;
+       for (int j = 0; j < 3; j++) v += LeviCivita[i][j][a] * D[j] * nHat[b] + LeviCivita[i][j][b] * D[j] * nHat[a];
+       NMatrix[PFT_XTORQUE + i][a][b] = v; }
+}
+static double HVMVP(const cdouble V1[3], const double M[3][3], const cdouble V2[3])
+{ double Sum = 0.0;
+  for (int Mu = 0; Mu < 3; Mu++) for (int Nu = 0; Nu < 3; Nu++) Sum += real(conj(V1[Mu]) * M[Mu][Nu] * V2[Nu]);
+  return Sum;
+}
+
+void GetDSIPFT(RWGGeometry *G, cdouble Omega, double *kBloch, HVector *KN, IncField *IF, double PFT[NUMPFT],
+               char *DSIMesh, double DSIRadius, int DSIPoints, bool FarField, char *PlotFileName, void *GT1, void *GT2)
+{ (void)FarField;
+  if (PlotFileName) Warn("GetDSIPFT: flux plots are not written by the device path");
+  std::vector<double> SCR = GetSCRMatrix(DSIMesh, DSIRadius, DSIPoints, (const GTrans *)GT1, (const GTrans *)GT2);
+  const int NX = (int)(SCR.size() / 7);
+  // all cubature points are assumed to lie in one region: that of the first point (DSIPFT.cc:473-481)
+  const int RegionIndex = G->GetRegionIndex(&SCR[0]);
+  if (RegionIndex < 0) ErrExit("GetDSIPFT: the bounding surface lies inside a PEC body");
+  cdouble EpsRel, MuRel; G->RegionMPs[RegionIndex]->GetEpsMu(Omega, &EpsRel, &MuRel);
+  const double TENTHIRDS = 3.33333333333333333333333;
+  const double EpsAbs = TENTHIRDS * real(EpsRel) / ZVAC, MuAbs = TENTHIRDS * real(MuRel) * ZVAC;
+  double XTorque[3] = { 0.0, 0.0, 0.0 };
+  if (GT1) ((const GTrans *)GT1)->Apply(XTorque, 1);
+  if (GT2) ((const GTrans *)GT2)->Apply(XTorque, 1);
+  HMatrix XMatrix(NX, 3, LHM_REAL);
+  for (int nx = 0; nx < NX; nx++) for (int m = 0; m < 3; m++) XMatrix.SetEntry(nx, m, SCR[7 * nx + m]);
+  HMatrix *FScat = G->GetFields(0, KN, Omega, kBloch, &XMatrix, 0);          // the O(N NX) part, on the device
+  HMatrix *FInc = IF ? G->GetFields(IF, 0, Omega, kBloch, &XMatrix, 0) : 0;
+  memset(PFT, 0, NUMPFT * sizeof(double));
+  for (int nr = 0; nr < NX; nr++)
+   { const double *X = &SCR[7 * nr], *nHat = X + 3, w = SCR[7 * nr + 6];
+     double NMatrix[NUMPFT][3][3];
+     GetNMatrices(nHat, X, XTorque, NMatrix);
+     cdouble ES[3], HS[3], E[3], H[3];
+     for (int m = 0; m < 3; m++)
+      { ES[m] = FScat->GetEntry(nr, m); HS[m] = FScat->GetEntry(nr, 3 + m);
+        E[m] = ES[m] + (FInc ? FInc->GetEntry(nr, m) : cdouble(0.0)); H[m] = HS[m] + (FInc ? FInc->GetEntry(nr, 3 + m) : cdouble(0.0)); }
+     PFT[PFT_PABS] += -0.25 * w * (HVMVP(E, NMatrix[PFT_PABS], H) - HVMVP(H, NMatrix[PFT_PABS], E));
+     PFT[PFT_PSCAT] += 0.25 * w * (HVMVP(ES, NMatrix[PFT_PABS], HS) - HVMVP(HS, NMatrix[PFT_PABS], ES));
+     for (int nq = 2; nq < NUMPFT; nq++)
+      PFT[nq] += 0.25 * w * (EpsAbs * HVMVP(E, NMatrix[nq], E) + MuAbs * HVMVP(H, NMatrix[nq], H)); }
+  delete FScat; if (FInc) delete FInc;
+}
+
 void RWGGeometry::GetPFT(int SurfaceIndex, HVector *KN, cdouble Omega, double PFT[NUMPFT], PFTOptions *Options)
 { PFTOptions Default; if (Options == 0) { Options = &Default; InitPFTOptions(Options); }
   if (SurfaceIndex < 0 || SurfaceIndex >= NumSurfaces) ErrExit("GetPFT: invalid surface index %i", SurfaceIndex);
@@ -284,7 +384,17 @@ void RWGGeometry::GetPFT(int SurfaceIndex, HVector *KN, cdouble Omega, double PF
                      Options->Interior || Options->PFTMethod == SCUFF_PFT_EMT_INTERIOR, Options->EMTPFTIMethod);
      for (int nq = 0; nq < NUMPFT; nq++) PFT[nq] = PFTMatrix->GetEntryD(SurfaceIndex, nq);
      delete PFTMatrix; }
-  else ErrExit("GetPFT: PFT method %i is not available on the device path (only the energy/momentum-transfer method, SCUFF_PFT_EMT)", Options->PFTMethod);
+  else if (Options->PFTMethod == SCUFF_PFT_DSI)
+   { if (Options->DRMatrix) ErrExit("GetPFT: the trace (Rytov-matrix) form of the DSI method is not available on the device path");
+     RWGSurface *S = Surfaces[SurfaceIndex];
+     double DSIRadius = Options->DSIRadius;
+     if (DSIRadius == 0.0)                                   // AutodetectDSIRadius (GetPFT.cc:73-86): 1.5 x the extent about the origin
+      { double Radius = 0.0;
+        for (int np = 0; np < S->NumPanels; np++) Radius = fmax(Radius, VecDistance(S->Origin, S->Panels[np]->Centroid));
+        DSIRadius = 1.5 * Radius; }
+     GetDSIPFT(this, Omega, Options->kBloch, KN, Options->IF, PFT, Options->DSIMesh, DSIRadius, Options->DSIPoints,
+               Options->DSIFarField, Options->FluxFileName, S->OTGT, S->GT); }
+  else ErrExit("GetPFT: PFT method %i is not available on the device path (energy/momentum transfer SCUFF_PFT_EMT and displaced surface integral SCUFF_PFT_DSI are)", Options->PFTMethod);
 }
 
 HMatrix *RWGGeometry::GetPFTMatrix(HVector *KN, cdouble Omega, PFTOptions *Options, HMatrix *PFTMatrix)
@@ -295,7 +405,10 @@ HMatrix *RWGGeometry::GetPFTMatrix(HVector *KN, cdouble Omega, PFTOptions *Optio
   if (Options->PFTMethod == SCUFF_PFT_EMT_EXTERIOR || Options->PFTMethod == SCUFF_PFT_EMT_INTERIOR)
    GetEMTPFTMatrix(this, Omega, Options->IF, KN, Options->DRMatrix, PFTMatrix,
                    Options->Interior || Options->PFTMethod == SCUFF_PFT_EMT_INTERIOR, Options->EMTPFTIMethod);
-  else ErrExit("GetPFTMatrix: PFT method %i is not available on the device path (only SCUFF_PFT_EMT)", Options->PFTMethod);
+  else
+   for (int ns = 0; ns < NumSurfaces; ns++)
+    { double PFT[NUMPFT]; GetPFT(ns, KN, Omega, PFT, Options);
+      for (int nq = 0; nq < NUMPFT; nq++) PFTMatrix->SetEntry(ns, nq, PFT[nq]); }
   return PFTMatrix;
 }
 

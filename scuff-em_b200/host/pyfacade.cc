@@ -165,6 +165,14 @@ void *scuffb200_get_rf_matrix(void *g, double wr, double wi, int nx, const doubl
 { GUARD(RWGGeometry *G = (RWGGeometry *)g;
         HMatrix XM(nx, 3, LHM_REAL); for (int i = 0; i < nx; i++) for (int m = 0; m < 3; m++) XM.SetEntry(i, m, X[3 * i + m]);
         return (void *)G->GetRFMatrix(cdouble(wr, wi), 0, &XM, 0);, 0) }
+/* PFT by the displaced-surface-integral method (radius 0 = automatic; mesh may be NULL); out: NumSurfaces x 8 */
+int scuffb200_get_dsipft_matrix(void *g, void *kn, double wr, double wi, void *incfield, double radius, int npoints, const char *mesh, double *out)
+{ GUARD(RWGGeometry *G = (RWGGeometry *)g;
+        PFTOptions Opts; InitPFTOptions(&Opts); Opts.PFTMethod = SCUFF_PFT_DSI; Opts.IF = (IncField *)incfield; Opts.DSIRadius = radius; Opts.DSIPoints = npoints;
+        Opts.DSIMesh = (mesh && mesh[0]) ? (char *)mesh : 0;
+        HMatrix *P = G->GetPFTMatrix((HVector *)(HMatrix *)kn, cdouble(wr, wi), &Opts, 0);
+        for (int ns = 0; ns < G->NumSurfaces; ns++) for (int nq = 0; nq < NUMPFT; nq++) out[ns * NUMPFT + nq] = P->GetEntryD(ns, nq);
+        delete P; return 0;, 1) }
 int scuffb200_surface_origin(void *g, int ns, double *out) { for (int m = 0; m < 3; m++) out[m] = ((RWGGeometry *)g)->Surfaces[ns]->Origin[m]; return 0; }
 
 }  // extern "C"

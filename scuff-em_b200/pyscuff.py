@@ -162,6 +162,7 @@ def host_lib():
         L.scuffb200_get_pft_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.scuffb200_surface_origin.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.scuffb200_get_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.scuffb200_get_dsipft_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_char_p, C.c_void_p]
         L.scuffb200_get_rf_matrix.restype = C.c_void_p
         L.scuffb200_get_rf_matrix.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
         _host = L
@@ -364,6 +365,13 @@ class RWGGeometry:
         out = np.zeros((self.NumSurfaces, 8))
         _check(host_lib().scuffb200_get_pft_matrix(self.ptr, KN.ptr, float(np.real(Omega)), float(np.imag(Omega)),
                                                     IF.ptr if IF is not None else None, int(Interior), int(EMTPFTIMethod), out.ctypes.data))
+        return out
+
+    def GetDSIPFTMatrix(self, KN, Omega, IF=None, DSIRadius=0.0, DSIPoints=302, DSIMesh=None):
+        """GetPFTMatrix with PFTMethod = SCUFF_PFT_DSI (fields on the bounding surface from the device)"""
+        out = np.zeros((self.NumSurfaces, 8))
+        _check(host_lib().scuffb200_get_dsipft_matrix(self.ptr, KN.ptr, float(np.real(Omega)), float(np.imag(Omega)), IF.ptr if IF is not None else None,
+                                                       float(DSIRadius), int(DSIPoints), (DSIMesh or "").encode(), out.ctypes.data))
         return out
 
     def GetFields(self, IF, KN, Omega, X):

@@ -143,7 +143,7 @@ def rel_fro(A, B):
 
 
 def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=None, nopft=False, tmpdir="/tmp/scuff_ref_cache", env=None,
-                points=None, rf=False):
+                points=None, rf=False, dsi=None):
     """One frequency point of the reference's scuff-scatter flow (ref_driver scatter): AssembleBEMMatrix, AssembleRHSVector,
     LU solve, GetPFTMatrix (EMT method).  pw = (E0[3] complex, nHat[3]); ps_src = (X0[3], P[3] complex) or None.
     Returns (RHS, KN, PFT[NS, 8], info).  Cached on disk."""
@@ -151,7 +151,7 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
         pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
     os.makedirs(tmpdir, exist_ok=True)
     pkey = None if points is None else hashlib.md5(np.ascontiguousarray(points, dtype=np.float64).tobytes()).hexdigest()
-    key = hashlib.md5(repr(("scatter", geo, complex(omega), pw, ps_src, interior, method, trans, nopft, pkey, rf)).encode()).hexdigest()[:16]
+    key = hashlib.md5(repr(("scatter", geo, complex(omega), pw, ps_src, interior, method, trans, nopft, pkey, rf, dsi)).encode()).hexdigest()[:16]
     out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
     meta = out + ".json"
     if not (os.path.exists(out) and os.path.exists(meta)):
@@ -170,6 +170,8 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
         cmd += ["--method", str(method)]
         if trans is not None:
             cmd += ["--transfile", trans[0], "--trans", str(trans[1])]
+        if dsi is not None:
+            cmd += ["--dsi", repr(float(dsi[0])), str(int(dsi[1]))]
         if points is not None:
             np.ascontiguousarray(points, dtype=np.float64).tofile(out + ".pts")
             cmd += ["--fields", out + ".pts"] + (["--rf"] if rf else [])
@@ -182,9 +184,12 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
     RHS = raw[:2 * N].view(np.complex128).copy()
     KN = raw[2 * N:4 * N].view(np.complex128).copy()
     PFT = raw[4 * N:4 * N + 8 * NS].reshape(NS, 8).copy()
+    o = 4 * N + 8 * NS
+    if dsi is not None:
+        info["dsipft"] = raw[o:o + 8 * NS].reshape(NS, 8).copy()
+        o += 8 * NS
     if points is not None:
         NX = np.asarray(points).reshape(-1, 3).shape[0]
-        o = 4 * N + 8 * NS
         info["fields"] = raw[o:o + 12 * NX].view(np.complex128).reshape(NX, 6).copy()
         if rf:
             o += 12 * NX

@@ -70,3 +70,23 @@ def test_point_on_the_surface_is_refused(ps):
     KN = G.AllocateRHSVector(); KN.set(np.ones(G.TotalBFs, dtype=complex))
     with pytest.raises(ps.ScuffError, match="GetReducedFields_Nearby"):
         G.GetFields(None, KN, 1.0, [[0.0, 0.0, 1.02]])
+
+
+@pytest.mark.parametrize("name,omega,trans,dsi", [("SiO2Sphere_501.scuffgeo", 1.0, None, (0.0, 302)), ("PECSphere_501.scuffgeo", 1.0, None, (2.5, 110)),
+                                                  ("E10Spheres_327.scuffgeo", 0.8, ("Spheres.trans", 4), (0.0, 302))])
+def test_dsipft(ps, name, omega, trans, dsi):
+    """power, force, torque by the displaced-surface-integral method (GetDSIPFT, DSIPFT.cc:449-590; the reference's tests/Mie checks it):
+    Lebedev rule on a sphere around each body (automatic radius and an explicit one), fields from the device; the second body of the
+    two-sphere case is displaced by a transformation, so its sphere and torque centre move with it"""
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, trans=trans, dsi=dsi)
+    G = ps.RWGGeometry(geo(name))
+    if trans is not None:
+        G.transform(open(os.path.join(GEODIR, trans[0])).read().splitlines()[trans[1]])
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    IF = ps.PlaneWave(*PW_X)
+    G.AssembleRHSVector(omega, IF)
+    P = G.GetDSIPFTMatrix(KN, omega, IF, DSIRadius=dsi[0], DSIPoints=dsi[1])
+    ref = info["dsipft"]
+    for cols in ((0, 1), (2, 3, 4), (5, 6, 7)):
+        scale = np.max(np.abs(ref[:, cols]))
+        assert np.max(np.abs(P[:, cols] - ref[:, cols])) <= 1e-10 * scale, (P, ref)
