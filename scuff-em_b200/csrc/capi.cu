@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include "kernels.h"
 #include "sw_kernels.h"
 #include "pbc.h"
@@ -65,6 +66,8 @@ int scuffcuda_create(int device, scuffcuda_context **out)
   CK(cudaMemset(ctx->dcounters, 0, 16 * sizeof(unsigned long long)));
   { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
     CK(cudaStreamCreateWithPriority(&ctx->nearStream, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithPriority(&ctx->tdStream, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&ctx->evTd[i], cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     for (int i = 0; i < 7; i++) CK(cudaEventCreate(&ctx->ev[i])); }
   *out = ctx;
@@ -88,6 +91,8 @@ void scuffcuda_destroy(scuffcuda_context *ctx)
   for (auto &b : ctx->mapped) if (b.second.p) cudaFreeHost(b.second.p);
   for (int i = 0; i < 7; i++) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
   if (ctx->nearStream) cudaStreamDestroy(ctx->nearStream);
+  if (ctx->tdStream) cudaStreamDestroy(ctx->tdStream);
+  for (int i = 0; i < 2; i++) if (ctx->evTd[i]) cudaEventDestroy(ctx->evTd[i]);
   if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->solver) cusolverDnDestroy(ctx->solver);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -415,7 +420,12 @@ static cdouble csqrt2(cdouble z)   // libs/libhrutil/libhrutil.cc:692-699
 { cdouble r = std::sqrt(z); return (imag(r) < 0.0) ? -r : r; }
 
 int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args *a, int h)
-{ Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
+{ // SCUFF_CUDA_HOST_TIMING=1: host-side timestamps (us since entry) of the phases of this call on stderr (developer switch)
+  static const bool hostTiming = (getenv("SCUFF_CUDA_HOST_TIMING") && getenv("SCUFF_CUDA_HOST_TIMING")[0] == '1');
+  const auto tEntry = std::chrono::steady_clock::now();
+  auto stamp = [&](const char *what) { if (hostTiming) fprintf(stderr, "[assemble_block] %-28s %9.1f us\n", what,
+                     std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - tEntry).count()); };
+  Matrix *M = get_matrix(ctx, h); if (!M) return fail(ctx, "invalid matrix handle %d", h);
   int NS = (int)ctx->surfaces.size();
   if (nsa < 0 || nsa >= NS || nsb < 0 || nsb >= NS) return fail(ctx, "assemble_block: invalid surface index");
   Surface &Sa = ctx->surfaces[nsa], &Sb = ctx->surfaces[nsb];
@@ -451,6 +461,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   cudaEvent_t *ev = ctx->ev;                     // owned by the context: nothing to release on the error paths below
   cudaStream_t sMain = ctx->stream, sNear = near_stream(ctx);
   struct StreamGuard { scuffcuda_context *c; cudaStream_t s; ~StreamGuard() { c->stream = s; } } restoreStream{ ctx, sMain };
+  stamp("prologue done");
   CK(cudaEventRecord(ev[0], ctx->stream));
   CK(cudaMemsetAsync(ctx->dcounters, 0, 16 * sizeof(unsigned long long), ctx->stream));
   M->factored = false;
@@ -514,9 +525,11 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      F.K = K; F.S = SP; F.counters = ctx->dcounters;
      far_set_zero_event(ctx, ev[6]);              // launch_far waits for it unless it takes the two-pass path
      CK(cudaEventRecord(ev[1], sMain));           // the counters are reset
+     stamp("before launch_far");
      launch_far(ctx, F, kmode);
      CK(cudaGetLastError());
      CK(cudaEventRecord(ev[2], sMain));
+     stamp("far launched");
      // Two-pass path with the atomic gather: the FP64-bound first pass has the SMs to itself, then the HBM-bound gather
      // runs beside the latency-bound near/singular kernels.  Otherwise the near kernels run beside the far kernel.
      const bool gatherBesideNear = far_twopass_pending(ctx) && far_gather_red();
@@ -525,20 +538,25 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
         launch_far_gather(ctx); CK(cudaGetLastError()); }
      if (!a->far_only)
       { // near/singular work on the second stream
-        CK(cudaStreamWaitEvent(sNear, gatherBesideNear ? ev[2] : ev[1], 0));  // (the counters are reset; the block was cleared on this stream)
+        // SCUFF_CUDA_NEAR_EARLY=1: start the near/singular kernels together with the first pass instead of after it (experiment switch)
+        static const bool nearEarly = (getenv("SCUFF_CUDA_NEAR_EARLY") && getenv("SCUFF_CUDA_NEAR_EARLY")[0] == '1');
+        CK(cudaStreamWaitEvent(sNear, (gatherBesideNear && !nearEarly) ? ev[2] : ev[1], 0));  // (the counters are reset; the block was cleared on this stream)
         CK(cudaEventRecord(ev[4], sNear));
         ctx->stream = sNear;
+        stamp("before run_near");
         int rc = run_near(ctx, nsa, nsb, a, K, SP, kmode, std::abs(k));
         ctx->stream = sMain;
         if (rc) return 1;
         CK(cudaEventRecord(ev[5], sNear));
-        CK(cudaStreamWaitEvent(sMain, ev[5], 0)); }
+        CK(cudaStreamWaitEvent(sMain, ev[5], 0));
+        stamp("near launched"); }
      // two-pass far path: the gather adds the panel-pair values to what the near kernels stamped (and mirrors a symmetric block)
      CK(cudaStreamWaitEvent(sMain, ev[6], 0));
      if (launch_far_gather(ctx)) mirrored = true;
      CK(cudaGetLastError());
      CK(cudaEventRecord(ev[3], sMain));
      CK(cudaEventSynchronize(ev[3]));
+     stamp("region synchronised");
      float t; cudaEventElapsedTime(&t, ev[1], ev[2]); farMs += t;
      gatherMs += far_gather_elapsed_ms(ctx);
      if (!a->far_only) { cudaEventElapsedTime(&t, ev[4], ev[5]); nearMs += t; }
@@ -549,7 +567,13 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   CK(cudaGetLastError());
   CK(cudaEventRecord(ev[3], ctx->stream));
   CK(cudaEventSynchronize(ev[3]));
+  stamp("mirror synchronised");
   float tot; cudaEventElapsedTime(&tot, ev[0], ev[3]);
+  if (hostTiming)
+   { float e1 = 0, e2 = 0, e4 = 0, e5 = 0, e6 = 0;
+     cudaEventElapsedTime(&e6, ev[0], ev[6]); cudaEventElapsedTime(&e1, ev[0], ev[1]); cudaEventElapsedTime(&e2, ev[0], ev[2]);
+     if (!a->far_only) { cudaEventElapsedTime(&e4, ev[0], ev[4]); cudaEventElapsedTime(&e5, ev[0], ev[5]); }
+     fprintf(stderr, "[assemble_block] device ms since ev0: cleared %.3f  far start %.3f  far end %.3f  near start %.3f  near end %.3f  all done %.3f\n", e6, e1, e2, e4, e5, tot); }
   ctx->timing[0] = tot; ctx->timing[1] = farMs; ctx->timing[2] = nearMs; ctx->timing[4] = gatherMs;
   // counters come back through mapped host memory (no D2H copy-engine transfer: one may be busy with a matrix download)
   unsigned long long *hc = (unsigned long long *)scuffcuda::mapped_host_scratch(ctx, 16 * sizeof(unsigned long long), 0);
@@ -559,6 +583,7 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
   CK(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < 5; i++) ctx->counts[i] = hc[i];
   ctx->pairCounts[0] = hc[5]; ctx->pairCounts[1] = hc[6];
+  stamp("counters back");
   return 0;
 }
 

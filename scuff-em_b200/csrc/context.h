@@ -130,6 +130,8 @@ struct scuffcuda_context
   int smCount = 148;
   // per-context helper streams, events and mapped host buffers (created with the context, destroyed with it)
   cudaStream_t nearStream = nullptr;          // high priority: near/singular kernels, concurrent with the far kernel
+  cudaStream_t tdStream = nullptr;            // high priority: Taylor-Duffy kernels, concurrent with the desingularised-pair kernel
+  cudaEvent_t evTd[2] = { nullptr, nullptr };
   cudaStream_t copyStream = nullptr;          // downloads overlapping with assembly
   cudaEvent_t ev[7] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr };
   struct MappedBuf { void *p = nullptr; size_t n = 0; };

@@ -92,6 +92,7 @@ __global__ void near_assess_kernel(const PanelRec *pa, const PanelRec *pb, const
 __global__ void __launch_bounds__(NEAR_THREADS)
 near_desing_kernel(const NearArgs A)
 { int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) A.counters[6] = (unsigned long long)A.nNear;     // number of near pairs of this block (scuffcuda_get_pair_counts)
   if (idx >= A.nNear) return;
   const NearPair N = A.near[idx];
   const PanelRec &Pa = A.pa[N.pa], &Pb = A.pb[N.pb];
@@ -335,17 +336,32 @@ int run_near(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args 
   Plan *P = get_plan(ctx, nsa, nsb, a->symmetric != 0, a->use_displacement != 0, L, status);
   if (!P) return status ? status : 1;
   if (P->nNear == 0) return 0;
-  { unsigned long long nn = (unsigned long long)P->nNear;
-    cudaMemcpyAsync(ctx->dcounters + 6, &nn, sizeof nn, cudaMemcpyHostToDevice, ctx->stream); cudaStreamSynchronize(ctx->stream); }
   NearArgs A;
   A.pa = ctx->surfaces[nsa].dpanels; A.pb = ctx->surfaces[nsb].dpanels; A.near = P->dnear; A.nNear = P->nNear;
   A.useDisp = a->use_displacement ? 1 : 0; for (int i = 0; i < 3; i++) A.L[i] = A.useDisp ? L[i] : 0.0;
   A.forceTD = a->force_taylor_duffy ? 1 : 0; A.kabs = kabs; A.fippi = ctx->fippi.drec;
   A.K = K; A.S = SP; A.counters = ctx->dcounters;
+  // The desingularised pairs (near_desing_kernel) and the Taylor-Duffy pairs (run_td) are disjoint and both scatter with atomic
+  // adds, so they run side by side: the first on the caller's (near) stream, the second on the Taylor-Duffy stream, which starts
+  // where the near stream stands now (block cleared, far pass done) and is joined again before returning.  Nothing here blocks
+  // the host before the kernels are queued (the pair count reaches the counters through the kernel), so both start the moment
+  // the far pass ends.  SCUFF_CUDA_TD_STREAM=0: one stream, one after the other.
+  static const bool twoStreams = !(getenv("SCUFF_CUDA_TD_STREAM") && getenv("SCUFF_CUDA_TD_STREAM")[0] == '0');
+  cudaStream_t sNear = ctx->stream;
+  if (twoStreams && ctx->tdStream)
+   { CKN(cudaEventRecord(ctx->evTd[0], sNear));
+     CKN(cudaStreamWaitEvent(ctx->tdStream, ctx->evTd[0], 0)); }
   ctx->launches++;
-  near_desing_kernel<<<(P->nNear + NEAR_THREADS - 1) / NEAR_THREADS, NEAR_THREADS, 0, ctx->stream>>>(A);
+  near_desing_kernel<<<(P->nNear + NEAR_THREADS - 1) / NEAR_THREADS, NEAR_THREADS, 0, sNear>>>(A);
   CKN(cudaGetLastError());
-  return run_td(ctx, *P, A, kmode);
+  if (!(twoStreams && ctx->tdStream)) return run_td(ctx, *P, A, kmode);
+  ctx->stream = ctx->tdStream;
+  const int rc = run_td(ctx, *P, A, kmode);
+  ctx->stream = sNear;
+  if (rc) return rc;
+  CKN(cudaEventRecord(ctx->evTd[1], ctx->tdStream));
+  CKN(cudaStreamWaitEvent(sNear, ctx->evTd[1], 0));
+  return 0;
 }
 
 }  // namespace scuffcuda
