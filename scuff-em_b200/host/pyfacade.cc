@@ -173,6 +173,16 @@ int scuffb200_get_dsipft_matrix(void *g, void *kn, double wr, double wi, void *i
         HMatrix *P = G->GetPFTMatrix((HVector *)(HMatrix *)kn, cdouble(wr, wi), &Opts, 0);
         for (int ns = 0; ns < G->NumSurfaces; ns++) for (int nq = 0; nq < NUMPFT; nq++) out[ns * NUMPFT + nq] = P->GetEntryD(ns, nq);
         delete P; return 0;, 1) }
+/* IncField::GetFields / GetFieldGradients of the host classes at npts points (the caller's own evaluation; no device involved) */
+int scuffb200_incfield_eval(void *incfield, double wr, double wi, const double *epsmu, int npts, const double *X, double *eh, double *deh)
+{ GUARD(IncField *IF = (IncField *)incfield;
+        IF->SetFrequencyAndEpsMu(cdouble(wr, wi), cdouble(epsmu[0], epsmu[1]), cdouble(epsmu[2], epsmu[3]), false);
+        for (int n = 0; n < npts; n++)
+         { cdouble EH[6]; IF->GetFields(X + 3 * n, EH);
+           for (int q = 0; q < 6; q++) { eh[12 * n + 2 * q] = real(EH[q]); eh[12 * n + 2 * q + 1] = imag(EH[q]); }
+           if (deh) { cdouble dEH[3][6]; IF->GetFieldGradients(X + 3 * n, dEH);
+                      for (int m = 0; m < 3; m++) for (int q = 0; q < 6; q++) { deh[36 * n + 12 * m + 2 * q] = real(dEH[m][q]); deh[36 * n + 12 * m + 2 * q + 1] = imag(dEH[m][q]); } } }
+        return 0;, 1) }
 int scuffb200_surface_origin(void *g, int ns, double *out) { for (int m = 0; m < 3; m++) out[m] = ((RWGGeometry *)g)->Surfaces[ns]->Origin[m]; return 0; }
 
 }  // extern "C"

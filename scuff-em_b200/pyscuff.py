@@ -163,6 +163,7 @@ def host_lib():
         L.scuffb200_surface_origin.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.scuffb200_get_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.scuffb200_get_dsipft_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_char_p, C.c_void_p]
+        L.scuffb200_incfield_eval.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.scuffb200_get_rf_matrix.restype = C.c_void_p
         L.scuffb200_get_rf_matrix.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
         _host = L
@@ -319,6 +320,16 @@ class IncField:
     def __init__(self, ptr):
         self.ptr = ptr
         self.next = None
+
+    def eval(self, Omega, X, eps=1.0, mu=1.0, gradients=False):
+        """GetFields (and GetFieldGradients) of this field alone in a medium (eps, mu): (NX, 6) [and (NX, 3, 6)] complex"""
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1, 3))
+        em = np.array([np.real(eps), np.imag(eps), np.real(mu), np.imag(mu)], dtype=np.float64)
+        eh = np.zeros((X.shape[0], 6), dtype=np.complex128)
+        deh = np.zeros((X.shape[0], 3, 6), dtype=np.complex128) if gradients else None
+        _check(host_lib().scuffb200_incfield_eval(self.ptr, float(np.real(Omega)), float(np.imag(Omega)), em.ctypes.data, X.shape[0], X.ctypes.data,
+                                                   eh.ctypes.data, deh.ctypes.data if gradients else None))
+        return (eh, deh) if gradients else eh
 
     def chain(self, other):
         host_lib().scuffb200_incfield_set_next(self.ptr, other.ptr if other is not None else None)

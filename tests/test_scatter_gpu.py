@@ -145,3 +145,24 @@ def test_lazy_host_mode(ps, monkeypatch):
     assert pft_err(P, PFTr) <= 1e-6
     M2 = G.AssembleBEMMatrix(omega)                       # default mode: host copy current
     assert not M2.state()["HostStale"]
+
+
+@pytest.mark.parametrize("name,omega", [("PECSphere_501", 1.0), ("SiO2Sphere_501", 1.0), ("E10Spheres_327", 0.8)])
+def test_against_committed_golden(ps, name, omega):
+    """the whole scattering point against the committed reference vectors (tests/golden/scatter_golden.npz, made by
+    tests/golden/make_scatter_golden.py from the unmodified reference): no reference binary needed at test time"""
+    from conftest import GOLDEN
+    Gd = np.load(os.path.join(GOLDEN, "scatter_golden.npz"))
+    key = "%s@%g" % (name, omega)
+    G = ps.RWGGeometry(geo(name + ".scuffgeo"))
+    IF = ps.PlaneWave(*PW_X)
+    M = G.AssembleBEMMatrix(omega, to_host=False)
+    KN = G.AssembleRHSVector(omega, IF)
+    assert rel(KN.array, Gd[key + ":rhs"]) <= 1e-12
+    M.lu_factorize(); M.lu_solve_vector(KN)
+    assert rel(KN.array, Gd[key + ":kn"]) <= 1e-8
+    KNr = G.AllocateRHSVector(); KNr.set(Gd[key + ":kn"])
+    assert pft_err(G.GetPFTMatrix(KNr, omega, IF, EMTPFTIMethod=0), Gd[key + ":emtpft0"]) <= 1e-9
+    assert pft_err(G.GetDSIPFTMatrix(KNr, omega, IF), Gd[key + ":dsipft"]) <= 1e-10
+    F = G.GetFields(IF, KNr, omega, Gd[key + ":x"])
+    assert rel(F, Gd[key + ":fields"]) <= 1e-11
