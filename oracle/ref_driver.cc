@@ -12,12 +12,13 @@
  *        AssembleBEMMatrixBlock (AssembleBEMMatrix.cc:349-391) with GradM[3] and dMdT[NumTorqueAxes] (CreateGammaMatrix,
  *        EdgeEdgeInteractions.cc:241-270): writes the value block, the three gradient blocks and the torque blocks one after
  *        the other (complex, or real with --imag as scuff-cas3D allocates them)
- *   ref_driver scatter <geo> <wRe> <wIm> <out.bin> --pw E0xr E0xi E0yr E0yi E0zr E0zi nx ny nz [--ps x y z Pxr Pxi Pyr Pyi Pzr Pzi]
- *                      [--interior] [--method m] [--transfile f --trans n] [--nopft] [--dsi radius npoints] [--fields pts.bin [--rf]]
+ *   ref_driver scatter <geo> <wRe> <wIm> <out.bin> --pw E0xr E0xi E0yr E0yi E0zr E0zi nx ny nz [--region label] [--ps x y z Pxr Pxi Pyr Pyi Pzr Pzi]
+ *                      [--interior] [--method m] [--transfile f --trans n] [--nopft] [--dsi radius npoints] [--fields pts.bin [--rf]] [--kbloch kx ky]
  *        one frequency point of scuff-scatter (scuff-scatter.cc:402-520): AssembleBEMMatrix, AssembleRHSVector with the given
  *        incident-field chain (plane wave first, then an optional point source), LUFactorize, LUSolve, GetPFTMatrix by the
  *        energy/momentum-transfer method with integral method m (default 0 = SCUFF_EMTPFTI_EHDERIVATIVES1).  Writes RHS
  *        (TotalBFs complex), the solution KN (TotalBFs complex) and the PFT matrix (NumSurfaces x 8 doubles, row-major).
+ *        --kbloch: periodic geometry (use with --nopft): AssembleBEMMatrix / AssembleRHSVector with the Bloch vector.
  *        --dsi: then the PFT matrix by the displaced-surface-integral method (GetDSIPFT, DSIPFT.cc:449-590; radius 0 = automatic), NS x 8.
  *        --fields: then GetFields (GetFields.cc:336-395) at the points of pts.bin (raw doubles x,y,z): NX x 6 complex, row-major,
  *        appended; --rf: then GetRFMatrix (:141-330), TotalBFs x 6NX complex column-major, appended.
@@ -202,7 +203,7 @@ int main(int argc, char **argv)
 
   if(!strcmp(Cmd,"scatter"))
    { cdouble Omega(atof(argv[3]),atof(argv[4])); const char *Out=argv[5];
-     IncField *IFList=0, *Tail=0; bool Interior=false, NoPFT=false, WantRF=false, WantDSI=false; double DSIRadius=0.0; int DSIPoints=302; int Method=0; const char *TransFile=0, *PtsFile=0; int nTrans=0;
+     IncField *IFList=0, *Tail=0; bool Interior=false, NoPFT=false, WantRF=false, WantDSI=false, HaveKB=false; double kBloch[2]={0,0}; double DSIRadius=0.0; int DSIPoints=302; int Method=0; const char *TransFile=0, *PtsFile=0; int nTrans=0;
      for(int n=6;n<argc;n++)
       { IncField *New=0;
         if(!strcmp(argv[n],"--pw") && n+9<argc)
@@ -213,9 +214,11 @@ int main(int argc, char **argv)
          { double X0[3]; cdouble P[3];
            for(int m=0;m<3;m++) { X0[m]=atof(argv[n+1+m]); P[m]=cdouble(atof(argv[n+4+2*m]),atof(argv[n+5+2*m])); }
            New=new PointSource(X0,P); n+=9; }
+        else if(!strcmp(argv[n],"--region") && Tail) Tail->SetRegionLabel(argv[++n]);      // region of the sources of the last field given
         else if(!strcmp(argv[n],"--interior")) Interior=true;
         else if(!strcmp(argv[n],"--nopft")) NoPFT=true;
         else if(!strcmp(argv[n],"--rf")) WantRF=true;
+        else if(!strcmp(argv[n],"--kbloch")) { kBloch[0]=atof(argv[n+1]); kBloch[1]=atof(argv[n+2]); HaveKB=true; n+=2; }
         else if(!strcmp(argv[n],"--dsi")) { WantDSI=true; DSIRadius=atof(argv[n+1]); DSIPoints=atoi(argv[n+2]); n+=2; }
         else if(!strcmp(argv[n],"--fields")) PtsFile=argv[++n];
         else if(!strcmp(argv[n],"--method")) Method=atoi(argv[++n]);
@@ -228,9 +231,9 @@ int main(int argc, char **argv)
         if(nTrans<0||nTrans>=(int)GTCs.size()) { fprintf(stderr,"no transformation %i in %s\n",nTrans,TransFile); return 2; }
         G->Transform(GTCs[nTrans]); }
      double t0=Now();
-     HMatrix *M=G->AssembleBEMMatrix(Omega,(HMatrix *)0);
+     HMatrix *M=G->AssembleBEMMatrix(Omega,HaveKB ? kBloch : 0,(HMatrix *)0);
      double t1=Now();
-     HVector *KN=G->AssembleRHSVector(Omega,IFList,0), *RHS=new HVector(KN->N,LHM_COMPLEX);
+     HVector *KN=G->AssembleRHSVector(Omega,HaveKB ? kBloch : 0,IFList,0), *RHS=new HVector(KN->N,LHM_COMPLEX);
      RHS->Copy(KN);
      double t2=Now();
      M->LUFactorize(); M->LUSolve(KN);

@@ -139,12 +139,17 @@ int RWGGeometry::GetRegionIndex(const double X[3])
 int RWGGeometry::UpdateIncFields(IncField *IFList, cdouble Omega, double *kBloch)
 { if (IFList == 0) return 0;
   if ((LBasis == 0 && kBloch != 0) || (LBasis != 0 && kBloch == 0)) ErrExit("%s:%i: internal error", __FILE__, __LINE__);
-  if (LBasis) ErrExit("AssembleRHSVector: incident fields in periodic geometries are not on the device path yet (Bloch-periodic sources)");
+  // periodic geometries: a plane wave is its own Bloch-periodic field (PlaneWave::GetFields ignores the lattice), so the inner products
+  // over the unit cell's basis functions — straddlers included, their second panel lies in the neighbour cell — are the same integrals;
+  // lattice sums of localised sources (PointSource::GetFields_Periodic) are not on the device path
+  if (LBasis)
+   for (IncField *IF = IFList; IF; IF = IF->Next)
+    if (!dynamic_cast<PlaneWave *>(IF)) ErrExit("AssembleRHSVector: in periodic geometries only plane-wave incident fields are on the device path");
   UpdateCachedEpsMuValues(Omega);
   int NIF = 0;
   for (IncField *IF = IFList; IF; NIF++, IF = IF->Next)
    { double X[3];
-     if (IF->GetSourcePoint(X)) IF->RegionIndex = GetRegionIndex(X);
+     if (!LBasis && IF->GetSourcePoint(X)) IF->RegionIndex = GetRegionIndex(X);
      else if (IF->RegionLabel) IF->RegionIndex = GetRegionByLabel(IF->RegionLabel);
      else IF->RegionIndex = 0;
      if (IF->RegionIndex < 0 || IF->RegionIndex > NumRegions) ErrExit("invalid region index %i", IF->RegionIndex);

@@ -145,6 +145,8 @@ void scuffb200_incfield_set_next(void *a, void *b) { ((IncField *)a)->Next = (In
 void scuffb200_incfield_free(void *a) { delete (IncField *)a; }
 int scuffb200_assemble_rhs(void *g, double wr, double wi, void *incfield, void *vec)
 { GUARD(((RWGGeometry *)g)->AssembleRHSVector(cdouble(wr, wi), (IncField *)incfield, (HVector *)(HMatrix *)vec); return 0;, 1) }
+int scuffb200_assemble_rhs_kbloch(void *g, double wr, double wi, const double *kBloch, void *incfield, void *vec)
+{ GUARD(((RWGGeometry *)g)->AssembleRHSVector(cdouble(wr, wi), (double *)kBloch, (IncField *)incfield, (HVector *)(HMatrix *)vec); return 0;, 1) }
 int scuffb200_lu_solve_vector(void *m, void *vec) { GUARD(return ((HMatrix *)m)->LUSolve((HVector *)(HMatrix *)vec);, 1) }
 int scuffb200_vector_copy(void *dst, void *src) { GUARD(((HVector *)(HMatrix *)dst)->Copy((HVector *)(HMatrix *)src); return 0;, 1) }
 /* out: NumSurfaces x 8, row-major */

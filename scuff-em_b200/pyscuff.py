@@ -157,6 +157,7 @@ def host_lib():
         L.scuffb200_incfield_set_next.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffb200_incfield_free.argtypes = [C.c_void_p]
         L.scuffb200_assemble_rhs.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.scuffb200_assemble_rhs_kbloch.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.scuffb200_lu_solve_vector.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffb200_vector_copy.argtypes = [C.c_void_p, C.c_void_p]
         L.scuffb200_get_pft_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -366,10 +367,14 @@ class RWGGeometry:
     def AllocateRHSVector(self, PureImagFreq=False):
         return HVector.new(self.TotalBFs, bool(PureImagFreq) and self.LDim == 0)
 
-    def AssembleRHSVector(self, Omega, IF, RHS=None):
+    def AssembleRHSVector(self, Omega, IF, RHS=None, kBloch=None):
         if RHS is None:
             RHS = self.AllocateRHSVector()
-        _check(host_lib().scuffb200_assemble_rhs(self.ptr, float(np.real(Omega)), float(np.imag(Omega)), IF.ptr, RHS.ptr))
+        if kBloch is not None:
+            kb = (C.c_double * 2)(float(kBloch[0]), float(kBloch[1]))
+            _check(host_lib().scuffb200_assemble_rhs_kbloch(self.ptr, float(np.real(Omega)), float(np.imag(Omega)), kb, IF.ptr, RHS.ptr))
+        else:
+            _check(host_lib().scuffb200_assemble_rhs(self.ptr, float(np.real(Omega)), float(np.imag(Omega)), IF.ptr, RHS.ptr))
         return RHS
 
     def GetPFTMatrix(self, KN, Omega, IF=None, Interior=False, EMTPFTIMethod=0):

@@ -143,7 +143,7 @@ def rel_fro(A, B):
 
 
 def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=None, nopft=False, tmpdir="/tmp/scuff_ref_cache", env=None,
-                points=None, rf=False, dsi=None):
+                points=None, rf=False, dsi=None, kbloch=None, pw_region=None):
     """One frequency point of the reference's scuff-scatter flow (ref_driver scatter): AssembleBEMMatrix, AssembleRHSVector,
     LU solve, GetPFTMatrix (EMT method).  pw = (E0[3] complex, nHat[3]); ps_src = (X0[3], P[3] complex) or None.
     Returns (RHS, KN, PFT[NS, 8], info).  Cached on disk."""
@@ -151,7 +151,7 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
         pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
     os.makedirs(tmpdir, exist_ok=True)
     pkey = None if points is None else hashlib.md5(np.ascontiguousarray(points, dtype=np.float64).tobytes()).hexdigest()
-    key = hashlib.md5(repr(("scatter", geo, complex(omega), pw, ps_src, interior, method, trans, nopft, pkey, rf, dsi)).encode()).hexdigest()[:16]
+    key = hashlib.md5(repr(("scatter", geo, complex(omega), pw, ps_src, interior, method, trans, nopft, pkey, rf, dsi, kbloch, pw_region)).encode()).hexdigest()[:16]
     out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
     meta = out + ".json"
     if not (os.path.exists(out) and os.path.exists(meta)):
@@ -159,6 +159,8 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
         for z in pw[0]:
             cmd += [repr(float(np.real(z))), repr(float(np.imag(z)))]
         cmd += [repr(float(x)) for x in pw[1]]
+        if pw_region is not None:
+            cmd += ["--region", pw_region]
         if ps_src is not None:
             cmd += ["--ps"] + [repr(float(x)) for x in ps_src[0]]
             for z in ps_src[1]:
@@ -172,6 +174,8 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
             cmd += ["--transfile", trans[0], "--trans", str(trans[1])]
         if dsi is not None:
             cmd += ["--dsi", repr(float(dsi[0])), str(int(dsi[1]))]
+        if kbloch is not None:
+            cmd += ["--kbloch", repr(float(kbloch[0])), repr(float(kbloch[1]))]
         if points is not None:
             np.ascontiguousarray(points, dtype=np.float64).tofile(out + ".pts")
             cmd += ["--fields", out + ".pts"] + (["--rf"] if rf else [])

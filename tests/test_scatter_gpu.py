@@ -166,3 +166,23 @@ def test_against_committed_golden(ps, name, omega):
     assert pft_err(G.GetDSIPFTMatrix(KNr, omega, IF), Gd[key + ":dsipft"]) <= 1e-10
     F = G.GetFields(IF, KNr, omega, Gd[key + ":x"])
     assert rel(F, Gd[key + ":fields"]) <= 1e-11
+
+
+@pytest.mark.parametrize("name,omega,kbloch,region", [("SiSlab_40.scuffgeo", 1.1, (0.0, 0.0), "UpperHalfSpace"), ("SiSlab_40.scuffgeo", 1.1, (0.7, 0.9), "UpperHalfSpace"),
+                                                      ("PECPlate_40.scuffgeo", 0.8, (0.3, 0.0), None)])
+def test_periodic_geometry_planewave_rhs_and_solve(ps, name, omega, kbloch, region):
+    """periodic (LATTICE) geometries: a plane wave is its own Bloch-periodic field, so AssembleRHSVector is the same set of inner
+    products over the unit cell's basis functions (straddlers reach into the neighbour cell); RHS and the solution of the periodic
+    BEM system against the reference (scuff-transmission's flow)"""
+    pw = ((1.0, 0.0, 0.0), (0.0, 0.0, -1.0))
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, pw, nopft=True, kbloch=kbloch, pw_region=region, env={"OMP_NUM_THREADS": "1"})
+    assert np.max(np.abs(RHSr)) > 0
+    G = ps.RWGGeometry(geo(name))
+    IF = ps.PlaneWave(pw[0], pw[1], region)
+    RHS = G.AssembleRHSVector(omega, IF, kBloch=kbloch)
+    assert rel(RHS.array, RHSr) <= 1e-12
+    M = G.AssembleBEMMatrix(omega, kBloch=kbloch, to_host=False)
+    M.lu_factorize(); M.lu_solve_vector(RHS)
+    assert rel(RHS.array, KNr) <= 1e-7
+    with pytest.raises(ps.ScuffError, match="plane-wave"):
+        G.AssembleRHSVector(omega, ps.PointSource((0, 0, 2.0), (1, 0, 0)), kBloch=kbloch)
