@@ -324,8 +324,8 @@ class RWGGeometry
    HMatrix *GetPFTMatrix(HVector *KN, cdouble Omega, PFTOptions *Options = 0, HMatrix *PFTMatrix = 0);
    int GetRegionIndex(const double X[3]);
    /* scattered + incident fields at the rows of XMatrix (NX x 3): FMatrix NX x 6 complex (E, H) (libscuff.h:512-520, GetFields.cc:336-417);
-    * GetRFMatrix: the reduced-field matrix TotalBFs x 6 NX whose columns contract with KN to the scattered fields (:141-330).  Evaluation
-    * points closer than one basis-function radius to the surface (the reference's GetReducedFields_Nearby branch) are refused.        */
+    * GetRFMatrix: the reduced-field matrix TotalBFs x 6 NX whose columns contract with KN to the scattered fields (:141-330), incl. the
+    * near-field branch (GetReducedFields_Nearby) for points closer than one basis-function radius to a surface.                      */
    HMatrix *GetFields(IncField *IF, HVector *KN, cdouble Omega, double *kBloch, HMatrix *XMatrix, HMatrix *FMatrix = NULL);
    HMatrix *GetFields(IncField *IF, HVector *KN, cdouble Omega, HMatrix *XMatrix, HMatrix *FMatrix = NULL);
    void GetFields(IncField *IF, HVector *KN, cdouble Omega, double *X, cdouble *EH);

@@ -227,8 +227,8 @@ int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_
  * (GetFields.cc:262-270).  kn_handle != 0: F[12*npts] (host; E then H as (re,im)) += sum over the surface's basis functions of
  * (reduced fields) x (solution entries).  rf_handle != 0: the reduced-field matrix entries RFMatrix[bf_offset + .., 6*rf_columns[i] + mu]
  * are stored in that device matrix (TotalBFs x 6 NX complex).  16-point rule beyond 4 basis-function radii, 78-point rule beyond 1
- * (:171-181, :284-295); pairs closer than that need GetReducedFields_Nearby, which is not on the device path: *near_pairs counts them
- * (their contribution is NOT included; callers treat a non-zero count as an error).                                      */
+ * (:171-181, :284-295); closer pairs: GetReducedFields_Nearby (libs/libscuff/GetNearFields.cc:60-905: closed-form static panel
+ * integrals + 21-point rule for the desingularised remainder), *near_pairs counts them (diagnostic).                      */
 int scuffcuda_get_fields(scuffcuda_context *ctx, int ns, const double k[2], const double zrel[2], double sign, int npts, const double *X,
                          int kn_handle, int bf_offset, double *F, int rf_handle, const int *rf_columns, long *near_pairs);
 

@@ -34,6 +34,7 @@
 #include "generated_tcr20.h"
 #include "generated_tcr9.h"
 #include "generated_tcr7.h"
+#include "nearfield.cuh"
 
 #define ZVAC 376.73031346177      /* libscuff.h:78 */
 #define TENTHIRDS 3.33333333333333333333333   /* PFTOptions.h:64 */
@@ -43,7 +44,7 @@
 
 namespace scuffcuda {
 
-struct EdgeRec { double QP[3], V1[3], V2[3], QM[3]; double len; int hasM; int pad; };   // 112 B
+struct EdgeRec { double QP[3], V1[3], V2[3], QM[3]; double len; int hasM; int pad; int pP, iP, pM, iM; };   // 128 B; pP/iP: positive panel and the index of QP in it, pM/iM: negative panel
 
 // one cubature point of a panel with the surface currents there (160 B)
 struct __align__(16) CurPt
@@ -109,6 +110,7 @@ static void host_edge(const Surface &S, int ne, EdgeRec &E)
    { E.V1[m] = S.V[3 * (size_t)t[0] + m]; E.V2[m] = S.V[3 * (size_t)t[1] + m]; E.QP[m] = S.V[3 * (size_t)t[2] + m];
      E.QM[m] = t[3] >= 0 ? S.V[3 * (size_t)t[3] + m] : 0.0; }
   E.len = S.edgeLen[ne]; E.hasM = (t[3] >= 0 && t[5] >= 0); E.pad = 0;
+  E.pP = t[4]; E.iP = t[6]; E.pM = t[5]; E.iM = t[7];
 }
 static int ensure_edges(scuffcuda_context *ctx, Surface &S)
 { if (S.dedges && S.edgesGen == S.generation && S.generation != 0) return 0;
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(PFT_THREADS) pft_ext_kernel(const __grid_const
 struct FieldArgs
 { const EdgeRec *edges; int NE; const double *X; int NX; const double *tcr7, *tcr20;
   cd k, zrel; double sign;
+  const PanelRec *panels; const double *tcr9;
   const double *kn; int offset, isPEC;
   double *F;                       // 12 doubles per point, accumulated
   double *RF; long ldRF; const int *colOf;   // RFMatrix (complex, column-major, leading dimension ldRF), column block 6*colOf[nx]
@@ -551,9 +554,18 @@ __global__ void __launch_bounds__(PFT_THREADS) fields_kernel(const __grid_consta
        for (int m = 0; m < 3; m++) { a += (E.QP[m] - c[m]) * (E.QP[m] - c[m]); b += (E.V1[m] - c[m]) * (E.V1[m] - c[m]); q += (E.V2[m] - c[m]) * (E.V2[m] - c[m]); qm += (E.QM[m] - c[m]) * (E.QM[m] - c[m]); }
        rad = fmax(sqrt(a), fmax(sqrt(b), sqrt(q))); if (E.hasM) rad = fmax(rad, sqrt(qm)); }
      const double rRel = sqrt(d2) / rad;
-     if (rRel < 1.0) { atomicAdd(A.nearCount, 1ull); continue; }
-     const double *tcr = rRel >= 4.0 ? A.tcr7 : A.tcr20; const int npts = rRel >= 4.0 ? SC_TCR7_NPTS : SC_TCR20_NPTS;
      cd GC[6]; for (int q = 0; q < 6; q++) GC[q] = mk(0.0, 0.0);
+     if (rRel < 1.0)
+      { // closer than one basis-function radius: closed-form static integrals + desingularised cubature (nearfield.cuh)
+        atomicAdd(A.nearCount, 1ull);
+        cd e[3], h[3];
+        nf_reduced_fields_panel(A.panels[E.pP], E.iP, X0, A.k, A.tcr9, e, h);
+        if (E.hasM)
+         { cd eM[3], hM[3];
+           nf_reduced_fields_panel(A.panels[E.pM], E.iM, X0, A.k, A.tcr9, eM, hM);
+           for (int m = 0; m < 3; m++) { e[m] -= eM[m]; h[m] -= hM[m]; } }
+        for (int m = 0; m < 3; m++) { GC[m] = e[m]; GC[3 + m] = h[m] * oomik; } }
+     const double *tcr = rRel >= 4.0 ? A.tcr7 : A.tcr20; const int npts = rRel < 1.0 ? 0 : (rRel >= 4.0 ? SC_TCR7_NPTS : SC_TCR20_NPTS);
      for (int np = 0; np < npts; np++)
       { const double u = tcr[3 * np], v = tcr[3 * np + 1], w = tcr[3 * np + 2];
         for (int pm = 0; pm < (E.hasM ? 2 : 1); pm++)
@@ -879,6 +891,7 @@ int scuffcuda_get_fields(scuffcuda_context *ctx, int ns, const double k[2], cons
   FieldArgs A;
   A.edges = (const EdgeRec *)S.dedges; A.NE = S.NE; A.X = dX; A.NX = npts; A.tcr7 = P->dtcr7; A.tcr20 = P->dtcr20;
   A.k = mk(k[0], k[1]); A.zrel = mk(zrel[0], zrel[1]); A.sign = sign;
+  A.panels = S.dpanels; A.tcr9 = P->dtcr9;
   A.kn = KN ? KN->d : nullptr; A.offset = bf_offset; A.isPEC = S.isPEC; A.F = dF;
   A.RF = RF ? RF->d : nullptr; A.ldRF = RF ? RF->NR : 0; A.colOf = dcol; A.nearCount = dcnt;
   fields_kernel<<<npts, PFT_THREADS, 0, ctx->stream>>>(A);

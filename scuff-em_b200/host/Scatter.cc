@@ -446,8 +446,7 @@ static void ReducedFieldsOnDevice(RWGGeometry *G, cdouble Omega, HMatrix *XMatri
         if (scuffcuda_get_fields(ctx, ns, kk, zz, Sign, (int)Idx.size(), X.data(), KN ? KN->DeviceHandle : 0, G->BFIndexOffset[ns],
                                  KN ? Fr.data() : 0, RFMatrix ? RFMatrix->DeviceHandle : 0, RFMatrix ? Idx.data() : 0, &Near))
          ErrExit("%s", scuffcuda_last_error(ctx));
-        if (Near) ErrExit("GetFields: %li (basis function, evaluation point) pairs are closer than one basis-function radius; the reference's "
-                          "desingularised near-field integrals (GetReducedFields_Nearby) are not available on the device path", Near); }
+        (void)Near; }                        // pairs closer than one basis-function radius: closed-form static integrals on the device
      if (KN) for (size_t i = 0; i < Idx.size(); i++) for (int q = 0; q < 12; q++) F[12 * (size_t)Idx[i] + q] += Fr[12 * i + q]; }
   if (RFMatrix) { RFMatrix->HostStale = true; RFMatrix->DeviceStale = false; }
 }

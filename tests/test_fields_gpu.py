@@ -65,11 +65,41 @@ def test_two_bodies_and_rf_matrix(ps):
     assert rel((KNr @ RF).reshape(-1, 6), Fs) <= 1e-12
 
 
-def test_point_on_the_surface_is_refused(ps):
-    G = ps.RWGGeometry(geo("PECSphere_501.scuffgeo"))
-    KN = G.AllocateRHSVector(); KN.set(np.ones(G.TotalBFs, dtype=complex))
-    with pytest.raises(ps.ScuffError, match="GetReducedFields_Nearby"):
-        G.GetFields(None, KN, 1.0, [[0.0, 0.0, 1.02]])
+@pytest.mark.parametrize("name,omega", [("PECSphere_501.scuffgeo", 1.0), ("SiO2Sphere_501.scuffgeo", 1.0), ("PECSphere_255.scuffgeo", 0.3)])
+def test_near_fields(ps, name, omega):
+    """evaluation points closer than one basis-function radius to the surface (down to 1 % of the sphere radius, outside and — for the
+    dielectric — inside): the reference's GetReducedFields_Nearby branch (closed-form static panel integrals + desingularised cubature),
+    restated in csrc/nearfield.cuh.  Tolerance 1e-9 relative to the largest field component: the closed forms cancel for points close to
+    a panel's plane; both sides evaluate the same expressions, libm vs CUDA log/atan/pow differ in the last bit"""
+    X = np.vstack([points_outside(30, 11, 1.01, 1.3), [[0.0, 0.0, 1.02], [0.0, 0.6, 0.85]]])
+    if "PEC" not in name:
+        X = np.vstack([X, points_outside(20, 12, 0.7, 0.97)])
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, points=X, rf=True)
+    G = ps.RWGGeometry(geo(name))
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    IF = ps.PlaneWave(*PW_X)
+    G.AssembleRHSVector(omega, IF)
+    F = G.GetFields(IF, KN, omega, X)
+    err = np.max(np.abs(F - info["fields"]), axis=1) / np.max(np.abs(info["fields"]))
+    print(name, "near-field parity, worst point:", err.max(), "at", X[np.argmax(err)])
+    assert err.max() <= 1e-9
+    RF = G.GetRFMatrix(omega, X).array
+    assert rel(RF, info["rf"]) <= 1e-9
+
+
+def test_dsipft_default_radius_on_a_coarse_mesh(ps):
+    """PECSphere_255: the automatic DSI radius (1.5 x extent) puts cubature points within one basis-function radius of the surface"""
+    name, omega = "PECSphere_255.scuffgeo", 1.0
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, dsi=(0.0, 302))
+    G = ps.RWGGeometry(geo(name))
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    IF = ps.PlaneWave(*PW_X)
+    G.AssembleRHSVector(omega, IF)
+    P = G.GetDSIPFTMatrix(KN, omega, IF)
+    ref = info["dsipft"]
+    # (the torque on a sphere vanishes by symmetry: its 1e-10 noise is compared on the scale of force x radius)
+    for cols in ((0, 1), (2, 3, 4, 5, 6, 7)):
+        assert np.max(np.abs(P[:, cols] - ref[:, cols])) <= 1e-9 * np.max(np.abs(ref[:, cols])), (P, ref)
 
 
 @pytest.mark.parametrize("name,omega,trans,dsi", [("SiO2Sphere_501.scuffgeo", 1.0, None, (0.0, 302)), ("PECSphere_501.scuffgeo", 1.0, None, (2.5, 110)),
