@@ -47,6 +47,19 @@ def test_fields_outside_and_inside(ps, name, omega):
     assert np.max(np.abs(Fs)) > 0
 
 
+def test_nested_bodies_fields_in_every_region(ps):
+    """a sphere inside a sphere: evaluation points in the exterior, in the shell (bounded by both surfaces, with opposite signs) and in the core"""
+    name, omega = "NestedSpheres.scuffgeo", 0.9
+    X = np.vstack([points_outside(8, 21, 1.2, 4.0), points_outside(10, 22, 0.4, 0.85), points_outside(5, 23, 0.0, 0.15), points_outside(4, 24, 0.26, 0.3)])
+    RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, nopft=True, points=X)
+    G = ps.RWGGeometry(geo(name))
+    KN = G.AllocateRHSVector(); KN.set(KNr)
+    IF = ps.PlaneWave(*PW_X)
+    G.AssembleRHSVector(omega, IF)
+    F = G.GetFields(IF, KN, omega, X)
+    assert rel(F, info["fields"]) <= 1e-9
+
+
 def test_two_bodies_and_rf_matrix(ps):
     name, omega = "E10Spheres_327.scuffgeo", 1.0
     X = np.vstack([points_outside(12, 3, 1.5, 3.0, (0, 0, 1.5)) + [[3.0, 0, 0]], points_outside(4, 4, 0.0, 0.5, (0, 0, 3.0)), points_outside(4, 5, 0.0, 0.5)])

@@ -43,7 +43,9 @@ CASES = [("PECSphere_501.scuffgeo", 1.0, PW_X, None),
          ("SiO2Sphere_501.scuffgeo", 0.1, PW_OBL, None),
          ("PECSpheres_327.scuffgeo", 0.7, PW_OBL, None),
          ("E10Spheres_327.scuffgeo", 1.0, PW_X, ("Spheres.trans", 2)),
-         ("GoldSphere_501.scuffgeo", 2.0, PW_X, None)]
+         ("GoldSphere_501.scuffgeo", 2.0, PW_X, None),
+         ("NestedSpheres.scuffgeo", 0.9, PW_OBL, None),        # a body inside a body: the "A contained in B" branches (EMTPFT.cc:655-660)
+         ("OpenPlate_40.scuffgeo", 1.0, PW_OBL, None)]         # open PEC surface: exterior edges carry no basis function
 
 
 @pytest.mark.parametrize("name,omega,pw,trans", CASES)
@@ -73,8 +75,8 @@ def test_rhs_solve_pft_planewave(ps, name, omega, pw, trans):
     assert pft_err(P2, PFTr) <= 1e-6, (P2, PFTr)
 
 
-def test_interior_pft(ps):
-    name, omega = "SiO2Sphere_501.scuffgeo", 1.0
+@pytest.mark.parametrize("name,omega", [("SiO2Sphere_501.scuffgeo", 1.0), ("NestedSpheres.scuffgeo", 0.9)])
+def test_interior_pft(ps, name, omega):
     RHSr, KNr, PFTr, info = ref_scatter(geo(name), omega, PW_X, interior=True)
     G = ps.RWGGeometry(geo(name))
     KN = G.AllocateRHSVector(); KN.set(KNr)
