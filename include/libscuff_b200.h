@@ -330,6 +330,9 @@ class RWGGeometry
    HMatrix *GetFields(IncField *IF, HVector *KN, cdouble Omega, HMatrix *XMatrix, HMatrix *FMatrix = NULL);
    void GetFields(IncField *IF, HVector *KN, cdouble Omega, double *X, cdouble *EH);
    HMatrix *GetRFMatrix(cdouble Omega, double *kBloch, HMatrix *XMatrix, HMatrix *RFMatrix = 0, bool MinuskBloch = false, int ColumnOffset = 0);
+   /* scattering parts of the electric and magnetic dyadic Green's functions at the rows of XMatrix (NX x 3: one-point; NX x 6: destination,
+    * source) (libscuff.h:390-405, GetDyadicGFs.cc:58-190): GMatrix NX x 18 complex (GE row-major, then GM); M = the LU-factorised BEM matrix   */
+   HMatrix *GetDyadicGFs(cdouble Omega, double *kBloch, HMatrix *XMatrix, HMatrix *M, HMatrix *GMatrix = 0, bool ScatteringOnly = true);
 
    void UpdateCachedEpsMuValues(cdouble Omega);
    int GetRegionByLabel(const char *Label);

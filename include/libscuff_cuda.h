@@ -232,6 +232,12 @@ int scuffcuda_emtpft(scuffcuda_context *ctx, int kn_handle, const scuffcuda_pft_
 int scuffcuda_get_fields(scuffcuda_context *ctx, int ns, const double k[2], const double zrel[2], double sign, int npts, const double *X,
                          int kn_handle, int bf_offset, double *F, int rf_handle, const int *rf_columns, long *near_pairs);
 
+/* RWGGeometry::GetDyadicGFs (libs/libscuff/GetDyadicGFs.cc:58-190), the contraction step: with D = the reduced-field matrix of the
+ * destination points and S = the LU-solved reduced-field matrix of the source points (both TotalBFs x 6 NX device matrices from
+ * scuffcuda_get_fields / scuffcuda_lu_solve_device), out[36*nx + 2*(3i+j)] = sum_bf D[bf,6nx+i] S[bf,6nx+j] (electric, re/im) and
+ * out[36*nx + 18 + 2*(3i+j)] the same with the magnetic columns 3..5; host buffer.  The normalisation factors are the caller's.   */
+int scuffcuda_dgf_contract(scuffcuda_context *ctx, int rf_dest_handle, int rf_source_handle, int npts, double *out);
+
 /* PPI algorithm counters of the last assemble_block call, same order as the reference's
  * log line (SurfaceSurfaceInteractions.cc:550-558; libscuffInternals.h PPIALG_*):
  * [0] low-order cubature, [1] high-order cubature, [2] Taylor-Duffy, [3] high-k TD,

@@ -22,6 +22,9 @@
  *        --dsi: then the PFT matrix by the displaced-surface-integral method (GetDSIPFT, DSIPFT.cc:449-590; radius 0 = automatic), NS x 8.
  *        --fields: then GetFields (GetFields.cc:336-395) at the points of pts.bin (raw doubles x,y,z): NX x 6 complex, row-major,
  *        appended; --rf: then GetRFMatrix (:141-330), TotalBFs x 6NX complex column-major, appended.
+ *   ref_driver dgf <geo> <wRe> <wIm> <pts.bin> <ncols> <out.bin> [--total]
+ *        RWGGeometry::GetDyadicGFs (GetDyadicGFs.cc:58-190) at the rows of pts.bin (ncols = 3: one-point, 6: destination + source):
+ *        AssembleBEMMatrix, LUFactorize, then NX x 18 complex (GE, GM row-major); --total adds the direct (homogeneous) contribution.
  *   ref_driver ssi    <geo> <wRe> <wIm> <nsa> <nsb> <Lx> <Ly> <Lz> <out.bin> [--cache-out f]
  *        GetSurfaceSurfaceInteractions (SurfaceSurfaceInteractions.cc:426-585) for one surface pair with surface b displaced
  *        by L (the neighbour-cell blocks of the periodic assembly, AssembleBEMMatrix.cc:72-114), not Symmetric
@@ -261,6 +264,24 @@ int main(int argc, char **argv)
         HMatrix *FM=G->GetFields(IFList,KN,Omega,XM);
         for(long nx=0;nx<NX;nx++) for(int q=0;q<6;q++) { cdouble v=FM->GetEntry(nx,q); fwrite(&v,sizeof(cdouble),1,f); }
         if(WantRF) { HMatrix *RF=G->GetRFMatrix(Omega,0,XM,0); fwrite(RF->ZM,sizeof(cdouble),(size_t)RF->NR*RF->NC,f); } }
+     fclose(f); return 0;
+   }
+
+  if(!strcmp(Cmd,"dgf"))
+   { cdouble Omega(atof(argv[3]),atof(argv[4])); const char *Pts=argv[5]; int ncols=atoi(argv[6]); const char *Out=argv[7];
+     bool Total=false; for(int n=8;n<argc;n++) if(!strcmp(argv[n],"--total")) Total=true;
+     FILE *fp=fopen(Pts,"rb"); if(!fp) return 1;
+     fseek(fp,0,SEEK_END); long NX=ftell(fp)/(ncols*sizeof(double)); fseek(fp,0,SEEK_SET);
+     HMatrix *XM=new HMatrix(NX,ncols);
+     for(long nx=0;nx<NX;nx++) for(int c=0;c<ncols;c++) { double v; if(fread(&v,sizeof(double),1,fp)!=1) return 1; XM->SetEntry(nx,c,v); }
+     fclose(fp);
+     HMatrix *M=G->AssembleBEMMatrix(Omega,(HMatrix *)0);
+     M->LUFactorize();
+     double t0=Now();
+     HMatrix *GM=G->GetDyadicGFs(Omega,0,XM,M,0,!Total);
+     printf("{\"NX\": %li, \"threads\": %i, \"dgf_s\": %.6f}\n",NX,omp_get_max_threads(),Now()-t0);
+     FILE *f=fopen(Out,"wb"); if(!f) return 1;
+     for(long nx=0;nx<NX;nx++) for(int q=0;q<18;q++) { cdouble v=GM->GetEntry(nx,q); fwrite(&v,sizeof(cdouble),1,f); }
      fclose(f); return 0;
    }
 

@@ -608,6 +608,30 @@ __global__ void __launch_bounds__(PFT_THREADS) fields_kernel(const __grid_consta
      A.F[12 * (size_t)nx + threadIdx.x] += sum; }
 }
 
+// dyadic Green's functions (GetDyadicGFs.cc:150-172): for every evaluation point nx the 3x3 contractions over the basis functions
+//   GE[i][j] = sum_bf D[bf, 6 nx + i] S[bf, 6 nx + j] ,  GM[i][j] = sum_bf D[bf, 6 nx + 3 + i] S[bf, 6 nx + 3 + j]
+// of the destination reduced-field matrix D with the LU-solved source reduced-field matrix S.  One CTA per point.
+__global__ void __launch_bounds__(PFT_THREADS) dgf_contract_kernel(const double *D, const double *S, int NBF, double *out)
+{ __shared__ double red[PFT_THREADS / 32][36];
+  const int nx = blockIdx.x;
+  const double *Dc = D + 2 * (size_t)6 * nx * NBF, *Sc = S + 2 * (size_t)6 * nx * NBF;
+  double acc[36]; for (int q = 0; q < 36; q++) acc[q] = 0.0;
+  for (int bf = threadIdx.x; bf < NBF; bf += PFT_THREADS)
+   { cd d[6], sv[6];
+     for (int c = 0; c < 6; c++) { d[c] = mk(Dc[2 * ((size_t)c * NBF + bf)], Dc[2 * ((size_t)c * NBF + bf) + 1]); sv[c] = mk(Sc[2 * ((size_t)c * NBF + bf)], Sc[2 * ((size_t)c * NBF + bf) + 1]); }
+     for (int half = 0; half < 2; half++)
+      for (int i = 0; i < 3; i++)
+       for (int j = 0; j < 3; j++)
+        { const cd p = d[3 * half + i] * sv[3 * half + j]; acc[2 * (9 * half + 3 * i + j)] += p.x; acc[2 * (9 * half + 3 * i + j) + 1] += p.y; } }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = 0; q < 36; q++) for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+  if (lane == 0) for (int q = 0; q < 36; q++) red[warp][q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < 36)
+   { double sum = 0.0; for (int wq = 0; wq < PFT_THREADS / 32; wq++) sum += red[wq][threadIdx.x];
+     out[36 * (size_t)nx + threadIdx.x] = sum; }
+}
+
 // ---- host side: near basis-function pairs of a surface pair (AssessBFPair, AssessPanelPair.cc:200-241) -----------
 static int build_near_list(scuffcuda_context *ctx, int nsa, int nsb, PftNearList &L)
 { Surface &SA = ctx->surfaces[nsa], &SB = ctx->surfaces[nsb];
@@ -907,6 +931,22 @@ int scuffcuda_get_fields(scuffcuda_context *ctx, int ns, const double k[2], cons
      for (size_t i = 0; i < h.size(); i++) F[i] += h[i]; }
   else PCK(cudaStreamSynchronize(ctx->stream));
   if (near_pairs) *near_pairs = (long)cnt;
+  return 0;
+}
+
+int scuffcuda_dgf_contract(scuffcuda_context *ctx, int rf_dest_handle, int rf_source_handle, int npts, double *out)
+{ Matrix *D = find_matrix(ctx, rf_dest_handle), *S = find_matrix(ctx, rf_source_handle);
+  if (!D || !S || D->isReal || S->isReal) return pfail(ctx, "dgf_contract: invalid reduced-field matrix handle");
+  if (D->NR != S->NR || D->NC != S->NC || npts <= 0 || D->NC != 6 * npts) return pfail(ctx, "dgf_contract: the matrices must be TotalBFs x 6 NX");
+  PCK(cudaSetDevice(ctx->device));
+  PftState *P = pft_state(ctx);
+  if (grow(ctx, P->dpart, P->partCap, (size_t)36 * npts)) return 1;
+  dgf_contract_kernel<<<npts, PFT_THREADS, 0, ctx->stream>>>(D->d, S->d, D->NR, P->dpart);
+  ctx->launches++;
+  PCK(cudaGetLastError());
+  PCK(cudaMemcpyAsync(out, P->dpart, (size_t)36 * npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PCK(cudaStreamSynchronize(ctx->stream));
+  ctx->d2hBytes += (size_t)36 * npts * sizeof(double);
   return 0;
 }
 

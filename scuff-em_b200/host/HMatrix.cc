@@ -132,6 +132,9 @@ int HMatrix::LUSolve(HMatrix *X)
   if (!DeviceHandle) ErrExit("LUSolve: matrix has not been LU-factorized");
   if (DeviceStale) ErrExit("LUSolve: the matrix was modified on the host after LUFactorize()");
   if (X->NR != NR || X->RealComplex != RealComplex) ErrExit("LUSolve: dimension/type mismatch");
+  if (X->DeviceHandle && X->HostStale && !X->DeviceStale)      // right-hand sides that already live in HBM (e.g. a reduced-field matrix)
+   { if (scuffcuda_lu_solve_device(ctx, DeviceHandle, X->DeviceHandle)) ErrExit("%s", scuffcuda_last_error(ctx));
+     return 0; }
   X->SyncToHost();
   void *p = RealComplex == LHM_REAL ? (void *)X->DM : (void *)X->ZM;
   if (scuffcuda_lu_solve(ctx, DeviceHandle, p, X->NC)) ErrExit("%s", scuffcuda_last_error(ctx));

@@ -491,4 +491,57 @@ void RWGGeometry::GetFields(IncField *IF, HVector *KN, cdouble Omega, double *X,
 { HMatrix XMatrix(1, 3, LHM_REAL, LHM_NORMAL, (void *)X), FMatrix(1, 6, LHM_COMPLEX, LHM_NORMAL, (void *)EH);
   GetFields(IF, KN, Omega, 0, &XMatrix, &FMatrix); }
 
+// scattering parts of the dyadic Green's functions (GetDyadicGFs.cc:58-190): reduced-field matrices of the destination and source points
+// in HBM, 6 NX right-hand sides solved there, 3x3 contractions over the basis functions on the device
+HMatrix *RWGGeometry::GetDyadicGFs(cdouble Omega, double *kBloch, HMatrix *XMatrix, HMatrix *M, HMatrix *GMatrix, bool ScatteringOnly)
+{ if (LBasis || kBloch) ErrExit("GetDyadicGFs: periodic geometries are not supported on the device path");
+  const int NX = XMatrix->NR;
+  if (GMatrix == 0 || GMatrix->NR != NX || GMatrix->NC != 18)
+   { if (GMatrix) { Warn("wrong-size GMatrix passed to GetDyadicGFs (reallocating)"); delete GMatrix; }
+     GMatrix = new HMatrix(NX, 18, LHM_COMPLEX); }
+  const bool TwoPointDGF = (XMatrix->NC >= 6), AddDirectContribution = TwoPointDGF && !ScatteringOnly;
+  HMatrix *RFDest = GetRFMatrix(Omega, 0, XMatrix, 0, true), *RFSource = 0;
+  if (TwoPointDGF) RFSource = GetRFMatrix(Omega, 0, XMatrix, 0, false, 3);
+  else
+   { RFSource = new HMatrix(TotalBFs, 6 * NX, LHM_COMPLEX);
+     RFSource->EnsureDevice();
+     scuffcuda_context *c0 = GetCudaContext();
+     if (scuffcuda_matrix_copy(c0, RFSource->DeviceHandle, RFDest->DeviceHandle)) ErrExit("%s", scuffcuda_last_error(c0));
+     RFSource->HostStale = true; RFSource->DeviceStale = false; }
+  M->LUSolve(RFSource);
+  scuffcuda_context *ctx = GetCudaContext();
+  std::vector<double> C(36 * (size_t)NX);
+  if (scuffcuda_dgf_contract(ctx, RFDest->DeviceHandle, RFSource->DeviceHandle, NX, C.data())) ErrExit("%s", scuffcuda_last_error(ctx));
+  delete RFDest; delete RFSource;
+  GMatrix->Zero();
+  cdouble P0[3] = { 0.0, 0.0, 0.0 }; double X00[3] = { 0.0, 0.0, 0.0 };
+  PointSource PS(X00, P0);
+  for (int nx = 0; nx < NX; nx++)
+   { double XDest[3] = { XMatrix->GetEntryD(nx, 0), XMatrix->GetEntryD(nx, 1), XMatrix->GetEntryD(nx, 2) };
+     const int nr = GetRegionIndex(XDest);
+     if (nr == -1) continue;
+     cdouble Eps, Mu; RegionMPs[nr]->GetEpsMu(Omega, &Eps, &Mu);
+     const cdouble k = Omega * sqrt(Eps * Mu), ZRel = sqrt(Mu / Eps);
+     const cdouble GEScatNormFac = -1.0 / (II * k * ZVAC * ZVAC * ZRel), GMScatNormFac = ZRel / (II * k);
+     cdouble GEDirect[3][3], GMDirect[3][3];
+     if (AddDirectContribution)
+      { const cdouble GEDirectNormFac = k * k / Eps, GMDirectNormFac = k * k / Mu;
+        for (int m = 0; m < 3; m++) PS.X0[m] = XMatrix->GetEntryD(nx, 3 + m);
+        UpdateIncFields(&PS, Omega, 0);
+        for (int i = 0; i < 3; i++)
+         { cdouble EH[6];
+           for (int m = 0; m < 3; m++) PS.P[m] = (m == i) ? 1.0 : 0.0;
+           PS.Type = LIF_ELECTRIC_DIPOLE; PS.GetFields(XDest, EH);
+           for (int j = 0; j < 3; j++) GEDirect[j][i] = EH[j] / GEDirectNormFac;
+           PS.Type = LIF_MAGNETIC_DIPOLE; PS.GetFields(XDest, EH);
+           for (int j = 0; j < 3; j++) GMDirect[j][i] = EH[3 + j] / GMDirectNormFac; } }
+     for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+       { cdouble GE = GEScatNormFac * cdouble(C[36 * (size_t)nx + 2 * (3 * i + j)], C[36 * (size_t)nx + 2 * (3 * i + j) + 1]);
+         cdouble GM = GMScatNormFac * cdouble(C[36 * (size_t)nx + 18 + 2 * (3 * i + j)], C[36 * (size_t)nx + 18 + 2 * (3 * i + j) + 1]);
+         if (AddDirectContribution) { GE += GEDirect[i][j]; GM += GMDirect[i][j]; }
+         GMatrix->SetEntry(nx, 3 * i + j, GE); GMatrix->SetEntry(nx, 9 + 3 * i + j, GM); } }
+  return GMatrix;
+}
+
 }  // namespace scuff

@@ -185,6 +185,13 @@ int scuffb200_incfield_eval(void *incfield, double wr, double wi, const double *
            if (deh) { cdouble dEH[3][6]; IF->GetFieldGradients(X + 3 * n, dEH);
                       for (int m = 0; m < 3; m++) for (int q = 0; q < 6; q++) { deh[36 * n + 12 * m + 2 * q] = real(dEH[m][q]); deh[36 * n + 12 * m + 2 * q + 1] = imag(dEH[m][q]); } } }
         return 0;, 1) }
+/* X: NX x ncols (3 or 6) row-major; out: NX x 18 complex row-major; m = the LU-factorised BEM matrix */
+int scuffb200_get_dyadic_gfs(void *g, void *m, double wr, double wi, int nx, int ncols, const double *X, int scattering_only, double *out)
+{ GUARD(RWGGeometry *G = (RWGGeometry *)g;
+        HMatrix XM(nx, ncols, LHM_REAL); for (int i = 0; i < nx; i++) for (int c = 0; c < ncols; c++) XM.SetEntry(i, c, X[ncols * i + c]);
+        HMatrix *GM = G->GetDyadicGFs(cdouble(wr, wi), 0, &XM, (HMatrix *)m, 0, scattering_only != 0);
+        for (int i = 0; i < nx; i++) for (int q = 0; q < 18; q++) { cdouble v = GM->GetEntry(i, q); out[36 * i + 2 * q] = real(v); out[36 * i + 2 * q + 1] = imag(v); }
+        delete GM; return 0;, 1) }
 int scuffb200_surface_origin(void *g, int ns, double *out) { for (int m = 0; m < 3; m++) out[m] = ((RWGGeometry *)g)->Surfaces[ns]->Origin[m]; return 0; }
 
 }  // extern "C"

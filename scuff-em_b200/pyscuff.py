@@ -165,6 +165,7 @@ def host_lib():
         L.scuffb200_get_fields.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.scuffb200_get_dsipft_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_double, C.c_int, C.c_char_p, C.c_void_p]
         L.scuffb200_incfield_eval.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.scuffb200_get_dyadic_gfs.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.scuffb200_get_rf_matrix.restype = C.c_void_p
         L.scuffb200_get_rf_matrix.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_void_p]
         _host = L
@@ -397,6 +398,15 @@ class RWGGeometry:
         _check(host_lib().scuffb200_get_fields(self.ptr, IF.ptr if IF is not None else None, KN.ptr if KN is not None else None,
                                                 float(np.real(Omega)), float(np.imag(Omega)), X.shape[0], X.ctypes.data, out.ctypes.data))
         return out
+
+    def GetDyadicGFs(self, Omega, X, M, ScatteringOnly=True):
+        """scattering parts of the electric / magnetic dyadic Green's functions at the rows of X (NX x 3, or NX x 6 = destination, source);
+        M = the LU-factorised BEM matrix.  Returns (GE, GM), each (NX, 3, 3) complex"""
+        X = np.ascontiguousarray(np.asarray(X, dtype=np.float64)); X = X.reshape(-1, X.shape[-1])
+        out = np.zeros((X.shape[0], 18), dtype=np.complex128)
+        _check(host_lib().scuffb200_get_dyadic_gfs(self.ptr, M.ptr, float(np.real(Omega)), float(np.imag(Omega)), X.shape[0], X.shape[1], X.ctypes.data,
+                                                    int(ScatteringOnly), out.ctypes.data))
+        return out[:, :9].reshape(-1, 3, 3), out[:, 9:].reshape(-1, 3, 3)
 
     def GetRFMatrix(self, Omega, X):
         X = np.ascontiguousarray(np.asarray(X, dtype=np.float64).reshape(-1, 3))

@@ -199,3 +199,21 @@ def ref_scatter(geo, omega, pw, ps_src=None, interior=False, method=0, trans=Non
             o += 12 * NX
             info["rf"] = raw[o:o + 2 * N * 6 * NX].view(np.complex128).reshape(6 * NX, N).T.copy()
     return RHS, KN, PFT, info
+
+
+def ref_dgf(geo, omega, X, total=False, tmpdir="/tmp/scuff_ref_cache", env=None):
+    """Reference RWGGeometry::GetDyadicGFs (ref_driver dgf) at the rows of X (NX x 3 or NX x 6): returns (GE, GM), each (NX, 3, 3)."""
+    if not have_ref():
+        pytest.skip("oracle/_ref not built (run make -C oracle where /root/reference exists)")
+    os.makedirs(tmpdir, exist_ok=True)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    key = hashlib.md5(repr(("dgf", geo, complex(omega), hashlib.md5(X.tobytes()).hexdigest(), X.shape, total)).encode()).hexdigest()[:16]
+    out = os.path.join(tmpdir, f"{os.path.basename(geo)}.{key}.bin")
+    if not os.path.exists(out):
+        X.tofile(out + ".pts")
+        cmd = [REF_DRIVER, "dgf", os.path.basename(geo), repr(float(np.real(omega))), repr(float(np.imag(omega))), out + ".pts", str(X.shape[1]), out]
+        if total:
+            cmd.append("--total")
+        subprocess.run(cmd, cwd=os.path.dirname(os.path.abspath(geo)), capture_output=True, text=True, check=True, env=dict(os.environ, **(env or {})))
+    A = np.fromfile(out, dtype=np.complex128).reshape(-1, 18)
+    return A[:, :9].reshape(-1, 3, 3), A[:, 9:].reshape(-1, 3, 3)

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GEODIR, ref_scatter
+from conftest import GEODIR, ref_scatter, ref_dgf
 
 pytestmark = pytest.mark.gpu
 
@@ -133,3 +133,21 @@ def test_dsipft(ps, name, omega, trans, dsi):
     for cols in ((0, 1), (2, 3, 4), (5, 6, 7)):
         scale = np.max(np.abs(ref[:, cols]))
         assert np.max(np.abs(P[:, cols] - ref[:, cols])) <= 1e-10 * scale, (P, ref)
+
+
+@pytest.mark.parametrize("name,omega", [("PECSphere_501.scuffgeo", 1.0), ("SiO2Sphere_501.scuffgeo", 0.7)])
+def test_dyadic_green_functions(ps, name, omega):
+    """RWGGeometry::GetDyadicGFs (scuff-ldos): one-point (source = destination) and two-point scattering dyadics, and the two-point
+    total dyadic (direct contribution of a point source added); reduced-field matrices, the 6 NX solves and the contractions on the device"""
+    G = ps.RWGGeometry(geo(name))
+    M = G.AssembleBEMMatrix(omega, to_host=False)
+    M.lu_factorize()
+    X1 = points_outside(6, 31, 1.05, 3.0)                    # incl. near-field points
+    GEr, GMr = ref_dgf(geo(name), omega, X1)
+    GE, GM = G.GetDyadicGFs(omega, X1, M)
+    assert rel(GE, GEr) <= 1e-8 and rel(GM, GMr) <= 1e-8
+    X2 = np.hstack([points_outside(5, 32, 1.5, 3.0), points_outside(5, 33, 1.5, 3.0)])
+    for total in (False, True):
+        GEr, GMr = ref_dgf(geo(name), omega, X2, total=total)
+        GE, GM = G.GetDyadicGFs(omega, X2, M, ScatteringOnly=not total)
+        assert rel(GE, GEr) <= 1e-8 and rel(GM, GMr) <= 1e-8
