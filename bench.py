@@ -241,6 +241,42 @@ def other_configs(ps, np, a, peak, with_ref):
             G.DestroyABMBAccelerator(h)
         del M, G
 
+    # the callers either side of the path on the Mie geometry, each phase timed on the device and — where the
+    # reference binary is present — by the reference on the host cores (ref_driver scatter / dgf print their own phase times)
+    try:
+        geo = os.path.join(GEODIR, "SiO2Sphere_501.scuffgeo")
+        G = ps.RWGGeometry(geo); N = G.TotalBFs; om = 1.0
+        IF = ps.PlaneWave((1.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+        M = G.AssembleBEMMatrix(om, to_host=False); KN = G.AssembleRHSVector(om, IF); M.lu_factorize(); M.lu_solve_vector(KN)
+        rng = np.random.default_rng(3)
+        d = rng.standard_normal((1000, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+        XF = d * rng.uniform(1.02, 4.0, 1000)[:, None]                 # 1000 evaluation points, a fifth of them in the near-field branch
+        XD = XF[:20]
+        calls = {"rhs_ms": lambda j: G.AssembleRHSVector(om, IF, KN2), "emtpft_ms": lambda j: G.GetPFTMatrix(KN, om, IF, EMTPFTIMethod=0),
+                 "dsipft_ms": lambda j: G.GetDSIPFTMatrix(KN, om, IF), "fields_1000_points_ms": lambda j: G.GetFields(IF, KN, om, XF),
+                 "dyadic_gfs_20_points_ms": lambda j: G.GetDyadicGFs(om, XD, M)}
+        KN2 = G.AllocateRHSVector()
+        r = {"workload": "SiO2Sphere_501 (1002 basis functions), omega=1, plane wave: the calls of scuff-scatter / scuff-ldos after the assembly"}
+        for k, fn in calls.items():
+            fn(0); r[k] = 1e3 * timed(fn, 3)
+        if with_ref:
+            XF[:200].tofile("/tmp/scuff_bench_pts.bin"); XD.tofile("/tmp/scuff_bench_dgf.bin")
+            env = ref_env()
+            cmd = [REF_DRIVER, "scatter", os.path.basename(geo), "1.0", "0", "/tmp/scuff_bench_scatter.bin", "--pw", "1", "0", "0", "0", "0", "0", "0", "0", "1",
+                   "--dsi", "0", "302"]
+            t0 = time.perf_counter(); o = subprocess.run(cmd, cwd=GEODIR, capture_output=True, text=True, check=True, env=env).stdout; t_all = time.perf_counter() - t0
+            ref = json.loads(o.strip().splitlines()[-1])
+            t0 = time.perf_counter()
+            o2 = subprocess.run([REF_DRIVER, "dgf", os.path.basename(geo), "1.0", "0", "/tmp/scuff_bench_dgf.bin", "3", "/tmp/scuff_bench_dgf.out"], cwd=GEODIR,
+                                capture_output=True, text=True, check=True, env=env).stdout
+            r["cpu_baseline"] = {"kind": "reference", "cores": ref["threads"], "rhs_ms": 1e3 * ref["rhs_s"], "emtpft_ms": 1e3 * ref["pft_s"],
+                                 "dyadic_gfs_20_points_ms": 1e3 * json.loads(o2.strip().splitlines()[-1])["dgf_s"],
+                                 "note": "EMTPFT with the same cubature integrals (method 0); the DSIPFT and field timings of the reference are inside its run (%.1f s in all)" % t_all}
+        out["scattering_run_sio2sphere_501"] = r
+        del M, KN, KN2, G
+    except Exception as e:  # noqa
+        out["scattering_run_sio2sphere_501"] = {"error": str(e)[:300]}
+
     # the other far-kernel variants at benchmark scale: imaginary frequency (real matrix) and PMCHWT (Phi and Psi)
     for name, nu, material, omega, imag, kind in (("icosphere_imag_freq", a.nu, None, 1j * a.omega, True, "pec_imag"),
                                                    ("icosphere_pmchwt", max(4, int(a.nu * 0.7)), "CONST_EPS_10", a.omega, False, "dielectric")):
