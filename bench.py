@@ -251,10 +251,10 @@ def other_configs(ps, np, a, peak, with_ref):
         rng = np.random.default_rng(3)
         d = rng.standard_normal((1000, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
         XF = d * rng.uniform(1.02, 4.0, 1000)[:, None]                 # 1000 evaluation points, a fifth of them in the near-field branch
-        XD = XF[:20]
+        XD = XF[:200]
         calls = {"rhs_ms": lambda j: G.AssembleRHSVector(om, IF, KN2), "emtpft_ms": lambda j: G.GetPFTMatrix(KN, om, IF, EMTPFTIMethod=0),
                  "dsipft_ms": lambda j: G.GetDSIPFTMatrix(KN, om, IF), "fields_1000_points_ms": lambda j: G.GetFields(IF, KN, om, XF),
-                 "dyadic_gfs_20_points_ms": lambda j: G.GetDyadicGFs(om, XD, M)}
+                 "dyadic_gfs_200_points_ms": lambda j: G.GetDyadicGFs(om, XD, M)}
         KN2 = G.AllocateRHSVector()
         r = {"workload": "SiO2Sphere_501 (1002 basis functions), omega=1, plane wave: the calls of scuff-scatter / scuff-ldos after the assembly"}
         for k, fn in calls.items():
@@ -270,7 +270,7 @@ def other_configs(ps, np, a, peak, with_ref):
             o2 = subprocess.run([REF_DRIVER, "dgf", os.path.basename(geo), "1.0", "0", "/tmp/scuff_bench_dgf.bin", "3", "/tmp/scuff_bench_dgf.out"], cwd=GEODIR,
                                 capture_output=True, text=True, check=True, env=env).stdout
             r["cpu_baseline"] = {"kind": "reference", "cores": ref["threads"], "rhs_ms": 1e3 * ref["rhs_s"], "emtpft_ms": 1e3 * ref["pft_s"],
-                                 "dyadic_gfs_20_points_ms": 1e3 * json.loads(o2.strip().splitlines()[-1])["dgf_s"],
+                                 "dyadic_gfs_200_points_ms": 1e3 * json.loads(o2.strip().splitlines()[-1])["dgf_s"],
                                  "note": "EMTPFT with the same cubature integrals (method 0); the DSIPFT and field timings of the reference are inside its run (%.1f s in all)" % t_all}
         out["scattering_run_sio2sphere_501"] = r
         del M, KN, KN2, G
