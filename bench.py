@@ -342,6 +342,33 @@ def reference_arm(a, rank, world):
     return 0
 
 
+def _bind_to_gpu_numa_node(torch, local):
+    """Several ranks share the host: run this rank's host threads (and therefore first-touch its page-locked matrix buffer) on the
+    NUMA node its GPU hangs off, so that the copy-back of every rank stays on its own socket's memory controllers.  Uses what the
+    kernel exposes (/sys/bus/pci/devices/<bus id>/numa_node, /sys/devices/system/node/nodeN/cpulist); a no-op on single-node hosts."""
+    info = {"node": None, "cpus": None}
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["cpus"] = len(cpus)
+    except Exception as e:  # noqa
+        info["error"] = str(e)[:120]
+    return info
+
+
 def _emit(line):
     """the ONE JSON line on the real stdout (stray library output, e.g. NCCL's version banner, was routed to stderr)"""
     sys.stdout.flush()
@@ -388,6 +415,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU reference)")
     torch.cuda.set_device(local)
+    numa = _bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -556,6 +584,8 @@ def main():
             "clocks": clocks}
     if split:
         line["matrix_split"] = split
+    if numa is not None:
+        line["numa_binding_rank0"] = numa
     if fippi_share:
         line["fippi_table_shared_build"] = fippi_share
     hbm = None
