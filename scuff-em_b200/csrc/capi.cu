@@ -65,8 +65,11 @@ int scuffcuda_create(int device, scuffcuda_context **out)
   CK(cudaMalloc(&ctx->dcounters, 16 * sizeof(unsigned long long)));
   CK(cudaMemset(ctx->dcounters, 0, 16 * sizeof(unsigned long long)));
   { int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    CK(cudaStreamCreateWithPriority(&ctx->nearStream, cudaStreamNonBlocking, hi));
-    CK(cudaStreamCreateWithPriority(&ctx->tdStream, cudaStreamNonBlocking, hi));
+    // SCUFF_CUDA_NEAR_PRIORITY=low: the near/singular streams below the main stream instead of above it (experiment switch)
+    const char *np = getenv("SCUFF_CUDA_NEAR_PRIORITY");
+    const int nearPrio = (np && !strcmp(np, "low")) ? lo : hi;
+    CK(cudaStreamCreateWithPriority(&ctx->nearStream, cudaStreamNonBlocking, nearPrio));
+    CK(cudaStreamCreateWithPriority(&ctx->tdStream, cudaStreamNonBlocking, nearPrio));
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&ctx->evTd[i], cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
     for (int i = 0; i < 7; i++) CK(cudaEventCreate(&ctx->ev[i])); }
