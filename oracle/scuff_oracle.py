@@ -337,3 +337,135 @@ def far_edge_pairs_gc0_extended(S, nea, neb, k):
             sign = (1 if sa == 0 else -1) * (1 if sb == 0 else -1)
             out += np.where(ok, sign * H0, 0)
     return S["EL"][nea].astype(LD) * S["EL"][neb].astype(LD) * out, far
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Scattering-run callers: the reference's formulation per basis function / per pair of basis
+# functions, vectorised — independent of the surface-current formulation of the CUDA kernels (csrc/rhs_pft.cu).
+#   AssembleRHSVector / GetInnerProducts      libs/libscuff/AssembleRHSVector.cc:172-229,282-345
+#   PlaneWave::GetFields                      libs/libIncField/PlaneWave.cc:75-88
+#   GetScatteredPFTIntegrals (method 0) +     libs/libscuff/EMTPFT.cc:82-176,308-334,640-725 (power only)
+#   GetExtinctionPFTT                         libs/libscuff/EMTPFT.cc:389-531 (power only)
+#   GetBFBFCubature2 / GetPanelCubature       libs/libscuff/PanelCubature.cc:155-236,791-893
+# Pinned by tests/test_scatter_cpu.py against the committed reference vectors tests/golden/scatter_golden.npz.
+# ------------------------------------------------------------------------------------------------------------------
+ZVAC = 376.73031346177
+
+
+def load_rule(header, name, npts):
+    """(u, v, w) table of a triangle rule as extracted from the compiled reference (scuff-em_b200/csrc/generated_tcr*.h)"""
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "scuff-em_b200", "csrc", header)).read()
+    body = re.search(r"%s\[\d+\] = \{(.*?)\};" % re.escape(name), src, flags=re.S).group(1)
+    return np.array([float(x) for x in body.replace("\n", " ").split(",") if x.strip()]).reshape(npts, 3)
+
+
+def planewave_fields(X, omega, E0, nhat, eps=1.0, mu=1.0):
+    k = np.sqrt(eps * mu + 0j) * omega
+    Z = ZVAC * np.sqrt((mu + 0j) / eps)
+    E = np.asarray(E0, dtype=complex)[None, :] * np.exp(1j * k * (X @ np.asarray(nhat, dtype=float)))[:, None]
+    return E, np.cross(np.asarray(nhat, dtype=float)[None, :], E) / Z
+
+
+def rhs_planewave(S, omega, E0, nhat, eps=1.0, mu=1.0, sign=-1.0):
+    """RHS entries of one surface for a plane wave whose sources lie in the surface's exterior region (sign -1): 78-point rule over
+    the positive panel (QP, V1, V2) minus the negative panel (V1, V2, QM); E-entries divided by ZVAC, H-entries for dielectric surfaces"""
+    T = load_rule("generated_tcr20.h", "SC_TCR20_H", 78)
+    V, ET, EL = S["V"], S["ET"], S["EL"]
+    out = np.zeros(S["NBF"], dtype=complex)
+    for ne in range(S["NE"]):
+        iV1, iV2, iQP, iQM = ET[ne, :4]
+        acc = np.zeros(2, dtype=complex)
+        for pm, (A0, A1, A2, Q) in enumerate(((V[iQP], V[iV1], V[iV2], V[iQP]), (V[iV1], V[iV2], V[iQM] if iQM >= 0 else None, V[iQM] if iQM >= 0 else None))):
+            if Q is None:
+                continue
+            X = A0[None, :] + T[:, 0, None] * (A1 - A0)[None, :] + T[:, 1, None] * (A2 - A0)[None, :]
+            E, H = planewave_fields(X, omega, E0, nhat, eps, mu)
+            f = X - Q[None, :]
+            w = T[:, 2] * EL[ne] * (1.0 if pm == 0 else -1.0)       # PreFac x Jacobian x w = (l/2A)(2A) w
+            acc[0] += np.sum(w * np.sum(f * E, axis=1)); acc[1] += np.sum(w * np.sum(f * H, axis=1))
+        if S["IsPEC"]:
+            out[ne] = sign * acc[0] / ZVAC
+        else:
+            out[2 * ne] = sign * acc[0] / ZVAC; out[2 * ne + 1] = sign * acc[1]
+    return out
+
+
+def _bf_points(S, ne, rule):
+    """cubature points, basis-function values and weights of one RWG function as GetBFBFCubature2 forms them: both panels
+    parametrised from their source vertex, X = Q + u (V1 - Q) + v (V2 - Q)"""
+    V, ET, EL = S["V"], S["ET"], S["EL"]
+    iV1, iV2, iQP, iQM = ET[ne, :4]
+    X, b, div, W = [], [], [], []
+    for sgn, iQ in ((1.0, iQP), (-1.0, iQM)):
+        if iQ < 0:
+            continue
+        Q, A, B = V[iQ], V[iV1] - V[iQ], V[iV2] - V[iQ]
+        area2 = np.linalg.norm(np.cross(A, B))
+        pre = sgn * EL[ne] / area2
+        d = rule[:, 0, None] * A[None, :] + rule[:, 1, None] * B[None, :]
+        X.append(d + Q[None, :]); b.append(pre * d); div.append(np.full(len(rule), 2.0 * pre)); W.append(area2 * rule[:, 2])
+    return np.vstack(X), np.vstack(b), np.concatenate(div), np.concatenate(W)
+
+
+def emtpft_power_single_surface(S, KN, omega, E0, nhat, eps=1.0, mu=1.0):
+    """(PAbs, PScat) of a single closed surface in a medium (eps, mu) by the energy/momentum-transfer method with the cubature
+    integrals (EMTPFTIMethod 0), exterior expansion: PScat from all ordered pairs of basis functions (same surface: only the
+    imaginary parts of the kernels, order 9 if the two functions share a vertex, else 4), PAbs = extinction - PScat."""
+    T4, T9 = TCR4, load_rule("generated_tcr9.h", "SC_TCR9_H", 21)
+    NE = S["NE"]
+    k = float(np.real(np.sqrt(eps * mu + 0j) * omega))
+    pec = S["IsPEC"]
+    kc = KN if pec else KN[0::2]
+    nc = np.zeros(NE, dtype=complex) if pec else -ZVAC * KN[1::2]
+    pts = {4: [_bf_points(S, ne, T4) for ne in range(NE)], 9: [_bf_points(S, ne, T9) for ne in range(NE)]}
+    verts = [set(int(v) for v in S["ET"][ne, :4] if v >= 0) for ne in range(NE)]
+
+    def kernels(r):
+        kr = k * r
+        small = np.abs(kr) < 1e-3
+        rs = np.where(small, 1.0, r)
+        phi = np.where(small, (1.0 - kr * kr / 6.0) * k / (4 * np.pi), np.sin(kr) / (4 * np.pi * rs))
+        psi = np.where(small, -(1.0 - kr * kr / 10.0) * k ** 3 / (12 * np.pi), (kr * np.cos(kr) - np.sin(kr)) / (4 * np.pi * rs ** 3))
+        return phi, psi
+
+    pscat = 0.0
+    for a in range(NE):
+        for order in (4, 9):
+            bs = [b for b in range(NE) if (len(verts[a] & verts[b]) > 0) == (order == 9)]
+            if not bs:
+                continue
+            Xa, ba, da, Wa = pts[order][a]
+            Xb = np.vstack([pts[order][b][0] for b in bs]); bb = np.vstack([pts[order][b][1] for b in bs])
+            db = np.concatenate([pts[order][b][2] for b in bs]); Wb = np.concatenate([pts[order][b][3] for b in bs])
+            starts = np.concatenate([[0], np.cumsum([len(pts[order][b][3]) for b in bs])[:-1]])       # column ranges of the functions b
+            R = Xa[:, None, :] - Xb[None, :, :]
+            r = np.linalg.norm(R, axis=2)
+            phi, psi = kernels(r)
+            W = Wa[:, None] * Wb[None, :]
+            pefie = ba @ bb.T - np.outer(da, db) / (k * k)
+            pmfie = np.einsum("ijm,ijm->ij", np.cross(ba[:, None, :], bb[None, :, :]), R)                 # (bA x bB).R
+            qkk = np.add.reduceat((W * pefie * omega * mu * phi).sum(axis=0), starts)                      # Im QKK (= Im QNN mu/eps)
+            qkn = np.add.reduceat((W * pmfie * psi).sum(axis=0), starts)                                   # Im QKNmNK
+            kb, nb = kc[bs], nc[bs]
+            u0kk = np.conj(kc[a]) * kb * ZVAC
+            e0nn = np.conj(nc[a]) * nb / ZVAC
+            knmnk = np.conj(kc[a]) * nb - np.conj(nc[a]) * kb
+            pscat += 0.5 * np.sum(u0kk.real * qkk + e0nn.real * (qkk * eps / mu) + knmnk.imag * qkn)
+    # extinction: 21-point rule of every panel in the panel's own vertex order, per basis function
+    pext = 0.0
+    V, PVI = S["V"], S["PVI"]
+    for ne in range(NE):
+        iV1, iV2, iQP, iQM = S["ET"][ne, :4]
+        for sgn, npan, iQ in ((1.0, S["ET"][ne, 4], iQP), (-1.0, S["ET"][ne, 5], iQM)):
+            if iQ < 0 or npan < 0:
+                continue
+            V0, V1, V2 = V[PVI[npan, 0]], V[PVI[npan, 1]], V[PVI[npan, 2]]
+            area2 = np.linalg.norm(np.cross(V1 - V0, V2 - V0))
+            X = V0[None, :] + T9[:, 0, None] * (V1 - V0)[None, :] + T9[:, 1, None] * (V2 - V0)[None, :]
+            b = sgn * S["EL"][ne] / area2 * (X - V[iQ][None, :])
+            E, H = planewave_fields(X, omega, E0, nhat, eps, mu)
+            w = area2 * T9[:, 2]
+            pext += 0.5 * np.real(np.conj(kc[ne]) * np.sum(w * np.sum(b * E, axis=1)) + np.conj(nc[ne]) * np.sum(w * np.sum(b * H, axis=1)))
+    return pext - pscat, pscat

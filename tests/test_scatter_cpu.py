@@ -100,3 +100,22 @@ def test_no_cpu_fallback_for_the_scattering_run(ps):
     G = ps.RWGGeometry(os.path.join(GEODIR, "PECSphere_255.scuffgeo"))
     with pytest.raises(ps.ScuffError):
         G.AssembleRHSVector(1.0, ps.PlaneWave((1, 0, 0), (0, 0, 1)))
+
+
+def test_oracle_rhs_and_emtpft_power_pinned_to_the_reference(oracle):
+    """numpy restatement (oracle/scuff_oracle.py) of the reference's per-basis-function formulation of the plane-wave right-hand side
+    and of the energy/momentum-transfer powers, against the committed reference vectors: pins the oracle for SURVEY 8 row f2"""
+    Gd = np.load(os.path.join(GOLDEN, "scatter_golden.npz"))
+    for name, pec in (("PECSphere_501", True), ("SiO2Sphere_501", False)):
+        S = oracle.parse_geom_dump(os.path.join(GOLDEN, "geom", name + ".geom.txt"))[2][0]
+        key = name + "@1"
+        rhs = oracle.rhs_planewave(S, 1.0, (1.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+        assert np.max(np.abs(rhs - Gd[key + ":rhs"])) <= 1e-13 * np.max(np.abs(Gd[key + ":rhs"]))
+    # powers (501^2 pairs of basis functions x 4 panel pairs x 36 / 441 point pairs, vectorised: ~15 s each): PEC (electric currents
+    # only) and dielectric (electric and magnetic currents, all four bilinears)
+    for name in ("PECSphere_501", "SiO2Sphere_501"):
+        S = oracle.parse_geom_dump(os.path.join(GOLDEN, "geom", name + ".geom.txt"))[2][0]
+        pabs, pscat = oracle.emtpft_power_single_surface(S, Gd[name + "@1:kn"], 1.0, (1.0, 0.0, 0.0), (0.0, 0.0, 1.0))
+        ref = Gd[name + "@1:emtpft0"][0]
+        assert abs(pscat - ref[1]) <= 1e-10 * abs(ref[1]), (name, pscat, ref[1])
+        assert abs(pabs - ref[0]) <= 1e-10 * max(abs(ref[0]), abs(ref[1])), (name, pabs, ref[0])
