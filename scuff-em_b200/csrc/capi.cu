@@ -479,7 +479,14 @@ int scuffcuda_assemble_block(scuffcuda_context *ctx, int nsa, int nsb, const scu
      int c0 = a->col_offset, c1 = a->col_offset + NBFB;
      if (a->col_end > 0 && a->col_end != 0x7fffffff) { c0 = std::max(c0, a->col_begin); c1 = std::min(c1, a->col_end); }
      ctx->stream = sNear;
-     launch_zero_block(ctx, *M, a->row_offset, NBFA, c0, c1 - c0);
+     // col_end == 0x7fffffff on a symmetric diagonal block: the caller mirrors the WHOLE matrix afterwards (RWGGeometry::AssembleBEMMatrix),
+     // so only the upper triangle of the block is ever read — clear just that (half the HBM writes that run beside the first far pass);
+     // SCUFF_CUDA_CLEAR_FULL=1 clears the whole block as every other call does
+     static const bool clearFull = (getenv("SCUFF_CUDA_CLEAR_FULL") && getenv("SCUFF_CUDA_CLEAR_FULL")[0] == '1');
+     if (a->symmetric && a->col_end == 0x7fffffff && a->row_offset == a->col_offset && NBFA == NBFB && !clearFull)
+      launch_zero_upper(ctx, *M, a->row_offset, NBFA);
+     else
+      launch_zero_block(ctx, *M, a->row_offset, NBFA, c0, c1 - c0);
      ctx->stream = sMain; }
   CK(cudaEventRecord(ev[6], sNear));
 

@@ -55,6 +55,7 @@ int run_near(scuffcuda_context *ctx, int nsa, int nsb, const scuffcuda_ssi_args 
 
 // matrix utilities (matrix_kernels.cu)
 void launch_zero_block(scuffcuda_context *ctx, const Matrix &M, int rowOff, int nRows, int colOff, int nCols);
+void launch_zero_upper(scuffcuda_context *ctx, const Matrix &M, int off, int n);
 void launch_copy_block(scuffcuda_context *ctx, const Matrix &M, int dstRow, int dstCol, int nRows, int nCols, int srcRow, int srcCol);
 void launch_symmetrize(scuffcuda_context *ctx, const Matrix &M, int off, int n);
 double run_fp64_peak(scuffcuda_context *ctx);

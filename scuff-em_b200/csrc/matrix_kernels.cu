@@ -14,6 +14,18 @@ __global__ void zero_block_kernel(double *M, long ld, int w, int rowOff, int nRo
    }
 }
 
+// upper triangle (diagonal included) of the square block at (off, off): column c holds c + 1 entries to clear.  Used for symmetric
+// blocks whose lower triangle the caller overwrites with the mirror image afterwards: half the bytes of a full clear
+__global__ void zero_upper_kernel(double *M, long ld, int w, int off, int n)
+{ for (int c = blockIdx.x; c < n; c += gridDim.x)
+   { double *col = M + ((size_t)off + (size_t)(off + c) * ld) * w;
+     if (w == 2)
+      { double2 *c2 = (double2 *)col; const double2 z = make_double2(0.0, 0.0);
+        for (int i = threadIdx.x; i <= c; i += blockDim.x) c2[i] = z; }
+     else
+      for (int i = threadIdx.x; i <= c; i += blockDim.x) col[i] = 0.0; }
+}
+
 __global__ void copy_block_kernel(double *M, long ld, int w, int dstRow, int dstCol, int nRows, int nCols, int srcRow, int srcCol)
 { long n = (long)nRows * nCols;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
@@ -113,6 +125,11 @@ void launch_zero_block(scuffcuda_context *ctx, const Matrix &M, int rowOff, int 
    { cudaMemsetAsync(M.d, 0, (size_t)M.NR * M.NC * w * sizeof(double), ctx->stream); return; }
   ctx->launches++;
   zero_block_kernel<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(M.d, M.NR, w, rowOff, nRows, colOff, nCols);
+}
+void launch_zero_upper(scuffcuda_context *ctx, const Matrix &M, int off, int n)
+{ if (n <= 0) return;
+  ctx->launches++;
+  zero_upper_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(M.d, M.NR, M.isReal ? 1 : 2, off, n);
 }
 void launch_copy_block(scuffcuda_context *ctx, const Matrix &M, int dstRow, int dstCol, int nRows, int nCols, int srcRow, int srcCol)
 { if (nRows <= 0 || nCols <= 0) return;
