@@ -119,3 +119,22 @@ def test_oracle_rhs_and_emtpft_power_pinned_to_the_reference(oracle):
         ref = Gd[name + "@1:emtpft0"][0]
         assert abs(pscat - ref[1]) <= 1e-10 * abs(ref[1]), (name, pscat, ref[1])
         assert abs(pabs - ref[0]) <= 1e-10 * max(abs(ref[0]), abs(ref[1])), (name, pabs, ref[0])
+
+
+def test_torque_centre_follows_the_surface(ps):
+    """RWGSurface::Origin (the torque centre of GetPFT) starts at the object's DISPLACED/ROTATED origin and moves with every
+    transformation, as in the reference (RWGSurface.cc:423-429, :609, :657); host logic, no device"""
+    G = ps.RWGGeometry(os.path.join(GEODIR, "E10Spheres_327.scuffgeo"))
+    assert np.allclose(G.surface_origin(0), [0, 0, 3]) and np.allclose(G.surface_origin(1), [0, 0, 0])
+    G.transform("TRANS 3.4 SURFACE UpperSphere DISP 0 0 0.4")
+    assert np.allclose(G.surface_origin(0), [0, 0, 3.4]) and np.allclose(G.surface_origin(1), [0, 0, 0])
+    G.untransform()
+    assert np.allclose(G.surface_origin(0), [0, 0, 3])
+
+
+def test_nested_geometry_regions(ps):
+    """a body inside a body: the inner surface's exterior region is the outer body's interior (the branches of the PFT sums and of
+    GetFields that the nested fixture exercises on the GPU)"""
+    G = ps.RWGGeometry(os.path.join(GEODIR, "NestedSpheres.scuffgeo"))
+    assert [G.surface(i)["Regions"] for i in range(2)] == [(0, 1), (1, 2)]
+    assert [r[0] for r in G.regions()] == ["EXTERIOR", "Shell", "Core"]
